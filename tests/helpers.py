@@ -1,0 +1,38 @@
+"""Shared test helpers: demo workloads built both for the oracle and for the product."""
+import os
+
+import numpy as np
+import pandas as pd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# Demo_InfectionStates.ipynb:885-891, :8575-8578, :17472-17476  (lognorm s, scale)
+PRIORS = {
+    "zero_i": [("mu", 3, 1e-8), ("phi", 3, 1e-8), ("beta", 1, 25)],
+    "one_i": [("mu", 3, 1e-8), ("phi", 3, 1e-8), ("beta", 1, 20), ("lam", 2, 0.1)],
+    "two_i": [("mu", 3, 1e-8), ("phi", 3, 1e-8), ("beta", 1, 20), ("lam", 2, 0.1), ("tau", 2, 1)],
+}
+STATES = {"zero_i": ["S", "V"], "one_i": ["S", "I1", "V"], "two_i": ["S", "I1", "I2", "V"]}
+SUMS = {"zero_i": None, "one_i": {"H": ["S", "I1"]}, "two_i": {"H": ["S", "I1", "I2"]}}
+TSTEPS = {"zero_i": 288, "one_i": 1000, "two_i": 1000}
+
+
+def demo_df(name):
+    df = pd.read_csv(os.path.join(GOLDEN, "demodata.csv"))
+    return df.replace({"virus": "V", "host": "S" if name == "zero_i" else "H"})
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, f"{name}.npz"))
+
+
+def oracle_tables(name):
+    from oracle import odelib_oracle as orc
+    inits = None if name == "zero_i" else {"S": 5236900}
+    return orc.build_tables(demo_df(name), STATES[name], SUMS[name], TSTEPS[name], inits)
+
+
+def oracle_rhs(name):
+    from oracle import odelib_oracle as orc
+    return getattr(orc, name)
