@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline metric on B200 (BASELINE.json: ODE solves/s + MCMC chain-steps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one rank per GPU under torchrun)
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   the reference's CPU path (oracle port)
+
+One "step" = one pass of the forward sweep (BASELINE.json configs[1]): `--sets` (default 1,048,576) parameter
+sets per GPU drawn from the two_i priors of the demo, each integrated to the demo's observation grid and
+scored (chi, R^2) -- one launch of odl_sweep_kernel.  `value` = solves/s with theta resident in HBM, timed
+with CUDA events on the launching stream; `e2e` = the same through ModelFramework.sweep with pinned HOST
+buffers (H2D + D2H inside the timed call).  The MCMC leg (chain-steps/s) is reported in the same JSON line
+under "mcmc".  Prints exactly one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "two_i"
+TSTEPS = 1000
+CENTER = {"two_i": [7.475e-09, 1.069e-07, 19.73, 1.934, 2.799]}   # posterior medians of the demo notebook (:15120-15128)
+
+
+def demo_frame():
+    import pandas as pd
+    df = pd.read_csv(os.path.join(ROOT, "tests", "golden", "demodata.csv"))
+    return df.replace({"virus": "V", "host": "H"})
+
+
+def prior_draws(n, seed, offset=0):
+    """iid draws from the demo's lognorm priors, reproducible per global row index block."""
+    from odelib_b200 import demo_models
+    rng = np.random.default_rng([seed, offset])
+    pri = demo_models.PRIORS[MODEL]
+    names = demo_models.PARAMETER_NAMES[MODEL]
+    return np.column_stack([pri[p][1] * np.exp(pri[p][0] * rng.standard_normal(n)) for p in names])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU side: the reference's algorithm (oracle port: scipy odeint + numpy masked chi) on host cores
+# ----------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init():
+    from oracle import odelib_oracle as orc
+    from odelib_b200 import demo_models
+    _CPU["orc"] = orc
+    _CPU["tab"] = orc.build_tables(demo_frame(), demo_models.STATE_NAMES[MODEL], {"H": ["S", "I1", "I2"]}, TSTEPS,
+                                   {"S": 5236900})
+
+
+def _cpu_chunk(theta):
+    import warnings
+    warnings.filterwarnings("ignore")
+    orc, tab = _CPU["orc"], _CPU["tab"]
+    out = np.empty(len(theta))
+    for i, th in enumerate(theta):
+        out[i] = orc.solve_unit(orc.two_i, th, tab)[1]
+    return out
+
+
+def cpu_sweep_rate(theta, cores, pool=None):
+    """solves/s of the oracle port over `theta` with `cores` processes (fork; like the reference's Pool)."""
+    import multiprocessing as mp
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
+        pool.map(_cpu_chunk, [theta[:2]] * cores)            # spin the workers up outside the timing
+    chunks = np.array_split(theta, cores * 4)
+    t0 = time.perf_counter()
+    pool.map(_cpu_chunk, chunks)
+    dt = time.perf_counter() - t0
+    if own:
+        pool.close(); pool.join()
+    return len(theta) / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm for the path, all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n = cores * 2000
+    theta = prior_draws(n, 0)
+    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
+    pool.map(_cpu_chunk, [theta[:2]] * cores)
+    for _ in range(args.warmup):
+        cpu_sweep_rate(theta, cores, pool)
+    total = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_sweep_rate(theta, cores, pool)
+        total += dt
+    pool.close(); pool.join()
+    value = n * args.steps / total
+    sample = f"{n} of the 1,048,576-set sweep's prior draws per step (seed 0), scipy odeint + masked chi, {cores} processes"
+    print(json.dumps({
+        "impl": "reference", "metric": "ode_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def workload_config(args, n_gpus):
+    return {"workload": f"forward sweep: {args.sets} prior-sampled parameter sets per GPU of the demo {MODEL} "
+                        f"infection model (4 states, 5 parameters) integrated to the 37 demo observations "
+                        f"(19 grid times of t_steps={TSTEPS}) + chi/R^2 [BASELINE.json configs[1]]",
+            "sets_per_gpu": args.sets, "sets_total": args.sets * n_gpus, "rtol": 1.49012e-8, "atol": 1.49012e-8,
+            "solver": "dopri5(4) dense output", "l2": "flushed between timed steps (256 MiB write)",
+            "parallelism": f"shard{n_gpus}"}
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import odelib_b200 as ODElib
+    from odelib_b200 import _capi, demo_models, engine
+    from odelib_b200.rhat import allgather_summaries, rhat_from_summaries
+    import scipy.stats
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- the model, through the reference-facing surface -------------------------------------------
+    pri = demo_models.PRIORS[MODEL]
+    pobj = {p: ODElib.parameter(stats_gen=scipy.stats.lognorm, hyperparameters={"s": s, "scale": sc}, init_value=sc)
+            for p, (s, sc) in pri.items()}
+    model = ODElib.ModelFramework(ODE=demo_models.two_i, parameter_names=demo_models.PARAMETER_NAMES[MODEL],
+                                  state_names=demo_models.STATE_NAMES[MODEL], dataframe=demo_frame(),
+                                  state_summations={"H": ["S", "I1", "I2"]}, S=5236900, t_steps=TSTEPS, device=local,
+                                  **pobj)
+    dm = model._device()
+    n, P, ns = args.sets, dm.n_param, dm.n_state
+    theta_host = torch.from_numpy(prior_draws(n, 0, offset=rank)).pin_memory()      # weak scaling: own block per rank
+    theta_dev = theta_host.to(dev)
+    out = {"chi": torch.empty(n, dtype=torch.float64, device=dev), "r2": torch.empty(n, dtype=torch.float64, device=dev),
+           "status": torch.empty(n, dtype=torch.int32, device=dev), "nsteps": torch.empty(n, dtype=torch.int32, device=dev)}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    launches0 = _capi.lib().odl_launch_count()
+
+    peak_tflops, _ = engine.fp64_peak(local)
+
+    # ---- device-resident sweep: `value` -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        dm.sweep(theta_dev, out=out)
+    clocks = ClockSampler(local)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    clocks.start()
+    l0 = _capi.lib().odl_launch_count()
+    for a, b in ev:
+        flush.fill_(1)                      # L2 flush between timed steps (outside the event pair)
+        a.record()
+        dm.sweep(theta_dev, out=out)
+        b.record()
+    barrier()
+    timed_launches = _capi.lib().odl_launch_count() - l0
+    ms = [a.elapsed_time(b) for a, b in ev]
+    t_total = max_over_ranks(sum(ms) * 1e-3)
+    clk = clocks.stop()
+    value = n * world * args.steps / t_total
+    nsteps = out["nsteps"].to(torch.int64)
+    status = out["status"]
+    flops_step = 6 * dm.rhs_flops + 71 * ns + 10                     # SURVEY.md §8d flop model
+    flops_launch = float(nsteps.sum().item()) * flops_step + n * (dm.n_slot * (30 + 12 * ns) + dm.n_obs * 8)
+    avg_ms = float(np.mean(ms))
+    achieved = flops_launch / (avg_ms * 1e-3) / 1e12
+    bytes_launch = n * (P * 8 + 8 + 8 + 4 + 4)
+    ok_frac = float((status == 0).float().mean().item())
+    mean_steps = float(nsteps.double().mean().item())
+
+    # ---- end to end through the facade with pinned host buffers: `e2e` ---------------------------------
+    th_np = theta_host.numpy()
+    host_out = {k: torch.empty(n, dtype=(torch.float64 if k in ("chi", "r2") else torch.int32)).pin_memory().numpy()
+                for k in ("chi", "r2", "status", "nsteps")}
+    for _ in range(2):
+        dm.sweep(th_np, out=host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model._device().sweep(th_np, out=host_out)          # H2D of theta, kernel, D2H of chi/r2/status/nsteps, sync
+    torch.cuda.synchronize()
+    e2e_t = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": n * world * args.steps / e2e_t, "unit": "solves/s", "h2d_bytes_per_step": n * P * 8,
+           "d2h_bytes_per_step": n * 24, "api": "ModelFramework.sweep(numpy pinned) -> odl_sweep(ODL_MEM_HOST)"}
+    assert np.array_equal(host_out["nsteps"], out["nsteps"].cpu().numpy())
+
+    # ---- MCMC leg: chain-steps/s ---------------------------------------------------------------------
+    mcmc = None
+    if args.chains > 0:
+        C, nits = args.chains, args.nits
+        rng = np.random.default_rng([1, rank])
+        starts = torch.from_numpy(np.array(CENTER[MODEL]) * np.exp(0.05 * rng.standard_normal((C, P)))).to(dev)
+        kw = dict(nits=nits, rng_mode="philox", seed=0, chain_offset=rank * C, pnum=P, device_buffers=True)
+        dm.mcmc(starts, **dict(kw, nits=min(nits, 20)))                        # warm-up launch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        res = dm.mcmc(starts, **kw)
+        b.record()
+        barrier()
+        t_m = max_over_ranks(a.elapsed_time(b) * 1e-3)
+        summ = allgather_summaries(res["summaries"]) if world > 1 else res["summaries"]     # the one collective
+        rh = rhat_from_summaries(summ.cpu().numpy(), P)
+        steps_total = sum_over_ranks(float(res["step_count"].sum().item()))
+        kept_bytes = C * res["n_keep"] * (P + 5) * 8
+        mcmc = {"chain_steps_per_s": C * world * (nits - 1) / t_m, "chains_per_gpu": C, "chains_total": C * world,
+                "iterations": nits, "seconds": t_m, "solves_per_s": C * world * nits / t_m,
+                "fp64_tflops": (steps_total * flops_step) / t_m / 1e12 / world,
+                "sample_stream_GBps": kept_bytes / t_m / 1e9,
+                "accept_rate": float(res["chain_state"][:, 2].mean().item()) / (nits - 1),
+                "rhat_max": float(np.nanmax(rh)), "rhat_collective": "nccl all_gather" if world > 1 else "none (1 GPU)"}
+
+    launches = _capi.lib().odl_launch_count() - launches0
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's algorithm on the host cores ---------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        ncpu = min(cores * 4000, n)
+        rate, dt = cpu_sweep_rate(theta_host.numpy()[:ncpu], cores)
+        # cross-check while we are here: GPU chi vs oracle chi on healthy rows
+        cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
+               "sample": f"first {ncpu} parameter sets of the same sweep, scipy odeint (LSODA, default tol) + numpy "
+                         f"masked chi in {cores} forked processes, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "ode_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tflops, "traffic": None,
+                         "kernel": "odl_sweep_kernel", "avg_launch_ms": avg_ms,
+                         "peak_source": "measured live: odl_fp64_peak DFMA chains (MEASURED_PEAKS.json has no FP64 figure)",
+                         "flops_per_launch": flops_launch, "flops_per_step_attempt": flops_step,
+                         "mean_steps_per_solve": mean_steps,
+                         "hbm": {"algorithmic_bytes_per_launch": bytes_launch,
+                                 "achieved_GBps": bytes_launch / (avg_ms * 1e-3) / 1e9, "peak_GBps": hbm_peak(),
+                                 "frac": bytes_launch / (avg_ms * 1e-3) / 1e9 / hbm_peak()}},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(timed_launches), "gpu_launches_total": int(launches),
+            "clocks": clk, "ok_fraction": ok_frac, "mcmc": mcmc,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:  # noqa: BLE001
+        return 6650.0   # fallback stated in B200_PROFILING.md
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sets", type=int, default=1 << 20, help="parameter sets per GPU per step")
+    ap.add_argument("--chains", type=int, default=4096, help="MCMC chains per GPU (0 = skip the MCMC leg)")
+    ap.add_argument("--nits", type=int, default=500, help="iterations per chain in the MCMC leg")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

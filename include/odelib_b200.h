@@ -1,0 +1,137 @@
+/* odelib_b200.h -- C ABI of the B200-native ODElib hot path (libodelib_b200.so).
+ *
+ * Plain C, plain pointers and sizes; no torch / C++ types cross this boundary.  The reference
+ * (SEpapoulis/ODElib 0.1.1) is pure Python and has NO FFI of its own; each entry point below
+ * replaces one of its natural batch seams (paths are into /root/reference):
+ *
+ *   odl_model_create     <- the user's RHS callable handed to ModelFramework (ODElib/Framework.py:168,
+ *                           :212) and evaluated by scipy odeint (Framework.py:656).  Here: CUDA source
+ *                           of the traced RHS, NVRTC-compiled for sm_100a together with the integrators.
+ *   odl_model_set_data   <- ModelFramework.__init__ data setup: _formatdf/_df_fitsetup
+ *                           (Framework.py:281-329), times (:234), inits (:246-258, :496-510),
+ *                           '<state>0' parameters (Statistics/Samplers.py:110-114).
+ *   odl_model_set_grid   <- self.times, the output grid of integrate() (Framework.py:234, :241).
+ *   odl_sweep            <- _Fit_worker(model, parameter_list) (Framework.py:41-48): for every
+ *                           parameter set integrate(predict_obs=True) + get_chi (:622-697), plus
+ *                           get_Rsqrd (:699-702).
+ *   odl_trajectory       <- ModelFramework.integrate(...) full-grid result (Framework.py:656, :683).
+ *   odl_mcmc             <- Samplers.MetropolisHastings (Statistics/Samplers.py:53-174) for many
+ *                           chains at once; _Chain_worker / the serial loop (Framework.py:19-22,
+ *                           :1025-1030).
+ *   odl_fp64_peak        <- (no reference counterpart) measures the FP64 FMA roofline denominator.
+ *
+ * Conventions: every function returns 0 on success or an ODL_E* code; odl_last_error() gives the
+ * message of the calling thread's last failure.  Numerical failure of a single system is NOT an
+ * error: it is reported in that system's status word and its chi is NaN (the reference silently
+ * yields NaN / masked there and the sampler rejects, Samplers.py:127).  The caller owns all buffers.
+ * `mem` says where the caller's arrays live: ODL_MEM_HOST (library stages them through its own
+ * device scratch; copies are inside the call) or ODL_MEM_DEVICE (CUDA device pointers, e.g. torch
+ * tensor .data_ptr(); nothing is copied).  `stream` is a cudaStream_t (NULL = default stream).
+ * Calls are asynchronous only for ODL_MEM_DEVICE; host-memory calls return after their results
+ * have landed.  Handles are not thread-safe; use one per host thread / per GPU.
+ */
+#ifndef ODELIB_B200_H
+#define ODELIB_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODL_ABI_VERSION 1
+
+enum { ODL_SUCCESS = 0, ODL_EINVAL = 1, ODL_ECUDA = 2, ODL_ECOMPILE = 3, ODL_ENODEVICE = 4, ODL_EIO = 5 };
+enum { ODL_MEM_HOST = 0, ODL_MEM_DEVICE = 1 };
+enum { ODL_SOLVER_DOPRI5 = 0, ODL_SOLVER_ROS23 = 1, ODL_SOLVER_AUTO = 2 };
+enum { ODL_RNG_PHILOX = 0, ODL_RNG_HOST_STREAMS = 1, ODL_RNG_FORCED = 2 };
+/* per-system status words */
+enum { ODL_ST_OK = 0, ODL_ST_MAXSTEPS = 1, ODL_ST_NONFINITE = 2, ODL_ST_HUNDERFLOW = 3, ODL_ST_STIFF = 4,
+       ODL_ST_ALLMASKED = 8 };
+
+typedef struct odl_model odl_model;
+
+typedef struct odl_build_opts {
+  int device;          /* CUDA ordinal; -1 = current device */
+  int block_threads;   /* threads per CTA, 0 = default (128) */
+  int min_blocks;      /* __launch_bounds__ min CTAs per SM, 0 = default (4) */
+  int dense_output;    /* 1 = dense output at the observation times (default), 0 = land on them */
+  int compile_only;    /* 1 = NVRTC-compile (and cache) but do not touch a GPU */
+  int reserved[3];
+  const char* cache_dir; /* directory for compiled cubins, NULL = no cache */
+} odl_build_opts;
+
+typedef struct odl_solver_opts {
+  double rtol, atol;   /* scipy odeint defaults are 1.49012e-8 (Framework.py:656) */
+  double h0, hmax;     /* 0 = automatic */
+  int max_steps;       /* attempted steps per solve before ODL_ST_MAXSTEPS */
+  int solver;          /* ODL_SOLVER_* */
+  int stiff_check;     /* DOPRI5: detect stiffness and stop with ODL_ST_STIFF */
+  int reserved;
+} odl_solver_opts;
+
+typedef struct odl_mcmc_opts {
+  int n_chain;
+  int chain_offset;    /* global index of the first chain (multi-GPU shard; keys the Philox stream) */
+  int nits;            /* as Samplers.MetropolisHastings(nits): nits-1 iterations */
+  int burnin;          /* rows are kept iff iteration > burnin */
+  int it_begin, it_end;/* run iterations [it_begin, it_end); 0,0 = whole chain [1, nits) */
+  int rng_mode;        /* ODL_RNG_* */
+  int n_walk;          /* number of walking (non-static) parameters */
+  const int* walk;     /* [n_walk] their indices in parameter_names order */
+  int pnum;            /* _pnum for AIC (Framework.py:261-263) */
+  int row_stride;      /* doubles per sample row, >= n_param+5 */
+  double step_sd;      /* 0.05 (Framework.py:107) */
+  unsigned long long seed;
+} odl_mcmc_opts;
+
+typedef struct odl_mcmc_io {
+  double* theta;           /* [n_chain][n_param] in: starts (or current points), out: current points */
+  double* chain_state;     /* [n_chain][4] chi, r2, accepts, unused; in when it_begin>1, always out */
+  double* samples;         /* [n_chain][nits-1-burnin][row_stride] or NULL:
+                              theta.., chi, rsquared, aic, iteration, acceptance_ratio (Samplers.py:160-165) */
+  double* summaries;       /* [n_chain][1+2*n_param] count, mean, M2 of ln(theta) over kept rows, or NULL
+                              (must be zeroed by the caller before the first segment) */
+  const double* z;         /* [n_chain][nits-1][n_walk]  proposal increments (ODL_RNG_HOST_STREAMS) */
+  const double* u;         /* [n_chain][nits-1]          acceptance uniforms (HOST_STREAMS, FORCED) */
+  const double* forced;    /* [n_chain][nits-1][n_param] proposals (ODL_RNG_FORCED) */
+  double* trace_chinew;    /* optional [n_chain][nits-1] */
+  unsigned char* trace_accept; /* optional [n_chain][nits-1] */
+  int* fail_count;         /* optional [n_chain], accumulated */
+  long long* step_count;   /* optional [n_chain], accumulated attempted integrator steps */
+} odl_mcmc_io;
+
+int odl_abi_version(void);
+const char* odl_last_error(void);
+
+int odl_model_create(const char* model_cuda_src, int n_state, int n_param, int n_out,
+                     const odl_build_opts* opts, odl_model** out);
+int odl_model_destroy(odl_model* m);
+/* compile log of the NVRTC run (warnings included); valid until the model is destroyed */
+const char* odl_model_build_log(const odl_model* m);
+/* resource usage of a compiled kernel ("sweep", "mcmc", "traj"): registers/thread, local (spill) bytes */
+int odl_model_kernel_info(const odl_model* m, const char* kernel, int* regs, int* local_bytes, int* max_blocks_per_sm);
+
+int odl_model_set_data(odl_model* m, int n_slot, const double* slot_time, int n_obs, const int* obs_slot,
+                       const int* obs_col, const double* ln_obs, const double* log_sigma, double sstot,
+                       const double* y0, const int* y0_from_param, double t0);
+int odl_model_set_grid(odl_model* m, int n_t, const double* times, const double* y0, const int* y0_from_param);
+
+int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, const double* theta, int mem,
+              double* chi, double* r2, int* status, int* nsteps, double* pred_or_null, void* stream);
+int odl_trajectory(odl_model* m, const odl_solver_opts* so, long long n, const double* theta,
+                   const double* y0_or_null, int mem, double* traj, int* status, int* nsteps, void* stream);
+int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_opts* mo, const odl_mcmc_io* io, int mem,
+             void* stream);
+
+/* device time (ms) of the kernels launched by the last odl_sweep/odl_mcmc/odl_trajectory call on this
+   model, measured with CUDA events on the launching stream; blocks until they have completed */
+int odl_model_last_kernel_ms(odl_model* m, float* ms);
+/* number of kernel launches issued by this library in this process */
+long long odl_launch_count(void);
+
+/* FP64 roofline denominator: sustained DFMA throughput of `device` in TFLOP/s (FMA = 2 flop) */
+int odl_fp64_peak(int device, int repeats, double* tflops, float* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODELIB_B200_H */

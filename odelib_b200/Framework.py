@@ -1,0 +1,530 @@
+"""ModelFramework / parameter: ODElib's Python surface (ODElib/Framework.py) over the B200 hot path.
+
+Same constructor, ``integrate`` / ``get_chi`` / ``get_residuals`` / ``fit_survey`` / ``MCMC`` signatures and
+return frames as the reference, so a notebook written against ODElib keeps working; what changed is what
+happens underneath:
+
+* the ODE callable is traced once and compiled by NVRTC (tracer.py, engine.DeviceModel) instead of being
+  called back from scipy's LSODA (Framework.py:656);
+* ``fit_survey`` / the ``_Fit_worker`` loop (Framework.py:41-48, :800-816) is one launch of the batched
+  DOPRI5 kernel with chi / R^2 fused;
+* ``MCMC`` / ``Samplers.MetropolisHastings`` (Framework.py:946-1061, Samplers.py:53-174) run all chains in
+  one device-resident kernel; ``cpu_cores`` is accepted and ignored;
+* there is no CPU fallback: without the CUDA library / a B200 every compute call raises.
+
+Documented deviations from the reference: ``get_residuals`` returns the aligned
+observation-row residuals (A19, the reference's pandas alignment is a cartesian product); plain numeric
+parameter kwargs in the ctor are accepted (A15, broken in the reference); no debug prints (A4).
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import pandas as pd
+
+from .engine import SCIPY_TOL, DeviceModel, ObsTables
+from .rhat import allgather_summaries, rhat_from_summaries, shard_bounds
+from .Statistics import Samplers, stats
+
+
+def rawstats(pdseries):
+    """Log-space median and log-normal standard deviation of a posterior column (Framework.py:11-17)."""
+    lx = np.log(pdseries)
+    log_mean = lx.mean()
+    log_std = lx.std()
+    return np.exp(log_mean), ((np.exp(log_std ** 2) - 1) * np.exp(2 * log_mean + log_std ** 2.0)) ** 0.5
+
+
+class parameter:
+    """A parameter value with an optional scipy.stats prior and its hyper-parameters (Framework.py:50-163)."""
+
+    def __init__(self, stats_gen=None, hyperparameters=None, init_value=None, name=None):
+        self.dist = stats_gen
+        self.hp = hyperparameters
+        self.name = name
+        if init_value:                                            # 0 counts as "not given", as in the reference
+            self.val = np.array(init_value)
+        else:
+            if not self.dist:
+                raise ValueError("You must specify a scipy distribution if not passing a value")
+            self.val = np.array(self.dist.rvs(**self.hp))
+        self._dim = self.val.shape
+
+    def pdf(self, val=None):
+        """Prior density at ``val``; without an argument, at a fresh prior draw (Framework.py:97-105)."""
+        if not self.dist:
+            return 1.0
+        if val:
+            return self.dist.pdf(val, **self.hp)
+        return self.dist.pdf(self.dist.rvs(**self.hp), **self.hp)
+
+    def rwalk(self, std=.05):
+        """Multiplicative log-normal random-walk step (Framework.py:107-122)."""
+        self.val = np.exp(np.log(self.val) + np.random.normal(0, np.full(np.shape(self.val), std)))
+
+    def has_distribution(self):
+        return bool(self.dist)
+
+    def copy(self):
+        return parameter(init_value=self.val, stats_gen=self.dist, hyperparameters=self.hp, name=self.name)
+
+    def __repr__(self):
+        out = [str(self.val) + '  ']
+        if self.dist:
+            out.append("(distribution:{}, ".format(self.dist.name))
+            out.append("hyperparameters:{})".format(str(self.hp)))
+        return ' '.join(out)
+
+    __str__ = __repr__
+
+
+class ModelFramework:
+    """Drop-in for ODElib.ModelFramework (Framework.py:166-1165) for the integrate / score / sweep / MCMC path."""
+
+    def __init__(self, ODE, parameter_names, state_names, dataframe=None, state_summations=None,
+                 t_end=5, t_steps=1000, random_seed=0, **kwargs):
+        self._pnames = tuple(parameter_names)
+        self._snames = tuple(state_names)
+        self._model = ODE
+        self.parameters = {p: None for p in self._pnames}
+        self.istates = {s: 0 for s in self._snames}
+        self.random_seed = random_seed
+        # device-side options (not in the reference): tolerances default to scipy odeint's
+        self.rtol = kwargs.pop("rtol", None)
+        self.atol = kwargs.pop("atol", None)
+        self.device = kwargs.pop("device", None)
+        self._dm = None
+        self._dm_stamp = None
+        if state_summations:
+            (self._summations_index, self._summation_snames, self._sumkeep,
+             self._suminds) = self._get_summation_index(state_summations)
+        else:
+            self._summations_index, self._summation_snames, self._sumkeep, self._suminds = {}, tuple(), tuple(), tuple()
+        self._obs_logabundance, self._obs_logsigma, self._obs_abundance = {}, {}, {}
+        self._pred_tindex = {}
+        if isinstance(dataframe, pd.DataFrame):
+            self.df = self._formatdf(dataframe.copy())
+            self.times = np.linspace(0, max(self.df['time']), t_steps)
+            self._samples = len(self.df)
+            self._pred_tindex, self._obs_logabundance, self._obs_logsigma = self._df_fitsetup()
+        else:
+            self.df = None
+            self._samples = None
+            self.times = np.linspace(0, t_end, t_steps)
+        inits, params = {}, {}
+        if self.df is not None:
+            first = self.df[self.df['time'] == 0]['abundance']
+            for org, abundance in first.items():
+                inits.setdefault(org, abundance)
+        for k, v in kwargs.items():
+            if k in self._pnames:
+                params[k] = v
+            if k in self._snames:
+                inits[k] = v
+        self.set_parameters(**params)
+        self.set_inits(**inits)
+        self._pnum = 0
+        for p in self.parameters:
+            if self.parameters[p] is not None:
+                self._pnum += np.count_nonzero(self.parameters[p].val)
+
+    # ------------------------------------------------------------------ data setup (Framework.py:266-381)
+    def reset_dataframe(self, df):
+        self.df = self._formatdf(df.copy())
+        self.times = np.linspace(0, max(self.df['time']), len(self.times))
+        self._pred_tindex, self._obs_logabundance, self._obs_logsigma = self._df_fitsetup()
+        self._samples = len(self.df)
+        inits = {}
+        for org, abundance in self.df[self.df['time'] == 0]['abundance'].items():
+            inits.setdefault(org, abundance)
+        self.set_inits(**inits)
+        self._dm_stamp = None
+
+    def _formatdf(self, df):
+        """(organism, time, abundance[, log_sigma | replicate]) -> frame indexed by organism, time-sorted."""
+        df = df.sort_values(by=['organism', 'time'])
+        if 'replicate' in df:
+            work = df[['organism', 'time', 'abundance']].copy()
+            work['log_abundance'] = np.log(work['abundance'])
+            agg = work.groupby(by=['time', 'organism']).mean()
+            agg['log_sigma'] = work.groupby(by=['time', 'organism']).std()['log_abundance']
+            df = agg.reset_index(level='time').sort_values(by='time', kind='stable').sort_index(kind='stable')
+        else:
+            df = df.set_index('organism')
+            if 'abundance' in df and 'log_abundance' not in df:
+                df['log_abundance'] = np.log(df['abundance'].to_numpy())
+            if 'log_sigma' not in df:
+                df['log_sigma'] = 1
+                warnings.warn("log_sigma not found, setting log variance to 1")
+        return df
+
+    def _df_fitsetup(self):
+        """Nearest output-grid index of every observation row (first minimum) + per-organism arrays."""
+        tindex, logab, logsig = {}, {}, {}
+        for org in dict.fromkeys(self.df.index):
+            rows = self.df.loc[[org]]
+            tt = rows['time'].to_numpy(dtype=float)
+            gap = np.abs(tt[:, None] - self.times[None, :])
+            tindex[org] = np.argmax(gap == gap.min(axis=1, keepdims=True), axis=1).astype(np.int64)
+            logab[org] = rows['log_abundance'].to_numpy(dtype=float)
+            logsig[org] = rows['log_sigma'].to_numpy(dtype=float)
+        return tindex, logab, logsig
+
+    def _get_summation_index(self, summation_mapping):
+        """{first member index: member indices}, names after summation, kept columns, renamed indices."""
+        where = {s: i for i, s in enumerate(self._snames)}
+        sums, renamed, used = {}, {}, set()
+        for new_name, members in summation_mapping.items():
+            idx = []
+            for member in members:
+                if member in used:
+                    raise ValueError("{} state varaiable cannot be used in two summations".format(member))
+                if member not in where:
+                    raise ValueError("{} state varaiable is not a valid state name".format(member))
+                used.add(member)
+                idx.append(where[member])
+            if len(idx) < 1:
+                raise ValueError("Summation of {} needs two or more state variables".format(new_name))
+            idx.sort()
+            sums[idx[0]] = tuple(idx)
+            renamed[idx[0]] = new_name
+        names, keep = [], []
+        for i, s in enumerate(self._snames):
+            if i in renamed:
+                names.append(renamed[i]); keep.append(i)
+            elif s not in used:
+                names.append(s); keep.append(i)
+        return sums, tuple(names), tuple(keep), renamed
+
+    # ------------------------------------------------------------------ names / values
+    def get_pnames(self):
+        return list(self._pnames)
+
+    def get_snames(self, after_summation=True, predict_obs=False):
+        if after_summation and self._summations_index:
+            return list(self._summation_snames)
+        if predict_obs:
+            return list(self._pred_tindex.keys())
+        return list(self._snames)
+
+    def get_numstatevar(self):
+        return len(self._snames)
+
+    def get_model(self):
+        return self._model
+
+    def __repr__(self):
+        out = ["Current Model = {}".format(str(self._model.__module__) + '.' + str(self._model.__name__)), "Parameters:"]
+        out += ["\t{} = {}".format(p, self.parameters[p]) for p in self.get_pnames()]
+        out.append("Initial States:")
+        out += ["\t{} = {}".format(s, self.istates[s]) for s in self._snames]
+        if self._summations_index:
+            out.append("Current State Summations")
+            for i, members in self._summations_index.items():
+                out.append("\t{}={}".format(self._suminds[i], '+'.join(self._snames[j] for j in members)))
+        return '\n'.join(out)
+
+    __str__ = __repr__
+
+    def set_parameters(self, **kwargs):
+        for p, v in kwargs.items():
+            if p not in self.parameters:
+                raise Exception("{} is an unknown parameter. Acceptable parameters are: {}".format(p, ', '.join(self._pnames)))
+            if isinstance(v, parameter):
+                self.parameters[p] = v
+                if not v.name:
+                    v.name = p
+            elif self.parameters[p] is not None:
+                self.parameters[p].val = v
+            else:
+                self.parameters[p] = parameter(init_value=v, name=p)
+
+    def set_inits(self, **kwargs):
+        summed = set(self._summation_snames)
+        for s, v in kwargs.items():
+            if s in self.istates:
+                self.istates[s] = v
+            elif s in summed:
+                pass                     # initial value of a summed observable: accepted, not enforced (:476-493)
+            else:
+                raise Exception("{} is an unknown state variable. Acceptable parameters are: {}".format(s, ', '.join(self._snames)))
+
+    def get_inits(self, as_dict=False):
+        if as_dict:
+            return self.istates
+        return np.array([self.istates[s] for s in self._snames])
+
+    def get_parameters(self, as_dict=False, **kwargs):
+        vals = [kwargs[p] if p in kwargs else self.parameters[p].val for p in self._pnames]
+        if as_dict:
+            return dict(zip(self._pnames, vals))
+        return tuple([vals])
+
+    def _current_theta(self):
+        return np.array([float(self.parameters[p].val) for p in self._pnames], dtype=np.float64)
+
+    # ------------------------------------------------------------------ device model
+    def _y0_map(self):
+        """'<state>0' parameters double as that state's initial value (Samplers.py:110-114)."""
+        return np.array([self._pnames.index(s + '0') if (s + '0') in self._pnames else -1 for s in self._snames], np.int32)
+
+    def _observe_groups(self):
+        if not self._summations_index:
+            return [(i,) for i in range(len(self._snames))]
+        return [self._summations_index.get(i, (i,)) for i in self._sumkeep]
+
+    def _device(self):
+        """Compile (once) and (re)load tables when data / initial states changed."""
+        if self._dm is None:
+            for p in self._pnames:
+                if self.parameters[p] is not None and np.ndim(self.parameters[p].val) != 0:
+                    raise NotImplementedError("array-valued parameters are not supported on the device path")
+            self._dm = DeviceModel(self._model, len(self._snames), len(self._pnames), self._observe_groups(),
+                                   device=self.device)
+        y0 = np.asarray(self.get_inits(), dtype=np.float64)
+        stamp = (self.times.tobytes(), y0.tobytes(), id(self.df), self._samples)
+        if stamp != self._dm_stamp:
+            if self.df is not None:
+                out_names = self.get_snames(after_summation=True)
+                cols = [(i, self._pred_tindex[s], self._obs_logabundance[s], self._obs_logsigma[s])
+                        for i, s in enumerate(out_names) if s in self._pred_tindex]
+                self._obs_order = [s for s in out_names if s in self._pred_tindex]
+                self._dm.set_data(ObsTables(self.times, cols), y0, self._y0_map())
+            self._dm.set_grid(self.times, y0, self._y0_map())
+            self._dm_stamp = stamp
+        return self._dm
+
+    # ------------------------------------------------------------------ integrate + score (Framework.py:617-722)
+    def integrate(self, inits=None, parameters=None, predict_obs=False, as_dataframe=True, sum_subpopulations=True):
+        """Solve on ``self.times``; same four return shapes as the reference (Framework.py:622-683)."""
+        dm = self._device()
+        theta = np.asarray(parameters[0] if parameters else self.get_parameters()[0], dtype=np.float64)
+        y0 = None if inits is None else np.asarray(inits, dtype=np.float64)
+        traj, status, _ = dm.trajectory(theta[None, :], y0=y0, rtol=self.rtol, atol=self.atol)
+        if status[0] != 0:
+            warnings.warn("integration stopped early (status {}); remaining rows are NaN".format(int(status[0])))
+        mod = traj[0]
+        if sum_subpopulations and self._summations_index:
+            for first, members in self._summations_index.items():
+                mod[:, first] = mod[:, list(members)].sum(axis=1)
+            mod = mod[:, list(self._sumkeep)]
+        if as_dataframe:
+            df = pd.DataFrame(mod, columns=self.get_snames(after_summation=sum_subpopulations))
+            df['time'] = self.times
+            if predict_obs:
+                parts = []
+                for s in self.get_snames(predict_obs=True):
+                    idx = self._pred_tindex[s]
+                    parts.append(pd.DataFrame({'time': self.times[idx], 'abundance': df[s].to_numpy()[idx]},
+                                              index=pd.Index([s] * len(idx), name='organism')))
+                return pd.concat(parts)
+            return df
+        if predict_obs:
+            return {s: mod[:, i][self._pred_tindex[s]]
+                    for i, s in enumerate(self.get_snames(after_summation=sum_subpopulations)) if s in self._pred_tindex}
+        return mod
+
+    def get_chi(self, mod_dict):
+        O, Cc, S = [], [], []
+        with np.errstate(all="ignore"):
+            for s in mod_dict:
+                O.append(self._obs_logabundance[s]); Cc.append(np.log(mod_dict[s])); S.append(self._obs_logsigma[s])
+        return stats.chi(np.concatenate(O), np.concatenate(Cc), np.concatenate(S))
+
+    def get_Rsqrd(self, mod_dict):
+        return stats.Rsqrd(mod_dict, {s: np.exp(self._obs_logabundance[s]) for s in self._obs_logabundance if s in mod_dict})
+
+    def get_AIC(self, chi):
+        return stats.AIC(chi, self._pnum)
+
+    def get_adjRsqrd(self, mod_dict, Rsqrd=None):
+        if not Rsqrd:
+            Rsqrd = self.get_Rsqrd(mod_dict)
+        return stats.get_adjusted_rsquared(Rsqrd, self._samples, self._pnum)
+
+    def get_fitstats(self, prediction_dict=dict()):
+        if not prediction_dict:
+            prediction_dict = self.integrate(predict_obs=True, as_dataframe=False)
+        fs = {'Chi': self.get_chi(prediction_dict), 'R^2': self.get_Rsqrd(prediction_dict)}
+        fs['AIC'] = self.get_AIC(fs['Chi'])
+        return fs
+
+    def get_residuals(self):
+        """Linear-space residual (model - data) per observation row, index = organism."""
+        mod = self.integrate(predict_obs=True)
+        parts = [self.df.loc[[s]]['abundance'].to_numpy() for s in self.get_snames(predict_obs=True)]
+        return pd.Series(mod['abundance'].to_numpy() - np.concatenate(parts), index=mod.index, name='abundance')
+
+    # ------------------------------------------------------------------ batch seam: _Fit_worker (Framework.py:41-48)
+    def sweep(self, parameter_array, rtol=None, atol=None, solver="dopri5", as_dataframe=False):
+        """chi (and R^2, status, steps) for every row of ``parameter_array`` [n, P] (parameter_names order).
+
+        numpy in -> numpy out (host buffers, copies inside the call); torch CUDA tensor in -> tensors out."""
+        dm = self._device()
+        res = dm.sweep(parameter_array, rtol=self.rtol if rtol is None else rtol,
+                       atol=self.atol if atol is None else atol, solver=solver)
+        if as_dataframe:
+            df = pd.DataFrame(np.asarray(parameter_array), columns=self.get_pnames())
+            df['chi'] = res['chi']
+            return df
+        return res
+
+    def _lhs_samples(self, samples=100, **kwargs):
+        pdists, pstatic = {}, {}
+        for p in self.parameters:
+            if p in kwargs:
+                pdists[p] = kwargs[p]
+            elif self.parameters[p].has_distribution():
+                pdists[p] = self.parameters[p]
+            else:
+                pstatic[p] = self.parameters[p].val
+        df = Samplers.sample_lhs(parameter_dict=pdists, samples=samples)
+        for p in pstatic:
+            df[p] = float(pstatic[p])
+        return df
+
+    def fit_survey(self, samples=1000, cpu_cores=1):
+        """LHS sample of the priors, chi of every sample (Framework.py:800-816).  ``cpu_cores`` is ignored."""
+        ps = self._lhs_samples(samples)[self.get_pnames()]
+        res = self.sweep(ps.to_numpy(dtype=np.float64))
+        out = ps.reset_index(drop=True)
+        out['chi'] = res['chi']
+        return out
+
+    def explore_equilibriums(self, samples=1000, cpu_cores=1, **parameter_mapping):
+        """Final state of every LHS sample (Framework.py:819-854) -- one batched trajectory launch."""
+        ps = self._lhs_samples(samples, **parameter_mapping)[self.get_pnames()]
+        traj, _, _ = self._device().trajectory(ps.to_numpy(dtype=np.float64), rtol=self.rtol, atol=self.atol)
+        df = pd.DataFrame(traj[:, -1, :], columns=self.get_snames(after_summation=False))
+        for p in self.get_pnames():
+            df[p] = ps[p].to_numpy()
+        return df
+
+    def copy(self, overwrite=dict()):
+        """Independent copy sharing the compiled device model (Framework.py:901-943)."""
+        new = ModelFramework.__new__(ModelFramework)
+        for k, v in self.__dict__.items():
+            if k == 'parameters':
+                new.parameters = {p: (q.copy() if q is not None else None) for p, q in v.items()}
+            elif isinstance(v, (list, dict, pd.DataFrame, np.ndarray)):
+                new.__dict__[k] = v.copy()
+            else:
+                new.__dict__[k] = v
+        ps = {k: v for k, v in overwrite.items() if k in new._pnames}
+        st = {k: v for k, v in overwrite.items() if k in new._snames}
+        if ps:
+            new.set_parameters(**ps)
+        if st:
+            new.set_inits(**st)
+        return new
+
+    def set_best_params(self, posteriors):
+        im = posteriors['chi'].idxmin()
+        best = posteriors.loc[im][self.get_pnames()].to_dict()
+        self.set_parameters(**best)
+        if self._snames[0] + '0' in self.get_pnames():
+            self.set_inits(**{s: best[s + '0'] for s in self._snames})
+
+    # ------------------------------------------------------------------ MCMC (Framework.py:946-1061)
+    def _run_chains(self, starts, seeds, nits, burnin, static_parameters, rng="auto", rtol=None, atol=None,
+                    update_model=False, return_raw=False):
+        """All chains in one kernel.  starts: list of theta vectors; seeds: per-chain seeds (chain index)."""
+        dm = self._device()
+        static = set(static_parameters or ())
+        walk_names = [p for p in self._pnames if p not in static]
+        walk = [self._pnames.index(p) for p in walk_names]
+        theta0 = np.array(starts, dtype=np.float64)
+        C = theta0.shape[0]
+        n_iter = nits - 1
+        if not burnin:
+            burnin = int(nits / 2)
+        if rng == "auto":
+            rng = "reference" if C * n_iter * (2 * len(walk) + 1) <= 20_000_000 else "philox"
+        kw = dict(nits=nits, burnin=burnin, walk=walk, pnum=self._pnum, rtol=self.rtol if rtol is None else rtol,
+                  atol=self.atol if atol is None else atol)
+        if rng == "reference":
+            walking = [self.parameters[p] for p in walk_names]
+            z = np.empty((C, n_iter, len(walk)))
+            u = np.empty((C, n_iter))
+            for c, seed in enumerate(seeds):
+                z[c], u[c] = Samplers.reference_streams(seed, walking, n_iter)
+            out = dm.mcmc(theta0, rng_mode="host", z=z, u=u, **kw)
+        elif rng == "philox":
+            out = dm.mcmc(theta0, rng_mode="philox", seed=int(self.random_seed), chain_offset=int(seeds[0]), **kw)
+        else:
+            raise ValueError("rng must be 'auto', 'reference' or 'philox'")
+        self._last_mcmc = out
+        if return_raw:
+            return out
+        cols = self.get_pnames() + ['chi', 'rsquared', 'aic', 'iteration', 'acceptance_ratio']
+        frames = []
+        for c in range(C):
+            df = pd.DataFrame(out["samples"][c], columns=cols)
+            df['iteration'] = df['iteration'].astype(np.int64)
+            for p in static:   # reference quirk A13: static columns report the prior's scale (Samplers.py:166-170)
+                df[p] = self.parameters[p].hp['scale']
+            if df.empty:
+                df = pd.DataFrame([[np.nan] * (len(self._pnames) + 3)])
+            frames.append(df)
+        if update_model:
+            self.set_parameters(**dict(zip(self._pnames, out["theta"][0])))
+            if any(m >= 0 for m in self._y0_map()):
+                self.set_inits(**{s: out["theta"][0][m] for s, m in zip(self._snames, self._y0_map()) if m >= 0})
+        return frames
+
+    def MCMC(self, chain_inits=1, iterations_per_chain=1000, cpu_cores=1, static_parameters=list(), print_report=True,
+             fitsurvey_samples=1000, sd_fitdistance=3.0, rng="auto"):
+        """Many Metropolis-Hastings chains (Framework.py:946-1061); returns the concatenated posterior frame
+        with a ``chain#`` column.  ``cpu_cores`` is ignored: every chain runs concurrently on the GPU."""
+        if isinstance(chain_inits, pd.DataFrame):
+            chain_inits = [row.to_dict() for _, row in chain_inits[self.get_pnames()].iterrows()]
+        base = self._current_theta()
+        if isinstance(chain_inits, (int, np.integer)):
+            survey = self.fit_survey(samples=fitsurvey_samples)
+            survey = survey.dropna()
+            if survey.empty:
+                warnings.warn("Pre-sampling of Multidimentional space failed")
+                starts = [base.copy() for _ in range(chain_inits)]
+            else:
+                calc = {s: np.exp(self._obs_logabundance[s] + sd_fitdistance * self._obs_logsigma[s])
+                        for s in self._obs_logabundance}
+                cutchi = self.get_chi(calc)                      # = n_obs * sd^2 / 2
+                good = survey[survey['chi'] < cutchi]
+                if len(good) == 0:
+                    raise ValueError("Preliminary sampling found no parameter sets which meet the minimal threshold \n"
+                                     "  Try: \n   1. Increasing sd_fitdistance \n   2. Increasing fitsurvey_samples \n"
+                                     "   3. Different priors and / or different parameter guesses")
+                picks = good.sample(chain_inits, replace=True)
+                starts = [picks.iloc[i][self.get_pnames()].to_numpy(dtype=np.float64) for i in range(chain_inits)]
+        else:
+            starts = []
+            for d in chain_inits:
+                th = base.copy()
+                for k, v in d.items():
+                    if k in self._pnames:
+                        th[self._pnames.index(k)] = float(v)
+                starts.append(th)
+        seeds = list(range(len(starts)))                          # chain seed = chain index (:1015, :1020)
+        frames = self._run_chains(starts, seeds, iterations_per_chain, int(iterations_per_chain / 2),
+                                  static_parameters, rng=rng)
+        for i, df in enumerate(frames):
+            df['chain#'] = i
+        posterior = pd.concat(frames).reset_index(drop=True)
+        self.rhat = dict(zip(self.get_pnames(), rhat_from_summaries(self._last_mcmc["summaries"], len(self._pnames)))) \
+            if len(frames) > 1 and self._last_mcmc["n_keep"] > 1 else None
+        if print_report:
+            report = ["\nFitting Report\n==============="]
+            for col in self.get_pnames():
+                median, std = rawstats(posterior[col])
+                if (median != 0.0) and (std != 0.0):
+                    report.append("parameter: {}\n\tmedian = {:0.3e}, Standard deviation = {:0.3e}".format(col, median, std))
+            self.set_best_params(posterior)
+            fs = self.get_fitstats(self.integrate(predict_obs=True, as_dataframe=False))
+            report.append("\nMedian parameter fit stats:")
+            report.append("\tChi = {:0.3e}\n\tR-squared = {:0.3e}\n\tAIC = {:0.3e}".format(fs['Chi'], fs['R^2'], fs['AIC']))
+            if self.rhat:
+                report.append("\nGelman-Rubin R-hat (log-parameters): " +
+                              ", ".join("{}={:.3f}".format(k, v) for k, v in self.rhat.items()))
+            print('\n'.join(report))
+        return posterior

@@ -1,0 +1,94 @@
+// odl_abi.h -- plain-old-data kernel argument blocks shared by the host library (odl_capi.cu) and the
+// device code (odl_kernels.cuh, compiled by NVRTC).  Only fixed-size members: the layout must not depend
+// on the model so that one host build can drive every NVRTC-compiled model.
+#ifndef ODL_ABI_H
+#define ODL_ABI_H
+#define ODL_MAX_WALK 64
+
+// status words (per system)
+#define ODL_OK 0
+#define ODL_MAXSTEPS 1
+#define ODL_NONFINITE 2
+#define ODL_HUNDERFLOW 3
+#define ODL_STIFF 4
+#define ODL_ALLMASKED 8   // or-ed: every chi term was invalid (reference returns np.ma.masked)
+
+struct OdlData {                 // constant tables of one ModelFramework
+  const double* slot_t;          // [n_slot] distinct observation grid times, ascending
+  const double* obs_lnO;         // [n_obs] ln(abundance)              (Framework.py:326)
+  const double* obs_denom;       // [n_obs] 2*sigma^2                  (stats.py:41)
+  const double* obs_lin;         // [n_obs] exp(ln O)                  (Framework.py:700)
+  const int* obs_src;            // [n_obs] slot*n_out + column
+  const double* y0;              // [n_state]
+  const int* y0_from_param;      // [n_state] parameter index supplying the initial value, or -1
+  int n_slot;
+  int n_obs;
+  int stage_stride;              // doubles of staging per thread (odd, >= n_slot*n_out)
+  int pad_;
+  double t0;
+  double sstot;                  // sum_s n_s * var(O_s)               (stats.py:55)
+};
+
+struct OdlOpts {
+  double rtol, atol;
+  double h0;                     // 0 = automatic initial step
+  double hmax;                   // 0 = t_end - t0
+  int max_steps;
+  int stiff_check;               // 1 = run Hairer's stiffness test and bail out with ODL_STIFF
+  int reserved0, reserved1;
+};
+
+struct OdlSweepArgs {
+  const double* theta;           // [n][n_param]
+  const int* index;              // optional indirection (stiff list): system i reads theta[index[i]]
+  const int* index_count;        // optional device-side count for `index` (overrides n)
+  long long n;
+  double* chi;                   // [n]
+  double* r2;                    // [n]
+  int* status;                   // [n]
+  int* nsteps;                   // [n]  attempted steps
+  double* pred;                  // optional [n][n_obs] predictions at the observation rows
+  unsigned long long* counter;   // work counter, zeroed by the host before launch
+  int* stiff_list;               // optional: indices of systems that bailed out with ODL_STIFF
+  int* stiff_count;
+};
+
+struct OdlTrajArgs {
+  const double* theta;           // [n][n_param]
+  const double* y0;              // optional [n][n_state] per-system initial state
+  long long n;
+  double* traj;                  // [n][n_slot][n_state]  raw states on the output grid
+  int* status;
+  int* nsteps;
+  unsigned long long* counter;
+};
+
+struct OdlMcmcArgs {
+  double* theta_cur;             // [C][n_param] in: chain starts / current points; out: current points
+  double* chain_state;           // [C][4]  chi_cur, r2_cur, accepts, (unused)   (persist across launches)
+  int n_chain;
+  int chain_offset;              // global index of chain 0 of this launch (multi-GPU sharding / RNG key)
+  int it_begin, it_end;          // iterations [it_begin, it_end) of Samplers.py:104; it_begin==1 => a-priori solve first
+  int burnin;
+  int n_keep;                    // rows per chain in `samples` (= nits-1-burnin)
+  int row_stride;                // doubles per sample row (>= n_param + 5)
+  int rng_mode;                  // 0 Philox, 1 host z/u streams, 2 teacher-forced proposals + u
+  int n_walk;
+  int pnum;                      // for AIC = 2 chi + 2 pnum   (stats.py:44-47)
+  int walk[ODL_MAX_WALK];        // indices of walking parameters (parameter_names order)
+  double step_sd;                // 0.05 (Framework.py:107)
+  unsigned long long seed;
+  const double* z;               // [C][n_iter_total][n_walk]   (rng_mode 1)
+  const double* u;               // [C][n_iter_total]           (rng_mode 1,2)
+  const double* forced;          // [C][n_iter_total][n_param]    (rng_mode 2)
+  int n_iter_total;              // nits-1
+  int pad_;
+  double* samples;               // [C][n_keep][row_stride]: theta.., chi, rsquared, aic, iteration, acceptance_ratio
+  double* summaries;             // [C][1+2*n_param]: count, mean[P], M2[P] of ln(theta) over kept rows
+  double* trace_chinew;          // optional [C][n_iter_total]  chi of every proposal (parity tests)
+  unsigned char* trace_accept;   // optional [C][n_iter_total]
+  int* fail_count;               // optional [C] proposals whose solve failed
+  long long* step_count;         // optional [C] attempted integrator steps (flop accounting)
+};
+
+#endif  // ODL_ABI_H

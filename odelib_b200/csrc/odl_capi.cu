@@ -1,0 +1,653 @@
+// odl_capi.cu -- host side of libodelib_b200.so: the C ABI declared in include/odelib_b200.h.
+//
+// Runtime API (static cudart) for memory / streams / events; NVRTC compiles the traced model + the
+// integrator kernels (odl_kernels.cuh, embedded below) to an sm_100a cubin; the few driver entry
+// points needed to load and launch that cubin are fetched through cudaGetDriverEntryPoint, so the
+// library has no link-time dependency on libcuda and loads (but cannot compute) on a GPU-less host.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/odelib_b200.h"
+#include "odl_abi.h"
+
+static const char* kAbiHeaderSrc =
+#include "odl_abi_embedded.inc"
+    ;
+static const char* kKernelSrc =
+#include "odl_kernels_embedded.inc"
+    ;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define ODL_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? ODL_ENODEVICE : ODL_ECUDA, \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                          \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// driver entry points (module load + launch of NVRTC output)
+// ---------------------------------------------------------------------------------------------
+struct Driver {
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
+                           void**, void**) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+  CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  bool ok = false;
+};
+static Driver g_drv;
+
+template <class F>
+static bool entry(const char* name, F& fn) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+    return false;
+  fn = reinterpret_cast<F>(p);
+  return true;
+}
+static int load_driver() {
+  if (g_drv.ok) return 0;
+  bool ok = entry("cuModuleLoadData", g_drv.ModuleLoadData) && entry("cuModuleUnload", g_drv.ModuleUnload) &&
+            entry("cuModuleGetFunction", g_drv.ModuleGetFunction) && entry("cuLaunchKernel", g_drv.LaunchKernel) &&
+            entry("cuFuncSetAttribute", g_drv.FuncSetAttribute) && entry("cuFuncGetAttribute", g_drv.FuncGetAttribute) &&
+            entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", g_drv.OccupancyMaxActiveBlocksPerMultiprocessor) &&
+            entry("cuGetErrorString", g_drv.GetErrorString);
+  if (!ok) {
+    cudaGetLastError();
+    return fail(ODL_ENODEVICE, "CUDA driver entry points unavailable (no GPU / driver on this host)");
+  }
+  g_drv.ok = true;
+  return 0;
+}
+static std::string cu_err(CUresult r) {
+  const char* s = nullptr;
+  if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
+  return s ? s : "unknown CUDA driver error";
+}
+#define ODL_CU(call)                                                                  \
+  do {                                                                                \
+    CUresult r_ = (call);                                                             \
+    if (r_ != CUDA_SUCCESS) return fail(ODL_ECUDA, std::string(#call) + ": " + cu_err(r_)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// model handle
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = std::max<size_t>(bytes, 256);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return fail(ODL_ECUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Tables {
+  DevBuf buf;
+  OdlData d{};
+  bool set = false;
+};
+
+struct odl_model {
+  int device = 0;
+  int n_state = 0, n_param = 0, n_out = 0;
+  int block = 128, minblocks = 4, dense = 1;
+  int sm_count = 0;
+  bool on_gpu = false;
+  std::vector<char> cubin;
+  std::string log;
+  CUmodule mod = nullptr;
+  CUfunction k_sweep = nullptr, k_traj = nullptr, k_mcmc = nullptr;
+  CUfunction k_sweep_ros = nullptr, k_mcmc_ros = nullptr;
+  Tables data, grid;
+  DevBuf counter;
+  DevBuf scratch[16];
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+};
+
+static uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+static int compile_model(odl_model* m, const std::string& src, const char* cache_dir) {
+  std::vector<std::string> opt = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device",
+                                  "-DODL_BLOCK=" + std::to_string(m->block),
+                                  "-DODL_MINBLOCKS=" + std::to_string(m->minblocks),
+                                  "-DODL_DENSE=" + std::to_string(m->dense)};
+  int major = 0, minor = 0;
+  nvrtcVersion(&major, &minor);
+  std::string keysrc = src + kKernelSrc + kAbiHeaderSrc;
+  for (auto& o : opt) keysrc += o;
+  keysrc += "nvrtc" + std::to_string(major) + "." + std::to_string(minor);
+  char name[64];
+  snprintf(name, sizeof name, "odl_%016llx.cubin", (unsigned long long)fnv1a(keysrc.data(), keysrc.size()));
+  std::string path;
+  if (cache_dir && *cache_dir) {
+    path = std::string(cache_dir) + "/" + name;
+    if (FILE* f = fopen(path.c_str(), "rb")) {
+      fseek(f, 0, SEEK_END);
+      long sz = ftell(f);
+      fseek(f, 0, SEEK_SET);
+      m->cubin.resize(sz > 0 ? sz : 0);
+      size_t got = sz > 0 ? fread(m->cubin.data(), 1, sz, f) : 0;
+      fclose(f);
+      if (sz > 0 && got == (size_t)sz) { m->log = "cubin cache hit: " + path; return 0; }
+      m->cubin.clear();
+    }
+  }
+  nvrtcProgram prog;
+  const char* hdr_src[2] = {kKernelSrc, kAbiHeaderSrc};
+  const char* hdr_name[2] = {"odl_kernels.cuh", "odl_abi.h"};
+  std::string full = src + "\n#include \"odl_kernels.cuh\"\n";
+  if (nvrtcCreateProgram(&prog, full.c_str(), "odl_model.cu", 2, hdr_src, hdr_name) != NVRTC_SUCCESS)
+    return fail(ODL_ECOMPILE, "nvrtcCreateProgram failed");
+  std::vector<const char*> copt;
+  for (auto& o : opt) copt.push_back(o.c_str());
+  nvrtcResult r = nvrtcCompileProgram(prog, (int)copt.size(), copt.data());
+  size_t logsz = 0;
+  nvrtcGetProgramLogSize(prog, &logsz);
+  m->log.assign(logsz, '\0');
+  if (logsz) nvrtcGetProgramLog(prog, &m->log[0]);
+  if (r != NVRTC_SUCCESS) {
+    nvrtcDestroyProgram(&prog);
+    return fail(ODL_ECOMPILE, std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + m->log);
+  }
+  size_t sz = 0;
+  if (nvrtcGetCUBINSize(prog, &sz) != NVRTC_SUCCESS || sz == 0) {
+    nvrtcDestroyProgram(&prog);
+    return fail(ODL_ECOMPILE, "NVRTC produced no cubin");
+  }
+  m->cubin.resize(sz);
+  nvrtcGetCUBIN(prog, m->cubin.data());
+  nvrtcDestroyProgram(&prog);
+  if (!path.empty()) {
+    std::string tmp = path + ".tmp";
+    if (FILE* f = fopen(tmp.c_str(), "wb")) {
+      fwrite(m->cubin.data(), 1, sz, f);
+      fclose(f);
+      rename(tmp.c_str(), path.c_str());
+    }
+  }
+  return 0;
+}
+
+extern "C" int odl_abi_version(void) { return ODL_ABI_VERSION; }
+extern "C" const char* odl_last_error(void) { return g_err.c_str(); }
+extern "C" long long odl_launch_count(void) { return g_launches.load(); }
+
+extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_param, int n_out,
+                                const odl_build_opts* opts, odl_model** out) {
+  if (!model_cuda_src || !out || n_state < 1 || n_param < 0 || n_out < 1)
+    return fail(ODL_EINVAL, "odl_model_create: bad arguments");
+  if (n_param > ODL_MAX_WALK) return fail(ODL_EINVAL, "odl_model_create: more than 64 parameters are not supported");
+  *out = nullptr;
+  odl_model* m = new odl_model();
+  m->n_state = n_state; m->n_param = n_param; m->n_out = n_out;
+  int device = -1;
+  bool compile_only = false;
+  const char* cache_dir = nullptr;
+  if (opts) {
+    device = opts->device;
+    if (opts->block_threads > 0) m->block = opts->block_threads;
+    if (opts->min_blocks > 0) m->minblocks = opts->min_blocks;
+    m->dense = opts->dense_output ? 1 : 0;
+    compile_only = opts->compile_only != 0;
+    cache_dir = opts->cache_dir;
+  }
+  if (m->block % 32 || m->block > 1024) { delete m; return fail(ODL_EINVAL, "block_threads must be a multiple of 32, <= 1024"); }
+  int rc = compile_model(m, model_cuda_src, cache_dir);
+  if (rc) { delete m; return rc; }
+  if (compile_only) { *out = m; return 0; }
+  // ---- GPU side ----
+  auto bail = [&](int code) { odl_model_destroy(m); return code; };
+  if (device >= 0) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) return bail(fail(ODL_ENODEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e))); }
+  { cudaError_t e = cudaFree(0); if (e != cudaSuccess) return bail(fail(ODL_ENODEVICE, std::string("no usable CUDA device: ") + cudaGetErrorString(e))); }
+  if (cudaGetDevice(&m->device) != cudaSuccess) return bail(fail(ODL_ENODEVICE, "cudaGetDevice failed"));
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, m->device) != cudaSuccess) return bail(fail(ODL_ECUDA, "cudaGetDeviceProperties failed"));
+  if (prop.major != 10) return bail(fail(ODL_ENODEVICE, std::string("device '") + prop.name + "' is not sm_100 (Blackwell B200); this library has no other code path"));
+  m->sm_count = prop.multiProcessorCount;
+  if ((rc = load_driver())) return bail(rc);
+  { CUresult r = g_drv.ModuleLoadData(&m->mod, m->cubin.data()); if (r != CUDA_SUCCESS) return bail(fail(ODL_ECUDA, "cuModuleLoadData: " + cu_err(r))); }
+  struct { const char* name; CUfunction* fn; bool required; } ks[] = {
+      {"odl_sweep_kernel", &m->k_sweep, true}, {"odl_traj_kernel", &m->k_traj, true}, {"odl_mcmc_kernel", &m->k_mcmc, true},
+      {"odl_sweep_ros23_kernel", &m->k_sweep_ros, false}, {"odl_mcmc_ros23_kernel", &m->k_mcmc_ros, false}};
+  for (auto& k : ks) {
+    CUresult r = g_drv.ModuleGetFunction(k.fn, m->mod, k.name);
+    if (r != CUDA_SUCCESS) {
+      *k.fn = nullptr;
+      if (k.required) return bail(fail(ODL_ECUDA, std::string("cuModuleGetFunction(") + k.name + "): " + cu_err(r)));
+    }
+  }
+  if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
+    return bail(fail(ODL_ECUDA, "cudaEventCreate failed"));
+  if ((rc = m->counter.ensure(256))) return bail(rc);
+  m->on_gpu = true;
+  *out = m;
+  return 0;
+}
+
+extern "C" int odl_model_destroy(odl_model* m) {
+  if (!m) return 0;
+  if (m->on_gpu || m->mod) {
+    cudaSetDevice(m->device);
+    if (m->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(m->mod);
+  }
+  m->data.buf.release(); m->grid.buf.release(); m->counter.release();
+  for (auto& s : m->scratch) s.release();
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  delete m;
+  return 0;
+}
+
+extern "C" const char* odl_model_build_log(const odl_model* m) { return m ? m->log.c_str() : ""; }
+
+static CUfunction kernel_by_name(const odl_model* m, const char* k) {
+  if (!k) return nullptr;
+  if (!strcmp(k, "sweep")) return m->k_sweep;
+  if (!strcmp(k, "mcmc")) return m->k_mcmc;
+  if (!strcmp(k, "traj")) return m->k_traj;
+  if (!strcmp(k, "sweep_ros23")) return m->k_sweep_ros;
+  if (!strcmp(k, "mcmc_ros23")) return m->k_mcmc_ros;
+  return nullptr;
+}
+
+static size_t smem_bytes(const OdlData& d, int block) {
+  size_t doubles = (size_t)d.n_slot + 3 * (size_t)d.n_obs + ((size_t)d.n_obs + 1) / 2 + (size_t)block * d.stage_stride;
+  return doubles * sizeof(double);
+}
+
+extern "C" int odl_model_kernel_info(const odl_model* m, const char* kernel, int* regs, int* local_bytes,
+                                     int* max_blocks_per_sm) {
+  if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_model_kernel_info: model is not loaded on a GPU");
+  CUfunction f = kernel_by_name(m, kernel);
+  if (!f) return fail(ODL_EINVAL, "odl_model_kernel_info: unknown kernel");
+  int r = 0, l = 0, b = 0;
+  ODL_CU(g_drv.FuncGetAttribute(&r, CU_FUNC_ATTRIBUTE_NUM_REGS, f));
+  ODL_CU(g_drv.FuncGetAttribute(&l, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f));
+  size_t sm = m->data.set ? smem_bytes(m->data.d, m->block) : 0;
+  g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max<size_t>(sm, 1024));
+  ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&b, f, m->block, sm));
+  if (regs) *regs = r;
+  if (local_bytes) *local_bytes = l;
+  if (max_blocks_per_sm) *max_blocks_per_sm = b;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// data tables
+// ---------------------------------------------------------------------------------------------
+static int upload_tables(odl_model* m, Tables& T, int n_slot, const double* slot_time, int n_obs, const int* obs_slot,
+                         const int* obs_col, const double* ln_obs, const double* log_sigma, double sstot,
+                         const double* y0, const int* y0_from_param, double t0) {
+  if (!m->on_gpu) return fail(ODL_ENODEVICE, "model was created compile_only / without a GPU");
+  if (n_slot < 1 || !slot_time) return fail(ODL_EINVAL, "need at least one output time");
+  for (int i = 1; i < n_slot; ++i)
+    if (!(slot_time[i] > slot_time[i - 1])) return fail(ODL_EINVAL, "output times must be strictly ascending");
+  if (!(slot_time[0] >= t0)) return fail(ODL_EINVAL, "first output time precedes t0");
+  ODL_CUDA(cudaSetDevice(m->device));
+  const int N = m->n_state;
+  // layout: slot_t[K] lnO[n_obs] denom[n_obs] lin[n_obs] y0[N] | src[n_obs] y0p[N]
+  size_t nd = (size_t)n_slot + 3 * (size_t)n_obs + N;
+  size_t ni = (size_t)n_obs + N;
+  std::vector<double> hd(nd);
+  std::vector<int> hi(ni);
+  double* slot = hd.data();
+  double* lnO = slot + n_slot;
+  double* den = lnO + n_obs;
+  double* lin = den + n_obs;
+  double* hy0 = lin + n_obs;
+  int* src = hi.data();
+  int* y0p = src + n_obs;
+  std::copy(slot_time, slot_time + n_slot, slot);
+  for (int o = 0; o < n_obs; ++o) {
+    if (obs_slot[o] < 0 || obs_slot[o] >= n_slot || obs_col[o] < 0 || obs_col[o] >= m->n_out)
+      return fail(ODL_EINVAL, "observation row refers to a slot/column out of range");
+    lnO[o] = ln_obs[o];
+    const double s2 = log_sigma[o] * log_sigma[o];     // S**2
+    den[o] = 2.0 * s2;                                 // 2*(S**2)     (stats.py:41)
+    lin[o] = std::exp(ln_obs[o]);                      // Framework.py:700
+    src[o] = obs_slot[o] * m->n_out + obs_col[o];
+  }
+  for (int i = 0; i < N; ++i) {
+    hy0[i] = y0 ? y0[i] : 0.0;
+    y0p[i] = y0_from_param ? y0_from_param[i] : -1;
+    if (y0p[i] >= m->n_param) return fail(ODL_EINVAL, "y0_from_param index out of range");
+  }
+  int rc = T.buf.ensure(nd * sizeof(double) + ni * sizeof(int));
+  if (rc) return rc;
+  char* base = static_cast<char*>(T.buf.p);
+  ODL_CUDA(cudaMemcpy(base, hd.data(), nd * sizeof(double), cudaMemcpyHostToDevice));
+  ODL_CUDA(cudaMemcpy(base + nd * sizeof(double), hi.data(), ni * sizeof(int), cudaMemcpyHostToDevice));
+  double* dd = reinterpret_cast<double*>(base);
+  int* di = reinterpret_cast<int*>(base + nd * sizeof(double));
+  OdlData& d = T.d;
+  d.slot_t = dd; d.obs_lnO = dd + n_slot; d.obs_denom = d.obs_lnO + n_obs; d.obs_lin = d.obs_denom + n_obs;
+  d.y0 = d.obs_lin + n_obs;
+  d.obs_src = di; d.y0_from_param = di + n_obs;
+  d.n_slot = n_slot; d.n_obs = n_obs;
+  d.stage_stride = (n_slot * m->n_out) | 1;
+  d.pad_ = 0; d.t0 = t0; d.sstot = sstot;
+  T.set = true;
+  return 0;
+}
+
+extern "C" int odl_model_set_data(odl_model* m, int n_slot, const double* slot_time, int n_obs, const int* obs_slot,
+                                  const int* obs_col, const double* ln_obs, const double* log_sigma, double sstot,
+                                  const double* y0, const int* y0_from_param, double t0) {
+  if (!m) return fail(ODL_EINVAL, "null model");
+  if (n_obs < 1 || !obs_slot || !obs_col || !ln_obs || !log_sigma) return fail(ODL_EINVAL, "need observation rows");
+  return upload_tables(m, m->data, n_slot, slot_time, n_obs, obs_slot, obs_col, ln_obs, log_sigma, sstot, y0,
+                       y0_from_param, t0);
+}
+
+extern "C" int odl_model_set_grid(odl_model* m, int n_t, const double* times, const double* y0,
+                                  const int* y0_from_param) {
+  if (!m) return fail(ODL_EINVAL, "null model");
+  return upload_tables(m, m->grid, n_t, times, 0, nullptr, nullptr, nullptr, nullptr, 1.0, y0, y0_from_param,
+                       times ? times[0] : 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+static void fill_opts(OdlOpts& o, const odl_solver_opts* so) {
+  o.rtol = so && so->rtol > 0 ? so->rtol : 1.49012e-8;
+  o.atol = so && so->atol > 0 ? so->atol : 1.49012e-8;
+  o.h0 = so ? so->h0 : 0.0;
+  o.hmax = so ? so->hmax : 0.0;
+  o.max_steps = so && so->max_steps > 0 ? so->max_steps : 500000;
+  o.stiff_check = so ? so->stiff_check : 0;
+  o.reserved0 = o.reserved1 = 0;
+}
+
+static int launch(odl_model* m, CUfunction f, unsigned grid, unsigned block, size_t smem, cudaStream_t s, void** params) {
+  if (smem > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+  ODL_CU(g_drv.LaunchKernel(f, grid, 1, 1, block, 1, 1, (unsigned)smem, (CUstream)s, params, nullptr));
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+// stage a host array on the device (in) or reserve room for a result (out)
+struct Staging {
+  odl_model* m; cudaStream_t s; int next = 0; int mem;
+  struct Out { void* host; void* dev; size_t bytes; };
+  std::vector<Out> outs;
+  template <class T> int in(const T* host, size_t count, const T** dev) {
+    if (!host) { *dev = nullptr; return 0; }
+    if (mem == ODL_MEM_DEVICE) { *dev = host; return 0; }
+    DevBuf& b = m->scratch[next++];
+    int rc = b.ensure(count * sizeof(T)); if (rc) return rc;
+    ODL_CUDA(cudaMemcpyAsync(b.p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    *dev = static_cast<const T*>(b.p);
+    return 0;
+  }
+  template <class T> int inout(T* host, size_t count, T** dev, bool copy_in) {
+    if (!host) { *dev = nullptr; return 0; }
+    if (mem == ODL_MEM_DEVICE) { *dev = host; return 0; }
+    DevBuf& b = m->scratch[next++];
+    int rc = b.ensure(count * sizeof(T)); if (rc) return rc;
+    if (copy_in) ODL_CUDA(cudaMemcpyAsync(b.p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    *dev = static_cast<T*>(b.p);
+    outs.push_back({host, b.p, count * sizeof(T)});
+    return 0;
+  }
+  int finish() {
+    if (mem == ODL_MEM_DEVICE) return 0;
+    for (auto& o : outs) ODL_CUDA(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, s));
+    ODL_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  }
+};
+
+extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, const double* theta, int mem,
+                         double* chi, double* r2, int* status, int* nsteps, double* pred_or_null, void* stream) {
+  if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_sweep: model is not loaded on a GPU (no CPU fallback exists)");
+  if (!m->data.set) return fail(ODL_EINVAL, "odl_sweep: call odl_model_set_data first");
+  if (n < 0 || (n > 0 && (!theta || !chi || !r2 || !status || !nsteps))) return fail(ODL_EINVAL, "odl_sweep: null buffer");
+  if (n == 0) return 0;
+  const int solver = so ? so->solver : ODL_SOLVER_DOPRI5;
+  if (solver != ODL_SOLVER_DOPRI5 && !m->k_sweep_ros) return fail(ODL_EINVAL, "odl_sweep: ROS23 kernels are not in this build");
+  ODL_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  Staging st{m, s, 0, mem};
+  OdlSweepArgs A{};
+  int rc;
+  if ((rc = st.in(theta, (size_t)n * m->n_param, &A.theta))) return rc;
+  if ((rc = st.inout(chi, (size_t)n, &A.chi, false))) return rc;
+  if ((rc = st.inout(r2, (size_t)n, &A.r2, false))) return rc;
+  if ((rc = st.inout(status, (size_t)n, &A.status, false))) return rc;
+  if ((rc = st.inout(nsteps, (size_t)n, &A.nsteps, false))) return rc;
+  if ((rc = st.inout(pred_or_null, (size_t)n * m->data.d.n_obs, &A.pred, false))) return rc;
+  A.n = n; A.index = nullptr; A.index_count = nullptr;
+  A.counter = static_cast<unsigned long long*>(m->counter.p);
+  int* stiff_count = reinterpret_cast<int*>(static_cast<char*>(m->counter.p) + 64);
+  unsigned long long* counter2 = reinterpret_cast<unsigned long long*>(static_cast<char*>(m->counter.p) + 128);
+  A.stiff_list = nullptr; A.stiff_count = stiff_count;
+  OdlOpts O; fill_opts(O, so);
+  const bool autosw = (solver == ODL_SOLVER_AUTO);
+  if (autosw) {
+    O.stiff_check = 1;
+    DevBuf& b = m->scratch[st.next++];
+    if ((rc = b.ensure((size_t)n * sizeof(int)))) return rc;
+    A.stiff_list = static_cast<int*>(b.p);
+  }
+  ODL_CUDA(cudaMemsetAsync(m->counter.p, 0, 256, s));
+  OdlData D = m->data.d;
+  const size_t smem = smem_bytes(D, m->block);
+  CUfunction f = (solver == ODL_SOLVER_ROS23) ? m->k_sweep_ros : m->k_sweep;
+  if (smem > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+  int per_sm = 0;
+  ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, m->block, smem));
+  if (per_sm < 1) return fail(ODL_ECUDA, "sweep kernel does not fit on an SM (shared memory / registers)");
+  long long want = (n + m->block - 1) / m->block;
+  unsigned grid = (unsigned)std::min<long long>(want, (long long)per_sm * m->sm_count);
+  ODL_CUDA(cudaEventRecord(m->ev0, s));
+  void* params[] = {&D, &O, &A};
+  if ((rc = launch(m, f, grid, m->block, smem, s, params))) return rc;
+  if (autosw) {
+    // second pass: the systems DOPRI5 flagged as stiff, read from the device-side list (no host sync)
+    OdlSweepArgs B = A;
+    B.index = A.stiff_list; B.index_count = stiff_count; B.counter = counter2;
+    B.stiff_list = nullptr; B.stiff_count = stiff_count;
+    OdlOpts O2 = O; O2.stiff_check = 0;
+    CUfunction f2 = m->k_sweep_ros;
+    int per_sm2 = 0;
+    if (smem > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(f2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+    ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, f2, m->block, smem));
+    if (per_sm2 < 1) return fail(ODL_ECUDA, "ROS23 sweep kernel does not fit on an SM");
+    unsigned grid2 = (unsigned)std::min<long long>(want, (long long)per_sm2 * m->sm_count);
+    void* params2[] = {&D, &O2, &B};
+    if ((rc = launch(m, f2, grid2, m->block, smem, s, params2))) return rc;
+  }
+  ODL_CUDA(cudaEventRecord(m->ev1, s));
+  m->timed = true;
+  return st.finish();
+}
+
+extern "C" int odl_trajectory(odl_model* m, const odl_solver_opts* so, long long n, const double* theta,
+                              const double* y0_or_null, int mem, double* traj, int* status, int* nsteps, void* stream) {
+  if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_trajectory: model is not loaded on a GPU (no CPU fallback exists)");
+  if (!m->grid.set) return fail(ODL_EINVAL, "odl_trajectory: call odl_model_set_grid first");
+  if (n < 0 || (n > 0 && (!theta || !traj || !status || !nsteps))) return fail(ODL_EINVAL, "odl_trajectory: null buffer");
+  if (n == 0) return 0;
+  ODL_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  Staging st{m, s, 0, mem};
+  OdlTrajArgs A{};
+  int rc;
+  OdlData D = m->grid.d;
+  if ((rc = st.in(theta, (size_t)n * m->n_param, &A.theta))) return rc;
+  if ((rc = st.in(y0_or_null, (size_t)n * m->n_state, &A.y0))) return rc;
+  if ((rc = st.inout(traj, (size_t)n * D.n_slot * m->n_state, &A.traj, false))) return rc;
+  if ((rc = st.inout(status, (size_t)n, &A.status, false))) return rc;
+  if ((rc = st.inout(nsteps, (size_t)n, &A.nsteps, false))) return rc;
+  A.n = n; A.counter = nullptr;
+  OdlOpts O; fill_opts(O, so);
+  const size_t smem = (size_t)D.n_slot * sizeof(double);
+  const unsigned block = 32;
+  unsigned grid = (unsigned)((n + block - 1) / block);
+  ODL_CUDA(cudaEventRecord(m->ev0, s));
+  void* params[] = {&D, &O, &A};
+  if ((rc = launch(m, m->k_traj, grid, block, smem, s, params))) return rc;
+  ODL_CUDA(cudaEventRecord(m->ev1, s));
+  m->timed = true;
+  return st.finish();
+}
+
+extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_opts* mo, const odl_mcmc_io* io, int mem,
+                        void* stream) {
+  if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_mcmc: model is not loaded on a GPU (no CPU fallback exists)");
+  if (!m->data.set) return fail(ODL_EINVAL, "odl_mcmc: call odl_model_set_data first");
+  if (!mo || !io || !io->theta || !io->chain_state) return fail(ODL_EINVAL, "odl_mcmc: null argument");
+  if (mo->n_chain < 1 || mo->nits < 2) return fail(ODL_EINVAL, "odl_mcmc: need n_chain >= 1 and nits >= 2");
+  if (mo->n_walk < 0 || mo->n_walk > m->n_param || (mo->n_walk > 0 && !mo->walk)) return fail(ODL_EINVAL, "odl_mcmc: bad walk list");
+  const int solver = so ? so->solver : ODL_SOLVER_DOPRI5;
+  if (solver != ODL_SOLVER_DOPRI5 && !m->k_mcmc_ros) return fail(ODL_EINVAL, "odl_mcmc: ROS23 kernels are not in this build");
+  const int P = m->n_param, C = mo->n_chain, n_iter = mo->nits - 1;
+  int it_begin = mo->it_begin, it_end = mo->it_end;
+  if (it_begin == 0 && it_end == 0) { it_begin = 1; it_end = mo->nits; }
+  if (it_begin < 1 || it_end > mo->nits || it_begin > it_end) return fail(ODL_EINVAL, "odl_mcmc: bad iteration range");
+  const int n_keep = std::max(0, n_iter - mo->burnin);
+  const int stride = mo->row_stride > 0 ? mo->row_stride : P + 5;
+  if (stride < P + 5) return fail(ODL_EINVAL, "odl_mcmc: row_stride < n_param+5");
+  if (mo->rng_mode == ODL_RNG_HOST_STREAMS && (!io->z || !io->u)) return fail(ODL_EINVAL, "odl_mcmc: host streams need z and u");
+  if (mo->rng_mode == ODL_RNG_FORCED && (!io->forced || !io->u)) return fail(ODL_EINVAL, "odl_mcmc: forced mode needs proposals and u");
+  ODL_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  Staging st{m, s, 0, mem};
+  OdlMcmcArgs A{};
+  int rc;
+  if ((rc = st.inout(io->theta, (size_t)C * P, &A.theta_cur, true))) return rc;
+  if ((rc = st.inout(io->chain_state, (size_t)C * 4, &A.chain_state, true))) return rc;
+  if ((rc = st.inout(io->samples, (size_t)C * n_keep * stride, &A.samples, it_begin > 1))) return rc;
+  if ((rc = st.inout(io->summaries, (size_t)C * (1 + 2 * P), &A.summaries, true))) return rc;
+  if ((rc = st.in(io->z, (size_t)C * n_iter * mo->n_walk, &A.z))) return rc;
+  if ((rc = st.in(io->u, (size_t)C * n_iter, &A.u))) return rc;
+  if ((rc = st.in(io->forced, (size_t)C * n_iter * P, &A.forced))) return rc;
+  if ((rc = st.inout(io->trace_chinew, (size_t)C * n_iter, &A.trace_chinew, it_begin > 1))) return rc;
+  if ((rc = st.inout(io->trace_accept, (size_t)C * n_iter, &A.trace_accept, it_begin > 1))) return rc;
+  if ((rc = st.inout(io->fail_count, (size_t)C, &A.fail_count, true))) return rc;
+  if ((rc = st.inout(io->step_count, (size_t)C, &A.step_count, true))) return rc;
+  A.n_chain = C; A.chain_offset = mo->chain_offset; A.it_begin = it_begin; A.it_end = it_end;
+  A.burnin = mo->burnin; A.n_keep = n_keep; A.row_stride = stride; A.rng_mode = mo->rng_mode;
+  A.n_walk = mo->n_walk; A.pnum = mo->pnum;
+  for (int j = 0; j < ODL_MAX_WALK; ++j) A.walk[j] = -1;
+  for (int j = 0; j < mo->n_walk; ++j) {
+    if (mo->walk[j] < 0 || mo->walk[j] >= P) return fail(ODL_EINVAL, "odl_mcmc: walk index out of range");
+    A.walk[j] = mo->walk[j];
+  }
+  A.step_sd = mo->step_sd > 0 ? mo->step_sd : 0.05;
+  A.seed = mo->seed; A.n_iter_total = n_iter; A.pad_ = 0;
+  OdlOpts O; fill_opts(O, so);
+  OdlData D = m->data.d;
+  // few chains: spread them over the SMs with one warp per CTA; many chains: full CTAs
+  unsigned block = (unsigned)m->block;
+  while (block > 32 && (long long)C < (long long)m->sm_count * block * 2) block /= 2;
+  const size_t smem = smem_bytes(D, (int)block);
+  unsigned grid = (unsigned)((C + block - 1) / block);
+  CUfunction f = (solver == ODL_SOLVER_DOPRI5) ? m->k_mcmc : m->k_mcmc_ros;
+  ODL_CUDA(cudaEventRecord(m->ev0, s));
+  void* params[] = {&D, &O, &A};
+  if ((rc = launch(m, f, grid, block, smem, s, params))) return rc;
+  ODL_CUDA(cudaEventRecord(m->ev1, s));
+  m->timed = true;
+  return st.finish();
+}
+
+extern "C" int odl_model_last_kernel_ms(odl_model* m, float* ms) {
+  if (!m || !ms) return fail(ODL_EINVAL, "null argument");
+  if (!m->on_gpu || !m->timed) return fail(ODL_EINVAL, "no kernel has been launched on this model yet");
+  ODL_CUDA(cudaEventSynchronize(m->ev1));
+  ODL_CUDA(cudaEventElapsedTime(ms, m->ev0, m->ev1));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 roofline denominator: 8 independent DFMA chains per thread, no memory traffic
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) odl_dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true; keeps the chains alive
+}
+
+extern "C" int odl_fp64_peak(int device, int repeats, double* tflops, float* ms_per_launch) {
+  if (!tflops) return fail(ODL_EINVAL, "null argument");
+  if (device >= 0) ODL_CUDA(cudaSetDevice(device));
+  ODL_CUDA(cudaFree(0));
+  int dev = 0;
+  ODL_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  ODL_CUDA(cudaGetDeviceProperties(&prop, dev));
+  const int block = 256, per_sm = 8, iters = 4096;
+  const int grid = prop.multiProcessorCount * per_sm;
+  double* d = nullptr;
+  ODL_CUDA(cudaMalloc(&d, (size_t)grid * block * sizeof(double)));
+  cudaEvent_t e0, e1;
+  ODL_CUDA(cudaEventCreate(&e0));
+  ODL_CUDA(cudaEventCreate(&e1));
+  if (repeats < 1) repeats = 5;
+  for (int w = 0; w < 2; ++w) odl_dfma_peak_kernel<<<grid, block>>>(d, iters, 0.999999, 1e-9);
+  float best = 1e30f;
+  for (int r = 0; r < repeats; ++r) {
+    ODL_CUDA(cudaEventRecord(e0));
+    odl_dfma_peak_kernel<<<grid, block>>>(d, iters, 0.999999, 1e-9);
+    g_launches.fetch_add(1);
+    ODL_CUDA(cudaEventRecord(e1));
+    ODL_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    ODL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+  }
+  ODL_CUDA(cudaGetLastError());
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  const double flops = 2.0 * 64.0 * (double)iters * (double)grid * block;   // 8 chains x 8 unroll x FMA
+  *tflops = flops / (best * 1e-3) / 1e12;
+  if (ms_per_launch) *ms_per_launch = best;
+  return 0;
+}

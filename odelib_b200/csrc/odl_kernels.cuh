@@ -1,0 +1,654 @@
+// odl_kernels.cuh -- device code of the ODElib hot path for sm_100a (B200).
+//
+// Compiled per model by NVRTC at run time (odl_capi.cu prepends the traced model) and by nvcc at
+// build time for the demo models (register/spill checks).  The including translation unit must
+// define, before this file:
+//     ODL_N, ODL_P, ODL_NOUT            state / parameter / observed-column counts
+//     odl_rhs, odl_jac, odl_dfdt, odl_observe   (emitted by odelib_b200/tracer.py)
+// Optional: ODL_BLOCK (threads per CTA), ODL_MINBLOCKS, ODL_DENSE (1 = dense output, 0 = land on slots).
+//
+// What replaces what (reference file:line -> here):
+//   Framework.py:656   odeint(func, y0, times, args)       -> Dopri5 stepper, one system per thread
+//   Framework.py:659-664, :677-682  summation + obs pick   -> odl_observe on the dense output at the
+//                                                             19 distinct observation grid times
+//   Framework.py:685-697 + stats.py:41   masked chi        -> odl_score (warp-cooperative)
+//   stats.py:49-56  R^2                                    -> odl_score
+//   Framework.py:41-48   _Fit_worker loop                  -> odl_sweep_kernel
+//   Samplers.py:53-174   MetropolisHastings                -> odl_mcmc_kernel (one chain per thread)
+//
+// Execution model: every thread owns one ODE system at a time and keeps its state, the 7 stage
+// derivatives and the parameter vector in registers.  The main loop is a flat state machine:
+//     [finished lanes: warp-cooperative chi/R^2, write results, fetch next work, re-init]
+//     [one adaptive step attempt for all lanes that have work]
+//     [lanes whose accepted step crossed observation times: dense output -> shared staging]
+// so a lane that finishes refills immediately (sweep: next parameter set from a global counter;
+// MCMC: accept/reject and propose the chain's next point) while its warp mates keep stepping; a warp
+// leaves when a vote says no lane has work.  Trajectories never reach HBM: predictions at the
+// observation slots are staged per thread in shared memory and consumed by the fused scorer.
+
+#ifndef ODL_BLOCK
+#define ODL_BLOCK 128
+#endif
+#ifndef ODL_MINBLOCKS
+#define ODL_MINBLOCKS 4
+#endif
+#ifndef ODL_DENSE
+#define ODL_DENSE 1
+#endif
+
+#define ODL_FULL 0xffffffffu
+#define ODL_DBL_MIN 2.2250738585072014e-308
+#define ODL_DBL_MAX 1.7976931348623157e308
+
+#include "odl_abi.h"
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool odl_finite(double x) { return fabs(x) <= ODL_DBL_MAX; }
+
+__device__ __forceinline__ double odl_shfl_xor(double v, int m) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(ODL_FULL, lo, m);
+  hi = __shfl_xor_sync(ODL_FULL, hi, m);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double odl_warp_sum(double v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += odl_shfl_xor(v, m);
+  return v;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11) -- counter-based, one independent stream per (chain, iteration)
+struct OdlPhilox { unsigned int x, y, z, w; };
+__device__ __forceinline__ OdlPhilox odl_philox(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3,
+                                                 unsigned int k0, unsigned int k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  OdlPhilox o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+  return o;
+}
+// 53-bit uniform in [0,1) from two words; (0,1] variant for the logarithm of Box-Muller
+__device__ __forceinline__ double odl_u53(unsigned int a, unsigned int b) {
+  const unsigned long long v = (((unsigned long long)a) << 21) ^ ((unsigned long long)b >> 11);
+  return (double)(v & ((1ull << 53) - 1)) * 1.1102230246251565e-16;  // 2^-53
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory view of the data tables + per-thread staging
+// ------------------------------------------------------------------------------------------------
+struct OdlShared {
+  double* slot_t; double* lnO; double* denom; double* lin; int* src; double* stage;
+};
+__device__ __forceinline__ OdlShared odl_carve(double* base, const OdlData& D) {
+  OdlShared S;
+  S.slot_t = base;
+  S.lnO = S.slot_t + D.n_slot;
+  S.denom = S.lnO + D.n_obs;
+  S.lin = S.denom + D.n_obs;
+  S.src = (int*)(S.lin + D.n_obs);
+  S.stage = S.lin + D.n_obs + (D.n_obs + 1) / 2;
+  return S;
+}
+__device__ __forceinline__ void odl_load_tables(const OdlShared& S, const OdlData& D) {
+  for (int i = threadIdx.x; i < D.n_slot; i += blockDim.x) S.slot_t[i] = D.slot_t[i];
+  for (int i = threadIdx.x; i < D.n_obs; i += blockDim.x) {
+    S.lnO[i] = D.obs_lnO[i]; S.denom[i] = D.obs_denom[i]; S.lin[i] = D.obs_lin[i]; S.src[i] = D.obs_src[i];
+  }
+  __syncthreads();
+}
+
+// Warp-cooperative chi + R^2 of the system staged by lane `leader` (stats.py:41, :49-56).
+// All 32 lanes must call.  Every lane returns the reduced values.
+__device__ __forceinline__ void odl_score(const OdlShared& S, const OdlData& D, const double* stage_leader, int lane,
+                                          double* pred_out, double& chi, double& ssres, int& nvalid) {
+  double c = 0.0, s = 0.0;
+  int k = 0;
+  for (int o = lane; o < D.n_obs; o += 32) {
+    const double pred = stage_leader[S.src[o]];
+    if (pred_out) pred_out[o] = pred;
+    const double d = __dadd_rn(S.lnO[o], -log(pred));          // masked_invalid(O) - C
+    const double dd = __dmul_rn(d, d);                          // (...)**2   : masked when not finite
+    const double den = S.denom[o];
+    const double term = dd / den;                               // / (2*S**2): masked on domain or non-finite
+    const bool ok = odl_finite(dd) && odl_finite(term) && !(fabs(dd) * ODL_DBL_MIN >= fabs(den));
+    if (ok) { c += term; ++k; }
+    const double r = __dadd_rn(pred, -S.lin[o]);
+    const double rr = __dmul_rn(r, r);
+    if (rr == rr) s += rr;                                      // np.nansum
+  }
+  chi = odl_warp_sum(c);
+  ssres = odl_warp_sum(s);
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) k += __shfl_xor_sync(ODL_FULL, k, m);
+  nvalid = k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dormand-Prince 5(4), coefficients of Hairer/Norsett/Wanner (dopri5.f); PI step controller.
+// ------------------------------------------------------------------------------------------------
+struct OdlStepper {
+  double y[ODL_N];       // state at t
+  double k1[ODL_N];      // f(t, y)  (FSAL)
+  double t, h, tend;
+  float facold;
+  int nsteps;            // attempted steps
+  int slot;              // next observation slot to produce
+  int status;
+  int iasti, nonsti;     // stiffness detection counters
+  bool last_rejected;
+};
+
+__device__ __forceinline__ float odl_err_ratio(double e, double sk) {
+  // |e|/sk in fp32: only the step controller sees it (3 digits are plenty); SFU reciprocal instead
+  // of a 20-instruction fp64 division.  sk >= atol > 0.
+  return (float)e * __frcp_rn((float)sk);
+}
+
+__device__ __forceinline__ void odl_init_system(OdlStepper& st, const double (&p)[ODL_P], const OdlData& D,
+                                                const OdlOpts& O, const double* y0_override) {
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) {
+    const int src = D.y0_from_param[i];
+    double v = y0_override ? y0_override[i] : D.y0[i];
+#pragma unroll
+    for (int q = 0; q < ODL_P; ++q) if (src == q) v = p[q];     // '<state>0' parameters (Samplers.py:110-114)
+    st.y[i] = v;
+  }
+  st.t = D.t0;
+  st.tend = D.slot_t[D.n_slot - 1];
+  st.nsteps = 0; st.slot = 0; st.status = ODL_OK; st.iasti = 0; st.nonsti = 0;
+  st.facold = 1e-4f; st.last_rejected = false;
+  odl_rhs(st.y, st.t, p, st.k1);
+  const double span = st.tend - st.t;
+  const double hmax = (O.hmax > 0.0) ? O.hmax : span;
+  double h = O.h0;
+  if (!(h > 0.0)) {
+    // Hairer's hinit: h ~ 0.01 |y|/|f|, refined with a difference quotient of f along an Euler step.
+    // A heuristic -> fp32 norms (SFU reciprocal / pow), guarded below against overflow.
+    float dnf = 0.f, dny = 0.f;
+    float rsk[ODL_N];
+#pragma unroll
+    for (int i = 0; i < ODL_N; ++i) {
+      rsk[i] = __frcp_rn((float)(O.atol + O.rtol * fabs(st.y[i])));
+      const float a = (float)st.k1[i] * rsk[i], b = (float)st.y[i] * rsk[i];
+      dnf += a * a; dny += b * b;
+    }
+    float hf = (dnf <= 1e-10f || dny <= 1e-10f) ? 1e-6f : 0.01f * sqrtf(dny / dnf);
+    h = fmin((double)hf, hmax);
+    double y1[ODL_N], f1[ODL_N];
+#pragma unroll
+    for (int i = 0; i < ODL_N; ++i) y1[i] = st.y[i] + h * st.k1[i];
+    odl_rhs(y1, st.t + h, p, f1);
+    float der2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < ODL_N; ++i) {
+      const float a = (float)(f1[i] - st.k1[i]) * rsk[i];
+      der2 += a * a;
+    }
+    der2 = sqrtf(der2) / (float)h;
+    const float der12 = fmaxf(der2, sqrtf(dnf));
+    const float h1 = (der12 <= 1e-15f) ? fmaxf(1e-6f, (float)h * 1e-3f) : __powf(0.01f / der12, 0.2f);
+    h = fmin(fmin(100.0 * h, (double)h1), hmax);
+  }
+  if (!(h > 0.0) || !odl_finite(h)) h = 1e-6 * (span > 0.0 ? span : 1.0);
+  st.h = h;
+}
+
+// dense output of the last accepted step [t0, t0+h] at time ts (Hairer's contd5)
+#define ODL_D1 (-12715105075.0 / 11282082432.0)
+#define ODL_D3 (87487479700.0 / 32700410799.0)
+#define ODL_D4 (-10690763975.0 / 1880347072.0)
+#define ODL_D5 (701980252875.0 / 199316789632.0)
+#define ODL_D6 (-1453857185.0 / 822651844.0)
+#define ODL_D7 (69997945.0 / 29380423.0)
+
+// One step attempt.  On acceptance the lambda-like macro ODL_ON_SLOT is not used; instead the caller
+// passes a functor `sink(slot, yi)` that receives the interpolated state at every crossed slot.
+template <class Sink>
+__device__ __forceinline__ void odl_dopri5_attempt(OdlStepper& st, const double (&p)[ODL_P], const OdlShared& S,
+                                                   const OdlData& D, const OdlOpts& O, Sink& sink) {
+  const double t = st.t;
+  double h = st.h;
+  bool last = false;
+#if ODL_DENSE
+  if ((t + 1.01 * h - st.tend) > 0.0) { h = st.tend - t; last = true; }
+  const bool truncated = false;
+  const double h_untrunc = h;
+#else
+  // land exactly on the next observation slot instead of interpolating
+  const double ttarget = S.slot_t[st.slot];
+  bool truncated = false;
+  const double h_untrunc = h;
+  if ((t + 1.01 * h - ttarget) > 0.0) { h = ttarget - t; truncated = true; last = (st.slot == D.n_slot - 1); }
+#endif
+  ++st.nsteps;
+  double k2[ODL_N], k3[ODL_N], k4[ODL_N], k5[ODL_N], k6[ODL_N], k7[ODL_N], yt[ODL_N], yn[ODL_N];
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) yt[i] = st.y[i] + h * (0.2 * st.k1[i]);
+  odl_rhs(yt, t + 0.2 * h, p, k2);
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) yt[i] = st.y[i] + h * ((3.0 / 40.0) * st.k1[i] + (9.0 / 40.0) * k2[i]);
+  odl_rhs(yt, t + 0.3 * h, p, k3);
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i)
+    yt[i] = st.y[i] + h * ((44.0 / 45.0) * st.k1[i] + (-56.0 / 15.0) * k2[i] + (32.0 / 9.0) * k3[i]);
+  odl_rhs(yt, t + 0.8 * h, p, k4);
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i)
+    yt[i] = st.y[i] + h * ((19372.0 / 6561.0) * st.k1[i] + (-25360.0 / 2187.0) * k2[i] + (64448.0 / 6561.0) * k3[i] +
+                           (-212.0 / 729.0) * k4[i]);
+  odl_rhs(yt, t + (8.0 / 9.0) * h, p, k5);
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i)
+    yt[i] = st.y[i] + h * ((9017.0 / 3168.0) * st.k1[i] + (-355.0 / 33.0) * k2[i] + (46732.0 / 5247.0) * k3[i] +
+                           (49.0 / 176.0) * k4[i] + (-5103.0 / 18656.0) * k5[i]);
+  const double tph = t + h;
+  odl_rhs(yt, tph, p, k6);
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i)
+    yn[i] = st.y[i] + h * ((35.0 / 384.0) * st.k1[i] + (500.0 / 1113.0) * k3[i] + (125.0 / 192.0) * k4[i] +
+                           (-2187.0 / 6784.0) * k5[i] + (11.0 / 84.0) * k6[i]);
+  odl_rhs(yn, tph, p, k7);
+
+  // embedded error estimate, scaled RMS norm
+  float errsq = 0.f;
+  bool finite_all = true;
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) {
+    const double e = h * ((71.0 / 57600.0) * st.k1[i] + (-71.0 / 16695.0) * k3[i] + (71.0 / 1920.0) * k4[i] +
+                          (-17253.0 / 339200.0) * k5[i] + (22.0 / 525.0) * k6[i] + (-1.0 / 40.0) * k7[i]);
+    const double sk = O.atol + O.rtol * fmax(fabs(st.y[i]), fabs(yn[i]));
+    const float r = odl_err_ratio(e, sk);
+    errsq += r * r;
+    finite_all = finite_all && odl_finite(yn[i]);
+  }
+  const float err = sqrtf(errsq * (1.0f / ODL_N));
+  // PI controller (beta = 0.04): fac11 = err^(0.2 - 0.75 beta), SFU pow
+  const float fac11 = __powf(err, 0.2f - 0.04f * 0.75f);
+  if (err <= 1.0f && finite_all) {
+    // ---- accepted ----
+    float fac = fac11 / __powf(st.facold, 0.04f);
+    fac = fmaxf(0.1f, fminf(5.0f, fac * (1.0f / 0.9f)));      // h_new = h / fac, growth <= 10, shrink <= 5
+    double hnew = h / (double)fac;
+    if (!(err > 0.f)) hnew = h * 10.0;
+    st.facold = fmaxf(err, 1e-4f);
+    if (O.stiff_check && ((st.nsteps % 10) == 0 || st.iasti > 0)) {
+      // Hairer's test: h * |k7 - k6| / |ynew - y6| approximates h * |lambda_max|
+      double num = 0.0, den = 0.0;
+#pragma unroll
+      for (int i = 0; i < ODL_N; ++i) {
+        const double a = k7[i] - k6[i], b = yn[i] - yt[i];
+        num += a * a; den += b * b;
+      }
+      if (den > 0.0) {
+        const double hlamb = h * sqrt(num / den);
+        if (hlamb > 3.25) {
+          st.nonsti = 0;
+          if (++st.iasti == 15) st.status = ODL_STIFF;
+        } else if (++st.nonsti == 6) st.iasti = 0;
+      }
+    }
+#if ODL_DENSE
+    const double tnew = last ? st.tend : tph;
+#else
+    const double tnew = truncated ? ttarget : tph;
+#endif
+#if ODL_DENSE
+    if (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew) {
+      double rc2[ODL_N], rc3[ODL_N], rc4[ODL_N], rc5[ODL_N];
+#pragma unroll
+      for (int i = 0; i < ODL_N; ++i) {
+        rc2[i] = yn[i] - st.y[i];
+        rc3[i] = h * st.k1[i] - rc2[i];
+        rc4[i] = rc2[i] - h * k7[i] - rc3[i];
+        rc5[i] = h * (ODL_D1 * st.k1[i] + ODL_D3 * k3[i] + ODL_D4 * k4[i] + ODL_D5 * k5[i] + ODL_D6 * k6[i] +
+                      ODL_D7 * k7[i]);
+      }
+      do {
+        const double th = (S.slot_t[st.slot] - t) / h, th1 = 1.0 - th;
+        double yi[ODL_N];
+#pragma unroll
+        for (int i = 0; i < ODL_N; ++i)
+          yi[i] = st.y[i] + th * (rc2[i] + th1 * (rc3[i] + th * (rc4[i] + th1 * rc5[i])));
+        sink(st.slot, yi);
+        ++st.slot;
+      } while (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew);
+    }
+#else
+    if (truncated) {
+      // several slots may share a time only if the host deduplicated badly; loop is defensive
+      do { sink(st.slot, yn); ++st.slot; } while (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew);
+      hnew = fmax(hnew, h_untrunc);
+    }
+#endif
+#pragma unroll
+    for (int i = 0; i < ODL_N; ++i) { st.y[i] = yn[i]; st.k1[i] = k7[i]; }
+    st.t = tnew;
+    if (st.last_rejected) hnew = fmin(hnew, h);
+    st.last_rejected = false;
+    st.h = hnew;
+    (void)truncated; (void)h_untrunc;
+  } else {
+    // ---- rejected ----
+    double hnew;
+    if (err == err && finite_all && err < 3.0e38f) hnew = h / (double)fminf(5.0f, fac11 * (1.0f / 0.9f));
+    else hnew = 0.2 * h;                                        // NaN / overflow inside the step
+    st.last_rejected = true;
+    st.h = hnew;
+    if (!(fabs(hnew) > 4.0 * 2.220446049250313e-16 * fmax(fabs(t), fabs(st.tend)))) st.status = ODL_HUNDERFLOW;
+  }
+  if (st.nsteps >= O.max_steps && st.slot < D.n_slot && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
+}
+
+// slots at (or before) the start time take the initial state (odeint returns y0 at times[0])
+template <class Sink>
+__device__ __forceinline__ void odl_emit_initial_slots(OdlStepper& st, const OdlShared& S, const OdlData& D, Sink& sink) {
+  while (st.slot < D.n_slot && S.slot_t[st.slot] <= st.t) { sink(st.slot, st.y); ++st.slot; }
+}
+
+struct OdlStageSink {            // observation columns -> per-thread shared staging
+  double* stage;
+  __device__ __forceinline__ void operator()(int slot, const double (&yi)[ODL_N]) {
+    double out[ODL_NOUT];
+    odl_observe(yi, out);
+#pragma unroll
+    for (int c = 0; c < ODL_NOUT; ++c) stage[slot * ODL_NOUT + c] = out[c];
+  }
+};
+struct OdlTrajSink {             // raw states -> global trajectory
+  double* traj;
+  __device__ __forceinline__ void operator()(int slot, const double (&yi)[ODL_N]) {
+#pragma unroll
+    for (int i = 0; i < ODL_N; ++i) traj[(long long)slot * ODL_N + i] = yi[i];
+  }
+};
+
+// fetch `want` lanes' worth of indices from a global counter with one atomic per warp
+__device__ __forceinline__ long long odl_fetch(unsigned long long* counter, bool want, int lane) {
+  const unsigned m = __ballot_sync(ODL_FULL, want);
+  if (m == 0) return -1;
+  const int leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+  base = ((unsigned long long)__shfl_sync(ODL_FULL, (int)(base >> 32), leader) << 32) |
+         (unsigned int)__shfl_sync(ODL_FULL, (int)(base & 0xffffffffu), leader);
+  return (long long)(base + __popc(m & ((1u << lane) - 1)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward sweep: Framework.py:41-48 (_Fit_worker) for n parameter sets
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
+odl_sweep_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
+  extern __shared__ double odl_smem[];
+  const OdlShared S = odl_carve(odl_smem, D);
+  odl_load_tables(S, D);
+  const int lane = threadIdx.x & 31;
+  double* my_stage = S.stage + (size_t)threadIdx.x * D.stage_stride;
+  OdlStageSink sink; sink.stage = my_stage;
+  const long long n = A.index_count ? (long long)(*A.index_count) : A.n;
+
+  OdlStepper st;
+  double p[ODL_P];
+  long long sys = -1;            // slot in the work list
+  long long row = -1;            // row of theta / outputs
+  bool active = false, done = false;
+  st.status = ODL_OK; st.nsteps = 0; st.slot = 0;
+
+  // first fetch
+  bool want = true;
+  for (;;) {
+    // ---- (A) finished lanes: cooperative score, write-back ----
+    const bool fin = active && done;
+    unsigned m = __ballot_sync(ODL_FULL, fin);
+    while (m) {
+      const int L = __ffs(m) - 1;
+      m &= m - 1;
+      const long long rowL = ((long long)__shfl_sync(ODL_FULL, (int)(row >> 32), L) << 32) |
+                             (unsigned int)__shfl_sync(ODL_FULL, (int)(row & 0xffffffff), L);
+      const int statL = __shfl_sync(ODL_FULL, st.status, L);
+      double chi, ss; int nv;
+      double* pred_out = (A.pred && statL == ODL_OK) ? A.pred + rowL * D.n_obs : nullptr;
+      odl_score(S, D, S.stage + (size_t)((threadIdx.x & ~31) + L) * D.stage_stride, lane, pred_out, chi, ss, nv);
+      if (lane == L) {
+        int status = st.status;
+        double r2 = 1.0 - ss / D.sstot;
+        if (status != ODL_OK) { chi = __longlong_as_double(0x7ff8000000000000LL); r2 = chi; }
+        else if (nv == 0) { chi = __longlong_as_double(0x7ff8000000000000LL); status |= ODL_ALLMASKED; }
+        A.chi[row] = chi; A.r2[row] = r2; A.status[row] = status; A.nsteps[row] = st.nsteps;
+        if (st.status == ODL_STIFF && A.stiff_list) A.stiff_list[atomicAdd(A.stiff_count, 1)] = (int)row;
+      }
+    }
+    if (fin) { active = false; done = false; want = true; }
+    // ---- (B) refill ----
+    {
+      const long long got = odl_fetch(A.counter, want, lane);
+      if (want) {
+        want = false;
+        if (got >= 0 && got < n) {
+          sys = got;
+          row = A.index ? (long long)A.index[sys] : sys;
+#pragma unroll
+          for (int q = 0; q < ODL_P; ++q) p[q] = A.theta[row * ODL_P + q];
+          odl_init_system(st, p, D, O, nullptr);
+          odl_emit_initial_slots(st, S, D, sink);
+          active = true;
+          done = (st.slot >= D.n_slot);
+        }
+      }
+    }
+    if (!__any_sync(ODL_FULL, active)) break;
+    // ---- (C) one step attempt ----
+    if (active && !done) {
+      odl_dopri5_attempt(st, p, S, D, O, sink);
+      done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Full trajectories on the output grid (ModelFramework.integrate, Framework.py:622-683)
+// ------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
+odl_traj_kernel(const OdlData D, const OdlOpts O, const OdlTrajArgs A) {
+  extern __shared__ double odl_smem[];
+  OdlShared S;
+  S.slot_t = odl_smem; S.lnO = S.denom = S.lin = nullptr; S.src = nullptr; S.stage = nullptr;
+  for (int i = threadIdx.x; i < D.n_slot; i += blockDim.x) S.slot_t[i] = D.slot_t[i];
+  __syncthreads();
+  const long long sys = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sys >= A.n) return;
+  double p[ODL_P];
+#pragma unroll
+  for (int q = 0; q < ODL_P; ++q) p[q] = A.theta[sys * ODL_P + q];
+  OdlStepper st;
+  OdlTrajSink sink; sink.traj = A.traj + sys * (long long)D.n_slot * ODL_N;
+  odl_init_system(st, p, D, O, A.y0 ? A.y0 + sys * ODL_N : nullptr);
+  odl_emit_initial_slots(st, S, D, sink);
+  while (st.slot < D.n_slot && st.status == ODL_OK) odl_dopri5_attempt(st, p, S, D, O, sink);
+  if (st.status != ODL_OK) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int s = st.slot; s < D.n_slot; ++s)
+      for (int i = 0; i < ODL_N; ++i) sink.traj[(long long)s * ODL_N + i] = nan;
+  }
+  A.status[sys] = st.status; A.nsteps[sys] = st.nsteps;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Metropolis-Hastings: Samplers.py:53-174, one chain per thread, device resident
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void odl_propose(double (&p)[ODL_P], const OdlMcmcArgs& A, int chain_local, int it) {
+  // theta' = exp(log(theta_old) + N(0, step_sd))   for every walking parameter (Framework.py:119)
+  const double* cur = A.theta_cur + (size_t)chain_local * ODL_P;
+#pragma unroll
+  for (int q = 0; q < ODL_P; ++q) p[q] = cur[q];
+  const long long k = (long long)chain_local * A.n_iter_total + (it - 1);
+  if (A.rng_mode == 2) {
+#pragma unroll
+    for (int q = 0; q < ODL_P; ++q) p[q] = A.forced[k * ODL_P + q];
+    return;
+  }
+  const unsigned long long gchain = (unsigned long long)(A.chain_offset + chain_local);
+  for (int j = 0; j < A.n_walk; j += 2) {
+    double z0, z1 = 0.0;
+    if (A.rng_mode == 1) {
+      z0 = A.z[k * A.n_walk + j];
+      if (j + 1 < A.n_walk) z1 = A.z[k * A.n_walk + j + 1];
+    } else {
+      const OdlPhilox r = odl_philox((unsigned int)it, (unsigned int)(1 + (j >> 1)), (unsigned int)gchain,
+                                     (unsigned int)(gchain >> 32), (unsigned int)A.seed, (unsigned int)(A.seed >> 32));
+      const double u1 = 1.0 - odl_u53(r.x, r.y);                // (0,1]
+      const double u2 = odl_u53(r.z, r.w);
+      const double rad = sqrt(-2.0 * log(u1));
+      double sn, cs;
+      sincospi(2.0 * u2, &sn, &cs);
+      z0 = A.step_sd * (rad * cs);
+      z1 = A.step_sd * (rad * sn);
+    }
+#pragma unroll
+    for (int q = 0; q < ODL_P; ++q) {
+      if (A.walk[j] == q) p[q] = exp(log(p[q]) + z0);
+      if (j + 1 < A.n_walk && A.walk[j + 1] == q) p[q] = exp(log(p[q]) + z1);
+    }
+  }
+}
+
+__device__ __forceinline__ double odl_mh_uniform(const OdlMcmcArgs& A, int chain_local, int it) {
+  if (A.rng_mode != 0) return A.u[(long long)chain_local * A.n_iter_total + (it - 1)];
+  const unsigned long long gchain = (unsigned long long)(A.chain_offset + chain_local);
+  const OdlPhilox r = odl_philox((unsigned int)it, 0u, (unsigned int)gchain, (unsigned int)(gchain >> 32),
+                                 (unsigned int)A.seed, (unsigned int)(A.seed >> 32));
+  return odl_u53(r.x, r.y);
+}
+
+extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
+odl_mcmc_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
+  extern __shared__ double odl_smem[];
+  const OdlShared S = odl_carve(odl_smem, D);
+  odl_load_tables(S, D);
+  const int lane = threadIdx.x & 31;
+  double* my_stage = S.stage + (size_t)threadIdx.x * D.stage_stride;
+  OdlStageSink sink; sink.stage = my_stage;
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;      // local chain index
+  const bool has_chain = chain < A.n_chain;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+
+  OdlStepper st;
+  double p[ODL_P];
+  st.status = ODL_OK; st.nsteps = 0; st.slot = 0;
+  // it == it_begin-1 marks the a-priori solve of a fresh chain (Samplers.py:88-90)
+  int it = A.it_begin;
+  double chi_cur = nan, r2_cur = nan;
+  int accepts = 0, fails = 0;
+  long long steps = 0;
+  bool apriori = false;
+  bool active = false, done = false;
+  if (has_chain) {
+    if (A.it_begin == 1) {
+      apriori = true;
+#pragma unroll
+      for (int q = 0; q < ODL_P; ++q) p[q] = A.theta_cur[(size_t)chain * ODL_P + q];
+    } else {
+      chi_cur = A.chain_state[(size_t)chain * 4 + 0];
+      r2_cur = A.chain_state[(size_t)chain * 4 + 1];
+      accepts = (int)A.chain_state[(size_t)chain * 4 + 2];
+      odl_propose(p, A, chain, it);
+    }
+    if (apriori || it < A.it_end) {
+      odl_init_system(st, p, D, O, nullptr);
+      odl_emit_initial_slots(st, S, D, sink);
+      active = true;
+      done = (st.slot >= D.n_slot);
+    }
+  }
+
+  for (;;) {
+    const bool fin = active && done;
+    unsigned m = __ballot_sync(ODL_FULL, fin);
+    double my_chi = nan, my_r2 = nan;
+    while (m) {
+      const int L = __ffs(m) - 1;
+      m &= m - 1;
+      double chi, ss; int nv;
+      odl_score(S, D, S.stage + (size_t)((threadIdx.x & ~31) + L) * D.stage_stride, lane, nullptr, chi, ss, nv);
+      if (lane == L) {
+        if (st.status == ODL_OK && nv > 0) { my_chi = chi; my_r2 = 1.0 - ss / D.sstot; }
+        else if (st.status == ODL_OK) { my_chi = nan; my_r2 = 1.0 - ss / D.sstot; }   // np.ma.masked chi
+      }
+    }
+    if (fin) {
+      steps += st.nsteps;
+      if (st.status != ODL_OK) ++fails;
+      double* cur = A.theta_cur + (size_t)chain * ODL_P;
+      if (apriori) {
+        apriori = false;
+        chi_cur = my_chi; r2_cur = my_r2;
+      } else {
+        const double u = odl_mh_uniform(A, chain, it);
+        const double acc = exp(chi_cur - my_chi);                // Samplers.py:124-125
+        const bool accept = acc > u;                             // :127  (NaN compares false => reject)
+        if (accept) {
+          chi_cur = my_chi; r2_cur = my_r2; ++accepts;
+#pragma unroll
+          for (int q = 0; q < ODL_P; ++q) cur[q] = p[q];
+        }
+        const long long k = (long long)chain * A.n_iter_total + (it - 1);
+        if (A.trace_chinew) A.trace_chinew[k] = my_chi;
+        if (A.trace_accept) A.trace_accept[k] = accept ? 1 : 0;
+        if (it > A.burnin) {                                     // :147
+          const int rowi = it - A.burnin - 1;
+          if (A.samples && rowi < A.n_keep) {
+            double* row = A.samples + ((size_t)chain * A.n_keep + rowi) * A.row_stride;
+#pragma unroll
+            for (int q = 0; q < ODL_P; ++q) row[q] = cur[q];
+            row[ODL_P + 0] = chi_cur;
+            row[ODL_P + 1] = r2_cur;
+            row[ODL_P + 2] = 2.0 * chi_cur + 2.0 * (double)A.pnum;   // stats.py:46
+            row[ODL_P + 3] = (double)it;
+            row[ODL_P + 4] = (double)accepts / (double)it;            // Samplers.py:153
+          }
+          if (A.summaries) {                                     // Welford over ln(theta) for R-hat
+            double* sm = A.summaries + (size_t)chain * (1 + 2 * ODL_P);
+            const double cnt = sm[0] + 1.0;
+            sm[0] = cnt;
+#pragma unroll
+            for (int q = 0; q < ODL_P; ++q) {
+              const double x = log(cur[q]);
+              const double dlt = x - sm[1 + q];
+              const double mean = sm[1 + q] + dlt / cnt;
+              sm[1 + q] = mean;
+              sm[1 + ODL_P + q] += dlt * (x - mean);
+            }
+          }
+        }
+        ++it;
+      }
+      done = false;
+      if (it < A.it_end) {
+        odl_propose(p, A, chain, it);
+        odl_init_system(st, p, D, O, nullptr);
+        odl_emit_initial_slots(st, S, D, sink);
+        done = (st.slot >= D.n_slot);
+      } else {
+        active = false;
+        A.chain_state[(size_t)chain * 4 + 0] = chi_cur;
+        A.chain_state[(size_t)chain * 4 + 1] = r2_cur;
+        A.chain_state[(size_t)chain * 4 + 2] = (double)accepts;
+        if (A.fail_count) A.fail_count[chain] += fails;
+        if (A.step_count) A.step_count[chain] += steps;
+      }
+    }
+    if (!__any_sync(ODL_FULL, active)) break;
+    if (active && !done) {
+      odl_dopri5_attempt(st, p, S, D, O, sink);
+      done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
+    }
+  }
+}

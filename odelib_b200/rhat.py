@@ -1,0 +1,54 @@
+"""Gelman-Rubin R-hat from per-chain Welford summaries, and the one collective of the path.
+
+R-hat does not exist in the reference (its only posterior summary is rawstats, Framework.py:11-17); the
+definition is pinned in SURVEY.md §8e: per parameter on x = ln(theta), m chains of n kept samples,
+W = mean_j s_j^2, B = n var_j(mean_j) (ddof=1), var+ = (n-1)/n W + B/n, R-hat = sqrt(var+/W).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def rhat_from_summaries(summaries, n_param):
+    """summaries [m, 1+2P] = (count, mean[P], M2[P]) per chain (numpy) -> R-hat [P]."""
+    s = np.asarray(summaries, dtype=np.float64)
+    n = s[:, 0]
+    if not np.all(n == n[0]):
+        raise ValueError("chains have different numbers of kept samples")
+    n = float(n[0])
+    means = s[:, 1:1 + n_param]
+    var = s[:, 1 + n_param:1 + 2 * n_param] / (n - 1.0)
+    W = var.mean(axis=0)
+    B = n * means.var(axis=0, ddof=1)
+    with np.errstate(all="ignore"):
+        return np.sqrt(((n - 1.0) / n * W + B / n) / W)
+
+
+def shard_bounds(n_total, world_size, rank):
+    """Contiguous block of chains / parameter sets owned by `rank`."""
+    base, rem = divmod(int(n_total), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allgather_summaries(local, n_total=None, group=None):
+    """All-gather per-chain summaries over the process group (NCCL on GPUs, gloo in CPU tests).
+
+    local: torch tensor [m_local, 1+2P].  Shards may differ by one row; they are padded to the largest
+    shard for the collective and trimmed afterwards.  Returns a tensor [m_total, 1+2P] on every rank.
+    """
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    ws = dist.get_world_size(group)
+    counts = torch.zeros(ws, dtype=torch.int64, device=local.device)
+    counts[dist.get_rank(group)] = local.shape[0]
+    dist.all_reduce(counts, group=group)
+    mmax = int(counts.max().item())
+    pad = torch.zeros((mmax, local.shape[1]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((ws * mmax, local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    parts = [out[r * mmax: r * mmax + int(counts[r].item())] for r in range(ws)]
+    return torch.cat(parts, dim=0)

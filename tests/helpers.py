@@ -36,3 +36,28 @@ def oracle_tables(name):
 def oracle_rhs(name):
     from oracle import odelib_oracle as orc
     return getattr(orc, name)
+
+
+def obs_tables_from_oracle(tab):
+    """oracle Tables -> product ObsTables (same content the facade derives itself)."""
+    from odelib_b200.engine import ObsTables
+    cols = tab.out_columns()
+    columns = [(cols[s], tab.tindex[s], tab.ln_obs[s], tab.log_sigma[s]) for s in tab.obs_order]
+    return ObsTables(tab.times, columns)
+
+
+def device_model(name, **kw):
+    """DeviceModel of a demo workload with the demo data loaded."""
+    from odelib_b200 import demo_models
+    from odelib_b200.engine import DeviceModel
+    f, n, P, groups = demo_models.MODELS[name]
+    dm = DeviceModel(f, n, P, groups, **kw)
+    tab = oracle_tables(name)
+    dm.set_data(obs_tables_from_oracle(tab), tab.y0)
+    dm.set_grid(tab.times, tab.y0)
+    return dm, tab
+
+
+def prior_draws(name, n, seed=0):
+    rng = np.random.default_rng(seed)
+    return np.column_stack([sc * np.exp(s * rng.standard_normal(n)) for _, s, sc in PRIORS[name]])

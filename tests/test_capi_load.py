@@ -1,0 +1,75 @@
+"""CPU-only checks of the C-ABI library: it loads, exports what include/odelib_b200.h declares, NVRTC
+compiles the demo models for sm_100a offline, and compute entry points refuse loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from odelib_b200 import _capi, demo_models, engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "odelib_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(odl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _capi.lib()
+    names = _declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/odelib_b200.h but not exported"
+    assert sorted(_capi.EXPORTS) == names
+    assert L.odl_abi_version() == 1
+
+
+@pytest.mark.parametrize("name", ["zero_i", "one_i", "two_i"])
+def test_nvrtc_compiles_demo_models_offline(name, tmp_path):
+    f, n, P, g = demo_models.MODELS[name]
+    m = engine.DeviceModel(f, n, P, g, compile_only=True, cache_dir=str(tmp_path))
+    cubins = [p for p in os.listdir(tmp_path) if p.endswith(".cubin")]
+    assert len(cubins) == 1 and os.path.getsize(tmp_path / cubins[0]) > 10000
+    # second build hits the cache
+    m2 = engine.DeviceModel(f, n, P, g, compile_only=True, cache_dir=str(tmp_path))
+    assert "cache hit" in m2.build_log
+    m.close(); m2.close()
+
+
+def test_bad_model_source_reports_nvrtc_log():
+    L = _capi.lib()
+    h = ctypes.c_void_p()
+    bo = _capi.BuildOpts(); bo.device = -1; bo.dense_output = 1; bo.compile_only = 1
+    rc = L.odl_model_create(b"#define ODL_N 1\n#define ODL_P 1\n#define ODL_NOUT 1\nthis is not CUDA;\n", 1, 1, 1,
+                            ctypes.byref(bo), ctypes.byref(h))
+    assert rc == _capi.ECOMPILE
+    assert b"error" in L.odl_last_error()
+
+
+def test_compute_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    f, n, P, g = demo_models.MODELS["zero_i"]
+    with pytest.raises(_capi.OdlError) as e:
+        engine.DeviceModel(f, n, P, g)
+    assert e.value.code == _capi.ENODEVICE
+    m = engine.DeviceModel(f, n, P, g, compile_only=True)
+    with pytest.raises(_capi.OdlError):
+        m.sweep(np.ones((4, 3)))
+    m.close()
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32-10."""
+    z = engine.philox4x32_10(np.zeros(4, np.uint32), np.zeros(2, np.uint32))
+    assert [int(x) for x in z] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = engine.philox4x32_10(np.full(4, 0xffffffff, np.uint32), np.full(2, 0xffffffff, np.uint32))
+    assert [int(x) for x in f] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    zz, uu = engine.philox_streams(7, np.arange(4), 50, 5)
+    assert zz.shape == (4, 50, 5) and uu.shape == (4, 50)
+    assert 0 <= uu.min() and uu.max() < 1 and abs(zz.std() / 0.05 - 1) < 0.1

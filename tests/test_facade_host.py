@@ -1,0 +1,120 @@
+"""Host-side logic of the ModelFramework facade (no GPU): the tables it derives equal the reference's
+(golden vectors), names / errors / return shapes follow ODElib/Framework.py."""
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.stats
+
+import odelib_b200 as ODElib
+from odelib_b200 import demo_models
+from odelib_b200.Statistics import Samplers, stats
+from oracle import odelib_oracle as orc
+from tests.helpers import PRIORS, STATES, SUMS, TSTEPS, demo_df, golden
+
+
+def make_model(name, **kw):
+    pri = {n: ODElib.parameter(stats_gen=scipy.stats.lognorm, hyperparameters={"s": s, "scale": sc}, init_value=sc)
+           for n, s, sc in PRIORS[name]}
+    extra = {} if name == "zero_i" else {"S": 5236900}
+    return ODElib.ModelFramework(ODE=demo_models.MODELS[name][0], parameter_names=[p[0] for p in PRIORS[name]],
+                                 state_names=STATES[name], dataframe=demo_df(name), state_summations=SUMS[name],
+                                 t_steps=TSTEPS[name], **pri, **extra, **kw)
+
+
+@pytest.mark.parametrize("name", ["zero_i", "one_i", "two_i"])
+def test_ctor_tables_equal_reference(name):
+    g = golden(name)
+    m = make_model(name)
+    assert np.array_equal(m.times, g["times"])
+    order = [s for s in m.get_snames(after_summation=True) if s in m._pred_tindex]
+    assert order == list(g["obs_order"])
+    for s in order:
+        assert np.array_equal(m._pred_tindex[s], g["tindex_" + s])
+    assert np.array_equal(np.concatenate([m._obs_logabundance[s] for s in order]), g["ln_obs"])
+    assert np.array_equal(np.concatenate([m._obs_logsigma[s] for s in order]), g["log_sigma"])
+    assert np.array_equal(np.asarray(m.get_inits(), float), g["y0"])
+    assert m._pnum == int(g["pnum"]) and m._samples == 37
+    groups = m._observe_groups()
+    assert [tuple(x) for x in groups] == [tuple(x) for x in demo_models.MODELS[name][3]]
+
+
+def test_names_errors_and_parameter_semantics():
+    m = make_model("two_i")
+    assert m.get_pnames() == ["mu", "phi", "beta", "lam", "tau"]
+    assert m.get_snames() == ["H", "V"] and m.get_snames(after_summation=False) == ["S", "I1", "I2", "V"]
+    with pytest.raises(Exception, match="unknown parameter"):
+        m.set_parameters(nope=1.0)
+    with pytest.raises(Exception, match="unknown state"):
+        m.set_inits(nope=1.0)
+    with pytest.raises(ValueError):
+        ODElib.ModelFramework(demo_models.two_i, ["mu", "phi", "beta", "lam", "tau"], ["S", "I1", "I2", "V"],
+                              state_summations={"H": ["S", "I1"], "G": ["I1", "V"]})
+    with pytest.raises(ValueError):
+        ODElib.parameter()
+    m.set_parameters(mu=2e-8)
+    assert m.get_parameters()[0][0] == 2e-8 and m.get_parameters(as_dict=True)["mu"] == 2e-8
+    c = m.copy(overwrite={"mu": 3e-8, "S": 10.0})
+    assert c.get_parameters()[0][0] == 3e-8 and m.get_parameters()[0][0] == 2e-8
+    assert c.get_inits()[0] == 10.0 and m.get_inits()[0] == 5236900
+    assert "Current State Summations" in repr(m)
+    p = ODElib.parameter(scipy.stats.lognorm, {"s": 1, "scale": 2.0}, init_value=1.5)
+    np.random.seed(0)
+    p.rwalk()
+    assert float(p.val) == pytest.approx(1.5 * np.exp(0.05 * 1.764052345967664), rel=1e-15)
+    assert ODElib.parameter(init_value=3.0).pdf() == 1.0
+
+
+def test_host_stats_match_reference_formulas():
+    rng = np.random.default_rng(0)
+    O = rng.normal(10, 1, 37); S = rng.uniform(0.05, 0.6, 37)
+    with np.errstate(all="ignore"):
+        C = np.log(rng.normal(3e4, 2e4, 37))        # some negative -> NaN
+        S[5] = 0.0
+        ref = orc.chi(O, C, S)
+    assert stats.chi(O, C, S) == pytest.approx(float(ref), rel=1e-14)
+    assert stats.chi(O, np.full(37, np.nan), S) is np.ma.masked
+    assert stats.AIC(10.0, 3) == 26.0
+    Cd = {"a": np.array([1.0, 2.0, np.nan]), "b": np.array([3.0, 4.0])}
+    Od = {"a": np.array([1.5, 2.5, 3.0]), "b": np.array([2.0, 5.0])}
+    sst = 3 * np.var(Od["a"]) + 2 * np.var(Od["b"])
+    assert stats.Rsqrd(Cd, Od) == pytest.approx(1 - (0.25 + 0.25 + 1 + 1) / sst)
+
+
+def test_reference_streams_equal_golden_and_lhs_is_latin():
+    g = golden("two_i")
+    m = make_model("two_i")
+    walking = [m.parameters[p] for p in m.get_pnames()]
+    z, u = Samplers.reference_streams(0, walking, int(g["chain_def_s0_nits"]) - 1)
+    assert np.array_equal(z, g["chain_def_s0_z"]) and np.array_equal(u, g["chain_def_s0_u"])
+    # odd count per iteration (one parameter without prior) takes the scalar path
+    walking[0] = ODElib.parameter(init_value=1.0)
+    z2, u2 = Samplers.reference_streams(3, walking, 20)
+    rs = np.random.RandomState(3)
+    for i in range(20):
+        for j in range(5):
+            assert z2[i, j] == rs.normal(0, 0.05)
+        for _ in range(4):
+            rs.standard_normal()
+        assert u2[i] == rs.rand()
+    np.random.seed(1)
+    d = Samplers.lhs(3, 50)
+    assert d.shape == (50, 3)
+    for j in range(3):
+        assert sorted(np.floor(d[:, j] * 50).astype(int)) == list(range(50))
+    np.random.seed(2)
+    df = m._lhs_samples(64)
+    assert list(df.columns) == m.get_pnames() and len(df) == 64 and (df > 0).all().all()
+
+
+def test_replicate_dataframe_format():
+    rows = []
+    for org in ("S", "V"):
+        for t in (0.0, 1.0, 2.0):
+            for r in range(3):
+                rows.append({"organism": org, "time": t, "abundance": 100.0 * (1 + r) * (1 + t), "replicate": r})
+    pri = {n: ODElib.parameter(init_value=v) for n, v in (("mu", 1e-8), ("phi", 1e-8), ("beta", 20.0))}
+    m = ODElib.ModelFramework(demo_models.zero_i, ["mu", "phi", "beta"], ["S", "V"], dataframe=pd.DataFrame(rows),
+                              t_steps=21, **pri)
+    assert m._samples == 6
+    np.testing.assert_allclose(m._obs_logabundance["S"], [np.log([100., 200, 300]).mean() + np.log(1 + t) for t in (0, 1, 2)])
+    assert list(m._pred_tindex["V"]) == [0, 10, 20]

@@ -1,0 +1,81 @@
+"""The drop-in surface on the GPU: these read like a session with the reference (the demo notebook) and
+are checked against vectors recorded from the unmodified reference."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests.helpers import golden
+from tests.test_facade_host import make_model
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["zero_i", "one_i", "two_i"])
+def test_integrate_and_fitstats_like_the_reference(name):
+    g = golden(name)
+    m = make_model(name, rtol=1e-12, atol=1e-12)
+    th = g["theta"][0]
+    m.set_parameters(**dict(zip(m.get_pnames(), th)))
+    pred = m.integrate(predict_obs=True, as_dataframe=False)
+    assert list(pred) == list(g["obs_order"])
+    vec = np.concatenate([pred[s] for s in pred])
+    np.testing.assert_allclose(vec, g["pred_tight"][0], rtol=2e-9)
+    assert m.get_chi(pred) == pytest.approx(g["chi_tight"][0], rel=1e-9)
+    fs = m.get_fitstats()
+    assert fs["R^2"] == pytest.approx(g["r2_tight"][0], rel=1e-8, abs=1e-9)
+    assert fs["AIC"] == pytest.approx(2 * g["chi_tight"][0] + 2 * int(g["pnum"]), rel=1e-9)
+    full = m.integrate()
+    assert list(full.columns) == m.get_snames() + ["time"] and len(full) == len(m.times)
+    raw = m.integrate(as_dataframe=False, sum_subpopulations=False)
+    assert raw.shape == (len(m.times), len(m._snames))
+    long = m.integrate(predict_obs=True)
+    assert len(long) == 37 and list(long.columns) == ["time", "abundance"]
+    res = m.get_residuals()
+    assert len(res) == 37
+
+
+def test_fit_survey_frame_and_chi_consistency():
+    m = make_model("zero_i")
+    np.random.seed(0)
+    sv = m.fit_survey(samples=2000, cpu_cores=8)
+    assert list(sv.columns) == ["mu", "phi", "beta", "chi"] and len(sv) == 2000
+    again = m.sweep(sv[["mu", "phi", "beta"]].to_numpy())
+    assert np.array_equal(again["chi"], sv["chi"].to_numpy(), equal_nan=True)
+    assert (sv["chi"] < 666).sum() > 20          # ~9.5 % of zero_i prior draws pass sd=6
+
+
+def test_metropolis_hastings_reproduces_the_reference_chain():
+    """Same start, same seed: the GPU chain IS the reference chain (its random numbers are regenerated)."""
+    from odelib_b200.Statistics import Samplers
+    name = "zero_i"
+    g = golden(name)
+    pre = "chain_tight_s0_"
+    m = make_model(name, rtol=1e-13, atol=1e-13)
+    m.set_parameters(**dict(zip(m.get_pnames(), g[pre + "theta0"])))
+    m.random_seed = 0
+    df = Samplers.MetropolisHastings(m, nits=int(g[pre + "nits"]), print_progress=False)
+    assert list(df.columns) == m.get_pnames() + ["chi", "rsquared", "aic", "iteration", "acceptance_ratio"]
+    kept = g[pre + "kept"]
+    assert len(df) == len(kept)
+    np.testing.assert_array_equal(df["iteration"].to_numpy(), kept[:, -2])
+    np.testing.assert_array_equal(df["acceptance_ratio"].to_numpy(), kept[:, -1])     # identical decisions
+    np.testing.assert_allclose(df[m.get_pnames()].to_numpy(), kept[:, :3], rtol=1e-12)
+    np.testing.assert_allclose(df["chi"].to_numpy(), kept[:, 3], rtol=1e-8)
+
+
+def test_mcmc_demo_call_shapes_and_report(capsys):
+    m = make_model("two_i")
+    np.random.seed(3)
+    post = m.MCMC(chain_inits=8, iterations_per_chain=200, cpu_cores=8, fitsurvey_samples=4000, sd_fitdistance=6.0)
+    cols = m.get_pnames() + ["chi", "rsquared", "aic", "iteration", "acceptance_ratio", "chain#"]
+    assert list(post.columns) == cols
+    assert len(post) == 8 * 99 and set(post["chain#"]) == set(range(8))       # nits-1-burnin rows per chain
+    assert post["iteration"].min() == 101 and post["iteration"].max() == 199
+    assert "Fitting Report" in capsys.readouterr().out
+    assert m.rhat is not None and len(m.rhat) == 5
+    # explicit starts + static parameter: column reports the prior scale (reference quirk A13)
+    starts = [dict(zip(m.get_pnames(), post[m.get_pnames()].iloc[i])) for i in (0, 150)]
+    p2 = m.MCMC(chain_inits=starts, iterations_per_chain=100, static_parameters=["tau"], print_report=False)
+    assert np.all(p2["tau"] == 1) and len(p2) == 2 * 49
+    with pytest.raises(ValueError):
+        m.MCMC(chain_inits=2, iterations_per_chain=50, fitsurvey_samples=50, sd_fitdistance=0.01, print_report=False)

@@ -1,0 +1,148 @@
+"""GPU parity of the device-resident Metropolis-Hastings kernel (odl_mcmc) with the reference chain
+(golden vectors recorded from the unmodified Samplers.MetropolisHastings) and with the oracle."""
+import numpy as np
+import pytest
+
+from odelib_b200 import engine
+from oracle import odelib_oracle as orc
+from tests.helpers import device_model, golden, oracle_rhs
+
+pytestmark = pytest.mark.gpu
+MODELS = ["zero_i", "one_i", "two_i"]
+
+
+def _near_tie(chi_cur, chinew, u, delta):
+    with np.errstate(all="ignore"):
+        return np.abs((chi_cur - chinew) - np.log(u)) < delta
+
+
+def _replay(chi0, chinew, u):
+    """Decisions and running chi implied by a chinew sequence (Samplers.py:124-127)."""
+    acc = np.zeros(len(u), bool); cur = np.empty(len(u)); c = chi0
+    for k in range(len(u)):
+        cur[k] = c
+        with np.errstate(all="ignore"):
+            if np.exp(c - chinew[k]) > u[k]:
+                acc[k] = True; c = chinew[k]
+    return acc, cur
+
+
+@pytest.mark.parametrize("name", MODELS)
+@pytest.mark.parametrize("tag,tol,delta,rtol_chi", [("def", None, 1e-4, 2e-5), ("tight", 1e-13, 1e-8, 1e-9)])
+def test_teacher_forced_decisions_match_reference(name, tag, tol, delta, rtol_chi):
+    """Reference proposals fed to the GPU: chinew within tolerance, decisions identical except near-ties."""
+    g = golden(name)
+    pre = f"chain_{tag}_s0_"
+    nits = int(g[pre + "nits"])
+    dm, _ = device_model(name)
+    out = dm.mcmc(g[pre + "theta0"][None, :], nits=nits, rng_mode="forced", forced=g[pre + "proposals"][None],
+                  u=g[pre + "u"][None], rtol=tol, atol=tol, trace=True, pnum=int(g["pnum"]), max_steps=2000000)
+    ref_acc, ref_cur = _replay(float(g[pre + "chi0"]), g[pre + "chinew"], g[pre + "u"])
+    assert np.array_equal(ref_acc, g[pre + "accepted"])
+    fin = np.isfinite(g[pre + "chinew"])
+    np.testing.assert_allclose(out["chinew"][0][fin], g[pre + "chinew"][fin], rtol=rtol_chi, atol=1e-7)
+    tie = _near_tie(ref_cur, g[pre + "chinew"], g[pre + "u"], delta)
+    assert tie.sum() <= 2
+    first_tie = np.flatnonzero(tie)[0] if tie.any() else len(tie)
+    assert np.array_equal(out["accepted"][0][:first_tie].astype(bool), ref_acc[:first_tie])
+    if not tie.any():
+        # no near-tie: the whole chain (kept rows: theta, iteration, acceptance ratio) is the reference's
+        kept = g[pre + "kept"]; P = dm.n_param
+        np.testing.assert_array_equal(out["samples"][0][:, :P], kept[:, :P])          # bit-identical samples
+        np.testing.assert_array_equal(out["samples"][0][:, P + 3:], kept[:, P + 3:])  # iteration, acceptance
+        np.testing.assert_allclose(out["samples"][0][:, P:P + 3], kept[:, P:P + 3], rtol=rtol_chi, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_free_running_host_streams_match_reference(name):
+    """Host z/u streams (the reference's own random numbers): the device forms exp(log(theta)+z) itself."""
+    g = golden(name)
+    pre = "chain_tight_s0_"
+    nits = int(g[pre + "nits"])
+    dm, _ = device_model(name)
+    z, u = orc.reference_streams(0, dm.n_param, nits - 1)
+    assert np.array_equal(z, g[pre + "z"])
+    out = dm.mcmc(g[pre + "theta0"][None, :], nits=nits, rng_mode="host", z=z[None], u=u[None], rtol=1e-13,
+                  atol=1e-13, trace=True, pnum=int(g["pnum"]), max_steps=2000000)
+    ref_acc, ref_cur = _replay(float(g[pre + "chi0"]), g[pre + "chinew"], g[pre + "u"])
+    tie = _near_tie(ref_cur, g[pre + "chinew"], g[pre + "u"], 1e-7)
+    first_tie = np.flatnonzero(tie)[0] if tie.any() else len(tie)
+    assert first_tie > 50
+    assert np.array_equal(out["accepted"][0][:first_tie].astype(bool), ref_acc[:first_tie])
+    if not tie.any():
+        kept = g[pre + "kept"]; P = dm.n_param
+        # device exp/log differ from numpy's by <= 1 ulp per step: a few ulp after a random walk
+        np.testing.assert_allclose(out["samples"][0][:, :P], kept[:, :P], rtol=1e-12)
+        np.testing.assert_allclose(out["samples"][0][:, P], kept[:, P], rtol=1e-8)
+        np.testing.assert_array_equal(out["samples"][0][:, P + 3:], kept[:, P + 3:])
+
+
+def test_philox_chains_match_oracle_with_recomputed_streams():
+    """Device Philox streams recomputed on the host and fed to the oracle chain: same decisions."""
+    name = "zero_i"
+    g = golden(name)
+    dm, tab = device_model(name)
+    nits, C, seed = 120, 6, 1234
+    theta0 = np.tile(g["chain_def_s0_theta0"], (C, 1)) * np.exp(0.01 * np.arange(C))[:, None]
+    out = dm.mcmc(theta0, nits=nits, rng_mode="philox", seed=seed, chain_offset=10, rtol=1e-12, atol=1e-12, trace=True)
+    z, u = engine.philox_streams(seed, 10 + np.arange(C), nits - 1, dm.n_param)
+    rhs = oracle_rhs(name)
+    for c in range(C):
+        ref = orc.mh_chain(rhs, theta0[c], tab, dm.n_param, nits=nits, z=z[c], u=u[c], rtol=1e-13, atol=1e-13)
+        _, cur = _replay(np.nan, ref["chinew"], u[c])
+        assert np.array_equal(out["accepted"][c].astype(bool), ref["accepted"])
+        np.testing.assert_allclose(out["chinew"][c], ref["chinew"], rtol=1e-8)
+        np.testing.assert_allclose(out["samples"][c][:, :3], ref["kept"][:, :3], rtol=1e-11)
+        np.testing.assert_array_equal(out["samples"][c][:, -2], ref["kept"][:, -2])
+        np.testing.assert_allclose(out["samples"][c][:, -1], ref["kept"][:, -1], rtol=1e-15)
+
+
+def test_static_parameters_do_not_walk_and_segments_continue():
+    name = "two_i"
+    g = golden(name)
+    dm, _ = device_model(name)
+    theta0 = np.tile(g["chain_def_s0_theta0"], (64, 1))
+    a = dm.mcmc(theta0, nits=200, walk=[0, 1, 2, 4], seed=5, trace=True)
+    assert np.all(a["samples"][:, :, 3] == theta0[0, 3])            # lam static
+    assert np.all(a["theta"][:, 3] == theta0[0, 3])
+    # the same chains in 4 launches give bit-identical results (state persists in the buffers)
+    b = dm.mcmc(theta0, nits=200, walk=[0, 1, 2, 4], seed=5, trace=True, segments=4)
+    assert np.array_equal(a["samples"], b["samples"])
+    assert np.array_equal(a["accepted"], b["accepted"])
+    assert np.array_equal(a["summaries"], b["summaries"])
+    # chains differ from one another (per-chain streams) and accept at a sane rate
+    assert len({tuple(r) for r in a["theta"]}) > 32
+    rate = a["accepted"].mean()
+    assert 0.02 < rate < 0.9
+
+
+def test_summaries_are_welford_of_kept_log_samples_and_rhat():
+    name = "zero_i"
+    g = golden(name)
+    dm, _ = device_model(name)
+    C = 32
+    theta0 = np.tile(g["chain_def_s0_theta0"], (C, 1))
+    out = dm.mcmc(theta0, nits=400, seed=3)
+    P = dm.n_param
+    logs = np.log(out["samples"][:, :, :P])
+    np.testing.assert_array_equal(out["summaries"][:, 0], out["n_keep"])
+    np.testing.assert_allclose(out["summaries"][:, 1:1 + P], logs.mean(axis=1), rtol=1e-12)
+    m2 = ((logs - logs.mean(axis=1, keepdims=True)) ** 2).sum(axis=1)
+    np.testing.assert_allclose(out["summaries"][:, 1 + P:], m2, rtol=1e-9, atol=1e-18)
+    from odelib_b200.rhat import rhat_from_summaries
+    np.testing.assert_allclose(rhat_from_summaries(out["summaries"], P), orc.rhat(logs), rtol=1e-10)
+
+
+def test_edge_semantics_nan_chi_rejects_and_device_buffers():
+    import torch
+    name = "zero_i"
+    g = golden(name)
+    dm, _ = device_model(name)
+    th = np.tile(g["chain_def_s0_theta0"], (8, 1))
+    th[3, 0] = np.nan                           # a chain whose a-priori solve fails never accepts
+    out = dm.mcmc(th, nits=60, seed=1, trace=True)
+    assert out["accepted"][3].sum() == 0 and np.isnan(out["chain_state"][3, 0])
+    assert out["fail_count"][3] > 0
+    dev = dm.mcmc(torch.from_numpy(th).cuda(), nits=60, seed=1, trace=True, device_buffers=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev["samples"].cpu().numpy(), out["samples"], equal_nan=True)
