@@ -65,7 +65,7 @@ typedef struct odl_solver_opts {
   int max_steps;       /* attempted steps per solve before ODL_ST_MAXSTEPS */
   int solver;          /* ODL_SOLVER_* */
   int stiff_check;     /* DOPRI5: detect stiffness and stop with ODL_ST_STIFF */
-  int reserved;
+  int stiff_min_steps; /* ... only while more than this many steps of the current size remain (0 = 2000) */
 } odl_solver_opts;
 
 typedef struct odl_mcmc_opts {
@@ -107,7 +107,8 @@ int odl_model_create(const char* model_cuda_src, int n_state, int n_param, int n
 int odl_model_destroy(odl_model* m);
 /* compile log of the NVRTC run (warnings included); valid until the model is destroyed */
 const char* odl_model_build_log(const odl_model* m);
-/* resource usage of a compiled kernel ("sweep", "mcmc", "traj"): registers/thread, local (spill) bytes */
+/* resource usage of a compiled kernel ("sweep", "mcmc", "traj", "sweep_ros23", "mcmc_ros23", "mcmc_auto"):
+   registers/thread, local (spill) bytes, resident CTAs per SM */
 int odl_model_kernel_info(const odl_model* m, const char* kernel, int* regs, int* local_bytes, int* max_blocks_per_sm);
 
 int odl_model_set_data(odl_model* m, int n_slot, const double* slot_time, int n_obs, const int* obs_slot,

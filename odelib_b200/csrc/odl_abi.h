@@ -35,7 +35,8 @@ struct OdlOpts {
   double hmax;                   // 0 = t_end - t0
   int max_steps;
   int stiff_check;               // 1 = run Hairer's stiffness test and bail out with ODL_STIFF
-  int reserved0, reserved1;
+  int stiff_min_steps;           // bail out only if more than this many steps of the current size remain
+  int reserved1;
 };
 
 struct OdlSweepArgs {

@@ -131,7 +131,7 @@ struct odl_model {
   std::string log;
   CUmodule mod = nullptr;
   CUfunction k_sweep = nullptr, k_traj = nullptr, k_mcmc = nullptr;
-  CUfunction k_sweep_ros = nullptr, k_mcmc_ros = nullptr;
+  CUfunction k_sweep_ros = nullptr, k_mcmc_ros = nullptr, k_mcmc_auto = nullptr;
   Tables data, grid;
   DevBuf counter;
   DevBuf scratch[16];
@@ -247,7 +247,8 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
   { CUresult r = g_drv.ModuleLoadData(&m->mod, m->cubin.data()); if (r != CUDA_SUCCESS) return bail(fail(ODL_ECUDA, "cuModuleLoadData: " + cu_err(r))); }
   struct { const char* name; CUfunction* fn; bool required; } ks[] = {
       {"odl_sweep_kernel", &m->k_sweep, true}, {"odl_traj_kernel", &m->k_traj, true}, {"odl_mcmc_kernel", &m->k_mcmc, true},
-      {"odl_sweep_ros23_kernel", &m->k_sweep_ros, false}, {"odl_mcmc_ros23_kernel", &m->k_mcmc_ros, false}};
+      {"odl_sweep_ros23_kernel", &m->k_sweep_ros, true}, {"odl_mcmc_ros23_kernel", &m->k_mcmc_ros, true},
+      {"odl_mcmc_auto_kernel", &m->k_mcmc_auto, true}};
   for (auto& k : ks) {
     CUresult r = g_drv.ModuleGetFunction(k.fn, m->mod, k.name);
     if (r != CUDA_SUCCESS) {
@@ -286,6 +287,7 @@ static CUfunction kernel_by_name(const odl_model* m, const char* k) {
   if (!strcmp(k, "traj")) return m->k_traj;
   if (!strcmp(k, "sweep_ros23")) return m->k_sweep_ros;
   if (!strcmp(k, "mcmc_ros23")) return m->k_mcmc_ros;
+  if (!strcmp(k, "mcmc_auto")) return m->k_mcmc_auto;
   return nullptr;
 }
 
@@ -395,7 +397,8 @@ static void fill_opts(OdlOpts& o, const odl_solver_opts* so) {
   o.hmax = so ? so->hmax : 0.0;
   o.max_steps = so && so->max_steps > 0 ? so->max_steps : 500000;
   o.stiff_check = so ? so->stiff_check : 0;
-  o.reserved0 = o.reserved1 = 0;
+  o.stiff_min_steps = so && so->stiff_min_steps > 0 ? so->stiff_min_steps : 2000;
+  o.reserved1 = 0;
 }
 
 static int launch(odl_model* m, CUfunction f, unsigned grid, unsigned block, size_t smem, cudaStream_t s, void** params) {
@@ -583,7 +586,8 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   while (block > 32 && (long long)C < (long long)m->sm_count * block * 2) block /= 2;
   const size_t smem = smem_bytes(D, (int)block);
   unsigned grid = (unsigned)((C + block - 1) / block);
-  CUfunction f = (solver == ODL_SOLVER_DOPRI5) ? m->k_mcmc : m->k_mcmc_ros;
+  CUfunction f = (solver == ODL_SOLVER_DOPRI5) ? m->k_mcmc : (solver == ODL_SOLVER_ROS23 ? m->k_mcmc_ros : m->k_mcmc_auto);
+  if (solver == ODL_SOLVER_AUTO) O.stiff_check = 1;
   ODL_CUDA(cudaEventRecord(m->ev0, s));
   void* params[] = {&D, &O, &A};
   if ((rc = launch(m, f, grid, block, smem, s, params))) return rc;

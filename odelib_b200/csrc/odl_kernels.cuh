@@ -15,6 +15,7 @@
 //   stats.py:49-56  R^2                                    -> odl_score
 //   Framework.py:41-48   _Fit_worker loop                  -> odl_sweep_kernel
 //   Samplers.py:53-174   MetropolisHastings                -> odl_mcmc_kernel (one chain per thread)
+//   (stiff parameter regions, LSODA's BDF branch)         -> ROS23 stepper: odl_*_ros23_kernel, odl_mcmc_auto_kernel
 //
 // Execution model: every thread owns one ODE system at a time and keeps its state, the 7 stage
 // derivatives and the parameter vector in registers.  The main loop is a flat state machine:
@@ -34,6 +35,9 @@
 #endif
 #ifndef ODL_DENSE
 #define ODL_DENSE 1
+#endif
+#ifndef ODL_MINBLOCKS_ROS
+#define ODL_MINBLOCKS_ROS (ODL_MINBLOCKS > 2 ? ODL_MINBLOCKS - 1 : ODL_MINBLOCKS)
 #endif
 
 #define ODL_FULL 0xffffffffu
@@ -291,7 +295,9 @@ __device__ __forceinline__ void odl_dopri5_attempt(OdlStepper& st, const double 
         const double hlamb = h * sqrt(num / den);
         if (hlamb > 3.25) {
           st.nonsti = 0;
-          if (++st.iasti == 15) st.status = ODL_STIFF;
+          // stiff for 15 checks in a row AND still far from the end at this (stability-limited) step size:
+          // hand the system to the Rosenbrock path; mildly stiff / nearly finished systems stay here
+          if (++st.iasti >= 15 && (st.tend - tph) > (double)O.stiff_min_steps * h) st.status = ODL_STIFF;
         } else if (++st.nonsti == 6) st.iasti = 0;
       }
     }
@@ -370,6 +376,168 @@ struct OdlTrajSink {             // raw states -> global trajectory
   }
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// Rosenbrock-W 2(3) of Shampine & Reichelt ("The MATLAB ODE suite", SIAM J. Sci. Comput. 18, 1997: ode23s)
+// for the stiff parameter regions.  Analytic Jacobian from the tracer, W = I - h d J factorised in
+// registers (fully unrolled LU with partial pivoting; swap decisions kept in a bit mask and replayed on
+// the three right-hand sides), L-stable second-order advance with third-order error estimate, FSAL on f.
+// ------------------------------------------------------------------------------------------------
+#define ODL_ROS_D 0.29289321881345254      /* 1/(2+sqrt 2) */
+#define ODL_ROS_E32 7.414213562373095      /* 6+sqrt 2 */
+
+struct OdlLU {
+  double a[ODL_N][ODL_N];
+  double inv[ODL_N];
+  unsigned long long swaps;
+};
+__device__ __forceinline__ void odl_lu_factor(OdlLU& F) {
+  unsigned long long sw = 0ull;
+  int bit = 0;
+#pragma unroll
+  for (int k = 0; k < ODL_N; ++k) {
+#pragma unroll
+    for (int i = k + 1; i < ODL_N; ++i) {
+      const bool s = fabs(F.a[i][k]) > fabs(F.a[k][k]);
+      if (s) sw |= (1ull << (bit & 63));
+      ++bit;
+#pragma unroll
+      for (int j = 0; j < ODL_N; ++j) {
+        const double u = F.a[k][j], v = F.a[i][j];
+        F.a[k][j] = s ? v : u;
+        F.a[i][j] = s ? u : v;
+      }
+    }
+    F.inv[k] = 1.0 / F.a[k][k];
+#pragma unroll
+    for (int i = k + 1; i < ODL_N; ++i) {
+      const double l = F.a[i][k] * F.inv[k];
+      F.a[i][k] = l;
+#pragma unroll
+      for (int j = k + 1; j < ODL_N; ++j) F.a[i][j] -= l * F.a[k][j];
+    }
+  }
+  F.swaps = sw;
+}
+__device__ __forceinline__ void odl_lu_solve(const OdlLU& F, double (&b)[ODL_N]) {
+  int bit = 0;
+#pragma unroll
+  for (int k = 0; k < ODL_N; ++k) {
+#pragma unroll
+    for (int i = k + 1; i < ODL_N; ++i) {
+      const bool s = (F.swaps >> (bit & 63)) & 1ull;
+      ++bit;
+      const double u = b[k], v = b[i];
+      b[k] = s ? v : u;
+      b[i] = s ? u : v;
+    }
+#pragma unroll
+    for (int i = k + 1; i < ODL_N; ++i) b[i] -= F.a[i][k] * b[k];
+  }
+#pragma unroll
+  for (int k = ODL_N - 1; k >= 0; --k) {
+    double acc = b[k];
+#pragma unroll
+    for (int j = k + 1; j < ODL_N; ++j) acc -= F.a[k][j] * b[j];
+    b[k] = acc * F.inv[k];
+  }
+}
+
+template <class Sink>
+__device__ __forceinline__ void odl_ros23_attempt(OdlStepper& st, const double (&p)[ODL_P], const OdlShared& S,
+                                                  const OdlData& D, const OdlOpts& O, Sink& sink) {
+  static_assert(ODL_N * (ODL_N - 1) / 2 <= 64, "ROS23 pivot mask holds at most 64 swap decisions (n <= 11)");
+  const double t = st.t;
+  double h = st.h;
+  bool last = false;
+  if ((t + 1.01 * h - st.tend) > 0.0) { h = st.tend - t; last = true; }
+  ++st.nsteps;
+  OdlLU F;
+  odl_jac(st.y, t, p, F.a);
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i)
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) F.a[i][j] = ((i == j) ? 1.0 : 0.0) - (h * ODL_ROS_D) * F.a[i][j];
+  odl_lu_factor(F);
+  double hdT[ODL_N];
+#if ODL_AUTONOMOUS
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) hdT[i] = 0.0;
+#else
+  odl_dfdt(st.y, t, p, hdT);
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) hdT[i] *= h * ODL_ROS_D;
+#endif
+  double k1[ODL_N], k2[ODL_N], k3[ODL_N], F1[ODL_N], F2[ODL_N], yt[ODL_N], yn[ODL_N];
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) k1[i] = st.k1[i] + hdT[i];
+  odl_lu_solve(F, k1);
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) yt[i] = st.y[i] + (0.5 * h) * k1[i];
+  odl_rhs(yt, t + 0.5 * h, p, F1);
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) k2[i] = F1[i] - k1[i];
+  odl_lu_solve(F, k2);
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) { k2[i] += k1[i]; yn[i] = st.y[i] + h * k2[i]; }
+  const double tph = t + h;
+  odl_rhs(yn, tph, p, F2);
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) k3[i] = F2[i] - ODL_ROS_E32 * (k2[i] - F1[i]) - 2.0 * (k1[i] - st.k1[i]) + hdT[i];
+  odl_lu_solve(F, k3);
+  float errsq = 0.f;
+  bool finite_all = true;
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) {
+    const double e = (h * (1.0 / 6.0)) * (k1[i] - 2.0 * k2[i] + k3[i]);
+    const double sk = O.atol + O.rtol * fmax(fabs(st.y[i]), fabs(yn[i]));
+    const float r = odl_err_ratio(e, sk);
+    errsq += r * r;
+    finite_all = finite_all && odl_finite(yn[i]);
+  }
+  const float err = sqrtf(errsq * (1.0f / ODL_N));
+  const float fac = 0.8f * __powf(err, -1.0f / 3.0f);           // h_new = h * clamp(0.8 err^(-1/3), 0.2, 5)
+  if (err <= 1.0f && finite_all) {
+    double hnew = (err > 0.f) ? h * (double)fminf(5.0f, fmaxf(0.2f, fac)) : 5.0 * h;
+    const double tnew = last ? st.tend : tph;
+    if (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew) {
+      do {   // ode23s interpolant: y + h (k1 s(1-s)/(1-2d) + k2 s(s-2d)/(1-2d))
+        const double s1 = (S.slot_t[st.slot] - t) / h;
+        const double c1 = s1 * (1.0 - s1) * (1.0 / (1.0 - 2.0 * ODL_ROS_D));
+        const double c2 = s1 * (s1 - 2.0 * ODL_ROS_D) * (1.0 / (1.0 - 2.0 * ODL_ROS_D));
+        double yi[ODL_N];
+#pragma unroll
+        for (int i = 0; i < ODL_N; ++i) yi[i] = st.y[i] + h * (c1 * k1[i] + c2 * k2[i]);
+        sink(st.slot, yi);
+        ++st.slot;
+      } while (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew);
+    }
+#pragma unroll
+    for (int i = 0; i < ODL_N; ++i) { st.y[i] = yn[i]; st.k1[i] = F2[i]; }
+    st.t = tnew;
+    if (st.last_rejected) hnew = fmin(hnew, h);
+    st.last_rejected = false;
+    st.h = hnew;
+  } else {
+    double hnew;
+    if (err == err && finite_all && err < 3.0e38f) hnew = h * (double)fmaxf(0.2f, fminf(0.9f, fac));
+    else hnew = 0.2 * h;
+    st.last_rejected = true;
+    st.h = hnew;
+    if (!(fabs(hnew) > 4.0 * 2.220446049250313e-16 * fmax(fabs(t), fabs(st.tend)))) st.status = ODL_HUNDERFLOW;
+  }
+  if (st.nsteps >= O.max_steps && st.slot < D.n_slot && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
+}
+
+// solver dispatch: 0 = DOPRI5, 1 = ROS23, 2 = per-system choice (DOPRI5 until it reports stiffness)
+template <int SOLVER, class Sink>
+__device__ __forceinline__ void odl_attempt(OdlStepper& st, const double (&p)[ODL_P], const OdlShared& S, const OdlData& D,
+                                            const OdlOpts& O, Sink& sink, bool use_ros) {
+  if (SOLVER == 0) odl_dopri5_attempt(st, p, S, D, O, sink);
+  else if (SOLVER == 1) odl_ros23_attempt(st, p, S, D, O, sink);
+  else { if (use_ros) odl_ros23_attempt(st, p, S, D, O, sink); else odl_dopri5_attempt(st, p, S, D, O, sink); }
+}
+
 // fetch `want` lanes' worth of indices from a global counter with one atomic per warp
 __device__ __forceinline__ long long odl_fetch(unsigned long long* counter, bool want, int lane) {
   const unsigned m = __ballot_sync(ODL_FULL, want);
@@ -385,8 +553,8 @@ __device__ __forceinline__ long long odl_fetch(unsigned long long* counter, bool
 // ------------------------------------------------------------------------------------------------
 // Forward sweep: Framework.py:41-48 (_Fit_worker) for n parameter sets
 // ------------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
-odl_sweep_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
+template <int SOLVER>
+__device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& O, const OdlSweepArgs& A) {
   extern __shared__ double odl_smem[];
   const OdlShared S = odl_carve(odl_smem, D);
   odl_load_tables(S, D);
@@ -422,7 +590,8 @@ odl_sweep_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
         double r2 = 1.0 - ss / D.sstot;
         if (status != ODL_OK) { chi = __longlong_as_double(0x7ff8000000000000LL); r2 = chi; }
         else if (nv == 0) { chi = __longlong_as_double(0x7ff8000000000000LL); status |= ODL_ALLMASKED; }
-        A.chi[row] = chi; A.r2[row] = r2; A.status[row] = status; A.nsteps[row] = st.nsteps;
+        A.chi[row] = chi; A.r2[row] = r2; A.status[row] = status;
+        A.nsteps[row] = st.nsteps + (A.index ? A.nsteps[row] : 0);   // second (stiff) pass adds to the first
         if (st.status == ODL_STIFF && A.stiff_list) A.stiff_list[atomicAdd(A.stiff_count, 1)] = (int)row;
       }
     }
@@ -447,11 +616,15 @@ odl_sweep_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
     if (!__any_sync(ODL_FULL, active)) break;
     // ---- (C) one step attempt ----
     if (active && !done) {
-      odl_dopri5_attempt(st, p, S, D, O, sink);
+      odl_attempt<SOLVER>(st, p, S, D, O, sink, false);
       done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
     }
   }
 }
+extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
+odl_sweep_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<0>(D, O, A); }
+extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
+odl_sweep_ros23_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<1>(D, O, A); }
 
 // ------------------------------------------------------------------------------------------------
 // Full trajectories on the output grid (ModelFramework.integrate, Framework.py:622-683)
@@ -528,8 +701,8 @@ __device__ __forceinline__ double odl_mh_uniform(const OdlMcmcArgs& A, int chain
   return odl_u53(r.x, r.y);
 }
 
-extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
-odl_mcmc_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
+template <int SOLVER>
+__device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O, const OdlMcmcArgs& A) {
   extern __shared__ double odl_smem[];
   const OdlShared S = odl_carve(odl_smem, D);
   odl_load_tables(S, D);
@@ -549,7 +722,7 @@ odl_mcmc_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
   int accepts = 0, fails = 0;
   long long steps = 0;
   bool apriori = false;
-  bool active = false, done = false;
+  bool active = false, done = false, use_ros = false;
   if (has_chain) {
     if (A.it_begin == 1) {
       apriori = true;
@@ -583,8 +756,17 @@ odl_mcmc_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
         else if (st.status == ODL_OK) { my_chi = nan; my_r2 = 1.0 - ss / D.sstot; }   // np.ma.masked chi
       }
     }
+    if (SOLVER == 2 && fin && st.status == ODL_STIFF && !use_ros) {
+      // DOPRI5 gave up on a stiff proposal: redo this very solve with the Rosenbrock stepper
+      steps += st.nsteps;
+      use_ros = true;
+      odl_init_system(st, p, D, O, nullptr);
+      odl_emit_initial_slots(st, S, D, sink);
+      done = (st.slot >= D.n_slot);
+    } else
     if (fin) {
       steps += st.nsteps;
+      use_ros = false;
       if (st.status != ODL_OK) ++fails;
       double* cur = A.theta_cur + (size_t)chain * ODL_P;
       if (apriori) {
@@ -647,8 +829,14 @@ odl_mcmc_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
     }
     if (!__any_sync(ODL_FULL, active)) break;
     if (active && !done) {
-      odl_dopri5_attempt(st, p, S, D, O, sink);
+      odl_attempt<SOLVER>(st, p, S, D, O, sink, use_ros);
       done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
     }
   }
 }
+extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
+odl_mcmc_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<0>(D, O, A); }
+extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
+odl_mcmc_ros23_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<1>(D, O, A); }
+extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
+odl_mcmc_auto_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<2>(D, O, A); }

@@ -1,0 +1,104 @@
+"""The Rosenbrock-23 path (odl_*_ros23_kernel, solver='auto') on the stiff host-virus variant
+(BASELINE.json config 4: rates spanning 6 orders of magnitude) against scipy odeint (LSODA -> BDF)."""
+import numpy as np
+import pytest
+
+from oracle import odelib_oracle as orc
+from tests.helpers import STATES, SUMS, demo_df, device_model, golden, obs_tables_from_oracle, oracle_rhs
+
+pytestmark = pytest.mark.gpu
+
+
+def stiff_thetas(n, seed=0):
+    """two_i with tau ~ lognorm(0.5, 1e4), lam ~ lognorm(0.5, 1e-2); mu, phi, beta around (0.5, 1e-7, 50)."""
+    rng = np.random.default_rng(seed)
+    th = np.empty((n, 5))
+    th[:, 0] = 0.5 * np.exp(0.2 * rng.standard_normal(n))
+    th[:, 1] = 1e-7 * np.exp(0.2 * rng.standard_normal(n))
+    th[:, 2] = 50.0 * np.exp(0.2 * rng.standard_normal(n))
+    th[:, 3] = 1e-2 * np.exp(0.5 * rng.standard_normal(n))
+    th[:, 4] = 1e4 * np.exp(0.5 * rng.standard_normal(n))
+    return th
+
+
+def test_ros23_matches_lsoda_on_stiff_systems():
+    dm, tab = device_model("two_i")
+    theta = stiff_thetas(32)
+    out = dm.sweep(theta, solver="ros23", return_pred=True, max_steps=2000000)
+    assert np.all(out["status"] == 0)
+    rhs = oracle_rhs("two_i")
+    for k in range(len(theta)):
+        vec, chi, r2 = orc.solve_unit(rhs, theta[k], tab, 1e-11, 1e-11, mxstep=500000)
+        # order-2 method at rtol=atol=1.49e-8: global error of a few 1e-7 .. 1e-6 relative
+        np.testing.assert_allclose(out["pred"][k], vec, rtol=2e-5, atol=1e-3)
+        np.testing.assert_allclose(out["chi"][k], chi, rtol=2e-4)
+
+
+def test_ros23_tight_tolerance_converges_to_lsoda():
+    dm, tab = device_model("two_i")
+    theta = stiff_thetas(4, seed=1)
+    out = dm.sweep(theta, solver="ros23", rtol=1e-11, atol=1e-11, return_pred=True, max_steps=5000000)
+    assert np.all(out["status"] == 0)
+    rhs = oracle_rhs("two_i")
+    for k in range(len(theta)):
+        vec, chi, _ = orc.solve_unit(rhs, theta[k], tab, 1e-13, 1e-13, mxstep=500000)
+        np.testing.assert_allclose(out["pred"][k], vec, rtol=2e-7, atol=1e-4)
+        np.testing.assert_allclose(out["chi"][k], chi, rtol=2e-6)
+
+
+def test_ros23_agrees_with_dopri5_on_nonstiff_systems():
+    g = golden("two_i")
+    dm, _ = device_model("two_i")
+    theta = g["theta"][:8]
+    a = dm.sweep(theta, solver="dopri5", rtol=1e-10, atol=1e-10, return_pred=True)
+    b = dm.sweep(theta, solver="ros23", rtol=1e-10, atol=1e-10, return_pred=True, max_steps=5000000)
+    ok = (a["status"] == 0) & (b["status"] == 0) & np.all(a["pred"] > 1.0, axis=1)
+    assert ok.sum() >= 5
+    np.testing.assert_allclose(b["pred"][ok], a["pred"][ok], rtol=5e-6)
+
+
+def test_auto_routes_stiff_systems_and_keeps_the_rest():
+    dm, tab = device_model("two_i")
+    g = golden("two_i")
+    theta = np.vstack([stiff_thetas(24, seed=2), g["theta"][:24]])
+    plain = dm.sweep(theta, solver="dopri5", stiff_check=True, max_steps=2000000)
+    assert (plain["status"][:24] == 4).sum() >= 20            # DOPRI5 alone flags the stiff block
+    auto = dm.sweep(theta, solver="auto", return_pred=True, max_steps=2000000)
+    assert np.all(auto["status"][:24] == 0)
+    routed = plain["status"] == 4
+    ros = dm.sweep(theta[routed], solver="ros23", max_steps=2000000)
+    np.testing.assert_array_equal(auto["chi"][routed], ros["chi"])              # same kernel, same numbers
+    ref = dm.sweep(theta[~routed], solver="dopri5", max_steps=2000000)
+    np.testing.assert_array_equal(auto["chi"][~routed], ref["chi"])
+    # far fewer steps than the explicit method needs on the stiff block
+    full = dm.sweep(theta[:4], solver="dopri5", max_steps=2000000)
+    assert np.all(auto["nsteps"][:4] < full["nsteps"][:4])
+
+
+def test_mcmc_on_the_stiff_variant_ros23_and_auto():
+    """Config 4: chains on synthetic stiff data; ROS23 and auto make the same decisions on host streams."""
+    from odelib_b200 import demo_models
+    from odelib_b200.engine import DeviceModel
+    center = np.array([0.5, 1e-7, 50.0, 1e-2, 1e4])
+    tab0 = orc.build_tables(demo_df("two_i"), STATES["two_i"], SUMS["two_i"], 1000, {"S": 5236900})
+    # synthetic data: the reference odeint at the centre + log-normal noise (seed 0) on the demo's time points
+    vec, _, _ = orc.solve_unit(orc.two_i, center, tab0, 1e-12, 1e-12, mxstep=500000)
+    rng = np.random.default_rng(0)
+    df = demo_df("two_i").sort_values(by=["organism", "time"]).reset_index(drop=True)
+    df["abundance"] = vec * np.exp(0.2 * rng.standard_normal(len(vec)))
+    df["log_sigma"] = 0.2
+    tab = orc.build_tables(df, STATES["two_i"], SUMS["two_i"], 1000, {"S": 5236900, "V": 10981000})
+    f, n, P, groups = demo_models.MODELS["two_i"]
+    dm = DeviceModel(f, n, P, groups)
+    dm.set_data(obs_tables_from_oracle(tab), tab.y0)
+    C, nits = 8, 40
+    starts = center * np.exp(0.02 * rng.standard_normal((C, 5)))
+    z = 0.05 * rng.standard_normal((C, nits - 1, 5))
+    u = rng.random((C, nits - 1))
+    a = dm.mcmc(starts, nits=nits, rng_mode="host", z=z, u=u, solver="ros23", trace=True, max_steps=2000000)
+    b = dm.mcmc(starts, nits=nits, rng_mode="host", z=z, u=u, solver="auto", trace=True, max_steps=2000000)
+    assert np.isfinite(a["chinew"]).all() and a["fail_count"].sum() == 0
+    np.testing.assert_allclose(b["chinew"], a["chinew"], rtol=1e-9)     # auto ends up on the same ROS23 solves
+    assert np.array_equal(a["accepted"], b["accepted"])
+    ref = orc.mh_chain(orc.two_i, starts[0], tab, 5, nits=nits, z=z[0], u=u[0], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(a["chinew"][0], ref["chinew"], rtol=5e-4)

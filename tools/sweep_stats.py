@@ -1,0 +1,30 @@
+"""Dev tool (GPU): step-count distribution and timing of the 1M-set two_i prior sweep per solver mode."""
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from tests.helpers import device_model  # noqa: E402
+import bench  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+dm, tab = device_model("two_i")
+theta = torch.from_numpy(bench.prior_draws(n, 0, 0)).cuda()
+res = {}
+for mode, kw in (("dopri5_cap20k", dict(solver="dopri5", max_steps=20000)),
+                 ("auto", dict(solver="auto", max_steps=200000)),
+                 ("auto_min500", dict(solver="auto", max_steps=200000, stiff_min_steps=500))):
+    for rep in range(2):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        out = dm.sweep(theta, **kw)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    ns = out["nsteps"].cpu().numpy(); st = out["status"].cpu().numpy()
+    q = np.percentile(ns, [50, 90, 99, 99.9, 99.99, 100])
+    res[mode] = {"seconds": dt, "kernel_ms": dm.last_kernel_ms(), "solves_per_s": n / dt, "mean_steps": float(ns.mean()),
+                 "pct_50_90_99_999_9999_max": q.tolist(), "status_counts": {int(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))},
+                 "chi_finite": int(np.isfinite(out["chi"].cpu().numpy()).sum())}
+    print(mode, json.dumps(res[mode]), flush=True)
+json.dump(res, open("gpurun_out/sweep_stats.json", "w"), indent=1)
