@@ -41,7 +41,7 @@ extern "C" {
 
 enum { ODL_SUCCESS = 0, ODL_EINVAL = 1, ODL_ECUDA = 2, ODL_ECOMPILE = 3, ODL_ENODEVICE = 4, ODL_EIO = 5 };
 enum { ODL_MEM_HOST = 0, ODL_MEM_DEVICE = 1 };
-enum { ODL_SOLVER_DOPRI5 = 0, ODL_SOLVER_ROS23 = 1, ODL_SOLVER_AUTO = 2 };
+enum { ODL_SOLVER_DOPRI5 = 0, ODL_SOLVER_ROS23 = 1, ODL_SOLVER_AUTO = 2, ODL_SOLVER_RADAU5 = 3 };
 enum { ODL_RNG_PHILOX = 0, ODL_RNG_HOST_STREAMS = 1, ODL_RNG_FORCED = 2 };
 /* per-system status words */
 enum { ODL_ST_OK = 0, ODL_ST_MAXSTEPS = 1, ODL_ST_NONFINITE = 2, ODL_ST_HUNDERFLOW = 3, ODL_ST_STIFF = 4,
@@ -66,6 +66,8 @@ typedef struct odl_solver_opts {
   int solver;          /* ODL_SOLVER_* */
   int stiff_check;     /* DOPRI5: detect stiffness and stop with ODL_ST_STIFF */
   int stiff_min_steps; /* ... only while more than this many steps of the current size remain (0 = 2000) */
+  int pass_cap0;       /* ODL_SOLVER_AUTO: step cap of the first DOPRI5 pass (0 = 512) */
+  int pass_cap1;       /* ODL_SOLVER_AUTO: step cap of the second DOPRI5 pass (0 = 8192) */
 } odl_solver_opts;
 
 typedef struct odl_mcmc_opts {

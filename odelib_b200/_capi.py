@@ -33,7 +33,8 @@ class BuildOpts(C.Structure):
 
 class SolverOpts(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("h0", C.c_double), ("hmax", C.c_double),
-                ("max_steps", C.c_int), ("solver", C.c_int), ("stiff_check", C.c_int), ("stiff_min_steps", C.c_int)]
+                ("max_steps", C.c_int), ("solver", C.c_int), ("stiff_check", C.c_int), ("stiff_min_steps", C.c_int),
+                ("pass_cap0", C.c_int), ("pass_cap1", C.c_int)]
 
 
 class McmcOpts(C.Structure):

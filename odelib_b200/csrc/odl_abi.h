@@ -50,8 +50,8 @@ struct OdlSweepArgs {
   int* nsteps;                   // [n]  attempted steps
   double* pred;                  // optional [n][n_obs] predictions at the observation rows
   unsigned long long* counter;   // work counter, zeroed by the host before launch
-  int* stiff_list;               // optional: indices of systems that bailed out with ODL_STIFF
-  int* stiff_count;
+  int* defer_list[2];            // optional: rows that stopped with [0] ODL_MAXSTEPS, [1] ODL_STIFF are appended
+  int* defer_count[2];           //           here for a later pass (device-side lists, no host round trip)
 };
 
 struct OdlTrajArgs {

@@ -132,6 +132,7 @@ struct odl_model {
   CUmodule mod = nullptr;
   CUfunction k_sweep = nullptr, k_traj = nullptr, k_mcmc = nullptr;
   CUfunction k_sweep_ros = nullptr, k_mcmc_ros = nullptr, k_mcmc_auto = nullptr;
+  CUfunction k_sweep_radau = nullptr, k_mcmc_radau = nullptr;
   Tables data, grid;
   DevBuf counter;
   DevBuf scratch[16];
@@ -248,7 +249,8 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
   struct { const char* name; CUfunction* fn; bool required; } ks[] = {
       {"odl_sweep_kernel", &m->k_sweep, true}, {"odl_traj_kernel", &m->k_traj, true}, {"odl_mcmc_kernel", &m->k_mcmc, true},
       {"odl_sweep_ros23_kernel", &m->k_sweep_ros, true}, {"odl_mcmc_ros23_kernel", &m->k_mcmc_ros, true},
-      {"odl_mcmc_auto_kernel", &m->k_mcmc_auto, true}};
+      {"odl_mcmc_auto_kernel", &m->k_mcmc_auto, true}, {"odl_sweep_radau5_kernel", &m->k_sweep_radau, true},
+      {"odl_mcmc_radau5_kernel", &m->k_mcmc_radau, true}};
   for (auto& k : ks) {
     CUresult r = g_drv.ModuleGetFunction(k.fn, m->mod, k.name);
     if (r != CUDA_SUCCESS) {
@@ -258,7 +260,7 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
   }
   if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
     return bail(fail(ODL_ECUDA, "cudaEventCreate failed"));
-  if ((rc = m->counter.ensure(256))) return bail(rc);
+  if ((rc = m->counter.ensure(512))) return bail(rc);
   m->on_gpu = true;
   *out = m;
   return 0;
@@ -288,6 +290,8 @@ static CUfunction kernel_by_name(const odl_model* m, const char* k) {
   if (!strcmp(k, "sweep_ros23")) return m->k_sweep_ros;
   if (!strcmp(k, "mcmc_ros23")) return m->k_mcmc_ros;
   if (!strcmp(k, "mcmc_auto")) return m->k_mcmc_auto;
+  if (!strcmp(k, "sweep_radau5")) return m->k_sweep_radau;
+  if (!strcmp(k, "mcmc_radau5")) return m->k_mcmc_radau;
   return nullptr;
 }
 
@@ -447,7 +451,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   if (n < 0 || (n > 0 && (!theta || !chi || !r2 || !status || !nsteps))) return fail(ODL_EINVAL, "odl_sweep: null buffer");
   if (n == 0) return 0;
   const int solver = so ? so->solver : ODL_SOLVER_DOPRI5;
-  if (solver != ODL_SOLVER_DOPRI5 && !m->k_sweep_ros) return fail(ODL_EINVAL, "odl_sweep: ROS23 kernels are not in this build");
+  if (solver < 0 || solver > ODL_SOLVER_RADAU5) return fail(ODL_EINVAL, "odl_sweep: unknown solver");
   ODL_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
   Staging st{m, s, 0, mem};
@@ -460,45 +464,67 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   if ((rc = st.inout(nsteps, (size_t)n, &A.nsteps, false))) return rc;
   if ((rc = st.inout(pred_or_null, (size_t)n * m->data.d.n_obs, &A.pred, false))) return rc;
   A.n = n; A.index = nullptr; A.index_count = nullptr;
-  A.counter = static_cast<unsigned long long*>(m->counter.p);
-  int* stiff_count = reinterpret_cast<int*>(static_cast<char*>(m->counter.p) + 64);
-  unsigned long long* counter2 = reinterpret_cast<unsigned long long*>(static_cast<char*>(m->counter.p) + 128);
-  A.stiff_list = nullptr; A.stiff_count = stiff_count;
+  // counter block (zeroed per call): [0] work counter pass 0, [64] count of list A, [128] work counter pass 1,
+  // [192] count of list B, [256] work counter pass 2
+  char* cb = static_cast<char*>(m->counter.p);
+  auto ctr = [&](int off) { return reinterpret_cast<unsigned long long*>(cb + off); };
+  auto cnt = [&](int off) { return reinterpret_cast<int*>(cb + off); };
+  A.counter = ctr(0);
   OdlOpts O; fill_opts(O, so);
-  const bool autosw = (solver == ODL_SOLVER_AUTO);
-  if (autosw) {
-    O.stiff_check = 1;
-    DevBuf& b = m->scratch[st.next++];
-    if ((rc = b.ensure((size_t)n * sizeof(int)))) return rc;
-    A.stiff_list = static_cast<int*>(b.p);
-  }
-  ODL_CUDA(cudaMemsetAsync(m->counter.p, 0, 256, s));
+  ODL_CUDA(cudaMemsetAsync(m->counter.p, 0, 512, s));
   OdlData D = m->data.d;
-  const size_t smem = smem_bytes(D, m->block);
-  CUfunction f = (solver == ODL_SOLVER_ROS23) ? m->k_sweep_ros : m->k_sweep;
-  if (smem > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
-  int per_sm = 0;
-  ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, m->block, smem));
-  if (per_sm < 1) return fail(ODL_ECUDA, "sweep kernel does not fit on an SM (shared memory / registers)");
-  long long want = (n + m->block - 1) / m->block;
-  unsigned grid = (unsigned)std::min<long long>(want, (long long)per_sm * m->sm_count);
+  auto go = [&](CUfunction f, const OdlOpts& Ox, const OdlSweepArgs& Ax, unsigned block, long long items) -> int {
+    const size_t smem = smem_bytes(D, (int)block);
+    if (smem > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+    int per_sm = 0;
+    ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, (int)block, smem));
+    if (per_sm < 1) return fail(ODL_ECUDA, "sweep kernel does not fit on an SM (shared memory / registers)");
+    long long want = (items + block - 1) / block;
+    unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)per_sm * m->sm_count));
+    OdlData Dl = D; OdlOpts Ol = Ox; OdlSweepArgs Al = Ax;
+    void* params[] = {&Dl, &Ol, &Al};
+    return launch(m, f, grid, block, smem, s, params);
+  };
   ODL_CUDA(cudaEventRecord(m->ev0, s));
-  void* params[] = {&D, &O, &A};
-  if ((rc = launch(m, f, grid, m->block, smem, s, params))) return rc;
-  if (autosw) {
-    // second pass: the systems DOPRI5 flagged as stiff, read from the device-side list (no host sync)
-    OdlSweepArgs B = A;
-    B.index = A.stiff_list; B.index_count = stiff_count; B.counter = counter2;
-    B.stiff_list = nullptr; B.stiff_count = stiff_count;
+  if (solver != ODL_SOLVER_AUTO) {
+    A.defer_list[0] = A.defer_list[1] = nullptr; A.defer_count[0] = A.defer_count[1] = nullptr;
+    CUfunction f1 = solver == ODL_SOLVER_ROS23 ? m->k_sweep_ros : (solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau : m->k_sweep);
+    if ((rc = go(f1, O, A, solver == ODL_SOLVER_RADAU5 ? 32u : (unsigned)m->block, n))) return rc;
+  } else {
+    // Cohort passes (no host synchronisation in between; list lengths stay on the device):
+    //   pass 0  DOPRI5, every system, at most cap0 attempted steps; the few that need more go to list A,
+    //           those Hairer's test calls stiff go straight to list B
+    //   pass 1  DOPRI5 on list A with cap1; still unfinished or stiff -> list B
+    //   pass 2  Radau5 on list B, up to max_steps  (pass_cap1 <= pass_cap0 skips pass 1: list A is list B)
+    // Step counts are heavy-tailed (two_i prior: median 56, mean 103, p99.9 3200, max > 1e5): capping a pass
+    // bounds how long the lanes of a warp wait for their slowest neighbour once the work counter runs dry.
+    DevBuf& la = m->scratch[st.next++];
+    DevBuf& lb = m->scratch[st.next++];
+    if ((rc = la.ensure((size_t)n * sizeof(int)))) return rc;
+    if ((rc = lb.ensure((size_t)n * sizeof(int)))) return rc;
+    int* listA = static_cast<int*>(la.p);
+    int* listB = static_cast<int*>(lb.p);
+    const int cap0 = so && so->pass_cap0 > 0 ? so->pass_cap0 : 512;
+    const int cap1 = so && so->pass_cap1 > 0 ? so->pass_cap1 : 8192;
+    OdlOpts O0 = O; O0.stiff_check = 1; O0.max_steps = std::min(cap0, O.max_steps);
+    const bool two_dopri = cap1 > cap0;
+    OdlSweepArgs A0 = A;
+    A0.defer_list[0] = two_dopri ? listA : listB; A0.defer_count[0] = two_dopri ? cnt(64) : cnt(192);
+    A0.defer_list[1] = listB; A0.defer_count[1] = cnt(192);
+    if ((rc = go(m->k_sweep, O0, A0, (unsigned)m->block, n))) return rc;
+    if (two_dopri) {
+      OdlOpts O1 = O; O1.stiff_check = 1; O1.max_steps = std::min(cap1, O.max_steps);
+      OdlSweepArgs A1 = A;
+      A1.index = listA; A1.index_count = cnt(64); A1.counter = ctr(128);
+      A1.defer_list[0] = listB; A1.defer_count[0] = cnt(192);
+      A1.defer_list[1] = listB; A1.defer_count[1] = cnt(192);
+      if ((rc = go(m->k_sweep, O1, A1, 32u, std::max<long long>(32, n / 16)))) return rc;
+    }
     OdlOpts O2 = O; O2.stiff_check = 0;
-    CUfunction f2 = m->k_sweep_ros;
-    int per_sm2 = 0;
-    if (smem > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(f2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
-    ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, f2, m->block, smem));
-    if (per_sm2 < 1) return fail(ODL_ECUDA, "ROS23 sweep kernel does not fit on an SM");
-    unsigned grid2 = (unsigned)std::min<long long>(want, (long long)per_sm2 * m->sm_count);
-    void* params2[] = {&D, &O2, &B};
-    if ((rc = launch(m, f2, grid2, m->block, smem, s, params2))) return rc;
+    OdlSweepArgs A2 = A;
+    A2.index = listB; A2.index_count = cnt(192); A2.counter = ctr(256);
+    A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
+    if ((rc = go(m->k_sweep_radau, O2, A2, 32u, std::max<long long>(32, n / 16)))) return rc;
   }
   ODL_CUDA(cudaEventRecord(m->ev1, s));
   m->timed = true;
@@ -543,7 +569,7 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   if (mo->n_chain < 1 || mo->nits < 2) return fail(ODL_EINVAL, "odl_mcmc: need n_chain >= 1 and nits >= 2");
   if (mo->n_walk < 0 || mo->n_walk > m->n_param || (mo->n_walk > 0 && !mo->walk)) return fail(ODL_EINVAL, "odl_mcmc: bad walk list");
   const int solver = so ? so->solver : ODL_SOLVER_DOPRI5;
-  if (solver != ODL_SOLVER_DOPRI5 && !m->k_mcmc_ros) return fail(ODL_EINVAL, "odl_mcmc: ROS23 kernels are not in this build");
+  if (solver < 0 || solver > ODL_SOLVER_RADAU5) return fail(ODL_EINVAL, "odl_mcmc: unknown solver");
   const int P = m->n_param, C = mo->n_chain, n_iter = mo->nits - 1;
   int it_begin = mo->it_begin, it_end = mo->it_end;
   if (it_begin == 0 && it_end == 0) { it_begin = 1; it_end = mo->nits; }
@@ -584,9 +610,11 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   // few chains: spread them over the SMs with one warp per CTA; many chains: full CTAs
   unsigned block = (unsigned)m->block;
   while (block > 32 && (long long)C < (long long)m->sm_count * block * 2) block /= 2;
+  if (solver == ODL_SOLVER_RADAU5) block = 32;              // that kernel is compiled for one warp per CTA
   const size_t smem = smem_bytes(D, (int)block);
   unsigned grid = (unsigned)((C + block - 1) / block);
-  CUfunction f = (solver == ODL_SOLVER_DOPRI5) ? m->k_mcmc : (solver == ODL_SOLVER_ROS23 ? m->k_mcmc_ros : m->k_mcmc_auto);
+  CUfunction f = (solver == ODL_SOLVER_DOPRI5) ? m->k_mcmc : (solver == ODL_SOLVER_ROS23 ? m->k_mcmc_ros :
+                 (solver == ODL_SOLVER_RADAU5 ? m->k_mcmc_radau : m->k_mcmc_auto));
   if (solver == ODL_SOLVER_AUTO) O.stiff_check = 1;
   ODL_CUDA(cudaEventRecord(m->ev0, s));
   void* params[] = {&D, &O, &A};

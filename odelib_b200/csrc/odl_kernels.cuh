@@ -51,6 +51,7 @@
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool odl_finite(double x) { return fabs(x) <= ODL_DBL_MAX; }
 
+#ifndef ODL_HOST_HARNESS
 __device__ __forceinline__ double odl_shfl_xor(double v, int m) {
   int lo = __double2loint(v), hi = __double2hiint(v);
   lo = __shfl_xor_sync(ODL_FULL, lo, m);
@@ -62,6 +63,8 @@ __device__ __forceinline__ double odl_warp_sum(double v) {
   for (int m = 16; m > 0; m >>= 1) v += odl_shfl_xor(v, m);
   return v;
 }
+
+#endif  // ODL_HOST_HARNESS
 
 // Philox4x32-10 (Salmon et al., SC'11) -- counter-based, one independent stream per (chain, iteration)
 struct OdlPhilox { unsigned int x, y, z, w; };
@@ -100,6 +103,7 @@ __device__ __forceinline__ OdlShared odl_carve(double* base, const OdlData& D) {
   S.stage = S.lin + D.n_obs + (D.n_obs + 1) / 2;
   return S;
 }
+#ifndef ODL_HOST_HARNESS
 __device__ __forceinline__ void odl_load_tables(const OdlShared& S, const OdlData& D) {
   for (int i = threadIdx.x; i < D.n_slot; i += blockDim.x) S.slot_t[i] = D.slot_t[i];
   for (int i = threadIdx.x; i < D.n_obs; i += blockDim.x) {
@@ -133,6 +137,8 @@ __device__ __forceinline__ void odl_score(const OdlShared& S, const OdlData& D, 
   for (int m = 16; m > 0; m >>= 1) k += __shfl_xor_sync(ODL_FULL, k, m);
   nvalid = k;
 }
+
+#endif  // ODL_HOST_HARNESS
 
 // ------------------------------------------------------------------------------------------------
 // Dormand-Prince 5(4), coefficients of Hairer/Norsett/Wanner (dopri5.f); PI step controller.
@@ -529,15 +535,308 @@ __device__ __forceinline__ void odl_ros23_attempt(OdlStepper& st, const double (
   if (st.nsteps >= O.max_steps && st.slot < D.n_slot && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
 }
 
-// solver dispatch: 0 = DOPRI5, 1 = ROS23, 2 = per-system choice (DOPRI5 until it reports stiffness)
+
+// ------------------------------------------------------------------------------------------------
+// Radau IIA, 3 stages, order 5 (Hairer & Wanner, Solving ODEs II, ch. IV.8: RADAU5) -- the high-order
+// stiff stepper.  ROS23 is second order and needs 1e4-1e5 steps at rtol 1.5e-8 on the stiff corner of
+// the demo priors where LSODA's BDF needs a few hundred; Radau5 needs about as few as LSODA.
+// Simplified Newton on the transformed collocation system (one real and one complex n x n LU per
+// step, factorised in registers), analytic Jacobian refreshed every step, embedded third-order error
+// estimate, Gustafsson's predictive controller, collocation polynomial as dense output and as the
+// starting guess of the next step.
+// ------------------------------------------------------------------------------------------------
+#define ODL_RAD_MU 3.637834252744496               /* real eigenvalue of A^-1 */
+#define ODL_RAD_ALPHA 2.6810828736277523           /* complex pair alpha -+ i beta */
+#define ODL_RAD_BETA 3.050430199247411
+#define ODL_RAD_C0 0.15505102572168222             /* (4 - sqrt 6)/10 */
+#define ODL_RAD_C1 0.6449489742783178              /* (4 + sqrt 6)/10 */
+#define ODL_RAD_NEWTON 6
+
+struct OdlCLU {                  // complex LU in split storage
+  double ar[ODL_N][ODL_N], ai[ODL_N][ODL_N];
+  double ir[ODL_N], ii[ODL_N];   // reciprocal pivots
+  unsigned long long swaps;
+};
+__device__ __forceinline__ void odl_clu_factor(OdlCLU& F) {
+  unsigned long long sw = 0ull;
+  int bit = 0;
+#pragma unroll
+  for (int k = 0; k < ODL_N; ++k) {
+#pragma unroll
+    for (int i = k + 1; i < ODL_N; ++i) {
+      const bool s = (fabs(F.ar[i][k]) + fabs(F.ai[i][k])) > (fabs(F.ar[k][k]) + fabs(F.ai[k][k]));
+      if (s) sw |= (1ull << (bit & 63));
+      ++bit;
+#pragma unroll
+      for (int j = 0; j < ODL_N; ++j) {
+        const double ur = F.ar[k][j], vr = F.ar[i][j], ui = F.ai[k][j], vi = F.ai[i][j];
+        F.ar[k][j] = s ? vr : ur; F.ar[i][j] = s ? ur : vr;
+        F.ai[k][j] = s ? vi : ui; F.ai[i][j] = s ? ui : vi;
+      }
+    }
+    const double pr = F.ar[k][k], pi = F.ai[k][k];
+    const double den = 1.0 / (pr * pr + pi * pi);
+    F.ir[k] = pr * den; F.ii[k] = -pi * den;
+#pragma unroll
+    for (int i = k + 1; i < ODL_N; ++i) {
+      const double lr = F.ar[i][k] * F.ir[k] - F.ai[i][k] * F.ii[k];
+      const double li = F.ar[i][k] * F.ii[k] + F.ai[i][k] * F.ir[k];
+      F.ar[i][k] = lr; F.ai[i][k] = li;
+#pragma unroll
+      for (int j = k + 1; j < ODL_N; ++j) {
+        F.ar[i][j] -= lr * F.ar[k][j] - li * F.ai[k][j];
+        F.ai[i][j] -= lr * F.ai[k][j] + li * F.ar[k][j];
+      }
+    }
+  }
+  F.swaps = sw;
+}
+__device__ __forceinline__ void odl_clu_solve(const OdlCLU& F, double (&br)[ODL_N], double (&bi)[ODL_N]) {
+  int bit = 0;
+#pragma unroll
+  for (int k = 0; k < ODL_N; ++k) {
+#pragma unroll
+    for (int i = k + 1; i < ODL_N; ++i) {
+      const bool s = (F.swaps >> (bit & 63)) & 1ull;
+      ++bit;
+      const double ur = br[k], vr = br[i], ui = bi[k], vi = bi[i];
+      br[k] = s ? vr : ur; br[i] = s ? ur : vr;
+      bi[k] = s ? vi : ui; bi[i] = s ? ui : vi;
+    }
+#pragma unroll
+    for (int i = k + 1; i < ODL_N; ++i) {
+      br[i] -= F.ar[i][k] * br[k] - F.ai[i][k] * bi[k];
+      bi[i] -= F.ar[i][k] * bi[k] + F.ai[i][k] * br[k];
+    }
+  }
+#pragma unroll
+  for (int k = ODL_N - 1; k >= 0; --k) {
+    double xr = br[k], xi = bi[k];
+#pragma unroll
+    for (int j = k + 1; j < ODL_N; ++j) {
+      xr -= F.ar[k][j] * br[j] - F.ai[k][j] * bi[j];
+      xi -= F.ar[k][j] * bi[j] + F.ai[k][j] * br[j];
+    }
+    br[k] = xr * F.ir[k] - xi * F.ii[k];
+    bi[k] = xr * F.ii[k] + xi * F.ir[k];
+  }
+}
+
+struct OdlRadauAux {
+  double Q[3][ODL_N];            // collocation polynomial of the last accepted step: y(t0 + x h) = y0 + Q0 x + Q1 x^2 + Q2 x^3
+  double h_old;
+  float err_old;
+  bool have_sol, rejected;
+  __device__ __forceinline__ void reset() { have_sol = false; rejected = false; h_old = 0.0; err_old = 0.f; }
+};
+struct OdlNoAux { __device__ __forceinline__ void reset() {} };
+
+template <class Sink>
+__device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& ax, const double (&p)[ODL_P],
+                                                   const OdlShared& S, const OdlData& D, const OdlOpts& O, Sink& sink) {
+  static_assert(ODL_N * (ODL_N - 1) / 2 <= 64, "pivot mask holds at most 64 swap decisions (n <= 11)");
+  // transformation matrices of RADAU5 (eigen-decomposition of A^-1), TI = T^-1
+  const double T00 = 0.09443876248897524, T01 = -0.1412552950209542, T02 = 0.03002919410514742;
+  const double T10 = 0.2502131229653333, T11 = 0.20412935229379994, T12 = -0.3829421127572619;
+  // T2x = (1, 1, 0)
+  const double I00 = 4.178718591551904, I01 = 0.32768282076106237, I02 = 0.5233764454994495;
+  const double I10 = -4.178718591551904, I11 = -0.32768282076106237, I12 = 0.47662355450055044;
+  const double I20 = 0.5028726349457868, I21 = -2.571926949855605, I22 = 0.5960392048282249;
+  const double E0 = -10.048809399827414, E1 = 1.382142733160748, E2 = -0.3333333333333333;   // (-13 -+ 7 sqrt6)/3, -1/3
+  const double P00 = 10.048809399827414, P01 = -25.62959144707664, P02 = 15.580782047249224;
+  const double P10 = -1.382142733160748, P11 = 10.296258113743303, P12 = -8.914115380582556;
+  const double P20 = 0.3333333333333333, P21 = -2.6666666666666665, P22 = 3.3333333333333335;
+
+  const double t = st.t;
+  double h = st.h;
+  bool last = false;
+  if ((t + 1.01 * h - st.tend) > 0.0) { h = st.tend - t; last = true; }
+  ++st.nsteps;
+  const double mr = ODL_RAD_MU / h, ca = ODL_RAD_ALPHA / h, cb = -ODL_RAD_BETA / h;   // M_complex = ca + i cb
+  OdlLU R;
+  OdlCLU Cx;
+  {
+    double J[ODL_N][ODL_N];
+    odl_jac(st.y, t, p, J);
+#pragma unroll
+    for (int i = 0; i < ODL_N; ++i)
+#pragma unroll
+      for (int j = 0; j < ODL_N; ++j) {
+        R.a[i][j] = ((i == j) ? mr : 0.0) - J[i][j];
+        Cx.ar[i][j] = ((i == j) ? ca : 0.0) - J[i][j];
+        Cx.ai[i][j] = (i == j) ? cb : 0.0;
+      }
+  }
+  odl_lu_factor(R);
+  odl_clu_factor(Cx);
+
+  float rsc[ODL_N];
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i) rsc[i] = __frcp_rn((float)(O.atol + O.rtol * fabs(st.y[i])));
+  const float newton_tol = fmaxf((float)(10.0 * 2.220446049250313e-16 / O.rtol), fminf(0.03f, sqrtf((float)O.rtol)));
+
+  double Z0[ODL_N], Z1[ODL_N], Z2[ODL_N], W0[ODL_N], W1[ODL_N], W2[ODL_N];
+  if (ax.have_sol) {
+    const double r = h / ax.h_old;
+    const double x0 = 1.0 + r * ODL_RAD_C0, x1 = 1.0 + r * ODL_RAD_C1, x2 = 1.0 + r;
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) {
+      const double q0 = ax.Q[0][j], q1 = ax.Q[1][j], q2 = ax.Q[2][j];
+      const double one = q0 + q1 + q2;
+      Z0[j] = x0 * (q0 + x0 * (q1 + x0 * q2)) - one;
+      Z1[j] = x1 * (q0 + x1 * (q1 + x1 * q2)) - one;
+      Z2[j] = x2 * (q0 + x2 * (q1 + x2 * q2)) - one;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) { Z0[j] = 0.0; Z1[j] = 0.0; Z2[j] = 0.0; }
+  }
+#pragma unroll
+  for (int j = 0; j < ODL_N; ++j) {
+    W0[j] = I00 * Z0[j] + I01 * Z1[j] + I02 * Z2[j];
+    W1[j] = I10 * Z0[j] + I11 * Z1[j] + I12 * Z2[j];
+    W2[j] = I20 * Z0[j] + I21 * Z1[j] + I22 * Z2[j];
+  }
+  bool converged = false;
+  int n_iter = 0;
+  float rate = -1.f, dwn_old = -1.f;
+  for (int k = 0; k < ODL_RAD_NEWTON; ++k) {
+    ++n_iter;
+    double F0[ODL_N], F1[ODL_N], F2[ODL_N], yt[ODL_N];
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) yt[j] = st.y[j] + Z0[j];
+    odl_rhs(yt, t + ODL_RAD_C0 * h, p, F0);
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) yt[j] = st.y[j] + Z1[j];
+    odl_rhs(yt, t + ODL_RAD_C1 * h, p, F1);
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) yt[j] = st.y[j] + Z2[j];
+    odl_rhs(yt, t + h, p, F2);
+    bool fin = true;
+    double dr[ODL_N], dcr[ODL_N], dci[ODL_N];
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) {
+      fin = fin && odl_finite(F0[j]) && odl_finite(F1[j]) && odl_finite(F2[j]);
+      dr[j] = I00 * F0[j] + I01 * F1[j] + I02 * F2[j] - mr * W0[j];
+      dcr[j] = I10 * F0[j] + I11 * F1[j] + I12 * F2[j] - (ca * W1[j] - cb * W2[j]);
+      dci[j] = I20 * F0[j] + I21 * F1[j] + I22 * F2[j] - (cb * W1[j] + ca * W2[j]);
+    }
+    if (!fin) break;
+    odl_lu_solve(R, dr);
+    odl_clu_solve(Cx, dcr, dci);
+    float nrm = 0.f;
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) {
+      const float a = (float)dr[j] * rsc[j], b = (float)dcr[j] * rsc[j], c = (float)dci[j] * rsc[j];
+      nrm += a * a + b * b + c * c;
+    }
+    const float dwn = sqrtf(nrm * (1.0f / (3 * ODL_N)));
+    if (!(dwn == dwn)) break;
+    if (dwn_old >= 0.f) rate = dwn / dwn_old;
+    if (rate >= 0.f && (rate >= 1.f || __powf(rate, (float)(ODL_RAD_NEWTON - k)) / (1.f - rate) * dwn > newton_tol)) break;
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) {
+      W0[j] += dr[j]; W1[j] += dcr[j]; W2[j] += dci[j];
+      Z0[j] = T00 * W0[j] + T01 * W1[j] + T02 * W2[j];
+      Z1[j] = T10 * W0[j] + T11 * W1[j] + T12 * W2[j];
+      Z2[j] = W0[j] + W1[j];
+    }
+    if (dwn == 0.f || (rate >= 0.f && rate / (1.f - rate) * dwn < newton_tol)) { converged = true; break; }
+    dwn_old = dwn;
+  }
+  const double hmin = 4.0 * 2.220446049250313e-16 * fmax(fabs(t), fabs(st.tend));
+  if (!converged) {
+    st.h = 0.5 * h;
+    if (!(st.h > hmin)) st.status = ODL_HUNDERFLOW;
+    if (st.nsteps >= O.max_steps && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
+    return;
+  }
+  double yn[ODL_N], ze[ODL_N], er[ODL_N];
+  const double rh = 1.0 / h;
+  float errsq = 0.f;
+  bool finite_all = true;
+#pragma unroll
+  for (int j = 0; j < ODL_N; ++j) {
+    yn[j] = st.y[j] + Z2[j];
+    ze[j] = (E0 * Z0[j] + E1 * Z1[j] + E2 * Z2[j]) * rh;
+    er[j] = st.k1[j] + ze[j];
+    finite_all = finite_all && odl_finite(yn[j]);
+  }
+  odl_lu_solve(R, er);
+  float rs2[ODL_N];
+#pragma unroll
+  for (int j = 0; j < ODL_N; ++j) {
+    rs2[j] = __frcp_rn((float)(O.atol + O.rtol * fmax(fabs(st.y[j]), fabs(yn[j]))));
+    const float a = (float)er[j] * rs2[j];
+    errsq += a * a;
+  }
+  float err = sqrtf(errsq * (1.0f / ODL_N));
+  const float safety = 0.9f * (2 * ODL_RAD_NEWTON + 1) / (float)(2 * ODL_RAD_NEWTON + n_iter);
+  if (ax.rejected && err > 1.0f) {
+    double yt[ODL_N], fe[ODL_N];
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) yt[j] = st.y[j] + er[j];
+    odl_rhs(yt, t, p, fe);
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) er[j] = fe[j] + ze[j];
+    odl_lu_solve(R, er);
+    errsq = 0.f;
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) { const float a = (float)er[j] * rs2[j]; errsq += a * a; }
+    err = sqrtf(errsq * (1.0f / ODL_N));
+  }
+  // Gustafsson: factor = min(1, h/h_old (err_old/err)^(1/4)) err^(-1/4)
+  float mult = 1.f;
+  if (ax.have_sol && ax.err_old > 0.f && err > 0.f) mult = (float)(h / ax.h_old) * __powf(ax.err_old / err, 0.25f);
+  float factor = fminf(1.f, mult) * __powf(err, -0.25f);
+  if (!(err > 0.f)) factor = 10.f;
+  if (!(err <= 1.0f) || !finite_all) {
+    double hnew = (err == err && err < 3.0e38f) ? h * (double)fmaxf(0.2f, fminf(0.95f, safety * factor)) : 0.2 * h;
+    ax.rejected = true;
+    st.h = hnew;
+    if (!(hnew > hmin)) st.status = ODL_HUNDERFLOW;
+    if (st.nsteps >= O.max_steps && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
+    return;
+  }
+  // ---- accepted ----
+  const double tnew = last ? st.tend : t + h;
+#pragma unroll
+  for (int j = 0; j < ODL_N; ++j) {
+    ax.Q[0][j] = P00 * Z0[j] + P10 * Z1[j] + P20 * Z2[j];
+    ax.Q[1][j] = P01 * Z0[j] + P11 * Z1[j] + P21 * Z2[j];
+    ax.Q[2][j] = P02 * Z0[j] + P12 * Z1[j] + P22 * Z2[j];
+  }
+  while (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew) {
+    const double x = (S.slot_t[st.slot] - t) * rh;
+    double yi[ODL_N];
+#pragma unroll
+    for (int j = 0; j < ODL_N; ++j) yi[j] = st.y[j] + x * (ax.Q[0][j] + x * (ax.Q[1][j] + x * ax.Q[2][j]));
+    sink(st.slot, yi);
+    ++st.slot;
+  }
+#pragma unroll
+  for (int j = 0; j < ODL_N; ++j) st.y[j] = yn[j];
+  odl_rhs(st.y, tnew, p, st.k1);
+  st.t = tnew;
+  ax.h_old = h; ax.err_old = fmaxf(err, 1e-10f); ax.have_sol = true; ax.rejected = false;
+  st.h = h * (double)fminf(10.f, fmaxf(0.2f, safety * factor));
+  if (st.nsteps >= O.max_steps && st.slot < D.n_slot && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
+}
+
+template <int SOLVER> struct OdlAuxOf { typedef OdlNoAux type; };
+template <> struct OdlAuxOf<3> { typedef OdlRadauAux type; };
+
+// solver dispatch: 0 = DOPRI5, 1 = ROS23, 2 = per-system choice (DOPRI5 until it reports stiffness), 3 = Radau5
 template <int SOLVER, class Sink>
-__device__ __forceinline__ void odl_attempt(OdlStepper& st, const double (&p)[ODL_P], const OdlShared& S, const OdlData& D,
-                                            const OdlOpts& O, Sink& sink, bool use_ros) {
-  if (SOLVER == 0) odl_dopri5_attempt(st, p, S, D, O, sink);
-  else if (SOLVER == 1) odl_ros23_attempt(st, p, S, D, O, sink);
+__device__ __forceinline__ void odl_attempt(OdlStepper& st, typename OdlAuxOf<SOLVER>::type& ax, const double (&p)[ODL_P],
+                                            const OdlShared& S, const OdlData& D, const OdlOpts& O, Sink& sink, bool use_ros) {
+  if constexpr (SOLVER == 0) odl_dopri5_attempt(st, p, S, D, O, sink);
+  else if constexpr (SOLVER == 1) odl_ros23_attempt(st, p, S, D, O, sink);
+  else if constexpr (SOLVER == 3) odl_radau5_attempt(st, ax, p, S, D, O, sink);
   else { if (use_ros) odl_ros23_attempt(st, p, S, D, O, sink); else odl_dopri5_attempt(st, p, S, D, O, sink); }
 }
 
+#ifndef ODL_HOST_HARNESS
 // fetch `want` lanes' worth of indices from a global counter with one atomic per warp
 __device__ __forceinline__ long long odl_fetch(unsigned long long* counter, bool want, int lane) {
   const unsigned m = __ballot_sync(ODL_FULL, want);
@@ -564,6 +863,7 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
   const long long n = A.index_count ? (long long)(*A.index_count) : A.n;
 
   OdlStepper st;
+  typename OdlAuxOf<SOLVER>::type ax;
   double p[ODL_P];
   long long sys = -1;            // slot in the work list
   long long row = -1;            // row of theta / outputs
@@ -591,8 +891,9 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
         if (status != ODL_OK) { chi = __longlong_as_double(0x7ff8000000000000LL); r2 = chi; }
         else if (nv == 0) { chi = __longlong_as_double(0x7ff8000000000000LL); status |= ODL_ALLMASKED; }
         A.chi[row] = chi; A.r2[row] = r2; A.status[row] = status;
-        A.nsteps[row] = st.nsteps + (A.index ? A.nsteps[row] : 0);   // second (stiff) pass adds to the first
-        if (st.status == ODL_STIFF && A.stiff_list) A.stiff_list[atomicAdd(A.stiff_count, 1)] = (int)row;
+        A.nsteps[row] = st.nsteps;
+        if (st.status == ODL_MAXSTEPS && A.defer_list[0]) A.defer_list[0][atomicAdd(A.defer_count[0], 1)] = (int)row;
+        if (st.status == ODL_STIFF && A.defer_list[1]) A.defer_list[1][atomicAdd(A.defer_count[1], 1)] = (int)row;
       }
     }
     if (fin) { active = false; done = false; want = true; }
@@ -607,6 +908,7 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
 #pragma unroll
           for (int q = 0; q < ODL_P; ++q) p[q] = A.theta[row * ODL_P + q];
           odl_init_system(st, p, D, O, nullptr);
+          ax.reset();
           odl_emit_initial_slots(st, S, D, sink);
           active = true;
           done = (st.slot >= D.n_slot);
@@ -616,7 +918,7 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
     if (!__any_sync(ODL_FULL, active)) break;
     // ---- (C) one step attempt ----
     if (active && !done) {
-      odl_attempt<SOLVER>(st, p, S, D, O, sink, false);
+      odl_attempt<SOLVER>(st, ax, p, S, D, O, sink, false);
       done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
     }
   }
@@ -625,6 +927,8 @@ extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
 odl_sweep_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<0>(D, O, A); }
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
 odl_sweep_ros23_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<1>(D, O, A); }
+extern "C" __global__ void __launch_bounds__(32, 1)
+odl_sweep_radau5_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<3>(D, O, A); }
 
 // ------------------------------------------------------------------------------------------------
 // Full trajectories on the output grid (ModelFramework.integrate, Framework.py:622-683)
@@ -714,6 +1018,8 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
 
   OdlStepper st;
+  typename OdlAuxOf<SOLVER>::type ax;
+  ax.reset();
   double p[ODL_P];
   st.status = ODL_OK; st.nsteps = 0; st.slot = 0;
   // it == it_begin-1 marks the a-priori solve of a fresh chain (Samplers.py:88-90)
@@ -761,6 +1067,7 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
       steps += st.nsteps;
       use_ros = true;
       odl_init_system(st, p, D, O, nullptr);
+      ax.reset();
       odl_emit_initial_slots(st, S, D, sink);
       done = (st.slot >= D.n_slot);
     } else
@@ -816,6 +1123,7 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
       if (it < A.it_end) {
         odl_propose(p, A, chain, it);
         odl_init_system(st, p, D, O, nullptr);
+        ax.reset();
         odl_emit_initial_slots(st, S, D, sink);
         done = (st.slot >= D.n_slot);
       } else {
@@ -829,7 +1137,7 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
     }
     if (!__any_sync(ODL_FULL, active)) break;
     if (active && !done) {
-      odl_attempt<SOLVER>(st, p, S, D, O, sink, use_ros);
+      odl_attempt<SOLVER>(st, ax, p, S, D, O, sink, use_ros);
       done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
     }
   }
@@ -840,3 +1148,6 @@ extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
 odl_mcmc_ros23_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<1>(D, O, A); }
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
 odl_mcmc_auto_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<2>(D, O, A); }
+extern "C" __global__ void __launch_bounds__(32, 1)
+odl_mcmc_radau5_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<3>(D, O, A); }
+#endif  // ODL_HOST_HARNESS

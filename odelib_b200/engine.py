@@ -128,15 +128,16 @@ class DeviceModel:
 
     # -- helpers -----------------------------------------------------------------------------------
     @staticmethod
-    def _solver_opts(rtol, atol, max_steps, solver, stiff_check, h0=0.0, hmax=0.0, stiff_min_steps=0):
+    def _solver_opts(rtol, atol, max_steps, solver, stiff_check, h0=0.0, hmax=0.0, stiff_min_steps=0, pass_caps=(0, 0)):
         so = _capi.SolverOpts()
         so.rtol = SCIPY_TOL if rtol is None else float(rtol)
         so.atol = SCIPY_TOL if atol is None else float(atol)
         so.h0, so.hmax = float(h0), float(hmax)
         so.max_steps = int(max_steps)
-        so.solver = {"dopri5": 0, "ros23": 1, "auto": 2}[solver] if isinstance(solver, str) else int(solver)
+        so.solver = {"dopri5": 0, "ros23": 1, "auto": 2, "radau5": 3}[solver] if isinstance(solver, str) else int(solver)
         so.stiff_check = 1 if stiff_check else 0
         so.stiff_min_steps = int(stiff_min_steps)
+        so.pass_cap0, so.pass_cap1 = int(pass_caps[0]), int(pass_caps[1])
         return so
 
     @staticmethod
@@ -146,11 +147,12 @@ class DeviceModel:
 
     # -- forward sweep: _Fit_worker (Framework.py:41-48) -------------------------------------------
     def sweep(self, theta, rtol=None, atol=None, max_steps=500000, solver="dopri5", stiff_check=False,
-              return_pred=False, out=None, stiff_min_steps=0):
+              return_pred=False, out=None, stiff_min_steps=0, pass_caps=(0, 0)):
         """theta [n, P] (numpy -> host path, torch cuda tensor -> device path).
 
         Returns dict(chi, r2, status, nsteps[, pred]) of the same kind as the input."""
-        so = self._solver_opts(rtol, atol, max_steps, solver, stiff_check, stiff_min_steps=stiff_min_steps)
+        so = self._solver_opts(rtol, atol, max_steps, solver, stiff_check, stiff_min_steps=stiff_min_steps,
+                               pass_caps=pass_caps)
         if _is_torch_cuda(theta):
             import torch
             th = theta.contiguous()

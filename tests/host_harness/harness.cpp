@@ -1,0 +1,62 @@
+// Host harness (TEST INFRASTRUCTURE ONLY): compiles the device steppers of odl_kernels.cuh with g++ so the
+// DOPRI5 / ROS23 / Radau5 step logic can be exercised against scipy on a GPU-less box.  Not part of the
+// product: nothing in odelib_b200/ loads this; the kernels and warp-collective code are compiled out.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define ODL_HOST_HARNESS 1
+#define __device__
+#define __forceinline__ inline
+#define __global__
+#define __launch_bounds__(...)
+static inline float __frcp_rn(float x) { return 1.0f / x; }
+#define __powf(a, b) powf((a), (b))
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+static inline unsigned int __umulhi(unsigned int a, unsigned int b) { return (unsigned int)(((unsigned long long)a * b) >> 32); }
+static inline void sincospi(double x, double* s, double* c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }
+
+#include ODL_MODEL_HEADER
+#include "odl_kernels.cuh"
+
+struct HostSink {
+  double* out;
+  inline void operator()(int slot, const double (&yi)[ODL_N]) {
+    for (int i = 0; i < ODL_N; ++i) out[(long long)slot * ODL_N + i] = yi[i];
+  }
+};
+
+extern "C" int harness_dims(int* n, int* p) { *n = ODL_N; *p = ODL_P; return 0; }
+
+// solver: 0 DOPRI5, 1 ROS23, 3 Radau5.  out: [n_slot][ODL_N].  Returns the status word.
+extern "C" int harness_solve(int solver, const double* theta, const double* slot_t, int n_slot, const double* y0,
+                             double t0, double rtol, double atol, int max_steps, double* out, int* nsteps) {
+  int y0p[ODL_N];
+  for (int i = 0; i < ODL_N; ++i) y0p[i] = -1;
+  OdlData D;
+  memset(&D, 0, sizeof D);
+  D.slot_t = slot_t; D.y0 = y0; D.y0_from_param = y0p; D.n_slot = n_slot; D.t0 = t0;
+  OdlOpts O;
+  memset(&O, 0, sizeof O);
+  O.rtol = rtol; O.atol = atol; O.max_steps = max_steps; O.stiff_min_steps = 2000;
+  OdlShared S;
+  memset(&S, 0, sizeof S);
+  S.slot_t = const_cast<double*>(slot_t);
+  double p[ODL_P];
+  for (int q = 0; q < ODL_P; ++q) p[q] = theta[q];
+  OdlStepper st;
+  HostSink sink{out};
+  odl_init_system(st, p, D, O, nullptr);
+  odl_emit_initial_slots(st, S, D, sink);
+  OdlRadauAux ax;
+  ax.reset();
+  while (st.slot < D.n_slot && st.status == ODL_OK) {
+    if (solver == 0) odl_dopri5_attempt(st, p, S, D, O, sink);
+    else if (solver == 1) odl_ros23_attempt(st, p, S, D, O, sink);
+    else odl_radau5_attempt(st, ax, p, S, D, O, sink);
+  }
+  *nsteps = st.nsteps;
+  return st.status;
+}

@@ -1,0 +1,79 @@
+"""CPU checks of the stepper code in odl_kernels.cuh (DOPRI5, ROS23, Radau5), compiled for the host by
+tests/host_harness (g++; kernels and warp code compiled out) and compared with scipy's odeint.
+These pin the integrator logic without a GPU; the GPU tests pin the kernels themselves."""
+import numpy as np
+import pytest
+from scipy.integrate import odeint
+
+from odelib_b200 import demo_models
+from oracle import odelib_oracle as orc
+from tests import host_harness as hh
+from tests.helpers import golden, oracle_tables
+
+TOL = 1.49012e-8
+
+
+@pytest.fixture(scope="module")
+def two_i():
+    f, n, P, groups = demo_models.MODELS["two_i"]
+    tab = oracle_tables("two_i")
+    slots = tab.times[np.unique(np.concatenate([tab.tindex[s] for s in tab.obs_order]))]
+    return hh.build(f, n, P, groups), tab, slots
+
+
+def _ref(theta, tab, slots):
+    return odeint(orc.two_i, list(tab.y0), slots, args=(list(theta),), rtol=1e-12, atol=1e-12, mxstep=500000)
+
+
+def _relerr(out, ref):
+    return np.nanmax(np.abs(out - ref) / (np.abs(ref) + 1.0))
+
+
+@pytest.mark.parametrize("solver,bound,max_mean_steps", [("dopri5", 5e-7, 400), ("radau5", 5e-8, 900), ("ros23", 1e-4, 8000)])
+def test_steppers_at_default_tolerance(two_i, solver, bound, max_mean_steps):
+    lib, tab, slots = two_i
+    g = golden("two_i")
+    steps = []
+    for th in g["theta"][:6]:
+        out, st, ns = hh.solve(lib, solver, th, slots, tab.y0, TOL, TOL)
+        assert st == 0
+        assert _relerr(out, _ref(th, tab, slots)) < bound
+        steps.append(ns)
+    assert np.mean(steps) < max_mean_steps
+
+
+def test_radau5_converges_with_tolerance(two_i):
+    lib, tab, slots = two_i
+    th = golden("two_i")["theta"][0]
+    ref = _ref(th, tab, slots)
+    errs = []
+    for tol in (1e-5, 1e-8, 1e-11):
+        out, st, _ = hh.solve(lib, "radau5", th, slots, tab.y0, tol, tol)
+        assert st == 0
+        errs.append(_relerr(out, ref))
+    assert errs[0] > errs[1] > errs[2] and errs[2] < 1e-9
+
+
+def test_stiff_variant_radau5_is_cheap_and_dopri5_is_not(two_i):
+    """BASELINE config 4 point (tau=1e4, lam=1e-2): LSODA runs BDF; Radau5 needs a few hundred steps."""
+    lib, tab, slots = two_i
+    th = np.array([0.5, 1e-7, 50.0, 1e-2, 1e4])
+    ref = _ref(th, tab, slots)
+    out, st, ns = hh.solve(lib, "radau5", th, slots, tab.y0, TOL, TOL)
+    assert st == 0 and ns < 1500 and _relerr(out, ref) < 1e-6
+    out2, st2, ns2 = hh.solve(lib, "ros23", th, slots, tab.y0, TOL, TOL)
+    assert st2 == 0 and _relerr(out2, ref) < 1e-4
+    out3, st3, ns3 = hh.solve(lib, "dopri5", th, slots, tab.y0, TOL, TOL)
+    assert ns3 > 5 * ns                      # stability-limited explicit steps
+    assert st3 == 0 and _relerr(out3, ref) < 1e-5
+
+
+def test_step_budget_and_nonfinite_inputs_end_in_status_words(two_i):
+    lib, tab, slots = two_i
+    th = golden("two_i")["theta"][0]
+    for solver in ("dopri5", "ros23", "radau5"):
+        _, st, ns = hh.solve(lib, solver, th, slots, tab.y0, TOL, TOL, max_steps=7)
+        assert st == 1 and ns == 7
+        bad = th.copy(); bad[1] = np.nan
+        _, st, _ = hh.solve(lib, solver, bad, slots, tab.y0, TOL, TOL, max_steps=100000)
+        assert st != 0

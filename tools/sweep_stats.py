@@ -16,7 +16,12 @@ theta = torch.from_numpy(bench.prior_draws(n, 0, 0)).cuda()
 res = {}
 for mode, kw in (("dopri5_cap20k", dict(solver="dopri5", max_steps=20000)),
                  ("auto", dict(solver="auto", max_steps=200000)),
-                 ("auto_min500", dict(solver="auto", max_steps=200000, stiff_min_steps=500))):
+                 ("auto_256_4096", dict(solver="auto", max_steps=200000, pass_caps=(256, 4096))),
+                 ("auto_512_2048", dict(solver="auto", max_steps=200000, pass_caps=(512, 2048))),
+                 ("auto_512_0", dict(solver="auto", max_steps=200000, pass_caps=(512, 1))),
+                 ("auto_256_0", dict(solver="auto", max_steps=200000, pass_caps=(256, 1))),
+                 ("auto_1024_0", dict(solver="auto", max_steps=200000, pass_caps=(1024, 1))),
+                 ("dopri5_cap512", dict(solver="dopri5", max_steps=512))):
     for rep in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         out = dm.sweep(theta, **kw)
@@ -28,3 +33,10 @@ for mode, kw in (("dopri5_cap20k", dict(solver="dopri5", max_steps=20000)),
                  "chi_finite": int(np.isfinite(out["chi"].cpu().numpy()).sum())}
     print(mode, json.dumps(res[mode]), flush=True)
 json.dump(res, open("gpurun_out/sweep_stats.json", "w"), indent=1)
+# worst systems of the last mode: parameters + step counts, to study on the CPU with LSODA
+ns = out["nsteps"].cpu().numpy()
+order = np.argsort(-ns)[:200]
+np.savez("gpurun_out/worst.npz", theta=theta.cpu().numpy()[order], nsteps=ns[order], chi=out["chi"].cpu().numpy()[order])
+plain = dm.sweep(theta, solver="dopri5", stiff_check=True, max_steps=200000)
+st = plain["status"].cpu().numpy()
+print("routed to ROS23:", int((st == 4).sum()), "of", n)
