@@ -67,7 +67,7 @@ typedef struct odl_solver_opts {
   int stiff_check;     /* DOPRI5: detect stiffness and stop with ODL_ST_STIFF */
   int stiff_min_steps; /* ... only while more than this many steps of the current size remain (0 = 2000) */
   int pass_cap0;       /* ODL_SOLVER_AUTO: step cap of the first DOPRI5 pass (0 = 512) */
-  int pass_cap1;       /* ODL_SOLVER_AUTO: step cap of the second DOPRI5 pass (0 = 8192) */
+  int pass_cap1;       /* ODL_SOLVER_AUTO: step cap of the second DOPRI5 pass (0 = 2048; <= pass_cap0 skips it) */
 } odl_solver_opts;
 
 typedef struct odl_mcmc_opts {
@@ -128,6 +128,9 @@ int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_opts* mo, c
 /* device time (ms) of the kernels launched by the last odl_sweep/odl_mcmc/odl_trajectory call on this
    model, measured with CUDA events on the launching stream; blocks until they have completed */
 int odl_model_last_kernel_ms(odl_model* m, float* ms);
+/* the same split over the passes of the last ODL_SOLVER_AUTO sweep: ms3[0] DOPRI5 bulk pass, ms3[1] DOPRI5
+   pass over the deferred long systems, ms3[2] Radau5 pass over the stiff ones (single-pass calls: ms3[0]) */
+int odl_model_last_pass_ms(odl_model* m, float* ms3);
 /* number of kernel launches issued by this library in this process */
 long long odl_launch_count(void);
 

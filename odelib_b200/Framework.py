@@ -357,13 +357,13 @@ class ModelFramework:
         return pd.Series(mod['abundance'].to_numpy() - np.concatenate(parts), index=mod.index, name='abundance')
 
     # ------------------------------------------------------------------ batch seam: _Fit_worker (Framework.py:41-48)
-    def sweep(self, parameter_array, rtol=None, atol=None, solver="dopri5", as_dataframe=False):
+    def sweep(self, parameter_array, rtol=None, atol=None, solver="auto", as_dataframe=False, out=None):
         """chi (and R^2, status, steps) for every row of ``parameter_array`` [n, P] (parameter_names order).
 
         numpy in -> numpy out (host buffers, copies inside the call); torch CUDA tensor in -> tensors out."""
         dm = self._device()
         res = dm.sweep(parameter_array, rtol=self.rtol if rtol is None else rtol,
-                       atol=self.atol if atol is None else atol, solver=solver)
+                       atol=self.atol if atol is None else atol, solver=solver, out=out)
         if as_dataframe:
             df = pd.DataFrame(np.asarray(parameter_array), columns=self.get_pnames())
             df['chi'] = res['chi']

@@ -17,7 +17,7 @@ ST_OK, ST_MAXSTEPS, ST_NONFINITE, ST_HUNDERFLOW, ST_STIFF, ST_ALLMASKED = 0, 1, 
 
 EXPORTS = ["odl_abi_version", "odl_last_error", "odl_model_create", "odl_model_destroy", "odl_model_build_log",
            "odl_model_kernel_info", "odl_model_set_data", "odl_model_set_grid", "odl_sweep", "odl_trajectory",
-           "odl_mcmc", "odl_model_last_kernel_ms", "odl_launch_count", "odl_fp64_peak"]
+           "odl_mcmc", "odl_model_last_kernel_ms", "odl_model_last_pass_ms", "odl_launch_count", "odl_fp64_peak"]
 
 
 class OdlError(RuntimeError):
@@ -81,6 +81,7 @@ def lib():
     L.odl_mcmc.argtypes = [C.c_void_p, C.POINTER(SolverOpts), C.POINTER(McmcOpts), C.POINTER(McmcIO), C.c_int,
                            C.c_void_p]
     L.odl_model_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.odl_model_last_pass_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.odl_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     if L.odl_abi_version() != 1:
         raise OdlError(EIO, "libodelib_b200.so ABI version mismatch - rebuild")

@@ -137,6 +137,8 @@ struct odl_model {
   DevBuf counter;
   DevBuf scratch[16];
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evp[2] = {nullptr, nullptr};   // between the cohort passes of an AUTO sweep
+  int n_pass = 0;
   bool timed = false;
 };
 
@@ -258,7 +260,8 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
       if (k.required) return bail(fail(ODL_ECUDA, std::string("cuModuleGetFunction(") + k.name + "): " + cu_err(r)));
     }
   }
-  if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
+  if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess ||
+      cudaEventCreate(&m->evp[0]) != cudaSuccess || cudaEventCreate(&m->evp[1]) != cudaSuccess)
     return bail(fail(ODL_ECUDA, "cudaEventCreate failed"));
   if ((rc = m->counter.ensure(512))) return bail(rc);
   m->on_gpu = true;
@@ -276,6 +279,7 @@ extern "C" int odl_model_destroy(odl_model* m) {
   for (auto& s : m->scratch) s.release();
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
+  for (auto& e : m->evp) if (e) cudaEventDestroy(e);
   delete m;
   return 0;
 }
@@ -486,6 +490,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     return launch(m, f, grid, block, smem, s, params);
   };
   ODL_CUDA(cudaEventRecord(m->ev0, s));
+  m->n_pass = 1;
   if (solver != ODL_SOLVER_AUTO) {
     A.defer_list[0] = A.defer_list[1] = nullptr; A.defer_count[0] = A.defer_count[1] = nullptr;
     CUfunction f1 = solver == ODL_SOLVER_ROS23 ? m->k_sweep_ros : (solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau : m->k_sweep);
@@ -505,13 +510,14 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     int* listA = static_cast<int*>(la.p);
     int* listB = static_cast<int*>(lb.p);
     const int cap0 = so && so->pass_cap0 > 0 ? so->pass_cap0 : 512;
-    const int cap1 = so && so->pass_cap1 > 0 ? so->pass_cap1 : 8192;
+    const int cap1 = so && so->pass_cap1 > 0 ? so->pass_cap1 : 2048;
     OdlOpts O0 = O; O0.stiff_check = 1; O0.max_steps = std::min(cap0, O.max_steps);
     const bool two_dopri = cap1 > cap0;
     OdlSweepArgs A0 = A;
     A0.defer_list[0] = two_dopri ? listA : listB; A0.defer_count[0] = two_dopri ? cnt(64) : cnt(192);
     A0.defer_list[1] = listB; A0.defer_count[1] = cnt(192);
     if ((rc = go(m->k_sweep, O0, A0, (unsigned)m->block, n))) return rc;
+    ODL_CUDA(cudaEventRecord(m->evp[0], s));
     if (two_dopri) {
       OdlOpts O1 = O; O1.stiff_check = 1; O1.max_steps = std::min(cap1, O.max_steps);
       OdlSweepArgs A1 = A;
@@ -520,6 +526,8 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       A1.defer_list[1] = listB; A1.defer_count[1] = cnt(192);
       if ((rc = go(m->k_sweep, O1, A1, 32u, std::max<long long>(32, n / 16)))) return rc;
     }
+    ODL_CUDA(cudaEventRecord(m->evp[1], s));
+    m->n_pass = 3;
     OdlOpts O2 = O; O2.stiff_check = 0;
     OdlSweepArgs A2 = A;
     A2.index = listB; A2.index_count = cnt(192); A2.counter = ctr(256);
@@ -555,6 +563,7 @@ extern "C" int odl_trajectory(odl_model* m, const odl_solver_opts* so, long long
   unsigned grid = (unsigned)((n + block - 1) / block);
   ODL_CUDA(cudaEventRecord(m->ev0, s));
   void* params[] = {&D, &O, &A};
+  m->n_pass = 1;
   if ((rc = launch(m, m->k_traj, grid, block, smem, s, params))) return rc;
   ODL_CUDA(cudaEventRecord(m->ev1, s));
   m->timed = true;
@@ -618,10 +627,26 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   if (solver == ODL_SOLVER_AUTO) O.stiff_check = 1;
   ODL_CUDA(cudaEventRecord(m->ev0, s));
   void* params[] = {&D, &O, &A};
+  m->n_pass = 1;
   if ((rc = launch(m, f, grid, block, smem, s, params))) return rc;
   ODL_CUDA(cudaEventRecord(m->ev1, s));
   m->timed = true;
   return st.finish();
+}
+
+extern "C" int odl_model_last_pass_ms(odl_model* m, float* ms3) {
+  if (!m || !ms3) return fail(ODL_EINVAL, "null argument");
+  if (!m->on_gpu || !m->timed) return fail(ODL_EINVAL, "no kernel has been launched on this model yet");
+  ODL_CUDA(cudaEventSynchronize(m->ev1));
+  ms3[0] = ms3[1] = ms3[2] = 0.f;
+  if (m->n_pass == 3) {
+    ODL_CUDA(cudaEventElapsedTime(&ms3[0], m->ev0, m->evp[0]));
+    ODL_CUDA(cudaEventElapsedTime(&ms3[1], m->evp[0], m->evp[1]));
+    ODL_CUDA(cudaEventElapsedTime(&ms3[2], m->evp[1], m->ev1));
+  } else {
+    ODL_CUDA(cudaEventElapsedTime(&ms3[0], m->ev0, m->ev1));
+  }
+  return 0;
 }
 
 extern "C" int odl_model_last_kernel_ms(odl_model* m, float* ms) {

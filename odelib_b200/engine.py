@@ -108,6 +108,11 @@ class DeviceModel:
         _capi.check(self._L.odl_model_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def last_pass_ms(self):
+        ms = (C.c_float * 3)()
+        _capi.check(self._L.odl_model_last_pass_ms(self._h, ms))
+        return [float(x) for x in ms]
+
     # -- tables ------------------------------------------------------------------------------------
     def set_data(self, tables: ObsTables, y0, y0_from_param=None):
         y0 = np.ascontiguousarray(y0, dtype=np.float64)

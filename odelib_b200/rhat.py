@@ -52,3 +52,20 @@ def allgather_summaries(local, n_total=None, group=None):
     dist.all_gather_into_tensor(out, pad, group=group)
     parts = [out[r * mmax: r * mmax + int(counts[r].item())] for r in range(ws)]
     return torch.cat(parts, dim=0)
+
+
+def sharded_mcmc(dm, theta0_all, group=None, **mcmc_kw):
+    """Run this rank's contiguous block of chains and all-gather the chain summaries for R-hat.
+
+    theta0_all [C_total, P] is the same on every rank; chain c keeps its global index (Philox key / seed), so
+    the per-chain results do not depend on the number of GPUs.  Returns (local result dict, R-hat[P] over all
+    chains, (lo, hi))."""
+    import torch
+    import torch.distributed as dist
+    ws = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if ws > 1 else 0
+    lo, hi = shard_bounds(len(theta0_all), ws, rank)
+    res = dm.mcmc(theta0_all[lo:hi], chain_offset=lo, device_buffers=True, **mcmc_kw)
+    summ = allgather_summaries(res["summaries"], group=group)
+    rh = rhat_from_summaries(summ.cpu().numpy(), dm.n_param)
+    return res, rh, (lo, hi)

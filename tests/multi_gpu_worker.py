@@ -1,0 +1,50 @@
+"""Worker for tests/test_gpu_multi.py: run under torchrun (one rank per GPU).  Each rank runs its contiguous
+block of chains + its block of a parameter sweep; rank 0 saves the gathered results for comparison with a
+single-GPU run of the very same chains."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from odelib_b200.rhat import shard_bounds, sharded_mcmc  # noqa: E402
+from tests.helpers import device_model, golden, prior_draws  # noqa: E402
+
+
+def main(out_path):
+    rank = int(os.environ.get("RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dm, _ = device_model("two_i", device=local)
+    g = golden("two_i")
+    C, nits = 96, 120
+    rng = np.random.default_rng(42)
+    theta0 = g["chain_def_s0_theta0"] * np.exp(0.05 * rng.standard_normal((C, 5)))
+    res, rh, (lo, hi) = sharded_mcmc(dm, torch.from_numpy(theta0).cuda(), nits=nits, seed=9, rng_mode="philox")
+    samples = res["samples"]
+    theta = prior_draws("two_i", 5000, seed=4)
+    slo, shi = shard_bounds(len(theta), ws, rank)
+    sw = dm.sweep(torch.from_numpy(theta[slo:shi]).cuda(), solver="auto")
+    chi = sw["chi"]
+    if ws > 1:
+        # gather the per-rank blocks only to let the test compare them; the data path itself has no collective
+        parts = [None] * ws
+        dist.all_gather_object(parts, (lo, samples.cpu().numpy(), slo, chi.cpu().numpy()))
+    else:
+        parts = [(lo, samples.cpu().numpy(), slo, chi.cpu().numpy())]
+    if rank == 0:
+        parts.sort(key=lambda p: p[0])
+        np.savez(out_path, samples=np.concatenate([p[1] for p in parts]), chi=np.concatenate([p[3] for p in parts]),
+                 rhat=rh, world=ws)
+    if ws > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

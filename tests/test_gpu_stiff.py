@@ -116,8 +116,9 @@ def test_mcmc_on_the_stiff_variant_ros23_and_auto():
     a = dm.mcmc(starts, nits=nits, rng_mode="host", z=z, u=u, solver="ros23", trace=True, max_steps=2000000)
     b = dm.mcmc(starts, nits=nits, rng_mode="host", z=z, u=u, solver="auto", trace=True, max_steps=2000000)
     assert np.isfinite(a["chinew"]).all() and a["fail_count"].sum() == 0
-    np.testing.assert_allclose(b["chinew"], a["chinew"], rtol=1e-9)     # auto ends up on the same ROS23 solves
-    assert np.array_equal(a["accepted"], b["accepted"])
+    # auto = DOPRI5 until Hairer's test calls a proposal stiff, then ROS23 for that solve: same chi to solver accuracy
+    np.testing.assert_allclose(b["chinew"], a["chinew"], rtol=1e-5)
+    assert (a["accepted"] != b["accepted"]).sum() <= 2
     ref = orc.mh_chain(orc.two_i, starts[0], tab, 5, nits=nits, z=z[0], u=u[0], rtol=1e-10, atol=1e-10)
     np.testing.assert_allclose(a["chinew"][0], ref["chinew"], rtol=5e-4)
     c = dm.mcmc(starts, nits=nits, rng_mode="host", z=z, u=u, solver="radau5", trace=True)
