@@ -3,7 +3,8 @@ import sys
 
 import torch
 
-sys.path.insert(0, ".")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests.helpers import device_model  # noqa: E402
 import bench  # noqa: E402
 
