@@ -55,7 +55,8 @@ typedef struct odl_build_opts {
   int min_blocks;      /* __launch_bounds__ min CTAs per SM, 0 = default (4) */
   int dense_output;    /* 1 = dense output at the observation times (default), 0 = land on them */
   int compile_only;    /* 1 = NVRTC-compile (and cache) but do not touch a GPU */
-  int reserved[3];
+  int y0_from_param;   /* 1 = some state's initial value is a parameter ('<state>0', Samplers.py:110-114) */
+  int reserved[2];
   const char* cache_dir; /* directory for compiled cubins, NULL = no cache */
 } odl_build_opts;
 

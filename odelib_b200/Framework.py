@@ -281,7 +281,7 @@ class ModelFramework:
                 if self.parameters[p] is not None and np.ndim(self.parameters[p].val) != 0:
                     raise NotImplementedError("array-valued parameters are not supported on the device path")
             self._dm = DeviceModel(self._model, len(self._snames), len(self._pnames), self._observe_groups(),
-                                   device=self.device)
+                                   device=self.device, y0_from_param=bool((self._y0_map() >= 0).any()))
         y0 = np.asarray(self.get_inits(), dtype=np.float64)
         stamp = (self.times.tobytes(), y0.tobytes(), id(self.df), self._samples)
         if stamp != self._dm_stamp:

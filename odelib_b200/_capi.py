@@ -28,7 +28,8 @@ class OdlError(RuntimeError):
 
 class BuildOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("block_threads", C.c_int), ("min_blocks", C.c_int), ("dense_output", C.c_int),
-                ("compile_only", C.c_int), ("reserved", C.c_int * 3), ("cache_dir", C.c_char_p)]
+                ("compile_only", C.c_int), ("y0_from_param", C.c_int), ("reserved", C.c_int * 2),
+                ("cache_dir", C.c_char_p)]
 
 
 class SolverOpts(C.Structure):

@@ -73,7 +73,7 @@ def check_kernels(models=None, outdir=None, block=128, minblocks=4, dense=1):
         cu = os.path.join(outdir, f"{name}.cu")
         open(cu, "w").write(src + '#include "odl_kernels.cuh"\n')
         cmd = [NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-I" + HERE, f"-DODL_BLOCK={block}",
-               f"-DODL_MINBLOCKS={minblocks}", f"-DODL_DENSE={dense}", "-Xptxas", "-v", "-cubin", "-o",
+               f"-DODL_MINBLOCKS={minblocks}", f"-DODL_DENSE={dense}", "-DODL_Y0P=0", "-Xptxas", "-v", "-cubin", "-o",
                os.path.join(outdir, f"{name}.cubin"), cu]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:

@@ -124,7 +124,7 @@ struct Tables {
 struct odl_model {
   int device = 0;
   int n_state = 0, n_param = 0, n_out = 0;
-  int block = 128, minblocks = 4, dense = 1;
+  int block = 128, minblocks = 4, dense = 1, y0p = 0;
   int sm_count = 0;
   bool on_gpu = false;
   std::vector<char> cubin;
@@ -152,7 +152,7 @@ static int compile_model(odl_model* m, const std::string& src, const char* cache
   std::vector<std::string> opt = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device",
                                   "-DODL_BLOCK=" + std::to_string(m->block),
                                   "-DODL_MINBLOCKS=" + std::to_string(m->minblocks),
-                                  "-DODL_DENSE=" + std::to_string(m->dense)};
+                                  "-DODL_DENSE=" + std::to_string(m->dense), "-DODL_Y0P=" + std::to_string(m->y0p)};
   int major = 0, minor = 0;
   nvrtcVersion(&major, &minor);
   std::string keysrc = src + kKernelSrc + kAbiHeaderSrc;
@@ -230,6 +230,7 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
     if (opts->block_threads > 0) m->block = opts->block_threads;
     if (opts->min_blocks > 0) m->minblocks = opts->min_blocks;
     m->dense = opts->dense_output ? 1 : 0;
+    m->y0p = opts->y0_from_param ? 1 : 0;
     compile_only = opts->compile_only != 0;
     cache_dir = opts->cache_dir;
   }
@@ -360,6 +361,8 @@ static int upload_tables(odl_model* m, Tables& T, int n_slot, const double* slot
     hy0[i] = y0 ? y0[i] : 0.0;
     y0p[i] = y0_from_param ? y0_from_param[i] : -1;
     if (y0p[i] >= m->n_param) return fail(ODL_EINVAL, "y0_from_param index out of range");
+    if (y0p[i] >= 0 && !m->y0p)
+      return fail(ODL_EINVAL, "model was built with y0_from_param = 0 but a state takes its initial value from a parameter");
   }
   int rc = T.buf.ensure(nd * sizeof(double) + ni * sizeof(int));
   if (rc) return rc;

@@ -36,6 +36,9 @@
 #ifndef ODL_DENSE
 #define ODL_DENSE 1
 #endif
+#ifndef ODL_Y0P
+#define ODL_Y0P 1
+#endif
 #ifndef ODL_MINBLOCKS_ROS
 #define ODL_MINBLOCKS_ROS (ODL_MINBLOCKS > 2 ? ODL_MINBLOCKS - 1 : ODL_MINBLOCKS)
 #endif
@@ -138,6 +141,26 @@ __device__ __forceinline__ void odl_score(const OdlShared& S, const OdlData& D, 
   nvalid = k;
 }
 
+
+// Same sums, one system per lane (the MCMC kernel finalises all lanes of a warp together).
+__device__ __forceinline__ void odl_score_self(const OdlShared& S, const OdlData& D, const double* stage, double& chi,
+                                               double& ssres, int& nvalid) {
+  double c = 0.0, s = 0.0;
+  int k = 0;
+  for (int o = 0; o < D.n_obs; ++o) {
+    const double pred = stage[S.src[o]];
+    const double d = __dadd_rn(S.lnO[o], -log(pred));
+    const double dd = __dmul_rn(d, d);
+    const double den = S.denom[o];
+    const double term = dd / den;
+    const bool ok = odl_finite(dd) && odl_finite(term) && !(fabs(dd) * ODL_DBL_MIN >= fabs(den));
+    if (ok) { c += term; ++k; }
+    const double r = __dadd_rn(pred, -S.lin[o]);
+    const double rr = __dmul_rn(r, r);
+    if (rr == rr) s += rr;
+  }
+  chi = c; ssres = s; nvalid = k;
+}
 #endif  // ODL_HOST_HARNESS
 
 // ------------------------------------------------------------------------------------------------
@@ -155,20 +178,45 @@ struct OdlStepper {
   bool last_rejected;
 };
 
-__device__ __forceinline__ float odl_err_ratio(double e, double sk) {
-  // |e|/sk in fp32: only the step controller sees it (3 digits are plenty); SFU reciprocal instead
-  // of a 20-instruction fp64 division.  sk >= atol > 0.
-  return (float)e * __frcp_rn((float)sk);
+// Approximate fp64 reciprocal (one MUFU.RCP64H, ~20 bits): only step-size control sees it -- the scaled
+// error norms need 2-3 digits -- so no 20-instruction IEEE division and no fp64<->fp32 conversions.
+#ifndef ODL_HOST_HARNESS
+__device__ __forceinline__ double odl_rcp_approx(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
 }
+#else
+__device__ __forceinline__ double odl_rcp_approx(double x) { return 1.0 / x; }
+#endif
+__device__ __forceinline__ float odl_err_ratio(double e, double sk) { return (float)(e * odl_rcp_approx(sk)); }
+
+// Butcher tableau of DOPRI5 (Hairer/Norsett/Wanner, dopri5.f) in constant memory: DFMA takes c[bank][offset]
+// operands directly, whereas literals are re-materialised with two UMOVs per use (13 % of the issued
+// instructions in the first profile, profiles/r1_sweep_bulk_ncu.txt).
+__constant__ double ODL_TAB[36] = {
+    0.2,                                                                    // 0  a21
+    3.0 / 40.0, 9.0 / 40.0,                                                 // 1  a31 a32
+    44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0,                                  // 3  a41 a42 a43
+    19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0,  // 6  a51..a54
+    9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0,   // 10 a61..a65
+    35.0 / 384.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0,          // 15 a71 a73 a74 a75 a76
+    71.0 / 57600.0, -71.0 / 16695.0, 71.0 / 1920.0, -17253.0 / 339200.0, 22.0 / 525.0, -1.0 / 40.0,  // 20 e1 e3 e4 e5 e6 e7
+    -12715105075.0 / 11282082432.0, 87487479700.0 / 32700410799.0, -10690763975.0 / 1880347072.0,
+    701980252875.0 / 199316789632.0, -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0,            // 26 d1 d3 d4 d5 d6 d7
+    0.3, 0.8, 8.0 / 9.0, 0.0};                                                                        // 32 c3 c4 c5
+#define ODL_T(i) ODL_TAB[i]
 
 __device__ __forceinline__ void odl_init_system(OdlStepper& st, const double (&p)[ODL_P], const OdlData& D,
                                                 const OdlOpts& O, const double* y0_override) {
 #pragma unroll
   for (int i = 0; i < ODL_N; ++i) {
-    const int src = D.y0_from_param[i];
     double v = y0_override ? y0_override[i] : D.y0[i];
+#if ODL_Y0P
+    const int src = D.y0_from_param[i];
 #pragma unroll
     for (int q = 0; q < ODL_P; ++q) if (src == q) v = p[q];     // '<state>0' parameters (Samplers.py:110-114)
+#endif
     st.y[i] = v;
   }
   st.t = D.t0;
@@ -182,29 +230,30 @@ __device__ __forceinline__ void odl_init_system(OdlStepper& st, const double (&p
   if (!(h > 0.0)) {
     // Hairer's hinit: h ~ 0.01 |y|/|f|, refined with a difference quotient of f along an Euler step.
     // A heuristic -> fp32 norms (SFU reciprocal / pow), guarded below against overflow.
-    float dnf = 0.f, dny = 0.f;
-    float rsk[ODL_N];
+    double dnf = 0.0, dny = 0.0;
+    double rsk[ODL_N];
 #pragma unroll
     for (int i = 0; i < ODL_N; ++i) {
-      rsk[i] = __frcp_rn((float)(O.atol + O.rtol * fabs(st.y[i])));
-      const float a = (float)st.k1[i] * rsk[i], b = (float)st.y[i] * rsk[i];
+      rsk[i] = odl_rcp_approx(O.atol + O.rtol * fabs(st.y[i]));
+      const double a = st.k1[i] * rsk[i], b = st.y[i] * rsk[i];
       dnf += a * a; dny += b * b;
     }
-    float hf = (dnf <= 1e-10f || dny <= 1e-10f) ? 1e-6f : 0.01f * sqrtf(dny / dnf);
+    const float fnf = (float)dnf, fny = (float)dny;
+    const float hf = (fnf <= 1e-10f || fny <= 1e-10f) ? 1e-6f : 0.01f * sqrtf(fny * __frcp_rn(fnf));
     h = fmin((double)hf, hmax);
     double y1[ODL_N], f1[ODL_N];
 #pragma unroll
     for (int i = 0; i < ODL_N; ++i) y1[i] = st.y[i] + h * st.k1[i];
     odl_rhs(y1, st.t + h, p, f1);
-    float der2 = 0.f;
+    double d2 = 0.0;
 #pragma unroll
     for (int i = 0; i < ODL_N; ++i) {
-      const float a = (float)(f1[i] - st.k1[i]) * rsk[i];
-      der2 += a * a;
+      const double a = (f1[i] - st.k1[i]) * rsk[i];
+      d2 += a * a;
     }
-    der2 = sqrtf(der2) / (float)h;
-    const float der12 = fmaxf(der2, sqrtf(dnf));
-    const float h1 = (der12 <= 1e-15f) ? fmaxf(1e-6f, (float)h * 1e-3f) : __powf(0.01f / der12, 0.2f);
+    const float der2 = sqrtf((float)d2) * __frcp_rn((float)h);
+    const float der12 = fmaxf(der2, sqrtf(fnf));
+    const float h1 = (der12 <= 1e-15f) ? fmaxf(1e-6f, (float)h * 1e-3f) : __powf(0.01f * __frcp_rn(der12), 0.2f);
     h = fmin(fmin(100.0 * h, (double)h1), hmax);
   }
   if (!(h > 0.0) || !odl_finite(h)) h = 1e-6 * (span > 0.0 ? span : 1.0);
@@ -212,12 +261,6 @@ __device__ __forceinline__ void odl_init_system(OdlStepper& st, const double (&p
 }
 
 // dense output of the last accepted step [t0, t0+h] at time ts (Hairer's contd5)
-#define ODL_D1 (-12715105075.0 / 11282082432.0)
-#define ODL_D3 (87487479700.0 / 32700410799.0)
-#define ODL_D4 (-10690763975.0 / 1880347072.0)
-#define ODL_D5 (701980252875.0 / 199316789632.0)
-#define ODL_D6 (-1453857185.0 / 822651844.0)
-#define ODL_D7 (69997945.0 / 29380423.0)
 
 // One step attempt.  On acceptance the lambda-like macro ODL_ON_SLOT is not used; instead the caller
 // passes a functor `sink(slot, yi)` that receives the interpolated state at every crossed slot.
@@ -241,52 +284,50 @@ __device__ __forceinline__ void odl_dopri5_attempt(OdlStepper& st, const double 
   ++st.nsteps;
   double k2[ODL_N], k3[ODL_N], k4[ODL_N], k5[ODL_N], k6[ODL_N], k7[ODL_N], yt[ODL_N], yn[ODL_N];
 #pragma unroll
-  for (int i = 0; i < ODL_N; ++i) yt[i] = st.y[i] + h * (0.2 * st.k1[i]);
-  odl_rhs(yt, t + 0.2 * h, p, k2);
+  for (int i = 0; i < ODL_N; ++i) yt[i] = st.y[i] + h * (ODL_T(0) * st.k1[i]);
+  odl_rhs(yt, t + ODL_T(0) * h, p, k2);
 #pragma unroll
-  for (int i = 0; i < ODL_N; ++i) yt[i] = st.y[i] + h * ((3.0 / 40.0) * st.k1[i] + (9.0 / 40.0) * k2[i]);
-  odl_rhs(yt, t + 0.3 * h, p, k3);
-#pragma unroll
-  for (int i = 0; i < ODL_N; ++i)
-    yt[i] = st.y[i] + h * ((44.0 / 45.0) * st.k1[i] + (-56.0 / 15.0) * k2[i] + (32.0 / 9.0) * k3[i]);
-  odl_rhs(yt, t + 0.8 * h, p, k4);
+  for (int i = 0; i < ODL_N; ++i) yt[i] = st.y[i] + h * (ODL_T(1) * st.k1[i] + ODL_T(2) * k2[i]);
+  odl_rhs(yt, t + ODL_T(32) * h, p, k3);
 #pragma unroll
   for (int i = 0; i < ODL_N; ++i)
-    yt[i] = st.y[i] + h * ((19372.0 / 6561.0) * st.k1[i] + (-25360.0 / 2187.0) * k2[i] + (64448.0 / 6561.0) * k3[i] +
-                           (-212.0 / 729.0) * k4[i]);
-  odl_rhs(yt, t + (8.0 / 9.0) * h, p, k5);
+    yt[i] = st.y[i] + h * (ODL_T(3) * st.k1[i] + ODL_T(4) * k2[i] + ODL_T(5) * k3[i]);
+  odl_rhs(yt, t + ODL_T(33) * h, p, k4);
 #pragma unroll
   for (int i = 0; i < ODL_N; ++i)
-    yt[i] = st.y[i] + h * ((9017.0 / 3168.0) * st.k1[i] + (-355.0 / 33.0) * k2[i] + (46732.0 / 5247.0) * k3[i] +
-                           (49.0 / 176.0) * k4[i] + (-5103.0 / 18656.0) * k5[i]);
+    yt[i] = st.y[i] + h * (ODL_T(6) * st.k1[i] + ODL_T(7) * k2[i] + ODL_T(8) * k3[i] + ODL_T(9) * k4[i]);
+  odl_rhs(yt, t + ODL_T(34) * h, p, k5);
+#pragma unroll
+  for (int i = 0; i < ODL_N; ++i)
+    yt[i] = st.y[i] + h * (ODL_T(10) * st.k1[i] + ODL_T(11) * k2[i] + ODL_T(12) * k3[i] + ODL_T(13) * k4[i] +
+                           ODL_T(14) * k5[i]);
   const double tph = t + h;
   odl_rhs(yt, tph, p, k6);
 #pragma unroll
   for (int i = 0; i < ODL_N; ++i)
-    yn[i] = st.y[i] + h * ((35.0 / 384.0) * st.k1[i] + (500.0 / 1113.0) * k3[i] + (125.0 / 192.0) * k4[i] +
-                           (-2187.0 / 6784.0) * k5[i] + (11.0 / 84.0) * k6[i]);
+    yn[i] = st.y[i] + h * (ODL_T(15) * st.k1[i] + ODL_T(16) * k3[i] + ODL_T(17) * k4[i] + ODL_T(18) * k5[i] +
+                           ODL_T(19) * k6[i]);
   odl_rhs(yn, tph, p, k7);
 
   // embedded error estimate, scaled RMS norm
-  float errsq = 0.f;
+  double errsq = 0.0;
   bool finite_all = true;
 #pragma unroll
   for (int i = 0; i < ODL_N; ++i) {
-    const double e = h * ((71.0 / 57600.0) * st.k1[i] + (-71.0 / 16695.0) * k3[i] + (71.0 / 1920.0) * k4[i] +
-                          (-17253.0 / 339200.0) * k5[i] + (22.0 / 525.0) * k6[i] + (-1.0 / 40.0) * k7[i]);
+    const double e = h * (ODL_T(20) * st.k1[i] + ODL_T(21) * k3[i] + ODL_T(22) * k4[i] + ODL_T(23) * k5[i] +
+                          ODL_T(24) * k6[i] + ODL_T(25) * k7[i]);
     const double sk = O.atol + O.rtol * fmax(fabs(st.y[i]), fabs(yn[i]));
-    const float r = odl_err_ratio(e, sk);
+    const double r = e * odl_rcp_approx(sk);
     errsq += r * r;
     finite_all = finite_all && odl_finite(yn[i]);
   }
-  const float err = sqrtf(errsq * (1.0f / ODL_N));
-  // PI controller (beta = 0.04): fac11 = err^(0.2 - 0.75 beta), SFU pow
-  const float fac11 = __powf(err, 0.2f - 0.04f * 0.75f);
+  const float err = sqrtf((float)errsq * (1.0f / ODL_N));
+  // PI controller (Hairer, beta = 0.04): h_new = h * 0.9 * facold^beta / err^(0.2 - 0.75 beta), one SFU exp2
+  const float lg_err = __log2f(err);
   if (err <= 1.0f && finite_all) {
     // ---- accepted ----
-    float fac = fac11 / __powf(st.facold, 0.04f);
-    fac = fmaxf(0.1f, fminf(5.0f, fac * (1.0f / 0.9f)));      // h_new = h / fac, growth <= 10, shrink <= 5
-    double hnew = h / (double)fac;
+    const float inv = 0.9f * exp2f(0.04f * __log2f(st.facold) - (0.2f - 0.04f * 0.75f) * lg_err);
+    double hnew = h * (double)fminf(10.0f, fmaxf(0.2f, inv));   // growth <= 10, shrink <= 5
     if (!(err > 0.f)) hnew = h * 10.0;
     st.facold = fmaxf(err, 1e-4f);
     if (O.stiff_check && ((st.nsteps % 10) == 0 || st.iasti > 0)) {
@@ -320,11 +361,12 @@ __device__ __forceinline__ void odl_dopri5_attempt(OdlStepper& st, const double 
         rc2[i] = yn[i] - st.y[i];
         rc3[i] = h * st.k1[i] - rc2[i];
         rc4[i] = rc2[i] - h * k7[i] - rc3[i];
-        rc5[i] = h * (ODL_D1 * st.k1[i] + ODL_D3 * k3[i] + ODL_D4 * k4[i] + ODL_D5 * k5[i] + ODL_D6 * k6[i] +
-                      ODL_D7 * k7[i]);
+        rc5[i] = h * (ODL_T(26) * st.k1[i] + ODL_T(27) * k3[i] + ODL_T(28) * k4[i] + ODL_T(29) * k5[i] +
+                      ODL_T(30) * k6[i] + ODL_T(31) * k7[i]);
       }
+      const double rh = 1.0 / h;
       do {
-        const double th = (S.slot_t[st.slot] - t) / h, th1 = 1.0 - th;
+        const double th = (S.slot_t[st.slot] - t) * rh, th1 = 1.0 - th;
         double yi[ODL_N];
 #pragma unroll
         for (int i = 0; i < ODL_N; ++i)
@@ -350,7 +392,8 @@ __device__ __forceinline__ void odl_dopri5_attempt(OdlStepper& st, const double 
   } else {
     // ---- rejected ----
     double hnew;
-    if (err == err && finite_all && err < 3.0e38f) hnew = h / (double)fminf(5.0f, fac11 * (1.0f / 0.9f));
+    if (err == err && finite_all && err < 3.0e38f)
+      hnew = h * (double)fmaxf(0.2f, 0.9f * exp2f(-(0.2f - 0.04f * 0.75f) * lg_err));
     else hnew = 0.2 * h;                                        // NaN / overflow inside the step
     st.last_rejected = true;
     st.h = hnew;
@@ -1048,29 +1091,40 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
     }
   }
 
+  // Lock-step per warp: every lane integrates its chain's current proposal; when the last lane of the warp is
+  // done, all lanes score / accept / record / propose TOGETHER.  (The first version finalised lane by lane as
+  // lanes finished: half of all issued instructions ran with one lane active -- profiles/r1_mcmc_ncu.txt.
+  // Proposals of neighbouring chains cost nearly the same number of steps, so waiting is cheap here, unlike in
+  // the heavy-tailed prior sweep.)
   for (;;) {
-    const bool fin = active && done;
-    unsigned m = __ballot_sync(ODL_FULL, fin);
-    double my_chi = nan, my_r2 = nan;
-    while (m) {
-      const int L = __ffs(m) - 1;
-      m &= m - 1;
-      double chi, ss; int nv;
-      odl_score(S, D, S.stage + (size_t)((threadIdx.x & ~31) + L) * D.stage_stride, lane, nullptr, chi, ss, nv);
-      if (lane == L) {
-        if (st.status == ODL_OK && nv > 0) { my_chi = chi; my_r2 = 1.0 - ss / D.sstot; }
-        else if (st.status == ODL_OK) { my_chi = nan; my_r2 = 1.0 - ss / D.sstot; }   // np.ma.masked chi
+    if (active && !done) {
+      odl_attempt<SOLVER>(st, ax, p, S, D, O, sink, use_ros);
+      done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
+    }
+    if (__ballot_sync(ODL_FULL, active && !done)) continue;
+    if (!__any_sync(ODL_FULL, active)) break;
+    if (SOLVER == 2) {
+      // DOPRI5 gave up on a stiff proposal: redo this very solve with the Rosenbrock stepper
+      const bool restart = active && st.status == ODL_STIFF && !use_ros;
+      if (__ballot_sync(ODL_FULL, restart)) {
+        if (restart) {
+          steps += st.nsteps;
+          use_ros = true;
+          odl_init_system(st, p, D, O, nullptr);
+          ax.reset();
+          odl_emit_initial_slots(st, S, D, sink);
+          done = (st.slot >= D.n_slot);
+        }
+        continue;
       }
     }
-    if (SOLVER == 2 && fin && st.status == ODL_STIFF && !use_ros) {
-      // DOPRI5 gave up on a stiff proposal: redo this very solve with the Rosenbrock stepper
-      steps += st.nsteps;
-      use_ros = true;
-      odl_init_system(st, p, D, O, nullptr);
-      ax.reset();
-      odl_emit_initial_slots(st, S, D, sink);
-      done = (st.slot >= D.n_slot);
-    } else
+    const bool fin = active;
+    double my_chi = nan, my_r2 = nan;
+    if (fin) {
+      double chi, ss; int nv;
+      odl_score_self(S, D, my_stage, chi, ss, nv);
+      if (st.status == ODL_OK) { my_chi = (nv > 0) ? chi : nan; my_r2 = 1.0 - ss / D.sstot; }   // nv == 0: np.ma.masked
+    }
     if (fin) {
       steps += st.nsteps;
       use_ros = false;
@@ -1134,11 +1188,6 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
         if (A.fail_count) A.fail_count[chain] += fails;
         if (A.step_count) A.step_count[chain] += steps;
       }
-    }
-    if (!__any_sync(ODL_FULL, active)) break;
-    if (active && !done) {
-      odl_attempt<SOLVER>(st, ax, p, S, D, O, sink, use_ros);
-      done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
     }
   }
 }

@@ -10,6 +10,8 @@
 #define __forceinline__ inline
 #define __global__
 #define __launch_bounds__(...)
+#define __constant__ static const
+#define __log2f(x) log2f(x)
 static inline float __frcp_rn(float x) { return 1.0f / x; }
 #define __powf(a, b) powf((a), (b))
 static inline double __dadd_rn(double a, double b) { return a + b; }
