@@ -158,7 +158,7 @@ def workload_config(args, n_gpus):
                         f"infection model (4 states, 5 parameters) integrated to the 37 demo observations "
                         f"(19 grid times of t_steps={TSTEPS}) + chi/R^2 [BASELINE.json configs[1]]",
             "sets_per_gpu": args.sets, "sets_total": args.sets * n_gpus, "rtol": 1.49012e-8, "atol": 1.49012e-8,
-            "solver": "auto: dopri5(4) dense output, <=512 steps -> dopri5 <=2048 steps -> radau5", "l2": "flushed between timed steps (256 MiB write)",
+            "solver": "auto: dopri5(4) dense output <=512 steps -> {dopri5 <=1536 steps || radau5} -> radau5", "l2": "flushed between timed steps (256 MiB write)",
             "parallelism": f"shard{n_gpus}"}
 
 

@@ -36,7 +36,8 @@ struct OdlOpts {
   int max_steps;
   int stiff_check;               // 1 = run Hairer's stiffness test and bail out with ODL_STIFF
   int stiff_min_steps;           // bail out only if more than this many steps of the current size remain
-  int reserved1;
+  int defer_split_steps;         // > 0: a system stopped by max_steps goes to defer_list[1] instead of [0] when its
+                                 //      progress so far projects to more than this many steps in total
 };
 
 struct OdlSweepArgs {

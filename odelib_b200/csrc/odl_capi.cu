@@ -138,6 +138,8 @@ struct odl_model {
   DevBuf scratch[16];
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evp[2] = {nullptr, nullptr};   // between the cohort passes of an AUTO sweep
+  cudaEvent_t ev_aux = nullptr;
+  cudaStream_t aux = nullptr;                // helper stream: the Radau5 pass runs beside the deferred DOPRI5 pass
   int n_pass = 0;
   bool timed = false;
 };
@@ -262,8 +264,10 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
     }
   }
   if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess ||
-      cudaEventCreate(&m->evp[0]) != cudaSuccess || cudaEventCreate(&m->evp[1]) != cudaSuccess)
-    return bail(fail(ODL_ECUDA, "cudaEventCreate failed"));
+      cudaEventCreate(&m->evp[0]) != cudaSuccess || cudaEventCreate(&m->evp[1]) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_aux, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking) != cudaSuccess)
+    return bail(fail(ODL_ECUDA, "cudaEventCreate / cudaStreamCreate failed"));
   if ((rc = m->counter.ensure(512))) return bail(rc);
   m->on_gpu = true;
   *out = m;
@@ -281,6 +285,8 @@ extern "C" int odl_model_destroy(odl_model* m) {
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   for (auto& e : m->evp) if (e) cudaEventDestroy(e);
+  if (m->ev_aux) cudaEventDestroy(m->ev_aux);
+  if (m->aux) cudaStreamDestroy(m->aux);
   delete m;
   return 0;
 }
@@ -409,7 +415,7 @@ static void fill_opts(OdlOpts& o, const odl_solver_opts* so) {
   o.max_steps = so && so->max_steps > 0 ? so->max_steps : 500000;
   o.stiff_check = so ? so->stiff_check : 0;
   o.stiff_min_steps = so && so->stiff_min_steps > 0 ? so->stiff_min_steps : 2000;
-  o.reserved1 = 0;
+  o.defer_split_steps = 0;
 }
 
 static int launch(odl_model* m, CUfunction f, unsigned grid, unsigned block, size_t smem, cudaStream_t s, void** params) {
@@ -480,7 +486,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   OdlOpts O; fill_opts(O, so);
   ODL_CUDA(cudaMemsetAsync(m->counter.p, 0, 512, s));
   OdlData D = m->data.d;
-  auto go = [&](CUfunction f, const OdlOpts& Ox, const OdlSweepArgs& Ax, unsigned block, long long items) -> int {
+  auto go = [&](cudaStream_t sx, CUfunction f, const OdlOpts& Ox, const OdlSweepArgs& Ax, unsigned block, long long items) -> int {
     const size_t smem = smem_bytes(D, (int)block);
     if (smem > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
     int per_sm = 0;
@@ -490,52 +496,76 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)per_sm * m->sm_count));
     OdlData Dl = D; OdlOpts Ol = Ox; OdlSweepArgs Al = Ax;
     void* params[] = {&Dl, &Ol, &Al};
-    return launch(m, f, grid, block, smem, s, params);
+    return launch(m, f, grid, block, smem, sx, params);
   };
   ODL_CUDA(cudaEventRecord(m->ev0, s));
   m->n_pass = 1;
   if (solver != ODL_SOLVER_AUTO) {
     A.defer_list[0] = A.defer_list[1] = nullptr; A.defer_count[0] = A.defer_count[1] = nullptr;
     CUfunction f1 = solver == ODL_SOLVER_ROS23 ? m->k_sweep_ros : (solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau : m->k_sweep);
-    if ((rc = go(f1, O, A, solver == ODL_SOLVER_RADAU5 ? 32u : (unsigned)m->block, n))) return rc;
+    if ((rc = go(s, f1, O, A, solver == ODL_SOLVER_RADAU5 ? 32u : (unsigned)m->block, n))) return rc;
   } else {
     // Cohort passes (no host synchronisation in between; list lengths stay on the device):
     //   pass 0  DOPRI5, every system, at most cap0 attempted steps; the few that need more go to list A,
     //           those Hairer's test calls stiff go straight to list B
-    //   pass 1  DOPRI5 on list A with cap1; still unfinished or stiff -> list B
-    //   pass 2  Radau5 on list B, up to max_steps  (pass_cap1 <= pass_cap0 skips pass 1: list A is list B)
+    //           (as do those whose progress at the cap projects to more than cap1 steps)
+    //   pass 1  DOPRI5 on list A with cap1 (caller's stream)  ||  Radau5 on list B (helper stream), concurrently:
+    //           both are latency-bound on a few long systems and leave most of every SM idle on their own
+    //   pass 2  Radau5 on what pass 1 still could not finish (list C)
+    //   (pass_cap1 <= pass_cap0 skips the second DOPRI5 pass: everything deferred goes to Radau5)
     // Step counts are heavy-tailed (two_i prior: median 56, mean 103, p99.9 3200, max > 1e5): capping a pass
     // bounds how long the lanes of a warp wait for their slowest neighbour once the work counter runs dry.
     DevBuf& la = m->scratch[st.next++];
     DevBuf& lb = m->scratch[st.next++];
+    DevBuf& lc = m->scratch[st.next++];
     if ((rc = la.ensure((size_t)n * sizeof(int)))) return rc;
     if ((rc = lb.ensure((size_t)n * sizeof(int)))) return rc;
+    if ((rc = lc.ensure((size_t)n * sizeof(int)))) return rc;
     int* listA = static_cast<int*>(la.p);
     int* listB = static_cast<int*>(lb.p);
+    int* listC = static_cast<int*>(lc.p);
     const int cap0 = so && so->pass_cap0 > 0 ? so->pass_cap0 : 512;
-    const int cap1 = so && so->pass_cap1 > 0 ? so->pass_cap1 : 2048;
-    OdlOpts O0 = O; O0.stiff_check = 1; O0.max_steps = std::min(cap0, O.max_steps);
+    const int cap1 = so && so->pass_cap1 > 0 ? so->pass_cap1 : 1536;
     const bool two_dopri = cap1 > cap0;
+    // tail passes are latency-bound (a handful of long systems): modest grids so that both fit on the SMs at once
+    const long long tail_items = std::max<long long>(32, std::min<long long>(n / 16, (long long)m->sm_count * 4 * 32));
+    OdlOpts O0 = O; O0.stiff_check = 1; O0.max_steps = std::min(cap0, O.max_steps);
+    O0.defer_split_steps = two_dopri ? cap1 : 0;   // projected to need more than cap1 steps -> straight to Radau5
     OdlSweepArgs A0 = A;
     A0.defer_list[0] = two_dopri ? listA : listB; A0.defer_count[0] = two_dopri ? cnt(64) : cnt(192);
     A0.defer_list[1] = listB; A0.defer_count[1] = cnt(192);
-    if ((rc = go(m->k_sweep, O0, A0, (unsigned)m->block, n))) return rc;
+    if ((rc = go(s, m->k_sweep, O0, A0, (unsigned)m->block, n))) return rc;
     ODL_CUDA(cudaEventRecord(m->evp[0], s));
+    OdlOpts O2 = O; O2.stiff_check = 0;
     if (two_dopri) {
+      // list B (Radau5) on the helper stream, concurrently with list A (DOPRI5) on the caller's stream
+      ODL_CUDA(cudaStreamWaitEvent(m->aux, m->evp[0], 0));
+      OdlSweepArgs A2 = A;
+      A2.index = listB; A2.index_count = cnt(192); A2.counter = ctr(256);
+      A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
+      if ((rc = go(m->aux, m->k_sweep_radau, O2, A2, 32u, tail_items))) return rc;
+      ODL_CUDA(cudaEventRecord(m->ev_aux, m->aux));
       OdlOpts O1 = O; O1.stiff_check = 1; O1.max_steps = std::min(cap1, O.max_steps);
       OdlSweepArgs A1 = A;
       A1.index = listA; A1.index_count = cnt(64); A1.counter = ctr(128);
-      A1.defer_list[0] = listB; A1.defer_count[0] = cnt(192);
-      A1.defer_list[1] = listB; A1.defer_count[1] = cnt(192);
-      if ((rc = go(m->k_sweep, O1, A1, 32u, std::max<long long>(32, n / 16)))) return rc;
+      A1.defer_list[0] = listC; A1.defer_count[0] = cnt(320);
+      A1.defer_list[1] = listC; A1.defer_count[1] = cnt(320);
+      if ((rc = go(s, m->k_sweep, O1, A1, 32u, tail_items))) return rc;
+      ODL_CUDA(cudaEventRecord(m->evp[1], s));
+      ODL_CUDA(cudaStreamWaitEvent(s, m->ev_aux, 0));
+      // what DOPRI5 could not finish within cap1 after all (rare): Radau5
+      OdlSweepArgs A3 = A;
+      A3.index = listC; A3.index_count = cnt(320); A3.counter = ctr(384);
+      A3.defer_list[0] = A3.defer_list[1] = nullptr; A3.defer_count[0] = A3.defer_count[1] = nullptr;
+      if ((rc = go(s, m->k_sweep_radau, O2, A3, 32u, std::max<long long>(32, tail_items / 4)))) return rc;
+    } else {
+      ODL_CUDA(cudaEventRecord(m->evp[1], s));
+      OdlSweepArgs A2 = A;
+      A2.index = listB; A2.index_count = cnt(192); A2.counter = ctr(256);
+      A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
+      if ((rc = go(s, m->k_sweep_radau, O2, A2, 32u, tail_items))) return rc;
     }
-    ODL_CUDA(cudaEventRecord(m->evp[1], s));
     m->n_pass = 3;
-    OdlOpts O2 = O; O2.stiff_check = 0;
-    OdlSweepArgs A2 = A;
-    A2.index = listB; A2.index_count = cnt(192); A2.counter = ctr(256);
-    A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
-    if ((rc = go(m->k_sweep_radau, O2, A2, 32u, std::max<long long>(32, n / 16)))) return rc;
   }
   ODL_CUDA(cudaEventRecord(m->ev1, s));
   m->timed = true;

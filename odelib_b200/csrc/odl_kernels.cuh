@@ -713,10 +713,14 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
   odl_lu_factor(R);
   odl_clu_factor(Cx);
 
+  // RADAU5's tolerance transformation (radau5.f: RTOL' = 0.1 RTOL^(2/3), ATOL' = RTOL' ATOL/RTOL): the error
+  // estimate belongs to the embedded third-order formula while the fifth-order solution is what advances.
+  const double rtol = 0.1 * exp2(0.6666666666666666 * log2(O.rtol));
+  const double atol = rtol * (O.atol / O.rtol);
   float rsc[ODL_N];
 #pragma unroll
-  for (int i = 0; i < ODL_N; ++i) rsc[i] = __frcp_rn((float)(O.atol + O.rtol * fabs(st.y[i])));
-  const float newton_tol = fmaxf((float)(10.0 * 2.220446049250313e-16 / O.rtol), fminf(0.03f, sqrtf((float)O.rtol)));
+  for (int i = 0; i < ODL_N; ++i) rsc[i] = __frcp_rn((float)(atol + rtol * fabs(st.y[i])));
+  const float newton_tol = fmaxf((float)(10.0 * 2.220446049250313e-16 / rtol), fminf(0.03f, sqrtf((float)rtol)));
 
   double Z0[ODL_N], Z1[ODL_N], Z2[ODL_N], W0[ODL_N], W1[ODL_N], W2[ODL_N];
   if (ax.have_sol) {
@@ -809,7 +813,7 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
   float rs2[ODL_N];
 #pragma unroll
   for (int j = 0; j < ODL_N; ++j) {
-    rs2[j] = __frcp_rn((float)(O.atol + O.rtol * fmax(fabs(st.y[j]), fabs(yn[j]))));
+    rs2[j] = __frcp_rn((float)(atol + rtol * fmax(fabs(st.y[j]), fabs(yn[j]))));
     const float a = (float)er[j] * rs2[j];
     errsq += a * a;
   }
@@ -935,7 +939,14 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
         else if (nv == 0) { chi = __longlong_as_double(0x7ff8000000000000LL); status |= ODL_ALLMASKED; }
         A.chi[row] = chi; A.r2[row] = r2; A.status[row] = status;
         A.nsteps[row] = st.nsteps;
-        if (st.status == ODL_MAXSTEPS && A.defer_list[0]) A.defer_list[0][atomicAdd(A.defer_count[0], 1)] = (int)row;
+        if (st.status == ODL_MAXSTEPS && A.defer_list[0]) {
+          int which = 0;
+          if (O.defer_split_steps > 0) {
+            const double projected = (double)st.nsteps * (st.tend - D.t0) / (st.t - D.t0);
+            if (!(projected <= (double)O.defer_split_steps)) which = 1;
+          }
+          A.defer_list[which][atomicAdd(A.defer_count[which], 1)] = (int)row;
+        }
         if (st.status == ODL_STIFF && A.defer_list[1]) A.defer_list[1][atomicAdd(A.defer_count[1], 1)] = (int)row;
       }
     }

@@ -153,3 +153,20 @@ def test_full_size_properties_1m_sweep():
     # a slice recomputed alone matches
     c = dm.sweep(theta[12345:12345 + 4096])
     assert np.array_equal(c["chi"], chi[12345:12345 + 4096], equal_nan=True)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_auto_cohort_passes_solve_every_prior_draw(name):
+    """solver='auto' (DOPRI5 bulk -> DOPRI5 deferred || Radau5 -> Radau5): every prior draw ends with status 0,
+    and on the systems a single uncapped DOPRI5 launch also finishes the two agree to integration accuracy."""
+    dm, _ = device_model(name)
+    theta = prior_draws(name, 20000, seed=21)
+    auto = dm.sweep(theta, solver="auto", return_pred=True)
+    assert np.all((auto["status"] & 7) == 0)
+    plain = dm.sweep(theta, solver="dopri5", max_steps=20000, return_pred=True)
+    ok = (plain["status"] == 0) & np.all(plain["pred"] > FLOOR, axis=1) & np.all(auto["pred"] > FLOOR, axis=1)
+    assert ok.mean() > 0.5
+    np.testing.assert_allclose(auto["pred"][ok], plain["pred"][ok], rtol=2e-5)
+    np.testing.assert_allclose(auto["chi"][ok], plain["chi"][ok], rtol=2e-4, atol=1e-6)
+    same = auto["chi"][ok] == plain["chi"][ok]
+    assert same.mean() > 0.95           # the bulk never left DOPRI5: bit-identical to the single launch

@@ -29,7 +29,7 @@ def _relerr(out, ref):
     return np.nanmax(np.abs(out - ref) / (np.abs(ref) + 1.0))
 
 
-@pytest.mark.parametrize("solver,bound,max_mean_steps", [("dopri5", 5e-7, 400), ("radau5", 5e-8, 900), ("ros23", 1e-4, 8000)])
+@pytest.mark.parametrize("solver,bound,max_mean_steps", [("dopri5", 5e-7, 400), ("radau5", 1e-6, 500), ("ros23", 1e-4, 8000)])
 def test_steppers_at_default_tolerance(two_i, solver, bound, max_mean_steps):
     lib, tab, slots = two_i
     g = golden("two_i")
@@ -51,7 +51,7 @@ def test_radau5_converges_with_tolerance(two_i):
         out, st, _ = hh.solve(lib, "radau5", th, slots, tab.y0, tol, tol)
         assert st == 0
         errs.append(_relerr(out, ref))
-    assert errs[0] > errs[1] > errs[2] and errs[2] < 1e-9
+    assert errs[0] > errs[1] > errs[2] and errs[2] < 1e-8
 
 
 def test_stiff_variant_radau5_is_cheap_and_dopri5_is_not(two_i):

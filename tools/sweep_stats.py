@@ -15,13 +15,13 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 dm, tab = device_model("two_i")
 theta = torch.from_numpy(bench.prior_draws(n, 0, 0)).cuda()
 res = {}
-for mode, kw in (("dopri5_cap20k", dict(solver="dopri5", max_steps=20000)),
-                 ("auto", dict(solver="auto", max_steps=200000)),
-                 ("auto_256_4096", dict(solver="auto", max_steps=200000, pass_caps=(256, 4096))),
-                 ("auto_512_2048", dict(solver="auto", max_steps=200000, pass_caps=(512, 2048))),
-                 ("auto_512_0", dict(solver="auto", max_steps=200000, pass_caps=(512, 1))),
-                 ("auto_256_0", dict(solver="auto", max_steps=200000, pass_caps=(256, 1))),
-                 ("auto_1024_0", dict(solver="auto", max_steps=200000, pass_caps=(1024, 1))),
+for mode, kw in (("auto_512_2048", dict(solver="auto", max_steps=200000, pass_caps=(512, 2048))),
+                 ("auto_512_1536", dict(solver="auto", max_steps=200000, pass_caps=(512, 1536))),
+                 ("auto_512_1024", dict(solver="auto", max_steps=200000, pass_caps=(512, 1024))),
+                 ("auto_384_1536", dict(solver="auto", max_steps=200000, pass_caps=(384, 1536))),
+                 ("auto_384_1024", dict(solver="auto", max_steps=200000, pass_caps=(384, 1024))),
+                 ("auto_256_1024", dict(solver="auto", max_steps=200000, pass_caps=(256, 1024))),
+                 ("auto_512_3072", dict(solver="auto", max_steps=200000, pass_caps=(512, 3072))),
                  ("dopri5_cap512", dict(solver="dopri5", max_steps=512))):
     for rep in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -29,7 +29,7 @@ for mode, kw in (("dopri5_cap20k", dict(solver="dopri5", max_steps=20000)),
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
     ns = out["nsteps"].cpu().numpy(); st = out["status"].cpu().numpy()
     q = np.percentile(ns, [50, 90, 99, 99.9, 99.99, 100])
-    res[mode] = {"seconds": dt, "kernel_ms": dm.last_kernel_ms(), "solves_per_s": n / dt, "mean_steps": float(ns.mean()),
+    res[mode] = {"seconds": dt, "kernel_ms": dm.last_kernel_ms(), "pass_ms": dm.last_pass_ms(), "solves_per_s": n / dt, "mean_steps": float(ns.mean()),
                  "pct_50_90_99_999_9999_max": q.tolist(), "status_counts": {int(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))},
                  "chi_finite": int(np.isfinite(out["chi"].cpu().numpy()).sum())}
     print(mode, json.dumps(res[mode]), flush=True)
