@@ -306,6 +306,13 @@ static CUfunction kernel_by_name(const odl_model* m, const char* k) {
   return nullptr;
 }
 
+static size_t smem_bytes(const OdlData& d, int block);
+// largest CTA (<= preferred) whose tables + per-thread staging leave room for at least two CTAs per SM
+static unsigned pick_block(const OdlData& d, int preferred) {
+  int b = preferred;
+  while (b > 32 && smem_bytes(d, b) > 100 * 1024) b /= 2;
+  return (unsigned)b;
+}
 static size_t smem_bytes(const OdlData& d, int block) {
   size_t doubles = (size_t)d.n_slot + 3 * (size_t)d.n_obs + ((size_t)d.n_obs + 1) / 2 + (size_t)block * d.stage_stride;
   return doubles * sizeof(double);
@@ -503,7 +510,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   if (solver != ODL_SOLVER_AUTO) {
     A.defer_list[0] = A.defer_list[1] = nullptr; A.defer_count[0] = A.defer_count[1] = nullptr;
     CUfunction f1 = solver == ODL_SOLVER_ROS23 ? m->k_sweep_ros : (solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau : m->k_sweep);
-    if ((rc = go(s, f1, O, A, solver == ODL_SOLVER_RADAU5 ? 32u : (unsigned)m->block, n))) return rc;
+    if ((rc = go(s, f1, O, A, solver == ODL_SOLVER_RADAU5 ? 32u : pick_block(D, m->block), n))) return rc;
   } else {
     // Cohort passes (no host synchronisation in between; list lengths stay on the device):
     //   pass 0  DOPRI5, every system, at most cap0 attempted steps; the few that need more go to list A,
@@ -534,7 +541,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     OdlSweepArgs A0 = A;
     A0.defer_list[0] = two_dopri ? listA : listB; A0.defer_count[0] = two_dopri ? cnt(64) : cnt(192);
     A0.defer_list[1] = listB; A0.defer_count[1] = cnt(192);
-    if ((rc = go(s, m->k_sweep, O0, A0, (unsigned)m->block, n))) return rc;
+    if ((rc = go(s, m->k_sweep, O0, A0, pick_block(D, m->block), n))) return rc;
     ODL_CUDA(cudaEventRecord(m->evp[0], s));
     OdlOpts O2 = O; O2.stiff_check = 0;
     if (two_dopri) {
@@ -650,7 +657,7 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   OdlOpts O; fill_opts(O, so);
   OdlData D = m->data.d;
   // few chains: spread them over the SMs with one warp per CTA; many chains: full CTAs
-  unsigned block = (unsigned)m->block;
+  unsigned block = pick_block(D, m->block);
   while (block > 32 && (long long)C < (long long)m->sm_count * block * 2) block /= 2;
   if (solver == ODL_SOLVER_RADAU5) block = 32;              // that kernel is compiled for one warp per CTA
   const size_t smem = smem_bytes(D, (int)block);

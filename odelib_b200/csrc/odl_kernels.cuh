@@ -43,6 +43,15 @@
 #define ODL_MINBLOCKS_ROS (ODL_MINBLOCKS > 2 ? ODL_MINBLOCKS - 1 : ODL_MINBLOCKS)
 #endif
 
+// Small systems (n <= 8): every loop over states / parameters is unrolled and the arrays live in registers.
+// Larger systems: rolled loops, arrays in (L1-resident) local memory -- functional, not yet tuned.
+#if ODL_N <= 8
+#define ODL_UNROLL _Pragma("unroll")
+#define ODL_SMALL 1
+#else
+#define ODL_UNROLL _Pragma("unroll 1")
+#define ODL_SMALL 0
+#endif
 #define ODL_FULL 0xffffffffu
 #define ODL_DBL_MIN 2.2250738585072014e-308
 #define ODL_DBL_MAX 1.7976931348623157e308
@@ -209,12 +218,12 @@ __constant__ double ODL_TAB[36] = {
 
 __device__ __forceinline__ void odl_init_system(OdlStepper& st, const double (&p)[ODL_P], const OdlData& D,
                                                 const OdlOpts& O, const double* y0_override) {
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) {
     double v = y0_override ? y0_override[i] : D.y0[i];
 #if ODL_Y0P
     const int src = D.y0_from_param[i];
-#pragma unroll
+ODL_UNROLL
     for (int q = 0; q < ODL_P; ++q) if (src == q) v = p[q];     // '<state>0' parameters (Samplers.py:110-114)
 #endif
     st.y[i] = v;
@@ -232,7 +241,7 @@ __device__ __forceinline__ void odl_init_system(OdlStepper& st, const double (&p
     // A heuristic -> fp32 norms (SFU reciprocal / pow), guarded below against overflow.
     double dnf = 0.0, dny = 0.0;
     double rsk[ODL_N];
-#pragma unroll
+ODL_UNROLL
     for (int i = 0; i < ODL_N; ++i) {
       rsk[i] = odl_rcp_approx(O.atol + O.rtol * fabs(st.y[i]));
       const double a = st.k1[i] * rsk[i], b = st.y[i] * rsk[i];
@@ -242,11 +251,11 @@ __device__ __forceinline__ void odl_init_system(OdlStepper& st, const double (&p
     const float hf = (fnf <= 1e-10f || fny <= 1e-10f) ? 1e-6f : 0.01f * sqrtf(fny * __frcp_rn(fnf));
     h = fmin((double)hf, hmax);
     double y1[ODL_N], f1[ODL_N];
-#pragma unroll
+ODL_UNROLL
     for (int i = 0; i < ODL_N; ++i) y1[i] = st.y[i] + h * st.k1[i];
     odl_rhs(y1, st.t + h, p, f1);
     double d2 = 0.0;
-#pragma unroll
+ODL_UNROLL
     for (int i = 0; i < ODL_N; ++i) {
       const double a = (f1[i] - st.k1[i]) * rsk[i];
       d2 += a * a;
@@ -283,27 +292,27 @@ __device__ __forceinline__ void odl_dopri5_attempt(OdlStepper& st, const double 
 #endif
   ++st.nsteps;
   double k2[ODL_N], k3[ODL_N], k4[ODL_N], k5[ODL_N], k6[ODL_N], k7[ODL_N], yt[ODL_N], yn[ODL_N];
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) yt[i] = st.y[i] + h * (ODL_T(0) * st.k1[i]);
   odl_rhs(yt, t + ODL_T(0) * h, p, k2);
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) yt[i] = st.y[i] + h * (ODL_T(1) * st.k1[i] + ODL_T(2) * k2[i]);
   odl_rhs(yt, t + ODL_T(32) * h, p, k3);
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i)
     yt[i] = st.y[i] + h * (ODL_T(3) * st.k1[i] + ODL_T(4) * k2[i] + ODL_T(5) * k3[i]);
   odl_rhs(yt, t + ODL_T(33) * h, p, k4);
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i)
     yt[i] = st.y[i] + h * (ODL_T(6) * st.k1[i] + ODL_T(7) * k2[i] + ODL_T(8) * k3[i] + ODL_T(9) * k4[i]);
   odl_rhs(yt, t + ODL_T(34) * h, p, k5);
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i)
     yt[i] = st.y[i] + h * (ODL_T(10) * st.k1[i] + ODL_T(11) * k2[i] + ODL_T(12) * k3[i] + ODL_T(13) * k4[i] +
                            ODL_T(14) * k5[i]);
   const double tph = t + h;
   odl_rhs(yt, tph, p, k6);
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i)
     yn[i] = st.y[i] + h * (ODL_T(15) * st.k1[i] + ODL_T(16) * k3[i] + ODL_T(17) * k4[i] + ODL_T(18) * k5[i] +
                            ODL_T(19) * k6[i]);
@@ -312,7 +321,7 @@ __device__ __forceinline__ void odl_dopri5_attempt(OdlStepper& st, const double 
   // embedded error estimate, scaled RMS norm
   double errsq = 0.0;
   bool finite_all = true;
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) {
     const double e = h * (ODL_T(20) * st.k1[i] + ODL_T(21) * k3[i] + ODL_T(22) * k4[i] + ODL_T(23) * k5[i] +
                           ODL_T(24) * k6[i] + ODL_T(25) * k7[i]);
@@ -333,7 +342,7 @@ __device__ __forceinline__ void odl_dopri5_attempt(OdlStepper& st, const double 
     if (O.stiff_check && ((st.nsteps % 10) == 0 || st.iasti > 0)) {
       // Hairer's test: h * |k7 - k6| / |ynew - y6| approximates h * |lambda_max|
       double num = 0.0, den = 0.0;
-#pragma unroll
+ODL_UNROLL
       for (int i = 0; i < ODL_N; ++i) {
         const double a = k7[i] - k6[i], b = yn[i] - yt[i];
         num += a * a; den += b * b;
@@ -356,7 +365,7 @@ __device__ __forceinline__ void odl_dopri5_attempt(OdlStepper& st, const double 
 #if ODL_DENSE
     if (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew) {
       double rc2[ODL_N], rc3[ODL_N], rc4[ODL_N], rc5[ODL_N];
-#pragma unroll
+ODL_UNROLL
       for (int i = 0; i < ODL_N; ++i) {
         rc2[i] = yn[i] - st.y[i];
         rc3[i] = h * st.k1[i] - rc2[i];
@@ -368,7 +377,7 @@ __device__ __forceinline__ void odl_dopri5_attempt(OdlStepper& st, const double 
       do {
         const double th = (S.slot_t[st.slot] - t) * rh, th1 = 1.0 - th;
         double yi[ODL_N];
-#pragma unroll
+ODL_UNROLL
         for (int i = 0; i < ODL_N; ++i)
           yi[i] = st.y[i] + th * (rc2[i] + th1 * (rc3[i] + th * (rc4[i] + th1 * rc5[i])));
         sink(st.slot, yi);
@@ -382,7 +391,7 @@ __device__ __forceinline__ void odl_dopri5_attempt(OdlStepper& st, const double 
       hnew = fmax(hnew, h_untrunc);
     }
 #endif
-#pragma unroll
+ODL_UNROLL
     for (int i = 0; i < ODL_N; ++i) { st.y[i] = yn[i]; st.k1[i] = k7[i]; }
     st.t = tnew;
     if (st.last_rejected) hnew = fmin(hnew, h);
@@ -413,14 +422,14 @@ struct OdlStageSink {            // observation columns -> per-thread shared sta
   __device__ __forceinline__ void operator()(int slot, const double (&yi)[ODL_N]) {
     double out[ODL_NOUT];
     odl_observe(yi, out);
-#pragma unroll
+ODL_UNROLL
     for (int c = 0; c < ODL_NOUT; ++c) stage[slot * ODL_NOUT + c] = out[c];
   }
 };
 struct OdlTrajSink {             // raw states -> global trajectory
   double* traj;
   __device__ __forceinline__ void operator()(int slot, const double (&yi)[ODL_N]) {
-#pragma unroll
+ODL_UNROLL
     for (int i = 0; i < ODL_N; ++i) traj[(long long)slot * ODL_N + i] = yi[i];
   }
 };
@@ -435,6 +444,7 @@ struct OdlTrajSink {             // raw states -> global trajectory
 #define ODL_ROS_D 0.29289321881345254      /* 1/(2+sqrt 2) */
 #define ODL_ROS_E32 7.414213562373095      /* 6+sqrt 2 */
 
+#if ODL_SMALL
 struct OdlLU {
   double a[ODL_N][ODL_N];
   double inv[ODL_N];
@@ -443,14 +453,14 @@ struct OdlLU {
 __device__ __forceinline__ void odl_lu_factor(OdlLU& F) {
   unsigned long long sw = 0ull;
   int bit = 0;
-#pragma unroll
+ODL_UNROLL
   for (int k = 0; k < ODL_N; ++k) {
-#pragma unroll
+ODL_UNROLL
     for (int i = k + 1; i < ODL_N; ++i) {
       const bool s = fabs(F.a[i][k]) > fabs(F.a[k][k]);
       if (s) sw |= (1ull << (bit & 63));
       ++bit;
-#pragma unroll
+ODL_UNROLL
       for (int j = 0; j < ODL_N; ++j) {
         const double u = F.a[k][j], v = F.a[i][j];
         F.a[k][j] = s ? v : u;
@@ -458,11 +468,11 @@ __device__ __forceinline__ void odl_lu_factor(OdlLU& F) {
       }
     }
     F.inv[k] = 1.0 / F.a[k][k];
-#pragma unroll
+ODL_UNROLL
     for (int i = k + 1; i < ODL_N; ++i) {
       const double l = F.a[i][k] * F.inv[k];
       F.a[i][k] = l;
-#pragma unroll
+ODL_UNROLL
       for (int j = k + 1; j < ODL_N; ++j) F.a[i][j] -= l * F.a[k][j];
     }
   }
@@ -470,9 +480,9 @@ __device__ __forceinline__ void odl_lu_factor(OdlLU& F) {
 }
 __device__ __forceinline__ void odl_lu_solve(const OdlLU& F, double (&b)[ODL_N]) {
   int bit = 0;
-#pragma unroll
+ODL_UNROLL
   for (int k = 0; k < ODL_N; ++k) {
-#pragma unroll
+ODL_UNROLL
     for (int i = k + 1; i < ODL_N; ++i) {
       const bool s = (F.swaps >> (bit & 63)) & 1ull;
       ++bit;
@@ -480,22 +490,58 @@ __device__ __forceinline__ void odl_lu_solve(const OdlLU& F, double (&b)[ODL_N])
       b[k] = s ? v : u;
       b[i] = s ? u : v;
     }
-#pragma unroll
+ODL_UNROLL
     for (int i = k + 1; i < ODL_N; ++i) b[i] -= F.a[i][k] * b[k];
   }
-#pragma unroll
+ODL_UNROLL
   for (int k = ODL_N - 1; k >= 0; --k) {
     double acc = b[k];
-#pragma unroll
+ODL_UNROLL
     for (int j = k + 1; j < ODL_N; ++j) acc -= F.a[k][j] * b[j];
     b[k] = acc * F.inv[k];
   }
 }
 
+#else
+struct OdlLU {
+  double a[ODL_N][ODL_N];
+  double inv[ODL_N];
+  int piv[ODL_N];
+};
+__device__ __forceinline__ void odl_lu_factor(OdlLU& F) {
+  for (int k = 0; k < ODL_N; ++k) {
+    int best = k;
+    double big = fabs(F.a[k][k]);
+    for (int i = k + 1; i < ODL_N; ++i) { const double v = fabs(F.a[i][k]); if (v > big) { big = v; best = i; } }
+    F.piv[k] = best;
+    if (best != k) for (int j = 0; j < ODL_N; ++j) { const double u = F.a[k][j]; F.a[k][j] = F.a[best][j]; F.a[best][j] = u; }
+    F.inv[k] = 1.0 / F.a[k][k];
+    for (int i = k + 1; i < ODL_N; ++i) {
+      const double l = F.a[i][k] * F.inv[k];
+      F.a[i][k] = l;
+      if (l != 0.0) for (int j = k + 1; j < ODL_N; ++j) F.a[i][j] -= l * F.a[k][j];
+    }
+  }
+}
+__device__ __forceinline__ void odl_lu_solve(const OdlLU& F, double (&b)[ODL_N]) {
+  for (int k = 0; k < ODL_N; ++k) {
+    const int q = F.piv[k];
+    const double u = b[k]; b[k] = b[q]; b[q] = u;
+    const double bk = b[k];
+    if (bk != 0.0) for (int i = k + 1; i < ODL_N; ++i) b[i] -= F.a[i][k] * bk;
+  }
+  for (int k = ODL_N - 1; k >= 0; --k) {
+    double acc = b[k];
+    for (int j = k + 1; j < ODL_N; ++j) acc -= F.a[k][j] * b[j];
+    b[k] = acc * F.inv[k];
+  }
+}
+
+#endif  // ODL_SMALL
+
 template <class Sink>
 __device__ __forceinline__ void odl_ros23_attempt(OdlStepper& st, const double (&p)[ODL_P], const OdlShared& S,
                                                   const OdlData& D, const OdlOpts& O, Sink& sink) {
-  static_assert(ODL_N * (ODL_N - 1) / 2 <= 64, "ROS23 pivot mask holds at most 64 swap decisions (n <= 11)");
   const double t = st.t;
   double h = st.h;
   bool last = false;
@@ -503,40 +549,40 @@ __device__ __forceinline__ void odl_ros23_attempt(OdlStepper& st, const double (
   ++st.nsteps;
   OdlLU F;
   odl_jac(st.y, t, p, F.a);
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i)
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) F.a[i][j] = ((i == j) ? 1.0 : 0.0) - (h * ODL_ROS_D) * F.a[i][j];
   odl_lu_factor(F);
   double hdT[ODL_N];
 #if ODL_AUTONOMOUS
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) hdT[i] = 0.0;
 #else
   odl_dfdt(st.y, t, p, hdT);
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) hdT[i] *= h * ODL_ROS_D;
 #endif
   double k1[ODL_N], k2[ODL_N], k3[ODL_N], F1[ODL_N], F2[ODL_N], yt[ODL_N], yn[ODL_N];
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) k1[i] = st.k1[i] + hdT[i];
   odl_lu_solve(F, k1);
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) yt[i] = st.y[i] + (0.5 * h) * k1[i];
   odl_rhs(yt, t + 0.5 * h, p, F1);
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) k2[i] = F1[i] - k1[i];
   odl_lu_solve(F, k2);
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) { k2[i] += k1[i]; yn[i] = st.y[i] + h * k2[i]; }
   const double tph = t + h;
   odl_rhs(yn, tph, p, F2);
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) k3[i] = F2[i] - ODL_ROS_E32 * (k2[i] - F1[i]) - 2.0 * (k1[i] - st.k1[i]) + hdT[i];
   odl_lu_solve(F, k3);
   float errsq = 0.f;
   bool finite_all = true;
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) {
     const double e = (h * (1.0 / 6.0)) * (k1[i] - 2.0 * k2[i] + k3[i]);
     const double sk = O.atol + O.rtol * fmax(fabs(st.y[i]), fabs(yn[i]));
@@ -555,13 +601,13 @@ __device__ __forceinline__ void odl_ros23_attempt(OdlStepper& st, const double (
         const double c1 = s1 * (1.0 - s1) * (1.0 / (1.0 - 2.0 * ODL_ROS_D));
         const double c2 = s1 * (s1 - 2.0 * ODL_ROS_D) * (1.0 / (1.0 - 2.0 * ODL_ROS_D));
         double yi[ODL_N];
-#pragma unroll
+ODL_UNROLL
         for (int i = 0; i < ODL_N; ++i) yi[i] = st.y[i] + h * (c1 * k1[i] + c2 * k2[i]);
         sink(st.slot, yi);
         ++st.slot;
       } while (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew);
     }
-#pragma unroll
+ODL_UNROLL
     for (int i = 0; i < ODL_N; ++i) { st.y[i] = yn[i]; st.k1[i] = F2[i]; }
     st.t = tnew;
     if (st.last_rejected) hnew = fmin(hnew, h);
@@ -595,6 +641,7 @@ __device__ __forceinline__ void odl_ros23_attempt(OdlStepper& st, const double (
 #define ODL_RAD_C1 0.6449489742783178              /* (4 + sqrt 6)/10 */
 #define ODL_RAD_NEWTON 6
 
+#if ODL_SMALL
 struct OdlCLU {                  // complex LU in split storage
   double ar[ODL_N][ODL_N], ai[ODL_N][ODL_N];
   double ir[ODL_N], ii[ODL_N];   // reciprocal pivots
@@ -603,14 +650,14 @@ struct OdlCLU {                  // complex LU in split storage
 __device__ __forceinline__ void odl_clu_factor(OdlCLU& F) {
   unsigned long long sw = 0ull;
   int bit = 0;
-#pragma unroll
+ODL_UNROLL
   for (int k = 0; k < ODL_N; ++k) {
-#pragma unroll
+ODL_UNROLL
     for (int i = k + 1; i < ODL_N; ++i) {
       const bool s = (fabs(F.ar[i][k]) + fabs(F.ai[i][k])) > (fabs(F.ar[k][k]) + fabs(F.ai[k][k]));
       if (s) sw |= (1ull << (bit & 63));
       ++bit;
-#pragma unroll
+ODL_UNROLL
       for (int j = 0; j < ODL_N; ++j) {
         const double ur = F.ar[k][j], vr = F.ar[i][j], ui = F.ai[k][j], vi = F.ai[i][j];
         F.ar[k][j] = s ? vr : ur; F.ar[i][j] = s ? ur : vr;
@@ -620,12 +667,12 @@ __device__ __forceinline__ void odl_clu_factor(OdlCLU& F) {
     const double pr = F.ar[k][k], pi = F.ai[k][k];
     const double den = 1.0 / (pr * pr + pi * pi);
     F.ir[k] = pr * den; F.ii[k] = -pi * den;
-#pragma unroll
+ODL_UNROLL
     for (int i = k + 1; i < ODL_N; ++i) {
       const double lr = F.ar[i][k] * F.ir[k] - F.ai[i][k] * F.ii[k];
       const double li = F.ar[i][k] * F.ii[k] + F.ai[i][k] * F.ir[k];
       F.ar[i][k] = lr; F.ai[i][k] = li;
-#pragma unroll
+ODL_UNROLL
       for (int j = k + 1; j < ODL_N; ++j) {
         F.ar[i][j] -= lr * F.ar[k][j] - li * F.ai[k][j];
         F.ai[i][j] -= lr * F.ai[k][j] + li * F.ar[k][j];
@@ -636,9 +683,9 @@ __device__ __forceinline__ void odl_clu_factor(OdlCLU& F) {
 }
 __device__ __forceinline__ void odl_clu_solve(const OdlCLU& F, double (&br)[ODL_N], double (&bi)[ODL_N]) {
   int bit = 0;
-#pragma unroll
+ODL_UNROLL
   for (int k = 0; k < ODL_N; ++k) {
-#pragma unroll
+ODL_UNROLL
     for (int i = k + 1; i < ODL_N; ++i) {
       const bool s = (F.swaps >> (bit & 63)) & 1ull;
       ++bit;
@@ -646,16 +693,16 @@ __device__ __forceinline__ void odl_clu_solve(const OdlCLU& F, double (&br)[ODL_
       br[k] = s ? vr : ur; br[i] = s ? ur : vr;
       bi[k] = s ? vi : ui; bi[i] = s ? ui : vi;
     }
-#pragma unroll
+ODL_UNROLL
     for (int i = k + 1; i < ODL_N; ++i) {
       br[i] -= F.ar[i][k] * br[k] - F.ai[i][k] * bi[k];
       bi[i] -= F.ar[i][k] * bi[k] + F.ai[i][k] * br[k];
     }
   }
-#pragma unroll
+ODL_UNROLL
   for (int k = ODL_N - 1; k >= 0; --k) {
     double xr = br[k], xi = bi[k];
-#pragma unroll
+ODL_UNROLL
     for (int j = k + 1; j < ODL_N; ++j) {
       xr -= F.ar[k][j] * br[j] - F.ai[k][j] * bi[j];
       xi -= F.ar[k][j] * bi[j] + F.ai[k][j] * br[j];
@@ -664,6 +711,59 @@ __device__ __forceinline__ void odl_clu_solve(const OdlCLU& F, double (&br)[ODL_
     bi[k] = xr * F.ii[k] + xi * F.ir[k];
   }
 }
+
+#else
+struct OdlCLU {
+  double ar[ODL_N][ODL_N], ai[ODL_N][ODL_N];
+  double ir[ODL_N], ii[ODL_N];
+  int piv[ODL_N];
+};
+__device__ __forceinline__ void odl_clu_factor(OdlCLU& F) {
+  for (int k = 0; k < ODL_N; ++k) {
+    int best = k;
+    double big = fabs(F.ar[k][k]) + fabs(F.ai[k][k]);
+    for (int i = k + 1; i < ODL_N; ++i) { const double v = fabs(F.ar[i][k]) + fabs(F.ai[i][k]); if (v > big) { big = v; best = i; } }
+    F.piv[k] = best;
+    if (best != k) for (int j = 0; j < ODL_N; ++j) {
+      double u = F.ar[k][j]; F.ar[k][j] = F.ar[best][j]; F.ar[best][j] = u;
+      u = F.ai[k][j]; F.ai[k][j] = F.ai[best][j]; F.ai[best][j] = u;
+    }
+    const double pr = F.ar[k][k], pi = F.ai[k][k];
+    const double den = 1.0 / (pr * pr + pi * pi);
+    F.ir[k] = pr * den; F.ii[k] = -pi * den;
+    for (int i = k + 1; i < ODL_N; ++i) {
+      const double lr = F.ar[i][k] * F.ir[k] - F.ai[i][k] * F.ii[k];
+      const double li = F.ar[i][k] * F.ii[k] + F.ai[i][k] * F.ir[k];
+      F.ar[i][k] = lr; F.ai[i][k] = li;
+      if (lr != 0.0 || li != 0.0) for (int j = k + 1; j < ODL_N; ++j) {
+        F.ar[i][j] -= lr * F.ar[k][j] - li * F.ai[k][j];
+        F.ai[i][j] -= lr * F.ai[k][j] + li * F.ar[k][j];
+      }
+    }
+  }
+}
+__device__ __forceinline__ void odl_clu_solve(const OdlCLU& F, double (&br)[ODL_N], double (&bi)[ODL_N]) {
+  for (int k = 0; k < ODL_N; ++k) {
+    const int q = F.piv[k];
+    double u = br[k]; br[k] = br[q]; br[q] = u;
+    u = bi[k]; bi[k] = bi[q]; bi[q] = u;
+    for (int i = k + 1; i < ODL_N; ++i) {
+      br[i] -= F.ar[i][k] * br[k] - F.ai[i][k] * bi[k];
+      bi[i] -= F.ar[i][k] * bi[k] + F.ai[i][k] * br[k];
+    }
+  }
+  for (int k = ODL_N - 1; k >= 0; --k) {
+    double xr = br[k], xi = bi[k];
+    for (int j = k + 1; j < ODL_N; ++j) {
+      xr -= F.ar[k][j] * br[j] - F.ai[k][j] * bi[j];
+      xi -= F.ar[k][j] * bi[j] + F.ai[k][j] * br[j];
+    }
+    br[k] = xr * F.ir[k] - xi * F.ii[k];
+    bi[k] = xr * F.ii[k] + xi * F.ir[k];
+  }
+}
+
+#endif  // ODL_SMALL
 
 struct OdlRadauAux {
   double Q[3][ODL_N];            // collocation polynomial of the last accepted step: y(t0 + x h) = y0 + Q0 x + Q1 x^2 + Q2 x^3
@@ -677,7 +777,6 @@ struct OdlNoAux { __device__ __forceinline__ void reset() {} };
 template <class Sink>
 __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& ax, const double (&p)[ODL_P],
                                                    const OdlShared& S, const OdlData& D, const OdlOpts& O, Sink& sink) {
-  static_assert(ODL_N * (ODL_N - 1) / 2 <= 64, "pivot mask holds at most 64 swap decisions (n <= 11)");
   // transformation matrices of RADAU5 (eigen-decomposition of A^-1), TI = T^-1
   const double T00 = 0.09443876248897524, T01 = -0.1412552950209542, T02 = 0.03002919410514742;
   const double T10 = 0.2502131229653333, T11 = 0.20412935229379994, T12 = -0.3829421127572619;
@@ -701,9 +800,9 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
   {
     double J[ODL_N][ODL_N];
     odl_jac(st.y, t, p, J);
-#pragma unroll
+ODL_UNROLL
     for (int i = 0; i < ODL_N; ++i)
-#pragma unroll
+ODL_UNROLL
       for (int j = 0; j < ODL_N; ++j) {
         R.a[i][j] = ((i == j) ? mr : 0.0) - J[i][j];
         Cx.ar[i][j] = ((i == j) ? ca : 0.0) - J[i][j];
@@ -718,7 +817,7 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
   const double rtol = 0.1 * exp2(0.6666666666666666 * log2(O.rtol));
   const double atol = rtol * (O.atol / O.rtol);
   float rsc[ODL_N];
-#pragma unroll
+ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) rsc[i] = __frcp_rn((float)(atol + rtol * fabs(st.y[i])));
   const float newton_tol = fmaxf((float)(10.0 * 2.220446049250313e-16 / rtol), fminf(0.03f, sqrtf((float)rtol)));
 
@@ -726,7 +825,7 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
   if (ax.have_sol) {
     const double r = h / ax.h_old;
     const double x0 = 1.0 + r * ODL_RAD_C0, x1 = 1.0 + r * ODL_RAD_C1, x2 = 1.0 + r;
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) {
       const double q0 = ax.Q[0][j], q1 = ax.Q[1][j], q2 = ax.Q[2][j];
       const double one = q0 + q1 + q2;
@@ -735,10 +834,10 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
       Z2[j] = x2 * (q0 + x2 * (q1 + x2 * q2)) - one;
     }
   } else {
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) { Z0[j] = 0.0; Z1[j] = 0.0; Z2[j] = 0.0; }
   }
-#pragma unroll
+ODL_UNROLL
   for (int j = 0; j < ODL_N; ++j) {
     W0[j] = I00 * Z0[j] + I01 * Z1[j] + I02 * Z2[j];
     W1[j] = I10 * Z0[j] + I11 * Z1[j] + I12 * Z2[j];
@@ -750,18 +849,18 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
   for (int k = 0; k < ODL_RAD_NEWTON; ++k) {
     ++n_iter;
     double F0[ODL_N], F1[ODL_N], F2[ODL_N], yt[ODL_N];
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) yt[j] = st.y[j] + Z0[j];
     odl_rhs(yt, t + ODL_RAD_C0 * h, p, F0);
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) yt[j] = st.y[j] + Z1[j];
     odl_rhs(yt, t + ODL_RAD_C1 * h, p, F1);
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) yt[j] = st.y[j] + Z2[j];
     odl_rhs(yt, t + h, p, F2);
     bool fin = true;
     double dr[ODL_N], dcr[ODL_N], dci[ODL_N];
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) {
       fin = fin && odl_finite(F0[j]) && odl_finite(F1[j]) && odl_finite(F2[j]);
       dr[j] = I00 * F0[j] + I01 * F1[j] + I02 * F2[j] - mr * W0[j];
@@ -772,7 +871,7 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
     odl_lu_solve(R, dr);
     odl_clu_solve(Cx, dcr, dci);
     float nrm = 0.f;
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) {
       const float a = (float)dr[j] * rsc[j], b = (float)dcr[j] * rsc[j], c = (float)dci[j] * rsc[j];
       nrm += a * a + b * b + c * c;
@@ -781,7 +880,7 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
     if (!(dwn == dwn)) break;
     if (dwn_old >= 0.f) rate = dwn / dwn_old;
     if (rate >= 0.f && (rate >= 1.f || __powf(rate, (float)(ODL_RAD_NEWTON - k)) / (1.f - rate) * dwn > newton_tol)) break;
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) {
       W0[j] += dr[j]; W1[j] += dcr[j]; W2[j] += dci[j];
       Z0[j] = T00 * W0[j] + T01 * W1[j] + T02 * W2[j];
@@ -802,7 +901,7 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
   const double rh = 1.0 / h;
   float errsq = 0.f;
   bool finite_all = true;
-#pragma unroll
+ODL_UNROLL
   for (int j = 0; j < ODL_N; ++j) {
     yn[j] = st.y[j] + Z2[j];
     ze[j] = (E0 * Z0[j] + E1 * Z1[j] + E2 * Z2[j]) * rh;
@@ -811,7 +910,7 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
   }
   odl_lu_solve(R, er);
   float rs2[ODL_N];
-#pragma unroll
+ODL_UNROLL
   for (int j = 0; j < ODL_N; ++j) {
     rs2[j] = __frcp_rn((float)(atol + rtol * fmax(fabs(st.y[j]), fabs(yn[j]))));
     const float a = (float)er[j] * rs2[j];
@@ -821,14 +920,14 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
   const float safety = 0.9f * (2 * ODL_RAD_NEWTON + 1) / (float)(2 * ODL_RAD_NEWTON + n_iter);
   if (ax.rejected && err > 1.0f) {
     double yt[ODL_N], fe[ODL_N];
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) yt[j] = st.y[j] + er[j];
     odl_rhs(yt, t, p, fe);
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) er[j] = fe[j] + ze[j];
     odl_lu_solve(R, er);
     errsq = 0.f;
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) { const float a = (float)er[j] * rs2[j]; errsq += a * a; }
     err = sqrtf(errsq * (1.0f / ODL_N));
   }
@@ -847,7 +946,7 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
   }
   // ---- accepted ----
   const double tnew = last ? st.tend : t + h;
-#pragma unroll
+ODL_UNROLL
   for (int j = 0; j < ODL_N; ++j) {
     ax.Q[0][j] = P00 * Z0[j] + P10 * Z1[j] + P20 * Z2[j];
     ax.Q[1][j] = P01 * Z0[j] + P11 * Z1[j] + P21 * Z2[j];
@@ -856,12 +955,12 @@ __device__ __forceinline__ void odl_radau5_attempt(OdlStepper& st, OdlRadauAux& 
   while (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew) {
     const double x = (S.slot_t[st.slot] - t) * rh;
     double yi[ODL_N];
-#pragma unroll
+ODL_UNROLL
     for (int j = 0; j < ODL_N; ++j) yi[j] = st.y[j] + x * (ax.Q[0][j] + x * (ax.Q[1][j] + x * ax.Q[2][j]));
     sink(st.slot, yi);
     ++st.slot;
   }
-#pragma unroll
+ODL_UNROLL
   for (int j = 0; j < ODL_N; ++j) st.y[j] = yn[j];
   odl_rhs(st.y, tnew, p, st.k1);
   st.t = tnew;
@@ -959,7 +1058,7 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
         if (got >= 0 && got < n) {
           sys = got;
           row = A.index ? (long long)A.index[sys] : sys;
-#pragma unroll
+ODL_UNROLL
           for (int q = 0; q < ODL_P; ++q) p[q] = A.theta[row * ODL_P + q];
           odl_init_system(st, p, D, O, nullptr);
           ax.reset();
@@ -997,7 +1096,7 @@ odl_traj_kernel(const OdlData D, const OdlOpts O, const OdlTrajArgs A) {
   const long long sys = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (sys >= A.n) return;
   double p[ODL_P];
-#pragma unroll
+ODL_UNROLL
   for (int q = 0; q < ODL_P; ++q) p[q] = A.theta[sys * ODL_P + q];
   OdlStepper st;
   OdlTrajSink sink; sink.traj = A.traj + sys * (long long)D.n_slot * ODL_N;
@@ -1018,11 +1117,11 @@ odl_traj_kernel(const OdlData D, const OdlOpts O, const OdlTrajArgs A) {
 __device__ __forceinline__ void odl_propose(double (&p)[ODL_P], const OdlMcmcArgs& A, int chain_local, int it) {
   // theta' = exp(log(theta_old) + N(0, step_sd))   for every walking parameter (Framework.py:119)
   const double* cur = A.theta_cur + (size_t)chain_local * ODL_P;
-#pragma unroll
+ODL_UNROLL
   for (int q = 0; q < ODL_P; ++q) p[q] = cur[q];
   const long long k = (long long)chain_local * A.n_iter_total + (it - 1);
   if (A.rng_mode == 2) {
-#pragma unroll
+ODL_UNROLL
     for (int q = 0; q < ODL_P; ++q) p[q] = A.forced[k * ODL_P + q];
     return;
   }
@@ -1043,11 +1142,16 @@ __device__ __forceinline__ void odl_propose(double (&p)[ODL_P], const OdlMcmcArg
       z0 = A.step_sd * (rad * cs);
       z1 = A.step_sd * (rad * sn);
     }
-#pragma unroll
+#if ODL_SMALL
+ODL_UNROLL
     for (int q = 0; q < ODL_P; ++q) {
       if (A.walk[j] == q) p[q] = exp(log(p[q]) + z0);
       if (j + 1 < A.n_walk && A.walk[j + 1] == q) p[q] = exp(log(p[q]) + z1);
     }
+#else
+    p[A.walk[j]] = exp(log(p[A.walk[j]]) + z0);
+    if (j + 1 < A.n_walk) p[A.walk[j + 1]] = exp(log(p[A.walk[j + 1]]) + z1);
+#endif
   }
 }
 
@@ -1086,7 +1190,7 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
   if (has_chain) {
     if (A.it_begin == 1) {
       apriori = true;
-#pragma unroll
+ODL_UNROLL
       for (int q = 0; q < ODL_P; ++q) p[q] = A.theta_cur[(size_t)chain * ODL_P + q];
     } else {
       chi_cur = A.chain_state[(size_t)chain * 4 + 0];
@@ -1150,7 +1254,7 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
         const bool accept = acc > u;                             // :127  (NaN compares false => reject)
         if (accept) {
           chi_cur = my_chi; r2_cur = my_r2; ++accepts;
-#pragma unroll
+ODL_UNROLL
           for (int q = 0; q < ODL_P; ++q) cur[q] = p[q];
         }
         const long long k = (long long)chain * A.n_iter_total + (it - 1);
@@ -1160,7 +1264,7 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
           const int rowi = it - A.burnin - 1;
           if (A.samples && rowi < A.n_keep) {
             double* row = A.samples + ((size_t)chain * A.n_keep + rowi) * A.row_stride;
-#pragma unroll
+ODL_UNROLL
             for (int q = 0; q < ODL_P; ++q) row[q] = cur[q];
             row[ODL_P + 0] = chi_cur;
             row[ODL_P + 1] = r2_cur;
@@ -1172,7 +1276,7 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
             double* sm = A.summaries + (size_t)chain * (1 + 2 * ODL_P);
             const double cnt = sm[0] + 1.0;
             sm[0] = cnt;
-#pragma unroll
+ODL_UNROLL
             for (int q = 0; q < ODL_P; ++q) {
               const double x = log(cur[q]);
               const double dlt = x - sm[1 + q];

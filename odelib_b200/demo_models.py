@@ -70,3 +70,46 @@ PRIORS = {
     "one_i": {"mu": (3, 1e-8), "phi": (3, 1e-8), "beta": (1, 20), "lam": (2, 0.1)},
     "two_i": {"mu": (3, 1e-8), "phi": (3, 1e-8), "beta": (1, 20), "lam": (2, 0.1), "tau": (2, 1)},
 }
+
+
+def network(n_host=5, n_virus=5):
+    """Multi-strain host-virus network (BASELINE.json config 5).
+
+    States: S_i (n_host), I_ij (n_host*n_virus, row-major), V_j (n_virus).
+    Parameters: mu_i (n_host), phi_ij (n_host*n_virus), beta_j (n_virus), lam_j (n_virus).
+    dS_i = mu_i S_i - sum_j phi_ij S_i V_j;  dI_ij = phi_ij S_i V_j - lam_j I_ij;
+    dV_j = sum_i beta_j lam_j I_ij - sum_i phi_ij S_i V_j.
+    Observables: H_i = S_i + sum_j I_ij and V_j."""
+    H, V = n_host, n_virus
+
+    def model(y, t, ps):
+        S = [y[i] for i in range(H)]
+        I = [[y[H + i * V + j] for j in range(V)] for i in range(H)]
+        Vv = [y[H + H * V + j] for j in range(V)]
+        mu = [ps[i] for i in range(H)]
+        phi = [[ps[H + i * V + j] for j in range(V)] for i in range(H)]
+        beta = [ps[H + H * V + j] for j in range(V)]
+        lam = [ps[H + H * V + V + j] for j in range(V)]
+        inf = [[phi[i][j] * S[i] * Vv[j] for j in range(V)] for i in range(H)]
+        dS = []
+        for i in range(H):
+            acc = mu[i] * S[i]
+            for j in range(V):
+                acc = acc - inf[i][j]
+            dS.append(acc)
+        dI = [inf[i][j] - lam[j] * I[i][j] for i in range(H) for j in range(V)]
+        dV = []
+        for j in range(V):
+            acc = beta[j] * lam[j] * I[0][j]
+            for i in range(1, H):
+                acc = acc + beta[j] * lam[j] * I[i][j]
+            for i in range(H):
+                acc = acc - inf[i][j]
+            dV.append(acc)
+        return np.array(dS + dI + dV)
+
+    model.__name__ = f"network_{H}x{V}"
+    n_state = H + H * V + V
+    n_param = H + H * V + V + V
+    groups = [tuple([i] + [H + i * V + j for j in range(V)]) for i in range(H)] + [(H + H * V + j,) for j in range(V)]
+    return model, n_state, n_param, groups

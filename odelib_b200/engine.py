@@ -69,6 +69,10 @@ class DeviceModel:
             os.makedirs(cache_dir, exist_ok=True)
         bo = _capi.BuildOpts()
         bo.device = -1 if device is None else int(device)
+        if not min_blocks:      # registers per thread follow from the state count: 8n doubles of stages + state
+            min_blocks = 4 if n_state <= 4 else 3 if n_state <= 6 else 2 if n_state <= 8 else 1
+        if not block_threads and n_state > 8:
+            block_threads = 64
         bo.block_threads, bo.min_blocks = int(block_threads), int(min_blocks)
         bo.dense_output = 1 if dense_output else 0
         bo.compile_only = 1 if compile_only else 0

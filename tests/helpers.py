@@ -61,3 +61,36 @@ def device_model(name, **kw):
 def prior_draws(name, n, seed=0):
     rng = np.random.default_rng(seed)
     return np.column_stack([sc * np.exp(s * rng.standard_normal(n)) for _, s, sc in PRIORS[name]])
+
+
+DEMO_TIMES = [0.0, 0.2, 0.3, 0.5, 0.7, 0.9, 1.0, 1.2, 1.3, 1.5, 1.7, 1.8, 2.0, 2.2, 2.3, 2.5, 2.8, 3.0]
+
+
+def synthetic_problem(rhs, state_names, sums, center, y0, organisms, seed=0, sigma=0.2, t_steps=1000, device_kw=None):
+    """Synthetic data set: the oracle's odeint at `center` + log-normal noise on the demo's
+    time points, one block of rows per observed organism.  Returns (DeviceModel with the data loaded, oracle tables)."""
+    import pandas as pd
+    from odelib_b200.engine import DeviceModel
+    from oracle import odelib_oracle as orc
+    rows = [{"organism": o, "time": t, "abundance": 1.0, "log_sigma": sigma} for o in organisms for t in DEMO_TIMES]
+    df0 = pd.DataFrame(rows)
+    inits = dict(zip(state_names, y0))
+    tab0 = orc.build_tables(df0, state_names, sums, t_steps, inits)
+    tab0.y0 = np.asarray(y0, float)
+    vec, _, _ = orc.solve_unit(rhs, center, tab0, 1e-12, 1e-12, y0=np.asarray(y0, float), mxstep=500000)
+    rng = np.random.default_rng(seed)
+    df = df0.sort_values(by=["organism", "time"], kind="stable").reset_index(drop=True)
+    # rows of tab0 are ordered like chi concatenates them: by out-column order, which is not the alphabetical
+    # organism order in general -> assign per organism
+    off = 0
+    for o in tab0.obs_order:
+        nrow = len(tab0.tindex[o])
+        df.loc[df["organism"] == o, "abundance"] = np.maximum(vec[off:off + nrow], 1e-3) * np.exp(sigma * rng.standard_normal(nrow))
+        off += nrow
+    tab = orc.build_tables(df, state_names, sums, t_steps, inits)
+    tab.y0 = np.asarray(y0, float)
+    n, P = len(state_names), len(center)
+    groups = [tab.sum_index.get(i, (i,)) for i in tab.keep] if tab.sum_index else [(i,) for i in range(n)]
+    dm = DeviceModel(rhs, n, P, groups, **(device_kw or {}))
+    dm.set_data(obs_tables_from_oracle(tab), tab.y0)
+    return dm, tab
