@@ -535,7 +535,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     const int cap1 = so && so->pass_cap1 > 0 ? so->pass_cap1 : 1536;
     const bool two_dopri = cap1 > cap0;
     // tail passes are latency-bound (a handful of long systems): modest grids so that both fit on the SMs at once
-    const long long tail_items = std::max<long long>(32, std::min<long long>(n / 16, (long long)m->sm_count * 4 * 32));
+    const long long tail_items = std::max<long long>(32, std::min<long long>(n, (long long)m->sm_count * 4 * 32));
     OdlOpts O0 = O; O0.stiff_check = 1; O0.max_steps = std::min(cap0, O.max_steps);
     O0.defer_split_steps = two_dopri ? cap1 : 0;   // projected to need more than cap1 steps -> straight to Radau5
     OdlSweepArgs A0 = A;

@@ -460,8 +460,10 @@ ODL_UNROLL
       const bool s = fabs(F.a[i][k]) > fabs(F.a[k][k]);
       if (s) sw |= (1ull << (bit & 63));
       ++bit;
+      // rows are exchanged from column k on only (LINPACK dgefa/dgesl convention): the multipliers already
+      // stored in columns < k stay put, matching the interleaved swap-then-eliminate order of odl_lu_solve
 ODL_UNROLL
-      for (int j = 0; j < ODL_N; ++j) {
+      for (int j = k; j < ODL_N; ++j) {
         const double u = F.a[k][j], v = F.a[i][j];
         F.a[k][j] = s ? v : u;
         F.a[i][j] = s ? u : v;
@@ -514,7 +516,7 @@ __device__ __forceinline__ void odl_lu_factor(OdlLU& F) {
     double big = fabs(F.a[k][k]);
     for (int i = k + 1; i < ODL_N; ++i) { const double v = fabs(F.a[i][k]); if (v > big) { big = v; best = i; } }
     F.piv[k] = best;
-    if (best != k) for (int j = 0; j < ODL_N; ++j) { const double u = F.a[k][j]; F.a[k][j] = F.a[best][j]; F.a[best][j] = u; }
+    if (best != k) for (int j = k; j < ODL_N; ++j) { const double u = F.a[k][j]; F.a[k][j] = F.a[best][j]; F.a[best][j] = u; }
     F.inv[k] = 1.0 / F.a[k][k];
     for (int i = k + 1; i < ODL_N; ++i) {
       const double l = F.a[i][k] * F.inv[k];
@@ -658,7 +660,7 @@ ODL_UNROLL
       if (s) sw |= (1ull << (bit & 63));
       ++bit;
 ODL_UNROLL
-      for (int j = 0; j < ODL_N; ++j) {
+      for (int j = k; j < ODL_N; ++j) {
         const double ur = F.ar[k][j], vr = F.ar[i][j], ui = F.ai[k][j], vi = F.ai[i][j];
         F.ar[k][j] = s ? vr : ur; F.ar[i][j] = s ? ur : vr;
         F.ai[k][j] = s ? vi : ui; F.ai[i][j] = s ? ui : vi;
@@ -724,7 +726,7 @@ __device__ __forceinline__ void odl_clu_factor(OdlCLU& F) {
     double big = fabs(F.ar[k][k]) + fabs(F.ai[k][k]);
     for (int i = k + 1; i < ODL_N; ++i) { const double v = fabs(F.ar[i][k]) + fabs(F.ai[i][k]); if (v > big) { big = v; best = i; } }
     F.piv[k] = best;
-    if (best != k) for (int j = 0; j < ODL_N; ++j) {
+    if (best != k) for (int j = k; j < ODL_N; ++j) {
       double u = F.ar[k][j]; F.ar[k][j] = F.ar[best][j]; F.ar[best][j] = u;
       u = F.ai[k][j]; F.ai[k][j] = F.ai[best][j]; F.ai[best][j] = u;
     }
@@ -765,6 +767,9 @@ __device__ __forceinline__ void odl_clu_solve(const OdlCLU& F, double (&br)[ODL_
 
 #endif  // ODL_SMALL
 
+#ifdef ODL_HOST_HARNESS
+static long long odl_dbg[8];
+#endif
 struct OdlRadauAux {
   double Q[3][ODL_N];            // collocation polynomial of the last accepted step: y(t0 + x h) = y0 + Q0 x + Q1 x^2 + Q2 x^3
   double h_old;
@@ -891,6 +896,9 @@ ODL_UNROLL
     dwn_old = dwn;
   }
   const double hmin = 4.0 * 2.220446049250313e-16 * fmax(fabs(t), fabs(st.tend));
+#ifdef ODL_HOST_HARNESS
+  odl_dbg[0] += 1; odl_dbg[1] += n_iter; if (!converged) odl_dbg[2] += 1;
+#endif
   if (!converged) {
     st.h = 0.5 * h;
     if (!(st.h > hmin)) st.status = ODL_HUNDERFLOW;
@@ -937,6 +945,9 @@ ODL_UNROLL
   float factor = fminf(1.f, mult) * __powf(err, -0.25f);
   if (!(err > 0.f)) factor = 10.f;
   if (!(err <= 1.0f) || !finite_all) {
+#ifdef ODL_HOST_HARNESS
+    odl_dbg[3] += 1;
+#endif
     double hnew = (err == err && err < 3.0e38f) ? h * (double)fmaxf(0.2f, fminf(0.95f, safety * factor)) : 0.2 * h;
     ax.rejected = true;
     st.h = hnew;

@@ -30,6 +30,26 @@ struct HostSink {
   }
 };
 
+// LU self-test hooks: solve A x = b (real) and (Ar + i Ai) x = b (complex) with the steppers' in-register LU
+extern "C" void harness_lu(const double* A, const double* b, double* x) {
+  OdlLU F;
+  for (int i = 0; i < ODL_N; ++i) for (int j = 0; j < ODL_N; ++j) F.a[i][j] = A[i * ODL_N + j];
+  odl_lu_factor(F);
+  double v[ODL_N];
+  for (int i = 0; i < ODL_N; ++i) v[i] = b[i];
+  odl_lu_solve(F, v);
+  for (int i = 0; i < ODL_N; ++i) x[i] = v[i];
+}
+extern "C" void harness_clu(const double* Ar, const double* Ai, const double* br, const double* bi, double* xr, double* xi) {
+  OdlCLU F;
+  for (int i = 0; i < ODL_N; ++i) for (int j = 0; j < ODL_N; ++j) { F.ar[i][j] = Ar[i * ODL_N + j]; F.ai[i][j] = Ai[i * ODL_N + j]; }
+  odl_clu_factor(F);
+  double vr[ODL_N], vi[ODL_N];
+  for (int i = 0; i < ODL_N; ++i) { vr[i] = br[i]; vi[i] = bi[i]; }
+  odl_clu_solve(F, vr, vi);
+  for (int i = 0; i < ODL_N; ++i) { xr[i] = vr[i]; xi[i] = vi[i]; }
+}
+extern "C" void harness_dbg(long long* out) { for (int i = 0; i < 8; ++i) { out[i] = odl_dbg[i]; odl_dbg[i] = 0; } }
 extern "C" int harness_dims(int* n, int* p) { *n = ODL_N; *p = ODL_P; return 0; }
 
 // solver: 0 DOPRI5, 1 ROS23, 3 Radau5.  out: [n_slot][ODL_N].  Returns the status word.

@@ -64,5 +64,5 @@ def test_five_by_five_network():
         np.testing.assert_allclose(out["pred"][k], vec, rtol=1e-7, atol=1e-5)
         np.testing.assert_allclose(out["chi"][k], chi, rtol=1e-6)
     res = dm.mcmc(theta[:32], nits=24, seed=3)
-    assert np.isfinite(res["samples"]).all() and res["samples"].shape == (32, 12, P + 5)
+    assert np.isfinite(res["samples"]).all() and res["samples"].shape == (32, 11, P + 5)
     assert res["fail_count"].sum() == 0

@@ -77,3 +77,35 @@ def test_step_budget_and_nonfinite_inputs_end_in_status_words(two_i):
         bad = th.copy(); bad[1] = np.nan
         _, st, _ = hh.solve(lib, solver, bad, slots, tab.y0, TOL, TOL, max_steps=100000)
         assert st != 0
+
+
+@pytest.mark.parametrize("model", ["one_i", "two_i", "n_class_10"])
+def test_in_register_lu_with_pivoting(model):
+    """The LU the ROS23 / Radau5 steppers use (unrolled in registers for n <= 8, rolled for larger n), real and
+    complex, on matrices that force row exchanges -- against numpy.linalg.solve."""
+    import ctypes as C
+    if model == "n_class_10":
+        f, n, P, groups = demo_models.n_class(10), 12, 5, [tuple(range(11)), (11,)]
+    else:
+        f, n, P, groups = demo_models.MODELS[model]
+    lib = hh.build(f, n, P, groups)
+    rng = np.random.default_rng(0)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    for trial in range(400):
+        A = rng.standard_normal((n, n))
+        mode = trial % 4
+        if mode >= 1:
+            A[0, 0] = 0.0
+        if mode == 2:
+            A[1, 1] = 0.0
+        if mode == 3:
+            A = A[rng.permutation(n)] * (10.0 ** rng.integers(-6, 4, n))[:, None]
+        b = rng.standard_normal(n)
+        x = np.empty(n)
+        lib.harness_lu(ptr(A), ptr(b), ptr(x))
+        assert np.abs(A @ x - b).max() <= 1e-11 * (np.abs(A).max() * np.abs(x).max() + 1)
+        Ai, bi = rng.standard_normal((n, n)), rng.standard_normal(n)
+        xr, xi = np.empty(n), np.empty(n)
+        lib.harness_clu(ptr(A), ptr(Ai), ptr(b), ptr(bi), ptr(xr), ptr(xi))
+        M, z = A + 1j * Ai, xr + 1j * xi
+        assert np.abs(M @ z - (b + 1j * bi)).max() <= 1e-11 * (np.abs(M).max() * np.abs(z).max() + 1)

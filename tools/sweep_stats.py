@@ -12,16 +12,13 @@ from tests.helpers import device_model  # noqa: E402
 import bench  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-dm, tab = device_model("two_i")
-theta = torch.from_numpy(bench.prior_draws(n, 0, 0)).cuda()
+MODEL = sys.argv[2] if len(sys.argv) > 2 else "two_i"
+dm, tab = device_model(MODEL)
+from tests.helpers import prior_draws
+theta = torch.from_numpy(prior_draws(MODEL, n, seed=0)).cuda()
 res = {}
-for mode, kw in (("auto_512_2048", dict(solver="auto", max_steps=200000, pass_caps=(512, 2048))),
-                 ("auto_512_1536", dict(solver="auto", max_steps=200000, pass_caps=(512, 1536))),
-                 ("auto_512_1024", dict(solver="auto", max_steps=200000, pass_caps=(512, 1024))),
-                 ("auto_384_1536", dict(solver="auto", max_steps=200000, pass_caps=(384, 1536))),
-                 ("auto_384_1024", dict(solver="auto", max_steps=200000, pass_caps=(384, 1024))),
-                 ("auto_256_1024", dict(solver="auto", max_steps=200000, pass_caps=(256, 1024))),
-                 ("auto_512_3072", dict(solver="auto", max_steps=200000, pass_caps=(512, 3072))),
+for mode, kw in (("auto", dict(solver="auto", max_steps=200000)),
+                 ("radau5_all", dict(solver="radau5", max_steps=200000)),
                  ("dopri5_cap512", dict(solver="dopri5", max_steps=512))):
     for rep in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -38,6 +35,9 @@ json.dump(res, open("gpurun_out/sweep_stats.json", "w"), indent=1)
 ns = out["nsteps"].cpu().numpy()
 order = np.argsort(-ns)[:200]
 np.savez("gpurun_out/worst.npz", theta=theta.cpu().numpy()[order], nsteps=ns[order], chi=out["chi"].cpu().numpy()[order])
-plain = dm.sweep(theta, solver="dopri5", stiff_check=True, max_steps=200000)
+plain = dm.sweep(theta, solver="dopri5", stiff_check=True, max_steps=512)
 st = plain["status"].cpu().numpy()
-print("routed to ROS23:", int((st == 4).sum()), "of", n)
+print("pass0: stiff", int((st == 4).sum()), "maxsteps", int((st == 1).sum()), "of", n)
+rad = dm.sweep(theta[torch.from_numpy(np.flatnonzero(st != 0)).cuda()], solver="radau5", max_steps=200000)
+rn = rad["nsteps"].cpu().numpy()
+print("radau on deferred: n", rn.size, "steps pct 50/90/99/max", np.percentile(rn, [50, 90, 99, 100]).tolist(), "ms", dm.last_kernel_ms())
