@@ -68,7 +68,7 @@ typedef struct odl_solver_opts {
   int stiff_check;     /* DOPRI5: detect stiffness and stop with ODL_ST_STIFF */
   int stiff_min_steps; /* ... only while more than this many steps of the current size remain (0 = 2000) */
   int pass_cap0;       /* ODL_SOLVER_AUTO: step cap of the first DOPRI5 pass (0 = 512) */
-  int pass_cap1;       /* ODL_SOLVER_AUTO: step cap of the second DOPRI5 pass (0 = 1536; <= pass_cap0 skips it) */
+  int pass_cap1;       /* ODL_SOLVER_AUTO: step cap of the optional second DOPRI5 pass (0 = none) */
 } odl_solver_opts;
 
 typedef struct odl_mcmc_opts {
