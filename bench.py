@@ -301,6 +301,26 @@ def run_ours(args):
                 "accept_rate": float(res["chain_state"][:, 2].mean().item()) / (nits - 1),
                 "rhat_max": float(np.nanmax(rh)), "rhat_collective": "nccl all_gather" if world > 1 else "none (1 GPU)"}
 
+        # the same kernel with the GPU filled (BASELINE config 5's chain count per GPU x 8): throughput regime
+        if args.chains_large > 0:
+            CL, nl = args.chains_large, args.nits_large
+            st2 = torch.from_numpy(np.array(CENTER[MODEL]) * np.exp(0.05 * rng.standard_normal((CL, P)))).to(dev)
+            kw2 = dict(nits=nl, rng_mode="philox", seed=0, chain_offset=rank * CL, pnum=P, device_buffers=True, keep_samples=False)
+            dm.mcmc(st2, **dict(kw2, nits=10))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record()
+            r2 = dm.mcmc(st2, **kw2)
+            b.record()
+            barrier()
+            t_l = max_over_ranks(a.elapsed_time(b) * 1e-3)
+            steps_l = sum_over_ranks(float(r2["step_count"].sum().item()))
+            mcmc["filled_gpu"] = {"chains_per_gpu": CL, "iterations": nl, "seconds": t_l,
+                                  "chain_steps_per_s": CL * world * (nl - 1) / t_l,
+                                  "solves_per_s": CL * world * nl / t_l,
+                                  "fp64_tflops_per_gpu": steps_l * flops_step / t_l / 1e12 / world,
+                                  "frac_of_fp64_peak": steps_l * flops_step / t_l / 1e12 / world / peak_tflops}
+
     launches = _capi.lib().odl_launch_count() - launches0
 
     # ---- CPU baseline (rank 0, N=1 only): the reference's algorithm on the host cores ---------------
@@ -357,6 +377,8 @@ def main():
     ap.add_argument("--sets", type=int, default=1 << 20, help="parameter sets per GPU per step")
     ap.add_argument("--chains", type=int, default=4096, help="MCMC chains per GPU (0 = skip the MCMC leg)")
     ap.add_argument("--nits", type=int, default=500, help="iterations per chain in the MCMC leg")
+    ap.add_argument("--chains-large", type=int, default=65536, help="chains per GPU for the filled-GPU MCMC measurement (0 = skip)")
+    ap.add_argument("--nits-large", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -428,7 +428,7 @@ class ModelFramework:
 
     # ------------------------------------------------------------------ MCMC (Framework.py:946-1061)
     def _run_chains(self, starts, seeds, nits, burnin, static_parameters, rng="auto", rtol=None, atol=None,
-                    update_model=False, return_raw=False):
+                    update_model=False, return_raw=False, return_frame=False):
         """All chains in one kernel.  starts: list of theta vectors; seeds: per-chain seeds (chain index)."""
         dm = self._device()
         static = set(static_parameters or ())
@@ -458,15 +458,26 @@ class ModelFramework:
         if return_raw:
             return out
         cols = self.get_pnames() + ['chi', 'rsquared', 'aic', 'iteration', 'acceptance_ratio']
-        frames = []
-        for c in range(C):
-            df = pd.DataFrame(out["samples"][c], columns=cols)
+        samples = out["samples"]                                  # [C, n_keep, P+5], rows = the reference frame's columns
+        if return_frame:
+            # one frame for all chains, assembled without per-chain pandas work (Framework.py:1035-1038 equivalent)
+            flat = samples.reshape(-1, samples.shape[-1])
+            df = pd.DataFrame(flat, columns=cols)
             df['iteration'] = df['iteration'].astype(np.int64)
             for p in static:   # reference quirk A13: static columns report the prior's scale (Samplers.py:166-170)
                 df[p] = self.parameters[p].hp['scale']
-            if df.empty:
-                df = pd.DataFrame([[np.nan] * (len(self._pnames) + 3)])
-            frames.append(df)
+            df['chain#'] = np.repeat(np.arange(C), samples.shape[1])
+            frames = df
+        else:
+            frames = []
+            for c in range(C):
+                df = pd.DataFrame(samples[c], columns=cols)
+                df['iteration'] = df['iteration'].astype(np.int64)
+                for p in static:
+                    df[p] = self.parameters[p].hp['scale']
+                if df.empty:
+                    df = pd.DataFrame([[np.nan] * (len(self._pnames) + 3)])
+                frames.append(df)
         if update_model:
             self.set_parameters(**dict(zip(self._pnames, out["theta"][0])))
             if any(m >= 0 for m in self._y0_map()):
@@ -506,13 +517,11 @@ class ModelFramework:
                         th[self._pnames.index(k)] = float(v)
                 starts.append(th)
         seeds = list(range(len(starts)))                          # chain seed = chain index (:1015, :1020)
-        frames = self._run_chains(starts, seeds, iterations_per_chain, int(iterations_per_chain / 2),
-                                  static_parameters, rng=rng)
-        for i, df in enumerate(frames):
-            df['chain#'] = i
-        posterior = pd.concat(frames).reset_index(drop=True)
+        posterior = self._run_chains(starts, seeds, iterations_per_chain, int(iterations_per_chain / 2),
+                                     static_parameters, rng=rng, return_frame=True)
+        n_chains = len(starts)
         self.rhat = dict(zip(self.get_pnames(), rhat_from_summaries(self._last_mcmc["summaries"], len(self._pnames)))) \
-            if len(frames) > 1 and self._last_mcmc["n_keep"] > 1 else None
+            if n_chains > 1 and self._last_mcmc["n_keep"] > 1 else None
         if print_report:
             report = ["\nFitting Report\n==============="]
             for col in self.get_pnames():
