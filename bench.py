@@ -341,7 +341,11 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": None,
+                         "frac": achieved / peak_tflops,
+                         "traffic": (42734336 + 4911104) if n == (1 << 20) else None,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the bulk launch (odl_sweep_kernel, "
+                                         "1,048,576 sets), ncu --set full capture profiles/r1c_sweep_bulk_cap512_ncu.txt; "
+                                         "algorithmic bytes 40 MB in + 24 MB out (results still in L2 at kernel end)",
                          "kernel": "odl_sweep (2 launches: odl_sweep_kernel + odl_sweep_radau5_kernel)", "avg_launch_ms": avg_ms,
                          "peak_source": "measured live: odl_fp64_peak DFMA chains (MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_per_launch": flops_launch, "flops_per_step_attempt": flops_step,
