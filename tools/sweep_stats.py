@@ -17,14 +17,13 @@ dm, tab = device_model(MODEL)
 from tests.helpers import prior_draws
 theta = torch.from_numpy(prior_draws(MODEL, n, seed=0)).cuda()
 res = {}
-for mode, kw in (("auto_512_1536", dict(solver="auto", max_steps=200000, pass_caps=(512, 1536))),
-                 ("auto_512_0", dict(solver="auto", max_steps=200000, pass_caps=(512, 1))),
-                 ("auto_384_0", dict(solver="auto", max_steps=200000, pass_caps=(384, 1))),
-                 ("auto_320_0", dict(solver="auto", max_steps=200000, pass_caps=(320, 1))),
-                 ("auto_256_0", dict(solver="auto", max_steps=200000, pass_caps=(256, 1))),
-                 ("auto_192_0", dict(solver="auto", max_steps=200000, pass_caps=(192, 1))),
-                 ("auto_128_0", dict(solver="auto", max_steps=200000, pass_caps=(128, 1))),
-                 ("auto_256_768", dict(solver="auto", max_steps=200000, pass_caps=(256, 768))),
+for mode, kw in (("auto_default", dict(solver="auto", max_steps=200000)),
+                 ("auto_512_1024", dict(solver="auto", max_steps=200000, pass_caps=(512, 1024))),
+                 ("auto_512_1536", dict(solver="auto", max_steps=200000, pass_caps=(512, 1536))),
+                 ("auto_512_2048", dict(solver="auto", max_steps=200000, pass_caps=(512, 2048))),
+                 ("auto_384_1024", dict(solver="auto", max_steps=200000, pass_caps=(384, 1024))),
+                 ("auto_448_0", dict(solver="auto", max_steps=200000, pass_caps=(448, 1))),
+                 ("auto_640_0", dict(solver="auto", max_steps=200000, pass_caps=(640, 1))),
                  ("dopri5_cap512", dict(solver="dopri5", max_steps=512))):
     for rep in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
