@@ -37,11 +37,11 @@
 extern "C" {
 #endif
 
-#define ODL_ABI_VERSION 1
+#define ODL_ABI_VERSION 2
 
 enum { ODL_SUCCESS = 0, ODL_EINVAL = 1, ODL_ECUDA = 2, ODL_ECOMPILE = 3, ODL_ENODEVICE = 4, ODL_EIO = 5 };
 enum { ODL_MEM_HOST = 0, ODL_MEM_DEVICE = 1 };
-enum { ODL_SOLVER_DOPRI5 = 0, ODL_SOLVER_ROS23 = 1, ODL_SOLVER_AUTO = 2, ODL_SOLVER_RADAU5 = 3 };
+enum { ODL_SOLVER_DOPRI5 = 0, ODL_SOLVER_ROS23 = 1, ODL_SOLVER_AUTO = 2, ODL_SOLVER_RADAU5 = 3, ODL_SOLVER_BDF = 4 };
 enum { ODL_RNG_PHILOX = 0, ODL_RNG_HOST_STREAMS = 1, ODL_RNG_FORCED = 2 };
 /* per-system status words */
 enum { ODL_ST_OK = 0, ODL_ST_MAXSTEPS = 1, ODL_ST_NONFINITE = 2, ODL_ST_HUNDERFLOW = 3, ODL_ST_STIFF = 4,
@@ -69,6 +69,12 @@ typedef struct odl_solver_opts {
   int stiff_min_steps; /* ... only while more than this many steps of the current size remain (0 = 2000) */
   int pass_cap0;       /* ODL_SOLVER_AUTO: step cap of the first DOPRI5 pass (0 = 512) */
   int pass_cap1;       /* ODL_SOLVER_AUTO: step cap of the optional second DOPRI5 pass (0 = none) */
+  int tail_solver;     /* ODL_SOLVER_AUTO: stepper of the pass over what DOPRI5 did not finish:
+                          0 = default (ODL_SOLVER_BDF), or ODL_SOLVER_RADAU5 */
+  int early_check_steps; /* ODL_SOLVER_AUTO: the first pass drops a system after this many attempts when its progress
+                          projects beyond pass_cap0 (0 = pass_cap0/2, -1 = never) */
+  int tail_lanes;      /* ODL_SOLVER_AUTO: lanes per warp that take systems in the stiff pass (0 = 32) */
+  int reserved[1];
 } odl_solver_opts;
 
 typedef struct odl_mcmc_opts {
@@ -110,7 +116,8 @@ int odl_model_create(const char* model_cuda_src, int n_state, int n_param, int n
 int odl_model_destroy(odl_model* m);
 /* compile log of the NVRTC run (warnings included); valid until the model is destroyed */
 const char* odl_model_build_log(const odl_model* m);
-/* resource usage of a compiled kernel ("sweep", "mcmc", "traj", "sweep_ros23", "mcmc_ros23", "mcmc_auto"):
+/* resource usage of a compiled kernel ("sweep", "mcmc", "traj", "sweep_ros23", "mcmc_ros23", "mcmc_auto",
+   "sweep_radau5", "mcmc_radau5", "sweep_bdf", "mcmc_bdf"):
    registers/thread, local (spill) bytes, resident CTAs per SM */
 int odl_model_kernel_info(const odl_model* m, const char* kernel, int* regs, int* local_bytes, int* max_blocks_per_sm);
 

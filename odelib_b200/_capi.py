@@ -11,7 +11,7 @@ CACHE_DIR = os.path.join(_HERE, "_cubin_cache")
 
 SUCCESS, EINVAL, ECUDA, ECOMPILE, ENODEVICE, EIO = range(6)
 MEM_HOST, MEM_DEVICE = 0, 1
-SOLVER_DOPRI5, SOLVER_ROS23, SOLVER_AUTO = 0, 1, 2
+SOLVER_DOPRI5, SOLVER_ROS23, SOLVER_AUTO, SOLVER_RADAU5, SOLVER_BDF = 0, 1, 2, 3, 4
 RNG_PHILOX, RNG_HOST_STREAMS, RNG_FORCED = 0, 1, 2
 ST_OK, ST_MAXSTEPS, ST_NONFINITE, ST_HUNDERFLOW, ST_STIFF, ST_ALLMASKED = 0, 1, 2, 3, 4, 8
 
@@ -35,7 +35,7 @@ class BuildOpts(C.Structure):
 class SolverOpts(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("h0", C.c_double), ("hmax", C.c_double),
                 ("max_steps", C.c_int), ("solver", C.c_int), ("stiff_check", C.c_int), ("stiff_min_steps", C.c_int),
-                ("pass_cap0", C.c_int), ("pass_cap1", C.c_int)]
+                ("pass_cap0", C.c_int), ("pass_cap1", C.c_int), ("tail_solver", C.c_int), ("early_check_steps", C.c_int), ("tail_lanes", C.c_int), ("reserved", C.c_int * 1)]
 
 
 class McmcOpts(C.Structure):
@@ -84,7 +84,7 @@ def lib():
     L.odl_model_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.odl_model_last_pass_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.odl_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
-    if L.odl_abi_version() != 1:
+    if L.odl_abi_version() != 2:
         raise OdlError(EIO, "libodelib_b200.so ABI version mismatch - rebuild")
     _lib = L
     return L

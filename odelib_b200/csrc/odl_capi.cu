@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -133,6 +134,7 @@ struct odl_model {
   CUfunction k_sweep = nullptr, k_traj = nullptr, k_mcmc = nullptr;
   CUfunction k_sweep_ros = nullptr, k_mcmc_ros = nullptr, k_mcmc_auto = nullptr;
   CUfunction k_sweep_radau = nullptr, k_mcmc_radau = nullptr;
+  CUfunction k_sweep_bdf = nullptr, k_mcmc_bdf = nullptr;
   Tables data, grid;
   DevBuf counter;
   DevBuf scratch[16];
@@ -155,6 +157,17 @@ static int compile_model(odl_model* m, const std::string& src, const char* cache
                                   "-DODL_BLOCK=" + std::to_string(m->block),
                                   "-DODL_MINBLOCKS=" + std::to_string(m->minblocks),
                                   "-DODL_DENSE=" + std::to_string(m->dense), "-DODL_Y0P=" + std::to_string(m->y0p)};
+  // tuning hook (development): extra -D options for the kernel source, e.g. ODL_KERNEL_DEFINES="-DODL_INNER=8"
+  if (const char* extra = getenv("ODL_KERNEL_DEFINES")) {
+    std::string e(extra);
+    size_t pos = 0;
+    while (pos < e.size()) {
+      size_t sp = e.find(' ', pos);
+      if (sp == std::string::npos) sp = e.size();
+      if (sp > pos) opt.push_back(e.substr(pos, sp - pos));
+      pos = sp + 1;
+    }
+  }
   int major = 0, minor = 0;
   nvrtcVersion(&major, &minor);
   std::string keysrc = src + kKernelSrc + kAbiHeaderSrc;
@@ -255,7 +268,8 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
       {"odl_sweep_kernel", &m->k_sweep, true}, {"odl_traj_kernel", &m->k_traj, true}, {"odl_mcmc_kernel", &m->k_mcmc, true},
       {"odl_sweep_ros23_kernel", &m->k_sweep_ros, true}, {"odl_mcmc_ros23_kernel", &m->k_mcmc_ros, true},
       {"odl_mcmc_auto_kernel", &m->k_mcmc_auto, true}, {"odl_sweep_radau5_kernel", &m->k_sweep_radau, true},
-      {"odl_mcmc_radau5_kernel", &m->k_mcmc_radau, true}};
+      {"odl_mcmc_radau5_kernel", &m->k_mcmc_radau, true}, {"odl_sweep_bdf_kernel", &m->k_sweep_bdf, true},
+      {"odl_mcmc_bdf_kernel", &m->k_mcmc_bdf, true}};
   for (auto& k : ks) {
     CUresult r = g_drv.ModuleGetFunction(k.fn, m->mod, k.name);
     if (r != CUDA_SUCCESS) {
@@ -303,6 +317,8 @@ static CUfunction kernel_by_name(const odl_model* m, const char* k) {
   if (!strcmp(k, "mcmc_auto")) return m->k_mcmc_auto;
   if (!strcmp(k, "sweep_radau5")) return m->k_sweep_radau;
   if (!strcmp(k, "mcmc_radau5")) return m->k_mcmc_radau;
+  if (!strcmp(k, "sweep_bdf")) return m->k_sweep_bdf;
+  if (!strcmp(k, "mcmc_bdf")) return m->k_mcmc_bdf;
   return nullptr;
 }
 
@@ -423,6 +439,8 @@ static void fill_opts(OdlOpts& o, const odl_solver_opts* so) {
   o.stiff_check = so ? so->stiff_check : 0;
   o.stiff_min_steps = so && so->stiff_min_steps > 0 ? so->stiff_min_steps : 2000;
   o.defer_split_steps = 0;
+  o.early_check_steps = 0;
+  o.lanes = 0;
 }
 
 static int launch(odl_model* m, CUfunction f, unsigned grid, unsigned block, size_t smem, cudaStream_t s, void** params) {
@@ -471,7 +489,10 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   if (n < 0 || (n > 0 && (!theta || !chi || !r2 || !status || !nsteps))) return fail(ODL_EINVAL, "odl_sweep: null buffer");
   if (n == 0) return 0;
   const int solver = so ? so->solver : ODL_SOLVER_DOPRI5;
-  if (solver < 0 || solver > ODL_SOLVER_RADAU5) return fail(ODL_EINVAL, "odl_sweep: unknown solver");
+  if (solver < 0 || solver > ODL_SOLVER_BDF) return fail(ODL_EINVAL, "odl_sweep: unknown solver");
+  const int tail_solver = so && so->tail_solver > 0 ? so->tail_solver : ODL_SOLVER_BDF;
+  if (tail_solver != ODL_SOLVER_BDF && tail_solver != ODL_SOLVER_RADAU5)
+    return fail(ODL_EINVAL, "odl_sweep: tail_solver must be ODL_SOLVER_BDF or ODL_SOLVER_RADAU5");
   ODL_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
   Staging st{m, s, 0, mem};
@@ -509,8 +530,10 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   m->n_pass = 1;
   if (solver != ODL_SOLVER_AUTO) {
     A.defer_list[0] = A.defer_list[1] = nullptr; A.defer_count[0] = A.defer_count[1] = nullptr;
-    CUfunction f1 = solver == ODL_SOLVER_ROS23 ? m->k_sweep_ros : (solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau : m->k_sweep);
-    if ((rc = go(s, f1, O, A, solver == ODL_SOLVER_RADAU5 ? 32u : pick_block(D, m->block), n))) return rc;
+    const bool warp_cta = solver == ODL_SOLVER_RADAU5 || solver == ODL_SOLVER_BDF;   // compiled for one warp per CTA
+    CUfunction f1 = solver == ODL_SOLVER_ROS23 ? m->k_sweep_ros : (solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau :
+                    (solver == ODL_SOLVER_BDF ? m->k_sweep_bdf : m->k_sweep));
+    if ((rc = go(s, f1, O, A, warp_cta ? 32u : pick_block(D, m->block), n))) return rc;
   } else {
     // Cohort passes (no host synchronisation in between; list lengths stay on the device).  Default: two passes,
     // DOPRI5 capped at pass_cap0 attempted steps, then Radau5 on everything it did not finish (measured best on
@@ -536,23 +559,29 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     const int cap0 = so && so->pass_cap0 > 0 ? so->pass_cap0 : 512;
     const int cap1 = so && so->pass_cap1 > 0 ? so->pass_cap1 : 0;
     const bool two_dopri = cap1 > cap0;
+    CUfunction k_tail = tail_solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau : m->k_sweep_bdf;
     // tail passes are latency-bound (a handful of long systems): modest grids so that both fit on the SMs at once
     const long long tail_items = std::max<long long>(32, std::min<long long>(n, (long long)m->sm_count * 4 * 32));
     OdlOpts O0 = O; O0.stiff_check = 1; O0.max_steps = std::min(cap0, O.max_steps);
-    O0.defer_split_steps = two_dopri ? cap1 : 0;   // projected to need more than cap1 steps -> straight to Radau5
+    O0.defer_split_steps = two_dopri ? cap1 : 0;   // projected to need more than cap1 steps -> straight to the stiff pass
+    // half-way check: a system whose progress projects beyond the cap leaves at cap0/2 (recall ~100 %, precision ~50 %
+    // on the demo priors: the stiff pass gets twice the systems -- it is latency-bound, not throughput-bound -- and
+    // the warps of this pass wait half as long for their stragglers)
+    O0.early_check_steps = so && so->early_check_steps != 0 ? std::max(0, so->early_check_steps) : O0.max_steps / 2;
     OdlSweepArgs A0 = A;
     A0.defer_list[0] = two_dopri ? listA : listB; A0.defer_count[0] = two_dopri ? cnt(64) : cnt(192);
     A0.defer_list[1] = listB; A0.defer_count[1] = cnt(192);
     if ((rc = go(s, m->k_sweep, O0, A0, pick_block(D, m->block), n))) return rc;
     ODL_CUDA(cudaEventRecord(m->evp[0], s));
     OdlOpts O2 = O; O2.stiff_check = 0;
+    O2.lanes = so && so->tail_lanes > 0 ? std::min(32, so->tail_lanes) : 0;
     if (two_dopri) {
       // list B (Radau5) on the helper stream, concurrently with list A (DOPRI5) on the caller's stream
       ODL_CUDA(cudaStreamWaitEvent(m->aux, m->evp[0], 0));
       OdlSweepArgs A2 = A;
       A2.index = listB; A2.index_count = cnt(192); A2.counter = ctr(256);
       A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
-      if ((rc = go(m->aux, m->k_sweep_radau, O2, A2, 32u, tail_items))) return rc;
+      if ((rc = go(m->aux, k_tail, O2, A2, 32u, tail_items))) return rc;
       ODL_CUDA(cudaEventRecord(m->ev_aux, m->aux));
       OdlOpts O1 = O; O1.stiff_check = 1; O1.max_steps = std::min(cap1, O.max_steps);
       OdlSweepArgs A1 = A;
@@ -566,13 +595,13 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       OdlSweepArgs A3 = A;
       A3.index = listC; A3.index_count = cnt(320); A3.counter = ctr(384);
       A3.defer_list[0] = A3.defer_list[1] = nullptr; A3.defer_count[0] = A3.defer_count[1] = nullptr;
-      if ((rc = go(s, m->k_sweep_radau, O2, A3, 32u, std::max<long long>(32, tail_items / 4)))) return rc;
+      if ((rc = go(s, k_tail, O2, A3, 32u, std::max<long long>(32, tail_items / 4)))) return rc;
     } else {
       ODL_CUDA(cudaEventRecord(m->evp[1], s));
       OdlSweepArgs A2 = A;
       A2.index = listB; A2.index_count = cnt(192); A2.counter = ctr(256);
       A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
-      if ((rc = go(s, m->k_sweep_radau, O2, A2, 32u, n))) return rc;      // alone on the GPU: as many CTAs as fit
+      if ((rc = go(s, k_tail, O2, A2, 32u, O2.lanes > 0 ? n * (32 / O2.lanes) : n))) return rc;      // alone on the GPU: as many CTAs as fit
     }
     m->n_pass = 3;
   }
@@ -620,7 +649,7 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   if (mo->n_chain < 1 || mo->nits < 2) return fail(ODL_EINVAL, "odl_mcmc: need n_chain >= 1 and nits >= 2");
   if (mo->n_walk < 0 || mo->n_walk > m->n_param || (mo->n_walk > 0 && !mo->walk)) return fail(ODL_EINVAL, "odl_mcmc: bad walk list");
   const int solver = so ? so->solver : ODL_SOLVER_DOPRI5;
-  if (solver < 0 || solver > ODL_SOLVER_RADAU5) return fail(ODL_EINVAL, "odl_mcmc: unknown solver");
+  if (solver < 0 || solver > ODL_SOLVER_BDF) return fail(ODL_EINVAL, "odl_mcmc: unknown solver");
   const int P = m->n_param, C = mo->n_chain, n_iter = mo->nits - 1;
   int it_begin = mo->it_begin, it_end = mo->it_end;
   if (it_begin == 0 && it_end == 0) { it_begin = 1; it_end = mo->nits; }
@@ -661,11 +690,11 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   // few chains: spread them over the SMs with one warp per CTA; many chains: full CTAs
   unsigned block = pick_block(D, m->block);
   while (block > 32 && (long long)C < (long long)m->sm_count * block * 2) block /= 2;
-  if (solver == ODL_SOLVER_RADAU5) block = 32;              // that kernel is compiled for one warp per CTA
+  if (solver == ODL_SOLVER_RADAU5 || solver == ODL_SOLVER_BDF) block = 32;   // compiled for one warp per CTA
   const size_t smem = smem_bytes(D, (int)block);
   unsigned grid = (unsigned)((C + block - 1) / block);
   CUfunction f = (solver == ODL_SOLVER_DOPRI5) ? m->k_mcmc : (solver == ODL_SOLVER_ROS23 ? m->k_mcmc_ros :
-                 (solver == ODL_SOLVER_RADAU5 ? m->k_mcmc_radau : m->k_mcmc_auto));
+                 (solver == ODL_SOLVER_RADAU5 ? m->k_mcmc_radau : (solver == ODL_SOLVER_BDF ? m->k_mcmc_bdf : m->k_mcmc_auto)));
   if (solver == ODL_SOLVER_AUTO) O.stiff_check = 1;
   ODL_CUDA(cudaEventRecord(m->ev0, s));
   void* params[] = {&D, &O, &A};

@@ -39,6 +39,9 @@
 #ifndef ODL_Y0P
 #define ODL_Y0P 1
 #endif
+#ifndef ODL_INNER
+#define ODL_INNER 8
+#endif
 #ifndef ODL_MINBLOCKS_ROS
 #define ODL_MINBLOCKS_ROS (ODL_MINBLOCKS > 2 ? ODL_MINBLOCKS - 1 : ODL_MINBLOCKS)
 #endif
@@ -318,18 +321,22 @@ ODL_UNROLL
                            ODL_T(19) * k6[i]);
   odl_rhs(yn, tph, p, k7);
 
-  // embedded error estimate, scaled RMS norm
-  double errsq = 0.0;
-  bool finite_all = true;
+  // embedded error estimate, scaled RMS norm.  Scale: atol + rtol (|y| + |y_new|)/2 -- one DADD with |.| operand
+  // modifiers instead of the compare-and-select sequence fp64 max costs (5 % of the kernel's instructions in
+  // profiles/r1c); never larger than Hairer's max(|y|, |y_new|), i.e. never less strict.  Non-finite y_new shows in
+  // the sum below (a finite sum that overflows only costs a rejected step).
+  double errsq = 0.0, ysum = 0.0;
+  const double rtol_half = 0.5 * O.rtol;
 ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) {
     const double e = h * (ODL_T(20) * st.k1[i] + ODL_T(21) * k3[i] + ODL_T(22) * k4[i] + ODL_T(23) * k5[i] +
                           ODL_T(24) * k6[i] + ODL_T(25) * k7[i]);
-    const double sk = O.atol + O.rtol * fmax(fabs(st.y[i]), fabs(yn[i]));
+    const double sk = O.atol + rtol_half * (fabs(st.y[i]) + fabs(yn[i]));
     const double r = e * odl_rcp_approx(sk);
     errsq += r * r;
-    finite_all = finite_all && odl_finite(yn[i]);
+    ysum += fabs(yn[i]);
   }
+  const bool finite_all = odl_finite(ysum);
   const float err = sqrtf((float)errsq * (1.0f / ODL_N));
   // PI controller (Hairer, beta = 0.04): h_new = h * 0.9 * facold^beta / err^(0.2 - 0.75 beta), one SFU exp2
   const float lg_err = __log2f(err);
@@ -409,6 +416,11 @@ ODL_UNROLL
     if (!(fabs(hnew) > 4.0 * 2.220446049250313e-16 * fmax(fabs(t), fabs(st.tend)))) st.status = ODL_HUNDERFLOW;
   }
   if (st.nsteps >= O.max_steps && st.slot < D.n_slot && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
+  // capped pass of the cohort sweep: a system whose progress after early_check_steps attempts projects to more
+  // than max_steps in total leaves now instead of burning the rest of its budget (its warp waits for it)
+  if (O.early_check_steps > 0 && st.nsteps == O.early_check_steps && st.slot < D.n_slot && st.status == ODL_OK &&
+      (double)st.nsteps * (st.tend - D.t0) > (double)O.max_steps * (st.t - D.t0))
+    st.status = ODL_MAXSTEPS;
 }
 
 // slots at (or before) the start time take the initial state (odeint returns y0 at times[0])
@@ -481,19 +493,28 @@ ODL_UNROLL
   F.swaps = sw;
 }
 __device__ __forceinline__ void odl_lu_solve(const OdlLU& F, double (&b)[ODL_N]) {
-  int bit = 0;
+  if (F.swaps == 0ull) {
+    // no row was exchanged (the usual case for I - c J): skip the select pairs that replay the exchanges
 ODL_UNROLL
-  for (int k = 0; k < ODL_N; ++k) {
+    for (int k = 0; k < ODL_N; ++k) {
 ODL_UNROLL
-    for (int i = k + 1; i < ODL_N; ++i) {
-      const bool s = (F.swaps >> (bit & 63)) & 1ull;
-      ++bit;
-      const double u = b[k], v = b[i];
-      b[k] = s ? v : u;
-      b[i] = s ? u : v;
+      for (int i = k + 1; i < ODL_N; ++i) b[i] -= F.a[i][k] * b[k];
     }
+  } else {
+    int bit = 0;
 ODL_UNROLL
-    for (int i = k + 1; i < ODL_N; ++i) b[i] -= F.a[i][k] * b[k];
+    for (int k = 0; k < ODL_N; ++k) {
+ODL_UNROLL
+      for (int i = k + 1; i < ODL_N; ++i) {
+        const bool s = (F.swaps >> (bit & 63)) & 1ull;
+        ++bit;
+        const double u = b[k], v = b[i];
+        b[k] = s ? v : u;
+        b[i] = s ? u : v;
+      }
+ODL_UNROLL
+      for (int i = k + 1; i < ODL_N; ++i) b[i] -= F.a[i][k] * b[k];
+    }
   }
 ODL_UNROLL
   for (int k = ODL_N - 1; k >= 0; --k) {
@@ -980,16 +1001,317 @@ ODL_UNROLL
   if (st.nsteps >= O.max_steps && st.slot < D.n_slot && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Variable-order (1..5), quasi-constant step size BDF/NDF in backward differences (Shampine & Reichelt,
+// "The MATLAB ODE suite", ode15s; Byrne & Hindmarsh 1975 for the step-size change of the difference
+// array).  This is the method family of LSODA's stiff branch -- what the reference itself runs on these
+// systems (Framework.py:656) -- and the cheapest per step of the stiff steppers here: one real n x n LU
+// that is kept while the step size stands (it changes at most every order+1 accepted steps), two or
+// three simplified-Newton iterations of (one RHS + one back-substitution) per step.  Radau5 needs half as
+// many steps on the hard corner of the demo priors but ~6x the instructions per step (complex LU, three
+// stages), and the tail pass of the sweep is bound by the latency of its longest system.
+//
+// Storage: D[0] = y lives in st.y; the differences D[1..order+2] are kept REVERSED, E[k] = D[order+2-k],
+// so that everything touched on every step (d = D[order+1], D[order+2], the running sums) sits at
+// compile-time register indices whatever the current order is; only a step-size/order change (rare)
+// re-indexes, through a small local scratch array.
+// ------------------------------------------------------------------------------------------------
+#define ODL_BDF_MAXORD 5
+#define ODL_BDF_NEWTON 4
+#ifndef ODL_BDF_NEWTON_TOL
+#define ODL_BDF_NEWTON_TOL 0.03f
+#endif
+__constant__ double ODL_BDF_GAMMA[ODL_BDF_MAXORD + 1] = {0.0, 1.0, 1.5, 11.0 / 6.0, 25.0 / 12.0, 137.0 / 60.0};
+// alpha_q = (1 - kappa_q) gamma_q, kappa = (0, -0.1850, -1/9, -0.0823, -0.0415, 0)
+__constant__ double ODL_BDF_RALPHA[ODL_BDF_MAXORD + 1] = {
+    0.0, 1.0 / (1.1850 * 1.0), 1.0 / ((1.0 + 1.0 / 9.0) * 1.5), 1.0 / (1.0823 * (11.0 / 6.0)),
+    1.0 / (1.0415 * (25.0 / 12.0)), 1.0 / (137.0 / 60.0)};
+// error_const_q = kappa_q gamma_q + 1/(q+1)
+__constant__ float ODL_BDF_ERRC[ODL_BDF_MAXORD + 1] = {
+    1.0f, (float)(-0.1850 * 1.0 + 0.5), (float)(-1.5 / 9.0 + 1.0 / 3.0), (float)(-0.0823 * (11.0 / 6.0) + 0.25),
+    (float)(-0.0415 * (25.0 / 12.0) + 0.2), (float)(1.0 / 6.0)};
+__constant__ double ODL_BDF_INV[ODL_BDF_MAXORD + 2] = {0.0, 1.0, 0.5, 1.0 / 3.0, 0.25, 0.2, 1.0 / 6.0};
+
+struct OdlBdfAux {
+  double E[ODL_BDF_MAXORD + 2][ODL_N];   // E[k] = D[order+2-k], k = 0 .. order+1
+  OdlLU lu;                              // LU of I - (h/alpha_q) J
+  int order, n_equal;
+  float crate;                           // Newton contraction rate carried from step to step (reset with the LU)
+  bool have_lu, started;
+  __device__ __forceinline__ void reset() { started = false; have_lu = false; order = 1; n_equal = 0; crate = 1.f; }
+};
+
+// D[1..q_new] <- (R(factor) U)^T D[1..q_new]: the differences of the same interpolating polynomial on a grid
+// of spacing factor*h (scipy's change_D; R[i][m] = prod_{l<=i} (l-1-factor*m)/l, U = R(1) = (-1)^m C(j,m)).
+__device__ __forceinline__ void odl_bdf_change_D(OdlBdfAux& ax, int q_old, int q_new, double factor) {
+  double L[ODL_BDF_MAXORD + 2][ODL_N];
+#pragma unroll
+  for (int k = 0; k < ODL_BDF_MAXORD + 2; ++k)
+ODL_UNROLL
+    for (int c = 0; c < ODL_N; ++c) L[k][c] = ax.E[k][c];
+  double Dn[ODL_BDF_MAXORD + 1][ODL_N];          // natural order, [1..5]
+#pragma unroll
+  for (int i = 1; i <= ODL_BDF_MAXORD; ++i) {
+    const int src = (i <= q_new) ? q_old + 2 - i : 0;
+ODL_UNROLL
+    for (int c = 0; c < ODL_N; ++c) Dn[i][c] = (i <= q_new) ? L[src][c] : 0.0;
+  }
+  double tmp[ODL_BDF_MAXORD + 1][ODL_N];
+#pragma unroll
+  for (int m = 1; m <= ODL_BDF_MAXORD; ++m) {
+    double r = 1.0;
+ODL_UNROLL
+    for (int c = 0; c < ODL_N; ++c) tmp[m][c] = 0.0;
+    const double fm = factor * (double)m;
+#pragma unroll
+    for (int i = 1; i <= ODL_BDF_MAXORD; ++i) {
+      r *= ((double)(i - 1) - fm) * ODL_BDF_INV[i];
+      // rows beyond q_new hold zeros, columns beyond q_new are never read back
+ODL_UNROLL
+      for (int c = 0; c < ODL_N; ++c) tmp[m][c] += r * Dn[i][c];
+    }
+  }
+  // U^T: D'[j] = sum_{m<=j} (-1)^m C(j,m) tmp[m]
+  const double U[ODL_BDF_MAXORD + 1][ODL_BDF_MAXORD + 1] = {{0, 0, 0, 0, 0, 0},  {0, -1, -2, -3, -4, -5}, {0, 0, 1, 3, 6, 10},
+                                                            {0, 0, 0, -1, -4, -10}, {0, 0, 0, 0, 1, 5},  {0, 0, 0, 0, 0, -1}};
+#pragma unroll
+  for (int j = 1; j <= ODL_BDF_MAXORD; ++j)
+ODL_UNROLL
+    for (int c = 0; c < ODL_N; ++c) {
+      double acc = 0.0;
+#pragma unroll
+      for (int m = 1; m <= j; ++m) acc += U[m][j] * tmp[m][c];
+      L[j][c] = acc;                             // scratch reused: natural index j
+    }
+#pragma unroll
+  for (int k = 0; k < ODL_BDF_MAXORD + 2; ++k) {
+    const bool live = (k >= 2) && (k <= q_new + 1);
+    const int src = live ? q_new + 2 - k : 1;
+ODL_UNROLL
+    for (int c = 0; c < ODL_N; ++c) ax.E[k][c] = live ? L[src][c] : 0.0;
+  }
+}
+
+__device__ __forceinline__ float odl_bdf_rms(const double (&v)[ODL_N], const double (&rs)[ODL_N]) {
+  double s = 0.0;
+ODL_UNROLL
+  for (int c = 0; c < ODL_N; ++c) { const double a = v[c] * rs[c]; s += a * a; }
+  return sqrtf((float)s * (1.0f / ODL_N));
+}
+
+template <class Sink>
+__device__ __forceinline__ void odl_bdf_attempt(OdlStepper& st, OdlBdfAux& ax, const double (&p)[ODL_P], const OdlShared& S,
+                                                const OdlData& D, const OdlOpts& O, Sink& sink) {
+  const double t = st.t;
+  const double hmin = 4.0 * 2.220446049250313e-16 * fmax(fabs(t), fabs(st.tend));
+  if (!ax.started) {
+    // order 1 start: D[1] = h f(y0); initial step as in Hairer's hinit with the exponent of a first-order method
+    double rs0[ODL_N], y1[ODL_N], f1[ODL_N];
+ODL_UNROLL
+    for (int c = 0; c < ODL_N; ++c) rs0[c] = odl_rcp_approx(O.atol + O.rtol * fabs(st.y[c]));
+    const float d0 = odl_bdf_rms(st.y, rs0), d1 = odl_bdf_rms(st.k1, rs0);
+    double h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6 : 0.01 * (double)(d0 / d1);
+    h0 = fmin(h0, st.tend - t);
+ODL_UNROLL
+    for (int c = 0; c < ODL_N; ++c) y1[c] = st.y[c] + h0 * st.k1[c];
+    odl_rhs(y1, t + h0, p, f1);
+ODL_UNROLL
+    for (int c = 0; c < ODL_N; ++c) f1[c] -= st.k1[c];
+    const float d2 = odl_bdf_rms(f1, rs0) / (float)h0;
+    const float dm = fmaxf(d1, d2);
+    const double h1 = (dm <= 1e-15f) ? fmax(1e-6, h0 * 1e-3) : (double)sqrtf(0.01f / dm);
+    double h = fmin(fmin(100.0 * h0, h1), st.tend - t);
+    if (O.h0 > 0.0) h = fmin(O.h0, st.tend - t);
+    if (!(h > 0.0) || !odl_finite(h)) h = 1e-6 * (st.tend - t);
+    st.h = h;
+    ax.order = 1; ax.n_equal = 0; ax.have_lu = false; ax.started = true;
+#pragma unroll
+    for (int k = 0; k < ODL_BDF_MAXORD + 2; ++k)
+ODL_UNROLL
+      for (int c = 0; c < ODL_N; ++c) ax.E[k][c] = (k == 2) ? h * st.k1[c] : 0.0;
+  }
+  const int q = ax.order;
+  double h = st.h;
+  bool last = false;
+  if ((t + 1.01 * h - st.tend) > 0.0) {
+    const double hn = st.tend - t;
+    if (hn != h) { odl_bdf_change_D(ax, q, q, hn / h); ax.n_equal = 0; ax.have_lu = false; }
+    h = hn; st.h = hn; last = true;
+  }
+  ++st.nsteps;
+  const double tn = last ? st.tend : t + h;
+  const double ralpha = ODL_BDF_RALPHA[q];
+  const double cc = h * ralpha;
+
+  // predictor y_pred = sum_{i<=q} D[i], psi = sum_{i=1..q} gamma_i D[i] / alpha_q
+  double yp[ODL_N], psi[ODL_N], rs[ODL_N];
+ODL_UNROLL
+  for (int c = 0; c < ODL_N; ++c) { yp[c] = st.y[c]; psi[c] = 0.0; }
+#pragma unroll
+  for (int k = 2; k < ODL_BDF_MAXORD + 2; ++k)
+    if (k <= q + 1) {
+      const double g = ODL_BDF_GAMMA[q + 2 - k];
+ODL_UNROLL
+      for (int c = 0; c < ODL_N; ++c) { yp[c] += ax.E[k][c]; psi[c] += g * ax.E[k][c]; }
+    }
+ODL_UNROLL
+  for (int c = 0; c < ODL_N; ++c) { psi[c] *= ralpha; rs[c] = odl_rcp_approx(O.atol + O.rtol * fabs(yp[c])); }
+
+  bool fresh = false;
+  if (!ax.have_lu) {
+    odl_jac(yp, tn, p, ax.lu.a);
+ODL_UNROLL
+    for (int i = 0; i < ODL_N; ++i)
+ODL_UNROLL
+      for (int j = 0; j < ODL_N; ++j) ax.lu.a[i][j] = ((i == j) ? 1.0 : 0.0) - cc * ax.lu.a[i][j];
+    odl_lu_factor(ax.lu);
+    ax.have_lu = true; fresh = true;
+    ax.crate = 1.f;
+  }
+  // scipy's BDF asks for min(0.03, sqrt(rtol)) here; LSODA / CVODE accept a Newton error of a few per cent of
+  // the local error tolerance whatever rtol is, which halves the iterations at tight tolerances
+  const float newton_tol = fmaxf((float)(10.0 * 2.220446049250313e-16 / O.rtol), ODL_BDF_NEWTON_TOL);
+  double d[ODL_N], yk[ODL_N];
+ODL_UNROLL
+  for (int c = 0; c < ODL_N; ++c) { d[c] = 0.0; yk[c] = yp[c]; }
+  bool converged = false;
+  int n_iter = 0;
+  float rate = -1.f, dn_old = -1.f;
+  for (int k = 0; k < ODL_BDF_NEWTON; ++k) {
+    ++n_iter;
+    double f[ODL_N];
+    odl_rhs(yk, tn, p, f);
+    bool fin = true;
+ODL_UNROLL
+    for (int c = 0; c < ODL_N; ++c) { fin = fin && odl_finite(f[c]); f[c] = cc * f[c] - psi[c] - d[c]; }
+    if (!fin) break;
+    odl_lu_solve(ax.lu, f);
+    const float dn = odl_bdf_rms(f, rs);
+    if (!(dn == dn)) break;
+    // contraction rate: measured from the second iteration on; on the first one, the rate the previous steps saw
+    // with this very LU (as LSODA / CVODE do).  est = rate/(1-rate) dn bounds the remaining Newton error.
+    const bool measured = dn_old >= 0.f;
+    if (measured) rate = dn * __frcp_rn(dn_old);
+    const float r_use = measured ? rate : ((ax.crate < 0.3f) ? ax.crate : -1.f);
+    if (measured && !(rate < 0.9f)) break;                      // diverging or too slow: new Jacobian / smaller step
+ODL_UNROLL
+    for (int c = 0; c < ODL_N; ++c) { yk[c] += f[c]; d[c] += f[c]; }
+    if (dn == 0.f || (r_use >= 0.f && r_use * dn < newton_tol * (1.f - r_use))) { converged = true; break; }
+    dn_old = dn;
+  }
+  if (rate >= 0.f) ax.crate = fmaxf(0.2f * ax.crate, rate);
+#ifdef ODL_HOST_HARNESS
+  odl_dbg[0] += 1; odl_dbg[1] += n_iter; if (!converged) odl_dbg[2] += 1; if (fresh) odl_dbg[4] += 1;
+#endif
+  if (!converged) {
+    ax.have_lu = false;
+    if (fresh) {                                                // a current Jacobian did not help: halve the step
+      odl_bdf_change_D(ax, q, q, 0.5);
+      ax.n_equal = 0;
+      st.h = 0.5 * h;
+      if (!(st.h > hmin)) st.status = ODL_HUNDERFLOW;
+    }
+    if (st.nsteps >= O.max_steps && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
+    return;
+  }
+  const float safety = 0.9f * (2 * ODL_BDF_NEWTON + 1) / (float)(2 * ODL_BDF_NEWTON + n_iter);
+  bool finite_all = true;
+ODL_UNROLL
+  for (int c = 0; c < ODL_N; ++c) { finite_all = finite_all && odl_finite(yk[c]); rs[c] = odl_rcp_approx(O.atol + O.rtol * fabs(yk[c])); }
+  const float err = ODL_BDF_ERRC[q] * odl_bdf_rms(d, rs);
+  if (!(err <= 1.0f) || !finite_all) {
+#ifdef ODL_HOST_HARNESS
+    odl_dbg[3] += 1;
+#endif
+    const float fac = (err == err && err < 3.0e38f && finite_all)
+                          ? fmaxf(0.2f, safety * exp2f(-__log2f(err) * (float)ODL_BDF_INV[q + 1])) : 0.2f;
+    odl_bdf_change_D(ax, q, q, (double)fac);
+    ax.n_equal = 0; ax.have_lu = false;
+    st.h = h * (double)fac;
+    if (!(st.h > hmin)) st.status = ODL_HUNDERFLOW;
+    if (st.nsteps >= O.max_steps && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
+    return;
+  }
+  // ---- accepted: D[q+2] = d - D[q+1], D[q+1] = d, D[i] += D[i+1] (i = q .. 0) ----
+  ++ax.n_equal;
+ODL_UNROLL
+  for (int c = 0; c < ODL_N; ++c) { ax.E[0][c] = d[c] - ax.E[1][c]; ax.E[1][c] = d[c]; }
+#pragma unroll
+  for (int k = 2; k < ODL_BDF_MAXORD + 2; ++k)
+    if (k <= q + 1) {
+ODL_UNROLL
+      for (int c = 0; c < ODL_N; ++c) ax.E[k][c] += ax.E[k - 1][c];
+    }
+  // dense output: y(ts) = y_new + sum_{j=1..q} D[j] prod_{i<j} (ts - (tn - i h)) / (h (1+i))
+  if (st.slot < D.n_slot && S.slot_t[st.slot] <= tn) {
+    const double rh = 1.0 / h;
+    do {
+      const double x0 = (S.slot_t[st.slot] - tn) * rh;
+      double yi[ODL_N];
+ODL_UNROLL
+      for (int c = 0; c < ODL_N; ++c) yi[c] = yk[c];
+      double pr = 1.0;
+#pragma unroll
+      for (int k = ODL_BDF_MAXORD + 1; k >= 2; --k)
+        if (k <= q + 1) {
+          const int i = q + 1 - k;
+          pr *= (x0 + (double)i) * ODL_BDF_INV[i + 1];
+ODL_UNROLL
+          for (int c = 0; c < ODL_N; ++c) yi[c] += pr * ax.E[k][c];
+        }
+      sink(st.slot, yi);
+      ++st.slot;
+    } while (st.slot < D.n_slot && S.slot_t[st.slot] <= tn);
+  }
+ODL_UNROLL
+  for (int c = 0; c < ODL_N; ++c) st.y[c] = yk[c];
+  st.t = tn;
+  if (st.nsteps >= O.max_steps && st.slot < D.n_slot && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
+  // The order/step-size selection (+ change_D + Jacobian + LU, ~500 instructions) runs only on attempt numbers
+  // that are multiples of 3 (orders 1-2) or 6 (orders 3-5): the lanes of a warp step in lock step and mostly
+  // share their attempt count, so the expensive branch is issued every few warp steps for many lanes at once
+  // instead of on nearly every warp step for one lane or another.  The rule looks at this system only -- the
+  // result of a solve must not depend on which systems share its warp.
+  if (ax.n_equal < q + 1 || st.slot >= D.n_slot || (st.nsteps % (q >= 3 ? 6 : 3)) != 0) return;
+  // ---- order / step-size selection (every q+1 equal steps) ----
+  float f_m = 0.f, f_p = 0.f;
+  const float f_0 = (err > 0.f) ? exp2f(-__log2f(err) * (float)ODL_BDF_INV[q + 1]) : 3.0e38f;
+  if (q > 1) {
+    const float e = ODL_BDF_ERRC[q - 1] * odl_bdf_rms(ax.E[2], rs);
+    f_m = (e > 0.f) ? exp2f(-__log2f(e) * (float)ODL_BDF_INV[q]) : 3.0e38f;
+  }
+  if (q < ODL_BDF_MAXORD) {
+    const float e = ODL_BDF_ERRC[q + 1] * odl_bdf_rms(ax.E[0], rs);
+    f_p = (e > 0.f) ? exp2f(-__log2f(e) * (float)ODL_BDF_INV[q + 2]) : 3.0e38f;
+  }
+  int qn = q - 1;                                               // np.argmax: first maximum of (f_m, f_0, f_p)
+  float fbest = f_m;                                            // (0 when q == 1, and f_0 >= 1 on an accepted step)
+  if (f_0 > fbest) { fbest = f_0; qn = q; }
+  if (f_p > fbest) { fbest = f_p; qn = q + 1; }
+  const float fac = fminf(10.f, safety * fbest);
+  if (qn == q && fac >= 0.9f && fac < 1.2f) {
+    // same order, about the same step: keep the grid and the LU (LSODA / CVODE have the same dead band) and look
+    // again in a few steps
+    ax.n_equal = (q > 2) ? q - 2 : 0;
+    return;
+  }
+  odl_bdf_change_D(ax, q, qn, (double)fac);
+  ax.order = qn; ax.n_equal = 0; ax.have_lu = false;
+  st.h = h * (double)fac;
+}
+
 template <int SOLVER> struct OdlAuxOf { typedef OdlNoAux type; };
 template <> struct OdlAuxOf<3> { typedef OdlRadauAux type; };
+template <> struct OdlAuxOf<4> { typedef OdlBdfAux type; };
 
-// solver dispatch: 0 = DOPRI5, 1 = ROS23, 2 = per-system choice (DOPRI5 until it reports stiffness), 3 = Radau5
+// solver dispatch: 0 = DOPRI5, 1 = ROS23, 2 = per-system choice (DOPRI5 until it reports stiffness), 3 = Radau5, 4 = BDF
 template <int SOLVER, class Sink>
 __device__ __forceinline__ void odl_attempt(OdlStepper& st, typename OdlAuxOf<SOLVER>::type& ax, const double (&p)[ODL_P],
                                             const OdlShared& S, const OdlData& D, const OdlOpts& O, Sink& sink, bool use_ros) {
   if constexpr (SOLVER == 0) odl_dopri5_attempt(st, p, S, D, O, sink);
   else if constexpr (SOLVER == 1) odl_ros23_attempt(st, p, S, D, O, sink);
   else if constexpr (SOLVER == 3) odl_radau5_attempt(st, ax, p, S, D, O, sink);
+  else if constexpr (SOLVER == 4) odl_bdf_attempt(st, ax, p, S, D, O, sink);
   else { if (use_ros) odl_ros23_attempt(st, p, S, D, O, sink); else odl_dopri5_attempt(st, p, S, D, O, sink); }
 }
 
@@ -1027,8 +1349,10 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
   bool active = false, done = false;
   st.status = ODL_OK; st.nsteps = 0; st.slot = 0;
 
-  // first fetch
-  bool want = true;
+  // first fetch.  O.lanes < 32 (latency-bound tail passes): only the first O.lanes lanes of a warp take systems, so
+  // that the few long systems are spread over more warps -- a warp pays for the union of its lanes' branches.
+  const bool lane_on = (O.lanes <= 0) || (lane < O.lanes);
+  bool want = lane_on;
   for (;;) {
     // ---- (A) finished lanes: cooperative score, write-back ----
     const bool fin = active && done;
@@ -1060,7 +1384,7 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
         if (st.status == ODL_STIFF && A.defer_list[1]) A.defer_list[1][atomicAdd(A.defer_count[1], 1)] = (int)row;
       }
     }
-    if (fin) { active = false; done = false; want = true; }
+    if (fin) { active = false; done = false; want = lane_on; }
     // ---- (B) refill ----
     {
       const long long got = odl_fetch(A.counter, want, lane);
@@ -1080,10 +1404,15 @@ ODL_UNROLL
       }
     }
     if (!__any_sync(ODL_FULL, active)) break;
-    // ---- (C) one step attempt ----
-    if (active && !done) {
-      odl_attempt<SOLVER>(st, ax, p, S, D, O, sink, false);
-      done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
+    // ---- (C) ODL_INNER step attempts between visits of (A)/(B): the ballots, shuffles and the refill logic cost
+    //      about a fifth of a step; a finished lane idles for at most ODL_INNER-1 attempts (systems take ~90) ----
+#pragma unroll 1
+    for (int r = 0; r < ODL_INNER; ++r) {
+      if (active && !done) {
+        odl_attempt<SOLVER>(st, ax, p, S, D, O, sink, false);
+        done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
+      }
+      if (!__any_sync(ODL_FULL, active && !done)) break;
     }
   }
 }
@@ -1093,6 +1422,8 @@ extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
 odl_sweep_ros23_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<1>(D, O, A); }
 extern "C" __global__ void __launch_bounds__(32, 1)
 odl_sweep_radau5_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<3>(D, O, A); }
+extern "C" __global__ void __launch_bounds__(32, 1)
+odl_sweep_bdf_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<4>(D, O, A); }
 
 // ------------------------------------------------------------------------------------------------
 // Full trajectories on the output grid (ModelFramework.integrate, Framework.py:622-683)
@@ -1325,4 +1656,6 @@ extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
 odl_mcmc_auto_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<2>(D, O, A); }
 extern "C" __global__ void __launch_bounds__(32, 1)
 odl_mcmc_radau5_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<3>(D, O, A); }
+extern "C" __global__ void __launch_bounds__(32, 1)
+odl_mcmc_bdf_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<4>(D, O, A); }
 #endif  // ODL_HOST_HARNESS

@@ -30,6 +30,9 @@ def _is_torch_cuda(a):
     return (a is not None) and (not isinstance(a, np.ndarray)) and hasattr(a, "data_ptr") and a.is_cuda
 
 
+SOLVERS = {"dopri5": 0, "ros23": 1, "auto": 2, "radau5": 3, "bdf": 4}
+
+
 class ObsTables:
     """Observation tables in the layout odl_model_set_data wants.
 
@@ -138,13 +141,17 @@ class DeviceModel:
 
     # -- helpers -----------------------------------------------------------------------------------
     @staticmethod
-    def _solver_opts(rtol, atol, max_steps, solver, stiff_check, h0=0.0, hmax=0.0, stiff_min_steps=0, pass_caps=(0, 0)):
+    def _solver_opts(rtol, atol, max_steps, solver, stiff_check, h0=0.0, hmax=0.0, stiff_min_steps=0, pass_caps=(0, 0),
+                     tail_solver=None, early_check_steps=0, tail_lanes=0):
         so = _capi.SolverOpts()
         so.rtol = SCIPY_TOL if rtol is None else float(rtol)
         so.atol = SCIPY_TOL if atol is None else float(atol)
         so.h0, so.hmax = float(h0), float(hmax)
         so.max_steps = int(max_steps)
-        so.solver = {"dopri5": 0, "ros23": 1, "auto": 2, "radau5": 3}[solver] if isinstance(solver, str) else int(solver)
+        so.solver = SOLVERS[solver] if isinstance(solver, str) else int(solver)
+        so.tail_solver = 0 if tail_solver is None else SOLVERS[tail_solver]
+        so.early_check_steps = int(early_check_steps)
+        so.tail_lanes = int(tail_lanes)
         so.stiff_check = 1 if stiff_check else 0
         so.stiff_min_steps = int(stiff_min_steps)
         so.pass_cap0, so.pass_cap1 = int(pass_caps[0]), int(pass_caps[1])
@@ -157,12 +164,13 @@ class DeviceModel:
 
     # -- forward sweep: _Fit_worker (Framework.py:41-48) -------------------------------------------
     def sweep(self, theta, rtol=None, atol=None, max_steps=500000, solver="dopri5", stiff_check=False,
-              return_pred=False, out=None, stiff_min_steps=0, pass_caps=(0, 0)):
+              return_pred=False, out=None, stiff_min_steps=0, pass_caps=(0, 0), tail_solver=None, early_check_steps=0,
+              tail_lanes=0):
         """theta [n, P] (numpy -> host path, torch cuda tensor -> device path).
 
         Returns dict(chi, r2, status, nsteps[, pred]) of the same kind as the input."""
         so = self._solver_opts(rtol, atol, max_steps, solver, stiff_check, stiff_min_steps=stiff_min_steps,
-                               pass_caps=pass_caps)
+                               pass_caps=pass_caps, tail_solver=tail_solver, early_check_steps=early_check_steps, tail_lanes=tail_lanes)
         if _is_torch_cuda(theta):
             import torch
             th = theta.contiguous()

@@ -38,7 +38,7 @@ def solve(lib, solver, theta, slot_t, y0, rtol, atol, max_steps=2000000):
     y0 = np.ascontiguousarray(y0, np.float64)
     out = np.full((slot_t.size, y0.size), np.nan)
     ns = C.c_int()
-    st = lib.harness_solve({"dopri5": 0, "ros23": 1, "radau5": 3}[solver], theta.ctypes.data, slot_t.ctypes.data,
+    st = lib.harness_solve({"dopri5": 0, "ros23": 1, "radau5": 3, "bdf": 4}[solver], theta.ctypes.data, slot_t.ctypes.data,
                            slot_t.size, y0.ctypes.data, float(slot_t[0]) if slot_t[0] <= 0 else 0.0, rtol, atol,
                            max_steps, out.ctypes.data, C.byref(ns))
     return out, st, ns.value

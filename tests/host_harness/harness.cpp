@@ -52,7 +52,7 @@ extern "C" void harness_clu(const double* Ar, const double* Ai, const double* br
 extern "C" void harness_dbg(long long* out) { for (int i = 0; i < 8; ++i) { out[i] = odl_dbg[i]; odl_dbg[i] = 0; } }
 extern "C" int harness_dims(int* n, int* p) { *n = ODL_N; *p = ODL_P; return 0; }
 
-// solver: 0 DOPRI5, 1 ROS23, 3 Radau5.  out: [n_slot][ODL_N].  Returns the status word.
+// solver: 0 DOPRI5, 1 ROS23, 3 Radau5, 4 BDF.  out: [n_slot][ODL_N].  Returns the status word.
 extern "C" int harness_solve(int solver, const double* theta, const double* slot_t, int n_slot, const double* y0,
                              double t0, double rtol, double atol, int max_steps, double* out, int* nsteps) {
   int y0p[ODL_N];
@@ -74,10 +74,45 @@ extern "C" int harness_solve(int solver, const double* theta, const double* slot
   odl_emit_initial_slots(st, S, D, sink);
   OdlRadauAux ax;
   ax.reset();
+  OdlBdfAux bx;
+  bx.reset();
   while (st.slot < D.n_slot && st.status == ODL_OK) {
     if (solver == 0) odl_dopri5_attempt(st, p, S, D, O, sink);
     else if (solver == 1) odl_ros23_attempt(st, p, S, D, O, sink);
+    else if (solver == 4) odl_bdf_attempt(st, bx, p, S, D, O, sink);
     else odl_radau5_attempt(st, ax, p, S, D, O, sink);
+  }
+  *nsteps = st.nsteps;
+  return st.status;
+}
+
+// DOPRI5 progress profile (dev tool: how well does early progress predict the total step count?):
+// marks[k] = time reached after checkpoints[k] attempted steps (NaN if the solve ended earlier), hs[k] = step size then
+extern "C" int harness_progress(const double* theta, const double* slot_t, int n_slot, const double* y0, double t0,
+                                double rtol, double atol, int max_steps, const int* checkpoints, int n_check,
+                                double* marks, double* hs, int* nsteps) {
+  int y0p[ODL_N];
+  for (int i = 0; i < ODL_N; ++i) y0p[i] = -1;
+  OdlData D;
+  memset(&D, 0, sizeof D);
+  D.slot_t = slot_t; D.y0 = y0; D.y0_from_param = y0p; D.n_slot = n_slot; D.t0 = t0;
+  OdlOpts O;
+  memset(&O, 0, sizeof O);
+  O.rtol = rtol; O.atol = atol; O.max_steps = max_steps; O.stiff_min_steps = 2000;
+  OdlShared S;
+  memset(&S, 0, sizeof S);
+  S.slot_t = const_cast<double*>(slot_t);
+  double p[ODL_P];
+  for (int q = 0; q < ODL_P; ++q) p[q] = theta[q];
+  static double scratch[4096];
+  OdlStepper st;
+  HostSink sink{scratch};
+  odl_init_system(st, p, D, O, nullptr);
+  odl_emit_initial_slots(st, S, D, sink);
+  for (int k = 0; k < n_check; ++k) { marks[k] = NAN; hs[k] = NAN; }
+  while (st.slot < D.n_slot && st.status == ODL_OK) {
+    odl_dopri5_attempt(st, p, S, D, O, sink);
+    for (int k = 0; k < n_check; ++k) if (st.nsteps == checkpoints[k]) { marks[k] = st.t; hs[k] = st.h; }
   }
   *nsteps = st.nsteps;
   return st.status;

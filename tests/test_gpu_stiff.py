@@ -83,15 +83,38 @@ def test_auto_routes_stiff_systems_and_keeps_the_rest():
     assert (plain["status"][:24] == 4).sum() >= 12            # DOPRI5 alone flags (most of) the stiff block
     auto = dm.sweep(theta, solver="auto", max_steps=2000000)
     assert np.all(auto["status"][:24] == 0)
-    # every system was finished by exactly one of the two steppers: same kernel, same numbers
-    rad = dm.sweep(theta, solver="radau5", max_steps=2000000)
+    # every system was finished by exactly one of the two steppers (DOPRI5, or the BDF stiff pass): same kernel,
+    # same numbers -- a solve does not depend on which systems share its warp or which pass it ran in
+    bdf = dm.sweep(theta, solver="bdf", max_steps=2000000)
     dop = dm.sweep(theta, solver="dopri5", max_steps=2000000)
-    same_rad = (auto["chi"] == rad["chi"]) | (np.isnan(auto["chi"]) & np.isnan(rad["chi"]))
+    same_bdf = (auto["chi"] == bdf["chi"]) | (np.isnan(auto["chi"]) & np.isnan(bdf["chi"]))
     same_dop = (auto["chi"] == dop["chi"]) | (np.isnan(auto["chi"]) & np.isnan(dop["chi"]))
-    assert np.all(same_rad | same_dop)
-    assert same_rad[:24].sum() >= 12 and same_dop[24:].sum() >= 20
+    assert np.all(same_bdf | same_dop)
+    assert same_bdf[:24].sum() >= 12 and same_dop[24:].sum() >= 20
     # far fewer steps than the explicit method needs on the stiff block
     assert np.median(auto["nsteps"][:24]) < 0.2 * np.median(dop["nsteps"][:24])
+    # the Radau5 stiff pass is still selectable and agrees with the BDF one to solver accuracy
+    rad = dm.sweep(theta, solver="auto", tail_solver="radau5", max_steps=2000000)
+    np.testing.assert_allclose(rad["chi"][:24], auto["chi"][:24], rtol=2e-5)
+
+
+def test_bdf_matches_lsoda_on_stiff_systems():
+    """The stiff pass of the auto sweep: variable-order BDF, the method family of LSODA's stiff branch."""
+    dm, tab = device_model("two_i")
+    theta = stiff_thetas(32, seed=3)
+    out = dm.sweep(theta, solver="bdf", return_pred=True)
+    assert np.all(out["status"] == 0) and out["nsteps"].max() < 6000
+    rhs = oracle_rhs("two_i")
+    for k in range(len(theta)):
+        vec, chi, r2 = orc.solve_unit(rhs, theta[k], tab, 1e-11, 1e-11, mxstep=500000)
+        np.testing.assert_allclose(out["pred"][k], vec, rtol=5e-6, atol=1e-3)
+        np.testing.assert_allclose(out["chi"][k], chi, rtol=1e-4)
+    again = dm.sweep(theta[::-1].copy(), solver="bdf")
+    assert np.array_equal(again["chi"][::-1], out["chi"], equal_nan=True)      # lane placement does not matter
+    tight = dm.sweep(theta[:4], solver="bdf", rtol=1e-11, atol=1e-11, return_pred=True, max_steps=2000000)
+    for k in range(4):
+        vec, chi, _ = orc.solve_unit(rhs, theta[k], tab, 1e-13, 1e-13, mxstep=500000)
+        np.testing.assert_allclose(tight["pred"][k], vec, rtol=2e-7, atol=1e-4)
 
 
 def test_mcmc_on_the_stiff_variant_ros23_and_auto():

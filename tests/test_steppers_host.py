@@ -29,7 +29,8 @@ def _relerr(out, ref):
     return np.nanmax(np.abs(out - ref) / (np.abs(ref) + 1.0))
 
 
-@pytest.mark.parametrize("solver,bound,max_mean_steps", [("dopri5", 5e-7, 400), ("radau5", 1e-6, 500), ("ros23", 1e-4, 8000)])
+@pytest.mark.parametrize("solver,bound,max_mean_steps", [("dopri5", 5e-7, 400), ("radau5", 1e-6, 500), ("bdf", 3e-6, 600),
+                                                         ("ros23", 1e-4, 8000)])
 def test_steppers_at_default_tolerance(two_i, solver, bound, max_mean_steps):
     lib, tab, slots = two_i
     g = golden("two_i")
@@ -68,10 +69,27 @@ def test_stiff_variant_radau5_is_cheap_and_dopri5_is_not(two_i):
     assert st3 == 0 and _relerr(out3, ref) < 1e-5
 
 
+def test_bdf_converges_with_tolerance_and_is_cheap_on_the_stiff_variant(two_i):
+    """Variable-order BDF (LSODA's stiff family): error falls with the tolerance; on the config-4 point it needs a
+    few hundred steps where the explicit method is stability-limited."""
+    lib, tab, slots = two_i
+    th = golden("two_i")["theta"][0]
+    ref = _ref(th, tab, slots)
+    errs = []
+    for tol in (1e-5, 1e-8, 1e-11):
+        out, st, _ = hh.solve(lib, "bdf", th, slots, tab.y0, tol, tol)
+        assert st == 0
+        errs.append(_relerr(out, ref))
+    assert errs[0] > errs[1] > errs[2] and errs[2] < 1e-8
+    stiff = np.array([0.5, 1e-7, 50.0, 1e-2, 1e4])
+    out, st, ns = hh.solve(lib, "bdf", stiff, slots, tab.y0, TOL, TOL)
+    assert st == 0 and ns < 600 and _relerr(out, _ref(stiff, tab, slots)) < 1e-6
+
+
 def test_step_budget_and_nonfinite_inputs_end_in_status_words(two_i):
     lib, tab, slots = two_i
     th = golden("two_i")["theta"][0]
-    for solver in ("dopri5", "ros23", "radau5"):
+    for solver in ("dopri5", "ros23", "radau5", "bdf"):
         _, st, ns = hh.solve(lib, solver, th, slots, tab.y0, TOL, TOL, max_steps=7)
         assert st == 1 and ns == 7
         bad = th.copy(); bad[1] = np.nan
