@@ -42,6 +42,9 @@ extern "C" {
 enum { ODL_SUCCESS = 0, ODL_EINVAL = 1, ODL_ECUDA = 2, ODL_ECOMPILE = 3, ODL_ENODEVICE = 4, ODL_EIO = 5 };
 enum { ODL_MEM_HOST = 0, ODL_MEM_DEVICE = 1 };
 enum { ODL_SOLVER_DOPRI5 = 0, ODL_SOLVER_ROS23 = 1, ODL_SOLVER_AUTO = 2, ODL_SOLVER_RADAU5 = 3, ODL_SOLVER_BDF = 4 };
+/* odl_solver_opts.auto_flags */
+enum { ODL_AUTO_UNORDERED = 1,   /* process rows in input order (no cost ordering) */
+       ODL_AUTO_CONCURRENT = 2   /* run the stiff pass beside the DOPRI5 pass instead of after it (measured slower) */ };
 enum { ODL_RNG_PHILOX = 0, ODL_RNG_HOST_STREAMS = 1, ODL_RNG_FORCED = 2 };
 /* per-system status words */
 enum { ODL_ST_OK = 0, ODL_ST_MAXSTEPS = 1, ODL_ST_NONFINITE = 2, ODL_ST_HUNDERFLOW = 3, ODL_ST_STIFF = 4,
@@ -68,13 +71,13 @@ typedef struct odl_solver_opts {
   int stiff_check;     /* DOPRI5: detect stiffness and stop with ODL_ST_STIFF */
   int stiff_min_steps; /* ... only while more than this many steps of the current size remain (0 = 2000) */
   int pass_cap0;       /* ODL_SOLVER_AUTO: step cap of the first DOPRI5 pass (0 = 512) */
-  int pass_cap1;       /* ODL_SOLVER_AUTO: step cap of the optional second DOPRI5 pass (0 = none) */
+  int tail_warps;      /* ODL_AUTO_CONCURRENT: single-warp CTAs of the stiff pass per SM beside the DOPRI5 pass (0 = 2) */
   int tail_solver;     /* ODL_SOLVER_AUTO: stepper of the pass over what DOPRI5 did not finish:
                           0 = default (ODL_SOLVER_BDF), or ODL_SOLVER_RADAU5 */
   int early_check_steps; /* ODL_SOLVER_AUTO: the first pass drops a system after this many attempts when its progress
                           projects beyond pass_cap0 (0 = pass_cap0/2, -1 = never) */
   int tail_lanes;      /* ODL_SOLVER_AUTO: lanes per warp that take systems in the stiff pass (0 = 32) */
-  int reserved[1];
+  int auto_flags;      /* ODL_SOLVER_AUTO: ODL_AUTO_* bits, 0 = cost-ordered DOPRI5 pass, then the stiff pass */
 } odl_solver_opts;
 
 typedef struct odl_mcmc_opts {
@@ -136,9 +139,12 @@ int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_opts* mo, c
 /* device time (ms) of the kernels launched by the last odl_sweep/odl_mcmc/odl_trajectory call on this
    model, measured with CUDA events on the launching stream; blocks until they have completed */
 int odl_model_last_kernel_ms(odl_model* m, float* ms);
-/* the same split over the passes of the last ODL_SOLVER_AUTO sweep: ms3[0] DOPRI5 bulk pass, ms3[1] DOPRI5
-   pass over the deferred long systems, ms3[2] Radau5 pass over the stiff ones (single-pass calls: ms3[0]) */
+/* the same split for the last ODL_SOLVER_AUTO sweep: ms3[0] cost ordering, ms3[1] DOPRI5 bulk pass, ms3[2] what the
+   stiff pass (running beside the bulk pass) still needed after the bulk pass had ended (single-pass calls: ms3[0]) */
 int odl_model_last_pass_ms(odl_model* m, float* ms3);
+/* development aid: copies the first `count` ints of the device-side counter block of the last odl_sweep
+   ([0] work counter, [16] feed count, [32] feed ticket, [48] warps entered, [64] warps left, [80] watchdog) */
+int odl_debug_counters(odl_model* m, int* out, int count);
 /* number of kernel launches issued by this library in this process */
 long long odl_launch_count(void);
 

@@ -13,11 +13,12 @@ SUCCESS, EINVAL, ECUDA, ECOMPILE, ENODEVICE, EIO = range(6)
 MEM_HOST, MEM_DEVICE = 0, 1
 SOLVER_DOPRI5, SOLVER_ROS23, SOLVER_AUTO, SOLVER_RADAU5, SOLVER_BDF = 0, 1, 2, 3, 4
 RNG_PHILOX, RNG_HOST_STREAMS, RNG_FORCED = 0, 1, 2
+AUTO_UNORDERED, AUTO_CONCURRENT = 1, 2
 ST_OK, ST_MAXSTEPS, ST_NONFINITE, ST_HUNDERFLOW, ST_STIFF, ST_ALLMASKED = 0, 1, 2, 3, 4, 8
 
 EXPORTS = ["odl_abi_version", "odl_last_error", "odl_model_create", "odl_model_destroy", "odl_model_build_log",
            "odl_model_kernel_info", "odl_model_set_data", "odl_model_set_grid", "odl_sweep", "odl_trajectory",
-           "odl_mcmc", "odl_model_last_kernel_ms", "odl_model_last_pass_ms", "odl_launch_count", "odl_fp64_peak"]
+           "odl_mcmc", "odl_model_last_kernel_ms", "odl_model_last_pass_ms", "odl_launch_count", "odl_fp64_peak", "odl_debug_counters"]
 
 
 class OdlError(RuntimeError):
@@ -35,7 +36,8 @@ class BuildOpts(C.Structure):
 class SolverOpts(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("h0", C.c_double), ("hmax", C.c_double),
                 ("max_steps", C.c_int), ("solver", C.c_int), ("stiff_check", C.c_int), ("stiff_min_steps", C.c_int),
-                ("pass_cap0", C.c_int), ("pass_cap1", C.c_int), ("tail_solver", C.c_int), ("early_check_steps", C.c_int), ("tail_lanes", C.c_int), ("reserved", C.c_int * 1)]
+                ("pass_cap0", C.c_int), ("tail_warps", C.c_int), ("tail_solver", C.c_int), ("early_check_steps", C.c_int),
+                ("tail_lanes", C.c_int), ("auto_flags", C.c_int)]
 
 
 class McmcOpts(C.Structure):
@@ -83,6 +85,7 @@ def lib():
                            C.c_void_p]
     L.odl_model_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.odl_model_last_pass_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.odl_debug_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.odl_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     if L.odl_abi_version() != 2:
         raise OdlError(EIO, "libodelib_b200.so ABI version mismatch - rebuild")

@@ -41,6 +41,8 @@ struct OdlOpts {
   int early_check_steps;         // > 0: DOPRI5 stops with ODL_MAXSTEPS already after this many attempts when the
                                  //      progress so far projects to more than max_steps attempts in total
   int lanes;                     // sweep kernels: lanes per warp that take systems (0 = all 32)
+  int watchdog_spins;            // consumer: idle polls (~0.4 us each) of a warp before it gives up on the producer
+  int pad_;
 };
 
 struct OdlSweepArgs {
@@ -56,6 +58,27 @@ struct OdlSweepArgs {
   unsigned long long* counter;   // work counter, zeroed by the host before launch
   int* defer_list[2];            // optional: rows that stopped with [0] ODL_MAXSTEPS, [1] ODL_STIFF are appended
   int* defer_count[2];           //           here for a later pass (device-side lists, no host round trip)
+  // Coupling of the bulk pass (producer) and the stiff pass that runs BESIDE it (consumer), ODL_SOLVER_AUTO:
+  int* prod_started;             // producer: +1 per warp on entry ...
+  int* prod_exited;              //           ... and on exit (after its last deferral is visible)
+  const unsigned long long* prod_counter;  // consumer: the producer's work counter and item count; the feed is
+  long long prod_n;                        //   complete once the counter is dry and every warp that entered has left
+  unsigned long long* feed_ticket;         // consumer mode switch: next unclaimed entry of index[] (entries of index[]
+                                           //   start as -1 and land while the producer runs; *index_count grows)
+  int* watchdog;                           // consumer: incremented when a warp gave up waiting for the producer
+};
+
+// Cost ordering of a sweep (ODL_SOLVER_AUTO): key = |J(t0, y0, theta)|_inf (t_end - t0), quarter-octave bins,
+// processed from the highest bin down -- the systems that need the most steps (and those the stiff pass will
+// take over) start first, so nothing long is left for the end of the launch.
+#define ODL_ORDER_BINS 256
+struct OdlOrderArgs {
+  const double* theta;           // [n][n_param]
+  long long n;
+  unsigned char* bins;           // [n]
+  int* hist;                     // [ODL_ORDER_BINS] zeroed by the host
+  int* cursor;                   // [ODL_ORDER_BINS] start of every bin in index[] (descending bins), then a cursor
+  int* index;                    // [n] out: rows in processing order
 };
 
 struct OdlTrajArgs {

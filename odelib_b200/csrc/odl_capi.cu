@@ -135,12 +135,13 @@ struct odl_model {
   CUfunction k_sweep_ros = nullptr, k_mcmc_ros = nullptr, k_mcmc_auto = nullptr;
   CUfunction k_sweep_radau = nullptr, k_mcmc_radau = nullptr;
   CUfunction k_sweep_bdf = nullptr, k_mcmc_bdf = nullptr;
+  CUfunction k_order_key = nullptr, k_order_scan = nullptr, k_order_scatter = nullptr;
   Tables data, grid;
   DevBuf counter;
   DevBuf scratch[16];
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evp[2] = {nullptr, nullptr};   // between the cohort passes of an AUTO sweep
-  cudaEvent_t ev_aux = nullptr;
+  cudaEvent_t ev_aux = nullptr, ev_fork = nullptr;
   cudaStream_t aux = nullptr;                // helper stream: the Radau5 pass runs beside the deferred DOPRI5 pass
   int n_pass = 0;
   bool timed = false;
@@ -269,7 +270,8 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
       {"odl_sweep_ros23_kernel", &m->k_sweep_ros, true}, {"odl_mcmc_ros23_kernel", &m->k_mcmc_ros, true},
       {"odl_mcmc_auto_kernel", &m->k_mcmc_auto, true}, {"odl_sweep_radau5_kernel", &m->k_sweep_radau, true},
       {"odl_mcmc_radau5_kernel", &m->k_mcmc_radau, true}, {"odl_sweep_bdf_kernel", &m->k_sweep_bdf, true},
-      {"odl_mcmc_bdf_kernel", &m->k_mcmc_bdf, true}};
+      {"odl_mcmc_bdf_kernel", &m->k_mcmc_bdf, true}, {"odl_order_key_kernel", &m->k_order_key, true},
+      {"odl_order_scan_kernel", &m->k_order_scan, true}, {"odl_order_scatter_kernel", &m->k_order_scatter, true}};
   for (auto& k : ks) {
     CUresult r = g_drv.ModuleGetFunction(k.fn, m->mod, k.name);
     if (r != CUDA_SUCCESS) {
@@ -280,9 +282,10 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
   if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess ||
       cudaEventCreate(&m->evp[0]) != cudaSuccess || cudaEventCreate(&m->evp[1]) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_aux, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking) != cudaSuccess)
     return bail(fail(ODL_ECUDA, "cudaEventCreate / cudaStreamCreate failed"));
-  if ((rc = m->counter.ensure(512))) return bail(rc);
+  if ((rc = m->counter.ensure(4096))) return bail(rc);
   m->on_gpu = true;
   *out = m;
   return 0;
@@ -300,6 +303,7 @@ extern "C" int odl_model_destroy(odl_model* m) {
   if (m->ev1) cudaEventDestroy(m->ev1);
   for (auto& e : m->evp) if (e) cudaEventDestroy(e);
   if (m->ev_aux) cudaEventDestroy(m->ev_aux);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->aux) cudaStreamDestroy(m->aux);
   delete m;
   return 0;
@@ -441,6 +445,9 @@ static void fill_opts(OdlOpts& o, const odl_solver_opts* so) {
   o.defer_split_steps = 0;
   o.early_check_steps = 0;
   o.lanes = 0;
+  o.watchdog_spins = 75000000;   // ~30 s without a single entry and without the producer finishing
+  if (const char* w = getenv("ODL_WATCHDOG_SPINS")) o.watchdog_spins = std::max(1000, atoi(w));
+  o.pad_ = 0;
 }
 
 static int launch(odl_model* m, CUfunction f, unsigned grid, unsigned block, size_t smem, cudaStream_t s, void** params) {
@@ -512,7 +519,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   auto cnt = [&](int off) { return reinterpret_cast<int*>(cb + off); };
   A.counter = ctr(0);
   OdlOpts O; fill_opts(O, so);
-  ODL_CUDA(cudaMemsetAsync(m->counter.p, 0, 512, s));
+  ODL_CUDA(cudaMemsetAsync(m->counter.p, 0, 4096, s));
   OdlData D = m->data.d;
   auto go = [&](cudaStream_t sx, CUfunction f, const OdlOpts& Ox, const OdlSweepArgs& Ax, unsigned block, long long items) -> int {
     const size_t smem = smem_bytes(D, (int)block);
@@ -535,79 +542,126 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
                     (solver == ODL_SOLVER_BDF ? m->k_sweep_bdf : m->k_sweep));
     if ((rc = go(s, f1, O, A, warp_cta ? 32u : pick_block(D, m->block), n))) return rc;
   } else {
-    // Cohort passes (no host synchronisation in between; list lengths stay on the device).  Default: two passes,
-    // DOPRI5 capped at pass_cap0 attempted steps, then Radau5 on everything it did not finish (measured best on
-    // the demo priors: 1M two_i draws 4.2 + 2.8 ms).  pass_cap1 > pass_cap0 inserts a second DOPRI5 pass:
-    //   pass 0  DOPRI5, every system, at most cap0 attempted steps; the few that need more go to list A,
-    //           those Hairer's test calls stiff go straight to list B
-    //           (as do those whose progress at the cap projects to more than cap1 steps)
-    //   pass 1  DOPRI5 on list A with cap1 (caller's stream)  ||  Radau5 on list B (helper stream), concurrently:
-    //           both are latency-bound on a few long systems and leave most of every SM idle on their own
-    //   pass 2  Radau5 on what pass 1 still could not finish (list C)
-    //   (pass_cap1 <= pass_cap0 skips the second DOPRI5 pass: everything deferred goes to Radau5)
-    // Step counts are heavy-tailed (two_i prior: median 56, mean 103, p99.9 3200, max > 1e5): capping a pass
-    // bounds how long the lanes of a warp wait for their slowest neighbour once the work counter runs dry.
-    DevBuf& la = m->scratch[st.next++];
-    DevBuf& lb = m->scratch[st.next++];
-    DevBuf& lc = m->scratch[st.next++];
-    if ((rc = la.ensure((size_t)n * sizeof(int)))) return rc;
-    if ((rc = lb.ensure((size_t)n * sizeof(int)))) return rc;
-    if ((rc = lc.ensure((size_t)n * sizeof(int)))) return rc;
-    int* listA = static_cast<int*>(la.p);
-    int* listB = static_cast<int*>(lb.p);
-    int* listC = static_cast<int*>(lc.p);
+    // Cost-ordered bulk pass, then the stiff pass (no host synchronisation; list lengths stay on the device):
+    //   order    key = |J(t0,y0,theta)|_inf (t_end-t0) per system, quarter-octave bins, highest first -> index[]
+    //            (Spearman 0.73 with the DOPRI5 step count on the demo priors; the 1 % longest systems all sit in
+    //            the first tenth).  Long systems start first, so the launch does not end on a few stragglers, and
+    //            the ones DOPRI5 cannot finish are found while most of the sweep is still ahead.
+    //   bulk     DOPRI5, every system in that order, at most cap0 attempted steps (a half-way check drops systems
+    //            whose progress projects beyond the cap; Hairer's test drops the ones it calls stiff) -> feed list
+    //   stiff    variable-order BDF (or Radau5) over the feed list, single-warp CTAs, as many as fit.  It is bound by
+    //            the latency of its longest systems (~1000 sequential steps), not by throughput.
+    //            ODL_AUTO_CONCURRENT runs it BESIDE the bulk pass instead: a persistent grid of tail_warps CTAs
+    //            per SM, launched first on a helper stream, takes entries as they land, and the bulk grid is sized
+    //            to what fits next to it.  Measured on B200 (1M two_i prior draws): 6.5 ms against 5.25 ms for one
+    //            pass after the other -- a BDF warp holds 7.7k registers, the two consumer warps per SM that leave
+    //            room for three of the four bulk CTAs have to run three rounds, and every BDF step gets slower
+    //            next to twelve DOPRI5 warps.  Kept as an option; the default is sequential.
+    // Step counts are heavy-tailed (two_i prior: median 56, mean 103, p99.9 3200, max > 1e5 for DOPRI5).
+    DevBuf& bidx = m->scratch[st.next++];
+    DevBuf& bfeed = m->scratch[st.next++];
+    DevBuf& bbins = m->scratch[st.next++];
+    if ((rc = bidx.ensure((size_t)n * sizeof(int)))) return rc;
+    if ((rc = bfeed.ensure((size_t)n * sizeof(int)))) return rc;
+    if ((rc = bbins.ensure((size_t)n))) return rc;
+    int* index = static_cast<int*>(bidx.p);
+    int* feed = static_cast<int*>(bfeed.p);
+    const int flags = so ? so->auto_flags : 0;
+    const bool ordered = !(flags & ODL_AUTO_UNORDERED);
+    const bool concurrent = (flags & ODL_AUTO_CONCURRENT) != 0;
     const int cap0 = so && so->pass_cap0 > 0 ? so->pass_cap0 : 512;
-    const int cap1 = so && so->pass_cap1 > 0 ? so->pass_cap1 : 0;
-    const bool two_dopri = cap1 > cap0;
     CUfunction k_tail = tail_solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau : m->k_sweep_bdf;
-    // tail passes are latency-bound (a handful of long systems): modest grids so that both fit on the SMs at once
-    const long long tail_items = std::max<long long>(32, std::min<long long>(n, (long long)m->sm_count * 4 * 32));
+    // counter block (zeroed above): [0] bulk work counter, [64] feed count, [128] feed ticket, [192] warps entered,
+    // [256] warps left, [1024] hist[256], [2048] cursor[256]
+    ODL_CUDA(cudaMemsetAsync(feed, 0xFF, (size_t)n * sizeof(int), s));
+    if (ordered) {
+      OdlOrderArgs R{};
+      R.theta = A.theta; R.n = n; R.bins = static_cast<unsigned char*>(bbins.p);
+      R.hist = cnt(1024); R.cursor = cnt(2048); R.index = index;
+      OdlData Dl = D;
+      void* p1[] = {&Dl, &R};
+      void* p2[] = {&R};
+      const unsigned g1 = (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)m->sm_count * 8));
+      const unsigned g3 = (unsigned)std::max<long long>(1, std::min<long long>((n + 2047) / 2048, (long long)m->sm_count * 8));
+      if ((rc = launch(m, m->k_order_key, g1, 256, 0, s, p1))) return rc;
+      if ((rc = launch(m, m->k_order_scan, 1, ODL_ORDER_BINS, 0, s, p2))) return rc;
+      if ((rc = launch(m, m->k_order_scatter, g3, 256, 0, s, p2))) return rc;
+    }
+    ODL_CUDA(cudaEventRecord(m->evp[1], s));
+    const unsigned block0 = pick_block(D, m->block);
+    const size_t smem0 = smem_bytes(D, (int)block0), smem_t = smem_bytes(D, 32);
+    if (smem0 > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(m->k_sweep, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem0));
+    if (smem_t > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(k_tail, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem_t));
+    // both kernels must ask for the same L1/shared split, or no SM can hold CTAs of both at once (the second kernel
+    // would wait for the first to drain: measured -- the bulk pass started only after the consumers had given up)
+    ODL_CU(g_drv.FuncSetAttribute(m->k_sweep, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100));
+    ODL_CU(g_drv.FuncSetAttribute(k_tail, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100));
+    int per_sm0 = 0, per_sm_t = 0, regs0 = 0, regs_t = 0;
+    ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, m->k_sweep, (int)block0, smem0));
+    ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, k_tail, 32, smem_t));
+    ODL_CU(g_drv.FuncGetAttribute(&regs0, CU_FUNC_ATTRIBUTE_NUM_REGS, m->k_sweep));
+    ODL_CU(g_drv.FuncGetAttribute(&regs_t, CU_FUNC_ATTRIBUTE_NUM_REGS, k_tail));
+    if (per_sm0 < 1 || per_sm_t < 1) return fail(ODL_ECUDA, "sweep kernel does not fit on an SM (shared memory / registers)");
+    int tail_warps = so && so->tail_warps > 0 ? so->tail_warps : 2;
+    int bulk_ctas = per_sm0;
+    if (concurrent) {
+      // what fits beside tail_warps single-warp CTAs of the stiff kernel: registers (allocated per warp in units of
+      // 8 per thread) and shared memory of one SM
+      const long long reg_file = 65536, smem_sm = 227 * 1024;
+      const long long rt = (long long)((regs_t + 7) / 8 * 8) * 32, r0 = (long long)((regs0 + 7) / 8 * 8) * block0;
+      tail_warps = std::min(tail_warps, per_sm_t);
+      while (tail_warps > 1 && (reg_file - tail_warps * rt < r0 || smem_sm - tail_warps * (long long)(smem_t + 1024) < (long long)(smem0 + 1024)))
+        --tail_warps;
+      const long long by_regs = (reg_file - tail_warps * rt) / r0;
+      const long long by_smem = (smem_sm - tail_warps * (long long)(smem_t + 1024)) / (long long)(smem0 + 1024);
+      bulk_ctas = (int)std::max<long long>(1, std::min<long long>(per_sm0, std::min(by_regs, by_smem)));
+    } else {
+      tail_warps = per_sm_t;
+    }
     OdlOpts O0 = O; O0.stiff_check = 1; O0.max_steps = std::min(cap0, O.max_steps);
-    O0.defer_split_steps = two_dopri ? cap1 : 0;   // projected to need more than cap1 steps -> straight to the stiff pass
     // half-way check: a system whose progress projects beyond the cap leaves at cap0/2 (recall ~100 %, precision ~50 %
-    // on the demo priors: the stiff pass gets twice the systems -- it is latency-bound, not throughput-bound -- and
-    // the warps of this pass wait half as long for their stragglers)
+    // on the demo priors)
     O0.early_check_steps = so && so->early_check_steps != 0 ? std::max(0, so->early_check_steps) : O0.max_steps / 2;
     OdlSweepArgs A0 = A;
-    A0.defer_list[0] = two_dopri ? listA : listB; A0.defer_count[0] = two_dopri ? cnt(64) : cnt(192);
-    A0.defer_list[1] = listB; A0.defer_count[1] = cnt(192);
-    if ((rc = go(s, m->k_sweep, O0, A0, pick_block(D, m->block), n))) return rc;
-    ODL_CUDA(cudaEventRecord(m->evp[0], s));
+    A0.index = ordered ? index : nullptr;
+    A0.defer_list[0] = A0.defer_list[1] = feed; A0.defer_count[0] = A0.defer_count[1] = cnt(64);
+    A0.prod_started = cnt(192); A0.prod_exited = cnt(256);
     OdlOpts O2 = O; O2.stiff_check = 0;
     O2.lanes = so && so->tail_lanes > 0 ? std::min(32, so->tail_lanes) : 0;
-    if (two_dopri) {
-      // list B (Radau5) on the helper stream, concurrently with list A (DOPRI5) on the caller's stream
-      ODL_CUDA(cudaStreamWaitEvent(m->aux, m->evp[0], 0));
-      OdlSweepArgs A2 = A;
-      A2.index = listB; A2.index_count = cnt(192); A2.counter = ctr(256);
-      A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
-      if ((rc = go(m->aux, k_tail, O2, A2, 32u, tail_items))) return rc;
+    OdlSweepArgs A2 = A;
+    A2.index = feed; A2.index_count = cnt(64); A2.counter = nullptr; A2.feed_ticket = ctr(128);
+    A2.prod_counter = ctr(0); A2.prod_n = n; A2.prod_started = cnt(192); A2.prod_exited = cnt(256);
+    A2.watchdog = cnt(320);
+    A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
+    const unsigned grid0 = (unsigned)std::max<long long>(1, std::min<long long>((n + block0 - 1) / block0, (long long)bulk_ctas * m->sm_count));
+    const unsigned grid_t = (unsigned)std::max<long long>(1, std::min<long long>((n + 31) / 32, (long long)tail_warps * m->sm_count));
+    OdlData Dl = D;
+    void* pb[] = {&Dl, &O0, &A0};
+    void* pt[] = {&Dl, &O2, &A2};
+    if (concurrent) {
+      ODL_CUDA(cudaEventRecord(m->ev_fork, s));
+      ODL_CUDA(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
+      if ((rc = launch(m, k_tail, grid_t, 32, smem_t, m->aux, pt))) return rc;      // first: takes its SM share
       ODL_CUDA(cudaEventRecord(m->ev_aux, m->aux));
-      OdlOpts O1 = O; O1.stiff_check = 1; O1.max_steps = std::min(cap1, O.max_steps);
-      OdlSweepArgs A1 = A;
-      A1.index = listA; A1.index_count = cnt(64); A1.counter = ctr(128);
-      A1.defer_list[0] = listC; A1.defer_count[0] = cnt(320);
-      A1.defer_list[1] = listC; A1.defer_count[1] = cnt(320);
-      if ((rc = go(s, m->k_sweep, O1, A1, 32u, tail_items))) return rc;
-      ODL_CUDA(cudaEventRecord(m->evp[1], s));
+      if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc;
+      ODL_CUDA(cudaEventRecord(m->evp[0], s));
       ODL_CUDA(cudaStreamWaitEvent(s, m->ev_aux, 0));
-      // what DOPRI5 could not finish within cap1 after all (rare): Radau5
-      OdlSweepArgs A3 = A;
-      A3.index = listC; A3.index_count = cnt(320); A3.counter = ctr(384);
-      A3.defer_list[0] = A3.defer_list[1] = nullptr; A3.defer_count[0] = A3.defer_count[1] = nullptr;
-      if ((rc = go(s, k_tail, O2, A3, 32u, std::max<long long>(32, tail_items / 4)))) return rc;
     } else {
-      ODL_CUDA(cudaEventRecord(m->evp[1], s));
-      OdlSweepArgs A2 = A;
-      A2.index = listB; A2.index_count = cnt(192); A2.counter = ctr(256);
-      A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
-      if ((rc = go(s, k_tail, O2, A2, 32u, O2.lanes > 0 ? n * (32 / O2.lanes) : n))) return rc;      // alone on the GPU: as many CTAs as fit
+      if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc;
+      ODL_CUDA(cudaEventRecord(m->evp[0], s));
+      if ((rc = launch(m, k_tail, grid_t, 32, smem_t, s, pt))) return rc;
     }
     m->n_pass = 3;
   }
   ODL_CUDA(cudaEventRecord(m->ev1, s));
   m->timed = true;
-  return st.finish();
+  if ((rc = st.finish())) return rc;
+  if (solver == ODL_SOLVER_AUTO && mem == ODL_MEM_HOST) {
+    int gave_up = 0;
+    ODL_CUDA(cudaMemcpy(&gave_up, cnt(320), sizeof(int), cudaMemcpyDeviceToHost));
+    if (gave_up) return fail(ODL_ECUDA, "odl_sweep: the stiff pass gave up waiting for the DOPRI5 pass (watchdog); results are incomplete");
+  }
+  return 0;
 }
 
 extern "C" int odl_trajectory(odl_model* m, const odl_solver_opts* so, long long n, const double* theta,
@@ -705,15 +759,24 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   return st.finish();
 }
 
+/* development aid: the first `count` ints of the counter block of the last sweep (see odl_sweep) */
+extern "C" int odl_debug_counters(odl_model* m, int* out, int count) {
+  if (!m || !out || !m->on_gpu) return fail(ODL_EINVAL, "odl_debug_counters: bad argument");
+  if (count < 0 || count > 1024) return fail(ODL_EINVAL, "odl_debug_counters: count out of range");
+  ODL_CUDA(cudaSetDevice(m->device));
+  ODL_CUDA(cudaMemcpy(out, m->counter.p, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" int odl_model_last_pass_ms(odl_model* m, float* ms3) {
   if (!m || !ms3) return fail(ODL_EINVAL, "null argument");
   if (!m->on_gpu || !m->timed) return fail(ODL_EINVAL, "no kernel has been launched on this model yet");
   ODL_CUDA(cudaEventSynchronize(m->ev1));
   ms3[0] = ms3[1] = ms3[2] = 0.f;
   if (m->n_pass == 3) {
-    ODL_CUDA(cudaEventElapsedTime(&ms3[0], m->ev0, m->evp[0]));
-    ODL_CUDA(cudaEventElapsedTime(&ms3[1], m->evp[0], m->evp[1]));
-    ODL_CUDA(cudaEventElapsedTime(&ms3[2], m->evp[1], m->ev1));
+    ODL_CUDA(cudaEventElapsedTime(&ms3[0], m->ev0, m->evp[1]));
+    ODL_CUDA(cudaEventElapsedTime(&ms3[1], m->evp[1], m->evp[0]));
+    ODL_CUDA(cudaEventElapsedTime(&ms3[2], m->evp[0], m->ev1));
   } else {
     ODL_CUDA(cudaEventElapsedTime(&ms3[0], m->ev0, m->ev1));
   }

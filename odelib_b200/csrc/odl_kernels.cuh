@@ -202,6 +202,16 @@ __device__ __forceinline__ double odl_rcp_approx(double x) {
 __device__ __forceinline__ double odl_rcp_approx(double x) { return 1.0 / x; }
 #endif
 __device__ __forceinline__ float odl_err_ratio(double e, double sk) { return (float)(e * odl_rcp_approx(sk)); }
+// fp32 square root for step-size heuristics: one MUFU instead of the IEEE sequence (8 instructions)
+#ifndef ODL_HOST_HARNESS
+__device__ __forceinline__ float odl_sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+#else
+__device__ __forceinline__ float odl_sqrt_approx(float x) { return sqrtf(x); }
+#endif
 
 // Butcher tableau of DOPRI5 (Hairer/Norsett/Wanner, dopri5.f) in constant memory: DFMA takes c[bank][offset]
 // operands directly, whereas literals are re-materialised with two UMOVs per use (13 % of the issued
@@ -337,7 +347,7 @@ ODL_UNROLL
     ysum += fabs(yn[i]);
   }
   const bool finite_all = odl_finite(ysum);
-  const float err = sqrtf((float)errsq * (1.0f / ODL_N));
+  const float err = odl_sqrt_approx((float)errsq * (1.0f / ODL_N));
   // PI controller (Hairer, beta = 0.04): h_new = h * 0.9 * facold^beta / err^(0.2 - 0.75 beta), one SFU exp2
   const float lg_err = __log2f(err);
   if (err <= 1.0f && finite_all) {
@@ -1021,7 +1031,7 @@ ODL_UNROLL
 #ifndef ODL_BDF_NEWTON_TOL
 #define ODL_BDF_NEWTON_TOL 0.03f
 #endif
-__constant__ double ODL_BDF_GAMMA[ODL_BDF_MAXORD + 1] = {0.0, 1.0, 1.5, 11.0 / 6.0, 25.0 / 12.0, 137.0 / 60.0};
+__constant__ double ODL_BDF_GAMMA[8] = {0.0, 1.0, 1.5, 11.0 / 6.0, 25.0 / 12.0, 137.0 / 60.0, 0.0, 0.0};   // [(q+2-k) & 7]
 // alpha_q = (1 - kappa_q) gamma_q, kappa = (0, -0.1850, -1/9, -0.0823, -0.0415, 0)
 __constant__ double ODL_BDF_RALPHA[ODL_BDF_MAXORD + 1] = {
     0.0, 1.0 / (1.1850 * 1.0), 1.0 / ((1.0 + 1.0 / 9.0) * 1.5), 1.0 / (1.0823 * (11.0 / 6.0)),
@@ -1096,7 +1106,7 @@ __device__ __forceinline__ float odl_bdf_rms(const double (&v)[ODL_N], const dou
   double s = 0.0;
 ODL_UNROLL
   for (int c = 0; c < ODL_N; ++c) { const double a = v[c] * rs[c]; s += a * a; }
-  return sqrtf((float)s * (1.0f / ODL_N));
+  return odl_sqrt_approx((float)s * (1.0f / ODL_N));
 }
 
 template <class Sink>
@@ -1147,13 +1157,14 @@ ODL_UNROLL
   double yp[ODL_N], psi[ODL_N], rs[ODL_N];
 ODL_UNROLL
   for (int c = 0; c < ODL_N; ++c) { yp[c] = st.y[c]; psi[c] = 0.0; }
+  // rows k > q+1 of E are zero (change_D clears them, the update below never touches them): no predicate needed,
+  // and the gamma of a dead row may be anything finite
 #pragma unroll
-  for (int k = 2; k < ODL_BDF_MAXORD + 2; ++k)
-    if (k <= q + 1) {
-      const double g = ODL_BDF_GAMMA[q + 2 - k];
+  for (int k = 2; k < ODL_BDF_MAXORD + 2; ++k) {
+    const double g = ODL_BDF_GAMMA[(q + 2 - k) & 7];
 ODL_UNROLL
-      for (int c = 0; c < ODL_N; ++c) { yp[c] += ax.E[k][c]; psi[c] += g * ax.E[k][c]; }
-    }
+    for (int c = 0; c < ODL_N; ++c) { yp[c] += ax.E[k][c]; psi[c] += g * ax.E[k][c]; }
+  }
 ODL_UNROLL
   for (int c = 0; c < ODL_N; ++c) { psi[c] *= ralpha; rs[c] = odl_rcp_approx(O.atol + O.rtol * fabs(yp[c])); }
 
@@ -1181,10 +1192,10 @@ ODL_UNROLL
     ++n_iter;
     double f[ODL_N];
     odl_rhs(yk, tn, p, f);
-    bool fin = true;
+    double fsum = 0.0;
 ODL_UNROLL
-    for (int c = 0; c < ODL_N; ++c) { fin = fin && odl_finite(f[c]); f[c] = cc * f[c] - psi[c] - d[c]; }
-    if (!fin) break;
+    for (int c = 0; c < ODL_N; ++c) { fsum += fabs(f[c]); f[c] = cc * f[c] - psi[c] - d[c]; }
+    if (!odl_finite(fsum)) break;
     odl_lu_solve(ax.lu, f);
     const float dn = odl_bdf_rms(f, rs);
     if (!(dn == dn)) break;
@@ -1215,9 +1226,10 @@ ODL_UNROLL
     return;
   }
   const float safety = 0.9f * (2 * ODL_BDF_NEWTON + 1) / (float)(2 * ODL_BDF_NEWTON + n_iter);
-  bool finite_all = true;
+  double ysum = 0.0;
 ODL_UNROLL
-  for (int c = 0; c < ODL_N; ++c) { finite_all = finite_all && odl_finite(yk[c]); rs[c] = odl_rcp_approx(O.atol + O.rtol * fabs(yk[c])); }
+  for (int c = 0; c < ODL_N; ++c) { ysum += fabs(yk[c]); rs[c] = odl_rcp_approx(O.atol + O.rtol * fabs(yk[c])); }
+  const bool finite_all = odl_finite(ysum);
   const float err = ODL_BDF_ERRC[q] * odl_bdf_rms(d, rs);
   if (!(err <= 1.0f) || !finite_all) {
 #ifdef ODL_HOST_HARNESS
@@ -1328,6 +1340,108 @@ __device__ __forceinline__ long long odl_fetch(unsigned long long* counter, bool
   return (long long)(base + __popc(m & ((1u << lane) - 1)));
 }
 
+// loads that must observe what other kernels / CTAs published with atomics + __threadfence (L2, in program order)
+__device__ __forceinline__ int odl_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long odl_ld_acquire(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cost ordering of a sweep (see OdlOrderArgs): histogram of the keys, start offsets, scatter of the row numbers.
+// The order inside a bin is whatever the atomics give; it only decides when a system runs, never its result.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int odl_order_bin(const OdlData& D, const double* theta_row) {
+  double p[ODL_P], y[ODL_N];
+ODL_UNROLL
+  for (int q = 0; q < ODL_P; ++q) p[q] = theta_row[q];
+ODL_UNROLL
+  for (int i = 0; i < ODL_N; ++i) {
+    double v = D.y0[i];
+#if ODL_Y0P
+    const int src = D.y0_from_param[i];
+ODL_UNROLL
+    for (int q = 0; q < ODL_P; ++q) if (src == q) v = p[q];
+#endif
+    y[i] = v;
+  }
+  double J[ODL_N][ODL_N];
+  odl_jac(y, D.t0, p, J);
+  double nrm = 0.0;
+ODL_UNROLL
+  for (int i = 0; i < ODL_N; ++i) {
+    double r = 0.0;
+ODL_UNROLL
+    for (int j = 0; j < ODL_N; ++j) r += fabs(J[i][j]);
+    nrm = fmax(nrm, r);
+  }
+  const float key = (float)(nrm * (D.slot_t[D.n_slot - 1] - D.t0));
+  if (!(key == key) || key > 3.0e38f) return ODL_ORDER_BINS - 1;                 // not finite: fail fast, first
+  if (!(key > 0.f)) return 0;
+  const int b = (int)floorf((__log2f(key) + 32.0f) * 4.0f);                      // quarter octaves over 2^-32 .. 2^32
+  return b < 0 ? 0 : (b > ODL_ORDER_BINS - 1 ? ODL_ORDER_BINS - 1 : b);
+}
+extern "C" __global__ void __launch_bounds__(256)
+odl_order_key_kernel(const OdlData D, const OdlOrderArgs A) {
+  __shared__ int h[ODL_ORDER_BINS];
+  for (int i = threadIdx.x; i < ODL_ORDER_BINS; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = odl_order_bin(D, A.theta + i * ODL_P);
+    A.bins[i] = (unsigned char)b;
+    atomicAdd(&h[b], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ODL_ORDER_BINS; i += blockDim.x) if (h[i]) atomicAdd(&A.hist[i], h[i]);
+}
+extern "C" __global__ void __launch_bounds__(ODL_ORDER_BINS)
+odl_order_scan_kernel(const OdlOrderArgs A) {
+  // exclusive prefix over the bins taken from the highest down: cursor[b] = number of rows in bins above b
+  __shared__ int s[ODL_ORDER_BINS];
+  const int b = threadIdx.x;
+  s[b] = A.hist[ODL_ORDER_BINS - 1 - b];
+  __syncthreads();
+  for (int off = 1; off < ODL_ORDER_BINS; off <<= 1) {
+    const int v = (b >= off) ? s[b - off] : 0;
+    __syncthreads();
+    s[b] += v;
+    __syncthreads();
+  }
+  A.cursor[ODL_ORDER_BINS - 1 - b] = s[b] - A.hist[ODL_ORDER_BINS - 1 - b];
+}
+extern "C" __global__ void __launch_bounds__(256)
+odl_order_scatter_kernel(const OdlOrderArgs A) {
+  // one tile of rows per CTA: rank inside the tile from shared atomics, one global reservation per (tile, bin)
+  __shared__ int h[ODL_ORDER_BINS];
+  __shared__ int base[ODL_ORDER_BINS];
+  const long long tile = (long long)blockDim.x * 8;
+  for (long long t0 = (long long)blockIdx.x * tile; t0 < A.n; t0 += (long long)gridDim.x * tile) {
+    for (int i = threadIdx.x; i < ODL_ORDER_BINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    int myb[8], myr[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long i = t0 + (long long)k * blockDim.x + threadIdx.x;
+      myb[k] = -1; myr[k] = 0;
+      if (i < A.n) { myb[k] = A.bins[i]; myr[k] = atomicAdd(&h[myb[k]], 1); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ODL_ORDER_BINS; i += blockDim.x) base[i] = h[i] ? atomicAdd(&A.cursor[i], h[i]) : 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long i = t0 + (long long)k * blockDim.x + threadIdx.x;
+      if (myb[k] >= 0) A.index[base[myb[k]] + myr[k]] = (int)i;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Forward sweep: Framework.py:41-48 (_Fit_worker) for n parameter sets
 // ------------------------------------------------------------------------------------------------
@@ -1353,6 +1467,13 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
   // that the few long systems are spread over more warps -- a warp pays for the union of its lanes' branches.
   const bool lane_on = (O.lanes <= 0) || (lane < O.lanes);
   bool want = lane_on;
+  // consumer of a feed another kernel is still writing (the stiff pass beside the bulk pass): a lane takes a ticket
+  // and waits, `pending`, until that entry of index[] has landed or the producer is known to have finished short of it
+  const bool consumer = A.feed_ticket != nullptr;
+  bool pending = false;
+  long long ticket = -1;
+  unsigned int idle_spins = 0;
+  if (A.prod_started && !consumer && lane == 0) atomicAdd(A.prod_started, 1);     // before this warp's first fetch
   for (;;) {
     // ---- (A) finished lanes: cooperative score, write-back ----
     const bool fin = active && done;
@@ -1386,7 +1507,7 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
     }
     if (fin) { active = false; done = false; want = lane_on; }
     // ---- (B) refill ----
-    {
+    if (!consumer) {
       const long long got = odl_fetch(A.counter, want, lane);
       if (want) {
         want = false;
@@ -1402,8 +1523,49 @@ ODL_UNROLL
           done = (st.slot >= D.n_slot);
         }
       }
+      if (!__any_sync(ODL_FULL, active)) break;
+    } else {
+      const long long got = odl_fetch(A.feed_ticket, want, lane);
+      if (want) { want = false; pending = true; ticket = got; }
+      if (__any_sync(ODL_FULL, pending)) {
+        // producer state, read in this order: work counter dry -> warps entered -> warps left -> entries published.
+        // A warp that enters after the counter ran dry gets no work, so "dry and left == entered" is final.
+        int landed = 0, complete = 0;
+        if (lane == 0) {
+          const bool dry = odl_ld_acquire(A.prod_counter) >= (unsigned long long)A.prod_n;
+          const int entered = odl_ld_acquire(A.prod_started);
+          const int left = odl_ld_acquire(A.prod_exited);
+          complete = (dry && entered == left) ? 1 : 0;
+          landed = odl_ld_acquire(A.index_count);
+        }
+        landed = __shfl_sync(ODL_FULL, landed, 0);
+        complete = __shfl_sync(ODL_FULL, complete, 0);
+        if (pending) {
+          if (ticket < (long long)landed) {
+            int r;
+            do { r = odl_ld_acquire(A.index + ticket); } while (r < 0);       // written right after the count moved
+            sys = ticket; row = r;
+ODL_UNROLL
+            for (int q = 0; q < ODL_P; ++q) p[q] = A.theta[row * ODL_P + q];
+            odl_init_system(st, p, D, O, nullptr);
+            ax.reset();
+            odl_emit_initial_slots(st, S, D, sink);
+            active = true; pending = false;
+            done = (st.slot >= D.n_slot);
+          } else if (complete) {
+            pending = false;                                                   // the feed ended before this ticket
+          }
+        }
+      }
+      if (!__any_sync(ODL_FULL, active || pending)) break;
+      if (!__any_sync(ODL_FULL, active)) {                                      // nothing to integrate yet
+        // watchdog: a producer that never reports completion (a bug, a killed launch) must not hang the device
+        if (++idle_spins > (unsigned int)O.watchdog_spins) { if (lane == 0 && A.watchdog) atomicAdd(A.watchdog, 1); break; }
+        __nanosleep(400);
+        continue;
+      }
+      idle_spins = 0;
     }
-    if (!__any_sync(ODL_FULL, active)) break;
     // ---- (C) ODL_INNER step attempts between visits of (A)/(B): the ballots, shuffles and the refill logic cost
     //      about a fifth of a step; a finished lane idles for at most ODL_INNER-1 attempts (systems take ~90) ----
 #pragma unroll 1
@@ -1414,6 +1576,10 @@ ODL_UNROLL
       }
       if (!__any_sync(ODL_FULL, active && !done)) break;
     }
+  }
+  if (A.prod_exited && !consumer) {
+    __threadfence();                                                           // this warp's deferrals first
+    if (lane == 0) atomicAdd(A.prod_exited, 1);
   }
 }
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)

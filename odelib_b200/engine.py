@@ -142,7 +142,7 @@ class DeviceModel:
     # -- helpers -----------------------------------------------------------------------------------
     @staticmethod
     def _solver_opts(rtol, atol, max_steps, solver, stiff_check, h0=0.0, hmax=0.0, stiff_min_steps=0, pass_caps=(0, 0),
-                     tail_solver=None, early_check_steps=0, tail_lanes=0):
+                     tail_solver=None, early_check_steps=0, tail_lanes=0, tail_warps=0, auto_flags=0):
         so = _capi.SolverOpts()
         so.rtol = SCIPY_TOL if rtol is None else float(rtol)
         so.atol = SCIPY_TOL if atol is None else float(atol)
@@ -154,7 +154,8 @@ class DeviceModel:
         so.tail_lanes = int(tail_lanes)
         so.stiff_check = 1 if stiff_check else 0
         so.stiff_min_steps = int(stiff_min_steps)
-        so.pass_cap0, so.pass_cap1 = int(pass_caps[0]), int(pass_caps[1])
+        so.pass_cap0 = int(pass_caps[0]) if isinstance(pass_caps, (tuple, list)) else int(pass_caps)
+        so.tail_warps, so.auto_flags = int(tail_warps), int(auto_flags)
         return so
 
     @staticmethod
@@ -165,12 +166,13 @@ class DeviceModel:
     # -- forward sweep: _Fit_worker (Framework.py:41-48) -------------------------------------------
     def sweep(self, theta, rtol=None, atol=None, max_steps=500000, solver="dopri5", stiff_check=False,
               return_pred=False, out=None, stiff_min_steps=0, pass_caps=(0, 0), tail_solver=None, early_check_steps=0,
-              tail_lanes=0):
+              tail_lanes=0, tail_warps=0, auto_flags=0):
         """theta [n, P] (numpy -> host path, torch cuda tensor -> device path).
 
         Returns dict(chi, r2, status, nsteps[, pred]) of the same kind as the input."""
         so = self._solver_opts(rtol, atol, max_steps, solver, stiff_check, stiff_min_steps=stiff_min_steps,
-                               pass_caps=pass_caps, tail_solver=tail_solver, early_check_steps=early_check_steps, tail_lanes=tail_lanes)
+                               pass_caps=pass_caps, tail_solver=tail_solver, early_check_steps=early_check_steps, tail_lanes=tail_lanes,
+                               tail_warps=tail_warps, auto_flags=auto_flags)
         if _is_torch_cuda(theta):
             import torch
             th = theta.contiguous()

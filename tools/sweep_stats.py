@@ -14,15 +14,17 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 MODEL = sys.argv[2] if len(sys.argv) > 2 else "two_i"
 VARIANTS = sys.argv[3].split(",") if len(sys.argv) > 3 else [""]
 theta = torch.from_numpy(prior_draws(MODEL, n, seed=0)).cuda()
-MODES = (("auto_default", dict(solver="auto", max_steps=200000)),
-         ("auto_lanes16", dict(solver="auto", max_steps=200000, tail_lanes=16)),
-         ("auto_lanes8", dict(solver="auto", max_steps=200000, tail_lanes=8)),
-         ("auto_lanes4", dict(solver="auto", max_steps=200000, tail_lanes=4)),
-         ("auto_lanes2", dict(solver="auto", max_steps=200000, tail_lanes=2)),
-         ("auto_noearly", dict(solver="auto", max_steps=200000, early_check_steps=-1)),
-         ("auto_radau", dict(solver="auto", max_steps=200000, tail_solver="radau5", early_check_steps=-1)),
-         ("auto_384", dict(solver="auto", max_steps=200000, pass_caps=(384, 1))),
-         ("auto_640", dict(solver="auto", max_steps=200000, pass_caps=(640, 1))),
+K = dict(solver="auto", max_steps=200000)
+MODES = (("auto_default", dict(K)),
+         ("auto_noearly", dict(K, early_check_steps=-1)),
+         ("auto_early128", dict(K, early_check_steps=128)),
+         ("auto_unordered", dict(K, auto_flags=1)),
+         ("auto_concurrent", dict(K, auto_flags=2, early_check_steps=-1)),
+         ("auto_radau", dict(K, tail_solver="radau5", early_check_steps=-1)),
+         ("auto_384", dict(K, pass_caps=384)),
+         ("auto_448", dict(K, pass_caps=448)),
+         ("auto_640", dict(K, pass_caps=640)),
+         ("auto_768", dict(K, pass_caps=768)),
          ("dopri5_cap512", dict(solver="dopri5", max_steps=512)))
 res = {}
 for variant in VARIANTS:
