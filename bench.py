@@ -158,7 +158,9 @@ def workload_config(args, n_gpus):
                         f"infection model (4 states, 5 parameters) integrated to the 37 demo observations "
                         f"(19 grid times of t_steps={TSTEPS}) + chi/R^2 [BASELINE.json configs[1]]",
             "sets_per_gpu": args.sets, "sets_total": args.sets * n_gpus, "rtol": 1.49012e-8, "atol": 1.49012e-8,
-            "solver": "auto: dopri5(4) with dense output, <=512 attempted steps -> radau5 for the rest (~1.2 %)", "l2": "flushed between timed steps (256 MiB write)",
+            "solver": "auto: rows cost-ordered on the device (|J(y0)| key), dopri5(4) with dense output <=512 attempted "
+                      "steps (half-way projection check), then variable-order BDF for what is left (~2.5 %)",
+            "l2": "flushed between timed steps (256 MiB write)",
             "parallelism": f"shard{n_gpus}"}
 
 
@@ -216,7 +218,7 @@ def run_ours(args):
     peak_tflops, _ = engine.fp64_peak(local)
 
     # ---- device-resident sweep: `value` -------------------------------------------------------------
-    SW = dict(solver="auto", max_steps=500000)      # every system is solved: DOPRI5 bulk pass + Radau5 pass
+    SW = dict(solver="auto", max_steps=500000)      # every system is solved: ordering + DOPRI5 bulk pass + BDF pass
     for _ in range(max(args.warmup, 3)):
         dm.sweep(theta_dev, out=out, **SW)
     clocks = ClockSampler(local)
@@ -238,24 +240,31 @@ def run_ours(args):
     value = n * world * args.steps / t_total
     nsteps = out["nsteps"].to(torch.int64)
     status = out["status"]
-    flops_step = 6 * dm.rhs_flops + 71 * ns + 10                     # SURVEY.md §8d flop model
-    flops_launch = float(nsteps.sum().item()) * flops_step + n * (dm.n_slot * (30 + 12 * ns) + dm.n_obs * 8)
+    flops_step = 6 * dm.rhs_flops + 71 * ns + 10                     # SURVEY.md §8d flop model (DOPRI5)
+    flops_bdf_step = dm.rhs_flops + 2 * ns * ns + 37 * ns            # one Newton iteration; LU / change_D not counted
+    flops_solve = dm.n_slot * (30 + 12 * ns) + dm.n_obs * 8
     avg_ms = float(np.mean(ms))
-    achieved = flops_launch / (avg_ms * 1e-3) / 1e12
     bytes_launch = n * (P * 8 + 8 + 8 + 4 + 4)
     ok_frac = float((status == 0).float().mean().item())
     mean_steps = float(nsteps.double().mean().item())
-    # the bulk kernel on its own: one DOPRI5 pass capped at 512 attempted steps (what pass 0 of the sweep runs)
+    # the bulk kernel on its own: the DOPRI5 pass of the sweep (<= 512 attempted steps, half-way check at 256) in
+    # input order.  A solve depends on nothing but its own row, so this is also the exact set the sweep's DOPRI5 pass
+    # finishes; the rest was finished by the BDF pass.
     bulk_out = {k: torch.empty_like(v) for k, v in out.items()}
     for _ in range(2):
-        dm.sweep(theta_dev, out=bulk_out, solver="dopri5", max_steps=512, stiff_check=True)
+        dm.sweep(theta_dev, out=bulk_out, solver="dopri5", max_steps=512, stiff_check=True, early_check_steps=256)
     torch.cuda.synchronize()
     bulk_ms = dm.last_kernel_ms()
     bulk_ok = bulk_out["status"] == 0
     bulk_flops = float(bulk_out["nsteps"].to(torch.int64)[bulk_ok].sum().item()) * flops_step + \
-        float(bulk_ok.sum().item()) * (dm.n_slot * (30 + 12 * ns) + dm.n_obs * 8)
-    bulk = {"kernel": "odl_sweep_kernel (pass 0: DOPRI5, <= 512 attempted steps)", "ms": bulk_ms,
-            "finished_fraction": float(bulk_ok.float().mean().item()),
+        float(bulk_ok.sum().item()) * flops_solve
+    # algorithmic flops of the whole sweep: DOPRI5-finished systems at the DOPRI5 rate, BDF-finished ones at the
+    # (lower) BDF rate; the DOPRI5 attempts the deferred systems burned before leaving are not counted
+    stiff_steps = float(nsteps[~bulk_ok].sum().item())
+    flops_launch = bulk_flops + stiff_steps * flops_bdf_step + float((~bulk_ok).sum().item()) * flops_solve
+    achieved = flops_launch / (avg_ms * 1e-3) / 1e12
+    bulk = {"kernel": "odl_sweep_kernel (DOPRI5 pass: <= 512 attempted steps, projection check at 256), input order",
+            "ms": bulk_ms, "finished_fraction": float(bulk_ok.float().mean().item()),
             "achieved_TFLOPs": bulk_flops / (bulk_ms * 1e-3) / 1e12,
             "frac_of_fp64_peak": bulk_flops / (bulk_ms * 1e-3) / 1e12 / peak_tflops}
 
@@ -268,7 +277,7 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        model.sweep(th_np, out=host_out)          # H2D of theta, 3 kernel passes, D2H of chi/r2/status/nsteps, sync
+        model.sweep(th_np, out=host_out)          # H2D of theta, 5 kernels, D2H of chi/r2/status/nsteps, sync
     torch.cuda.synchronize()
     e2e_t = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": n * world * args.steps / e2e_t, "unit": "solves/s", "h2d_bytes_per_step": n * P * 8,
@@ -334,6 +343,7 @@ def run_ours(args):
                "sample": f"first {ncpu} parameter sets of the same sweep, scipy odeint (LSODA, default tol) + numpy "
                          f"masked chi in {cores} forked processes, {dt:.1f} s"}
 
+    traffic = ncu_traffic()
     if rank == 0:
         line = {
             "metric": "ode_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
@@ -342,17 +352,17 @@ def run_ours(args):
             "config": workload_config(args, world),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / peak_tflops,
-                         "traffic": (42734336 + 4911104) if n == (1 << 20) else None,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the bulk launch (odl_sweep_kernel, "
-                                         "1,048,576 sets), ncu --set full capture profiles/r1c_sweep_bulk_cap512_ncu.txt; "
-                                         "algorithmic bytes 40 MB in + 24 MB out (results still in L2 at kernel end)",
-                         "kernel": "odl_sweep (2 launches: odl_sweep_kernel + odl_sweep_radau5_kernel)", "avg_launch_ms": avg_ms,
+                         "traffic": traffic.get("bytes") if n == (1 << 20) else None,
+                         "traffic_note": traffic.get("note"),
+                         "kernel": "odl_sweep (5 launches: 3 ordering kernels + odl_sweep_kernel + odl_sweep_bdf_kernel)",
+                         "avg_launch_ms": avg_ms,
                          "peak_source": "measured live: odl_fp64_peak DFMA chains (MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_per_launch": flops_launch, "flops_per_step_attempt": flops_step,
                          "mean_steps_per_solve": mean_steps,
-                         "flop_model": "per attempted step 6*F_rhs+71n+10 (F_rhs=11, n=4 -> 360), + 19*(30+12n) + 37*8 per solve; "
-                                       "steps of the Radau5-finished systems (~1 %) are counted at the DOPRI5 rate (conservative)",
-                         "passes_ms": {"dopri5_bulk": pass_ms[0], "dopri5_deferred": pass_ms[1], "radau5_stiff": pass_ms[2]},
+                         "flop_model": "per attempted DOPRI5 step 6*F_rhs+71n+10 (F_rhs=11, n=4 -> 360), + 19*(30+12n) + 37*8 per "
+                                       "solve; steps of the BDF-finished systems at F_rhs+2n^2+37n (= 191) per attempt; the "
+                                       "DOPRI5 attempts of deferred systems, ordering, LU and change_D work are not counted",
+                         "passes_ms": {"ordering": pass_ms[0], "dopri5_bulk": pass_ms[1], "bdf_stiff": pass_ms[2]},
                          "bulk_kernel": bulk,
                          "hbm": {"algorithmic_bytes_per_launch": bytes_launch,
                                  "achieved_GBps": bytes_launch / (avg_ms * 1e-3) / 1e9, "peak_GBps": hbm_peak(),
@@ -363,6 +373,14 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """DRAM bytes of the dominant launch from the committed ncu capture (profiles/traffic.json), or {}."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:  # noqa: BLE001
+        return {}
 
 
 def hbm_peak():

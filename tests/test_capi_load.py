@@ -73,3 +73,20 @@ def test_philox_known_answers():
     zz, uu = engine.philox_streams(7, np.arange(4), 50, 5)
     assert zz.shape == (4, 50, 5) and uu.shape == (4, 50)
     assert 0 <= uu.min() and uu.max() < 1 and abs(zz.std() / 0.05 - 1) < 0.1
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / field offsets of the option structs as gcc sees include/odelib_b200.h vs the ctypes mirror."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "odelib_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(odl_solver_opts), '
+                   'offsetof(odl_solver_opts, max_steps), offsetof(odl_solver_opts, tail_solver), '
+                   'offsetof(odl_solver_opts, auto_flags), sizeof(odl_mcmc_opts), offsetof(odl_mcmc_opts, seed), '
+                   'sizeof(odl_mcmc_io), sizeof(odl_build_opts)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    S, M = _capi.SolverOpts, _capi.McmcOpts
+    assert got == [ctypes.sizeof(S), S.max_steps.offset, S.tail_solver.offset, S.auto_flags.offset, ctypes.sizeof(M),
+                   M.seed.offset, ctypes.sizeof(_capi.McmcIO), ctypes.sizeof(_capi.BuildOpts)]

@@ -170,3 +170,28 @@ def test_auto_cohort_passes_solve_every_prior_draw(name):
     np.testing.assert_allclose(auto["chi"][ok], plain["chi"][ok], rtol=2e-4, atol=1e-6)
     same = auto["chi"][ok] == plain["chi"][ok]
     assert same.mean() > 0.95           # the bulk never left DOPRI5: bit-identical to the single launch
+
+
+def test_auto_sweep_is_independent_of_ordering_and_of_how_the_passes_are_scheduled():
+    """ODL_SOLVER_AUTO: cost ordering (device counting sort on |J(y0)|), the stiff pass after or beside the DOPRI5
+    pass -- scheduling only; every row's numbers are those of the stepper that finished it."""
+    from odelib_b200 import _capi
+    dm, _ = device_model("two_i")
+    theta = prior_draws("two_i", 40000, seed=11)
+    base = dm.sweep(theta, solver="auto", max_steps=200000)
+    assert np.all(base["status"] == 0)
+    for flags in (_capi.AUTO_UNORDERED, _capi.AUTO_CONCURRENT, _capi.AUTO_UNORDERED | _capi.AUTO_CONCURRENT):
+        other = dm.sweep(theta, solver="auto", max_steps=200000, auto_flags=flags)
+        for k in ("chi", "r2", "status", "nsteps"):
+            assert np.array_equal(base[k], other[k], equal_nan=True), (flags, k)
+    # the DOPRI5 pass alone (cap 512, projection check at 256) finishes a set of rows; the rest carries BDF numbers
+    dop = dm.sweep(theta, solver="dopri5", max_steps=512, stiff_check=True, early_check_steps=256)
+    fin = dop["status"] == 0
+    assert 0.95 < fin.mean() < 0.999
+    assert np.array_equal(base["chi"][fin], dop["chi"][fin]) and np.array_equal(base["nsteps"][fin], dop["nsteps"][fin])
+    bdf = dm.sweep(theta[~fin], solver="bdf", max_steps=200000)
+    assert np.array_equal(base["chi"][~fin], bdf["chi"], equal_nan=True)
+    # ragged sizes around the tile / warp boundaries of the ordering kernels
+    for n in (1, 31, 33, 2047, 2049):
+        a = dm.sweep(theta[:n], solver="auto", max_steps=200000)
+        assert np.array_equal(a["chi"], base["chi"][:n], equal_nan=True)
