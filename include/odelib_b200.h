@@ -93,6 +93,10 @@ typedef struct odl_mcmc_opts {
   int row_stride;      /* doubles per sample row, >= n_param+5 */
   double step_sd;      /* 0.05 (Framework.py:107) */
   unsigned long long seed;
+  int speculate;       /* lanes per chain that evaluate consecutive iterations at once along the all-rejected path
+                          (prefetching MH; a power of two <= 32).  The chain is the same for every value;
+                          0 = automatic (fills an otherwise latency-bound GPU), 1 = one proposal at a time */
+  int reserved;
 } odl_mcmc_opts;
 
 typedef struct odl_mcmc_io {

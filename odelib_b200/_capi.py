@@ -44,7 +44,7 @@ class McmcOpts(C.Structure):
     _fields_ = [("n_chain", C.c_int), ("chain_offset", C.c_int), ("nits", C.c_int), ("burnin", C.c_int),
                 ("it_begin", C.c_int), ("it_end", C.c_int), ("rng_mode", C.c_int), ("n_walk", C.c_int),
                 ("walk", C.POINTER(C.c_int)), ("pnum", C.c_int), ("row_stride", C.c_int), ("step_sd", C.c_double),
-                ("seed", C.c_ulonglong)]
+                ("seed", C.c_ulonglong), ("speculate", C.c_int), ("reserved", C.c_int)]
 
 
 class McmcIO(C.Structure):

@@ -110,7 +110,8 @@ struct OdlMcmcArgs {
   const double* u;               // [C][n_iter_total]           (rng_mode 1,2)
   const double* forced;          // [C][n_iter_total][n_param]    (rng_mode 2)
   int n_iter_total;              // nits-1
-  int pad_;
+  int spec;                      // lanes per chain (power of two <= 32): iterations evaluated at once along the
+                                 //   all-rejected path (prefetching MH); 1 = one proposal at a time
   double* samples;               // [C][n_keep][row_stride]: theta.., chi, rsquared, aic, iteration, acceptance_ratio
   double* summaries;             // [C][1+2*n_param]: count, mean[P], M2[P] of ln(theta) over kept rows
   double* trace_chinew;          // optional [C][n_iter_total]  chi of every proposal (parity tests)

@@ -738,15 +738,28 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
     A.walk[j] = mo->walk[j];
   }
   A.step_sd = mo->step_sd > 0 ? mo->step_sd : 0.05;
-  A.seed = mo->seed; A.n_iter_total = n_iter; A.pad_ = 0;
+  A.seed = mo->seed; A.n_iter_total = n_iter;
   OdlOpts O; fill_opts(O, so);
   OdlData D = m->data.d;
-  // few chains: spread them over the SMs with one warp per CTA; many chains: full CTAs
+  const bool warp_cta = solver == ODL_SOLVER_RADAU5 || solver == ODL_SOLVER_BDF;   // compiled for one warp per CTA
+  // Prefetching MH: K lanes per chain evaluate K iterations at once along the all-rejected path (odl_mcmc_body).
+  // The chain itself does not depend on K; K only fills a GPU that few chains would leave latency-bound.
+  // Automatic: the largest power of two that keeps chains*K within half of what the kernel can hold, at most 16.
+  int K = mo->speculate;
+  if (K <= 0) {
+    const long long resident = (long long)m->sm_count * (warp_cta ? 8 * 32 : 512);
+    K = 1;
+    while (K < 16 && (long long)C * K * 2 * 2 <= resident) K *= 2;
+  }
+  if (K > 32 || (K & (K - 1))) return fail(ODL_EINVAL, "odl_mcmc: speculate must be a power of two <= 32");
+  A.spec = K;
+  const long long threads = (long long)C * K;
+  // few threads: spread them over the SMs with one warp per CTA; many: full CTAs
   unsigned block = pick_block(D, m->block);
-  while (block > 32 && (long long)C < (long long)m->sm_count * block * 2) block /= 2;
-  if (solver == ODL_SOLVER_RADAU5 || solver == ODL_SOLVER_BDF) block = 32;   // compiled for one warp per CTA
+  while (block > 32 && threads < (long long)m->sm_count * block * 2) block /= 2;
+  if (warp_cta) block = 32;
   const size_t smem = smem_bytes(D, (int)block);
-  unsigned grid = (unsigned)((C + block - 1) / block);
+  unsigned grid = (unsigned)((threads + block - 1) / block);
   CUfunction f = (solver == ODL_SOLVER_DOPRI5) ? m->k_mcmc : (solver == ODL_SOLVER_ROS23 ? m->k_mcmc_ros :
                  (solver == ODL_SOLVER_RADAU5 ? m->k_mcmc_radau : (solver == ODL_SOLVER_BDF ? m->k_mcmc_bdf : m->k_mcmc_auto)));
   if (solver == ODL_SOLVER_AUTO) O.stiff_check = 1;

@@ -1671,6 +1671,14 @@ __device__ __forceinline__ double odl_mh_uniform(const OdlMcmcArgs& A, int chain
   return odl_u53(r.x, r.y);
 }
 
+// Prefetching Metropolis-Hastings.  A chain is sequential, and with few chains (BASELINE config 3: 4096) the GPU
+// is latency-bound: one warp per SM.  A.spec = K lanes per chain (a power of two, chosen by the host from the
+// chain count) evaluate the next K iterations AT ONCE along the all-rejected path: lane j proposes
+// theta_cur * exp(z_{it+j}) -- what iteration it+j proposes if iterations it..it+j-1 reject, which is what
+// happens ~74 % of the time at the demo's acceptance rate -- and the group then consumes iterations up to and
+// including the first acceptance, discarding the rest.  Proposals and uniforms are keyed by (chain, iteration),
+// so the chain is the SAME chain, decision by decision and bit by bit, for every K (K = 1 is the plain loop);
+// expected iterations consumed per round (1 - (1-a)^K)/a: 2.7 for K = 4, 3.5 for K = 8 at a = 0.26.
 template <int SOLVER>
 __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O, const OdlMcmcArgs& A) {
   extern __shared__ double odl_smem[];
@@ -1679,8 +1687,12 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
   const int lane = threadIdx.x & 31;
   double* my_stage = S.stage + (size_t)threadIdx.x * D.stage_stride;
   OdlStageSink sink; sink.stage = my_stage;
-  const int chain = blockIdx.x * blockDim.x + threadIdx.x;      // local chain index
-  const bool has_chain = chain < A.n_chain;
+  const int K = (A.spec >= 1 && A.spec <= 32) ? A.spec : 1;
+  const int sub = lane & (K - 1), gbase = lane & ~(K - 1);
+  const unsigned gbits = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
+  const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int chain = (int)(gthread / K);                         // local chain index
+  const bool has_chain = gthread / K < (long long)A.n_chain;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
 
   OdlStepper st;
@@ -1688,129 +1700,175 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
   ax.reset();
   double p[ODL_P];
   st.status = ODL_OK; st.nsteps = 0; st.slot = 0;
-  // it == it_begin-1 marks the a-priori solve of a fresh chain (Samplers.py:88-90)
+  // group state, replicated on the K lanes of a chain.  it == next iteration of Samplers.py:104 to decide;
+  // apriori marks the solve of the starting point of a fresh chain (Samplers.py:88-90)
   int it = A.it_begin;
   double chi_cur = nan, r2_cur = nan;
-  int accepts = 0, fails = 0;
+  int accepts = 0;
+  bool apriori = A.it_begin == 1;                               // warp-uniform: the branches below hold collectives
+  // per-lane accumulators over CONSUMED solves (speculative work that was discarded is not counted)
+  int fails = 0;
   long long steps = 0;
-  bool apriori = false;
   bool active = false, done = false, use_ros = false;
-  if (has_chain) {
-    if (A.it_begin == 1) {
-      apriori = true;
+  if (has_chain && !apriori) {
+    chi_cur = A.chain_state[(size_t)chain * 4 + 0];
+    r2_cur = A.chain_state[(size_t)chain * 4 + 1];
+    accepts = (int)A.chain_state[(size_t)chain * 4 + 2];
+  }
+  bool more = has_chain && (apriori || it < A.it_end);
+
+  while (__any_sync(ODL_FULL, more)) {
+    // ---- start a round: lane `sub` takes iteration it+sub ----
+    const bool valid = more && (apriori ? (sub == 0) : (it + sub < A.it_end));
+    active = false; done = false; use_ros = false;
+    if (valid) {
+      if (apriori) {
 ODL_UNROLL
-      for (int q = 0; q < ODL_P; ++q) p[q] = A.theta_cur[(size_t)chain * ODL_P + q];
-    } else {
-      chi_cur = A.chain_state[(size_t)chain * 4 + 0];
-      r2_cur = A.chain_state[(size_t)chain * 4 + 1];
-      accepts = (int)A.chain_state[(size_t)chain * 4 + 2];
-      odl_propose(p, A, chain, it);
-    }
-    if (apriori || it < A.it_end) {
+        for (int q = 0; q < ODL_P; ++q) p[q] = A.theta_cur[(size_t)chain * ODL_P + q];
+      } else {
+        odl_propose(p, A, chain, it + sub);
+      }
       odl_init_system(st, p, D, O, nullptr);
+      ax.reset();
       odl_emit_initial_slots(st, S, D, sink);
       active = true;
       done = (st.slot >= D.n_slot);
     }
-  }
-
-  // Lock-step per warp: every lane integrates its chain's current proposal; when the last lane of the warp is
-  // done, all lanes score / accept / record / propose TOGETHER.  (The first version finalised lane by lane as
-  // lanes finished: half of all issued instructions ran with one lane active -- profiles/r1_mcmc_ncu.txt.
-  // Proposals of neighbouring chains cost nearly the same number of steps, so waiting is cheap here, unlike in
-  // the heavy-tailed prior sweep.)
-  for (;;) {
-    if (active && !done) {
-      odl_attempt<SOLVER>(st, ax, p, S, D, O, sink, use_ros);
-      done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
-    }
-    if (__ballot_sync(ODL_FULL, active && !done)) continue;
-    if (!__any_sync(ODL_FULL, active)) break;
-    if (SOLVER == 2) {
-      // DOPRI5 gave up on a stiff proposal: redo this very solve with the Rosenbrock stepper
-      const bool restart = active && st.status == ODL_STIFF && !use_ros;
-      if (__ballot_sync(ODL_FULL, restart)) {
-        if (restart) {
-          steps += st.nsteps;
-          use_ros = true;
-          odl_init_system(st, p, D, O, nullptr);
-          ax.reset();
-          odl_emit_initial_slots(st, S, D, sink);
-          done = (st.slot >= D.n_slot);
-        }
-        continue;
+    // ---- integrate: the lanes of a warp step together until the last one is done.  (Finalising lane by lane as
+    //      lanes finish left half of all issued instructions with one lane active -- profiles/r1a_mcmc_*; proposals
+    //      of neighbouring chains, and the K proposals of one chain, cost nearly the same number of steps.) ----
+    for (;;) {
+      if (active && !done) {
+        odl_attempt<SOLVER>(st, ax, p, S, D, O, sink, use_ros);
+        done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
       }
+      if (__ballot_sync(ODL_FULL, active && !done)) continue;
+      if (SOLVER == 2) {
+        // DOPRI5 gave up on a stiff proposal: redo this very solve with the Rosenbrock stepper
+        const bool restart = active && st.status == ODL_STIFF && !use_ros;
+        if (__ballot_sync(ODL_FULL, restart)) {
+          if (restart) {
+            steps += st.nsteps;
+            use_ros = true;
+            odl_init_system(st, p, D, O, nullptr);
+            ax.reset();
+            odl_emit_initial_slots(st, S, D, sink);
+            done = (st.slot >= D.n_slot);
+          }
+          continue;
+        }
+      }
+      break;
     }
-    const bool fin = active;
+    // ---- score every lane's own solve ----
     double my_chi = nan, my_r2 = nan;
-    if (fin) {
+    if (valid) {
       double chi, ss; int nv;
       odl_score_self(S, D, my_stage, chi, ss, nv);
       if (st.status == ODL_OK) { my_chi = (nv > 0) ? chi : nan; my_r2 = 1.0 - ss / D.sstot; }   // nv == 0: np.ma.masked
     }
-    if (fin) {
-      steps += st.nsteps;
-      use_ros = false;
-      if (st.status != ODL_OK) ++fails;
+    if (apriori) {
+      // the starting point's own chi: no decision, no iteration consumed
+      chi_cur = __shfl_sync(ODL_FULL, my_chi, gbase);
+      r2_cur = __shfl_sync(ODL_FULL, my_r2, gbase);
+      if (valid) { steps += st.nsteps; if (st.status != ODL_OK) ++fails; }
+      apriori = false;
+    } else {
+      // ---- decisions along the all-rejected path: acc = exp(chi - chinew) > u (Samplers.py:124-127; NaN rejects) ----
+      bool acc = false;
+      if (valid) {
+        const double u = odl_mh_uniform(A, chain, it + sub);
+        acc = exp(chi_cur - my_chi) > u;
+      }
+      const unsigned gacc = (__ballot_sync(ODL_FULL, acc) >> gbase) & gbits;
+      const int nvalid = __popc((__ballot_sync(ODL_FULL, valid) >> gbase) & gbits);     // valid lanes are a prefix
+      const int jstar = gacc ? (__ffs(gacc) - 1) : -1;                                    // first acceptance
+      const int adv = (jstar >= 0) ? jstar + 1 : nvalid;                                  // iterations consumed
+      const bool consumed = valid && sub < adv;
+      const bool is_acc = consumed && sub == jstar;
       double* cur = A.theta_cur + (size_t)chain * ODL_P;
-      if (apriori) {
-        apriori = false;
-        chi_cur = my_chi; r2_cur = my_r2;
-      } else {
-        const double u = odl_mh_uniform(A, chain, it);
-        const double acc = exp(chi_cur - my_chi);                // Samplers.py:124-125
-        const bool accept = acc > u;                             // :127  (NaN compares false => reject)
-        if (accept) {
-          chi_cur = my_chi; r2_cur = my_r2; ++accepts;
+      // the accepted proposal, on every lane of the group (for the summaries; lane jstar holds it in p)
+      double pacc[ODL_P];
+      const int src = gbase + (jstar >= 0 ? jstar : 0);
+ODL_UNROLL
+      for (int q = 0; q < ODL_P; ++q) pacc[q] = __shfl_sync(ODL_FULL, p[q], src);
+      const double chi_acc = __shfl_sync(ODL_FULL, my_chi, src), r2_acc = __shfl_sync(ODL_FULL, my_r2, src);
+      if (consumed) {
+        steps += st.nsteps;
+        if (st.status != ODL_OK) ++fails;
+        const int iter = it + sub;
+        const long long k = (long long)chain * A.n_iter_total + (iter - 1);
+        if (A.trace_chinew) A.trace_chinew[k] = my_chi;
+        if (A.trace_accept) A.trace_accept[k] = is_acc ? 1 : 0;
+        if (iter > A.burnin) {                                   // Samplers.py:147
+          const int rowi = iter - A.burnin - 1;
+          if (A.samples && rowi < A.n_keep) {
+            double* row = A.samples + ((size_t)chain * A.n_keep + rowi) * A.row_stride;
+            const double c = is_acc ? my_chi : chi_cur;
+ODL_UNROLL
+            for (int q = 0; q < ODL_P; ++q) row[q] = is_acc ? p[q] : cur[q];
+            row[ODL_P + 0] = c;
+            row[ODL_P + 1] = is_acc ? my_r2 : r2_cur;
+            row[ODL_P + 2] = 2.0 * c + 2.0 * (double)A.pnum;      // stats.py:46
+            row[ODL_P + 3] = (double)iter;
+            row[ODL_P + 4] = (double)(accepts + (is_acc ? 1 : 0)) / (double)iter;   // Samplers.py:153
+          }
+        }
+      }
+      // Welford over ln(theta) of the kept rows for R-hat: sequential in the iteration (the same recurrence, in the
+      // same order, whatever K is), by the group's first lane
+      if (A.summaries && has_chain && sub == 0 && it + adv - 1 > A.burnin) {
+        double* sm = A.summaries + (size_t)chain * (1 + 2 * ODL_P);
+        double cnt = sm[0];
+        double mean[ODL_P], m2[ODL_P], xr[ODL_P], xa[ODL_P];
+ODL_UNROLL
+        for (int q = 0; q < ODL_P; ++q) {
+          mean[q] = sm[1 + q]; m2[q] = sm[1 + ODL_P + q];
+          xr[q] = (jstar == 0) ? 0.0 : log(cur[q]);              // jstar == 0: the only consumed row is the accepted one
+          xa[q] = (jstar >= 0) ? log(pacc[q]) : 0.0;
+        }
+        for (int i = 0; i < adv; ++i) {
+          if (it + i <= A.burnin) continue;
+          cnt += 1.0;
+ODL_UNROLL
+          for (int q = 0; q < ODL_P; ++q) {
+            const double x = (i == jstar) ? xa[q] : xr[q];
+            const double dlt = x - mean[q];
+            mean[q] += dlt / cnt;
+            m2[q] += dlt * (x - mean[q]);
+          }
+        }
+        sm[0] = cnt;
+ODL_UNROLL
+        for (int q = 0; q < ODL_P; ++q) { sm[1 + q] = mean[q]; sm[1 + ODL_P + q] = m2[q]; }
+      }
+      __syncwarp();                                              // rows above read cur[] before it changes
+      if (jstar >= 0) {
+        chi_cur = chi_acc; r2_cur = r2_acc; ++accepts;
+        if (is_acc) {
 ODL_UNROLL
           for (int q = 0; q < ODL_P; ++q) cur[q] = p[q];
         }
-        const long long k = (long long)chain * A.n_iter_total + (it - 1);
-        if (A.trace_chinew) A.trace_chinew[k] = my_chi;
-        if (A.trace_accept) A.trace_accept[k] = accept ? 1 : 0;
-        if (it > A.burnin) {                                     // :147
-          const int rowi = it - A.burnin - 1;
-          if (A.samples && rowi < A.n_keep) {
-            double* row = A.samples + ((size_t)chain * A.n_keep + rowi) * A.row_stride;
-ODL_UNROLL
-            for (int q = 0; q < ODL_P; ++q) row[q] = cur[q];
-            row[ODL_P + 0] = chi_cur;
-            row[ODL_P + 1] = r2_cur;
-            row[ODL_P + 2] = 2.0 * chi_cur + 2.0 * (double)A.pnum;   // stats.py:46
-            row[ODL_P + 3] = (double)it;
-            row[ODL_P + 4] = (double)accepts / (double)it;            // Samplers.py:153
-          }
-          if (A.summaries) {                                     // Welford over ln(theta) for R-hat
-            double* sm = A.summaries + (size_t)chain * (1 + 2 * ODL_P);
-            const double cnt = sm[0] + 1.0;
-            sm[0] = cnt;
-ODL_UNROLL
-            for (int q = 0; q < ODL_P; ++q) {
-              const double x = log(cur[q]);
-              const double dlt = x - sm[1 + q];
-              const double mean = sm[1 + q] + dlt / cnt;
-              sm[1 + q] = mean;
-              sm[1 + ODL_P + q] += dlt * (x - mean);
-            }
-          }
-        }
-        ++it;
       }
-      done = false;
-      if (it < A.it_end) {
-        odl_propose(p, A, chain, it);
-        odl_init_system(st, p, D, O, nullptr);
-        ax.reset();
-        odl_emit_initial_slots(st, S, D, sink);
-        done = (st.slot >= D.n_slot);
-      } else {
-        active = false;
-        A.chain_state[(size_t)chain * 4 + 0] = chi_cur;
-        A.chain_state[(size_t)chain * 4 + 1] = r2_cur;
-        A.chain_state[(size_t)chain * 4 + 2] = (double)accepts;
-        if (A.fail_count) A.fail_count[chain] += fails;
-        if (A.step_count) A.step_count[chain] += steps;
-      }
+      it += adv;
+      __syncwarp();                                              // the next round's proposals read cur[]
+    }
+    more = has_chain && it < A.it_end;
+  }
+  // ---- chain state for the next segment, counters ----
+  // sums over the K lanes of the group (all 32 lanes take part in the shuffles)
+  for (int m = K >> 1; m > 0; m >>= 1) {
+    fails += __shfl_xor_sync(ODL_FULL, fails, m);
+    const int lo = __shfl_xor_sync(ODL_FULL, (int)(steps & 0xffffffffLL), m), hi = __shfl_xor_sync(ODL_FULL, (int)(steps >> 32), m);
+    steps += ((long long)hi << 32) | (unsigned int)lo;
+  }
+  if (has_chain) {
+    if (sub == 0) {
+      A.chain_state[(size_t)chain * 4 + 0] = chi_cur;
+      A.chain_state[(size_t)chain * 4 + 1] = r2_cur;
+      A.chain_state[(size_t)chain * 4 + 2] = (double)accepts;
+      if (A.fail_count) A.fail_count[chain] += fails;
+      if (A.step_count) A.step_count[chain] += steps;
     }
   }
 }

@@ -220,7 +220,7 @@ class DeviceModel:
     # -- Metropolis-Hastings: Samplers.py:53-174 for many chains -----------------------------------
     def mcmc(self, theta0, nits=1000, burnin=None, walk=None, pnum=None, rng_mode="philox", seed=0, chain_offset=0,
              z=None, u=None, forced=None, rtol=None, atol=None, max_steps=500000, solver="dopri5", step_sd=0.05,
-             trace=False, keep_samples=True, summaries=True, segments=1, device_buffers=False):
+             trace=False, keep_samples=True, summaries=True, segments=1, device_buffers=False, speculate=0):
         """Run len(theta0) independent chains.  Returns dict with numpy arrays (or torch tensors when
         device_buffers=True): theta (final points), samples [C, nits-1-burnin, P+5], summaries
         [C, 1+2P], chain_state [C,4], and with trace=True chinew/accepted [C, nits-1]."""
@@ -240,6 +240,7 @@ class DeviceModel:
         mo.pnum = int(P if pnum is None else pnum)
         mo.row_stride = P + 5
         mo.step_sd, mo.seed = float(step_sd), int(seed) & 0xFFFFFFFFFFFFFFFF
+        mo.speculate = int(speculate)
 
         if device_buffers:
             import torch

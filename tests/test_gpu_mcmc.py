@@ -146,3 +146,33 @@ def test_edge_semantics_nan_chi_rejects_and_device_buffers():
     dev = dm.mcmc(torch.from_numpy(th).cuda(), nits=60, seed=1, trace=True, device_buffers=True)
     torch.cuda.synchronize()
     assert np.array_equal(dev["samples"].cpu().numpy(), out["samples"], equal_nan=True)
+
+
+@pytest.mark.parametrize("rng_mode", ["philox", "host"])
+def test_prefetching_width_does_not_change_the_chain(rng_mode):
+    """odl_mcmc_opts.speculate = K lanes per chain evaluate K iterations at once along the all-rejected path:
+    every K gives the same chain bit for bit -- samples, per-iteration trace, summaries, final state, and the
+    count of consumed integrator steps (discarded speculative solves are not counted)."""
+    dm, _ = device_model("two_i")
+    rng = np.random.default_rng(5)
+    center = np.array([7.475e-09, 1.069e-07, 19.73, 1.934, 2.799])
+    C, nits = 37, 120                                           # ragged: 37 chains do not fill the last group/warp
+    starts = center * np.exp(0.05 * rng.standard_normal((C, 5)))
+    kw = dict(nits=nits, rng_mode=rng_mode, trace=True, seed=3)
+    if rng_mode == "host":
+        kw["z"] = 0.05 * rng.standard_normal((C, nits - 1, 5))
+        kw["u"] = rng.random((C, nits - 1))
+    base = dm.mcmc(starts, speculate=1, **kw)
+    assert 0.05 < base["accepted"].mean() < 0.7
+    for K in (2, 4, 8, 16, 32, 0):
+        out = dm.mcmc(starts, speculate=K, **kw)
+        for key in ("samples", "chinew", "accepted", "summaries", "chain_state", "theta", "step_count", "fail_count"):
+            assert np.array_equal(base[key], out[key], equal_nan=True), (K, key)
+    # segmented chains keep working with groups: two launches of 60 + 59 iterations
+    seg = dm.mcmc(starts, speculate=8, segments=2, **kw)
+    assert np.array_equal(base["samples"], seg["samples"]) and np.array_equal(base["summaries"], seg["summaries"])
+    # static parameters (walk list) and burn-in bookkeeping
+    a = dm.mcmc(starts, speculate=1, walk=[0, 2, 4], burnin=10, **kw)
+    b = dm.mcmc(starts, speculate=16, walk=[0, 2, 4], burnin=10, **kw)
+    assert np.array_equal(a["samples"], b["samples"]) and a["samples"].shape[1] == nits - 1 - 10
+    assert np.all(a["samples"][:, :, 1] == starts[:, None, 1])          # a static parameter never moves
