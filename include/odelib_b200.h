@@ -101,7 +101,9 @@ typedef struct odl_mcmc_opts {
 
 typedef struct odl_mcmc_io {
   double* theta;           /* [n_chain][n_param] in: starts (or current points), out: current points */
-  double* chain_state;     /* [n_chain][4] chi, r2, accepts, unused; in when it_begin>1, always out */
+  double* chain_state;     /* [n_chain][8] chi, r2, accepts, best_chi, best_iteration, 3 unused; in when
+                              it_begin>1, always out.  best_* = the first minimum of chi over the kept rows
+                              (what set_best_params' idxmin picks, Framework.py:725-731); best_iteration 0 = none */
   double* samples;         /* [n_chain][nits-1-burnin][row_stride] or NULL:
                               theta.., chi, rsquared, aic, iteration, acceptance_ratio (Samplers.py:160-165) */
   double* summaries;       /* [n_chain][1+2*n_param] count, mean, M2 of ln(theta) over kept rows, or NULL
@@ -113,6 +115,7 @@ typedef struct odl_mcmc_io {
   unsigned char* trace_accept; /* optional [n_chain][nits-1] */
   int* fail_count;         /* optional [n_chain], accumulated */
   long long* step_count;   /* optional [n_chain], accumulated attempted integrator steps */
+  double* best_theta;      /* optional [n_chain][n_param] parameters of the best kept row */
 } odl_mcmc_io;
 
 int odl_abi_version(void);
@@ -139,6 +142,16 @@ int odl_trajectory(odl_model* m, const odl_solver_opts* so, long long n, const d
                    const double* y0_or_null, int mem, double* traj, int* status, int* nsteps, void* stream);
 int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_opts* mo, const odl_mcmc_io* io, int mem,
              void* stream);
+
+/* Chain-start selection on the device (replaces the pandas filter of Framework.py:1004-1012).
+   odl_select_below: index_dev[0..*count_host) <- the rows i of chi_dev[0..n) with chi < cut, ascending (NaN never
+   qualifies); returns after *count_host is valid.  odl_gather_rows: dst_dev[r][:] = src_dev[row(r)][:] with
+   row(r) = index_dev[picks_host[r]] (or picks_host[r] when index_dev is NULL); picks are drawn by the caller
+   (the reference draws them with DataFrame.sample(n, replace=True), Framework.py:1012). */
+int odl_select_below(odl_model* m, const double* chi_dev, long long n, double cut, int* index_dev, long long* count_host,
+                     void* stream);
+int odl_gather_rows(odl_model* m, const double* src_dev, int row_len, const int* index_dev_or_null,
+                    const long long* picks_host, long long n_pick, double* dst_dev, void* stream);
 
 /* device time (ms) of the kernels launched by the last odl_sweep/odl_mcmc/odl_trajectory call on this
    model, measured with CUDA events on the launching stream; blocks until they have completed */

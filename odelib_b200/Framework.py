@@ -24,16 +24,37 @@ import numpy as np
 import pandas as pd
 
 from .engine import SCIPY_TOL, DeviceModel, ObsTables
-from .rhat import allgather_summaries, rhat_from_summaries, shard_bounds
+from .rhat import allgather_summaries, pooled_log_stats, rhat_from_summaries, shard_bounds
 from .Statistics import Samplers, stats
+
+
+def _rawstats_from_logmoments(log_mean, log_std):
+    return np.exp(log_mean), ((np.exp(log_std ** 2) - 1) * np.exp(2 * log_mean + log_std ** 2.0)) ** 0.5
 
 
 def rawstats(pdseries):
     """Log-space median and log-normal standard deviation of a posterior column (Framework.py:11-17)."""
     lx = np.log(pdseries)
-    log_mean = lx.mean()
-    log_std = lx.std()
-    return np.exp(log_mean), ((np.exp(log_std ** 2) - 1) * np.exp(2 * log_mean + log_std ** 2.0)) ** 0.5
+    return _rawstats_from_logmoments(lx.mean(), lx.std())
+
+
+class PosteriorSummary:
+    """What ``MCMC(..., posterior="summary")`` returns instead of the posterior frame: everything the reference's
+    fitting report and ``set_best_params`` take from that frame (Framework.py:1047-1060, :725-731), reduced on
+    the device -- per-parameter median / standard deviation (rawstats), the best kept row, R-hat -- without
+    materialising chains x rows x columns on the host (65,536 chains x 500 rows are 2.9 GB as a frame)."""
+
+    def __init__(self, pnames, n_chains, n_rows, stats, best, best_chi, rhat, acceptance_ratio):
+        self.parameter_names, self.n_chains, self.n_rows = list(pnames), int(n_chains), int(n_rows)
+        self.stats, self.best, self.best_chi, self.rhat = stats, best, float(best_chi), rhat
+        self.acceptance_ratio = float(acceptance_ratio)
+
+    def __repr__(self):
+        rows = ["PosteriorSummary: {} chains, {} kept rows".format(self.n_chains, self.n_rows)]
+        for p, (med, sd) in self.stats.items():
+            rows.append("  {}: median = {:0.3e}, sd = {:0.3e}, best = {:0.3e}".format(p, med, sd, self.best[p]))
+        rows.append("  best chi = {:0.3e}".format(self.best_chi))
+        return "\n".join(rows)
 
 
 class parameter:
@@ -428,13 +449,15 @@ class ModelFramework:
 
     # ------------------------------------------------------------------ MCMC (Framework.py:946-1061)
     def _run_chains(self, starts, seeds, nits, burnin, static_parameters, rng="auto", rtol=None, atol=None,
-                    update_model=False, return_raw=False, return_frame=False):
-        """All chains in one kernel.  starts: list of theta vectors; seeds: per-chain seeds (chain index)."""
+                    update_model=False, return_raw=False, return_frame=False, keep_samples=True):
+        """All chains in one kernel.  starts: list of theta vectors, or a CUDA tensor [C, P] (chain starts chosen on
+        the device); seeds: per-chain seeds (chain index)."""
         dm = self._device()
         static = set(static_parameters or ())
         walk_names = [p for p in self._pnames if p not in static]
         walk = [self._pnames.index(p) for p in walk_names]
-        theta0 = np.array(starts, dtype=np.float64)
+        on_device = hasattr(starts, "is_cuda")
+        theta0 = starts if on_device else np.array(starts, dtype=np.float64)
         C = theta0.shape[0]
         n_iter = nits - 1
         if not burnin:
@@ -442,7 +465,7 @@ class ModelFramework:
         if rng == "auto":
             rng = "reference" if C * n_iter * (2 * len(walk) + 1) <= 20_000_000 else "philox"
         kw = dict(nits=nits, burnin=burnin, walk=walk, pnum=self._pnum, rtol=self.rtol if rtol is None else rtol,
-                  atol=self.atol if atol is None else atol)
+                  atol=self.atol if atol is None else atol, keep_samples=keep_samples, device_buffers=on_device)
         if rng == "reference":
             walking = [self.parameters[p] for p in walk_names]
             z = np.empty((C, n_iter, len(walk)))
@@ -454,6 +477,10 @@ class ModelFramework:
             out = dm.mcmc(theta0, rng_mode="philox", seed=int(self.random_seed), chain_offset=int(seeds[0]), **kw)
         else:
             raise ValueError("rng must be 'auto', 'reference' or 'philox'")
+        if on_device:                                             # small per-chain results to the host; samples on demand
+            out = {k: (v.cpu().numpy() if hasattr(v, "is_cuda") and k != "samples" else v) for k, v in out.items()}
+            if out["samples"] is not None and (return_frame or not return_raw):
+                out["samples"] = out["samples"].cpu().numpy()
         self._last_mcmc = out
         if return_raw:
             return out
@@ -484,30 +511,71 @@ class ModelFramework:
                 self.set_inits(**{s: out["theta"][0][m] for s, m in zip(self._snames, self._y0_map()) if m >= 0})
         return frames
 
+    def _survey_starts_on_device(self, chain_inits, fitsurvey_samples, sd_fitdistance):
+        """Chain starts for ``MCMC(chain_inits=int)`` (Framework.py:993-1016) without bringing the survey back:
+        LHS sample -> device, one sweep, threshold filter + ordered compaction on the device, the reference's own
+        random picks (DataFrame.sample(n, replace=True) == np.random.choice(len, n, replace=True)) drawn on the
+        host from the COUNT alone, gather on the device.  Returns a CUDA tensor [chain_inits, P], or None when
+        the survey has no finite chi (the reference then warns and starts every chain from the current values)."""
+        import torch
+        dm = self._device()
+        ps = self._lhs_samples(fitsurvey_samples)[self.get_pnames()]
+        theta = torch.from_numpy(np.ascontiguousarray(ps.to_numpy(dtype=np.float64))).to(torch.device("cuda", dm.device))
+        res = dm.sweep(theta, rtol=self.rtol, atol=self.atol, solver="auto")
+        calc = {s: np.exp(self._obs_logabundance[s] + sd_fitdistance * self._obs_logsigma[s]) for s in self._obs_logabundance}
+        cutchi = self.get_chi(calc)                              # = n_obs * sd^2 / 2
+        _, n_finite = dm.select_below(res["chi"], np.inf)
+        if n_finite == 0:
+            warnings.warn("Pre-sampling of Multidimentional space failed")
+            return None
+        index, count = dm.select_below(res["chi"], float(cutchi))
+        if count == 0:
+            raise ValueError("Preliminary sampling found no parameter sets which meet the minimal threshold \n"
+                             "  Try: \n   1. Increasing sd_fitdistance \n   2. Increasing fitsurvey_samples \n"
+                             "   3. Different priors and / or different parameter guesses")
+        picks = np.random.choice(count, size=chain_inits, replace=True)
+        return dm.gather_rows(theta, picks, index=index)
+
+    def posterior_summary(self, static_parameters=()):
+        """PosteriorSummary of the last chains, from the device-side reductions alone."""
+        out = self._last_mcmc
+        P = len(self._pnames)
+        N, log_mean, log_std = pooled_log_stats(out["summaries"], P)
+        stats_ = {p: _rawstats_from_logmoments(log_mean[i], log_std[i]) for i, p in enumerate(self._pnames)}
+        best_chi = np.asarray(out["best_chi"], dtype=np.float64)
+        have = np.asarray(out["best_iteration"]) > 0
+        if have.any() and np.isfinite(best_chi[have]).any():
+            c = int(np.nanargmin(np.where(have, best_chi, np.nan)))       # first chain holding the minimum, as idxmin
+            best = dict(zip(self._pnames, np.asarray(out["best_theta"])[c]))
+            bchi = best_chi[c]
+        else:
+            best, bchi = dict(zip(self._pnames, self._current_theta())), np.nan
+        for p in static_parameters or ():                        # quirk A13: static columns hold the prior's scale
+            best[p] = self.parameters[p].hp['scale']
+        C = len(best_chi)
+        rh = dict(zip(self._pnames, rhat_from_summaries(out["summaries"], P))) if C > 1 and out["n_keep"] > 1 else None
+        n_iter = max(1, int(out["n_keep"]) + int(out["burnin"]))
+        acc = float(np.asarray(out["chain_state"])[:, 2].mean()) / n_iter
+        return PosteriorSummary(self._pnames, C, N, stats_, best, bchi, rh, acc)
+
     def MCMC(self, chain_inits=1, iterations_per_chain=1000, cpu_cores=1, static_parameters=list(), print_report=True,
-             fitsurvey_samples=1000, sd_fitdistance=3.0, rng="auto"):
+             fitsurvey_samples=1000, sd_fitdistance=3.0, rng="auto", posterior="frame"):
         """Many Metropolis-Hastings chains (Framework.py:946-1061); returns the concatenated posterior frame
-        with a ``chain#`` column.  ``cpu_cores`` is ignored: every chain runs concurrently on the GPU."""
+        with a ``chain#`` column.  ``cpu_cores`` is ignored: every chain runs concurrently on the GPU.
+
+        The steps either side of the chains stay on the device too: with ``chain_inits=int`` the survey is filtered
+        and the starts are gathered there (only the count of acceptable rows comes back), and the fitting report and
+        ``set_best_params`` read the kernel's own reductions (pooled log-moments, best kept row, R-hat) instead of
+        scanning the frame.  ``posterior="summary"`` skips the frame altogether and returns a PosteriorSummary."""
+        if posterior not in ("frame", "summary"):
+            raise ValueError("posterior must be 'frame' or 'summary'")
         if isinstance(chain_inits, pd.DataFrame):
             chain_inits = [row.to_dict() for _, row in chain_inits[self.get_pnames()].iterrows()]
         base = self._current_theta()
         if isinstance(chain_inits, (int, np.integer)):
-            survey = self.fit_survey(samples=fitsurvey_samples)
-            survey = survey.dropna()
-            if survey.empty:
-                warnings.warn("Pre-sampling of Multidimentional space failed")
+            starts = self._survey_starts_on_device(int(chain_inits), fitsurvey_samples, sd_fitdistance)
+            if starts is None:
                 starts = [base.copy() for _ in range(chain_inits)]
-            else:
-                calc = {s: np.exp(self._obs_logabundance[s] + sd_fitdistance * self._obs_logsigma[s])
-                        for s in self._obs_logabundance}
-                cutchi = self.get_chi(calc)                      # = n_obs * sd^2 / 2
-                good = survey[survey['chi'] < cutchi]
-                if len(good) == 0:
-                    raise ValueError("Preliminary sampling found no parameter sets which meet the minimal threshold \n"
-                                     "  Try: \n   1. Increasing sd_fitdistance \n   2. Increasing fitsurvey_samples \n"
-                                     "   3. Different priors and / or different parameter guesses")
-                picks = good.sample(chain_inits, replace=True)
-                starts = [picks.iloc[i][self.get_pnames()].to_numpy(dtype=np.float64) for i in range(chain_inits)]
         else:
             starts = []
             for d in chain_inits:
@@ -516,19 +584,24 @@ class ModelFramework:
                     if k in self._pnames:
                         th[self._pnames.index(k)] = float(v)
                 starts.append(th)
-        seeds = list(range(len(starts)))                          # chain seed = chain index (:1015, :1020)
-        posterior = self._run_chains(starts, seeds, iterations_per_chain, int(iterations_per_chain / 2),
-                                     static_parameters, rng=rng, return_frame=True)
         n_chains = len(starts)
-        self.rhat = dict(zip(self.get_pnames(), rhat_from_summaries(self._last_mcmc["summaries"], len(self._pnames)))) \
-            if n_chains > 1 and self._last_mcmc["n_keep"] > 1 else None
+        seeds = list(range(n_chains))                             # chain seed = chain index (:1015, :1020)
+        want_frame = posterior == "frame"
+        result = self._run_chains(starts, seeds, iterations_per_chain, int(iterations_per_chain / 2), static_parameters,
+                                  rng=rng, return_frame=want_frame, return_raw=not want_frame, keep_samples=want_frame)
+        summary = self.posterior_summary(static_parameters)
+        self.rhat = summary.rhat
         if print_report:
             report = ["\nFitting Report\n==============="]
             for col in self.get_pnames():
-                median, std = rawstats(posterior[col])
+                median, std = summary.stats[col]
+                if col in (static_parameters or ()):
+                    continue                                      # constant column: std == 0 in the reference's frame
                 if (median != 0.0) and (std != 0.0):
                     report.append("parameter: {}\n\tmedian = {:0.3e}, Standard deviation = {:0.3e}".format(col, median, std))
-            self.set_best_params(posterior)
+            self.set_parameters(**summary.best)                   # set_best_params (Framework.py:725-731)
+            if self._snames[0] + '0' in self.get_pnames():
+                self.set_inits(**{s_: summary.best[s_ + '0'] for s_ in self._snames})
             fs = self.get_fitstats(self.integrate(predict_obs=True, as_dataframe=False))
             report.append("\nMedian parameter fit stats:")
             report.append("\tChi = {:0.3e}\n\tR-squared = {:0.3e}\n\tAIC = {:0.3e}".format(fs['Chi'], fs['R^2'], fs['AIC']))
@@ -536,4 +609,4 @@ class ModelFramework:
                 report.append("\nGelman-Rubin R-hat (log-parameters): " +
                               ", ".join("{}={:.3f}".format(k, v) for k, v in self.rhat.items()))
             print('\n'.join(report))
-        return posterior
+        return result if want_frame else summary

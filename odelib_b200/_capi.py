@@ -18,7 +18,7 @@ ST_OK, ST_MAXSTEPS, ST_NONFINITE, ST_HUNDERFLOW, ST_STIFF, ST_ALLMASKED = 0, 1, 
 
 EXPORTS = ["odl_abi_version", "odl_last_error", "odl_model_create", "odl_model_destroy", "odl_model_build_log",
            "odl_model_kernel_info", "odl_model_set_data", "odl_model_set_grid", "odl_sweep", "odl_trajectory",
-           "odl_mcmc", "odl_model_last_kernel_ms", "odl_model_last_pass_ms", "odl_launch_count", "odl_fp64_peak", "odl_debug_counters"]
+           "odl_mcmc", "odl_model_last_kernel_ms", "odl_model_last_pass_ms", "odl_launch_count", "odl_fp64_peak", "odl_debug_counters", "odl_select_below", "odl_gather_rows"]
 
 
 class OdlError(RuntimeError):
@@ -51,7 +51,7 @@ class McmcIO(C.Structure):
     _fields_ = [("theta", C.c_void_p), ("chain_state", C.c_void_p), ("samples", C.c_void_p),
                 ("summaries", C.c_void_p), ("z", C.c_void_p), ("u", C.c_void_p), ("forced", C.c_void_p),
                 ("trace_chinew", C.c_void_p), ("trace_accept", C.c_void_p), ("fail_count", C.c_void_p),
-                ("step_count", C.c_void_p)]
+                ("step_count", C.c_void_p), ("best_theta", C.c_void_p)]
 
 
 _lib = None
@@ -86,6 +86,10 @@ def lib():
     L.odl_model_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.odl_model_last_pass_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.odl_debug_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.odl_select_below.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.POINTER(C.c_longlong),
+                                   C.c_void_p]
+    L.odl_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
+                                  C.c_void_p]
     L.odl_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     if L.odl_abi_version() != 2:
         raise OdlError(EIO, "libodelib_b200.so ABI version mismatch - rebuild")

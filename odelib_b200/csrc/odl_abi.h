@@ -4,6 +4,7 @@
 #ifndef ODL_ABI_H
 #define ODL_ABI_H
 #define ODL_MAX_WALK 64
+#define ODL_CHAIN_STATE 8
 
 // status words (per system)
 #define ODL_OK 0
@@ -93,7 +94,8 @@ struct OdlTrajArgs {
 
 struct OdlMcmcArgs {
   double* theta_cur;             // [C][n_param] in: chain starts / current points; out: current points
-  double* chain_state;           // [C][4]  chi_cur, r2_cur, accepts, (unused)   (persist across launches)
+  double* chain_state;           // [C][ODL_CHAIN_STATE] chi_cur, r2_cur, accepts, best_chi, best_iteration, 3 unused
+                                 //   (persist across launches); best_* = first minimum of chi over the kept rows
   int n_chain;
   int chain_offset;              // global index of chain 0 of this launch (multi-GPU sharding / RNG key)
   int it_begin, it_end;          // iterations [it_begin, it_end) of Samplers.py:104; it_begin==1 => a-priori solve first
@@ -118,6 +120,7 @@ struct OdlMcmcArgs {
   unsigned char* trace_accept;   // optional [C][n_iter_total]
   int* fail_count;               // optional [C] proposals whose solve failed
   long long* step_count;         // optional [C] attempted integrator steps (flop accounting)
+  double* best_theta;            // optional [C][n_param] parameters of the best kept row (Framework.py:725-731)
 };
 
 #endif  // ODL_ABI_H

@@ -719,7 +719,8 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   OdlMcmcArgs A{};
   int rc;
   if ((rc = st.inout(io->theta, (size_t)C * P, &A.theta_cur, true))) return rc;
-  if ((rc = st.inout(io->chain_state, (size_t)C * 4, &A.chain_state, true))) return rc;
+  if ((rc = st.inout(io->chain_state, (size_t)C * ODL_CHAIN_STATE, &A.chain_state, true))) return rc;
+  if ((rc = st.inout(io->best_theta, (size_t)C * P, &A.best_theta, it_begin > 1))) return rc;
   if ((rc = st.inout(io->samples, (size_t)C * n_keep * stride, &A.samples, it_begin > 1))) return rc;
   if ((rc = st.inout(io->summaries, (size_t)C * (1 + 2 * P), &A.summaries, true))) return rc;
   if ((rc = st.in(io->z, (size_t)C * n_iter * mo->n_walk, &A.z))) return rc;
@@ -801,6 +802,128 @@ extern "C" int odl_model_last_kernel_ms(odl_model* m, float* ms) {
   if (!m->on_gpu || !m->timed) return fail(ODL_EINVAL, "no kernel has been launched on this model yet");
   ODL_CUDA(cudaEventSynchronize(m->ev1));
   ODL_CUDA(cudaEventElapsedTime(ms, m->ev0, m->ev1));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chain-start selection (Framework.py:993-1016): the rows of a survey whose chi lies below the threshold, in
+// survey order (what `fitsurvey[fitsurvey['chi'] < cutchi]` keeps; NaN never qualifies), and the gather of the
+// rows the caller's random picks name.  Ordered compaction: per-tile counts, one scan, per-tile ranks.
+// ---------------------------------------------------------------------------------------------
+#define ODL_SEL_TILE 1024
+__global__ void __launch_bounds__(256) odl_select_count_kernel(const double* chi, long long n, double cut, int* tile_count) {
+  __shared__ int total;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * ODL_SEL_TILE;
+  int c = 0;
+  for (int k = threadIdx.x; k < ODL_SEL_TILE; k += blockDim.x) {
+    const long long i = base + k;
+    if (i < n && chi[i] < cut) ++c;
+  }
+  for (int m = 16; m > 0; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&total, c);
+  __syncthreads();
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) odl_select_scan_kernel(int* tile_count, int n_tile, long long* total_out) {
+  // exclusive prefix of the tile counts, in place; one CTA walks the tiles in chunks of blockDim.x
+  __shared__ int s[1024];
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < n_tile; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    const int v = t < n_tile ? tile_count[t] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+      const int a = threadIdx.x >= (unsigned)off ? s[threadIdx.x - off] : 0;
+      __syncthreads();
+      s[threadIdx.x] += a;
+      __syncthreads();
+    }
+    if (t < n_tile) tile_count[t] = (int)(carry + s[threadIdx.x] - v);
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += s[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void __launch_bounds__(256) odl_select_write_kernel(const double* chi, long long n, double cut, const int* tile_offset,
+                                                               int* index_out) {
+  // one warp per 256 rows of the tile, rows in order: ballot + popc give the rank inside a 32-row slice
+  __shared__ int warp_count[8][4];
+  const long long base = (long long)blockIdx.x * ODL_SEL_TILE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned masks[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const long long i = base + (long long)(warp * 4 + r) * 32 + lane;
+    masks[r] = __ballot_sync(0xffffffffu, i < n && chi[i] < cut);
+    if (lane == 0) warp_count[warp][r] = __popc(masks[r]);
+  }
+  __syncthreads();
+  int before = tile_offset[blockIdx.x];
+  for (int w = 0; w < warp; ++w) for (int r = 0; r < 4; ++r) before += warp_count[w][r];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const long long i = base + (long long)(warp * 4 + r) * 32 + lane;
+    if ((masks[r] >> lane) & 1u) index_out[before + __popc(masks[r] & ((1u << lane) - 1u))] = (int)i;
+    before += __popc(masks[r]);
+  }
+}
+__global__ void __launch_bounds__(256) odl_gather_rows_kernel(const double* src, int row_len, const int* index, const long long* picks,
+                                                              long long n_pick, double* dst) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_pick * row_len) return;
+  const long long r = e / row_len;
+  const int c = (int)(e - r * row_len);
+  const long long row = index ? (long long)index[picks[r]] : picks[r];
+  dst[e] = src[row * row_len + c];
+}
+
+extern "C" int odl_select_below(odl_model* m, const double* chi_dev, long long n, double cut, int* index_dev, long long* count_host,
+                                void* stream) {
+  if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_select_below: model is not loaded on a GPU (no CPU fallback exists)");
+  if (n < 0 || n > 2147483647LL || !count_host || (n > 0 && (!chi_dev || !index_dev))) return fail(ODL_EINVAL, "odl_select_below: bad argument");
+  *count_host = 0;
+  if (n == 0) return 0;
+  ODL_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n_tile = (int)((n + ODL_SEL_TILE - 1) / ODL_SEL_TILE);
+  DevBuf& b = m->scratch[15];
+  int rc = b.ensure((size_t)n_tile * sizeof(int) + 16);
+  if (rc) return rc;
+  int* tiles = static_cast<int*>(b.p);
+  long long* total = reinterpret_cast<long long*>(static_cast<char*>(b.p) + (((size_t)n_tile * sizeof(int) + 7) & ~(size_t)7));
+  odl_select_count_kernel<<<n_tile, 256, 0, s>>>(chi_dev, n, cut, tiles);
+  odl_select_scan_kernel<<<1, 1024, 0, s>>>(tiles, n_tile, total);
+  odl_select_write_kernel<<<n_tile, 256, 0, s>>>(chi_dev, n, cut, tiles, index_dev);
+  g_launches.fetch_add(3);
+  ODL_CUDA(cudaGetLastError());
+  ODL_CUDA(cudaMemcpyAsync(count_host, total, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  ODL_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int odl_gather_rows(odl_model* m, const double* src_dev, int row_len, const int* index_dev_or_null,
+                               const long long* picks_host, long long n_pick, double* dst_dev, void* stream) {
+  if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_gather_rows: model is not loaded on a GPU (no CPU fallback exists)");
+  if (n_pick < 0 || row_len < 1 || (n_pick > 0 && (!src_dev || !picks_host || !dst_dev))) return fail(ODL_EINVAL, "odl_gather_rows: bad argument");
+  if (n_pick == 0) return 0;
+  ODL_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  DevBuf& b = m->scratch[14];
+  int rc = b.ensure((size_t)n_pick * sizeof(long long));
+  if (rc) return rc;
+  ODL_CUDA(cudaMemcpyAsync(b.p, picks_host, (size_t)n_pick * sizeof(long long), cudaMemcpyHostToDevice, s));
+  const long long elems = n_pick * row_len;
+  odl_gather_rows_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, s>>>(src_dev, row_len, index_dev_or_null,
+                                                                       static_cast<const long long*>(b.p), n_pick, dst_dev);
+  g_launches.fetch_add(1);
+  ODL_CUDA(cudaGetLastError());
+  ODL_CUDA(cudaStreamSynchronize(s));      // picks_host may be reused by the caller
   return 0;
 }
 

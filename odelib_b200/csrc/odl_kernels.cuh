@@ -1700,21 +1700,14 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
   ax.reset();
   double p[ODL_P];
   st.status = ODL_OK; st.nsteps = 0; st.slot = 0;
-  // group state, replicated on the K lanes of a chain.  it == next iteration of Samplers.py:104 to decide;
-  // apriori marks the solve of the starting point of a fresh chain (Samplers.py:88-90)
+  // Chain state (chi_cur, r2_cur, accepts, best_chi, best_iteration) lives in A.chain_state, not in registers: it is
+  // touched once per round by a few lanes, and registers held across the integration loop are what the DOPRI5 stepper
+  // is short of (128 per thread at 4 CTAs/SM).  `it` = next iteration of Samplers.py:104 to decide, the same on the K
+  // lanes of a chain; apriori marks the solve of the starting point of a fresh chain (Samplers.py:88-90).
   int it = A.it_begin;
-  double chi_cur = nan, r2_cur = nan;
-  int accepts = 0;
   bool apriori = A.it_begin == 1;                               // warp-uniform: the branches below hold collectives
-  // per-lane accumulators over CONSUMED solves (speculative work that was discarded is not counted)
-  int fails = 0;
-  long long steps = 0;
   bool active = false, done = false, use_ros = false;
-  if (has_chain && !apriori) {
-    chi_cur = A.chain_state[(size_t)chain * 4 + 0];
-    r2_cur = A.chain_state[(size_t)chain * 4 + 1];
-    accepts = (int)A.chain_state[(size_t)chain * 4 + 2];
-  }
+  double* cs = A.chain_state + (size_t)(has_chain ? chain : 0) * ODL_CHAIN_STATE;
   bool more = has_chain && (apriori || it < A.it_end);
 
   while (__any_sync(ODL_FULL, more)) {
@@ -1748,7 +1741,7 @@ ODL_UNROLL
         const bool restart = active && st.status == ODL_STIFF && !use_ros;
         if (__ballot_sync(ODL_FULL, restart)) {
           if (restart) {
-            steps += st.nsteps;
+            if (A.step_count) atomicAdd((unsigned long long*)&A.step_count[chain], (unsigned long long)st.nsteps);
             use_ros = true;
             odl_init_system(st, p, D, O, nullptr);
             ax.reset();
@@ -1769,11 +1762,16 @@ ODL_UNROLL
     }
     if (apriori) {
       // the starting point's own chi: no decision, no iteration consumed
-      chi_cur = __shfl_sync(ODL_FULL, my_chi, gbase);
-      r2_cur = __shfl_sync(ODL_FULL, my_r2, gbase);
-      if (valid) { steps += st.nsteps; if (st.status != ODL_OK) ++fails; }
+      if (valid) {
+        cs[0] = my_chi; cs[1] = my_r2;
+        if (A.step_count) atomicAdd((unsigned long long*)&A.step_count[chain], (unsigned long long)st.nsteps);
+        if (A.fail_count && st.status != ODL_OK) atomicAdd(&A.fail_count[chain], 1);
+      }
       apriori = false;
+      __syncwarp();
     } else {
+      const double chi_cur = cs[0], r2_cur = cs[1];
+      const int accepts = (int)cs[2];
       // ---- decisions along the all-rejected path: acc = exp(chi - chinew) > u (Samplers.py:124-127; NaN rejects) ----
       bool acc = false;
       if (valid) {
@@ -1794,8 +1792,9 @@ ODL_UNROLL
       for (int q = 0; q < ODL_P; ++q) pacc[q] = __shfl_sync(ODL_FULL, p[q], src);
       const double chi_acc = __shfl_sync(ODL_FULL, my_chi, src), r2_acc = __shfl_sync(ODL_FULL, my_r2, src);
       if (consumed) {
-        steps += st.nsteps;
-        if (st.status != ODL_OK) ++fails;
+        // counters cover CONSUMED solves only (speculative work that was discarded is not counted)
+        if (A.step_count) atomicAdd((unsigned long long*)&A.step_count[chain], (unsigned long long)st.nsteps);
+        if (A.fail_count && st.status != ODL_OK) atomicAdd(&A.fail_count[chain], 1);
         const int iter = it + sub;
         const long long k = (long long)chain * A.n_iter_total + (iter - 1);
         if (A.trace_chinew) A.trace_chinew[k] = my_chi;
@@ -1842,34 +1841,37 @@ ODL_UNROLL
 ODL_UNROLL
         for (int q = 0; q < ODL_P; ++q) { sm[1 + q] = mean[q]; sm[1 + ODL_P + q] = m2[q]; }
       }
-      __syncwarp();                                              // rows above read cur[] before it changes
-      if (jstar >= 0) {
-        chi_cur = chi_acc; r2_cur = r2_acc; ++accepts;
-        if (is_acc) {
+      // Best kept row (set_best_params' idxmin, Framework.py:725-731): the first kept row carries the current point;
+      // after that only an accepted proposal can be a new minimum (rejected rows repeat a chi already seen)
+      if (has_chain && sub == 0) {
+        const int first_kept = A.burnin + 1;
+        double best_chi = cs[3], best_it = cs[4];
+        if (it <= first_kept && first_kept < it + adv && first_kept - it != jstar) {
+          best_chi = chi_cur; best_it = (double)first_kept;
+          if (A.best_theta) {
 ODL_UNROLL
-          for (int q = 0; q < ODL_P; ++q) cur[q] = p[q];
+            for (int q = 0; q < ODL_P; ++q) A.best_theta[(size_t)chain * ODL_P + q] = cur[q];
+          }
         }
+        if (jstar >= 0 && it + jstar > A.burnin && (chi_acc < best_chi || (best_chi != best_chi && chi_acc == chi_acc) || best_it == 0.0)) {
+          best_chi = chi_acc; best_it = (double)(it + jstar);
+          if (A.best_theta) {
+ODL_UNROLL
+            for (int q = 0; q < ODL_P; ++q) A.best_theta[(size_t)chain * ODL_P + q] = pacc[q];
+          }
+        }
+        cs[3] = best_chi; cs[4] = best_it;
+      }
+      __syncwarp();                                              // everything above read cur[] / cs[] before they change
+      if (is_acc) {
+        cs[0] = my_chi; cs[1] = my_r2; cs[2] = (double)(accepts + 1);
+ODL_UNROLL
+        for (int q = 0; q < ODL_P; ++q) cur[q] = p[q];
       }
       it += adv;
       __syncwarp();                                              // the next round's proposals read cur[]
     }
     more = has_chain && it < A.it_end;
-  }
-  // ---- chain state for the next segment, counters ----
-  // sums over the K lanes of the group (all 32 lanes take part in the shuffles)
-  for (int m = K >> 1; m > 0; m >>= 1) {
-    fails += __shfl_xor_sync(ODL_FULL, fails, m);
-    const int lo = __shfl_xor_sync(ODL_FULL, (int)(steps & 0xffffffffLL), m), hi = __shfl_xor_sync(ODL_FULL, (int)(steps >> 32), m);
-    steps += ((long long)hi << 32) | (unsigned int)lo;
-  }
-  if (has_chain) {
-    if (sub == 0) {
-      A.chain_state[(size_t)chain * 4 + 0] = chi_cur;
-      A.chain_state[(size_t)chain * 4 + 1] = r2_cur;
-      A.chain_state[(size_t)chain * 4 + 2] = (double)accepts;
-      if (A.fail_count) A.fail_count[chain] += fails;
-      if (A.step_count) A.step_count[chain] += steps;
-    }
   }
 }
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)

@@ -86,6 +86,10 @@ class DeviceModel:
         self._h = h
         self._L = L
         self.compile_only = compile_only
+        self.device = None
+        if not compile_only:
+            import torch
+            self.device = int(device) if device is not None else int(torch.cuda.current_device())
         self.n_obs = 0
         self.n_slot = 0
         self.n_grid = 0
@@ -204,6 +208,28 @@ class DeviceModel:
             res["pred"] = pred
         return res
 
+    # -- chain-start selection on the device (Framework.py:1004-1012) -------------------------------
+    def select_below(self, chi, cut):
+        """Rows of the CUDA tensor `chi` with chi < cut, ascending -> (index tensor [n] int32, count)."""
+        import torch
+        assert _is_torch_cuda(chi) and chi.dtype == torch.float64 and chi.is_contiguous()
+        index = torch.empty(chi.numel(), dtype=torch.int32, device=chi.device)
+        count = C.c_longlong(0)
+        _capi.check(self._L.odl_select_below(self._h, _ptr(chi), chi.numel(), float(cut), _ptr(index), C.byref(count),
+                                             self._stream()))
+        return index, int(count.value)
+
+    def gather_rows(self, src, picks, index=None):
+        """dst[r] = src[index[picks[r]]] (or src[picks[r]]) for a CUDA matrix `src`; picks: host int64 array."""
+        import torch
+        assert _is_torch_cuda(src) and src.dtype == torch.float64 and src.dim() == 2
+        src = src.contiguous()
+        picks = np.ascontiguousarray(picks, dtype=np.int64)
+        dst = torch.empty((picks.size, src.shape[1]), dtype=torch.float64, device=src.device)
+        _capi.check(self._L.odl_gather_rows(self._h, _ptr(src), int(src.shape[1]), _ptr(index), picks.ctypes.data,
+                                            picks.size, _ptr(dst), self._stream()))
+        return dst
+
     # -- full-grid trajectories: ModelFramework.integrate (Framework.py:656) -----------------------
     def trajectory(self, theta, y0=None, rtol=None, atol=None, max_steps=500000):
         so = self._solver_opts(rtol, atol, max_steps, "dopri5", False)
@@ -223,7 +249,8 @@ class DeviceModel:
              trace=False, keep_samples=True, summaries=True, segments=1, device_buffers=False, speculate=0):
         """Run len(theta0) independent chains.  Returns dict with numpy arrays (or torch tensors when
         device_buffers=True): theta (final points), samples [C, nits-1-burnin, P+5], summaries
-        [C, 1+2P], chain_state [C,4], and with trace=True chinew/accepted [C, nits-1]."""
+        [C, 1+2P], chain_state [C,8] (chi, r2, accepts, best_chi, best_iteration, ...), best_theta [C, P] (the
+        chain's first minimum of chi over its kept rows), and with trace=True chinew/accepted [C, nits-1]."""
         so = self._solver_opts(rtol, atol, max_steps, solver, False)
         P = self.n_param
         walk = list(range(P)) if walk is None else [int(w) for w in walk]
@@ -262,7 +289,8 @@ class DeviceModel:
         if theta.shape[1] != P:
             raise ValueError(f"theta0 must be [C, {P}]")
         mo.n_chain = Cn
-        state = new((Cn, 4))
+        state = new((Cn, 8))
+        best = new((Cn, P))
         samples = new((Cn, n_keep, P + 5)) if keep_samples else None
         summ = new((Cn, 1 + 2 * P)) if summaries else None
         tr_chi = new((Cn, n_iter)) if trace else None
@@ -271,7 +299,7 @@ class DeviceModel:
         steps = new((Cn,), i64)
         z, u, forced = conv(z), conv(u), conv(forced)
         io = _capi.McmcIO(_ptr(theta), _ptr(state), _ptr(samples), _ptr(summ), _ptr(z), _ptr(u), _ptr(forced),
-                          _ptr(tr_chi), _ptr(tr_acc), _ptr(fails), _ptr(steps))
+                          _ptr(tr_chi), _ptr(tr_acc), _ptr(fails), _ptr(steps), _ptr(best))
         # optional segmentation of long chains into several launches (state persists in the buffers)
         bounds = np.linspace(1, nits, int(segments) + 1).astype(int)
         ms = 0.0
@@ -283,7 +311,8 @@ class DeviceModel:
             if not device_buffers:
                 ms += self.last_kernel_ms()
         res = {"theta": theta, "chain_state": state, "samples": samples, "summaries": summ, "fail_count": fails,
-               "step_count": steps, "kernel_ms": ms, "n_keep": n_keep, "burnin": burnin}
+               "step_count": steps, "kernel_ms": ms, "n_keep": n_keep, "burnin": burnin,
+               "best_theta": best, "best_chi": state[:, 3], "best_iteration": state[:, 4]}
         if trace:
             res["chinew"], res["accepted"] = tr_chi, tr_acc
         return res

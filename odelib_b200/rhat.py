@@ -24,6 +24,25 @@ def rhat_from_summaries(summaries, n_param):
         return np.sqrt(((n - 1.0) / n * W + B / n) / W)
 
 
+def pooled_log_stats(summaries, n_param):
+    """Per-chain Welford summaries of ln(theta) -> (count, log_mean[P], log_std[P]) of ALL kept rows pooled.
+
+    log_std uses ddof=1 like pandas' Series.std(); these are the two numbers the reference's rawstats
+    (Framework.py:11-17) takes from the posterior frame, so the fitting report needs no frame at all."""
+    s = np.asarray(summaries, dtype=np.float64)
+    n = s[:, 0]
+    means = s[:, 1:1 + n_param]
+    m2 = s[:, 1 + n_param:1 + 2 * n_param]
+    N = n.sum()
+    if N < 1:
+        return 0.0, np.full(n_param, np.nan), np.full(n_param, np.nan)
+    mean = (n[:, None] * means).sum(axis=0) / N
+    M2 = m2.sum(axis=0) + (n[:, None] * (means - mean) ** 2).sum(axis=0)
+    with np.errstate(all="ignore"):
+        std = np.sqrt(M2 / (N - 1.0)) if N > 1 else np.full(n_param, np.nan)
+    return float(N), mean, std
+
+
 def shard_bounds(n_total, world_size, rank):
     """Contiguous block of chains / parameter sets owned by `rank`."""
     base, rem = divmod(int(n_total), int(world_size))

@@ -79,3 +79,60 @@ def test_mcmc_demo_call_shapes_and_report(capsys):
     assert np.all(p2["tau"] == 1) and len(p2) == 2 * 49
     with pytest.raises(ValueError):
         m.MCMC(chain_inits=2, iterations_per_chain=50, fitsurvey_samples=50, sd_fitdistance=0.01, print_report=False)
+
+
+def test_chain_start_selection_on_the_device_equals_the_pandas_filter():
+    """f1 (Framework.py:993-1016): threshold filter + ordered compaction + gather on the device pick exactly the rows
+    `fitsurvey[fitsurvey['chi'] < cutchi].sample(n, replace=True)` picks under the same numpy seed."""
+    import torch
+    m = make_model("zero_i")
+    dm = m._device()
+    np.random.seed(4)
+    ps = m._lhs_samples(5000)[m.get_pnames()]
+    theta = np.ascontiguousarray(ps.to_numpy(dtype=np.float64))
+    res = m.sweep(theta)
+    survey = ps.reset_index(drop=True).copy()
+    survey["chi"] = res["chi"]
+    survey = survey.dropna()
+    cut = 37 * 6.0 ** 2 / 2
+    np.random.seed(11)
+    ref = survey[survey["chi"] < cut].sample(16, replace=True)[m.get_pnames()].to_numpy()
+    th_dev = torch.from_numpy(theta).cuda()
+    chi_dev = torch.from_numpy(res["chi"]).cuda()
+    index, count = dm.select_below(chi_dev, cut)
+    assert count == int((survey["chi"] < cut).sum()) and count > 50
+    assert np.array_equal(index[:count].cpu().numpy(), np.flatnonzero(res["chi"] < cut))      # ascending, NaN excluded
+    np.random.seed(11)
+    got = dm.gather_rows(th_dev, np.random.choice(count, size=16, replace=True), index=index).cpu().numpy()
+    assert np.array_equal(got, ref)
+    # ragged sizes around the 1024-row tiles; nothing / everything selected
+    for n in (1, 1023, 1025, 4097):
+        idx, c = dm.select_below(chi_dev[:n].contiguous(), cut)
+        assert np.array_equal(idx[:c].cpu().numpy(), np.flatnonzero(res["chi"][:n] < cut))
+    assert dm.select_below(chi_dev, -1.0)[1] == 0
+    assert dm.select_below(chi_dev, np.inf)[1] == int(np.isfinite(res["chi"]).sum())
+
+
+def test_report_and_best_parameters_come_from_device_reductions(capsys):
+    """f2 (Framework.py:11-17, :725-731, :1047-1060): pooled log-moments and the best kept row from the kernel equal
+    rawstats / idxmin over the posterior frame; posterior='summary' returns them without building the frame."""
+    from odelib_b200.Framework import PosteriorSummary, rawstats
+    m = make_model("two_i")
+    np.random.seed(3)
+    post = m.MCMC(chain_inits=8, iterations_per_chain=200, fitsurvey_samples=4000, sd_fitdistance=6.0)
+    capsys.readouterr()
+    s = m.posterior_summary()
+    for p in m.get_pnames():
+        med, sd = rawstats(post[p])
+        assert s.stats[p][0] == pytest.approx(med, rel=1e-12) and s.stats[p][1] == pytest.approx(sd, rel=1e-9)
+    row = post.loc[post["chi"].idxmin()]
+    assert s.best_chi == row["chi"] and all(s.best[p] == row[p] for p in m.get_pnames())
+    assert all(float(m.get_parameters(as_dict=True)[p]) == row[p] for p in m.get_pnames())        # set_best_params ran
+    assert s.n_rows == len(post) and s.n_chains == 8
+    m2 = make_model("two_i")
+    np.random.seed(3)
+    summ = m2.MCMC(chain_inits=8, iterations_per_chain=200, fitsurvey_samples=4000, sd_fitdistance=6.0,
+                   posterior="summary")
+    assert isinstance(summ, PosteriorSummary) and "Fitting Report" in capsys.readouterr().out
+    assert summ.best == s.best and summ.stats == s.stats and summ.rhat == s.rhat
+    assert m2._last_mcmc["samples"] is None                     # no sample rows were produced at all

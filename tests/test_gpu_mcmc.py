@@ -176,3 +176,20 @@ def test_prefetching_width_does_not_change_the_chain(rng_mode):
     b = dm.mcmc(starts, speculate=16, walk=[0, 2, 4], burnin=10, **kw)
     assert np.array_equal(a["samples"], b["samples"]) and a["samples"].shape[1] == nits - 1 - 10
     assert np.all(a["samples"][:, :, 1] == starts[:, None, 1])          # a static parameter never moves
+
+
+def test_best_kept_row_per_chain_matches_idxmin_of_the_samples():
+    """chain_state[:, 3:5] / best_theta: the first minimum of chi over each chain's kept rows (what the reference's
+    set_best_params finds with idxmin over the posterior frame, Framework.py:725-731), tracked in the kernel."""
+    dm, _ = device_model("two_i")
+    rng = np.random.default_rng(9)
+    center = np.array([7.475e-09, 1.069e-07, 19.73, 1.934, 2.799])
+    starts = center * np.exp(0.1 * rng.standard_normal((53, 5)))
+    for spec, segments in ((1, 1), (8, 1), (4, 3)):
+        out = dm.mcmc(starts, nits=160, seed=2, speculate=spec, segments=segments)
+        chi = out["samples"][:, :, 5]
+        rows = np.argmin(chi, axis=1)                            # first occurrence of the minimum
+        c = np.arange(len(starts))
+        assert np.array_equal(out["best_chi"], chi[c, rows])
+        assert np.array_equal(out["best_iteration"], out["samples"][c, rows, 5 + 3])
+        assert np.array_equal(out["best_theta"], out["samples"][c, rows, :5])
