@@ -112,12 +112,12 @@ dm, tab = device_model("two_i")
 ns4 = 16384 if QUICK else 65536
 theta = torch.from_numpy(stiff_thetas(ns4, seed=0)).cuda()
 c4 = {}
-for solver in ("radau5", "ros23", "auto"):
+for solver in ("bdf", "radau5", "ros23", "auto"):
     t, r = timed(lambda: dm.sweep(theta, solver=solver, max_steps=2000000), reps=2)
     c4[f"sweep_{solver}"] = {"sets": ns4, "seconds": t, "solves_per_s": ns4 / t, "mean_steps": float(r["nsteps"].double().mean().item()),
                              "ok_fraction": float((r["status"] == 0).double().mean().item())}
 starts = theta[:1024]
-for solver in ("radau5", "ros23"):
+for solver in ("bdf", "radau5", "ros23"):
     its = 100 if QUICK else 400
     t, r = timed(lambda: dm.mcmc(starts, nits=its, solver=solver, seed=2, device_buffers=True, max_steps=2000000), reps=1)
     c4[f"mcmc_{solver}"] = {"chains": 1024, "iterations": its, "seconds": t, "chain_steps_per_s": 1024 * (its - 1) / t}
@@ -143,7 +143,7 @@ out["C5_network_5x5"] = {"states": 35, "parameters": 40, "chains_per_gpu": C5, "
                          "chain_steps_per_s": C5 * (its - 1) / t, "mean_integrator_steps_per_solve": steps / (C5 * its),
                          "fp64_tflops": steps * flops_per_step(dm) / t / 1e12, "kernel": dm.kernel_info("mcmc"),
                          "cpu_oracle_solves_per_s_1core": cpu_rate(rhs, starts[:20].cpu().numpy(), tab),
-                         "note": "thread-per-system with rolled loops / local memory (n > 8 path); warp-per-system mapping is future work"}
+                         "note": "thread-per-system with rolled loops / local memory (n > 8 path), prefetching MH; a sub-warp mapping is future work"}
 
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
