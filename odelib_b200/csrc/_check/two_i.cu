@@ -3,7 +3,8 @@
 #define ODL_NOUT 2
 #define ODL_RHS_FLOPS 11
 #define ODL_AUTONOMOUS 1
-__device__ __forceinline__ void odl_rhs(const double (&y)[ODL_N], const double t, const double (&p)[ODL_P], double (&dy)[ODL_N]) {
+template <class YV, class PV, class DV>
+__device__ __forceinline__ void odl_rhs(const YV& y, const double t, const PV& p, DV& dy) {
   const double v10 = p[0] * y[0];
   const double v11 = p[1] * y[0];
   const double v12 = v11 * y[3];
@@ -20,7 +21,8 @@ __device__ __forceinline__ void odl_rhs(const double (&y)[ODL_N], const double t
   dy[2] = v17;
   dy[3] = v20;
 }
-__device__ __forceinline__ void odl_jac(const double (&y)[ODL_N], const double t, const double (&p)[ODL_P], double (&J)[ODL_N][ODL_N]) {
+template <class YV, class PV>
+__device__ __forceinline__ void odl_jac(const YV& y, const double t, const PV& p, double (&J)[ODL_N][ODL_N]) {
   const double v11 = p[1] * y[0];
   const double v18 = p[2] * p[3];
   const double v23 = p[1] * y[3];
@@ -46,13 +48,15 @@ __device__ __forceinline__ void odl_jac(const double (&y)[ODL_N], const double t
   J[3][2] = v18;
   J[3][3] = v28;
 }
-__device__ __forceinline__ void odl_dfdt(const double (&y)[ODL_N], const double t, const double (&p)[ODL_P], double (&ft)[ODL_N]) {
+template <class YV, class PV, class DV>
+__device__ __forceinline__ void odl_dfdt(const YV& y, const double t, const PV& p, DV& ft) {
   ft[0] = 0.0;
   ft[1] = 0.0;
   ft[2] = 0.0;
   ft[3] = 0.0;
 }
-__device__ __forceinline__ void odl_observe(const double (&y)[ODL_N], double (&out)[ODL_NOUT]) {
+template <class YV>
+__device__ __forceinline__ void odl_observe(const YV& y, double (&out)[ODL_NOUT]) {
   out[0] = __dadd_rn(__dadd_rn(y[0], y[1]), y[2]);
   out[1] = y[3];
 }

@@ -136,6 +136,7 @@ struct odl_model {
   CUfunction k_sweep_radau = nullptr, k_mcmc_radau = nullptr;
   CUfunction k_sweep_bdf = nullptr, k_mcmc_bdf = nullptr;
   CUfunction k_order_key = nullptr, k_order_scan = nullptr, k_order_scatter = nullptr;
+  CUfunction k_sweep_coop = nullptr, k_mcmc_coop = nullptr;   // n > 8 only: several lanes per system
   Tables data, grid;
   DevBuf counter;
   DevBuf scratch[16];
@@ -271,7 +272,8 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
       {"odl_mcmc_auto_kernel", &m->k_mcmc_auto, true}, {"odl_sweep_radau5_kernel", &m->k_sweep_radau, true},
       {"odl_mcmc_radau5_kernel", &m->k_mcmc_radau, true}, {"odl_sweep_bdf_kernel", &m->k_sweep_bdf, true},
       {"odl_mcmc_bdf_kernel", &m->k_mcmc_bdf, true}, {"odl_order_key_kernel", &m->k_order_key, true},
-      {"odl_order_scan_kernel", &m->k_order_scan, true}, {"odl_order_scatter_kernel", &m->k_order_scatter, true}};
+      {"odl_order_scan_kernel", &m->k_order_scan, true}, {"odl_order_scatter_kernel", &m->k_order_scatter, true},
+      {"odl_sweep_coop_kernel", &m->k_sweep_coop, m->n_state > 8}, {"odl_mcmc_coop_kernel", &m->k_mcmc_coop, m->n_state > 8}};
   for (auto& k : ks) {
     CUresult r = g_drv.ModuleGetFunction(k.fn, m->mod, k.name);
     if (r != CUDA_SUCCESS) {
@@ -321,6 +323,8 @@ static CUfunction kernel_by_name(const odl_model* m, const char* k) {
   if (!strcmp(k, "mcmc_auto")) return m->k_mcmc_auto;
   if (!strcmp(k, "sweep_radau5")) return m->k_sweep_radau;
   if (!strcmp(k, "mcmc_radau5")) return m->k_mcmc_radau;
+  if (!strcmp(k, "sweep_coop")) return m->k_sweep_coop;
+  if (!strcmp(k, "mcmc_coop")) return m->k_mcmc_coop;
   if (!strcmp(k, "sweep_bdf")) return m->k_sweep_bdf;
   if (!strcmp(k, "mcmc_bdf")) return m->k_mcmc_bdf;
   return nullptr;
@@ -332,6 +336,15 @@ static unsigned pick_block(const OdlData& d, int preferred) {
   int b = preferred;
   while (b > 32 && smem_bytes(d, b) > 100 * 1024) b /= 2;
   return (unsigned)b;
+}
+// cooperative kernels (n > 8): lanes per system as in odl_kernels.cuh (ODL_G), CTA size, shared memory
+static int coop_lanes(int n_state) { return n_state <= 16 ? 4 : (n_state <= 64 ? 8 : (n_state <= 128 ? 16 : 32)); }
+static const unsigned kCoopBlock = 128;
+static size_t coop_smem_bytes(const odl_model* m, const OdlData& d) {
+  const size_t groups = kCoopBlock / coop_lanes(m->n_state);
+  size_t doubles = (size_t)d.n_slot + 3 * (size_t)d.n_obs + ((size_t)d.n_obs + 1) / 2 +
+                   groups * ((size_t)m->n_state + m->n_param + d.stage_stride);
+  return doubles * sizeof(double);
 }
 static size_t smem_bytes(const OdlData& d, int block) {
   size_t doubles = (size_t)d.n_slot + 3 * (size_t)d.n_obs + ((size_t)d.n_obs + 1) / 2 + (size_t)block * d.stage_stride;
@@ -533,6 +546,19 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     void* params[] = {&Dl, &Ol, &Al};
     return launch(m, f, grid, block, smem, sx, params);
   };
+  auto go_coop = [&](cudaStream_t sx, const OdlOpts& Ox, const OdlSweepArgs& Ax, long long items) -> int {
+    const size_t smem = coop_smem_bytes(m, D);
+    if (smem > 227 * 1024) return fail(ODL_ECUDA, "cooperative sweep kernel: tables + staging exceed shared memory");
+    if (smem > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(m->k_sweep_coop, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+    int per_sm = 0;
+    ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->k_sweep_coop, (int)kCoopBlock, smem));
+    if (per_sm < 1) return fail(ODL_ECUDA, "cooperative sweep kernel does not fit on an SM");
+    const long long groups = kCoopBlock / coop_lanes(m->n_state);
+    unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((items + groups - 1) / groups, (long long)per_sm * m->sm_count));
+    OdlData Dl = D; OdlOpts Ol = Ox; OdlSweepArgs Al = Ax;
+    void* params[] = {&Dl, &Ol, &Al};
+    return launch(m, m->k_sweep_coop, grid, kCoopBlock, smem, sx, params);
+  };
   ODL_CUDA(cudaEventRecord(m->ev0, s));
   m->n_pass = 1;
   if (solver != ODL_SOLVER_AUTO) {
@@ -540,7 +566,9 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     const bool warp_cta = solver == ODL_SOLVER_RADAU5 || solver == ODL_SOLVER_BDF;   // compiled for one warp per CTA
     CUfunction f1 = solver == ODL_SOLVER_ROS23 ? m->k_sweep_ros : (solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau :
                     (solver == ODL_SOLVER_BDF ? m->k_sweep_bdf : m->k_sweep));
-    if ((rc = go(s, f1, O, A, warp_cta ? 32u : pick_block(D, m->block), n))) return rc;
+    if (solver == ODL_SOLVER_DOPRI5 && m->k_sweep_coop && !O.stiff_check && O.early_check_steps == 0) {
+      if ((rc = go_coop(s, O, A, n))) return rc;               // n > 8: several lanes per system
+    } else if ((rc = go(s, f1, O, A, warp_cta ? 32u : pick_block(D, m->block), n))) return rc;
   } else {
     // Cost-ordered bulk pass, then the stiff pass (no host synchronisation; list lengths stay on the device):
     //   order    key = |J(t0,y0,theta)|_inf (t_end-t0) per system, quarter-octave bins, highest first -> index[]
@@ -568,7 +596,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     int* feed = static_cast<int*>(bfeed.p);
     const int flags = so ? so->auto_flags : 0;
     const bool ordered = !(flags & ODL_AUTO_UNORDERED);
-    const bool concurrent = (flags & ODL_AUTO_CONCURRENT) != 0;
+    const bool concurrent = (flags & ODL_AUTO_CONCURRENT) != 0 && !m->k_sweep_coop;
     const int cap0 = so && so->pass_cap0 > 0 ? so->pass_cap0 : 512;
     CUfunction k_tail = tail_solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau : m->k_sweep_bdf;
     // counter block (zeroed above): [0] bulk work counter, [64] feed count, [128] feed ticket, [192] warps entered,
@@ -647,7 +675,8 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       ODL_CUDA(cudaEventRecord(m->evp[0], s));
       ODL_CUDA(cudaStreamWaitEvent(s, m->ev_aux, 0));
     } else {
-      if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc;
+      if (m->k_sweep_coop) { if ((rc = go_coop(s, O0, A0, n))) return rc; }      // n > 8: several lanes per system
+      else if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc;
       ODL_CUDA(cudaEventRecord(m->evp[0], s));
       if ((rc = launch(m, k_tail, grid_t, 32, smem_t, s, pt))) return rc;
     }
@@ -761,6 +790,21 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   if (warp_cta) block = 32;
   const size_t smem = smem_bytes(D, (int)block);
   unsigned grid = (unsigned)((threads + block - 1) / block);
+  if (solver == ODL_SOLVER_DOPRI5 && m->k_mcmc_coop && mo->speculate <= 0) {
+    // n > 8: one chain per group of lanes (odl_mcmc_coop_kernel); the chain is the same chain as with every other mapping
+    const size_t smem_c = coop_smem_bytes(m, D);
+    if (smem_c > 227 * 1024) return fail(ODL_ECUDA, "cooperative MCMC kernel: tables + staging exceed shared memory");
+    if (smem_c > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(m->k_mcmc_coop, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem_c));
+    const long long lanes = (long long)C * coop_lanes(m->n_state);
+    A.spec = 1;
+    ODL_CUDA(cudaEventRecord(m->ev0, s));
+    void* params_c[] = {&D, &O, &A};
+    m->n_pass = 1;
+    if ((rc = launch(m, m->k_mcmc_coop, (unsigned)((lanes + kCoopBlock - 1) / kCoopBlock), kCoopBlock, smem_c, s, params_c))) return rc;
+    ODL_CUDA(cudaEventRecord(m->ev1, s));
+    m->timed = true;
+    return st.finish();
+  }
   CUfunction f = (solver == ODL_SOLVER_DOPRI5) ? m->k_mcmc : (solver == ODL_SOLVER_ROS23 ? m->k_mcmc_ros :
                  (solver == ODL_SOLVER_RADAU5 ? m->k_mcmc_radau : (solver == ODL_SOLVER_BDF ? m->k_mcmc_bdf : m->k_mcmc_auto)));
   if (solver == ODL_SOLVER_AUTO) O.stiff_check = 1;

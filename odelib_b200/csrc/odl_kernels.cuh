@@ -1884,4 +1884,433 @@ extern "C" __global__ void __launch_bounds__(32, 1)
 odl_mcmc_radau5_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<3>(D, O, A); }
 extern "C" __global__ void __launch_bounds__(32, 1)
 odl_mcmc_bdf_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<4>(D, O, A); }
+// ================================================================================================
+// Cooperative kernels for larger systems (n > 8): ODL_G lanes per system.
+//
+// Thread-per-system keeps y, the seven stage derivatives and the parameters in registers; beyond n = 8 that is
+// no longer possible and the arrays fall into local memory (35 states: 6 KB per thread, 200 KB per warp -- one warp
+// fills an SM's L1 and every access of the second warp goes to L2).  Here a system is spread over ODL_G lanes:
+// lane `sub` owns components sub, sub+G, sub+2G, ... (ODL_C per lane) of the state and of every stage -- static
+// register indices again -- and the stage combinations, the error norm and the dense output are sliced the same
+// way.  The right-hand side couples everything, so the slice owners publish the stage state to a per-system row in
+// shared memory and EVERY lane evaluates the full traced RHS from it, keeping only its own components (the
+// assignments to other components fold away after inlining, the arithmetic feeding them mostly does not): the lanes
+// of a group run one instruction stream, no divergence, no per-lane code.  Parameters sit in shared memory too.
+// Groups are independent: every collective below uses the group's own lane mask.
+// ================================================================================================
+#if !ODL_SMALL
+#ifndef ODL_G
+#define ODL_G (ODL_N <= 16 ? 4 : (ODL_N <= 64 ? 8 : (ODL_N <= 128 ? 16 : 32)))
+#endif
+#define ODL_C ((ODL_N + ODL_G - 1) / ODL_G)
+#ifndef ODL_COOP_BLOCK
+#define ODL_COOP_BLOCK 128
+#endif
+#ifndef ODL_COOP_MINBLOCKS
+#define ODL_COOP_MINBLOCKS 2
+#endif
+
+struct OdlSmemView {             // y[i] / p[i] of the traced code -> shared memory
+  const double* b;
+  __device__ __forceinline__ double operator[](int i) const { return b[i]; }
+};
+struct OdlSliceOut {             // dy[k] = v of the traced code: kept when component k is this lane's
+  double (&mine)[ODL_C];
+  int sub;
+  struct Ref {
+    OdlSliceOut& o; int k;
+    __device__ __forceinline__ void operator=(double v) { if ((k % ODL_G) == o.sub) o.mine[k / ODL_G] = v; }
+  };
+  __device__ __forceinline__ Ref operator[](int k) { return Ref{*this, k}; }
+};
+struct OdlGroup {                // this lane's place in its group and the group's scratch rows
+  int sub;                       // 0 .. ODL_G-1
+  unsigned mask;                 // lanes of the group
+  double* ysm;                   // [ODL_N]  stage state published for the RHS / the observation sums
+  double* psm;                   // [ODL_P]  parameters of the group's system
+  double* stage;                 // [stage_stride] predictions at the observation slots
+};
+__device__ __forceinline__ double odl_group_sum(double v, unsigned mask) {
+#pragma unroll
+  for (int m = ODL_G >> 1; m > 0; m >>= 1) {
+    const int lo = __shfl_xor_sync(mask, __double2loint(v), m), hi = __shfl_xor_sync(mask, __double2hiint(v), m);
+    v += __hiloint2double(hi, lo);
+  }
+  return v;
+}
+// f = rhs(t, state published from the lanes' slices `yl`), slice of this lane
+__device__ __forceinline__ void odl_coop_rhs(const double (&yl)[ODL_C], double t, const OdlGroup& G, double (&f)[ODL_C]) {
+#pragma unroll
+  for (int c = 0; c < ODL_C; ++c) { const int i = G.sub + c * ODL_G; if (i < ODL_N) G.ysm[i] = yl[c]; f[c] = 0.0; }
+  __syncwarp(G.mask);
+  const OdlSmemView yv{G.ysm}, pv{G.psm};
+  OdlSliceOut out{f, G.sub};
+  odl_rhs(yv, t, pv, out);
+  __syncwarp(G.mask);            // every lane has read the row before it is published again
+}
+
+struct OdlCoopStepper {
+  double y[ODL_C], k1[ODL_C];
+  double t, h, tend;
+  float facold;
+  int nsteps, slot, status;
+  bool last_rejected;
+};
+
+// observation columns of the state slices `yi` at `slot` -> the group's staging row (lane 0 writes)
+__device__ __forceinline__ void odl_coop_emit(const double (&yi)[ODL_C], int slot, const OdlGroup& G) {
+#pragma unroll
+  for (int c = 0; c < ODL_C; ++c) { const int i = G.sub + c * ODL_G; if (i < ODL_N) G.ysm[i] = yi[c]; }
+  __syncwarp(G.mask);
+  if (G.sub == 0) {
+    const OdlSmemView yv{G.ysm};
+    double out[ODL_NOUT];
+    odl_observe(yv, out);
+#pragma unroll
+    for (int c = 0; c < ODL_NOUT; ++c) G.stage[slot * ODL_NOUT + c] = out[c];
+  }
+  __syncwarp(G.mask);
+}
+
+__device__ __forceinline__ void odl_coop_init(OdlCoopStepper& st, const OdlGroup& G, const OdlData& D, const OdlOpts& O) {
+#pragma unroll
+  for (int c = 0; c < ODL_C; ++c) {
+    const int i = G.sub + c * ODL_G;
+    double v = 0.0;
+    if (i < ODL_N) {
+      v = D.y0[i];
+#if ODL_Y0P
+      const int src = D.y0_from_param[i];
+      if (src >= 0) v = G.psm[src];
+#endif
+    }
+    st.y[c] = v;
+  }
+  st.t = D.t0;
+  st.tend = D.slot_t[D.n_slot - 1];
+  st.nsteps = 0; st.slot = 0; st.status = ODL_OK;
+  st.facold = 1e-4f; st.last_rejected = false;
+  odl_coop_rhs(st.y, st.t, G, st.k1);
+  const double span = st.tend - st.t;
+  const double hmax = (O.hmax > 0.0) ? O.hmax : span;
+  double h = O.h0;
+  if (!(h > 0.0)) {
+    // Hairer's hinit, norms summed over the group
+    double dnf = 0.0, dny = 0.0, rsk[ODL_C];
+#pragma unroll
+    for (int c = 0; c < ODL_C; ++c) {
+      rsk[c] = odl_rcp_approx(O.atol + O.rtol * fabs(st.y[c]));
+      const double a = st.k1[c] * rsk[c], b = st.y[c] * rsk[c];
+      dnf += a * a; dny += b * b;
+    }
+    const float fnf = (float)odl_group_sum(dnf, G.mask), fny = (float)odl_group_sum(dny, G.mask);
+    const float hf = (fnf <= 1e-10f || fny <= 1e-10f) ? 1e-6f : 0.01f * sqrtf(fny * __frcp_rn(fnf));
+    h = fmin((double)hf, hmax);
+    double y1[ODL_C], f1[ODL_C];
+#pragma unroll
+    for (int c = 0; c < ODL_C; ++c) y1[c] = st.y[c] + h * st.k1[c];
+    odl_coop_rhs(y1, st.t + h, G, f1);
+    double d2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < ODL_C; ++c) { const double a = (f1[c] - st.k1[c]) * rsk[c]; d2 += a * a; }
+    const float der2 = sqrtf((float)odl_group_sum(d2, G.mask)) * __frcp_rn((float)h);
+    const float der12 = fmaxf(der2, sqrtf(fnf));
+    const float h1 = (der12 <= 1e-15f) ? fmaxf(1e-6f, (float)h * 1e-3f) : __powf(0.01f * __frcp_rn(der12), 0.2f);
+    h = fmin(fmin(100.0 * h, (double)h1), hmax);
+  }
+  if (!(h > 0.0) || !odl_finite(h)) h = 1e-6 * (span > 0.0 ? span : 1.0);
+  st.h = h;
+  // slots at (or before) the start time take the initial state
+  while (st.slot < D.n_slot && D.slot_t[st.slot] <= st.t) { odl_coop_emit(st.y, st.slot, G); ++st.slot; }
+}
+
+// One DOPRI5 step attempt of a group; the same arithmetic as odl_dopri5_attempt, sliced.  Control flow is uniform
+// inside the group (every decision comes from group-reduced numbers).
+__device__ __forceinline__ void odl_coop_attempt(OdlCoopStepper& st, const OdlGroup& G, const OdlShared& S, const OdlData& D,
+                                                 const OdlOpts& O) {
+  const double t = st.t;
+  double h = st.h;
+  bool last = false;
+  if ((t + 1.01 * h - st.tend) > 0.0) { h = st.tend - t; last = true; }
+  ++st.nsteps;
+  double k2[ODL_C], k3[ODL_C], k4[ODL_C], k5[ODL_C], k6[ODL_C], k7[ODL_C], yt[ODL_C], yn[ODL_C];
+#pragma unroll
+  for (int i = 0; i < ODL_C; ++i) yt[i] = st.y[i] + h * (ODL_T(0) * st.k1[i]);
+  odl_coop_rhs(yt, t + ODL_T(0) * h, G, k2);
+#pragma unroll
+  for (int i = 0; i < ODL_C; ++i) yt[i] = st.y[i] + h * (ODL_T(1) * st.k1[i] + ODL_T(2) * k2[i]);
+  odl_coop_rhs(yt, t + ODL_T(32) * h, G, k3);
+#pragma unroll
+  for (int i = 0; i < ODL_C; ++i) yt[i] = st.y[i] + h * (ODL_T(3) * st.k1[i] + ODL_T(4) * k2[i] + ODL_T(5) * k3[i]);
+  odl_coop_rhs(yt, t + ODL_T(33) * h, G, k4);
+#pragma unroll
+  for (int i = 0; i < ODL_C; ++i)
+    yt[i] = st.y[i] + h * (ODL_T(6) * st.k1[i] + ODL_T(7) * k2[i] + ODL_T(8) * k3[i] + ODL_T(9) * k4[i]);
+  odl_coop_rhs(yt, t + ODL_T(34) * h, G, k5);
+#pragma unroll
+  for (int i = 0; i < ODL_C; ++i)
+    yt[i] = st.y[i] + h * (ODL_T(10) * st.k1[i] + ODL_T(11) * k2[i] + ODL_T(12) * k3[i] + ODL_T(13) * k4[i] +
+                           ODL_T(14) * k5[i]);
+  const double tph = t + h;
+  odl_coop_rhs(yt, tph, G, k6);
+#pragma unroll
+  for (int i = 0; i < ODL_C; ++i)
+    yn[i] = st.y[i] + h * (ODL_T(15) * st.k1[i] + ODL_T(16) * k3[i] + ODL_T(17) * k4[i] + ODL_T(18) * k5[i] +
+                           ODL_T(19) * k6[i]);
+  odl_coop_rhs(yn, tph, G, k7);
+  double errsq = 0.0, ysum = 0.0;
+  const double rtol_half = 0.5 * O.rtol;
+#pragma unroll
+  for (int i = 0; i < ODL_C; ++i) {
+    const double e = h * (ODL_T(20) * st.k1[i] + ODL_T(21) * k3[i] + ODL_T(22) * k4[i] + ODL_T(23) * k5[i] +
+                          ODL_T(24) * k6[i] + ODL_T(25) * k7[i]);
+    const double sk = O.atol + rtol_half * (fabs(st.y[i]) + fabs(yn[i]));     // padding components: e = 0
+    const double r = e * odl_rcp_approx(sk);
+    errsq += r * r;
+    ysum += fabs(yn[i]);
+  }
+  errsq = odl_group_sum(errsq, G.mask);
+  ysum = odl_group_sum(ysum, G.mask);
+  const bool finite_all = odl_finite(ysum);
+  const float err = odl_sqrt_approx((float)errsq * (1.0f / ODL_N));
+  const float lg_err = __log2f(err);
+  if (err <= 1.0f && finite_all) {
+    const float inv = 0.9f * exp2f(0.04f * __log2f(st.facold) - (0.2f - 0.04f * 0.75f) * lg_err);
+    double hnew = h * (double)fminf(10.0f, fmaxf(0.2f, inv));
+    if (!(err > 0.f)) hnew = h * 10.0;
+    st.facold = fmaxf(err, 1e-4f);
+    const double tnew = last ? st.tend : tph;
+    if (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew) {
+      double rc2[ODL_C], rc3[ODL_C], rc4[ODL_C], rc5[ODL_C];
+#pragma unroll
+      for (int i = 0; i < ODL_C; ++i) {
+        rc2[i] = yn[i] - st.y[i];
+        rc3[i] = h * st.k1[i] - rc2[i];
+        rc4[i] = rc2[i] - h * k7[i] - rc3[i];
+        rc5[i] = h * (ODL_T(26) * st.k1[i] + ODL_T(27) * k3[i] + ODL_T(28) * k4[i] + ODL_T(29) * k5[i] +
+                      ODL_T(30) * k6[i] + ODL_T(31) * k7[i]);
+      }
+      const double rh = 1.0 / h;
+      do {
+        const double th = (S.slot_t[st.slot] - t) * rh, th1 = 1.0 - th;
+        double yi[ODL_C];
+#pragma unroll
+        for (int i = 0; i < ODL_C; ++i) yi[i] = st.y[i] + th * (rc2[i] + th1 * (rc3[i] + th * (rc4[i] + th1 * rc5[i])));
+        odl_coop_emit(yi, st.slot, G);
+        ++st.slot;
+      } while (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew);
+    }
+#pragma unroll
+    for (int i = 0; i < ODL_C; ++i) { st.y[i] = yn[i]; st.k1[i] = k7[i]; }
+    st.t = tnew;
+    if (st.last_rejected) hnew = fmin(hnew, h);
+    st.last_rejected = false;
+    st.h = hnew;
+  } else {
+    double hnew;
+    if (err == err && finite_all && err < 3.0e38f)
+      hnew = h * (double)fmaxf(0.2f, 0.9f * exp2f(-(0.2f - 0.04f * 0.75f) * lg_err));
+    else hnew = 0.2 * h;
+    st.last_rejected = true;
+    st.h = hnew;
+    if (!(fabs(hnew) > 4.0 * 2.220446049250313e-16 * fmax(fabs(t), fabs(st.tend)))) st.status = ODL_HUNDERFLOW;
+  }
+  if (st.nsteps >= O.max_steps && st.slot < D.n_slot && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
+}
+
+// chi / R^2 of the group's staging row: the group's lanes share the observation rows (stats.py:41, :49-56)
+__device__ __forceinline__ void odl_coop_score(const OdlShared& S, const OdlData& D, const OdlGroup& G, double* pred_out,
+                                               double& chi, double& ssres, int& nvalid) {
+  double c = 0.0, s = 0.0, k = 0.0;
+  for (int o = G.sub; o < D.n_obs; o += ODL_G) {
+    const double pred = G.stage[S.src[o]];
+    if (pred_out) pred_out[o] = pred;
+    const double d = __dadd_rn(S.lnO[o], -log(pred));
+    const double dd = __dmul_rn(d, d);
+    const double den = S.denom[o];
+    const double term = dd / den;
+    const bool ok = odl_finite(dd) && odl_finite(term) && !(fabs(dd) * ODL_DBL_MIN >= fabs(den));
+    if (ok) { c += term; k += 1.0; }
+    const double r = __dadd_rn(pred, -S.lin[o]);
+    const double rr = __dmul_rn(r, r);
+    if (rr == rr) s += rr;
+  }
+  chi = odl_group_sum(c, G.mask);
+  ssres = odl_group_sum(s, G.mask);
+  nvalid = (int)odl_group_sum(k, G.mask);
+}
+
+__device__ __forceinline__ OdlGroup odl_coop_group(const OdlShared& S, const OdlData& D) {
+  // shared memory after the tables: per group  ysm[ODL_N] | psm[ODL_P] | stage[stage_stride]
+  const int lane = threadIdx.x & 31;
+  OdlGroup G;
+  G.sub = lane & (ODL_G - 1);
+  G.mask = (ODL_G == 32) ? 0xffffffffu : (((1u << ODL_G) - 1u) << (lane & ~(ODL_G - 1)));
+  const int group = threadIdx.x / ODL_G;
+  double* base = S.stage + (size_t)group * (ODL_N + ODL_P + D.stage_stride);
+  G.ysm = base; G.psm = base + ODL_N; G.stage = base + ODL_N + ODL_P;
+  return G;
+}
+
+// ---- forward sweep, one group per system at a time, work counter refill ----
+extern "C" __global__ void __launch_bounds__(ODL_COOP_BLOCK, ODL_COOP_MINBLOCKS)
+odl_sweep_coop_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
+  extern __shared__ double odl_smem[];
+  const OdlShared S = odl_carve(odl_smem, D);
+  odl_load_tables(S, D);
+  const OdlGroup G = odl_coop_group(S, D);
+  const long long n = A.index_count ? (long long)(*A.index_count) : A.n;
+  OdlCoopStepper st;
+  if (A.prod_started && (threadIdx.x & 31) == 0) atomicAdd(A.prod_started, 1);
+  for (;;) {
+    long long sys = 0;
+    if (G.sub == 0) sys = (long long)atomicAdd(A.counter, 1ull);
+    sys = ((long long)__shfl_sync(G.mask, (int)(sys >> 32), 0, ODL_G) << 32) | (unsigned int)__shfl_sync(G.mask, (int)(sys & 0xffffffffLL), 0, ODL_G);
+    if (sys >= n) break;
+    const long long row = A.index ? (long long)A.index[sys] : sys;
+    for (int q = G.sub; q < ODL_P; q += ODL_G) G.psm[q] = A.theta[row * ODL_P + q];
+    __syncwarp(G.mask);
+    odl_coop_init(st, G, D, O);
+    while (st.slot < D.n_slot && st.status == ODL_OK) odl_coop_attempt(st, G, S, D, O);
+    double chi, ss; int nv;
+    double* pred_out = (A.pred && st.status == ODL_OK) ? A.pred + row * D.n_obs : nullptr;
+    odl_coop_score(S, D, G, pred_out, chi, ss, nv);
+    if (G.sub == 0) {
+      int status = st.status;
+      double r2 = 1.0 - ss / D.sstot;
+      if (status != ODL_OK) { chi = __longlong_as_double(0x7ff8000000000000LL); r2 = chi; }
+      else if (nv == 0) { chi = __longlong_as_double(0x7ff8000000000000LL); status |= ODL_ALLMASKED; }
+      A.chi[row] = chi; A.r2[row] = r2; A.status[row] = status; A.nsteps[row] = st.nsteps;
+      if (st.status == ODL_MAXSTEPS && A.defer_list[0]) A.defer_list[0][atomicAdd(A.defer_count[0], 1)] = (int)row;
+    }
+    __syncwarp(G.mask);
+  }
+  __syncwarp();
+  if (A.prod_exited) {
+    __threadfence();
+    if ((threadIdx.x & 31) == 0) atomicAdd(A.prod_exited, 1);
+  }
+}
+
+// ---- Metropolis-Hastings, one group per chain (Samplers.py:53-174); same outputs as odl_mcmc_body ----
+__device__ __forceinline__ void odl_coop_propose(const OdlGroup& G, const OdlMcmcArgs& A, int chain, int it) {
+  const double* cur = A.theta_cur + (size_t)chain * ODL_P;
+  const long long k = (long long)chain * A.n_iter_total + (it - 1);
+  if (A.rng_mode == 2) {
+    for (int q = G.sub; q < ODL_P; q += ODL_G) G.psm[q] = A.forced[k * ODL_P + q];
+    __syncwarp(G.mask);
+    return;
+  }
+  for (int q = G.sub; q < ODL_P; q += ODL_G) G.psm[q] = cur[q];
+  __syncwarp(G.mask);
+  const unsigned long long gchain = (unsigned long long)(A.chain_offset + chain);
+  for (int j = G.sub; j < A.n_walk; j += ODL_G) {
+    double z;
+    if (A.rng_mode == 1) {
+      z = A.z[k * A.n_walk + j];
+    } else {
+      const OdlPhilox r = odl_philox((unsigned int)it, (unsigned int)(1 + (j >> 1)), (unsigned int)gchain,
+                                     (unsigned int)(gchain >> 32), (unsigned int)A.seed, (unsigned int)(A.seed >> 32));
+      const double u1 = 1.0 - odl_u53(r.x, r.y);
+      const double u2 = odl_u53(r.z, r.w);
+      const double rad = sqrt(-2.0 * log(u1));
+      double sn, cs;
+      sincospi(2.0 * u2, &sn, &cs);
+      z = A.step_sd * (rad * ((j & 1) ? sn : cs));
+    }
+    const int q = A.walk[j];
+    G.psm[q] = exp(log(cur[q]) + z);
+  }
+  __syncwarp(G.mask);
+}
+
+extern "C" __global__ void __launch_bounds__(ODL_COOP_BLOCK, ODL_COOP_MINBLOCKS)
+odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
+  extern __shared__ double odl_smem[];
+  const OdlShared S = odl_carve(odl_smem, D);
+  odl_load_tables(S, D);
+  const OdlGroup G = odl_coop_group(S, D);
+  const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int chain = (int)(gthread / ODL_G);
+  if (gthread / ODL_G >= (long long)A.n_chain) return;             // whole groups leave together
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double* cs = A.chain_state + (size_t)chain * ODL_CHAIN_STATE;
+  double* cur = A.theta_cur + (size_t)chain * ODL_P;
+  OdlCoopStepper st;
+  bool apriori = A.it_begin == 1;
+  int it = A.it_begin;
+  while (apriori || it < A.it_end) {
+    if (apriori) {
+      for (int q = G.sub; q < ODL_P; q += ODL_G) G.psm[q] = cur[q];
+      __syncwarp(G.mask);
+    } else {
+      odl_coop_propose(G, A, chain, it);
+    }
+    odl_coop_init(st, G, D, O);
+    while (st.slot < D.n_slot && st.status == ODL_OK) odl_coop_attempt(st, G, S, D, O);
+    double chi, ss; int nv;
+    odl_coop_score(S, D, G, nullptr, chi, ss, nv);
+    double my_chi = nan, my_r2 = nan;
+    if (st.status == ODL_OK) { my_chi = (nv > 0) ? chi : nan; my_r2 = 1.0 - ss / D.sstot; }
+    if (G.sub == 0) {
+      if (A.step_count) A.step_count[chain] += st.nsteps;
+      if (A.fail_count && st.status != ODL_OK) A.fail_count[chain] += 1;
+    }
+    if (apriori) {
+      if (G.sub == 0) { cs[0] = my_chi; cs[1] = my_r2; }
+      apriori = false;
+      __syncwarp(G.mask);
+      continue;
+    }
+    const double chi_cur = cs[0], r2_cur = cs[1];
+    const int accepts = (int)cs[2];
+    const double u = odl_mh_uniform(A, chain, it);
+    const bool accept = exp(chi_cur - my_chi) > u;                 // Samplers.py:124-127 (NaN rejects)
+    __syncwarp(G.mask);                                            // everyone has read the state
+    if (G.sub == 0) {
+      const long long k = (long long)chain * A.n_iter_total + (it - 1);
+      if (A.trace_chinew) A.trace_chinew[k] = my_chi;
+      if (A.trace_accept) A.trace_accept[k] = accept ? 1 : 0;
+      const double c = accept ? my_chi : chi_cur, r = accept ? my_r2 : r2_cur;
+      const int acc_n = accepts + (accept ? 1 : 0);
+      if (accept) {
+        cs[0] = my_chi; cs[1] = my_r2; cs[2] = (double)acc_n;
+        for (int q = 0; q < ODL_P; ++q) cur[q] = G.psm[q];
+      }
+      if (it > A.burnin) {
+        const int rowi = it - A.burnin - 1;
+        if (A.samples && rowi < A.n_keep) {
+          double* rowp = A.samples + ((size_t)chain * A.n_keep + rowi) * A.row_stride;
+          for (int q = 0; q < ODL_P; ++q) rowp[q] = cur[q];
+          rowp[ODL_P + 0] = c; rowp[ODL_P + 1] = r;
+          rowp[ODL_P + 2] = 2.0 * c + 2.0 * (double)A.pnum;
+          rowp[ODL_P + 3] = (double)it;
+          rowp[ODL_P + 4] = (double)acc_n / (double)it;
+        }
+        if (A.summaries) {
+          double* sm = A.summaries + (size_t)chain * (1 + 2 * ODL_P);
+          const double cnt = sm[0] + 1.0;
+          sm[0] = cnt;
+          for (int q = 0; q < ODL_P; ++q) {
+            const double x = log(cur[q]);
+            const double dlt = x - sm[1 + q];
+            const double mean = sm[1 + q] + dlt / cnt;
+            sm[1 + q] = mean;
+            sm[1 + ODL_P + q] += dlt * (x - mean);
+          }
+        }
+        // best kept row: the first kept row carries the current point, afterwards only acceptances can improve it
+        const double best_chi = cs[3], best_it = cs[4];
+        const bool first_kept = (it == A.burnin + 1);
+        if (first_kept || (accept && (c < best_chi || (best_chi != best_chi && c == c) || best_it == 0.0))) {
+          cs[3] = c; cs[4] = (double)it;
+          if (A.best_theta) for (int q = 0; q < ODL_P; ++q) A.best_theta[(size_t)chain * ODL_P + q] = cur[q];
+        }
+      }
+    }
+    ++it;
+    __syncwarp(G.mask);
+  }
+}
+#endif  // !ODL_SMALL
 #endif  // ODL_HOST_HARNESS

@@ -417,29 +417,33 @@ class TracedModel:
         L.append(f"#define ODL_NOUT {len(groups)}")
         L.append(f"#define ODL_RHS_FLOPS {self.flops()}")
         L.append(f"#define ODL_AUTONOMOUS {1 if self.autonomous else 0}")
-        L.append("__device__ __forceinline__ void odl_rhs(const double (&y)[ODL_N], const double t, "
-                 "const double (&p)[ODL_P], double (&dy)[ODL_N]) {")
+        # vector arguments are template parameters: plain register arrays for thread-per-system kernels, shared-memory
+        # views / slice-keeping output proxies for the cooperative (several lanes per system) kernels
+        L.append("template <class YV, class PV, class DV>")
+        L.append("__device__ __forceinline__ void odl_rhs(const YV& y, const double t, const PV& p, DV& dy) {")
         names = self._emit(self.outputs, L, fmad)
         for k, o in enumerate(self.outputs):
             L.append(f"  dy[{k}] = {names[o]};")
         L.append("}")
         # Jacobian (dense n x n, row-major, structural zeros written as literal 0.0)
         J = self.jacobian()
-        L.append("__device__ __forceinline__ void odl_jac(const double (&y)[ODL_N], const double t, "
-                 "const double (&p)[ODL_P], double (&J)[ODL_N][ODL_N]) {")
+        L.append("template <class YV, class PV>")
+        L.append("__device__ __forceinline__ void odl_jac(const YV& y, const double t, const PV& p, "
+                 "double (&J)[ODL_N][ODL_N]) {")
         roots = [J[i][j] for i in range(n) for j in range(n)]
         names = self._emit(roots, L, True)
         for i in range(n):
             for j in range(n):
                 L.append(f"  J[{i}][{j}] = {names[J[i][j]]};")
         L.append("}")
-        L.append("__device__ __forceinline__ void odl_dfdt(const double (&y)[ODL_N], const double t, "
-                 "const double (&p)[ODL_P], double (&ft)[ODL_N]) {")
+        L.append("template <class YV, class PV, class DV>")
+        L.append("__device__ __forceinline__ void odl_dfdt(const YV& y, const double t, const PV& p, DV& ft) {")
         names = self._emit(self.dfdt(), L, True)
         for k, o in enumerate(self.dfdt()):
             L.append(f"  ft[{k}] = {names[o]};")
         L.append("}")
-        L.append("__device__ __forceinline__ void odl_observe(const double (&y)[ODL_N], double (&out)[ODL_NOUT]) {")
+        L.append("template <class YV>")
+        L.append("__device__ __forceinline__ void odl_observe(const YV& y, double (&out)[ODL_NOUT]) {")
         for c, grp in enumerate(groups):
             # numpy's .sum(axis=1) over <8 columns adds left to right
             expr = f"y[{grp[0]}]"

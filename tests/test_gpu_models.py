@@ -66,3 +66,48 @@ def test_five_by_five_network():
     res = dm.mcmc(theta[:32], nits=24, seed=3)
     assert np.isfinite(res["samples"]).all() and res["samples"].shape == (32, 11, P + 5)
     assert res["fail_count"].sum() == 0
+
+
+@pytest.mark.parametrize("which", ["n_class_10", "network_5x5"])
+def test_cooperative_mapping_agrees_with_thread_per_system(which):
+    """n > 8: the default kernels spread a system over several lanes (state slices in registers, RHS from a shared row);
+    asking for speculate=1 selects the thread-per-system kernel (arrays in local memory).  Same algorithm, different
+    summation order in the error norm: chi agrees to solver accuracy, decisions agree, the AUTO sweep agrees."""
+    rng = np.random.default_rng(7)
+    if which == "n_class_10":
+        rhs, names, sums, center, y0, orgs = nclass_problem(10)
+        P = 5
+    else:
+        rhs, n, P, groups = demo_models.network(5, 5)
+        H, V = 5, 5
+        names = [f"S{i}" for i in range(H)] + [f"I{i}{j}" for i in range(H) for j in range(V)] + [f"V{j}" for j in range(V)]
+        sums = {f"H{i}": [f"S{i}"] + [f"I{i}{j}" for j in range(V)] for i in range(H)}
+        r1 = np.random.default_rng(1)
+        center = np.concatenate([0.3 * np.exp(0.2 * r1.standard_normal(H)), 2e-8 * np.exp(0.5 * r1.standard_normal(H * V)),
+                                 20 * np.exp(0.1 * r1.standard_normal(V)), 2.0 * np.exp(0.2 * r1.standard_normal(V))])
+        y0 = [1e6 * (1 + i) for i in range(H)] + [0.0] * (H * V) + [2e6 * (1 + j) for j in range(V)]
+        orgs = [f"H{i}" for i in range(H)] + [f"V{j}" for j in range(V)]
+    dm, tab = synthetic_problem(rhs, names, sums, center, y0, orgs, seed=1)
+    assert dm.kernel_info("sweep_coop")["regs"] > 0
+    theta = center * np.exp(0.05 * rng.standard_normal((37, P)))          # ragged: 37 systems do not fill the groups
+    coop = dm.sweep(theta, rtol=1e-10, atol=1e-10, max_steps=2000000)
+    tps = dm.sweep(theta, rtol=1e-10, atol=1e-10, max_steps=2000000, stiff_check=True)   # stiff_check -> thread-per-system
+    assert np.all(coop["status"] == 0) and np.all(tps["status"] == 0)
+    np.testing.assert_allclose(coop["chi"], tps["chi"], rtol=1e-7)
+    # AUTO's bulk pass is the cooperative kernel (rows it finishes within its step cap carry exactly its numbers)
+    auto = dm.sweep(theta, solver="auto", max_steps=2000000)
+    plain = dm.sweep(theta, max_steps=512)
+    fin = plain["status"] == 0
+    assert fin.sum() >= 30 and np.all(auto["status"] == 0)
+    assert np.array_equal(auto["chi"][fin], plain["chi"][fin])
+    C, nits = 9, 40
+    a = dm.mcmc(theta[:C], nits=nits, seed=4, trace=True)
+    b = dm.mcmc(theta[:C], nits=nits, seed=4, trace=True, speculate=1)
+    np.testing.assert_allclose(a["chinew"], b["chinew"], rtol=2e-5)
+    assert (a["accepted"] != b["accepted"]).sum() <= 1
+    same = (a["accepted"] == b["accepted"]).all(axis=1)
+    np.testing.assert_allclose(a["samples"][same][:, :, :P], b["samples"][same][:, :, :P], rtol=1e-12)
+    assert np.array_equal(a["best_iteration"][same], b["best_iteration"][same])
+    np.testing.assert_allclose(a["summaries"][same], b["summaries"][same], rtol=1e-9, atol=1e-12)
+    seg = dm.mcmc(theta[:C], nits=nits, seed=4, trace=True, segments=3)
+    assert np.array_equal(seg["samples"], a["samples"]) and np.array_equal(seg["chain_state"], a["chain_state"])
