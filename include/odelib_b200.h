@@ -59,7 +59,9 @@ typedef struct odl_build_opts {
   int dense_output;    /* 1 = dense output at the observation times (default), 0 = land on them */
   int compile_only;    /* 1 = NVRTC-compile (and cache) but do not touch a GPU */
   int y0_from_param;   /* 1 = some state's initial value is a parameter ('<state>0', Samplers.py:110-114) */
-  int reserved[2];
+  int coop_lanes;      /* n_state > 8: lanes per system of the cooperative kernels (4, 8, 16 or 32);
+                          0 = by state count (4 up to 16 states, 8 up to 64, 16 up to 128, else 32) */
+  int reserved[1];
   const char* cache_dir; /* directory for compiled cubins, NULL = no cache */
 } odl_build_opts;
 

@@ -29,7 +29,7 @@ class OdlError(RuntimeError):
 
 class BuildOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("block_threads", C.c_int), ("min_blocks", C.c_int), ("dense_output", C.c_int),
-                ("compile_only", C.c_int), ("y0_from_param", C.c_int), ("reserved", C.c_int * 2),
+                ("compile_only", C.c_int), ("y0_from_param", C.c_int), ("coop_lanes", C.c_int), ("reserved", C.c_int * 1),
                 ("cache_dir", C.c_char_p)]
 
 

@@ -125,7 +125,7 @@ struct Tables {
 struct odl_model {
   int device = 0;
   int n_state = 0, n_param = 0, n_out = 0;
-  int block = 128, minblocks = 4, dense = 1, y0p = 0;
+  int block = 128, minblocks = 4, dense = 1, y0p = 0, coop = 0;
   int sm_count = 0;
   bool on_gpu = false;
   std::vector<char> cubin;
@@ -148,6 +148,9 @@ struct odl_model {
   bool timed = false;
 };
 
+// cooperative kernels (n > 8): default lanes per system, as odl_kernels.cuh's ODL_G
+static int coop_lanes_default(int n_state) { return n_state <= 16 ? 4 : (n_state <= 64 ? 8 : (n_state <= 128 ? 16 : 32)); }
+
 static uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
   const unsigned char* p = static_cast<const unsigned char*>(data);
   for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
@@ -159,6 +162,7 @@ static int compile_model(odl_model* m, const std::string& src, const char* cache
                                   "-DODL_BLOCK=" + std::to_string(m->block),
                                   "-DODL_MINBLOCKS=" + std::to_string(m->minblocks),
                                   "-DODL_DENSE=" + std::to_string(m->dense), "-DODL_Y0P=" + std::to_string(m->y0p)};
+  if (m->n_state > 8) opt.push_back("-DODL_G=" + std::to_string(m->coop));
   // tuning hook (development): extra -D options for the kernel source, e.g. ODL_KERNEL_DEFINES="-DODL_INNER=8"
   if (const char* extra = getenv("ODL_KERNEL_DEFINES")) {
     std::string e(extra);
@@ -248,10 +252,13 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
     if (opts->min_blocks > 0) m->minblocks = opts->min_blocks;
     m->dense = opts->dense_output ? 1 : 0;
     m->y0p = opts->y0_from_param ? 1 : 0;
+    m->coop = opts->coop_lanes;
     compile_only = opts->compile_only != 0;
     cache_dir = opts->cache_dir;
   }
   if (m->block % 32 || m->block > 1024) { delete m; return fail(ODL_EINVAL, "block_threads must be a multiple of 32, <= 1024"); }
+  if (m->coop == 0) m->coop = coop_lanes_default(n_state);
+  if (m->coop != 4 && m->coop != 8 && m->coop != 16 && m->coop != 32) { delete m; return fail(ODL_EINVAL, "coop_lanes must be 4, 8, 16 or 32"); }
   int rc = compile_model(m, model_cuda_src, cache_dir);
   if (rc) { delete m; return rc; }
   if (compile_only) { *out = m; return 0; }
@@ -338,10 +345,9 @@ static unsigned pick_block(const OdlData& d, int preferred) {
   return (unsigned)b;
 }
 // cooperative kernels (n > 8): lanes per system as in odl_kernels.cuh (ODL_G), CTA size, shared memory
-static int coop_lanes(int n_state) { return n_state <= 16 ? 4 : (n_state <= 64 ? 8 : (n_state <= 128 ? 16 : 32)); }
 static const unsigned kCoopBlock = 128;
 static size_t coop_smem_bytes(const odl_model* m, const OdlData& d) {
-  const size_t groups = kCoopBlock / coop_lanes(m->n_state);
+  const size_t groups = kCoopBlock / m->coop;
   size_t doubles = (size_t)d.n_slot + 3 * (size_t)d.n_obs + ((size_t)d.n_obs + 1) / 2 +
                    groups * ((size_t)m->n_state + m->n_param + d.stage_stride);
   return doubles * sizeof(double);
@@ -553,7 +559,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     int per_sm = 0;
     ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->k_sweep_coop, (int)kCoopBlock, smem));
     if (per_sm < 1) return fail(ODL_ECUDA, "cooperative sweep kernel does not fit on an SM");
-    const long long groups = kCoopBlock / coop_lanes(m->n_state);
+    const long long groups = kCoopBlock / m->coop;
     unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((items + groups - 1) / groups, (long long)per_sm * m->sm_count));
     OdlData Dl = D; OdlOpts Ol = Ox; OdlSweepArgs Al = Ax;
     void* params[] = {&Dl, &Ol, &Al};
@@ -795,7 +801,7 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
     const size_t smem_c = coop_smem_bytes(m, D);
     if (smem_c > 227 * 1024) return fail(ODL_ECUDA, "cooperative MCMC kernel: tables + staging exceed shared memory");
     if (smem_c > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(m->k_mcmc_coop, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem_c));
-    const long long lanes = (long long)C * coop_lanes(m->n_state);
+    const long long lanes = (long long)C * m->coop;
     A.spec = 1;
     ODL_CUDA(cudaEventRecord(m->ev0, s));
     void* params_c[] = {&D, &O, &A};

@@ -60,7 +60,8 @@ class ObsTables:
 
 class DeviceModel:
     def __init__(self, ode, n_state, n_param, observe_groups=None, device=None, block_threads=0, min_blocks=0,
-                 dense_output=True, fmad=True, compile_only=False, cache_dir=_capi.CACHE_DIR, y0_from_param=False):
+                 dense_output=True, fmad=True, compile_only=False, cache_dir=_capi.CACHE_DIR, y0_from_param=False,
+                 coop_lanes=0):
         self.traced = trace(ode, n_state, n_param)
         self.n_state, self.n_param = n_state, n_param
         self.groups = [tuple(g) for g in observe_groups] if observe_groups is not None else [(i,) for i in range(n_state)]
@@ -80,6 +81,7 @@ class DeviceModel:
         bo.dense_output = 1 if dense_output else 0
         bo.compile_only = 1 if compile_only else 0
         bo.y0_from_param = 1 if y0_from_param else 0
+        bo.coop_lanes = int(coop_lanes)
         bo.cache_dir = cache_dir.encode() if cache_dir else None
         h = C.c_void_p()
         _capi.check(L.odl_model_create(self.source.encode(), n_state, n_param, self.n_out, C.byref(bo), C.byref(h)))

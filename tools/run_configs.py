@@ -89,7 +89,7 @@ out["C2_forward_sweep"] = c2
 # ---- C3: N-class chain, 4096 chains ------------------------------------------------------------------------------
 c3 = {}
 nits = 300 if QUICK else 1000
-for N in ((2, 6) if QUICK else (1, 2, 4, 6, 8, 10)):
+for N in ((2, 6, 10) if QUICK else (1, 2, 4, 6, 8, 10)):
     if N == 1:
         dm, tab = device_model("one_i"); rhs = oracle_rhs("one_i")
         center = np.array([1.238e-08, 3.550e-08, 19.40, 1.835]); P = 4
@@ -103,7 +103,8 @@ for N in ((2, 6) if QUICK else (1, 2, 4, 6, 8, 10)):
     c3[f"N={N}"] = {"states": dm.n_state, "chains": 4096, "iterations": nits, "seconds": t,
                     "chain_steps_per_s": 4096 * (nits - 1) / t, "mean_integrator_steps_per_solve": steps / (4096 * nits),
                     "fp64_tflops": steps * flops_per_step(dm) / t / 1e12, "accept_rate": float(r["chain_state"][:, 2].mean().item()) / (nits - 1),
-                    "kernel": dm.kernel_info("mcmc"),
+                    "kernel": dm.kernel_info("mcmc_coop" if dm.n_state > 8 else "mcmc"),
+                    "mapping": "cooperative, lanes per system by state count" if dm.n_state > 8 else "thread per system, prefetching MH",
                     "cpu_oracle_solves_per_s_1core": cpu_rate(rhs, starts[:40].cpu().numpy(), tab)}
 out["C3_nclass_chains"] = c3
 
@@ -141,9 +142,9 @@ t, r = timed(lambda: dm.mcmc(starts, nits=its, rng_mode="philox", seed=1, device
 steps = float(r["step_count"].sum().item())
 out["C5_network_5x5"] = {"states": 35, "parameters": 40, "chains_per_gpu": C5, "iterations": its, "seconds": t,
                          "chain_steps_per_s": C5 * (its - 1) / t, "mean_integrator_steps_per_solve": steps / (C5 * its),
-                         "fp64_tflops": steps * flops_per_step(dm) / t / 1e12, "kernel": dm.kernel_info("mcmc"),
+                         "fp64_tflops": steps * flops_per_step(dm) / t / 1e12, "kernel": dm.kernel_info("mcmc_coop"),
                          "cpu_oracle_solves_per_s_1core": cpu_rate(rhs, starts[:20].cpu().numpy(), tab),
-                         "note": "thread-per-system with rolled loops / local memory (n > 8 path), prefetching MH; a sub-warp mapping is future work"}
+                         "note": "cooperative kernel: 8 lanes per system, state slices in registers, RHS from a shared row (DESIGN.md 4)"}
 
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
