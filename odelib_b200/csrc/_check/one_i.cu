@@ -3,7 +3,8 @@
 #define ODL_NOUT 2
 #define ODL_RHS_FLOPS 9
 #define ODL_AUTONOMOUS 1
-__device__ __forceinline__ void odl_rhs(const double (&y)[ODL_N], const double t, const double (&p)[ODL_P], double (&dy)[ODL_N]) {
+template <class YV, class PV, class DV>
+__device__ __forceinline__ void odl_rhs(const YV& y, const double t, const PV& p, DV& dy) {
   const double v8 = p[0] * y[0];
   const double v9 = p[1] * y[0];
   const double v10 = v9 * y[2];
@@ -17,7 +18,8 @@ __device__ __forceinline__ void odl_rhs(const double (&y)[ODL_N], const double t
   dy[1] = v13;
   dy[2] = v16;
 }
-__device__ __forceinline__ void odl_jac(const double (&y)[ODL_N], const double t, const double (&p)[ODL_P], double (&J)[ODL_N][ODL_N]) {
+template <class YV, class PV>
+__device__ __forceinline__ void odl_jac(const YV& y, const double t, const PV& p, double (&J)[ODL_N][ODL_N]) {
   const double v9 = p[1] * y[0];
   const double v14 = p[2] * p[3];
   const double v19 = p[1] * y[2];
@@ -35,12 +37,14 @@ __device__ __forceinline__ void odl_jac(const double (&y)[ODL_N], const double t
   J[2][1] = v14;
   J[2][2] = v23;
 }
-__device__ __forceinline__ void odl_dfdt(const double (&y)[ODL_N], const double t, const double (&p)[ODL_P], double (&ft)[ODL_N]) {
+template <class YV, class PV, class DV>
+__device__ __forceinline__ void odl_dfdt(const YV& y, const double t, const PV& p, DV& ft) {
   ft[0] = 0.0;
   ft[1] = 0.0;
   ft[2] = 0.0;
 }
-__device__ __forceinline__ void odl_observe(const double (&y)[ODL_N], double (&out)[ODL_NOUT]) {
+template <class YV>
+__device__ __forceinline__ void odl_observe(const YV& y, double (&out)[ODL_NOUT]) {
   out[0] = __dadd_rn(y[0], y[1]);
   out[1] = y[2];
 }

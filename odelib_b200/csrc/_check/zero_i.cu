@@ -3,7 +3,8 @@
 #define ODL_NOUT 2
 #define ODL_RHS_FLOPS 8
 #define ODL_AUTONOMOUS 1
-__device__ __forceinline__ void odl_rhs(const double (&y)[ODL_N], const double t, const double (&p)[ODL_P], double (&dy)[ODL_N]) {
+template <class YV, class PV, class DV>
+__device__ __forceinline__ void odl_rhs(const YV& y, const double t, const PV& p, DV& dy) {
   const double v6 = p[0] * y[0];
   const double v7 = p[1] * y[0];
   const double v8 = v7 * y[1];
@@ -15,7 +16,8 @@ __device__ __forceinline__ void odl_rhs(const double (&y)[ODL_N], const double t
   dy[0] = v9;
   dy[1] = v13;
 }
-__device__ __forceinline__ void odl_jac(const double (&y)[ODL_N], const double t, const double (&p)[ODL_P], double (&J)[ODL_N][ODL_N]) {
+template <class YV, class PV>
+__device__ __forceinline__ void odl_jac(const YV& y, const double t, const PV& p, double (&J)[ODL_N][ODL_N]) {
   const double v7 = p[1] * y[0];
   const double v10 = p[2] * p[1];
   const double v11 = v10 * y[0];
@@ -30,11 +32,13 @@ __device__ __forceinline__ void odl_jac(const double (&y)[ODL_N], const double t
   J[1][0] = v19;
   J[1][1] = v21;
 }
-__device__ __forceinline__ void odl_dfdt(const double (&y)[ODL_N], const double t, const double (&p)[ODL_P], double (&ft)[ODL_N]) {
+template <class YV, class PV, class DV>
+__device__ __forceinline__ void odl_dfdt(const YV& y, const double t, const PV& p, DV& ft) {
   ft[0] = 0.0;
   ft[1] = 0.0;
 }
-__device__ __forceinline__ void odl_observe(const double (&y)[ODL_N], double (&out)[ODL_NOUT]) {
+template <class YV>
+__device__ __forceinline__ void odl_observe(const YV& y, double (&out)[ODL_NOUT]) {
   out[0] = y[0];
   out[1] = y[1];
 }

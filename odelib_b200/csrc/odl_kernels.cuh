@@ -119,6 +119,7 @@ __device__ __forceinline__ OdlShared odl_carve(double* base, const OdlData& D) {
   return S;
 }
 #ifndef ODL_HOST_HARNESS
+extern __shared__ double odl_smem[];   // dynamic shared memory of every kernel: tables, then staging
 __device__ __forceinline__ void odl_load_tables(const OdlShared& S, const OdlData& D) {
   for (int i = threadIdx.x; i < D.n_slot; i += blockDim.x) S.slot_t[i] = D.slot_t[i];
   for (int i = threadIdx.x; i < D.n_obs; i += blockDim.x) {
@@ -1447,7 +1448,6 @@ odl_order_scatter_kernel(const OdlOrderArgs A) {
 // ------------------------------------------------------------------------------------------------
 template <int SOLVER>
 __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& O, const OdlSweepArgs& A) {
-  extern __shared__ double odl_smem[];
   const OdlShared S = odl_carve(odl_smem, D);
   odl_load_tables(S, D);
   const int lane = threadIdx.x & 31;
@@ -1596,7 +1596,6 @@ odl_sweep_bdf_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { o
 // ------------------------------------------------------------------------------------------------
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
 odl_traj_kernel(const OdlData D, const OdlOpts O, const OdlTrajArgs A) {
-  extern __shared__ double odl_smem[];
   OdlShared S;
   S.slot_t = odl_smem; S.lnO = S.denom = S.lin = nullptr; S.src = nullptr; S.stage = nullptr;
   for (int i = threadIdx.x; i < D.n_slot; i += blockDim.x) S.slot_t[i] = D.slot_t[i];
@@ -1681,7 +1680,6 @@ __device__ __forceinline__ double odl_mh_uniform(const OdlMcmcArgs& A, int chain
 // expected iterations consumed per round (1 - (1-a)^K)/a: 2.7 for K = 4, 3.5 for K = 8 at a = 0.26.
 template <int SOLVER>
 __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O, const OdlMcmcArgs& A) {
-  extern __shared__ double odl_smem[];
   const OdlShared S = odl_carve(odl_smem, D);
   odl_load_tables(S, D);
   const int lane = threadIdx.x & 31;
@@ -2155,7 +2153,6 @@ __device__ __forceinline__ OdlGroup odl_coop_group(const OdlShared& S, const Odl
 // ---- forward sweep, one group per system at a time, work counter refill ----
 extern "C" __global__ void __launch_bounds__(ODL_COOP_BLOCK, ODL_COOP_MINBLOCKS)
 odl_sweep_coop_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
-  extern __shared__ double odl_smem[];
   const OdlShared S = odl_carve(odl_smem, D);
   odl_load_tables(S, D);
   const OdlGroup G = odl_coop_group(S, D);
@@ -2226,7 +2223,6 @@ __device__ __forceinline__ void odl_coop_propose(const OdlGroup& G, const OdlMcm
 
 extern "C" __global__ void __launch_bounds__(ODL_COOP_BLOCK, ODL_COOP_MINBLOCKS)
 odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
-  extern __shared__ double odl_smem[];
   const OdlShared S = odl_carve(odl_smem, D);
   odl_load_tables(S, D);
   const OdlGroup G = odl_coop_group(S, D);

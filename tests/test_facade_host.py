@@ -118,3 +118,39 @@ def test_replicate_dataframe_format():
     assert m._samples == 6
     np.testing.assert_allclose(m._obs_logabundance["S"], [np.log([100., 200, 300]).mean() + np.log(1 + t) for t in (0, 1, 2)])
     assert list(m._pred_tindex["V"]) == [0, 10, 20]
+
+
+def test_pooled_log_stats_equal_rawstats_over_the_frame():
+    """f2: Welford summaries per chain -> pooled log-mean / log-std (ddof=1) == what rawstats takes from the
+    concatenated posterior frame (Framework.py:11-17)."""
+    from odelib_b200.Framework import _rawstats_from_logmoments, rawstats
+    from odelib_b200.rhat import pooled_log_stats
+    rng = np.random.default_rng(0)
+    C, n, P = 7, 41, 3
+    x = np.exp(rng.normal(size=(C, n, P)) * [0.1, 1.0, 3.0] + [0.0, -18.0, 3.0])
+    summ = np.zeros((C, 1 + 2 * P))
+    for c in range(C):                                           # the kernel's recurrence
+        for i in range(n):
+            summ[c, 0] += 1.0
+            lx = np.log(x[c, i])
+            d = lx - summ[c, 1:1 + P]
+            summ[c, 1:1 + P] += d / summ[c, 0]
+            summ[c, 1 + P:] += d * (lx - summ[c, 1:1 + P])
+    N, mean, std = pooled_log_stats(summ, P)
+    assert N == C * n
+    for q in range(P):
+        med, sd = rawstats(pd.Series(x[:, :, q].ravel()))
+        m2, s2 = _rawstats_from_logmoments(mean[q], std[q])
+        assert m2 == pytest.approx(med, rel=1e-12) and s2 == pytest.approx(sd, rel=1e-10)
+
+
+def test_chain_start_picks_are_what_dataframe_sample_draws():
+    """f1: `good.sample(n, replace=True)` (Framework.py:1012) == rows `np.random.choice(len(good), n, replace=True)`
+    of `good` under the same global numpy seed -- the device path needs only len(good) from the survey."""
+    good = pd.DataFrame({"a": np.arange(100.0, 163.0), "chi": np.linspace(1, 2, 63)}, index=np.arange(5, 68))
+    for seed in (0, 1, 12345):
+        np.random.seed(seed)
+        ref = good.sample(17, replace=True)["a"].to_numpy()
+        np.random.seed(seed)
+        picks = np.random.choice(len(good), size=17, replace=True)
+        assert np.array_equal(good["a"].to_numpy()[picks], ref)
