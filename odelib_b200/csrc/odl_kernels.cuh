@@ -42,6 +42,9 @@
 #ifndef ODL_INNER
 #define ODL_INNER 8
 #endif
+#ifndef ODL_MINBLOCKS_MCMC
+#define ODL_MINBLOCKS_MCMC ODL_MINBLOCKS
+#endif
 #ifndef ODL_MINBLOCKS_ROS
 #define ODL_MINBLOCKS_ROS (ODL_MINBLOCKS > 2 ? ODL_MINBLOCKS - 1 : ODL_MINBLOCKS)
 #endif
@@ -366,8 +369,9 @@ ODL_UNROLL
         num += a * a; den += b * b;
       }
       if (den > 0.0) {
-        const double hlamb = h * sqrt(num / den);
-        if (hlamb > 3.25) {
+        // h |lambda| ~ h sqrt(num/den) > 3.25, without the fp64 square root and division (the test runs on one step
+        // in ten of every lane, i.e. on most warp steps for one lane or another)
+        if (h * h * num > 10.5625 * den) {
           st.nonsti = 0;
           // stiff for 15 checks in a row AND still far from the end at this (stability-limited) step size:
           // hand the system to the Rosenbrock path; mildly stiff / nearly finished systems stay here
@@ -1461,7 +1465,15 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
   long long sys = -1;            // slot in the work list
   long long row = -1;            // row of theta / outputs
   bool active = false, done = false;
-  st.status = ODL_OK; st.nsteps = 0; st.slot = 0;
+  int fin_status = ODL_OK, fin_nsteps = 0;                       // of the system this lane finished (kept for (A))
+  // a defined state for lanes without a system: in the DOPRI5 kernel every lane runs the step code (see (C)), and a
+  // lane with slot == n_slot writes nothing
+  st.status = ODL_OK; st.nsteps = 0; st.slot = D.n_slot; st.iasti = 0; st.nonsti = 0;
+  st.t = 0.0; st.h = 0.0; st.tend = 0.0; st.facold = 1.f; st.last_rejected = false;
+ODL_UNROLL
+  for (int i = 0; i < ODL_N; ++i) { st.y[i] = 0.0; st.k1[i] = 0.0; }
+ODL_UNROLL
+  for (int q = 0; q < ODL_P; ++q) p[q] = 0.0;
 
   // first fetch.  O.lanes < 32 (latency-bound tail passes): only the first O.lanes lanes of a warp take systems, so
   // that the few long systems are spread over more warps -- a warp pays for the union of its lanes' branches.
@@ -1483,26 +1495,19 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
       m &= m - 1;
       const long long rowL = ((long long)__shfl_sync(ODL_FULL, (int)(row >> 32), L) << 32) |
                              (unsigned int)__shfl_sync(ODL_FULL, (int)(row & 0xffffffff), L);
-      const int statL = __shfl_sync(ODL_FULL, st.status, L);
+      const int statL = __shfl_sync(ODL_FULL, fin_status, L);
       double chi, ss; int nv;
       double* pred_out = (A.pred && statL == ODL_OK) ? A.pred + rowL * D.n_obs : nullptr;
       odl_score(S, D, S.stage + (size_t)((threadIdx.x & ~31) + L) * D.stage_stride, lane, pred_out, chi, ss, nv);
       if (lane == L) {
-        int status = st.status;
+        int status = fin_status;
         double r2 = 1.0 - ss / D.sstot;
         if (status != ODL_OK) { chi = __longlong_as_double(0x7ff8000000000000LL); r2 = chi; }
         else if (nv == 0) { chi = __longlong_as_double(0x7ff8000000000000LL); status |= ODL_ALLMASKED; }
         A.chi[row] = chi; A.r2[row] = r2; A.status[row] = status;
-        A.nsteps[row] = st.nsteps;
-        if (st.status == ODL_MAXSTEPS && A.defer_list[0]) {
-          int which = 0;
-          if (O.defer_split_steps > 0) {
-            const double projected = (double)st.nsteps * (st.tend - D.t0) / (st.t - D.t0);
-            if (!(projected <= (double)O.defer_split_steps)) which = 1;
-          }
-          A.defer_list[which][atomicAdd(A.defer_count[which], 1)] = (int)row;
-        }
-        if (st.status == ODL_STIFF && A.defer_list[1]) A.defer_list[1][atomicAdd(A.defer_count[1], 1)] = (int)row;
+        A.nsteps[row] = fin_nsteps;
+        if (fin_status == ODL_MAXSTEPS && A.defer_list[0]) A.defer_list[0][atomicAdd(A.defer_count[0], 1)] = (int)row;
+        if (fin_status == ODL_STIFF && A.defer_list[1]) A.defer_list[1][atomicAdd(A.defer_count[1], 1)] = (int)row;
       }
     }
     if (fin) { active = false; done = false; want = lane_on; }
@@ -1521,6 +1526,7 @@ ODL_UNROLL
           odl_emit_initial_slots(st, S, D, sink);
           active = true;
           done = (st.slot >= D.n_slot);
+          if (done) { fin_status = st.status; fin_nsteps = st.nsteps; }
         }
       }
       if (!__any_sync(ODL_FULL, active)) break;
@@ -1552,6 +1558,7 @@ ODL_UNROLL
             odl_emit_initial_slots(st, S, D, sink);
             active = true; pending = false;
             done = (st.slot >= D.n_slot);
+            if (done) { fin_status = st.status; fin_nsteps = st.nsteps; }
           } else if (complete) {
             pending = false;                                                   // the feed ended before this ticket
           }
@@ -1570,9 +1577,23 @@ ODL_UNROLL
     //      about a fifth of a step; a finished lane idles for at most ODL_INNER-1 attempts (systems take ~90) ----
 #pragma unroll 1
     for (int r = 0; r < ODL_INNER; ++r) {
-      if (active && !done) {
+      if constexpr (SOLVER == 0) {
+        // DOPRI5: EVERY lane runs the step code, with or without a system.  Wrapping the inlined step in
+        // `if (active && !done)` made the compiler reconcile ~40 registers on the path around it -- 7 % of the
+        // kernel's instructions, issued for the lanes that were NOT stepping (profiles/r1e).  A lane without work
+        // steps a defined dummy state and writes nothing (slot == n_slot); a finished lane keeps the status and
+        // step count of its solve in fin_*.
         odl_attempt<SOLVER>(st, ax, p, S, D, O, sink, false);
-        done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
+        if (active && !done) {
+          done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
+          if (done) { fin_status = st.status; fin_nsteps = st.nsteps; }
+        }
+      } else {
+        if (active && !done) {
+          odl_attempt<SOLVER>(st, ax, p, S, D, O, sink, false);
+          done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
+          if (done) { fin_status = st.status; fin_nsteps = st.nsteps; }
+        }
       }
       if (!__any_sync(ODL_FULL, active && !done)) break;
     }
@@ -1872,7 +1893,7 @@ ODL_UNROLL
     more = has_chain && it < A.it_end;
   }
 }
-extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
+extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_MCMC)
 odl_mcmc_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<0>(D, O, A); }
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
 odl_mcmc_ros23_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<1>(D, O, A); }
