@@ -414,9 +414,16 @@ class ModelFramework:
         return out
 
     def explore_equilibriums(self, samples=1000, cpu_cores=1, **parameter_mapping):
-        """Final state of every LHS sample (Framework.py:819-854) -- one batched trajectory launch."""
+        """Final state of every LHS sample (Framework.py:819-854, `_Equilibrium_worker` :24-38) -- one batched launch
+        of the trajectory kernel on a two-point output grid (t0, t_end): only the final states leave the device."""
         ps = self._lhs_samples(samples, **parameter_mapping)[self.get_pnames()]
-        traj, _, _ = self._device().trajectory(ps.to_numpy(dtype=np.float64), rtol=self.rtol, atol=self.atol)
+        dm = self._device()
+        y0 = np.asarray(self.get_inits(), dtype=np.float64)
+        dm.set_grid(np.array([self.times[0], self.times[-1]]), y0, self._y0_map())
+        try:
+            traj, _, _ = dm.trajectory(ps.to_numpy(dtype=np.float64), rtol=self.rtol, atol=self.atol)
+        finally:
+            dm.set_grid(self.times, y0, self._y0_map())           # integrate() expects the full grid
         df = pd.DataFrame(traj[:, -1, :], columns=self.get_snames(after_summation=False))
         for p in self.get_pnames():
             df[p] = ps[p].to_numpy()

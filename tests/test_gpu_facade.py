@@ -136,3 +136,25 @@ def test_report_and_best_parameters_come_from_device_reductions(capsys):
     assert isinstance(summ, PosteriorSummary) and "Fitting Report" in capsys.readouterr().out
     assert summ.best == s.best and summ.stats == s.stats and summ.rhat == s.rhat
     assert m2._last_mcmc["samples"] is None                     # no sample rows were produced at all
+
+
+def test_explore_equilibriums_returns_final_states():
+    """f3 (Framework.py:819-854): the final state of every LHS sample, from a two-point output grid."""
+    from scipy.integrate import odeint
+    from oracle import odelib_oracle as orc
+    m = make_model("one_i")
+    np.random.seed(5)
+    eq = m.explore_equilibriums(samples=64)
+    assert list(eq.columns) == m.get_snames(after_summation=False) + m.get_pnames() and len(eq) == 64
+    y0 = list(m.get_inits())
+    ok = 0
+    for k in (0, 17, 63):
+        th = eq[m.get_pnames()].iloc[k].to_numpy()
+        ref = odeint(orc.one_i, y0, [m.times[0], m.times[-1]], args=(list(th),), rtol=1e-12, atol=1e-12, mxstep=500000)[-1]
+        got = eq[m.get_snames(after_summation=False)].iloc[k].to_numpy()
+        if np.all(np.isfinite(got)):
+            np.testing.assert_allclose(got, ref, rtol=2e-5, atol=1.0)
+            ok += 1
+    assert ok >= 2
+    full = m.integrate()                                          # the full output grid is back in place
+    assert len(full) == len(m.times)
