@@ -44,7 +44,9 @@ enum { ODL_MEM_HOST = 0, ODL_MEM_DEVICE = 1 };
 enum { ODL_SOLVER_DOPRI5 = 0, ODL_SOLVER_ROS23 = 1, ODL_SOLVER_AUTO = 2, ODL_SOLVER_RADAU5 = 3, ODL_SOLVER_BDF = 4 };
 /* odl_solver_opts.auto_flags */
 enum { ODL_AUTO_UNORDERED = 1,   /* process rows in input order (no cost ordering) */
-       ODL_AUTO_CONCURRENT = 2   /* run the stiff pass beside the DOPRI5 pass instead of after it (measured slower) */ };
+       ODL_AUTO_CONCURRENT = 2,  /* run the stiff pass beside the DOPRI5 pass instead of after it (measured slower) */
+       ODL_AUTO_ONE_PIECE = 4    /* ODL_MEM_HOST: upload theta in one piece before anything runs (default: two pieces,
+                                    the second travelling while the first is swept) */ };
 enum { ODL_RNG_PHILOX = 0, ODL_RNG_HOST_STREAMS = 1, ODL_RNG_FORCED = 2 };
 /* per-system status words */
 enum { ODL_ST_OK = 0, ODL_ST_MAXSTEPS = 1, ODL_ST_NONFINITE = 2, ODL_ST_HUNDERFLOW = 3, ODL_ST_STIFF = 4,

@@ -13,7 +13,7 @@ SUCCESS, EINVAL, ECUDA, ECOMPILE, ENODEVICE, EIO = range(6)
 MEM_HOST, MEM_DEVICE = 0, 1
 SOLVER_DOPRI5, SOLVER_ROS23, SOLVER_AUTO, SOLVER_RADAU5, SOLVER_BDF = 0, 1, 2, 3, 4
 RNG_PHILOX, RNG_HOST_STREAMS, RNG_FORCED = 0, 1, 2
-AUTO_UNORDERED, AUTO_CONCURRENT = 1, 2
+AUTO_UNORDERED, AUTO_CONCURRENT, AUTO_ONE_PIECE = 1, 2, 4
 ST_OK, ST_MAXSTEPS, ST_NONFINITE, ST_HUNDERFLOW, ST_STIFF, ST_ALLMASKED = 0, 1, 2, 3, 4, 8
 
 EXPORTS = ["odl_abi_version", "odl_last_error", "odl_model_create", "odl_model_destroy", "odl_model_build_log",

@@ -80,6 +80,8 @@ struct OdlOrderArgs {
   int* hist;                     // [ODL_ORDER_BINS] zeroed by the host
   int* cursor;                   // [ODL_ORDER_BINS] start of every bin in index[] (descending bins), then a cursor
   int* index;                    // [n] out: rows in processing order
+  int row_base;                  // added to every row number written to index[] (theta / bins / index point at the
+  int pad_;                      //   start of a chunk of a larger sweep)
 };
 
 struct OdlTrajArgs {

@@ -143,6 +143,7 @@ struct odl_model {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evp[2] = {nullptr, nullptr};   // between the cohort passes of an AUTO sweep
   cudaEvent_t ev_aux = nullptr, ev_fork = nullptr;
+  cudaEvent_t ev_chunk[2] = {nullptr, nullptr};   // host-memory sweeps: theta arrives in two pieces on the helper stream
   cudaStream_t aux = nullptr;                // helper stream: the Radau5 pass runs beside the deferred DOPRI5 pass
   int n_pass = 0;
   bool timed = false;
@@ -292,9 +293,11 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
       cudaEventCreate(&m->evp[0]) != cudaSuccess || cudaEventCreate(&m->evp[1]) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_aux, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_chunk[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_chunk[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking) != cudaSuccess)
     return bail(fail(ODL_ECUDA, "cudaEventCreate / cudaStreamCreate failed"));
-  if ((rc = m->counter.ensure(4096))) return bail(rc);
+  if ((rc = m->counter.ensure(8192))) return bail(rc);
   m->on_gpu = true;
   *out = m;
   return 0;
@@ -313,6 +316,7 @@ extern "C" int odl_model_destroy(odl_model* m) {
   for (auto& e : m->evp) if (e) cudaEventDestroy(e);
   if (m->ev_aux) cudaEventDestroy(m->ev_aux);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  for (auto& e : m->ev_chunk) if (e) cudaEventDestroy(e);
   if (m->aux) cudaStreamDestroy(m->aux);
   delete m;
   return 0;
@@ -524,7 +528,17 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   Staging st{m, s, 0, mem};
   OdlSweepArgs A{};
   int rc;
-  if ((rc = st.in(theta, (size_t)n * m->n_param, &A.theta))) return rc;
+  // Host-memory ODL_SOLVER_AUTO sweep of a large table: theta travels in two pieces on the helper stream and the second
+  // piece arrives while the first is being ordered and integrated (each piece is ordered and swept on its own; the
+  // stiff pass runs once over what both leave).  Rows are independent, so the pieces change nothing in the results.
+  const int auto_flags = so ? so->auto_flags : 0;
+  const bool chunked = mem == ODL_MEM_HOST && solver == ODL_SOLVER_AUTO && n >= (1 << 18) && !m->k_sweep_coop &&
+                       !(auto_flags & (ODL_AUTO_UNORDERED | ODL_AUTO_CONCURRENT | ODL_AUTO_ONE_PIECE));
+  if (chunked) {
+    DevBuf& bt = m->scratch[st.next++];
+    if ((rc = bt.ensure((size_t)n * m->n_param * sizeof(double)))) return rc;
+    A.theta = static_cast<const double*>(bt.p);
+  } else if ((rc = st.in(theta, (size_t)n * m->n_param, &A.theta))) return rc;
   if ((rc = st.inout(chi, (size_t)n, &A.chi, false))) return rc;
   if ((rc = st.inout(r2, (size_t)n, &A.r2, false))) return rc;
   if ((rc = st.inout(status, (size_t)n, &A.status, false))) return rc;
@@ -538,7 +552,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   auto cnt = [&](int off) { return reinterpret_cast<int*>(cb + off); };
   A.counter = ctr(0);
   OdlOpts O; fill_opts(O, so);
-  ODL_CUDA(cudaMemsetAsync(m->counter.p, 0, 4096, s));
+  ODL_CUDA(cudaMemsetAsync(m->counter.p, 0, 8192, s));
   OdlData D = m->data.d;
   auto go = [&](cudaStream_t sx, CUfunction f, const OdlOpts& Ox, const OdlSweepArgs& Ax, unsigned block, long long items) -> int {
     const size_t smem = smem_bytes(D, (int)block);
@@ -608,19 +622,34 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     // counter block (zeroed above): [0] bulk work counter, [64] feed count, [128] feed ticket, [192] warps entered,
     // [256] warps left, [1024] hist[256], [2048] cursor[256]
     ODL_CUDA(cudaMemsetAsync(feed, 0xFF, (size_t)n * sizeof(int), s));
-    if (ordered) {
+    // ordering of one piece [lo, hi) of the table -> index[lo..hi) (global row numbers)
+    auto order_piece = [&](long long lo, long long hi, int piece) -> int {
       OdlOrderArgs R{};
-      R.theta = A.theta; R.n = n; R.bins = static_cast<unsigned char*>(bbins.p);
-      R.hist = cnt(1024); R.cursor = cnt(2048); R.index = index;
+      const long long np = hi - lo;
+      R.theta = A.theta + lo * m->n_param; R.n = np; R.bins = static_cast<unsigned char*>(bbins.p) + lo;
+      R.hist = cnt(piece ? 4096 : 1024); R.cursor = cnt(piece ? 5120 : 2048); R.index = index + lo;
+      R.row_base = (int)lo; R.pad_ = 0;
       OdlData Dl = D;
       void* p1[] = {&Dl, &R};
       void* p2[] = {&R};
-      const unsigned g1 = (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)m->sm_count * 8));
-      const unsigned g3 = (unsigned)std::max<long long>(1, std::min<long long>((n + 2047) / 2048, (long long)m->sm_count * 8));
-      if ((rc = launch(m, m->k_order_key, g1, 256, 0, s, p1))) return rc;
-      if ((rc = launch(m, m->k_order_scan, 1, ODL_ORDER_BINS, 0, s, p2))) return rc;
-      if ((rc = launch(m, m->k_order_scatter, g3, 256, 0, s, p2))) return rc;
+      const unsigned g1 = (unsigned)std::max<long long>(1, std::min<long long>((np + 255) / 256, (long long)m->sm_count * 8));
+      const unsigned g3 = (unsigned)std::max<long long>(1, std::min<long long>((np + 2047) / 2048, (long long)m->sm_count * 8));
+      int r;
+      if ((r = launch(m, m->k_order_key, g1, 256, 0, s, p1))) return r;
+      if ((r = launch(m, m->k_order_scan, 1, ODL_ORDER_BINS, 0, s, p2))) return r;
+      return launch(m, m->k_order_scatter, g3, 256, 0, s, p2);
+    };
+    const long long half = chunked ? ((n / 2 + 1023) / 1024) * 1024 : n;
+    if (chunked) {
+      for (int c = 0; c < 2; ++c) {
+        const long long lo = c ? half : 0, hi = c ? n : half;
+        ODL_CUDA(cudaMemcpyAsync(const_cast<double*>(A.theta) + lo * m->n_param, theta + lo * m->n_param,
+                                 (size_t)(hi - lo) * m->n_param * sizeof(double), cudaMemcpyHostToDevice, m->aux));
+        ODL_CUDA(cudaEventRecord(m->ev_chunk[c], m->aux));
+      }
+      ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[0], 0));
     }
+    if (ordered && (rc = order_piece(0, half, 0))) return rc;
     ODL_CUDA(cudaEventRecord(m->evp[1], s));
     const unsigned block0 = pick_block(D, m->block);
     const size_t smem0 = smem_bytes(D, (int)block0), smem_t = smem_bytes(D, 32);
@@ -664,7 +693,8 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     O2.lanes = so && so->tail_lanes > 0 ? std::min(32, so->tail_lanes) : 0;
     OdlSweepArgs A2 = A;
     A2.index = feed; A2.index_count = cnt(64); A2.counter = nullptr; A2.feed_ticket = ctr(128);
-    A2.prod_counter = ctr(0); A2.prod_n = n; A2.prod_started = cnt(192); A2.prod_exited = cnt(256);
+    A2.prod_counter = ctr(0); A2.prod_n = chunked ? half : n;    // the (first) bulk launch's counter and item count
+    A2.prod_started = cnt(192); A2.prod_exited = cnt(256);
     A2.watchdog = cnt(320);
     A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
     const unsigned grid0 = (unsigned)std::max<long long>(1, std::min<long long>((n + block0 - 1) / block0, (long long)bulk_ctas * m->sm_count));
@@ -682,7 +712,17 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       ODL_CUDA(cudaStreamWaitEvent(s, m->ev_aux, 0));
     } else {
       if (m->k_sweep_coop) { if ((rc = go_coop(s, O0, A0, n))) return rc; }      // n > 8: several lanes per system
-      else if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc;
+      else if (!chunked) { if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc; }
+      else {
+        OdlSweepArgs A1 = A0;
+        A0.n = half;                                         // pb points at A0: first piece, index[0..half)
+        if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc;
+        ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[1], 0));
+        if ((rc = order_piece(half, n, 1))) return rc;
+        A1.n = n - half; A1.index = index + half; A1.counter = ctr(384);
+        void* pb1[] = {&Dl, &O0, &A1};
+        if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb1))) return rc;
+      }
       ODL_CUDA(cudaEventRecord(m->evp[0], s));
       if ((rc = launch(m, k_tail, grid_t, 32, smem_t, s, pt))) return rc;
     }

@@ -1441,7 +1441,7 @@ odl_order_scatter_kernel(const OdlOrderArgs A) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const long long i = t0 + (long long)k * blockDim.x + threadIdx.x;
-      if (myb[k] >= 0) A.index[base[myb[k]] + myr[k]] = (int)i;
+      if (myb[k] >= 0) A.index[base[myb[k]] + myr[k]] = (int)i + A.row_base;
     }
     __syncthreads();
   }

@@ -195,3 +195,20 @@ def test_auto_sweep_is_independent_of_ordering_and_of_how_the_passes_are_schedul
     for n in (1, 31, 33, 2047, 2049):
         a = dm.sweep(theta[:n], solver="auto", max_steps=200000)
         assert np.array_equal(a["chi"], base["chi"][:n], equal_nan=True)
+
+
+def test_host_memory_sweep_in_two_pieces_equals_one_piece_and_the_device_call():
+    """ODL_MEM_HOST + ODL_SOLVER_AUTO on a large table: theta is uploaded in two pieces, the second travelling while the
+    first is ordered and swept.  Rows are independent: same numbers as the one-piece upload and the device call."""
+    import torch
+    from odelib_b200 import _capi
+    dm, _ = device_model("two_i")
+    n = (1 << 18) + 777                                          # above the threshold, ragged second piece
+    theta = prior_draws("two_i", n, seed=13)
+    a = dm.sweep(theta, solver="auto", max_steps=200000)
+    b = dm.sweep(theta, solver="auto", max_steps=200000, auto_flags=_capi.AUTO_ONE_PIECE)
+    c = dm.sweep(torch.from_numpy(theta).cuda(), solver="auto", max_steps=200000)
+    assert np.all(a["status"] == 0) and (a["nsteps"] > 512).sum() > 100
+    for k in ("chi", "r2", "status", "nsteps"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+        assert np.array_equal(a[k], c[k].cpu().numpy(), equal_nan=True), k
