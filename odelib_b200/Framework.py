@@ -115,6 +115,10 @@ class ModelFramework:
         self.rtol = kwargs.pop("rtol", None)
         self.atol = kwargs.pop("atol", None)
         self.device = kwargs.pop("device", None)
+        # stepper of the chains: "auto" probes the chain starts with the capped DOPRI5 pass and, when a quarter of them
+        # do not finish (a stiff posterior region -- where LSODA itself switches to BDF), runs the chains on the
+        # variable-order BDF kernel; "dopri5" / "bdf" / "radau5" / "ros23" force one
+        self.solver = kwargs.pop("solver", "auto")
         self._dm = None
         self._dm_stamp = None
         if state_summations:
@@ -471,8 +475,17 @@ class ModelFramework:
             burnin = int(nits / 2)
         if rng == "auto":
             rng = "reference" if C * n_iter * (2 * len(walk) + 1) <= 20_000_000 else "philox"
+        solver = self.solver
+        if solver == "auto":
+            probe = dm.sweep(theta0, rtol=self.rtol if rtol is None else rtol, atol=self.atol if atol is None else atol,
+                             solver="dopri5", max_steps=512, stiff_check=True)
+            st_ = probe["status"]
+            unfinished = float((st_ != 0).float().mean().item()) if on_device else float(np.mean(np.asarray(st_) != 0))
+            solver = "bdf" if unfinished > 0.25 else "dopri5"
+        self._last_solver = solver
         kw = dict(nits=nits, burnin=burnin, walk=walk, pnum=self._pnum, rtol=self.rtol if rtol is None else rtol,
-                  atol=self.atol if atol is None else atol, keep_samples=keep_samples, device_buffers=on_device)
+                  atol=self.atol if atol is None else atol, keep_samples=keep_samples, device_buffers=on_device,
+                  solver=solver, max_steps=2000000)
         if rng == "reference":
             walking = [self.parameters[p] for p in walk_names]
             z = np.empty((C, n_iter, len(walk)))

@@ -148,3 +148,29 @@ def test_mcmc_on_the_stiff_variant_ros23_and_auto():
     c = dm.mcmc(starts, nits=nits, rng_mode="host", z=z, u=u, solver="radau5", trace=True)
     np.testing.assert_allclose(c["chinew"][0], ref["chinew"], rtol=2e-5)
     assert c["step_count"].sum() < 0.5 * a["step_count"].sum()
+
+
+def test_facade_picks_the_bdf_kernel_for_a_stiff_posterior():
+    """ModelFramework(solver='auto') (the default): chains whose starts the capped DOPRI5 pass cannot finish run on the
+    BDF kernel -- the drop-in needs no hint for config 4's stiff variant; the demo's posterior stays on DOPRI5."""
+    import scipy.stats
+    import odelib_b200 as ODElib
+    from odelib_b200 import demo_models
+    center = dict(mu=0.5, phi=1e-7, beta=50.0, lam=1e-2, tau=1e4)
+    pobj = {p: ODElib.parameter(stats_gen=scipy.stats.lognorm, hyperparameters={"s": 0.5, "scale": v}, init_value=v)
+            for p, v in center.items()}
+    m = ODElib.ModelFramework(ODE=demo_models.two_i, parameter_names=demo_models.PARAMETER_NAMES["two_i"],
+                              state_names=demo_models.STATE_NAMES["two_i"], dataframe=demo_df("two_i"),
+                              state_summations={"H": ["S", "I1", "I2"]}, S=5236900, **pobj)
+    post = m.MCMC(chain_inits=[dict(center)] * 4, iterations_per_chain=60, print_report=False)
+    assert m._last_solver == "bdf" and len(post) == 4 * 29 and np.isfinite(post["chi"]).all()
+    assert m._last_mcmc["fail_count"].sum() == 0
+    g = golden("two_i")
+    pobj2 = {p: ODElib.parameter(stats_gen=scipy.stats.lognorm, hyperparameters={"s": s, "scale": sc}, init_value=sc)
+             for p, (s, sc) in demo_models.PRIORS["two_i"].items()}
+    m2 = ODElib.ModelFramework(ODE=demo_models.two_i, parameter_names=demo_models.PARAMETER_NAMES["two_i"],
+                               state_names=demo_models.STATE_NAMES["two_i"], dataframe=demo_df("two_i"),
+                               state_summations={"H": ["S", "I1", "I2"]}, S=5236900, **pobj2)
+    th = dict(zip(m2.get_pnames(), g["chain_def_s0_theta0"]))
+    m2.MCMC(chain_inits=[th] * 2, iterations_per_chain=40, print_report=False)
+    assert m2._last_solver == "dopri5"
