@@ -37,13 +37,10 @@ struct OdlOpts {
   int max_steps;
   int stiff_check;               // 1 = run Hairer's stiffness test and bail out with ODL_STIFF
   int stiff_min_steps;           // bail out only if more than this many steps of the current size remain
-  int defer_split_steps;         // > 0: a system stopped by max_steps goes to defer_list[1] instead of [0] when its
-                                 //      progress so far projects to more than this many steps in total
   int early_check_steps;         // > 0: DOPRI5 stops with ODL_MAXSTEPS already after this many attempts when the
                                  //      progress so far projects to more than max_steps attempts in total
   int lanes;                     // sweep kernels: lanes per warp that take systems (0 = all 32)
   int watchdog_spins;            // consumer: idle polls (~0.4 us each) of a warp before it gives up on the producer
-  int pad_;
 };
 
 struct OdlSweepArgs {

@@ -465,12 +465,10 @@ static void fill_opts(OdlOpts& o, const odl_solver_opts* so) {
   o.max_steps = so && so->max_steps > 0 ? so->max_steps : 500000;
   o.stiff_check = so ? so->stiff_check : 0;
   o.stiff_min_steps = so && so->stiff_min_steps > 0 ? so->stiff_min_steps : 2000;
-  o.defer_split_steps = 0;
   o.early_check_steps = so && so->early_check_steps > 0 ? so->early_check_steps : 0;   // AUTO sets its own default
   o.lanes = 0;
   o.watchdog_spins = 75000000;   // ~30 s without a single entry and without the producer finishing
   if (const char* w = getenv("ODL_WATCHDOG_SPINS")) o.watchdog_spins = std::max(1000, atoi(w));
-  o.pad_ = 0;
 }
 
 static int launch(odl_model* m, CUfunction f, unsigned grid, unsigned block, size_t smem, cudaStream_t s, void** params) {
