@@ -157,6 +157,13 @@ int odl_select_below(odl_model* m, const double* chi_dev, long long n, double cu
 int odl_gather_rows(odl_model* m, const double* src_dev, int row_len, const int* index_dev_or_null,
                     const long long* picks_host, long long n_pick, double* dst_dev, void* stream);
 
+/* Latin-hypercube sample of the priors on the device (replaces Samplers.sample_lhs, Samplers.py:6-51, for large
+   surveys): theta_dev[i][j] = ppf_j((stratum_j(i) + U) / n) with stratum_j a keyed permutation of 0..n-1 per
+   column.  kind[j]: 0 constant a[j]; 1 lognorm(s = a[j], loc = b[j], scale = c[j]); 2 norm(loc = b[j], scale = c[j]);
+   3 uniform(loc = b[j], scale = c[j]) -- scipy.stats parameterisation.  Deterministic in (seed, n). */
+int odl_sample_lhs(odl_model* m, long long n, int n_param, const int* kind, const double* a, const double* b,
+                   const double* c, unsigned long long seed, double* theta_dev, void* stream);
+
 /* device time (ms) of the kernels launched by the last odl_sweep/odl_mcmc/odl_trajectory call on this
    model, measured with CUDA events on the launching stream; blocks until they have completed */
 int odl_model_last_kernel_ms(odl_model* m, float* ms);

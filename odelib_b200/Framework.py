@@ -409,8 +409,48 @@ class ModelFramework:
             df[p] = float(pstatic[p])
         return df
 
-    def fit_survey(self, samples=1000, cpu_cores=1):
-        """LHS sample of the priors, chi of every sample (Framework.py:800-816).  ``cpu_cores`` is ignored."""
+    DEVICE_SAMPLING_FROM = 65536       # surveys at least this large are sampled on the device (sampler="auto")
+
+    def _prior_table(self):
+        """(kind, a, b, c) per parameter for the device sampler (engine.DeviceModel.sample_lhs), or None when a prior
+        is not one of lognorm / norm / uniform in scipy.stats' (s, loc, scale) parameterisation."""
+        table = []
+        for p in self._pnames:
+            par = self.parameters[p]
+            if par is None or not par.has_distribution():
+                table.append(("const", float(par.val) if par is not None else 0.0, 0.0, 0.0))
+                continue
+            name, hp = getattr(par.dist, "name", None), dict(par.hp or {})
+            extra = set(hp) - {"s", "loc", "scale"}
+            if name not in ("lognorm", "norm", "uniform") or extra or (name == "lognorm" and "s" not in hp):
+                return None
+            table.append((name, float(hp.get("s", 0.0)), float(hp.get("loc", 0.0)), float(hp.get("scale", 1.0))))
+        return table
+
+    def _lhs_samples_device(self, samples, sampler="auto"):
+        """Latin-hypercube sample of the priors as a CUDA tensor [samples, P], or None when the host sampler is to be
+        used (small survey, unsupported prior, sampler="host").  The seed is one draw from numpy's global RandomState,
+        so `np.random.seed(k)` keeps a survey reproducible -- as it does for the reference, whose pyDOE2.lhs draws
+        from that state too (Samplers.py:33)."""
+        if sampler == "host" or (sampler == "auto" and samples < self.DEVICE_SAMPLING_FROM):
+            return None
+        table = self._prior_table()
+        if table is None:
+            if sampler == "device":
+                raise NotImplementedError("device sampling supports lognorm / norm / uniform priors (s, loc, scale)")
+            return None
+        seed = int(np.random.randint(0, 2 ** 62))
+        return self._device().sample_lhs(table, samples, seed)
+
+    def fit_survey(self, samples=1000, cpu_cores=1, sampler="auto"):
+        """LHS sample of the priors, chi of every sample (Framework.py:800-816).  ``cpu_cores`` is ignored.
+        sampler: "host" = numpy (Samplers.sample_lhs), "device" = odl_sample_lhs, "auto" = device for large surveys."""
+        theta_dev = self._lhs_samples_device(samples, sampler)
+        if theta_dev is not None:
+            res = self._device().sweep(theta_dev, rtol=self.rtol, atol=self.atol, solver="auto")
+            out = pd.DataFrame(theta_dev.cpu().numpy(), columns=self.get_pnames())
+            out['chi'] = res['chi'].cpu().numpy()
+            return out
         ps = self._lhs_samples(samples)[self.get_pnames()]
         res = self.sweep(ps.to_numpy(dtype=np.float64))
         out = ps.reset_index(drop=True)
@@ -539,8 +579,10 @@ class ModelFramework:
         the survey has no finite chi (the reference then warns and starts every chain from the current values)."""
         import torch
         dm = self._device()
-        ps = self._lhs_samples(fitsurvey_samples)[self.get_pnames()]
-        theta = torch.from_numpy(np.ascontiguousarray(ps.to_numpy(dtype=np.float64))).to(torch.device("cuda", dm.device))
+        theta = self._lhs_samples_device(fitsurvey_samples)
+        if theta is None:
+            ps = self._lhs_samples(fitsurvey_samples)[self.get_pnames()]
+            theta = torch.from_numpy(np.ascontiguousarray(ps.to_numpy(dtype=np.float64))).to(torch.device("cuda", dm.device))
         res = dm.sweep(theta, rtol=self.rtol, atol=self.atol, solver="auto")
         calc = {s: np.exp(self._obs_logabundance[s] + sd_fitdistance * self._obs_logsigma[s]) for s in self._obs_logabundance}
         cutchi = self.get_chi(calc)                              # = n_obs * sd^2 / 2

@@ -1016,6 +1016,110 @@ extern "C" int odl_gather_rows(odl_model* m, const double* src_dev, int row_len,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Latin-hypercube sample of the priors on the device (Samplers.py:6-51 `sample_lhs`, Framework.py:589-615): row i of
+// column j takes stratum perm_j(i) of n, a uniform point inside it, and the prior's ppf.  perm_j is a keyed bijection of
+// [0, n) (4-round Feistel network on the next even power of two, cycle-walking back into range), so every column
+// visits every stratum exactly once without a sort; the point inside the stratum is Philox4x32-10 keyed by
+// (seed, column, row).  Priors: constant, lognorm(s, loc, scale), norm(loc, scale), uniform(loc, scale).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int odl_mix32(unsigned int x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ unsigned long long odl_feistel_perm(unsigned long long i, unsigned long long n, int half_bits,
+                                                              unsigned int key) {
+  const unsigned int mask = (half_bits >= 32) ? 0xffffffffu : ((1u << half_bits) - 1u);
+  unsigned long long x = i;
+  do {                                                            // cycle-walk: the domain is < 4 n
+    unsigned int L = (unsigned int)(x >> half_bits) & mask, R = (unsigned int)x & mask;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const unsigned int F = odl_mix32(R ^ (key + 0x9E3779B9u * (unsigned int)(r + 1))) & mask;
+      const unsigned int t = L ^ F;
+      L = R; R = t;
+    }
+    x = ((unsigned long long)L << half_bits) | R;
+  } while (x >= n);
+  return x;
+}
+__device__ __forceinline__ void odl_philox_host(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3,
+                                                unsigned int k0, unsigned int k1, unsigned int* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+struct OdlLhsArgs {
+  long long n;
+  int n_param, half_bits;
+  unsigned long long seed;
+  const int* kind;               // [n_param] 0 constant a, 1 lognorm(s=a, loc=b, scale=c), 2 norm(loc=b, scale=c), 3 uniform(loc=b, scale=c)
+  const double* a; const double* b; const double* c;
+  double* theta;                 // [n][n_param]
+};
+__global__ void __launch_bounds__(256) odl_lhs_kernel(const OdlLhsArgs A) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += (long long)gridDim.x * blockDim.x) {
+    for (int j = 0; j < A.n_param; ++j) {
+      const int kind = A.kind[j];
+      double v = A.a[j];
+      if (kind != 0) {
+        const unsigned int key = odl_mix32((unsigned int)A.seed ^ odl_mix32((unsigned int)(A.seed >> 32) + 0x85ebca6bu * (unsigned int)(j + 1)));
+        const unsigned long long stratum = odl_feistel_perm((unsigned long long)i, (unsigned long long)A.n, A.half_bits, key);
+        unsigned int r[4];
+        odl_philox_host((unsigned int)i, (unsigned int)(i >> 32), (unsigned int)j, 0x4c4853u, (unsigned int)A.seed,
+                        (unsigned int)(A.seed >> 32), r);
+        const unsigned long long bits = (((unsigned long long)r[0]) << 21) ^ ((unsigned long long)r[1] >> 11);
+        const double jitter = (double)(bits & ((1ull << 53) - 1)) * 1.1102230246251565e-16;          // [0, 1)
+        double u = ((double)stratum + jitter) / (double)A.n;
+        u = fmin(fmax(u, 1.1102230246251565e-16), 1.0 - 1.1102230246251565e-16);
+        if (kind == 1) v = A.b[j] + A.c[j] * exp(A.a[j] * normcdfinv(u));
+        else if (kind == 2) v = A.b[j] + A.c[j] * normcdfinv(u);
+        else v = A.b[j] + A.c[j] * u;
+      }
+      A.theta[i * A.n_param + j] = v;
+    }
+  }
+}
+
+extern "C" int odl_sample_lhs(odl_model* m, long long n, int n_param, const int* kind, const double* a, const double* b,
+                              const double* c, unsigned long long seed, double* theta_dev, void* stream) {
+  if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_sample_lhs: model is not loaded on a GPU (no CPU fallback exists)");
+  if (n < 0 || n_param < 1 || n_param > 4096 || !kind || !a || !b || !c || (n > 0 && !theta_dev))
+    return fail(ODL_EINVAL, "odl_sample_lhs: bad argument");
+  for (int j = 0; j < n_param; ++j) if (kind[j] < 0 || kind[j] > 3) return fail(ODL_EINVAL, "odl_sample_lhs: unknown prior kind");
+  if (n == 0) return 0;
+  ODL_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  DevBuf& bk = m->scratch[13];
+  int rc = bk.ensure((size_t)n_param * (sizeof(int) + 3 * sizeof(double)) + 64);
+  if (rc) return rc;
+  char* base = static_cast<char*>(bk.p);
+  double* da = reinterpret_cast<double*>(base);
+  double* db = da + n_param; double* dc = db + n_param;
+  int* dk = reinterpret_cast<int*>(dc + n_param);
+  ODL_CUDA(cudaMemcpyAsync(da, a, n_param * sizeof(double), cudaMemcpyHostToDevice, s));
+  ODL_CUDA(cudaMemcpyAsync(db, b, n_param * sizeof(double), cudaMemcpyHostToDevice, s));
+  ODL_CUDA(cudaMemcpyAsync(dc, c, n_param * sizeof(double), cudaMemcpyHostToDevice, s));
+  ODL_CUDA(cudaMemcpyAsync(dk, kind, n_param * sizeof(int), cudaMemcpyHostToDevice, s));
+  OdlLhsArgs A;
+  A.n = n; A.n_param = n_param; A.seed = seed; A.kind = dk; A.a = da; A.b = db; A.c = dc; A.theta = theta_dev;
+  int bits = 1;
+  while ((1ull << bits) < (unsigned long long)n) ++bits;
+  A.half_bits = (bits + 1) / 2;                                   // even number of bits: domain 2^(2*half_bits) < 4 n
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)m->sm_count * 16));
+  odl_lhs_kernel<<<grid, 256, 0, s>>>(A);
+  g_launches.fetch_add(1);
+  ODL_CUDA(cudaGetLastError());
+  ODL_CUDA(cudaStreamSynchronize(s));                              // the host arrays may be reused by the caller
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP64 roofline denominator: 8 independent DFMA chains per thread, no memory traffic
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) odl_dfma_peak_kernel(double* out, int iters, double a, double b) {

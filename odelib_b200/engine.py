@@ -210,6 +210,20 @@ class DeviceModel:
             res["pred"] = pred
         return res
 
+    # -- Latin-hypercube sample of the priors on the device (Samplers.py:6-51) ----------------------
+    PRIOR_KINDS = {"const": 0, "lognorm": 1, "norm": 2, "uniform": 3}
+
+    def sample_lhs(self, priors, n, seed=0):
+        """priors: one (kind, a, b, c) per parameter (kind in PRIOR_KINDS; scipy.stats parameterisation: lognorm
+        (s, loc, scale), norm (-, loc, scale), uniform (-, loc, scale), const (value, -, -)) -> CUDA tensor [n, P]."""
+        import torch
+        kind = np.array([self.PRIOR_KINDS[k] if isinstance(k, str) else int(k) for k, _, _, _ in priors], np.int32)
+        a, b, c = (np.array([float(p[i]) for p in priors], np.float64) for i in (1, 2, 3))
+        theta = torch.empty((int(n), len(priors)), dtype=torch.float64, device=torch.device("cuda", self.device))
+        _capi.check(self._L.odl_sample_lhs(self._h, int(n), len(priors), kind.ctypes.data, a.ctypes.data, b.ctypes.data,
+                                           c.ctypes.data, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(theta), self._stream()))
+        return theta
+
     # -- chain-start selection on the device (Framework.py:1004-1012) -------------------------------
     def select_below(self, chi, cut):
         """Rows of the CUDA tensor `chi` with chi < cut, ascending -> (index tensor [n] int32, count)."""

@@ -158,3 +158,42 @@ def test_explore_equilibriums_returns_final_states():
     assert ok >= 2
     full = m.integrate()                                          # the full output grid is back in place
     assert len(full) == len(m.times)
+
+
+def test_device_latin_hypercube_sampling_of_the_priors():
+    """odl_sample_lhs (Samplers.py:6-51 on the device): every column visits every stratum exactly once, the k-th
+    smallest value of a column lies between the prior's ppf at k/n and (k+1)/n, columns are independent, the sample is
+    reproducible through numpy's seed, and fit_survey uses it for large surveys with the same frame layout."""
+    import scipy.stats
+    m = make_model("two_i")
+    dm = m._device()
+    n = 40000
+    table = m._prior_table()
+    assert [t[0] for t in table] == ["lognorm"] * 5
+    th = dm.sample_lhs(table, n, seed=123).cpu().numpy()
+    again = dm.sample_lhs(table, n, seed=123).cpu().numpy()
+    other = dm.sample_lhs(table, n, seed=124).cpu().numpy()
+    assert np.array_equal(th, again) and not np.array_equal(th, other)
+    edges = np.arange(n + 1) / n
+    for j, (kind, s_, loc, scale) in enumerate(table):
+        lo = scipy.stats.lognorm.ppf(edges[:-1], s=s_, loc=loc, scale=scale)
+        hi = scipy.stats.lognorm.ppf(edges[1:], s=s_, loc=loc, scale=scale)
+        col = np.sort(th[:, j])
+        assert np.all(col >= lo * (1 - 1e-12)) and np.all(col <= hi * (1 + 1e-12))       # one point per stratum, right ppf
+    c = np.corrcoef(np.log(th).T)
+    assert np.abs(c - np.eye(5)).max() < 0.03
+    mixed = dm.sample_lhs([("const", 2.5, 0, 0), ("norm", 0, 1.0, 2.0), ("uniform", 0, -1.0, 4.0), ("lognorm", 1.0, 0, 3.0),
+                           ("const", 7.0, 0, 0)], 1000, seed=5).cpu().numpy()
+    assert np.all(mixed[:, 0] == 2.5) and np.all(mixed[:, 4] == 7.0)
+    assert -1.0 <= mixed[:, 2].min() < -0.99 and 2.99 < mixed[:, 2].max() <= 3.0
+    assert abs(mixed[:, 1].mean() - 1.0) < 0.01 and abs(mixed[:, 1].std() - 2.0) < 0.02
+    np.random.seed(8)
+    sv = m.fit_survey(samples=70000)                             # >= DEVICE_SAMPLING_FROM: sampled on the device
+    np.random.seed(8)
+    sv2 = m.fit_survey(samples=70000)
+    assert list(sv.columns) == m.get_pnames() + ["chi"] and len(sv) == 70000 and sv.equals(sv2)
+    host = m.sweep(np.ascontiguousarray(sv[m.get_pnames()].to_numpy()))
+    assert np.array_equal(host["chi"], sv["chi"].to_numpy(), equal_nan=True)
+    with pytest.raises(NotImplementedError):
+        m.parameters["mu"].dist = scipy.stats.gamma
+        m.fit_survey(samples=10, sampler="device")
