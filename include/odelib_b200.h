@@ -120,6 +120,9 @@ typedef struct odl_mcmc_io {
   int* fail_count;         /* optional [n_chain], accumulated */
   long long* step_count;   /* optional [n_chain], accumulated attempted integrator steps */
   double* best_theta;      /* optional [n_chain][n_param] parameters of the best kept row */
+  const long long* chain_ids; /* optional [n_chain] global chain index per chain (Philox key) for a batch that is not a
+                              contiguous block of chains, e.g. the chains re-run with another stepper; default
+                              chain_offset + local index */
 } odl_mcmc_io;
 
 int odl_abi_version(void);

@@ -410,6 +410,7 @@ class ModelFramework:
         return df
 
     DEVICE_SAMPLING_FROM = 65536       # surveys at least this large are sampled on the device (sampler="auto")
+    EXPLICIT_STEP_BUDGET = 4096        # solver="auto": DOPRI5 attempts per solve before the chain is handed to BDF
 
     def _prior_table(self):
         """(kind, a, b, c) per parameter for the device sampler (engine.DeviceModel.sample_lhs), or None when a prior
@@ -514,7 +515,9 @@ class ModelFramework:
         if not burnin:
             burnin = int(nits / 2)
         if rng == "auto":
-            rng = "reference" if C * n_iter * (2 * len(walk) + 1) <= 20_000_000 else "philox"
+            # the reference's own numpy streams (bit-for-bit the reference chain) are regenerated on the host, one
+            # Python loop per chain: fine for the reference's scale (tens of chains), seconds for thousands
+            rng = "reference" if C <= 256 and C * n_iter * (2 * len(walk) + 1) <= 20_000_000 else "philox"
         solver = self.solver
         if solver == "auto":
             probe = dm.sweep(theta0, rtol=self.rtol if rtol is None else rtol, atol=self.atol if atol is None else atol,
@@ -523,20 +526,46 @@ class ModelFramework:
             unfinished = float((st_ != 0).float().mean().item()) if on_device else float(np.mean(np.asarray(st_) != 0))
             solver = "bdf" if unfinished > 0.25 else "dopri5"
         self._last_solver = solver
+        # "auto" that settled on DOPRI5: every solve gets a bounded step budget, and a chain that ever exhausts it (a
+        # proposal in a stiff corner -- the reference's LSODA would switch to BDF there) is re-run, whole, on the BDF
+        # kernel.  A chain's result depends on that chain alone: all DOPRI5, or all BDF.
+        retry = self.solver == "auto" and solver == "dopri5"
         kw = dict(nits=nits, burnin=burnin, walk=walk, pnum=self._pnum, rtol=self.rtol if rtol is None else rtol,
                   atol=self.atol if atol is None else atol, keep_samples=keep_samples, device_buffers=on_device,
-                  solver=solver, max_steps=2000000)
+                  solver=solver, max_steps=self.EXPLICIT_STEP_BUDGET if retry else 2000000)
         if rng == "reference":
             walking = [self.parameters[p] for p in walk_names]
             z = np.empty((C, n_iter, len(walk)))
             u = np.empty((C, n_iter))
             for c, seed in enumerate(seeds):
                 z[c], u[c] = Samplers.reference_streams(seed, walking, n_iter)
-            out = dm.mcmc(theta0, rng_mode="host", z=z, u=u, **kw)
+            streams = dict(rng_mode="host", z=z, u=u)
         elif rng == "philox":
-            out = dm.mcmc(theta0, rng_mode="philox", seed=int(self.random_seed), chain_offset=int(seeds[0]), **kw)
+            streams = dict(rng_mode="philox", seed=int(self.random_seed), chain_ids=np.asarray(seeds, dtype=np.int64))
         else:
             raise ValueError("rng must be 'auto', 'reference' or 'philox'")
+        out = dm.mcmc(theta0, **streams, **kw)
+        self._last_rerun = 0
+        if retry:
+            fails = out["fail_count"]
+            bad = np.flatnonzero((fails.cpu().numpy() if on_device else np.asarray(fails)) > 0)
+            if bad.size:
+                self._last_rerun = int(bad.size)
+                sub = dict(streams)
+                if rng == "reference":
+                    sub["z"], sub["u"] = z[bad], u[bad]
+                else:
+                    sub["chain_ids"] = np.asarray(seeds, dtype=np.int64)[bad]
+                if on_device:
+                    import torch
+                    sel = torch.as_tensor(bad, device=theta0.device)
+                    again = dm.mcmc(theta0[sel].contiguous(), **sub, **dict(kw, solver="bdf", max_steps=2000000))
+                else:
+                    sel = bad
+                    again = dm.mcmc(theta0[bad], **sub, **dict(kw, solver="bdf", max_steps=2000000))
+                for key in ("theta", "chain_state", "samples", "summaries", "fail_count", "step_count", "best_theta"):
+                    if out.get(key) is not None:
+                        out[key][sel] = again[key]
         if on_device:                                             # small per-chain results to the host; samples on demand
             out = {k: (v.cpu().numpy() if hasattr(v, "is_cuda") and k != "samples" else v) for k, v in out.items()}
             if out["samples"] is not None and (return_frame or not return_raw):

@@ -120,6 +120,8 @@ struct OdlMcmcArgs {
   int* fail_count;               // optional [C] proposals whose solve failed
   long long* step_count;         // optional [C] attempted integrator steps (flop accounting)
   double* best_theta;            // optional [C][n_param] parameters of the best kept row (Framework.py:725-731)
+  const long long* chain_ids;    // optional [C] global chain index of every local chain (keys the Philox stream);
+                                 //   default chain_offset + local index
 };
 
 #endif  // ODL_ABI_H

@@ -1653,7 +1653,7 @@ ODL_UNROLL
     for (int q = 0; q < ODL_P; ++q) p[q] = A.forced[k * ODL_P + q];
     return;
   }
-  const unsigned long long gchain = (unsigned long long)(A.chain_offset + chain_local);
+  const unsigned long long gchain = A.chain_ids ? (unsigned long long)A.chain_ids[chain_local] : (unsigned long long)(A.chain_offset + chain_local);
   for (int j = 0; j < A.n_walk; j += 2) {
     double z0, z1 = 0.0;
     if (A.rng_mode == 1) {
@@ -1685,7 +1685,7 @@ ODL_UNROLL
 
 __device__ __forceinline__ double odl_mh_uniform(const OdlMcmcArgs& A, int chain_local, int it) {
   if (A.rng_mode != 0) return A.u[(long long)chain_local * A.n_iter_total + (it - 1)];
-  const unsigned long long gchain = (unsigned long long)(A.chain_offset + chain_local);
+  const unsigned long long gchain = A.chain_ids ? (unsigned long long)A.chain_ids[chain_local] : (unsigned long long)(A.chain_offset + chain_local);
   const OdlPhilox r = odl_philox((unsigned int)it, 0u, (unsigned int)gchain, (unsigned int)(gchain >> 32),
                                  (unsigned int)A.seed, (unsigned int)(A.seed >> 32));
   return odl_u53(r.x, r.y);
@@ -2221,7 +2221,7 @@ __device__ __forceinline__ void odl_coop_propose(const OdlGroup& G, const OdlMcm
   }
   for (int q = G.sub; q < ODL_P; q += ODL_G) G.psm[q] = cur[q];
   __syncwarp(G.mask);
-  const unsigned long long gchain = (unsigned long long)(A.chain_offset + chain);
+  const unsigned long long gchain = A.chain_ids ? (unsigned long long)A.chain_ids[chain] : (unsigned long long)(A.chain_offset + chain);
   for (int j = G.sub; j < A.n_walk; j += ODL_G) {
     double z;
     if (A.rng_mode == 1) {

@@ -262,7 +262,8 @@ class DeviceModel:
     # -- Metropolis-Hastings: Samplers.py:53-174 for many chains -----------------------------------
     def mcmc(self, theta0, nits=1000, burnin=None, walk=None, pnum=None, rng_mode="philox", seed=0, chain_offset=0,
              z=None, u=None, forced=None, rtol=None, atol=None, max_steps=500000, solver="dopri5", step_sd=0.05,
-             trace=False, keep_samples=True, summaries=True, segments=1, device_buffers=False, speculate=0):
+             trace=False, keep_samples=True, summaries=True, segments=1, device_buffers=False, speculate=0,
+             chain_ids=None):
         """Run len(theta0) independent chains.  Returns dict with numpy arrays (or torch tensors when
         device_buffers=True): theta (final points), samples [C, nits-1-burnin, P+5], summaries
         [C, 1+2P], chain_state [C,8] (chi, r2, accepts, best_chi, best_iteration, ...), best_theta [C, P] (the
@@ -314,8 +315,15 @@ class DeviceModel:
         fails = new((Cn,), i32)
         steps = new((Cn,), i64)
         z, u, forced = conv(z), conv(u), conv(forced)
+        ids = None
+        if chain_ids is not None:                               # global chain index per chain (Philox key)
+            if device_buffers:
+                ids = torch.as_tensor(np.asarray(chain_ids, dtype=np.int64), device=dev).contiguous()
+            else:
+                ids = np.ascontiguousarray(chain_ids, dtype=np.int64)
+            assert ids.shape[0] == Cn
         io = _capi.McmcIO(_ptr(theta), _ptr(state), _ptr(samples), _ptr(summ), _ptr(z), _ptr(u), _ptr(forced),
-                          _ptr(tr_chi), _ptr(tr_acc), _ptr(fails), _ptr(steps), _ptr(best))
+                          _ptr(tr_chi), _ptr(tr_acc), _ptr(fails), _ptr(steps), _ptr(best), _ptr(ids))
         # optional segmentation of long chains into several launches (state persists in the buffers)
         bounds = np.linspace(1, nits, int(segments) + 1).astype(int)
         ms = 0.0

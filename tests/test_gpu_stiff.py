@@ -174,3 +174,38 @@ def test_facade_picks_the_bdf_kernel_for_a_stiff_posterior():
     th = dict(zip(m2.get_pnames(), g["chain_def_s0_theta0"]))
     m2.MCMC(chain_inits=[th] * 2, iterations_per_chain=40, print_report=False)
     assert m2._last_solver == "dopri5"
+
+
+def test_chains_that_exhaust_the_explicit_budget_are_rerun_on_bdf():
+    """solver='auto' on a non-stiff start: DOPRI5 with a bounded step budget per solve; a chain that ever exhausts it is
+    re-run whole on the BDF kernel with the same random streams (chain_ids keep its Philox key).  Every chain is then
+    either the plain DOPRI5 chain or the plain BDF chain, bit for bit."""
+    import scipy.stats
+    import odelib_b200 as ODElib
+    from odelib_b200 import demo_models
+    pobj = {p: ODElib.parameter(stats_gen=scipy.stats.lognorm, hyperparameters={"s": s, "scale": sc}, init_value=sc)
+            for p, (s, sc) in demo_models.PRIORS["two_i"].items()}
+    m = ODElib.ModelFramework(ODE=demo_models.two_i, parameter_names=demo_models.PARAMETER_NAMES["two_i"],
+                              state_names=demo_models.STATE_NAMES["two_i"], dataframe=demo_df("two_i"),
+                              state_summations={"H": ["S", "I1", "I2"]}, S=5236900, **pobj)
+    m.EXPLICIT_STEP_BUDGET = 230                                 # low enough that some chains of this set exhaust it
+    rng = np.random.default_rng(3)
+    center = np.array([7.475e-09, 1.069e-07, 19.73, 1.934, 2.799])
+    starts = center * np.exp(0.3 * rng.standard_normal((48, 5)))
+    dm = m._device()
+    probe = dm.sweep(starts, solver="dopri5", max_steps=230)
+    starts = starts[probe["status"] == 0][:32]                  # all starts themselves are within the budget
+    assert len(starts) >= 16
+    C, nits = len(starts), 60
+    raw = m._run_chains([s for s in starts], list(range(C)), nits, nits // 2, [], rng="philox", return_raw=True)
+    assert m._last_solver == "dopri5" and 0 < m._last_rerun < C
+    assert raw["fail_count"].sum() == 0
+    plain = dm.mcmc(starts, nits=nits, rng_mode="philox", seed=int(m.random_seed), chain_ids=np.arange(C), max_steps=230)
+    bdf = dm.mcmc(starts, nits=nits, rng_mode="philox", seed=int(m.random_seed), chain_ids=np.arange(C), solver="bdf",
+                  max_steps=2000000)
+    bad = plain["fail_count"] > 0
+    assert bad.sum() == m._last_rerun
+    assert np.array_equal(raw["samples"][~bad], plain["samples"][~bad])
+    assert np.array_equal(raw["samples"][bad], bdf["samples"][bad])
+    assert np.array_equal(raw["summaries"][bad], bdf["summaries"][bad])
+    assert np.array_equal(raw["best_chi"][bad], bdf["best_chi"][bad], equal_nan=True)
