@@ -330,6 +330,26 @@ def run_ours(args):
                                   "fp64_tflops_per_gpu": steps_l * flops_step / t_l / 1e12 / world,
                                   "frac_of_fp64_peak": steps_l * flops_step / t_l / 1e12 / world / peak_tflops}
 
+    # ---- the callers either side of the path, through the reference's own API (rank 0 only; not part of `value`) ----
+    facade = None
+    if rank == 0 and not args.no_facade:
+        np.random.seed(0)
+        model.fit_survey(samples=1000)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        sv = model.fit_survey(samples=n)                          # device LHS + sweep + frame
+        torch.cuda.synchronize(); t_sv = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        summ = model.MCMC(chain_inits=4096, iterations_per_chain=200, fitsurvey_samples=n, sd_fitdistance=6.0,
+                          print_report=False, posterior="summary")
+        t_mc = time.perf_counter() - t0
+        facade = {"fit_survey": {"samples": n, "seconds": t_sv, "rows_below_chi_666": int((sv["chi"] < 666).sum()),
+                                 "api": "ModelFramework.fit_survey(samples) -> frame [samples, P+1] (device LHS, odl_sweep)"},
+                  "mcmc_from_survey": {"chains": 4096, "iterations_per_chain": 200, "fitsurvey_samples": n, "seconds": t_mc,
+                                       "chains_rerun_on_bdf": int(getattr(model, "_last_rerun", 0)),
+                                       "best_chi": summ.best_chi,
+                                       "api": "ModelFramework.MCMC(chain_inits=4096, posterior='summary'): survey, start "
+                                              "selection, chains, report reductions on the device"}}
+
     launches = _capi.lib().odl_launch_count() - launches0
 
     # ---- CPU baseline (rank 0, N=1 only): the reference's algorithm on the host cores ---------------
@@ -368,7 +388,7 @@ def run_ours(args):
                                  "achieved_GBps": bytes_launch / (avg_ms * 1e-3) / 1e9, "peak_GBps": hbm_peak(),
                                  "frac": bytes_launch / (avg_ms * 1e-3) / 1e9 / hbm_peak()}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(timed_launches), "gpu_launches_total": int(launches),
-            "clocks": clk, "ok_fraction": ok_frac, "mcmc": mcmc,
+            "clocks": clk, "ok_fraction": ok_frac, "mcmc": mcmc, "facade": facade,
         }
         print(json.dumps(line))
     if world > 1:
@@ -402,6 +422,7 @@ def main():
     ap.add_argument("--chains-large", type=int, default=65536, help="chains per GPU for the filled-GPU MCMC measurement (0 = skip)")
     ap.add_argument("--nits-large", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-facade", action="store_true", help="skip the fit_survey / MCMC-from-survey timings")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

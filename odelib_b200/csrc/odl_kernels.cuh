@@ -1051,9 +1051,14 @@ struct OdlBdfAux {
   double E[ODL_BDF_MAXORD + 2][ODL_N];   // E[k] = D[order+2-k], k = 0 .. order+1
   OdlLU lu;                              // LU of I - (h/alpha_q) J
   int order, n_equal;
+  int phase;                             // calls of odl_bdf_attempt for this system (waiting calls included)
+  int pend_order;                        // a step-size / order change that has been decided but not applied yet:
+  double pend_factor;                    //   new order, ratio new/old step (0 = none)
   float crate;                           // Newton contraction rate carried from step to step (reset with the LU)
   bool have_lu, started;
-  __device__ __forceinline__ void reset() { started = false; have_lu = false; order = 1; n_equal = 0; crate = 1.f; }
+  __device__ __forceinline__ void reset() {
+    started = false; have_lu = false; order = 1; n_equal = 0; crate = 1.f; phase = 0; pend_order = 1; pend_factor = 0.0;
+  }
 };
 
 // D[1..q_new] <- (R(factor) U)^T D[1..q_new]: the differences of the same interpolating polynomial on a grid
@@ -1145,14 +1150,26 @@ ODL_UNROLL
 ODL_UNROLL
       for (int c = 0; c < ODL_N; ++c) ax.E[k][c] = (k == 2) ? h * st.k1[c] : 0.0;
   }
-  const int q = ax.order;
-  double h = st.h;
-  bool last = false;
-  if ((t + 1.01 * h - st.tend) > 0.0) {
-    const double hn = st.tend - t;
-    if (hn != h) { odl_bdf_change_D(ax, q, q, hn / h); ax.n_equal = 0; ax.have_lu = false; }
-    h = hn; st.h = hn; last = true;
+  // Every change of the difference array -- order / step-size selection, a rejected step, a Newton failure, the
+  // clamp onto t_end -- is DECIDED where it arises (st.h already holds the new step) and APPLIED here, at the one
+  // place odl_bdf_change_D is inlined, on calls whose number is a multiple of 3.  The lanes of a warp share their
+  // call count, so the ~330 instructions are issued every third warp step for all lanes that need them, instead of on
+  // a quarter of all warp steps for the one lane that just rejected; a lane with a pending change waits (at most two
+  // calls).  The rule looks at this system only: a solve does not depend on its warp mates.
+  ++ax.phase;
+  bool force = false;
+  if (ax.pend_factor == 0.0 && (t + 1.01 * st.h - st.tend) > 0.0 && (st.tend - t) != st.h) {
+    ax.pend_factor = (st.tend - t) / st.h; ax.pend_order = ax.order; st.h = st.tend - t;      // once per solve: no waiting
+    force = true;
   }
+  if (ax.pend_factor != 0.0) {
+    if (!force && (ax.phase % 3) != 0) return;
+    odl_bdf_change_D(ax, ax.order, ax.pend_order, ax.pend_factor);
+    ax.order = ax.pend_order; ax.pend_factor = 0.0; ax.n_equal = 0; ax.have_lu = false;
+  }
+  const int q = ax.order;
+  const double h = st.h;
+  const bool last = (t + 1.01 * h - st.tend) > 0.0;              // after the clamp h == t_end - t exactly
   ++st.nsteps;
   const double tn = last ? st.tend : t + h;
   const double ralpha = ODL_BDF_RALPHA[q];
@@ -1222,7 +1239,7 @@ ODL_UNROLL
   if (!converged) {
     ax.have_lu = false;
     if (fresh) {                                                // a current Jacobian did not help: halve the step
-      odl_bdf_change_D(ax, q, q, 0.5);
+      ax.pend_factor = 0.5; ax.pend_order = q;
       ax.n_equal = 0;
       st.h = 0.5 * h;
       if (!(st.h > hmin)) st.status = ODL_HUNDERFLOW;
@@ -1242,7 +1259,7 @@ ODL_UNROLL
 #endif
     const float fac = (err == err && err < 3.0e38f && finite_all)
                           ? fmaxf(0.2f, safety * exp2f(-__log2f(err) * (float)ODL_BDF_INV[q + 1])) : 0.2f;
-    odl_bdf_change_D(ax, q, q, (double)fac);
+    ax.pend_factor = (double)fac; ax.pend_order = q;
     ax.n_equal = 0; ax.have_lu = false;
     st.h = h * (double)fac;
     if (!(st.h > hmin)) st.status = ODL_HUNDERFLOW;
@@ -1284,12 +1301,9 @@ ODL_UNROLL
   for (int c = 0; c < ODL_N; ++c) st.y[c] = yk[c];
   st.t = tn;
   if (st.nsteps >= O.max_steps && st.slot < D.n_slot && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
-  // The order/step-size selection (+ change_D + Jacobian + LU, ~500 instructions) runs only on attempt numbers
-  // that are multiples of 3 (orders 1-2) or 6 (orders 3-5): the lanes of a warp step in lock step and mostly
-  // share their attempt count, so the expensive branch is issued every few warp steps for many lanes at once
-  // instead of on nearly every warp step for one lane or another.  The rule looks at this system only -- the
-  // result of a solve must not depend on which systems share its warp.
-  if (ax.n_equal < q + 1 || st.slot >= D.n_slot || (st.nsteps % (q >= 3 ? 6 : 3)) != 0) return;
+  // The order/step-size selection is taken on calls whose successor is a multiple of 3 (orders 1-2) or 6 (orders
+  // 3-5), so that its change of the difference array is applied on an aligned call (see the top of this function).
+  if (ax.n_equal < q + 1 || st.slot >= D.n_slot || ((ax.phase + 1) % (q >= 3 ? 6 : 3)) != 0) return;
   // ---- order / step-size selection (every q+1 equal steps) ----
   float f_m = 0.f, f_p = 0.f;
   const float f_0 = (err > 0.f) ? exp2f(-__log2f(err) * (float)ODL_BDF_INV[q + 1]) : 3.0e38f;
@@ -1312,9 +1326,11 @@ ODL_UNROLL
     ax.n_equal = (q > 2) ? q - 2 : 0;
     return;
   }
-  odl_bdf_change_D(ax, q, qn, (double)fac);
-  ax.order = qn; ax.n_equal = 0; ax.have_lu = false;
-  st.h = h * (double)fac;
+  double hn = h * (double)fac;
+  if ((st.t + 1.01 * hn - st.tend) > 0.0) hn = st.tend - st.t;  // the clamp onto t_end, folded into this change
+  ax.pend_factor = hn / h; ax.pend_order = qn;                  // applied at the top of the next call (an aligned one)
+  ax.n_equal = 0;
+  st.h = hn;
 }
 
 template <int SOLVER> struct OdlAuxOf { typedef OdlNoAux type; };
