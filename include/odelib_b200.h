@@ -18,6 +18,10 @@
  *   odl_mcmc             <- Samplers.MetropolisHastings (Statistics/Samplers.py:53-174) for many
  *                           chains at once; _Chain_worker / the serial loop (Framework.py:19-22,
  *                           :1025-1030).
+ *   odl_select_below,    <- chain-start selection of MCMC(chain_inits=int): the threshold filter and the
+ *   odl_gather_rows         resampling of acceptable survey rows (Framework.py:993-1016).
+ *   odl_sample_lhs       <- Samplers.sample_lhs (Statistics/Samplers.py:6-51) under _lhs_samples
+ *                           (Framework.py:589-615), for large surveys.
  *   odl_fp64_peak        <- (no reference counterpart) measures the FP64 FMA roofline denominator.
  *
  * Conventions: every function returns 0 on success or an ODL_E* code; odl_last_error() gives the
@@ -134,7 +138,7 @@ int odl_model_destroy(odl_model* m);
 /* compile log of the NVRTC run (warnings included); valid until the model is destroyed */
 const char* odl_model_build_log(const odl_model* m);
 /* resource usage of a compiled kernel ("sweep", "mcmc", "traj", "sweep_ros23", "mcmc_ros23", "mcmc_auto",
-   "sweep_radau5", "mcmc_radau5", "sweep_bdf", "mcmc_bdf"):
+   "sweep_radau5", "mcmc_radau5", "sweep_bdf", "mcmc_bdf", and for n_state > 8 "sweep_coop", "mcmc_coop"):
    registers/thread, local (spill) bytes, resident CTAs per SM */
 int odl_model_kernel_info(const odl_model* m, const char* kernel, int* regs, int* local_bytes, int* max_blocks_per_sm);
 
@@ -170,8 +174,9 @@ int odl_sample_lhs(odl_model* m, long long n, int n_param, const int* kind, cons
 /* device time (ms) of the kernels launched by the last odl_sweep/odl_mcmc/odl_trajectory call on this
    model, measured with CUDA events on the launching stream; blocks until they have completed */
 int odl_model_last_kernel_ms(odl_model* m, float* ms);
-/* the same split for the last ODL_SOLVER_AUTO sweep: ms3[0] cost ordering, ms3[1] DOPRI5 bulk pass, ms3[2] what the
-   stiff pass (running beside the bulk pass) still needed after the bulk pass had ended (single-pass calls: ms3[0]) */
+/* the same split for the last ODL_SOLVER_AUTO sweep: ms3[0] cost ordering (of the first piece), ms3[1] DOPRI5 bulk
+   pass, ms3[2] stiff pass -- with ODL_AUTO_CONCURRENT: what it still needed after the bulk pass had ended
+   (single-pass calls: ms3[0]) */
 int odl_model_last_pass_ms(odl_model* m, float* ms3);
 /* development aid: copies the first `count` ints of the device-side counter block of the last odl_sweep
    ([0] work counter, [16] feed count, [32] feed ticket, [48] warps entered, [64] warps left, [80] watchdog) */
