@@ -212,3 +212,31 @@ def test_host_memory_sweep_in_two_pieces_equals_one_piece_and_the_device_call():
     for k in ("chi", "r2", "status", "nsteps"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
         assert np.array_equal(a[k], c[k].cpu().numpy(), equal_nan=True), k
+
+
+def test_auto_sweep_rows_of_both_steppers_against_the_oracle():
+    """The default path on real prior draws: rows the DOPRI5 pass finished and rows the BDF pass finished, each against
+    odeint at 1e-12 (healthy observations: the reference's own default-tolerance error there is ~1e-7, LSODA's stiff
+    branch up to 5e-7)."""
+    dm, tab = device_model("two_i")
+    theta = prior_draws("two_i", 30000, seed=21)
+    out = dm.sweep(theta, solver="auto", max_steps=200000, return_pred=True)
+    assert np.all(out["status"] == 0)
+    dop = dm.sweep(theta, solver="dopri5", max_steps=512, stiff_check=True, early_check_steps=256)
+    by_bdf = np.flatnonzero(dop["status"] != 0)
+    by_dop = np.flatnonzero(dop["status"] == 0)
+    assert len(by_bdf) > 300
+    rhs = oracle_rhs("two_i")
+    rng = np.random.default_rng(0)
+    worst = {}
+    for label, rows, bound in (("dopri5", rng.choice(by_dop, 30, replace=False), 2e-6), ("bdf", rng.choice(by_bdf, 30, replace=False), 5e-6)):
+        errs = []
+        for k in rows:
+            vec, chi, _ = orc.solve_unit(rhs, theta[k], tab, 1e-12, 1e-12, mxstep=500000)
+            ok = vec > FLOOR
+            if ok.sum() < 30:
+                continue
+            errs.append(np.max(np.abs(out["pred"][k][ok] - vec[ok]) / vec[ok]))
+        assert len(errs) >= 15
+        worst[label] = max(errs)
+        assert worst[label] < bound, (label, worst)
