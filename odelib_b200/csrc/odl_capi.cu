@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <unistd.h>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -222,7 +223,7 @@ static int compile_model(odl_model* m, const std::string& src, const char* cache
   nvrtcGetCUBIN(prog, m->cubin.data());
   nvrtcDestroyProgram(&prog);
   if (!path.empty()) {
-    std::string tmp = path + ".tmp";
+    std::string tmp = path + ".tmp." + std::to_string((long long)getpid());   // one writer per file: ranks compile the same model
     if (FILE* f = fopen(tmp.c_str(), "wb")) {
       fwrite(m->cubin.data(), 1, sz, f);
       fclose(f);
