@@ -197,3 +197,31 @@ def test_device_latin_hypercube_sampling_of_the_priors():
     with pytest.raises(NotImplementedError):
         m.parameters["mu"].dist = scipy.stats.gamma
         m.fit_survey(samples=10, sampler="device")
+
+
+def test_edge_sizes_of_the_device_side_helpers():
+    """Empty and one-row inputs of odl_select_below / odl_gather_rows / odl_sample_lhs, and bad arguments."""
+    import torch
+    from odelib_b200 import _capi
+    m = make_model("zero_i")
+    dm = m._device()
+    empty = torch.empty(0, dtype=torch.float64, device="cuda")
+    idx, c = dm.select_below(empty, 1.0)
+    assert c == 0 and idx.numel() == 0
+    one = torch.tensor([0.5], dtype=torch.float64, device="cuda")
+    assert dm.select_below(one, 1.0)[1] == 1 and dm.select_below(one, 0.5)[1] == 0          # strict <
+    nan = torch.tensor([float("nan"), 2.0, float("inf"), -1.0], dtype=torch.float64, device="cuda")
+    idx, c = dm.select_below(nan, float("inf"))
+    assert c == 2 and idx[:2].cpu().tolist() == [1, 3]
+    src = torch.arange(12, dtype=torch.float64, device="cuda").reshape(4, 3)
+    assert dm.gather_rows(src, np.array([], dtype=np.int64)).shape == (0, 3)
+    got = dm.gather_rows(src, np.array([3, 3, 0]))
+    assert got.cpu().tolist() == [[9, 10, 11], [9, 10, 11], [0, 1, 2]]
+    table = m._prior_table()
+    assert dm.sample_lhs(table, 0).shape == (0, 3)
+    one_row = dm.sample_lhs(table, 1, seed=1).cpu().numpy()
+    assert one_row.shape == (1, 3) and np.all(np.isfinite(one_row)) and np.all(one_row > 0)
+    three = dm.sample_lhs(table, 3, seed=1).cpu().numpy()
+    assert len(set(np.argsort(three[:, 0]))) == 3
+    with pytest.raises(_capi.OdlError):
+        dm.sample_lhs([(7, 1.0, 0.0, 1.0)] * 3, 4)                # unknown prior kind
