@@ -103,7 +103,9 @@ typedef struct odl_mcmc_opts {
   unsigned long long seed;
   int speculate;       /* lanes per chain that evaluate consecutive iterations at once along the all-rejected path
                           (prefetching MH; a power of two <= 32).  The chain is the same for every value;
-                          0 = automatic (fills an otherwise latency-bound GPU), 1 = one proposal at a time */
+                          0 = automatic (fills an otherwise latency-bound GPU), 1 = one proposal at a time.
+                          n_state > 8: values >= 1 select the thread-per-system kernel; 0 and negative values the
+                          cooperative kernel, -K = K groups of coop_lanes lanes per chain (K * coop_lanes <= 32) */
   int reserved;
 } odl_mcmc_opts;
 

@@ -837,12 +837,23 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   const size_t smem = smem_bytes(D, (int)block);
   unsigned grid = (unsigned)((threads + block - 1) / block);
   if (solver == ODL_SOLVER_DOPRI5 && m->k_mcmc_coop && mo->speculate <= 0) {
-    // n > 8: one chain per group of lanes (odl_mcmc_coop_kernel); the chain is the same chain as with every other mapping
+    // n > 8: one chain per K groups of lanes (odl_mcmc_coop_kernel); the chain is the same chain as with every other
+    // mapping.  speculate = -K asks for K groups per chain (K * coop_lanes <= 32), 0 = automatic as above
     const size_t smem_c = coop_smem_bytes(m, D);
     if (smem_c > 227 * 1024) return fail(ODL_ECUDA, "cooperative MCMC kernel: tables + staging exceed shared memory");
     if (smem_c > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(m->k_mcmc_coop, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem_c));
-    const long long lanes = (long long)C * m->coop;
-    A.spec = 1;
+    int per_sm_c = 0;
+    ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, m->k_mcmc_coop, (int)kCoopBlock, smem_c));
+    const int kmax = 32 / m->coop;
+    int Kc = -mo->speculate;
+    if (Kc <= 0) {
+      const long long resident_c = (long long)m->sm_count * std::max(1, per_sm_c) * kCoopBlock;
+      Kc = 1;
+      while (Kc < kmax && (long long)C * m->coop * Kc * 2 * 2 <= resident_c) Kc *= 2;
+    }
+    if (Kc > kmax || (Kc & (Kc - 1))) return fail(ODL_EINVAL, "odl_mcmc: -speculate must be a power of two with speculate * coop_lanes <= 32");
+    const long long lanes = (long long)C * m->coop * Kc;
+    A.spec = Kc;
     ODL_CUDA(cudaEventRecord(m->ev0, s));
     void* params_c[] = {&D, &O, &A};
     m->n_pass = 1;

@@ -2258,91 +2258,129 @@ __device__ __forceinline__ void odl_coop_propose(const OdlGroup& G, const OdlMcm
   __syncwarp(G.mask);
 }
 
+// One chain per K groups (A.spec = K, a power of two with K * ODL_G <= 32): prefetching MH as in odl_mcmc_body, a
+// group taking the place of a lane -- group kk evaluates iteration it+kk along the all-rejected path, the K groups
+// consume iterations up to and including the first acceptance.  The chain does not depend on K.
 extern "C" __global__ void __launch_bounds__(ODL_COOP_BLOCK, ODL_COOP_MINBLOCKS)
 odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
   const OdlShared S = odl_carve(odl_smem, D);
   odl_load_tables(S, D);
   const OdlGroup G = odl_coop_group(S, D);
+  const int lane = threadIdx.x & 31;
+  int K = (A.spec >= 1) ? A.spec : 1;
+  if (K * ODL_G > 32) K = 32 / ODL_G;
+  const int span = K * ODL_G;                                      // lanes of one chain
+  const int kk = (lane / ODL_G) & (K - 1);                         // this group's place among the chain's groups
+  const int sbase = lane & ~(span - 1);
+  const unsigned smask = (span == 32) ? 0xffffffffu : (((1u << span) - 1u) << sbase);
   const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int chain = (int)(gthread / ODL_G);
-  if (gthread / ODL_G >= (long long)A.n_chain) return;             // whole groups leave together
+  const int chain = (int)(gthread / span);
+  if (gthread / span >= (long long)A.n_chain) return;             // the lanes of a chain leave together
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  const bool lead = G.sub == 0;
+  const size_t group_doubles = (size_t)ODL_N + ODL_P + D.stage_stride;
   double* cs = A.chain_state + (size_t)chain * ODL_CHAIN_STATE;
   double* cur = A.theta_cur + (size_t)chain * ODL_P;
   OdlCoopStepper st;
+  st.status = ODL_OK; st.nsteps = 0;
   bool apriori = A.it_begin == 1;
   int it = A.it_begin;
   while (apriori || it < A.it_end) {
-    if (apriori) {
-      for (int q = G.sub; q < ODL_P; q += ODL_G) G.psm[q] = cur[q];
-      __syncwarp(G.mask);
-    } else {
-      odl_coop_propose(G, A, chain, it);
-    }
-    odl_coop_init(st, G, D, O);
-    while (st.slot < D.n_slot && st.status == ODL_OK) odl_coop_attempt(st, G, S, D, O);
-    double chi, ss; int nv;
-    odl_coop_score(S, D, G, nullptr, chi, ss, nv);
+    const bool valid = apriori ? (kk == 0) : (it + kk < A.it_end);
     double my_chi = nan, my_r2 = nan;
-    if (st.status == ODL_OK) { my_chi = (nv > 0) ? chi : nan; my_r2 = 1.0 - ss / D.sstot; }
-    if (G.sub == 0) {
-      if (A.step_count) A.step_count[chain] += st.nsteps;
-      if (A.fail_count && st.status != ODL_OK) A.fail_count[chain] += 1;
+    if (valid) {
+      if (apriori) {
+        for (int q = G.sub; q < ODL_P; q += ODL_G) G.psm[q] = cur[q];
+        __syncwarp(G.mask);
+      } else {
+        odl_coop_propose(G, A, chain, it + kk);
+      }
+      odl_coop_init(st, G, D, O);
+      while (st.slot < D.n_slot && st.status == ODL_OK) odl_coop_attempt(st, G, S, D, O);
+      double chi, ss; int nv;
+      odl_coop_score(S, D, G, nullptr, chi, ss, nv);
+      if (st.status == ODL_OK) { my_chi = (nv > 0) ? chi : nan; my_r2 = 1.0 - ss / D.sstot; }
     }
     if (apriori) {
-      if (G.sub == 0) { cs[0] = my_chi; cs[1] = my_r2; }
+      if (valid && lead) {
+        cs[0] = my_chi; cs[1] = my_r2;
+        if (A.step_count) A.step_count[chain] += st.nsteps;
+        if (A.fail_count && st.status != ODL_OK) A.fail_count[chain] += 1;
+      }
       apriori = false;
-      __syncwarp(G.mask);
+      __syncwarp(smask);
       continue;
     }
     const double chi_cur = cs[0], r2_cur = cs[1];
     const int accepts = (int)cs[2];
-    const double u = odl_mh_uniform(A, chain, it);
-    const bool accept = exp(chi_cur - my_chi) > u;                 // Samplers.py:124-127 (NaN rejects)
-    __syncwarp(G.mask);                                            // everyone has read the state
-    if (G.sub == 0) {
-      const long long k = (long long)chain * A.n_iter_total + (it - 1);
+    bool acc = false;
+    if (valid) acc = exp(chi_cur - my_chi) > odl_mh_uniform(A, chain, it + kk);   // Samplers.py:124-127 (NaN rejects)
+    const unsigned bacc = __ballot_sync(smask, acc && lead) >> sbase;
+    const int nvalid = __popc(__ballot_sync(smask, valid && lead));               // valid groups are a prefix
+    const int jstar = bacc ? (__ffs(bacc) - 1) / ODL_G : -1;                      // first acceptance
+    const int adv = (jstar >= 0) ? jstar + 1 : nvalid;
+    const bool consumed = valid && kk < adv;
+    const bool is_acc = consumed && kk == jstar;
+    const int src = sbase + (jstar >= 0 ? jstar : 0) * ODL_G;
+    const double chi_acc = __shfl_sync(smask, my_chi, src), r2_acc = __shfl_sync(smask, my_r2, src);
+    const double* pacc = G.psm + (long long)((jstar >= 0 ? jstar : kk) - kk) * (long long)group_doubles;   // accepted proposal (shared)
+    if (consumed && lead) {
+      if (A.step_count) atomicAdd((unsigned long long*)&A.step_count[chain], (unsigned long long)st.nsteps);
+      if (A.fail_count && st.status != ODL_OK) atomicAdd(&A.fail_count[chain], 1);
+      const int iter = it + kk;
+      const long long k = (long long)chain * A.n_iter_total + (iter - 1);
       if (A.trace_chinew) A.trace_chinew[k] = my_chi;
-      if (A.trace_accept) A.trace_accept[k] = accept ? 1 : 0;
-      const double c = accept ? my_chi : chi_cur, r = accept ? my_r2 : r2_cur;
-      const int acc_n = accepts + (accept ? 1 : 0);
-      if (accept) {
-        cs[0] = my_chi; cs[1] = my_r2; cs[2] = (double)acc_n;
-        for (int q = 0; q < ODL_P; ++q) cur[q] = G.psm[q];
-      }
-      if (it > A.burnin) {
-        const int rowi = it - A.burnin - 1;
+      if (A.trace_accept) A.trace_accept[k] = is_acc ? 1 : 0;
+      if (iter > A.burnin) {
+        const int rowi = iter - A.burnin - 1;
         if (A.samples && rowi < A.n_keep) {
           double* rowp = A.samples + ((size_t)chain * A.n_keep + rowi) * A.row_stride;
-          for (int q = 0; q < ODL_P; ++q) rowp[q] = cur[q];
-          rowp[ODL_P + 0] = c; rowp[ODL_P + 1] = r;
+          const double c = is_acc ? my_chi : chi_cur;
+          for (int q = 0; q < ODL_P; ++q) rowp[q] = is_acc ? G.psm[q] : cur[q];
+          rowp[ODL_P + 0] = c; rowp[ODL_P + 1] = is_acc ? my_r2 : r2_cur;
           rowp[ODL_P + 2] = 2.0 * c + 2.0 * (double)A.pnum;
-          rowp[ODL_P + 3] = (double)it;
-          rowp[ODL_P + 4] = (double)acc_n / (double)it;
+          rowp[ODL_P + 3] = (double)iter;
+          rowp[ODL_P + 4] = (double)(accepts + (is_acc ? 1 : 0)) / (double)iter;
         }
-        if (A.summaries) {
-          double* sm = A.summaries + (size_t)chain * (1 + 2 * ODL_P);
-          const double cnt = sm[0] + 1.0;
-          sm[0] = cnt;
+      }
+    }
+    if (kk == 0 && lead) {
+      // Welford over ln(theta) of the kept rows, sequential in the iteration; best kept row (see odl_mcmc_body)
+      if (A.summaries && it + adv - 1 > A.burnin) {
+        double* sm = A.summaries + (size_t)chain * (1 + 2 * ODL_P);
+        double cnt = sm[0];
+        for (int i = 0; i < adv; ++i) {
+          if (it + i <= A.burnin) continue;
+          cnt += 1.0;
           for (int q = 0; q < ODL_P; ++q) {
-            const double x = log(cur[q]);
+            const double x = log((i == jstar) ? pacc[q] : cur[q]);
             const double dlt = x - sm[1 + q];
             const double mean = sm[1 + q] + dlt / cnt;
             sm[1 + q] = mean;
             sm[1 + ODL_P + q] += dlt * (x - mean);
           }
         }
-        // best kept row: the first kept row carries the current point, afterwards only acceptances can improve it
-        const double best_chi = cs[3], best_it = cs[4];
-        const bool first_kept = (it == A.burnin + 1);
-        if (first_kept || (accept && (c < best_chi || (best_chi != best_chi && c == c) || best_it == 0.0))) {
-          cs[3] = c; cs[4] = (double)it;
-          if (A.best_theta) for (int q = 0; q < ODL_P; ++q) A.best_theta[(size_t)chain * ODL_P + q] = cur[q];
-        }
+        sm[0] = cnt;
       }
+      const int first_kept = A.burnin + 1;
+      double best_chi = cs[3], best_it = cs[4];
+      if (it <= first_kept && first_kept < it + adv && first_kept - it != jstar) {
+        best_chi = chi_cur; best_it = (double)first_kept;
+        if (A.best_theta) for (int q = 0; q < ODL_P; ++q) A.best_theta[(size_t)chain * ODL_P + q] = cur[q];
+      }
+      if (jstar >= 0 && it + jstar > A.burnin && (chi_acc < best_chi || (best_chi != best_chi && chi_acc == chi_acc) || best_it == 0.0)) {
+        best_chi = chi_acc; best_it = (double)(it + jstar);
+        if (A.best_theta) for (int q = 0; q < ODL_P; ++q) A.best_theta[(size_t)chain * ODL_P + q] = pacc[q];
+      }
+      cs[3] = best_chi; cs[4] = best_it;
     }
-    ++it;
-    __syncwarp(G.mask);
+    __syncwarp(smask);                                             // everything above read cur[] / cs[] before they change
+    if (is_acc && lead) {
+      cs[0] = my_chi; cs[1] = my_r2; cs[2] = (double)(accepts + 1);
+      for (int q = 0; q < ODL_P; ++q) cur[q] = G.psm[q];
+    }
+    it += adv;
+    __syncwarp(smask);
   }
 }
 #endif  // !ODL_SMALL

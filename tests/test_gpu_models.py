@@ -111,3 +111,8 @@ def test_cooperative_mapping_agrees_with_thread_per_system(which):
     np.testing.assert_allclose(a["summaries"][same], b["summaries"][same], rtol=1e-9, atol=1e-12)
     seg = dm.mcmc(theta[:C], nits=nits, seed=4, trace=True, segments=3)
     assert np.array_equal(seg["samples"], a["samples"]) and np.array_equal(seg["chain_state"], a["chain_state"])
+    # prefetching width of the cooperative kernel (speculate = -K: K groups of lanes per chain): the same chain, bit for bit
+    for K in (1, 2, 4):
+        k = dm.mcmc(theta[:C], nits=nits, seed=4, trace=True, speculate=-K)
+        for key in ("samples", "chinew", "accepted", "summaries", "chain_state", "theta", "step_count", "fail_count", "best_theta"):
+            assert np.array_equal(a[key], k[key], equal_nan=True), (K, key)

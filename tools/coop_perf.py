@@ -31,12 +31,12 @@ if __name__ == '__main__':
         flops_step = 6 * dm.rhs_flops + 71 * dm.n_state + 10
         print(label, "kernel info coop", dm.kernel_info("sweep_coop"), dm.kernel_info("mcmc_coop"), "tps", dm.kernel_info("mcmc"), flush=True)
         rng = np.random.default_rng(2)
-        for C, its in ((2048, 40), (8192, 40)):
+        for C, its in ((2048, 40), (4096, 40), (8192, 40)):
             starts = torch.from_numpy(center * np.exp(0.02 * rng.standard_normal((C, P)))).cuda()
-            for spec in (0,):
+            for spec in (0, -1, -2, -4):
                 t, r = timed(lambda: dm.mcmc(starts, nits=its, rng_mode="philox", seed=1, device_buffers=True, keep_samples=False, speculate=spec))
                 steps = float(r["step_count"].sum().item())
-                print(f"  mcmc chains {C:6d} speculate {spec} ({'coop' if spec == 0 else 'thread-per-system'}): {C * (its - 1) / t / 1e3:9.1f} k chain-steps/s, "
+                print(f"  mcmc chains {C:6d} speculate {spec} ({'coop' if spec <= 0 else 'thread-per-system'}): {C * (its - 1) / t / 1e3:9.1f} k chain-steps/s, "
                       f"{steps * flops_step / t / 1e12:6.3f} TFLOP/s (consumed)", flush=True)
         theta = torch.from_numpy(center * np.exp(0.05 * rng.standard_normal((65536, P)))).cuda()
         for kw, name in ((dict(), "coop dopri5"),):
