@@ -61,6 +61,16 @@ def test_compute_without_gpu_fails_loudly():
     m = engine.DeviceModel(f, n, P, g, compile_only=True)
     with pytest.raises(_capi.OdlError):
         m.sweep(np.ones((4, 3)))
+    # the device-side helpers either side of the path refuse as loudly (no CPU fallback anywhere)
+    L = _capi.lib()
+    cnt = ctypes.c_longlong(0)
+    buf = np.zeros(8)
+    kind = np.zeros(3, np.int32)
+    assert L.odl_select_below(m._h, buf.ctypes.data, 8, 1.0, buf.ctypes.data, ctypes.byref(cnt), None) == _capi.ENODEVICE
+    assert L.odl_gather_rows(m._h, buf.ctypes.data, 2, None, buf.ctypes.data, 1, buf.ctypes.data, None) == _capi.ENODEVICE
+    assert L.odl_sample_lhs(m._h, 2, 3, kind.ctypes.data, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, 0,
+                            buf.ctypes.data, None) == _capi.ENODEVICE
+    assert b"no CPU fallback" in L.odl_last_error()
     m.close()
 
 
