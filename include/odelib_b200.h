@@ -129,6 +129,12 @@ typedef struct odl_mcmc_io {
   const long long* chain_ids; /* optional [n_chain] global chain index per chain (Philox key) for a batch that is not a
                               contiguous block of chains, e.g. the chains re-run with another stepper; default
                               chain_offset + local index */
+  const double* prior_table; /* optional [n_param][4] = (kind, a, b, c) per parameter, kinds and parameterisation as
+                              odl_sample_lhs.  NULL (default) = the reference's chain: prior densities never enter the
+                              acceptance ratio (Samplers.py:118-127; the reference evaluates them and drops them).
+                              Given: Metropolis-Hastings on the posterior, exp((chi-chinew) + (lp'-lp) + sum
+                              ln(theta'/theta)) > u -- prior log-densities evaluated in the kernel, Hastings term of the
+                              multiplicative walk included.  chain_state[5] then holds lp of the current point. */
 } odl_mcmc_io;
 
 int odl_abi_version(void);

@@ -501,7 +501,7 @@ class ModelFramework:
 
     # ------------------------------------------------------------------ MCMC (Framework.py:946-1061)
     def _run_chains(self, starts, seeds, nits, burnin, static_parameters, rng="auto", rtol=None, atol=None,
-                    update_model=False, return_raw=False, return_frame=False, keep_samples=True):
+                    update_model=False, return_raw=False, return_frame=False, keep_samples=True, use_priors=False):
         """All chains in one kernel.  starts: list of theta vectors, or a CUDA tensor [C, P] (chain starts chosen on
         the device); seeds: per-chain seeds (chain index)."""
         dm = self._device()
@@ -533,6 +533,13 @@ class ModelFramework:
         kw = dict(nits=nits, burnin=burnin, walk=walk, pnum=self._pnum, rtol=self.rtol if rtol is None else rtol,
                   atol=self.atol if atol is None else atol, keep_samples=keep_samples, device_buffers=on_device,
                   solver=solver, max_steps=self.EXPLICIT_STEP_BUDGET if retry else 2000000)
+        if use_priors:
+            # not the reference's chain: the reference evaluates the priors and never uses them (Samplers.py:118-127)
+            table = self._prior_table()
+            if table is None:
+                raise NotImplementedError("use_priors supports lognorm / norm / uniform priors (s, loc, scale)")
+            kw["prior"] = [("const", 0, 0, 0) if (p in static or k == "const") else (k, a, b, c)
+                           for p, (k, a, b, c) in zip(self._pnames, table)]
         if rng == "reference":
             walking = [self.parameters[p] for p in walk_names]
             z = np.empty((C, n_iter, len(walk)))
@@ -650,14 +657,18 @@ class ModelFramework:
         return PosteriorSummary(self._pnames, C, N, stats_, best, bchi, rh, acc)
 
     def MCMC(self, chain_inits=1, iterations_per_chain=1000, cpu_cores=1, static_parameters=list(), print_report=True,
-             fitsurvey_samples=1000, sd_fitdistance=3.0, rng="auto", posterior="frame"):
+             fitsurvey_samples=1000, sd_fitdistance=3.0, rng="auto", posterior="frame", use_priors=False):
         """Many Metropolis-Hastings chains (Framework.py:946-1061); returns the concatenated posterior frame
         with a ``chain#`` column.  ``cpu_cores`` is ignored: every chain runs concurrently on the GPU.
 
         The steps either side of the chains stay on the device too: with ``chain_inits=int`` the survey is filtered
         and the starts are gathered there (only the count of acceptable rows comes back), and the fitting report and
         ``set_best_params`` read the kernel's own reductions (pooled log-moments, best kept row, R-hat) instead of
-        scanning the frame.  ``posterior="summary"`` skips the frame altogether and returns a PosteriorSummary."""
+        scanning the frame.  ``posterior="summary"`` skips the frame altogether and returns a PosteriorSummary.
+
+        ``use_priors=True`` (not reference behaviour): the acceptance ratio becomes the posterior's -- prior
+        log-densities of the walking parameters and the Hastings term of the multiplicative walk, evaluated in the
+        kernel.  The reference computes the prior densities every iteration and drops them (Samplers.py:118-127)."""
         if posterior not in ("frame", "summary"):
             raise ValueError("posterior must be 'frame' or 'summary'")
         if isinstance(chain_inits, pd.DataFrame):
@@ -679,7 +690,8 @@ class ModelFramework:
         seeds = list(range(n_chains))                             # chain seed = chain index (:1015, :1020)
         want_frame = posterior == "frame"
         result = self._run_chains(starts, seeds, iterations_per_chain, int(iterations_per_chain / 2), static_parameters,
-                                  rng=rng, return_frame=want_frame, return_raw=not want_frame, keep_samples=want_frame)
+                                  rng=rng, return_frame=want_frame, return_raw=not want_frame, keep_samples=want_frame,
+                                  use_priors=use_priors)
         summary = self.posterior_summary(static_parameters)
         self.rhat = summary.rhat
         if print_report:

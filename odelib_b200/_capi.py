@@ -51,7 +51,7 @@ class McmcIO(C.Structure):
     _fields_ = [("theta", C.c_void_p), ("chain_state", C.c_void_p), ("samples", C.c_void_p),
                 ("summaries", C.c_void_p), ("z", C.c_void_p), ("u", C.c_void_p), ("forced", C.c_void_p),
                 ("trace_chinew", C.c_void_p), ("trace_accept", C.c_void_p), ("fail_count", C.c_void_p),
-                ("step_count", C.c_void_p), ("best_theta", C.c_void_p), ("chain_ids", C.c_void_p)]
+                ("step_count", C.c_void_p), ("best_theta", C.c_void_p), ("chain_ids", C.c_void_p), ("prior_table", C.c_void_p)]
 
 
 _lib = None

@@ -122,6 +122,10 @@ struct OdlMcmcArgs {
   double* best_theta;            // optional [C][n_param] parameters of the best kept row (Framework.py:725-731)
   const long long* chain_ids;    // optional [C] global chain index of every local chain (keys the Philox stream);
                                  //   default chain_offset + local index
+  const double* prior;           // optional [n_param][4] (kind, a, b, c) as odl_sample_lhs: with it the acceptance ratio
+                                 //   is the posterior's, exp((chi-chinew) + (lp'-lp) + sum ln(theta'/theta)); without,
+                                 //   the reference's (priors never enter, Samplers.py:118-127); lp of the current point
+                                 //   lives in chain_state[5]
 };
 
 #endif  // ODL_ABI_H

@@ -796,6 +796,7 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   if ((rc = st.inout(io->chain_state, (size_t)C * ODL_CHAIN_STATE, &A.chain_state, true))) return rc;
   if ((rc = st.inout(io->best_theta, (size_t)C * P, &A.best_theta, it_begin > 1))) return rc;
   if ((rc = st.in(io->chain_ids, (size_t)C, &A.chain_ids))) return rc;
+  if ((rc = st.in(io->prior_table, (size_t)P * 4, &A.prior))) return rc;
   if ((rc = st.inout(io->samples, (size_t)C * n_keep * stride, &A.samples, it_begin > 1))) return rc;
   if ((rc = st.inout(io->summaries, (size_t)C * (1 + 2 * P), &A.summaries, true))) return rc;
   if ((rc = st.in(io->z, (size_t)C * n_iter * mo->n_walk, &A.z))) return rc;

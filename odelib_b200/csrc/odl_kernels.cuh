@@ -1699,6 +1699,37 @@ ODL_UNROLL
   }
 }
 
+// log prior density of one parameter value (scipy.stats parameterisation; table row = kind, a, b, c):
+// 1 lognorm(s = a, loc = b, scale = c), 2 norm(loc = b, scale = c), 3 uniform(loc = b, scale = c), else flat
+__device__ __forceinline__ double odl_log_prior_term(const double* T, double th) {
+  const int kind = (int)T[0];
+  const double a = T[1], b = T[2], c = T[3];
+  const double ninf = __longlong_as_double(0xfff0000000000000LL);
+  if (kind == 1) {
+    const double x = th - b;
+    if (!(x > 0.0)) return ninf;
+    const double lx = log(x / c);
+    return -log(x * a * 2.5066282746310002) - lx * lx / (2.0 * a * a);
+  }
+  if (kind == 2) {
+    const double zz = (th - b) / c;
+    return -log(c * 2.5066282746310002) - 0.5 * zz * zz;
+  }
+  if (kind == 3) return (th >= b && th <= b + c) ? -log(c) : ninf;
+  return 0.0;
+}
+// log prior of a parameter vector, and the Hastings term sum ln(theta'/theta) of the multiplicative walk against `cur`
+// (static parameters contribute ln 1 = 0)
+template <class PV>
+__device__ __forceinline__ void odl_log_prior(const OdlMcmcArgs& A, const PV& p, const double* cur, double& lp, double& hastings) {
+  lp = 0.0; hastings = 0.0;
+ODL_UNROLL
+  for (int q = 0; q < ODL_P; ++q) {
+    lp += odl_log_prior_term(A.prior + 4 * q, p[q]);
+    if (cur) hastings += log(p[q]) - log(cur[q]);
+  }
+}
+
 __device__ __forceinline__ double odl_mh_uniform(const OdlMcmcArgs& A, int chain_local, int it) {
   if (A.rng_mode != 0) return A.u[(long long)chain_local * A.n_iter_total + (it - 1)];
   const unsigned long long gchain = A.chain_ids ? (unsigned long long)A.chain_ids[chain_local] : (unsigned long long)(A.chain_offset + chain_local);
@@ -1799,6 +1830,7 @@ ODL_UNROLL
       // the starting point's own chi: no decision, no iteration consumed
       if (valid) {
         cs[0] = my_chi; cs[1] = my_r2;
+        if (A.prior) { double lp0, h0; odl_log_prior(A, p, nullptr, lp0, h0); cs[5] = lp0; }
         if (A.step_count) atomicAdd((unsigned long long*)&A.step_count[chain], (unsigned long long)st.nsteps);
         if (A.fail_count && st.status != ODL_OK) atomicAdd(&A.fail_count[chain], 1);
       }
@@ -1809,9 +1841,17 @@ ODL_UNROLL
       const int accepts = (int)cs[2];
       // ---- decisions along the all-rejected path: acc = exp(chi - chinew) > u (Samplers.py:124-127; NaN rejects) ----
       bool acc = false;
+      double lp_new = 0.0;
+      double* cur = A.theta_cur + (size_t)chain * ODL_P;
       if (valid) {
         const double u = odl_mh_uniform(A, chain, it + sub);
-        acc = exp(chi_cur - my_chi) > u;
+        if (!A.prior) {
+          acc = exp(chi_cur - my_chi) > u;
+        } else {                                                 // posterior ratio: prior log-densities + Hastings term
+          double hast;
+          odl_log_prior(A, p, cur, lp_new, hast);
+          acc = exp((chi_cur - my_chi) + (lp_new - cs[5]) + hast) > u;
+        }
       }
       const unsigned gacc = (__ballot_sync(ODL_FULL, acc) >> gbase) & gbits;
       const int nvalid = __popc((__ballot_sync(ODL_FULL, valid) >> gbase) & gbits);     // valid lanes are a prefix
@@ -1819,7 +1859,6 @@ ODL_UNROLL
       const int adv = (jstar >= 0) ? jstar + 1 : nvalid;                                  // iterations consumed
       const bool consumed = valid && sub < adv;
       const bool is_acc = consumed && sub == jstar;
-      double* cur = A.theta_cur + (size_t)chain * ODL_P;
       // the accepted proposal, on every lane of the group (for the summaries; lane jstar holds it in p)
       double pacc[ODL_P];
       const int src = gbase + (jstar >= 0 ? jstar : 0);
@@ -1900,6 +1939,7 @@ ODL_UNROLL
       __syncwarp();                                              // everything above read cur[] / cs[] before they change
       if (is_acc) {
         cs[0] = my_chi; cs[1] = my_r2; cs[2] = (double)(accepts + 1);
+        if (A.prior) cs[5] = lp_new;
 ODL_UNROLL
         for (int q = 0; q < ODL_P; ++q) cur[q] = p[q];
       }
@@ -2304,6 +2344,7 @@ odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
     if (apriori) {
       if (valid && lead) {
         cs[0] = my_chi; cs[1] = my_r2;
+        if (A.prior) { double lp0, h0; const OdlSmemView pv{G.psm}; odl_log_prior(A, pv, nullptr, lp0, h0); cs[5] = lp0; }
         if (A.step_count) A.step_count[chain] += st.nsteps;
         if (A.fail_count && st.status != ODL_OK) A.fail_count[chain] += 1;
       }
@@ -2314,7 +2355,18 @@ odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
     const double chi_cur = cs[0], r2_cur = cs[1];
     const int accepts = (int)cs[2];
     bool acc = false;
-    if (valid) acc = exp(chi_cur - my_chi) > odl_mh_uniform(A, chain, it + kk);   // Samplers.py:124-127 (NaN rejects)
+    double lp_new = 0.0;
+    if (valid) {
+      const double u = odl_mh_uniform(A, chain, it + kk);
+      if (!A.prior) {
+        acc = exp(chi_cur - my_chi) > u;                           // Samplers.py:124-127 (NaN rejects)
+      } else {
+        double hast;
+        const OdlSmemView pv{G.psm};
+        odl_log_prior(A, pv, cur, lp_new, hast);
+        acc = exp((chi_cur - my_chi) + (lp_new - cs[5]) + hast) > u;
+      }
+    }
     const unsigned bacc = __ballot_sync(smask, acc && lead) >> sbase;
     const int nvalid = __popc(__ballot_sync(smask, valid && lead));               // valid groups are a prefix
     const int jstar = bacc ? (__ffs(bacc) - 1) / ODL_G : -1;                      // first acceptance
@@ -2377,6 +2429,7 @@ odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
     __syncwarp(smask);                                             // everything above read cur[] / cs[] before they change
     if (is_acc && lead) {
       cs[0] = my_chi; cs[1] = my_r2; cs[2] = (double)(accepts + 1);
+      if (A.prior) cs[5] = lp_new;
       for (int q = 0; q < ODL_P; ++q) cur[q] = G.psm[q];
     }
     it += adv;

@@ -263,11 +263,15 @@ class DeviceModel:
     def mcmc(self, theta0, nits=1000, burnin=None, walk=None, pnum=None, rng_mode="philox", seed=0, chain_offset=0,
              z=None, u=None, forced=None, rtol=None, atol=None, max_steps=500000, solver="dopri5", step_sd=0.05,
              trace=False, keep_samples=True, summaries=True, segments=1, device_buffers=False, speculate=0,
-             chain_ids=None):
+             chain_ids=None, prior=None):
         """Run len(theta0) independent chains.  Returns dict with numpy arrays (or torch tensors when
         device_buffers=True): theta (final points), samples [C, nits-1-burnin, P+5], summaries
         [C, 1+2P], chain_state [C,8] (chi, r2, accepts, best_chi, best_iteration, ...), best_theta [C, P] (the
-        chain's first minimum of chi over its kept rows), and with trace=True chinew/accepted [C, nits-1]."""
+        chain's first minimum of chi over its kept rows), and with trace=True chinew/accepted [C, nits-1].
+
+        prior: None = the reference's chain (prior densities never enter the acceptance ratio, Samplers.py:118-127);
+        a list of (kind, a, b, c) per parameter (as sample_lhs) = Metropolis-Hastings on the posterior, the prior
+        log-densities and the Hastings term of the multiplicative walk evaluated in the kernel."""
         so = self._solver_opts(rtol, atol, max_steps, solver, False)
         P = self.n_param
         walk = list(range(P)) if walk is None else [int(w) for w in walk]
@@ -315,6 +319,12 @@ class DeviceModel:
         fails = new((Cn,), i32)
         steps = new((Cn,), i64)
         z, u, forced = conv(z), conv(u), conv(forced)
+        ptab = None
+        if prior is not None:                                   # (kind, a, b, c) per parameter: posterior-ratio chains
+            rows = [[float(self.PRIOR_KINDS[k] if isinstance(k, str) else k), float(a), float(b), float(c)]
+                    for k, a, b, c in prior]
+            assert len(rows) == P
+            ptab = conv(np.array(rows, dtype=np.float64))
         ids = None
         if chain_ids is not None:                               # global chain index per chain (Philox key)
             if device_buffers:
@@ -323,7 +333,7 @@ class DeviceModel:
                 ids = np.ascontiguousarray(chain_ids, dtype=np.int64)
             assert ids.shape[0] == Cn
         io = _capi.McmcIO(_ptr(theta), _ptr(state), _ptr(samples), _ptr(summ), _ptr(z), _ptr(u), _ptr(forced),
-                          _ptr(tr_chi), _ptr(tr_acc), _ptr(fails), _ptr(steps), _ptr(best), _ptr(ids))
+                          _ptr(tr_chi), _ptr(tr_acc), _ptr(fails), _ptr(steps), _ptr(best), _ptr(ids), _ptr(ptab))
         # optional segmentation of long chains into several launches (state persists in the buffers)
         bounds = np.linspace(1, nits, int(segments) + 1).astype(int)
         ms = 0.0

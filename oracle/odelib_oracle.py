@@ -254,7 +254,7 @@ def reference_streams(seed, n_walk, n_iter, n_prior_draws=None):
 
 
 def mh_chain(rhs, theta0, tab: Tables, n_params_total, nits=1000, burnin=None, walk=None,
-             z=None, u=None, seed=0, rtol=None, atol=None, y0_from_param=None):
+             z=None, u=None, seed=0, rtol=None, atol=None, y0_from_param=None, log_prior=None):
     """Samplers.py:53-174 restated for scalar parameters.
 
     theta0: start values in parameter_names order.  walk: boolean mask of walking parameters
@@ -262,6 +262,12 @@ def mh_chain(rhs, theta0, tab: Tables, n_params_total, nits=1000, burnin=None, w
     (generated with ``reference_streams(seed, ...)`` when omitted).
     y0_from_param: optional {state_index: param_index} for the '<state>0' convention
     (Samplers.py:110-114).
+
+    log_prior: None = the reference's chain (prior densities are evaluated but never enter the ratio,
+    Samplers.py:118-127 -- SURVEY.md A1, A3).  A callable theta -> log prior density switches to the
+    Metropolis-Hastings ratio of the posterior: acc = exp((chi - chinew) + (lp' - lp) + sum(ln theta' - ln theta)),
+    the last term being the Hastings correction of the multiplicative log-normal walk (the `facs` the reference
+    accumulates at Samplers.py:105-109 and drops).  Not reference behaviour: the product's opt-in `use_priors`.
 
     Returns dict with the per-iteration proposals/chinew/decisions and the kept rows
     (theta, chi, rsquared, aic, iteration, acceptance_ratio) exactly as the reference frame.
@@ -285,6 +291,7 @@ def mh_chain(rhs, theta0, tab: Tables, n_params_total, nits=1000, burnin=None, w
     apply_y0(theta)
     _, chi_cur, r2_cur = solve_unit(rhs, theta, tab, rtol, atol, y0)        # :88-90
     aic_cur = aic_of(chi_cur, n_params_total)
+    lp_cur = log_prior(theta) if log_prior is not None else 0.0
     old = theta.copy()
     accepts = 0
     props = np.empty((n_iter, P)); chinews = np.empty(n_iter); decisions = np.zeros(n_iter, bool)
@@ -299,8 +306,15 @@ def mh_chain(rhs, theta0, tab: Tables, n_params_total, nits=1000, burnin=None, w
         _, chinew, r2new = solve_unit(rhs, theta, tab, rtol, atol, y0)     # :115-116
         chinews[k] = chinew
         with np.errstate(all="ignore"):
-            acc = np.exp(np.log(np.exp(chi_cur - chinew)))                 # :124-125
+            if log_prior is None:
+                acc = np.exp(np.log(np.exp(chi_cur - chinew)))             # :124-125
+            else:
+                lp_new = log_prior(theta)
+                hast = float(np.sum(np.log(theta) - np.log(old)))
+                acc = np.exp((chi_cur - chinew) + (lp_new - lp_cur) + hast)
         if acc > u[k]:                                                     # :127  (NaN -> reject)
+            if log_prior is not None:
+                lp_cur = lp_new
             chi_cur, r2_cur = chinew, r2new
             aic_cur = aic_of(chi_cur, n_params_total)
             old = theta.copy()

@@ -225,3 +225,20 @@ def test_edge_sizes_of_the_device_side_helpers():
     assert len(set(np.argsort(three[:, 0]))) == 3
     with pytest.raises(_capi.OdlError):
         dm.sample_lhs([(7, 1.0, 0.0, 1.0)] * 3, 4)                # unknown prior kind
+
+
+def test_mcmc_use_priors_is_opt_in_and_changes_the_target(capsys):
+    """MCMC(use_priors=True): the posterior ratio (device prior log-densities + Hastings term) instead of the
+    reference's likelihood-only ratio; the default stays the reference's chain."""
+    m = make_model("two_i")
+    g = golden("two_i")
+    th = dict(zip(m.get_pnames(), g["chain_def_s0_theta0"]))
+    a = m.MCMC(chain_inits=[th] * 4, iterations_per_chain=120, print_report=False, rng="philox")
+    b = m.MCMC(chain_inits=[th] * 4, iterations_per_chain=120, print_report=False, rng="philox")
+    c = m.MCMC(chain_inits=[th] * 4, iterations_per_chain=120, print_report=False, rng="philox", use_priors=True)
+    assert a.equals(b) and not a.equals(c)
+    assert list(c.columns) == list(a.columns) and len(c) == len(a)
+    # static parameters drop out of the prior product (they never move)
+    d = m.MCMC(chain_inits=[th] * 2, iterations_per_chain=60, print_report=False, rng="philox", use_priors=True,
+               static_parameters=["tau"])
+    assert np.all(d["tau"] == 1)

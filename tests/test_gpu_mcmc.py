@@ -193,3 +193,41 @@ def test_best_kept_row_per_chain_matches_idxmin_of_the_samples():
         assert np.array_equal(out["best_chi"], chi[c, rows])
         assert np.array_equal(out["best_iteration"], out["samples"][c, rows, 5 + 3])
         assert np.array_equal(out["best_theta"], out["samples"][c, rows, :5])
+
+
+def test_posterior_ratio_with_device_prior_log_densities_matches_the_oracle():
+    """Opt-in `prior=` (north_star: the kernel evaluates prior log-densities): acceptance on the posterior ratio with the
+    Hastings term of the multiplicative walk, against the oracle's restatement with scipy's logpdf on the same streams;
+    without `prior=` the chain is the reference's (priors never enter), unchanged."""
+    import scipy.stats
+    dm, tab = device_model("two_i")
+    rng = np.random.default_rng(17)
+    center = np.array([7.475e-09, 1.069e-07, 19.73, 1.934, 2.799])
+    table = [("lognorm", 3.0, 0.0, 1e-8), ("lognorm", 3.0, 0.0, 1e-8), ("norm", 0.0, 20.0, 0.5), ("uniform", 0.0, 0.5, 3.0),
+             ("lognorm", 0.02, 0.0, 2.8)]                        # tight priors on beta / tau: they decide acceptances
+    dists = [scipy.stats.lognorm(3.0, 0.0, 1e-8), scipy.stats.lognorm(3.0, 0.0, 1e-8), scipy.stats.norm(20.0, 0.5),
+             scipy.stats.uniform(0.5, 3.0), scipy.stats.lognorm(0.02, 0.0, 2.8)]
+    log_prior = lambda th: float(sum(d.logpdf(x) for d, x in zip(dists, th)))
+    C, nits = 6, 80
+    starts = center * np.exp(0.02 * rng.standard_normal((C, 5)))
+    z = 0.05 * rng.standard_normal((C, nits - 1, 5))
+    u = rng.random((C, nits - 1))
+    kw = dict(nits=nits, rng_mode="host", z=z, u=u, rtol=1e-11, atol=1e-11, trace=True, max_steps=2000000)
+    plain = dm.mcmc(starts, **kw)
+    with_prior = dm.mcmc(starts, prior=table, **kw)
+    assert (plain["accepted"] != with_prior["accepted"]).sum() > 5            # the priors change decisions
+    rhs = oracle_rhs("two_i")
+    for c in range(3):
+        ref = orc.mh_chain(rhs, starts[c], tab, 5, nits=nits, z=z[c], u=u[c], rtol=1e-12, atol=1e-12, log_prior=log_prior)
+        assert np.array_equal(with_prior["accepted"][c].astype(bool), ref["accepted"])
+        np.testing.assert_allclose(with_prior["samples"][c][:, :5], ref["kept"][:, :5], rtol=1e-12)
+        ref0 = orc.mh_chain(rhs, starts[c], tab, 5, nits=nits, z=z[c], u=u[c], rtol=1e-12, atol=1e-12)
+        assert np.array_equal(plain["accepted"][c].astype(bool), ref0["accepted"])
+    # the current point's log prior rides in chain_state[5]; prefetching width does not change the chain
+    lp_end = [log_prior(th) for th in with_prior["theta"]]
+    np.testing.assert_allclose(with_prior["chain_state"][:, 5], lp_end, rtol=1e-12)
+    for K in (1, 8):
+        k = dm.mcmc(starts, prior=table, speculate=K, **kw)
+        assert np.array_equal(k["samples"], with_prior["samples"]) and np.array_equal(k["accepted"], with_prior["accepted"])
+    out = dm.mcmc(starts, prior=[("uniform", 0.0, 1.0, 1.0)] * 5, **kw)       # every proposal outside the support
+    assert out["accepted"].sum() == 0

@@ -111,6 +111,13 @@ def test_cooperative_mapping_agrees_with_thread_per_system(which):
     np.testing.assert_allclose(a["summaries"][same], b["summaries"][same], rtol=1e-9, atol=1e-12)
     seg = dm.mcmc(theta[:C], nits=nits, seed=4, trace=True, segments=3)
     assert np.array_equal(seg["samples"], a["samples"]) and np.array_equal(seg["chain_state"], a["chain_state"])
+    # posterior-ratio chains (prior log-densities in the kernel): both mappings make the same decisions
+    prior = [("lognorm", 0.3, 0.0, float(c_)) for c_ in center]
+    pa = dm.mcmc(theta[:C], nits=nits, seed=4, trace=True, prior=prior)
+    pb = dm.mcmc(theta[:C], nits=nits, seed=4, trace=True, prior=prior, speculate=1)
+    assert (pa["accepted"] != a["accepted"]).sum() > 0 and (pa["accepted"] != pb["accepted"]).sum() <= 1
+    np.testing.assert_allclose(pa["chain_state"][:, 5][(pa["accepted"] == pb["accepted"]).all(axis=1)],
+                               pb["chain_state"][:, 5][(pa["accepted"] == pb["accepted"]).all(axis=1)], rtol=1e-10)
     # prefetching width of the cooperative kernel (speculate = -K: K groups of lanes per chain): the same chain, bit for bit
     for K in (1, 2, 4):
         k = dm.mcmc(theta[:C], nits=nits, seed=4, trace=True, speculate=-K)
