@@ -1746,6 +1746,22 @@ __device__ __forceinline__ double odl_mh_uniform(const OdlMcmcArgs& A, int chain
 // including the first acceptance, discarding the rest.  Proposals and uniforms are keyed by (chain, iteration),
 // so the chain is the SAME chain, decision by decision and bit by bit, for every K (K = 1 is the plain loop);
 // expected iterations consumed per round (1 - (1-a)^K)/a: 2.7 for K = 4, 3.5 for K = 8 at a = 0.26.
+// One kept row (theta.., chi, rsquared, aic, iteration, acceptance_ratio) to HBM with 16-byte stores: rows are
+// contiguous 8 (P+5)-byte records, so a row starts on a 16-byte boundary or 8 bytes past one.
+__device__ __forceinline__ void odl_store_row(double* row, const double (&v)[ODL_P + 5]) {
+  constexpr int LEN = ODL_P + 5;
+  if ((((unsigned long long)row) & 15ull) == 0ull) {
+#pragma unroll
+    for (int i = 0; i + 1 < LEN; i += 2) *reinterpret_cast<double2*>(row + i) = make_double2(v[i], v[i + 1]);
+    if (LEN & 1) row[LEN - 1] = v[LEN - 1];
+  } else {
+    row[0] = v[0];
+#pragma unroll
+    for (int i = 1; i + 1 < LEN; i += 2) *reinterpret_cast<double2*>(row + i) = make_double2(v[i], v[i + 1]);
+    if (!(LEN & 1)) row[LEN - 1] = v[LEN - 1];
+  }
+}
+
 template <int SOLVER>
 __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O, const OdlMcmcArgs& A) {
   const OdlShared S = odl_carve(odl_smem, D);
@@ -1878,13 +1894,15 @@ ODL_UNROLL
           if (A.samples && rowi < A.n_keep) {
             double* row = A.samples + ((size_t)chain * A.n_keep + rowi) * A.row_stride;
             const double c = is_acc ? my_chi : chi_cur;
+            double v[ODL_P + 5];
 ODL_UNROLL
-            for (int q = 0; q < ODL_P; ++q) row[q] = is_acc ? p[q] : cur[q];
-            row[ODL_P + 0] = c;
-            row[ODL_P + 1] = is_acc ? my_r2 : r2_cur;
-            row[ODL_P + 2] = 2.0 * c + 2.0 * (double)A.pnum;      // stats.py:46
-            row[ODL_P + 3] = (double)iter;
-            row[ODL_P + 4] = (double)(accepts + (is_acc ? 1 : 0)) / (double)iter;   // Samplers.py:153
+            for (int q = 0; q < ODL_P; ++q) v[q] = is_acc ? p[q] : cur[q];
+            v[ODL_P + 0] = c;
+            v[ODL_P + 1] = is_acc ? my_r2 : r2_cur;
+            v[ODL_P + 2] = 2.0 * c + 2.0 * (double)A.pnum;        // stats.py:46
+            v[ODL_P + 3] = (double)iter;
+            v[ODL_P + 4] = (double)(accepts + (is_acc ? 1 : 0)) / (double)iter;   // Samplers.py:153
+            odl_store_row(row, v);
           }
         }
       }
