@@ -179,6 +179,14 @@ int odl_gather_rows(odl_model* m, const double* src_dev, int row_len, const int*
 int odl_sample_lhs(odl_model* m, long long n, int n_param, const int* kind, const double* a, const double* b,
                    const double* c, unsigned long long seed, double* theta_dev, void* stream);
 
+/* The reference chain's own random numbers (host code; works without a GPU): for every chain c, numpy's legacy
+   RandomState(seeds[c]) consumed as Samplers.MetropolisHastings consumes it per iteration (Samplers.py:70, :108,
+   :118-121, :127): n_walk normals N(0, step_sd) -> z[c][i][:], n_prior_draws discarded standard normals (the `rvs` of
+   lognorm / norm priors inside the unused pdf() calls), one uniform -> u[c][i].  z [n_chain][n_iter][n_walk],
+   u [n_chain][n_iter]; feed them to odl_mcmc with ODL_RNG_HOST_STREAMS. */
+int odl_reference_streams(const unsigned int* seeds, int n_chain, int n_iter, int n_walk, int n_prior_draws,
+                          double step_sd, double* z, double* u);
+
 /* device time (ms) of the kernels launched by the last odl_sweep/odl_mcmc/odl_trajectory call on this
    model, measured with CUDA events on the launching stream; blocks until they have completed */
 int odl_model_last_kernel_ms(odl_model* m, float* ms);

@@ -515,9 +515,10 @@ class ModelFramework:
         if not burnin:
             burnin = int(nits / 2)
         if rng == "auto":
-            # the reference's own numpy streams (bit-for-bit the reference chain) are regenerated on the host, one
-            # Python loop per chain: fine for the reference's scale (tens of chains), seconds for thousands
-            rng = "reference" if C <= 256 and C * n_iter * (2 * len(walk) + 1) <= 20_000_000 else "philox"
+            # the reference's own numpy streams (bit-for-bit the reference chain), regenerated on the host by the
+            # library (odl_reference_streams) while the streams stay small next to the run (160 MB of host memory);
+            # Philox on the device beyond that
+            rng = "reference" if C * n_iter * (len(walk) + 1) <= 20_000_000 else "philox"
         solver = self.solver
         if solver == "auto":
             probe = dm.sweep(theta0, rtol=self.rtol if rtol is None else rtol, atol=self.atol if atol is None else atol,
@@ -542,10 +543,7 @@ class ModelFramework:
                            for p, (k, a, b, c) in zip(self._pnames, table)]
         if rng == "reference":
             walking = [self.parameters[p] for p in walk_names]
-            z = np.empty((C, n_iter, len(walk)))
-            u = np.empty((C, n_iter))
-            for c, seed in enumerate(seeds):
-                z[c], u[c] = Samplers.reference_streams(seed, walking, n_iter)
+            z, u = Samplers.reference_streams_batch(seeds, walking, n_iter)
             streams = dict(rng_mode="host", z=z, u=u)
         elif rng == "philox":
             streams = dict(rng_mode="philox", seed=int(self.random_seed), chain_ids=np.asarray(seeds, dtype=np.int64))

@@ -17,6 +17,7 @@
 #include <unistd.h>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/odelib_b200.h"
@@ -1130,6 +1131,86 @@ extern "C" int odl_sample_lhs(odl_model* m, long long n, int n_param, const int*
   g_launches.fetch_add(1);
   ODL_CUDA(cudaGetLastError());
   ODL_CUDA(cudaStreamSynchronize(s));                              // the host arrays may be reused by the caller
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The reference chain's own random numbers, regenerated on the host (pure CPU code, no GPU needed): numpy's legacy
+// RandomState(seed) -- MT19937 seeded with init_genrand, doubles from two 32-bit words, gaussians by the polar method
+// with its one-value cache -- consumed exactly as Samplers.MetropolisHastings consumes it per iteration
+// (Samplers.py:70, :108, :118-121, :127; Framework.py:103, :119): n_walk normals N(0, step_sd) (the proposal
+// increments), n_prior_draws standard normals (the prior `rvs` inside the unused pdf() calls, one each for lognorm /
+// norm priors), one uniform.  Feeding these to odl_mcmc (ODL_RNG_HOST_STREAMS) reproduces the reference chain.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct LegacyMT {
+  uint32_t key[624];
+  int pos;
+  bool has_gauss;
+  double gauss;
+  explicit LegacyMT(uint32_t seed) : pos(624), has_gauss(false), gauss(0.0) {
+    for (int i = 0; i < 624; ++i) { key[i] = seed; seed = 1812433253u * (seed ^ (seed >> 30)) + (uint32_t)i + 1u; }
+  }
+  void twist() {
+    const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, A = 0x9908b0dfu;
+    int i;
+    uint32_t y;
+    for (i = 0; i < 624 - 397; ++i) { y = (key[i] & UPPER) | (key[i + 1] & LOWER); key[i] = key[i + 397] ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+    for (; i < 623; ++i) { y = (key[i] & UPPER) | (key[i + 1] & LOWER); key[i] = key[i + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+    y = (key[623] & UPPER) | (key[0] & LOWER);
+    key[623] = key[396] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+    pos = 0;
+  }
+  uint32_t next32() {
+    if (pos == 624) twist();
+    uint32_t y = key[pos++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+  }
+  double next_double() {
+    const int32_t a = (int32_t)(next32() >> 5), b = (int32_t)(next32() >> 6);
+    return (a * 67108864.0 + b) / 9007199254740992.0;
+  }
+  double next_gauss() {
+    if (has_gauss) { has_gauss = false; const double t = gauss; gauss = 0.0; return t; }
+    double f, x1, x2, r2;
+    do {
+      x1 = 2.0 * next_double() - 1.0;
+      x2 = 2.0 * next_double() - 1.0;
+      r2 = x1 * x1 + x2 * x2;
+    } while (r2 >= 1.0 || r2 == 0.0);
+    f = sqrt(-2.0 * log(r2) / r2);
+    gauss = f * x1; has_gauss = true;
+    return f * x2;
+  }
+};
+}  // namespace
+
+extern "C" int odl_reference_streams(const unsigned int* seeds, int n_chain, int n_iter, int n_walk, int n_prior_draws,
+                                     double step_sd, double* z, double* u) {
+  if (n_chain < 0 || n_iter < 0 || n_walk < 0 || n_prior_draws < 0 || (n_chain > 0 && (!seeds || !u || (n_walk > 0 && !z))))
+    return fail(ODL_EINVAL, "odl_reference_streams: bad argument");
+  auto run = [=](int c0, int c1) {
+    for (int c = c0; c < c1; ++c) {
+      LegacyMT rs(seeds[c]);
+      double* zc = z + (size_t)c * n_iter * n_walk;
+      double* uc = u + (size_t)c * n_iter;
+      for (int i = 0; i < n_iter; ++i) {
+        for (int j = 0; j < n_walk; ++j) zc[(size_t)i * n_walk + j] = 0.0 + step_sd * rs.next_gauss();
+        for (int j = 0; j < n_prior_draws; ++j) rs.next_gauss();
+        uc[i] = rs.next_double();
+      }
+    }
+  };
+  // chains are independent streams: split them over the host cores when there is enough work to pay for threads
+  int n_thr = (int)std::thread::hardware_concurrency();
+  if (n_thr > 16) n_thr = 16;
+  if ((long long)n_chain * n_iter < 200000 || n_thr < 2) { run(0, n_chain); return 0; }
+  if (n_thr > n_chain) n_thr = n_chain;
+  std::vector<std::thread> pool;
+  for (int t = 0; t < n_thr; ++t)
+    pool.emplace_back(run, (int)((long long)n_chain * t / n_thr), (int)((long long)n_chain * (t + 1) / n_thr));
+  for (auto& th : pool) th.join();
   return 0;
 }
 

@@ -96,6 +96,19 @@ def test_reference_streams_equal_golden_and_lhs_is_latin():
         for _ in range(4):
             rs.standard_normal()
         assert u2[i] == rs.rand()
+    # many chains at once: the library's MT19937 / polar-gauss restatement is numpy's legacy stream bit for bit,
+    # for both the even case and the odd one (gauss cache carried across the uniform), and for any 32-bit seed
+    even = [m.parameters[p] for p in m.get_pnames()]
+    for wk in (even, walking, even[:3]):
+        seeds = [0, 1, 7, 12345, 2 ** 32 - 1]
+        zb, ub = Samplers.reference_streams_batch(seeds, wk, 300)
+        for c, sd in enumerate(seeds):
+            zr, ur = Samplers.reference_streams(sd, wk, 300)
+            assert np.array_equal(zb[c], zr) and np.array_equal(ub[c], ur)
+    zb, ub = Samplers.reference_streams_batch(range(600), even, 400)          # enough work for the threaded split
+    for c in (0, 299, 599):
+        zr, ur = Samplers.reference_streams(c, even, 400)
+        assert np.array_equal(zb[c], zr) and np.array_equal(ub[c], ur)
     np.random.seed(1)
     d = Samplers.lhs(3, 50)
     assert d.shape == (50, 3)

@@ -63,6 +63,22 @@ def test_metropolis_hastings_reproduces_the_reference_chain():
     np.testing.assert_allclose(df["chi"].to_numpy(), kept[:, 3], rtol=1e-8)
 
 
+def test_hundreds_of_chains_keep_the_reference_streams():
+    """MCMC's default rng regenerates every chain's own numpy stream (seed = chain index, Framework.py:1015) with
+    the library's host code, so chain 7 of a 300-chain call is the chain a single seeded run produces."""
+    from odelib_b200.Statistics import Samplers
+    m = make_model("two_i")
+    th = m.get_parameters(as_dict=True)
+    post = m.MCMC(chain_inits=[th] * 300, iterations_per_chain=60, print_report=False)
+    for c in (7, 299):
+        m.set_parameters(**th)
+        m.random_seed = c
+        one = Samplers.MetropolisHastings(m, nits=60, burnin=30, print_progress=False)
+        mine = post[post["chain#"] == c].drop(columns="chain#").reset_index(drop=True)
+        assert len(one) == len(mine) and len(one) > 0
+        np.testing.assert_array_equal(mine.to_numpy(), one.reset_index(drop=True).to_numpy())
+
+
 def test_mcmc_demo_call_shapes_and_report(capsys):
     m = make_model("two_i")
     np.random.seed(3)
