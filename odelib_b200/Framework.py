@@ -24,7 +24,7 @@ import numpy as np
 import pandas as pd
 
 from .engine import SCIPY_TOL, DeviceModel, ObsTables
-from .rhat import allgather_summaries, pooled_log_stats, rhat_from_summaries, shard_bounds
+from .rhat import allgather_summaries, ess_from_summaries, pooled_log_stats, rhat_from_summaries, shard_bounds
 from .Statistics import Samplers, stats
 
 
@@ -44,9 +44,10 @@ class PosteriorSummary:
     the device -- per-parameter median / standard deviation (rawstats), the best kept row, R-hat -- without
     materialising chains x rows x columns on the host (65,536 chains x 500 rows are 2.9 GB as a frame)."""
 
-    def __init__(self, pnames, n_chains, n_rows, stats, best, best_chi, rhat, acceptance_ratio):
+    def __init__(self, pnames, n_chains, n_rows, stats, best, best_chi, rhat, acceptance_ratio, ess=None):
         self.parameter_names, self.n_chains, self.n_rows = list(pnames), int(n_chains), int(n_rows)
         self.stats, self.best, self.best_chi, self.rhat = stats, best, float(best_chi), rhat
+        self.ess = ess                                            # effective sample size per parameter (rhat.py)
         self.acceptance_ratio = float(acceptance_ratio)
 
     def __repr__(self):
@@ -64,7 +65,7 @@ class parameter:
         self.dist = stats_gen
         self.hp = hyperparameters
         self.name = name
-        if init_value:                                            # 0 counts as "not given", as in the reference
+        if init_value is not None and np.any(init_value):         # 0 counts as "not given", as in the reference
             self.val = np.array(init_value)
         else:
             if not self.dist:
@@ -76,7 +77,7 @@ class parameter:
         """Prior density at ``val``; without an argument, at a fresh prior draw (Framework.py:97-105)."""
         if not self.dist:
             return 1.0
-        if val:
+        if val is not None and np.any(val):                      # `if val:` in the reference (raises for arrays, :99)
             return self.dist.pdf(val, **self.hp)
         return self.dist.pdf(self.dist.rvs(**self.hp), **self.hp)
 
@@ -254,6 +255,12 @@ class ModelFramework:
 
     def set_parameters(self, **kwargs):
         for p, v in kwargs.items():
+            if p not in self.parameters and p in self._flat_slots():
+                owner, idx = self._flat_slots()[p]                # one element of an array-valued parameter: "phi[0,1]"
+                val = np.array(self.parameters[owner].val, dtype=np.float64)
+                val[idx] = v
+                self.parameters[owner].val = val
+                continue
             if p not in self.parameters:
                 raise Exception("{} is an unknown parameter. Acceptable parameters are: {}".format(p, ', '.join(self._pnames)))
             if isinstance(v, parameter):
@@ -286,13 +293,69 @@ class ModelFramework:
             return dict(zip(self._pnames, vals))
         return tuple([vals])
 
+    # -- flat layout: one slot per parameter ELEMENT (identical to parameter_names when every parameter is a scalar)
+    def _pshapes(self):
+        return tuple(() if self.parameters[p] is None else tuple(np.shape(self.parameters[p].val)) for p in self._pnames)
+
+    @property
+    def _flat_names(self):
+        shapes = self._pshapes()
+        if getattr(self, "_flat_cache", (None,))[0] != shapes:
+            names, slots = [], {}
+            for p, shape in zip(self._pnames, shapes):
+                for name, idx in zip(Samplers.element_names(p, shape), np.ndindex(*shape) if shape else [()]):
+                    names.append(name)
+                    slots[name] = (p, idx)
+            self._flat_cache = (shapes, tuple(names), slots)
+        return self._flat_cache[1]
+
+    def _flat_slots(self):
+        """element name -> (parameter name, index tuple)."""
+        self._flat_names
+        return self._flat_cache[2]
+
+    def _flat_owner(self):
+        slots = self._flat_slots()
+        return [slots[f][0] for f in self._flat_names]
+
+    def _flatten(self, values):
+        """One value (scalar or array) per parameter name, in parameter_names order -> flat theta."""
+        return np.concatenate([np.ravel(np.asarray(v, dtype=np.float64)) for v in values]) if len(values) else np.empty(0)
+
     def _current_theta(self):
-        return np.array([float(self.parameters[p].val) for p in self._pnames], dtype=np.float64)
+        return self._flatten([self.parameters[p].val for p in self._pnames])
+
+    def _set_theta(self, theta):
+        """Flat theta -> parameter values (arrays keep their shape)."""
+        k = 0
+        for p, shape in zip(self._pnames, self._pshapes()):
+            size = int(np.prod(shape)) if shape else 1
+            self.parameters[p].val = np.array(theta[k]) if shape == () else np.array(theta[k:k + size], dtype=np.float64).reshape(shape)
+            k += size
+
+    def _device_ode(self):
+        """The user's RHS as the tracer calls it: ``ps`` is the flat slot vector; array-valued parameters are handed to
+        the user's function as arrays of that shape (views of the slot vector), as odeint hands them over at
+        Framework.py:656."""
+        shapes = self._pshapes()
+        if all(sh == () for sh in shapes):
+            return self._model
+        ode = self._model
+
+        def flat_ode(y, t, ps):
+            vals, k = [], 0
+            for shape in shapes:
+                size = int(np.prod(shape)) if shape else 1
+                vals.append(ps[k] if shape == () else np.asarray(ps[k:k + size], dtype=object).reshape(shape))
+                k += size
+            return ode(y, t, vals)
+        return flat_ode
 
     # ------------------------------------------------------------------ device model
     def _y0_map(self):
         """'<state>0' parameters double as that state's initial value (Samplers.py:110-114)."""
-        return np.array([self._pnames.index(s + '0') if (s + '0') in self._pnames else -1 for s in self._snames], np.int32)
+        fn = self._flat_names
+        return np.array([fn.index(s + '0') if (s + '0') in fn else -1 for s in self._snames], np.int32)
 
     def _observe_groups(self):
         if not self._summations_index:
@@ -301,12 +364,11 @@ class ModelFramework:
 
     def _device(self):
         """Compile (once) and (re)load tables when data / initial states changed."""
-        if self._dm is None:
-            for p in self._pnames:
-                if self.parameters[p] is not None and np.ndim(self.parameters[p].val) != 0:
-                    raise NotImplementedError("array-valued parameters are not supported on the device path")
-            self._dm = DeviceModel(self._model, len(self._snames), len(self._pnames), self._observe_groups(),
+        if self._dm is None or getattr(self, "_dm_shapes", None) != self._pshapes():
+            self._dm_shapes = self._pshapes()                     # the slot layout is part of the compiled model
+            self._dm = DeviceModel(self._device_ode(), len(self._snames), len(self._flat_names), self._observe_groups(),
                                    device=self.device, y0_from_param=bool((self._y0_map() >= 0).any()))
+            self._dm_stamp = None
         y0 = np.asarray(self.get_inits(), dtype=np.float64)
         stamp = (self.times.tobytes(), y0.tobytes(), id(self.df), self._samples)
         if stamp != self._dm_stamp:
@@ -324,7 +386,7 @@ class ModelFramework:
     def integrate(self, inits=None, parameters=None, predict_obs=False, as_dataframe=True, sum_subpopulations=True):
         """Solve on ``self.times``; same four return shapes as the reference (Framework.py:622-683)."""
         dm = self._device()
-        theta = np.asarray(parameters[0] if parameters else self.get_parameters()[0], dtype=np.float64)
+        theta = self._flatten(parameters[0] if parameters else self.get_parameters()[0])
         y0 = None if inits is None else np.asarray(inits, dtype=np.float64)
         traj, status, _ = dm.trajectory(theta[None, :], y0=y0, rtol=self.rtol, atol=self.atol)
         if status[0] != 0:
@@ -390,7 +452,7 @@ class ModelFramework:
         res = dm.sweep(parameter_array, rtol=self.rtol if rtol is None else rtol,
                        atol=self.atol if atol is None else atol, solver=solver, out=out)
         if as_dataframe:
-            df = pd.DataFrame(np.asarray(parameter_array), columns=self.get_pnames())
+            df = pd.DataFrame(np.asarray(parameter_array), columns=list(self._flat_names))
             df['chi'] = res['chi']
             return df
         return res
@@ -406,7 +468,8 @@ class ModelFramework:
                 pstatic[p] = self.parameters[p].val
         df = Samplers.sample_lhs(parameter_dict=pdists, samples=samples)
         for p in pstatic:
-            df[p] = float(pstatic[p])
+            for name, v in zip(Samplers.element_names(p, np.shape(pstatic[p])), np.ravel(pstatic[p])):
+                df[name] = float(v)
         return df
 
     DEVICE_SAMPLING_FROM = 65536       # surveys at least this large are sampled on the device (sampler="auto")
@@ -416,10 +479,10 @@ class ModelFramework:
         """(kind, a, b, c) per parameter for the device sampler (engine.DeviceModel.sample_lhs), or None when a prior
         is not one of lognorm / norm / uniform in scipy.stats' (s, loc, scale) parameterisation."""
         table = []
-        for p in self._pnames:
-            par = self.parameters[p]
-            if par is None or not par.has_distribution():
-                table.append(("const", float(par.val) if par is not None else 0.0, 0.0, 0.0))
+        for f, value in zip(self._flat_owner(), self._current_theta()):
+            par = self.parameters[f]
+            if par is None or not par.has_distribution() or (np.ndim(par.val) and value == 0.0):
+                table.append(("const", float(value), 0.0, 0.0))   # no prior, or a structural zero of an array
                 continue
             name, hp = getattr(par.dist, "name", None), dict(par.hp or {})
             extra = set(hp) - {"s", "loc", "scale"}
@@ -449,10 +512,10 @@ class ModelFramework:
         theta_dev = self._lhs_samples_device(samples, sampler)
         if theta_dev is not None:
             res = self._device().sweep(theta_dev, rtol=self.rtol, atol=self.atol, solver="auto")
-            out = pd.DataFrame(theta_dev.cpu().numpy(), columns=self.get_pnames())
+            out = pd.DataFrame(theta_dev.cpu().numpy(), columns=list(self._flat_names))
             out['chi'] = res['chi'].cpu().numpy()
             return out
-        ps = self._lhs_samples(samples)[self.get_pnames()]
+        ps = self._lhs_samples(samples)[list(self._flat_names)]
         res = self.sweep(ps.to_numpy(dtype=np.float64))
         out = ps.reset_index(drop=True)
         out['chi'] = res['chi']
@@ -461,7 +524,7 @@ class ModelFramework:
     def explore_equilibriums(self, samples=1000, cpu_cores=1, **parameter_mapping):
         """Final state of every LHS sample (Framework.py:819-854, `_Equilibrium_worker` :24-38) -- one batched launch
         of the trajectory kernel on a two-point output grid (t0, t_end): only the final states leave the device."""
-        ps = self._lhs_samples(samples, **parameter_mapping)[self.get_pnames()]
+        ps = self._lhs_samples(samples, **parameter_mapping)[list(self._flat_names)]
         dm = self._device()
         y0 = np.asarray(self.get_inits(), dtype=np.float64)
         dm.set_grid(np.array([self.times[0], self.times[-1]]), y0, self._y0_map())
@@ -470,9 +533,59 @@ class ModelFramework:
         finally:
             dm.set_grid(self.times, y0, self._y0_map())           # integrate() expects the full grid
         df = pd.DataFrame(traj[:, -1, :], columns=self.get_snames(after_summation=False))
-        for p in self.get_pnames():
+        for p in self._flat_names:
             df[p] = ps[p].to_numpy()
         return df
+
+    def gradient(self, parameter_name, p_range, intialstates=None, seed_equilibrium=True, aggregate_enpoints=False,
+                 print_status=True):
+        """One simulation per value of ``parameter_name`` in ``p_range`` (Framework.py:1063-1127, as its docstring and
+        comments intend it: the reference's body cannot run -- it tests ``intialstates`` for None the wrong way round
+        (:1083-1086) and overwrites the ``parameter`` object with a number (:1095)).
+
+        seed_equilibrium=True: a continuation, each run starts from the previous run's final state floored at 0.001
+        (:1099-1101) -- sequential by construction, one single-system launch per value.  seed_equilibrium=False:
+        every run starts from the same state, so all of ``p_range`` is ONE batched launch.  Returns a frame with one
+        column per state variable (sub-populations not summed, :1097) plus ``parameter_name``: the final states
+        (``aggregate_enpoints=True``, [len(p_range), n+1]) or every grid row of every run ([len(p_range)*T, n+1])."""
+        if parameter_name not in self._flat_names:
+            raise ValueError("{} is not a (scalar or element) parameter of this model".format(parameter_name))
+        p_range = np.asarray(p_range, dtype=np.float64).ravel()
+        num_sim = len(p_range)
+        init = np.asarray(self.get_inits() if intialstates is None else intialstates, dtype=np.float64)
+        if init.shape != (len(self._snames),):
+            raise ValueError("intialstates must hold one value per state variable")
+        col = self.get_snames(after_summation=False) + [parameter_name]
+        if print_status and num_sim:
+            print("Preparing to run {} simulations between {} and {}".format(num_sim, p_range.min(), p_range.max()))
+        if num_sim == 0:
+            return pd.DataFrame(np.empty((0, len(col))), columns=col)
+        dm = self._device()
+        theta = np.tile(self._current_theta(), (num_sim, 1))
+        theta[:, self._flat_names.index(parameter_name)] = p_range
+        no_map = np.full(len(self._snames), -1, np.int32)          # explicit initial states win, as in integrate(inits=)
+        y0 = np.asarray(self.get_inits(), dtype=np.float64)
+        grid = np.array([self.times[0], self.times[-1]]) if aggregate_enpoints else self.times
+        dm.set_grid(grid, y0, no_map)
+        try:
+            if seed_equilibrium:
+                traj = np.empty((num_sim, len(grid), len(self._snames)))
+                for i in range(num_sim):
+                    if print_status:
+                        print("{:.2f}% Complete".format(i / num_sim * 100), end='\r')
+                    traj[i] = dm.trajectory(theta[i:i + 1], y0=init, rtol=self.rtol, atol=self.atol)[0][0]
+                    init = np.clip(traj[i, -1, :], a_min=.001, a_max=None)
+            else:
+                traj = dm.trajectory(theta, y0=init, rtol=self.rtol, atol=self.atol)[0]
+        finally:
+            dm.set_grid(self.times, y0, self._y0_map())
+        if print_status:
+            print("100.00% Complete")
+        if aggregate_enpoints:
+            rows = np.column_stack([traj[:, -1, :], p_range])
+        else:
+            rows = np.column_stack([traj.reshape(-1, traj.shape[2]), np.repeat(p_range, traj.shape[1])])
+        return pd.DataFrame(rows, columns=col)
 
     def copy(self, overwrite=dict()):
         """Independent copy sharing the compiled device model (Framework.py:901-943)."""
@@ -494,7 +607,7 @@ class ModelFramework:
 
     def set_best_params(self, posteriors):
         im = posteriors['chi'].idxmin()
-        best = posteriors.loc[im][self.get_pnames()].to_dict()
+        best = posteriors.loc[im][list(self._flat_names)].to_dict()
         self.set_parameters(**best)
         if self._snames[0] + '0' in self.get_pnames():
             self.set_inits(**{s: best[s + '0'] for s in self._snames})
@@ -507,7 +620,7 @@ class ModelFramework:
         dm = self._device()
         static = set(static_parameters or ())
         walk_names = [p for p in self._pnames if p not in static]
-        walk = [self._pnames.index(p) for p in walk_names]
+        walk = [i for i, owner in enumerate(self._flat_owner()) if owner not in static]
         on_device = hasattr(starts, "is_cuda")
         theta0 = starts if on_device else np.array(starts, dtype=np.float64)
         C = theta0.shape[0]
@@ -540,7 +653,7 @@ class ModelFramework:
             if table is None:
                 raise NotImplementedError("use_priors supports lognorm / norm / uniform priors (s, loc, scale)")
             kw["prior"] = [("const", 0, 0, 0) if (p in static or k == "const") else (k, a, b, c)
-                           for p, (k, a, b, c) in zip(self._pnames, table)]
+                           for p, (k, a, b, c) in zip(self._flat_owner(), table)]
         if rng == "reference":
             walking = [self.parameters[p] for p in walk_names]
             z, u = Samplers.reference_streams_batch(seeds, walking, n_iter)
@@ -578,15 +691,16 @@ class ModelFramework:
         self._last_mcmc = out
         if return_raw:
             return out
-        cols = self.get_pnames() + ['chi', 'rsquared', 'aic', 'iteration', 'acceptance_ratio']
+        cols = list(self._flat_names) + ['chi', 'rsquared', 'aic', 'iteration', 'acceptance_ratio']
+        static_cols = [(f, owner) for f, owner in zip(self._flat_names, self._flat_owner()) if owner in static]
         samples = out["samples"]                                  # [C, n_keep, P+5], rows = the reference frame's columns
         if return_frame:
             # one frame for all chains, assembled without per-chain pandas work (Framework.py:1035-1038 equivalent)
             flat = samples.reshape(-1, samples.shape[-1])
             df = pd.DataFrame(flat, columns=cols)
             df['iteration'] = df['iteration'].astype(np.int64)
-            for p in static:   # reference quirk A13: static columns report the prior's scale (Samplers.py:166-170)
-                df[p] = self.parameters[p].hp['scale']
+            for f, p in static_cols:   # reference quirk A13: static columns report the prior's scale (Samplers.py:166-170)
+                df[f] = self.parameters[p].hp['scale']
             df['chain#'] = np.repeat(np.arange(C), samples.shape[1])
             frames = df
         else:
@@ -594,13 +708,13 @@ class ModelFramework:
             for c in range(C):
                 df = pd.DataFrame(samples[c], columns=cols)
                 df['iteration'] = df['iteration'].astype(np.int64)
-                for p in static:
-                    df[p] = self.parameters[p].hp['scale']
+                for f, p in static_cols:
+                    df[f] = self.parameters[p].hp['scale']
                 if df.empty:
-                    df = pd.DataFrame([[np.nan] * (len(self._pnames) + 3)])
+                    df = pd.DataFrame([[np.nan] * (len(self._flat_names) + 3)])
                 frames.append(df)
         if update_model:
-            self.set_parameters(**dict(zip(self._pnames, out["theta"][0])))
+            self._set_theta(out["theta"][0])
             if any(m >= 0 for m in self._y0_map()):
                 self.set_inits(**{s: out["theta"][0][m] for s, m in zip(self._snames, self._y0_map()) if m >= 0})
         return frames
@@ -615,7 +729,7 @@ class ModelFramework:
         dm = self._device()
         theta = self._lhs_samples_device(fitsurvey_samples)
         if theta is None:
-            ps = self._lhs_samples(fitsurvey_samples)[self.get_pnames()]
+            ps = self._lhs_samples(fitsurvey_samples)[list(self._flat_names)]
             theta = torch.from_numpy(np.ascontiguousarray(ps.to_numpy(dtype=np.float64))).to(torch.device("cuda", dm.device))
         res = dm.sweep(theta, rtol=self.rtol, atol=self.atol, solver="auto")
         calc = {s: np.exp(self._obs_logabundance[s] + sd_fitdistance * self._obs_logsigma[s]) for s in self._obs_logabundance}
@@ -635,24 +749,27 @@ class ModelFramework:
     def posterior_summary(self, static_parameters=()):
         """PosteriorSummary of the last chains, from the device-side reductions alone."""
         out = self._last_mcmc
-        P = len(self._pnames)
+        fn = self._flat_names
+        P = len(fn)
         N, log_mean, log_std = pooled_log_stats(out["summaries"], P)
-        stats_ = {p: _rawstats_from_logmoments(log_mean[i], log_std[i]) for i, p in enumerate(self._pnames)}
+        stats_ = {p: _rawstats_from_logmoments(log_mean[i], log_std[i]) for i, p in enumerate(fn)}
         best_chi = np.asarray(out["best_chi"], dtype=np.float64)
         have = np.asarray(out["best_iteration"]) > 0
         if have.any() and np.isfinite(best_chi[have]).any():
             c = int(np.nanargmin(np.where(have, best_chi, np.nan)))       # first chain holding the minimum, as idxmin
-            best = dict(zip(self._pnames, np.asarray(out["best_theta"])[c]))
+            best = dict(zip(fn, np.asarray(out["best_theta"])[c]))
             bchi = best_chi[c]
         else:
-            best, bchi = dict(zip(self._pnames, self._current_theta())), np.nan
-        for p in static_parameters or ():                        # quirk A13: static columns hold the prior's scale
-            best[p] = self.parameters[p].hp['scale']
+            best, bchi = dict(zip(fn, self._current_theta())), np.nan
+        for f, p in zip(fn, self._flat_owner()):                  # quirk A13: static columns hold the prior's scale
+            if p in (static_parameters or ()):
+                best[f] = self.parameters[p].hp['scale']
         C = len(best_chi)
-        rh = dict(zip(self._pnames, rhat_from_summaries(out["summaries"], P))) if C > 1 and out["n_keep"] > 1 else None
+        rh = dict(zip(fn, rhat_from_summaries(out["summaries"], P))) if C > 1 and out["n_keep"] > 1 else None
+        ess = dict(zip(fn, ess_from_summaries(out["summaries"], P))) if rh is not None else None
         n_iter = max(1, int(out["n_keep"]) + int(out["burnin"]))
         acc = float(np.asarray(out["chain_state"])[:, 2].mean()) / n_iter
-        return PosteriorSummary(self._pnames, C, N, stats_, best, bchi, rh, acc)
+        return PosteriorSummary(fn, C, N, stats_, best, bchi, rh, acc, ess)
 
     def MCMC(self, chain_inits=1, iterations_per_chain=1000, cpu_cores=1, static_parameters=list(), print_report=True,
              fitsurvey_samples=1000, sd_fitdistance=3.0, rng="auto", posterior="frame", use_priors=False):
@@ -670,7 +787,7 @@ class ModelFramework:
         if posterior not in ("frame", "summary"):
             raise ValueError("posterior must be 'frame' or 'summary'")
         if isinstance(chain_inits, pd.DataFrame):
-            chain_inits = [row.to_dict() for _, row in chain_inits[self.get_pnames()].iterrows()]
+            chain_inits = [row.to_dict() for _, row in chain_inits[list(self._flat_names)].iterrows()]
         base = self._current_theta()
         if isinstance(chain_inits, (int, np.integer)):
             starts = self._survey_starts_on_device(int(chain_inits), fitsurvey_samples, sd_fitdistance)
@@ -680,9 +797,14 @@ class ModelFramework:
             starts = []
             for d in chain_inits:
                 th = base.copy()
+                fn = self._flat_names
                 for k, v in d.items():
-                    if k in self._pnames:
-                        th[self._pnames.index(k)] = float(v)
+                    if k in fn:
+                        th[fn.index(k)] = float(v)
+                    elif k in self._pnames:                       # a whole array-valued parameter
+                        lo = self._flat_owner().index(k)
+                        vals = np.ravel(np.asarray(v, dtype=np.float64))
+                        th[lo:lo + len(vals)] = vals
                 starts.append(th)
         n_chains = len(starts)
         seeds = list(range(n_chains))                             # chain seed = chain index (:1015, :1020)
@@ -691,12 +813,12 @@ class ModelFramework:
                                   rng=rng, return_frame=want_frame, return_raw=not want_frame, keep_samples=want_frame,
                                   use_priors=use_priors)
         summary = self.posterior_summary(static_parameters)
-        self.rhat = summary.rhat
+        self.rhat, self.ess = summary.rhat, summary.ess
         if print_report:
             report = ["\nFitting Report\n==============="]
-            for col in self.get_pnames():
+            for col, owner in zip(self._flat_names, self._flat_owner()):
                 median, std = summary.stats[col]
-                if col in (static_parameters or ()):
+                if owner in (static_parameters or ()):
                     continue                                      # constant column: std == 0 in the reference's frame
                 if (median != 0.0) and (std != 0.0):
                     report.append("parameter: {}\n\tmedian = {:0.3e}, Standard deviation = {:0.3e}".format(col, median, std))
@@ -709,5 +831,7 @@ class ModelFramework:
             if self.rhat:
                 report.append("\nGelman-Rubin R-hat (log-parameters): " +
                               ", ".join("{}={:.3f}".format(k, v) for k, v in self.rhat.items()))
+                report.append("Effective sample size (between/within chains): " +
+                              ", ".join("{}={:.0f}".format(k, v) for k, v in self.ess.items()))
             print('\n'.join(report))
         return result if want_frame else summary

@@ -27,18 +27,35 @@ def lhs(n, samples, random_state=None):
     return design
 
 
+def element_names(name, shape):
+    """Column names of a parameter's elements in the flat layout: ``name`` for a scalar, ``name[i]`` / ``name[i,j]``
+    (row-major) for an array-valued one."""
+    if tuple(shape) == ():
+        return [name]
+    return ["{}[{}]".format(name, ",".join(str(k) for k in idx)) for idx in np.ndindex(*shape)]
+
+
 def sample_lhs(parameter_dict, samples):
-    """LHS in the unit cube pushed through each prior's ppf (Samplers.py:6-51).  Scalar parameters only
-    (the reference's array branch is broken)."""
+    """LHS in the unit cube pushed through each prior's ppf (Samplers.py:6-51).
+
+    Array-valued parameters as the reference intends them (:26-32): one LHS dimension per NON-ZERO element, zeros are
+    structural and stay zero.  The reference's own array branch cannot run (``parameter_dict[p][0]`` at :45 subscripts a
+    parameter object); here the elements come back as one column each (``name[i,j]``) rather than as
+    arrays stored in the rows, which is the layout every batched call works on."""
     names = list(parameter_dict)
-    for p in names:
-        if np.ndim(parameter_dict[p].val) != 0:
-            raise NotImplementedError("array-valued parameters are not supported in LHS surveys")
-    cube = lhs(len(names), samples)
+    masks = {p: np.ravel(np.asarray(parameter_dict[p].val) != 0) if np.ndim(parameter_dict[p].val) else np.array([True])
+             for p in names}
+    cube = lhs(int(sum(m.sum() for m in masks.values())), samples)
     cols = {}
-    for j, p in enumerate(names):
+    j = 0
+    for p in names:
         par = parameter_dict[p]
-        cols[p] = np.asarray(par.dist.ppf(cube[:, j], **par.hp), dtype=np.float64)
+        for name, live in zip(element_names(p, np.shape(par.val)), masks[p]):
+            if live:
+                cols[name] = np.asarray(par.dist.ppf(cube[:, j], **par.hp), dtype=np.float64)
+                j += 1
+            else:
+                cols[name] = np.zeros(samples)
     return pd.DataFrame(cols)
 
 
@@ -53,10 +70,11 @@ def reference_streams(seed, walking, n_iter):
     seed consumes them (Samplers.py:70, :108, :119-121, :127; Framework.py:103, :119).
 
     walking: list of parameter objects in proposal order.  Per iteration the reference draws one
-    N(0, 0.05) per walking parameter, then one ``dist.rvs`` per walking parameter that has a prior (the
-    unused ``pdf()`` evaluation), then one uniform."""
+    N(0, 0.05) per walking parameter (per element of an array-valued one), then one ``dist.rvs`` per walking
+    parameter that has a prior (the unused ``pdf()`` evaluation), then one uniform."""
     rs = np.random.RandomState(seed)
-    nw = len(walking)
+    dims = [int(np.size(p.val)) for p in walking]                 # rwalk draws one normal per ELEMENT (Framework.py:108,:119)
+    nw = sum(dims)
     z = np.empty((n_iter, nw))
     u = np.empty(n_iter)
     with_prior = [p for p in walking if p.dist]
@@ -92,7 +110,7 @@ def reference_streams_batch(seeds, walking, n_iter):
     restatement of numpy's legacy RandomState (odl_reference_streams, host code, ~10 ns per draw); anything else
     goes through numpy chain by chain."""
     seeds = [int(s) for s in seeds]
-    nw = len(walking)
+    nw = sum(int(np.size(p.val)) for p in walking)                # one proposal increment per element
     with_prior = [p for p in walking if p.dist]
     if all(_one_gaussian_rvs(p) for p in with_prior) and all(0 <= s < 2 ** 32 for s in seeds):
         from .. import _capi

@@ -24,6 +24,26 @@ def rhat_from_summaries(summaries, n_param):
         return np.sqrt(((n - 1.0) / n * W + B / n) / W)
 
 
+def ess_from_summaries(summaries, n_param):
+    """Effective sample size per parameter from the same per-chain summaries: n_eff = m n var+ / B (Gelman et al.,
+    Bayesian Data Analysis, the between/within-chain estimate that goes with R-hat), capped at the m n kept rows.
+    Needs no autocorrelations, so no sample ever leaves the device for it; it is conservative while the chains have
+    not mixed (B large) and saturates at m n once the chain means agree.  New functionality like R-hat (SURVEY.md
+    §8 f2); not in the reference."""
+    s = np.asarray(summaries, dtype=np.float64)
+    n = s[:, 0]
+    if not np.all(n == n[0]):
+        raise ValueError("chains have different numbers of kept samples")
+    m, n = float(len(s)), float(n[0])
+    means = s[:, 1:1 + n_param]
+    var = s[:, 1 + n_param:1 + 2 * n_param] / (n - 1.0)
+    W = var.mean(axis=0)
+    B = n * means.var(axis=0, ddof=1)
+    with np.errstate(all="ignore"):
+        ess = m * n * ((n - 1.0) / n * W + B / n) / B
+    return np.where(np.isfinite(ess), np.minimum(ess, m * n), m * n)
+
+
 def pooled_log_stats(summaries, n_param):
     """Per-chain Welford summaries of ln(theta) -> (count, log_mean[P], log_std[P]) of ALL kept rows pooled.
 

@@ -21,6 +21,67 @@ def make_model(name, **kw):
                                  t_steps=TSTEPS[name], **pri, **extra, **kw)
 
 
+def split_phi(y, t, ps):
+    """zero_i with the adsorption rate given as an ARRAY-valued parameter of two summands (f4: the reference hands
+    arrays straight to the RHS, Framework.py:656)."""
+    mu, phi, beta = ps[0], ps[1], ps[2]
+    S, V = y[0], y[1]
+    a = phi[0] + phi[1]
+    return np.array([mu * S - a * S * V, beta * a * S * V - a * S * V])
+
+
+def make_array_model(phi=(0.7e-8, 0.65e-8), **kw):
+    LN = scipy.stats.lognorm
+    return ODElib.ModelFramework(
+        ODE=split_phi, parameter_names=["mu", "phi", "beta"], state_names=["S", "V"], dataframe=demo_df("zero_i"),
+        mu=ODElib.parameter(stats_gen=LN, hyperparameters={"s": 3, "scale": 1e-8}, init_value=1e-6),
+        phi=ODElib.parameter(stats_gen=LN, hyperparameters={"s": 3, "scale": 1e-8}, init_value=list(phi)),
+        beta=ODElib.parameter(stats_gen=LN, hyperparameters={"s": 1, "scale": 25}, init_value=19.4),
+        t_steps=288, **kw)
+
+
+def test_array_valued_parameters_flat_layout():
+    """f4: one slot per element; parameter_names and get_parameters keep the reference's shapes."""
+    from odelib_b200.tracer import trace
+    m = make_array_model()
+    assert m.get_pnames() == ["mu", "phi", "beta"]
+    assert m._flat_names == ("mu", "phi[0]", "phi[1]", "beta") and m._flat_owner() == ["mu", "phi", "phi", "beta"]
+    np.testing.assert_array_equal(m._current_theta(), [1e-6, 0.7e-8, 0.65e-8, 19.4])
+    ps = m.get_parameters()[0]
+    assert np.shape(ps[1]) == (2,) and np.shape(ps[0]) == ()
+    assert m._pnum == 4                                           # AIC counts non-zero elements (Framework.py:260-263)
+    # the RHS traced through the slot adapter == the user's function on arrays
+    tm = trace(m._device_ode(), 2, 4)
+    y = np.array([5.0e6, 1.0e7])
+    np.testing.assert_allclose(tm.evaluate(tm.outputs, y, 0.0, m._current_theta()),
+                               split_phi(y, 0.0, [1e-6, np.array([0.7e-8, 0.65e-8]), 19.4]), rtol=1e-15)
+    # element names address single elements; theta vectors round-trip with the shapes kept
+    m.set_parameters(**{"phi[1]": 1e-9})
+    np.testing.assert_array_equal(m.parameters["phi"].val, [0.7e-8, 1e-9])
+    m._set_theta(np.array([1.0, 2.0, 3.0, 4.0]))
+    assert np.shape(m.parameters["phi"].val) == (2,) and float(m.parameters["beta"].val) == 4.0
+    with pytest.raises(Exception, match="unknown parameter"):
+        m.set_parameters(**{"phi[2]": 1.0})
+    # LHS: one stratified column per NON-ZERO element, zeros are structural (Samplers.py:26-32)
+    z = make_array_model(phi=(1.3e-8, 0.0))
+    np.random.seed(2)
+    sv = z._lhs_samples(50)
+    assert list(sv.columns) == ["mu", "phi[0]", "phi[1]", "beta"] and np.all(sv["phi[1]"] == 0.0)
+    u = scipy.stats.lognorm.cdf(sv["phi[0]"], s=3, scale=1e-8)
+    assert sorted(np.floor(u * 50).astype(int)) == list(range(50))
+    assert z._prior_table()[2] == ("const", 0.0, 0.0, 0.0) and z._prior_table()[1][0] == "lognorm" and z._pnum == 3
+    # the reference chain draws one increment per element, one prior rvs per parameter object, one uniform
+    walking = [m.parameters[p] for p in m.get_pnames()]
+    zz, uu = Samplers.reference_streams_batch([5], walking, 30)
+    rs = np.random.RandomState(5)
+    for i in range(30):
+        for j in range(4):
+            assert zz[0, i, j] == rs.normal(0, 0.05)
+        for _ in range(3):
+            rs.standard_normal()
+        assert uu[0, i] == rs.rand()
+
+
 @pytest.mark.parametrize("name", ["zero_i", "one_i", "two_i"])
 def test_ctor_tables_equal_reference(name):
     g = golden(name)
@@ -155,6 +216,25 @@ def test_pooled_log_stats_equal_rawstats_over_the_frame():
         med, sd = rawstats(pd.Series(x[:, :, q].ravel()))
         m2, s2 = _rawstats_from_logmoments(mean[q], std[q])
         assert m2 == pytest.approx(med, rel=1e-12) and s2 == pytest.approx(sd, rel=1e-10)
+
+
+def test_effective_sample_size_from_chain_summaries():
+    """f2: n_eff = m n var+ / B from the per-chain (count, mean, M2) rows alone; ~m n for independent draws, far
+    below it for chains stuck at different levels, never above the number of kept rows."""
+    from odelib_b200.rhat import ess_from_summaries, rhat_from_summaries
+    rng = np.random.default_rng(1)
+    m, n, P = 64, 200, 2
+    x = rng.normal(size=(m, n, P))
+    x[:, :, 1] += 3.0 * rng.normal(size=(m, 1))                   # second parameter: chains disagree
+    summ = np.concatenate([np.full((m, 1), float(n)), x.mean(axis=1), ((x - x.mean(axis=1, keepdims=True)) ** 2).sum(axis=1)], axis=1)
+    ess = ess_from_summaries(summ, P)
+    W = x.var(axis=1, ddof=1).mean(axis=0)
+    B = n * x.mean(axis=1).var(axis=0, ddof=1)
+    np.testing.assert_allclose(ess, np.minimum(m * n, m * n * ((n - 1) / n * W + B / n) / B), rtol=1e-12)
+    assert ess[0] > 0.5 * m * n and ess[1] < 0.02 * m * n and np.all(ess <= m * n)
+    assert rhat_from_summaries(summ, P)[1] > 2.0
+    same = np.concatenate([np.full((3, 1), 5.0), np.ones((3, 1)), np.ones((3, 1))], axis=1)   # B == 0: capped
+    assert ess_from_summaries(same, 1)[0] == 15.0
 
 
 def test_chain_start_picks_are_what_dataframe_sample_draws():

@@ -5,7 +5,7 @@ import pandas as pd
 import pytest
 
 from tests.helpers import golden
-from tests.test_facade_host import make_model
+from tests.test_facade_host import make_array_model, make_model
 
 pytestmark = pytest.mark.gpu
 
@@ -174,6 +174,77 @@ def test_explore_equilibriums_returns_final_states():
     assert ok >= 2
     full = m.integrate()                                          # the full output grid is back in place
     assert len(full) == len(m.times)
+
+
+def test_gradient_batched_and_continuation():
+    """f3 (Framework.py:1063-1127, fixed): a 1-D parameter scan, batched when the runs are independent, a
+    continuation seeded by the previous end point otherwise -- both against scipy on the same recipe."""
+    from scipy.integrate import odeint
+    from oracle import odelib_oracle as orc
+    m = make_model("one_i")
+    names = m.get_snames(after_summation=False)
+    th0 = m._current_theta()
+    k = m.get_pnames().index("beta")
+    betas = np.linspace(10.0, 40.0, 7)
+    ends = m.gradient("beta", betas, seed_equilibrium=False, aggregate_enpoints=True, print_status=False)
+    assert list(ends.columns) == names + ["beta"] and len(ends) == 7
+    np.testing.assert_array_equal(ends["beta"].to_numpy(), betas)
+    y0 = np.asarray(m.get_inits(), dtype=np.float64)
+    for i in (0, 3, 6):
+        th = th0.copy(); th[k] = betas[i]
+        ref = odeint(orc.one_i, y0, [m.times[0], m.times[-1]], args=(list(th),), rtol=1e-12, atol=1e-12, mxstep=500000)[-1]
+        np.testing.assert_allclose(ends[names].iloc[i].to_numpy(), ref, rtol=2e-5, atol=1.0)
+    # every grid row of every run, and the same end points
+    full = m.gradient("beta", betas[:3], seed_equilibrium=False, print_status=False)
+    assert len(full) == 3 * len(m.times)
+    np.testing.assert_allclose(full[names].iloc[len(m.times) - 1].to_numpy(), ends[names].iloc[0].to_numpy(), rtol=1e-6, atol=1e-3)
+    np.testing.assert_array_equal(full[names].iloc[len(m.times)].to_numpy(), y0)
+    # continuation: run i starts from run i-1's final state floored at 0.001
+    cont = m.gradient("beta", betas[:4], seed_equilibrium=True, aggregate_enpoints=True, print_status=False)
+    init = y0.copy()
+    for i in range(4):
+        th = th0.copy(); th[k] = betas[i]
+        ref = odeint(orc.one_i, init, [m.times[0], m.times[-1]], args=(list(th),), rtol=1e-12, atol=1e-12, mxstep=500000)[-1]
+        np.testing.assert_allclose(cont[names].iloc[i].to_numpy(), ref, rtol=2e-5, atol=1.0)
+        init = np.clip(cont[names].iloc[i].to_numpy(), 0.001, None)     # like for like: seed scipy as the scan was seeded
+    np.testing.assert_array_equal(m._current_theta(), th0)        # the scanned parameter is restored
+    assert len(m.integrate()) == len(m.times)
+    assert len(m.gradient("beta", [], print_status=False)) == 0
+    with pytest.raises(ValueError):
+        m.gradient("nope", betas)
+
+
+def test_array_valued_parameters_on_the_device():
+    """f4: an array-valued parameter reaches the RHS as an array.  integrate / get_chi with arrays run in the reference
+    (its value for this model, recorded from the unmodified reference, is below); its sample_lhs (Samplers.py:45) and
+    chain (Framework.py:99) branches for arrays raise, so surveys and chains are checked against the equivalent scalar
+    model instead."""
+    m = make_array_model()
+    chi = m.get_chi(m.integrate(predict_obs=True, as_dataframe=False))
+    assert chi == pytest.approx(107.95005049151386, rel=2e-6)     # reference at odeint's default tolerance
+    z = make_model("zero_i")                                      # phi = phi[0] + phi[1]: the same arithmetic
+    rows = np.exp(np.random.default_rng(0).normal(size=(64, 4)) * 0.3) * m._current_theta()
+    a = m.sweep(rows)
+    b = z.sweep(np.column_stack([rows[:, 0], rows[:, 1] + rows[:, 2], rows[:, 3]]))
+    np.testing.assert_allclose(a["chi"], b["chi"], rtol=1e-12)
+    np.random.seed(4)
+    sv = m.fit_survey(samples=200)
+    assert list(sv.columns) == ["mu", "phi[0]", "phi[1]", "beta", "chi"] and len(sv) == 200
+    post = m.MCMC(chain_inits=[{"phi": [0.7e-8, 0.65e-8], "beta": 19.0}] * 3, iterations_per_chain=80,
+                  static_parameters=["mu"], print_report=True)
+    assert list(post.columns) == ["mu", "phi[0]", "phi[1]", "beta", "chi", "rsquared", "aic", "iteration",
+                                  "acceptance_ratio", "chain#"]
+    assert len(post) == 3 * 39 and np.all(post["mu"] == 1e-8)     # static column: the prior's scale (quirk A13)
+    assert post["phi[0]"].nunique() > 1 and post["phi[1]"].nunique() > 1
+    assert np.all(post["aic"] == 2 * post["chi"] + 2 * 4)
+    assert np.shape(m.parameters["phi"].val) == (2,)              # best row written back with the shape kept
+    best = post.loc[post["chi"].idxmin()]
+    np.testing.assert_array_equal(m.parameters["phi"].val, [best["phi[0]"], best["phi[1]"]])
+    # a structural zero stays zero along the chain and in the survey
+    s0 = make_array_model(phi=(1.35e-8, 0.0))
+    p0 = s0.MCMC(chain_inits=[{}] * 2, iterations_per_chain=40, print_report=False)
+    assert np.all(p0["phi[1]"] == 0.0) and p0["phi[0]"].nunique() > 1
+    assert np.all(p0["aic"] == 2 * p0["chi"] + 2 * 3)
 
 
 def test_device_latin_hypercube_sampling_of_the_priors():
