@@ -24,7 +24,8 @@ import numpy as np
 import pandas as pd
 
 from .engine import SCIPY_TOL, DeviceModel, ObsTables
-from .rhat import allgather_summaries, ess_from_summaries, pooled_log_stats, rhat_from_summaries, shard_bounds
+from .rhat import (allgather_rows, broadcast_rows, ess_from_summaries, pooled_log_stats, rhat_from_summaries,
+                   shard_bounds)
 from .Statistics import Samplers, stats
 
 
@@ -120,6 +121,10 @@ class ModelFramework:
         # do not finish (a stiff posterior region -- where LSODA itself switches to BDF), runs the chains on the
         # variable-order BDF kernel; "dopri5" / "bdf" / "radau5" / "ros23" force one
         self.solver = kwargs.pop("solver", "auto")
+        # distributed=True: under torchrun (one process per GPU, torch.distributed initialised) fit_survey and MCMC shard
+        # their rows / chains over the ranks in contiguous blocks and every rank returns the complete result -- what
+        # `cpu_cores` is to the reference (Framework.py:755-785).  Every rank must then make the same calls.
+        self.distributed = bool(kwargs.pop("distributed", False))
         self._dm = None
         self._dm_stamp = None
         if state_summations:
@@ -509,6 +514,8 @@ class ModelFramework:
     def fit_survey(self, samples=1000, cpu_cores=1, sampler="auto"):
         """LHS sample of the priors, chi of every sample (Framework.py:800-816).  ``cpu_cores`` is ignored.
         sampler: "host" = numpy (Samplers.sample_lhs), "device" = odl_sample_lhs, "auto" = device for large surveys."""
+        if self._world()[0] > 1:
+            return self._fit_survey_sharded(samples, sampler)
         theta_dev = self._lhs_samples_device(samples, sampler)
         if theta_dev is not None:
             res = self._device().sweep(theta_dev, rtol=self.rtol, atol=self.atol, solver="auto")
@@ -520,6 +527,84 @@ class ModelFramework:
         out = ps.reset_index(drop=True)
         out['chi'] = res['chi']
         return out
+
+    # ------------------------------------------------------------------ several GPUs
+    def _world(self):
+        """(world_size, rank) of the default process group for a model built with distributed=True, else (1, 0)."""
+        if not self.distributed:
+            return 1, 0
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1, 0
+        return dist.get_world_size(), dist.get_rank()
+
+    def _unfinished_fraction(self, n_bad, n):
+        """Share of the probed chain starts the capped DOPRI5 pass did not finish -- over ALL ranks when the chains
+        are sharded, so that the stepper (and with it every chain) does not depend on the number of GPUs."""
+        if self._world()[0] > 1:
+            import torch
+            import torch.distributed as dist
+            from .rhat import _collective_device
+            t = torch.tensor([float(n_bad), float(n)], dtype=torch.float64, device=_collective_device())
+            dist.all_reduce(t)
+            n_bad, n = t[0].item(), t[1].item()
+        return n_bad / max(1.0, float(n))
+
+    def _fit_survey_sharded(self, samples, sampler):
+        """fit_survey over all ranks: rank 0 draws the design (its numpy / device stream alone decides it) and
+        broadcasts it, every rank solves a contiguous block of rows, chi is all-gathered; no collective on the data
+        path itself.  Every rank returns the whole frame, rows in the design's order."""
+        import torch
+        ws, rank = self._world()
+        dm = self._device()
+        theta = None
+        if rank == 0:
+            theta = self._lhs_samples_device(samples, sampler)
+            if theta is None:
+                theta = np.ascontiguousarray(self._lhs_samples(samples)[list(self._flat_names)].to_numpy(dtype=np.float64))
+        theta = broadcast_rows(theta, (int(samples), len(self._flat_names))).to(torch.device("cuda", dm.device))
+        lo, hi = shard_bounds(int(samples), ws, rank)
+        if hi > lo:
+            chi = dm.sweep(theta[lo:hi], rtol=self.rtol, atol=self.atol, solver="auto")["chi"]
+        else:
+            chi = torch.empty(0, dtype=torch.float64, device=theta.device)
+        chi = allgather_rows(chi)
+        out = pd.DataFrame(theta.cpu().numpy(), columns=list(self._flat_names))
+        out['chi'] = chi.cpu().numpy()
+        return out
+
+    def _mcmc_sharded(self, starts, seeds, nits, static_parameters, rng, want_frame, use_priors):
+        """The chains of one MCMC call over all ranks: contiguous blocks, chain seed / Philox key = GLOBAL chain index
+        (so the chains do not depend on the number of GPUs), then one all-gather of the per-chain results (summaries
+        for R-hat and the report; the kept rows too when the frame is wanted)."""
+        ws, rank = self._world()
+        C = len(starts)
+        lo, hi = shard_bounds(C, ws, rank)
+        P = len(self._flat_names)
+        burnin = int(nits / 2)
+        if rng == "auto":                                         # decided on the whole run, not on this rank's block
+            n_walk = sum(1 for owner in self._flat_owner() if owner not in set(static_parameters or ()))
+            rng = self._auto_rng(C, nits - 1, n_walk)
+        if hi > lo:
+            local = self._run_chains(starts[lo:hi], seeds[lo:hi], nits, burnin, static_parameters, rng=rng,
+                                     return_raw=True, keep_samples=want_frame, use_priors=use_priors)
+        else:                                                     # fewer chains than ranks: this rank only takes part in the collectives
+            if self.solver == "auto":
+                self._unfinished_fraction(0, 0)
+            n_keep = max(0, nits - 1 - burnin)
+            local = {"theta": np.empty((0, P)), "chain_state": np.empty((0, 8)), "summaries": np.empty((0, 1 + 2 * P)),
+                     "fail_count": np.empty(0, np.int32), "step_count": np.empty(0, np.int64), "best_theta": np.empty((0, P)),
+                     "samples": np.empty((0, n_keep, P + 5)) if want_frame else None, "n_keep": n_keep, "burnin": burnin}
+        out = dict(local)
+        for key in ("theta", "chain_state", "summaries", "fail_count", "step_count", "best_theta"):
+            out[key] = allgather_rows(np.asarray(local[key]))
+        out["best_chi"], out["best_iteration"] = out["chain_state"][:, 3], out["chain_state"][:, 4]
+        if want_frame:
+            smp = local["samples"]
+            smp = allgather_rows(smp)
+            out["samples"] = smp.cpu().numpy() if hasattr(smp, "is_cuda") else smp
+        self._last_mcmc = out
+        return self._frame_from_samples(out["samples"], set(static_parameters or ())) if want_frame else out
 
     def explore_equilibriums(self, samples=1000, cpu_cores=1, **parameter_mapping):
         """Final state of every LHS sample (Framework.py:819-854, `_Equilibrium_worker` :24-38) -- one batched launch
@@ -631,14 +716,14 @@ class ModelFramework:
             # the reference's own numpy streams (bit-for-bit the reference chain), regenerated on the host by the
             # library (odl_reference_streams) while the streams stay small next to the run (160 MB of host memory);
             # Philox on the device beyond that
-            rng = "reference" if C * n_iter * (len(walk) + 1) <= 20_000_000 else "philox"
+            rng = self._auto_rng(C, n_iter, len(walk))
         solver = self.solver
         if solver == "auto":
             probe = dm.sweep(theta0, rtol=self.rtol if rtol is None else rtol, atol=self.atol if atol is None else atol,
                              solver="dopri5", max_steps=512, stiff_check=True)
             st_ = probe["status"]
-            unfinished = float((st_ != 0).float().mean().item()) if on_device else float(np.mean(np.asarray(st_) != 0))
-            solver = "bdf" if unfinished > 0.25 else "dopri5"
+            n_bad = int((st_ != 0).sum().item()) if on_device else int(np.sum(np.asarray(st_) != 0))
+            solver = "bdf" if self._unfinished_fraction(n_bad, C) > 0.25 else "dopri5"
         self._last_solver = solver
         # "auto" that settled on DOPRI5: every solve gets a bounded step budget, and a chain that ever exhausts it (a
         # proposal in a stiff corner -- the reference's LSODA would switch to BDF there) is re-run, whole, on the BDF
@@ -695,14 +780,7 @@ class ModelFramework:
         static_cols = [(f, owner) for f, owner in zip(self._flat_names, self._flat_owner()) if owner in static]
         samples = out["samples"]                                  # [C, n_keep, P+5], rows = the reference frame's columns
         if return_frame:
-            # one frame for all chains, assembled without per-chain pandas work (Framework.py:1035-1038 equivalent)
-            flat = samples.reshape(-1, samples.shape[-1])
-            df = pd.DataFrame(flat, columns=cols)
-            df['iteration'] = df['iteration'].astype(np.int64)
-            for f, p in static_cols:   # reference quirk A13: static columns report the prior's scale (Samplers.py:166-170)
-                df[f] = self.parameters[p].hp['scale']
-            df['chain#'] = np.repeat(np.arange(C), samples.shape[1])
-            frames = df
+            frames = self._frame_from_samples(samples, static)
         else:
             frames = []
             for c in range(C):
@@ -718,6 +796,22 @@ class ModelFramework:
             if any(m >= 0 for m in self._y0_map()):
                 self.set_inits(**{s: out["theta"][0][m] for s, m in zip(self._snames, self._y0_map()) if m >= 0})
         return frames
+
+    @staticmethod
+    def _auto_rng(n_chains, n_iter, n_walk):
+        return "reference" if n_chains * n_iter * (n_walk + 1) <= 20_000_000 else "philox"
+
+    def _frame_from_samples(self, samples, static):
+        """One frame for all chains from the kernel's kept rows [C, n_keep, P+5], assembled without per-chain pandas
+        work (Framework.py:1035-1038 equivalent)."""
+        cols = list(self._flat_names) + ['chi', 'rsquared', 'aic', 'iteration', 'acceptance_ratio']
+        df = pd.DataFrame(samples.reshape(-1, samples.shape[-1]), columns=cols)
+        df['iteration'] = df['iteration'].astype(np.int64)
+        for f, p in zip(self._flat_names, self._flat_owner()):
+            if p in static:            # reference quirk A13: static columns report the prior's scale (Samplers.py:166-170)
+                df[f] = self.parameters[p].hp['scale']
+        df['chain#'] = np.repeat(np.arange(samples.shape[0]), samples.shape[1])
+        return df
 
     def _survey_starts_on_device(self, chain_inits, fitsurvey_samples, sd_fitdistance):
         """Chain starts for ``MCMC(chain_inits=int)`` (Framework.py:993-1016) without bringing the survey back:
@@ -789,7 +883,26 @@ class ModelFramework:
         if isinstance(chain_inits, pd.DataFrame):
             chain_inits = [row.to_dict() for _, row in chain_inits[list(self._flat_names)].iterrows()]
         base = self._current_theta()
-        if isinstance(chain_inits, (int, np.integer)):
+        ws, rank = self._world()
+        if isinstance(chain_inits, (int, np.integer)) and ws > 1:
+            # rank 0 surveys and picks (its numpy stream alone decides the picks), everyone gets the starts
+            import torch
+            import torch.distributed as dist
+            meta, starts = [None, False], None
+            if rank == 0:
+                try:
+                    starts = self._survey_starts_on_device(int(chain_inits), fitsurvey_samples, sd_fitdistance)
+                    meta[1] = starts is not None
+                except ValueError as exc:
+                    meta[0] = str(exc)
+            dist.broadcast_object_list(meta, src=0)
+            if meta[0]:
+                raise ValueError(meta[0])
+            if meta[1]:
+                starts = broadcast_rows(starts, (int(chain_inits), len(base))).to(torch.device("cuda", self._device().device))
+            else:
+                starts = [base.copy() for _ in range(chain_inits)]
+        elif isinstance(chain_inits, (int, np.integer)):
             starts = self._survey_starts_on_device(int(chain_inits), fitsurvey_samples, sd_fitdistance)
             if starts is None:
                 starts = [base.copy() for _ in range(chain_inits)]
@@ -809,9 +922,12 @@ class ModelFramework:
         n_chains = len(starts)
         seeds = list(range(n_chains))                             # chain seed = chain index (:1015, :1020)
         want_frame = posterior == "frame"
-        result = self._run_chains(starts, seeds, iterations_per_chain, int(iterations_per_chain / 2), static_parameters,
-                                  rng=rng, return_frame=want_frame, return_raw=not want_frame, keep_samples=want_frame,
-                                  use_priors=use_priors)
+        if ws > 1:
+            result = self._mcmc_sharded(starts, seeds, iterations_per_chain, static_parameters, rng, want_frame, use_priors)
+        else:
+            result = self._run_chains(starts, seeds, iterations_per_chain, int(iterations_per_chain / 2), static_parameters,
+                                      rng=rng, return_frame=want_frame, return_raw=not want_frame, keep_samples=want_frame,
+                                      use_priors=use_priors)
         summary = self.posterior_summary(static_parameters)
         self.rhat, self.ess = summary.rhat, summary.ess
         if print_report:

@@ -93,6 +93,48 @@ def allgather_summaries(local, n_total=None, group=None):
     return torch.cat(parts, dim=0)
 
 
+def _collective_device(group=None):
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def allgather_rows(local, group=None):
+    """All-gather an array whose FIRST axis is sharded in contiguous blocks over the ranks (shards may differ in
+    length, also be empty).  numpy in -> numpy out, torch in -> torch out (on the collective's device)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    is_np = isinstance(local, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(local)) if is_np else local
+    t = t.to(_collective_device(group)).contiguous()
+    tail = tuple(t.shape[1:])
+    width = 1
+    for d in tail:
+        width *= int(d)
+    flat = t.reshape(t.shape[0], width)                           # explicit width: an empty shard has no -1 to infer
+    out = allgather_summaries(flat, group=group)
+    out = out.reshape((out.shape[0],) + tail)
+    return out.cpu().numpy() if is_np else out
+
+
+def broadcast_rows(arr, shape, src=0, group=None):
+    """Broadcast a float64 table from rank `src` (numpy or torch there, None elsewhere); every rank gets a torch tensor
+    on the collective's device."""
+    import torch
+    import torch.distributed as dist
+    dev = _collective_device(group)
+    if dist.get_rank(group) == src:
+        t = (torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)) if isinstance(arr, np.ndarray) else arr)
+        t = t.to(dev, dtype=torch.float64).contiguous()
+        assert tuple(t.shape) == tuple(shape)
+    else:
+        t = torch.empty(tuple(shape), dtype=torch.float64, device=dev)
+    dist.broadcast(t, src=src, group=group)
+    return t
+
+
 def sharded_mcmc(dm, theta0_all, group=None, **mcmc_kw):
     """Run this rank's contiguous block of chains and all-gather the chain summaries for R-hat.
 

@@ -37,10 +37,30 @@ def main(out_path):
         dist.all_gather_object(parts, (lo, samples.cpu().numpy(), slo, chi.cpu().numpy()))
     else:
         parts = [(lo, samples.cpu().numpy(), slo, chi.cpu().numpy())]
+    # the reference's own surface, sharded by the facade itself (ModelFramework(distributed=True)): every rank makes the
+    # same calls and gets the complete frames
+    from tests.test_facade_host import make_model
+    m = make_model("two_i", distributed=True, device=local)
+    np.random.seed(11)
+    sv = m.fit_survey(samples=3001)
+    np.random.seed(12)
+    post = m.MCMC(chain_inits=7, iterations_per_chain=80, fitsurvey_samples=3001, sd_fitdistance=6.0, print_report=False)
+    rh_f, ess_f = np.array(list(m.rhat.values())), np.array(list(m.ess.values()))
+    summ = m.MCMC(chain_inits=[m.get_parameters(as_dict=True)] * 5, iterations_per_chain=60, print_report=False,
+                  posterior="summary", rng="philox")
+    one = m.MCMC(chain_inits=[{}], iterations_per_chain=40, print_report=False)      # fewer chains than ranks
+    if ws > 1:
+        frames = [None] * ws
+        dist.all_gather_object(frames, (sv.to_numpy(), post.to_numpy()))
+        for f in frames[1:]:                                      # every rank holds the same complete result
+            np.testing.assert_array_equal(f[0], frames[0][0])
+            np.testing.assert_array_equal(f[1], frames[0][1])
     if rank == 0:
         parts.sort(key=lambda p: p[0])
         np.savez(out_path, samples=np.concatenate([p[1] for p in parts]), chi=np.concatenate([p[3] for p in parts]),
-                 rhat=rh, world=ws)
+                 rhat=rh, world=ws, facade_survey=sv.to_numpy(), facade_post=post.to_numpy(), facade_rhat=rh_f,
+                 facade_ess=ess_f, facade_best=np.array(list(summ.best.values()) + [summ.best_chi, summ.acceptance_ratio]),
+                 facade_one=one.to_numpy())
     if ws > 1:
         dist.barrier()
         dist.destroy_process_group()

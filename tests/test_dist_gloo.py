@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from odelib_b200.rhat import allgather_summaries, rhat_from_summaries, shard_bounds
+from odelib_b200.rhat import allgather_rows, allgather_summaries, broadcast_rows, rhat_from_summaries, shard_bounds
 from oracle import odelib_oracle as orc
 
 
@@ -40,6 +40,17 @@ def _worker(rank, ws, port, m_total, out_dir):
     lo, hi = shard_bounds(m_total, ws, rank)
     gathered = allgather_summaries(torch.from_numpy(full[lo:hi].copy()))
     np.save(os.path.join(out_dir, f"g{rank}.npy"), gathered.numpy())
+    # the facade's sharding helpers: ragged / empty first-axis shards of any rank, numpy and torch; table broadcast
+    cube = np.arange(m_total * 4 * 3, dtype=np.float64).reshape(m_total, 4, 3)
+    counts = np.arange(m_total, dtype=np.int32)
+    assert np.array_equal(allgather_rows(cube[lo:hi]), cube)
+    assert np.array_equal(allgather_rows(counts[lo:hi]), counts) and allgather_rows(counts[lo:hi]).dtype == np.int32
+    assert torch.equal(allgather_rows(torch.from_numpy(cube[lo:hi].copy())), torch.from_numpy(cube))
+    few = cube[:1]                                                # fewer rows than ranks: some shards are empty
+    flo, fhi = shard_bounds(1, ws, rank)
+    assert np.array_equal(allgather_rows(few[flo:fhi]), few)
+    table = broadcast_rows(cube[:, :, 0].copy() if rank == 0 else None, (m_total, 4))
+    assert np.array_equal(table.numpy(), cube[:, :, 0])
     dist.destroy_process_group()
 
 
