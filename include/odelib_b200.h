@@ -155,6 +155,8 @@ int odl_model_set_data(odl_model* m, int n_slot, const double* slot_time, int n_
                        const double* y0, const int* y0_from_param, double t0);
 int odl_model_set_grid(odl_model* m, int n_t, const double* times, const double* y0, const int* y0_from_param);
 
+/* chi[n] is required; r2[n], status[n], nsteps[n], pred[n][n_obs] are optional (NULL = not wanted: neither written by
+   the kernels nor copied back).  A solve that failed has chi = NaN whether or not its status word is asked for. */
 int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, const double* theta, int mem,
               double* chi, double* r2, int* status, int* nsteps, double* pred_or_null, void* stream);
 int odl_trajectory(odl_model* m, const odl_solver_opts* so, long long n, const double* theta,

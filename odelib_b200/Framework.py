@@ -449,13 +449,16 @@ class ModelFramework:
         return pd.Series(mod['abundance'].to_numpy() - np.concatenate(parts), index=mod.index, name='abundance')
 
     # ------------------------------------------------------------------ batch seam: _Fit_worker (Framework.py:41-48)
-    def sweep(self, parameter_array, rtol=None, atol=None, solver="auto", as_dataframe=False, out=None):
+    def sweep(self, parameter_array, rtol=None, atol=None, solver="auto", as_dataframe=False, out=None,
+              outputs=("chi", "r2", "status", "nsteps")):
         """chi (and R^2, status, steps) for every row of ``parameter_array`` [n, P] (parameter_names order).
 
-        numpy in -> numpy out (host buffers, copies inside the call); torch CUDA tensor in -> tensors out."""
+        numpy in -> numpy out (host buffers, copies inside the call); torch CUDA tensor in -> tensors out.
+        ``outputs``: what to produce besides chi -- ``("chi",)`` is what the reference's `_Fit_worker` returns
+        (Framework.py:41-48) and leaves 8 instead of 24 bytes per row to copy back."""
         dm = self._device()
         res = dm.sweep(parameter_array, rtol=self.rtol if rtol is None else rtol,
-                       atol=self.atol if atol is None else atol, solver=solver, out=out)
+                       atol=self.atol if atol is None else atol, solver=solver, out=out, outputs=outputs)
         if as_dataframe:
             df = pd.DataFrame(np.asarray(parameter_array), columns=list(self._flat_names))
             df['chi'] = res['chi']
@@ -518,12 +521,12 @@ class ModelFramework:
             return self._fit_survey_sharded(samples, sampler)
         theta_dev = self._lhs_samples_device(samples, sampler)
         if theta_dev is not None:
-            res = self._device().sweep(theta_dev, rtol=self.rtol, atol=self.atol, solver="auto")
+            res = self._device().sweep(theta_dev, rtol=self.rtol, atol=self.atol, solver="auto", outputs=("chi",))
             out = pd.DataFrame(theta_dev.cpu().numpy(), columns=list(self._flat_names))
             out['chi'] = res['chi'].cpu().numpy()
             return out
         ps = self._lhs_samples(samples)[list(self._flat_names)]
-        res = self.sweep(ps.to_numpy(dtype=np.float64))
+        res = self.sweep(ps.to_numpy(dtype=np.float64), outputs=("chi",))
         out = ps.reset_index(drop=True)
         out['chi'] = res['chi']
         return out
@@ -565,7 +568,7 @@ class ModelFramework:
         theta = broadcast_rows(theta, (int(samples), len(self._flat_names))).to(torch.device("cuda", dm.device))
         lo, hi = shard_bounds(int(samples), ws, rank)
         if hi > lo:
-            chi = dm.sweep(theta[lo:hi], rtol=self.rtol, atol=self.atol, solver="auto")["chi"]
+            chi = dm.sweep(theta[lo:hi], rtol=self.rtol, atol=self.atol, solver="auto", outputs=("chi",))["chi"]
         else:
             chi = torch.empty(0, dtype=torch.float64, device=theta.device)
         chi = allgather_rows(chi)
@@ -825,7 +828,7 @@ class ModelFramework:
         if theta is None:
             ps = self._lhs_samples(fitsurvey_samples)[list(self._flat_names)]
             theta = torch.from_numpy(np.ascontiguousarray(ps.to_numpy(dtype=np.float64))).to(torch.device("cuda", dm.device))
-        res = dm.sweep(theta, rtol=self.rtol, atol=self.atol, solver="auto")
+        res = dm.sweep(theta, rtol=self.rtol, atol=self.atol, solver="auto", outputs=("chi",))
         calc = {s: np.exp(self._obs_logabundance[s] + sd_fitdistance * self._obs_logsigma[s]) for s in self._obs_logabundance}
         cutchi = self.get_chi(calc)                              # = n_obs * sd^2 / 2
         _, n_finite = dm.select_below(res["chi"], np.inf)

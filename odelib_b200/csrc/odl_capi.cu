@@ -145,7 +145,7 @@ struct odl_model {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evp[2] = {nullptr, nullptr};   // between the cohort passes of an AUTO sweep
   cudaEvent_t ev_aux = nullptr, ev_fork = nullptr;
-  cudaEvent_t ev_chunk[2] = {nullptr, nullptr};   // host-memory sweeps: theta arrives in two pieces on the helper stream
+  cudaEvent_t ev_chunk[3] = {nullptr, nullptr, nullptr};   // host-memory sweeps: theta arrives in pieces on the helper stream
   cudaStream_t aux = nullptr;                // helper stream: the Radau5 pass runs beside the deferred DOPRI5 pass
   int n_pass = 0;
   bool timed = false;
@@ -297,6 +297,7 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
       cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_chunk[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_chunk[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_chunk[2], cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking) != cudaSuccess)
     return bail(fail(ODL_ECUDA, "cudaEventCreate / cudaStreamCreate failed"));
   if ((rc = m->counter.ensure(8192))) return bail(rc);
@@ -516,7 +517,9 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
                          double* chi, double* r2, int* status, int* nsteps, double* pred_or_null, void* stream) {
   if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_sweep: model is not loaded on a GPU (no CPU fallback exists)");
   if (!m->data.set) return fail(ODL_EINVAL, "odl_sweep: call odl_model_set_data first");
-  if (n < 0 || (n > 0 && (!theta || !chi || !r2 || !status || !nsteps))) return fail(ODL_EINVAL, "odl_sweep: null buffer");
+  // r2, status, nsteps are optional (NULL = not wanted: neither written nor copied back); the reference's own batch
+  // seam returns chi alone (_Fit_worker, Framework.py:41-48), a failed solve shows as chi = NaN either way
+  if (n < 0 || (n > 0 && (!theta || !chi))) return fail(ODL_EINVAL, "odl_sweep: null buffer");
   if (n == 0) return 0;
   const int solver = so ? so->solver : ODL_SOLVER_DOPRI5;
   if (solver < 0 || solver > ODL_SOLVER_BDF) return fail(ODL_EINVAL, "odl_sweep: unknown solver");
@@ -528,9 +531,10 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   Staging st{m, s, 0, mem};
   OdlSweepArgs A{};
   int rc;
-  // Host-memory ODL_SOLVER_AUTO sweep of a large table: theta travels in two pieces on the helper stream and the second
-  // piece arrives while the first is being ordered and integrated (each piece is ordered and swept on its own; the
-  // stiff pass runs once over what both leave).  Rows are independent, so the pieces change nothing in the results.
+  // Host-memory ODL_SOLVER_AUTO sweep of a large table: theta travels in three pieces (1/8, 3/8, 1/2 of the rows) on the
+  // helper stream; only the small first piece is waited for, the others arrive while the piece before is being ordered
+  // and integrated (each piece is ordered and swept on its own; the stiff pass runs once over what all of them leave).
+  // Rows are independent, so the pieces change nothing in the results.
   const int auto_flags = so ? so->auto_flags : 0;
   const bool chunked = mem == ODL_MEM_HOST && solver == ODL_SOLVER_AUTO && n >= (1 << 18) && !m->k_sweep_coop &&
                        !(auto_flags & (ODL_AUTO_UNORDERED | ODL_AUTO_CONCURRENT | ODL_AUTO_ONE_PIECE));
@@ -627,7 +631,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       OdlOrderArgs R{};
       const long long np = hi - lo;
       R.theta = A.theta + lo * m->n_param; R.n = np; R.bins = static_cast<unsigned char*>(bbins.p) + lo;
-      R.hist = cnt(piece ? 4096 : 1024); R.cursor = cnt(piece ? 5120 : 2048); R.index = index + lo;
+      R.hist = cnt(1024 + 2048 * piece); R.cursor = cnt(2048 + 2048 * piece); R.index = index + lo;
       R.row_base = (int)lo; R.pad_ = 0;
       OdlData Dl = D;
       void* p1[] = {&Dl, &R};
@@ -639,17 +643,19 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       if ((r = launch(m, m->k_order_scan, 1, ODL_ORDER_BINS, 0, s, p2))) return r;
       return launch(m, m->k_order_scatter, g3, 256, 0, s, p2);
     };
-    const long long half = chunked ? ((n / 2 + 1023) / 1024) * 1024 : n;
+    // piece boundaries: [0, n/8, n/2, n] rounded to 1024 rows (one piece when the table is already on the device)
+    const int n_piece = chunked ? 3 : 1;
+    long long cut[4] = {0, n, n, n};
+    if (chunked) { cut[1] = ((n / 8 + 1023) / 1024) * 1024; cut[2] = ((n / 2 + 1023) / 1024) * 1024; }
     if (chunked) {
-      for (int c = 0; c < 2; ++c) {
-        const long long lo = c ? half : 0, hi = c ? n : half;
-        ODL_CUDA(cudaMemcpyAsync(const_cast<double*>(A.theta) + lo * m->n_param, theta + lo * m->n_param,
-                                 (size_t)(hi - lo) * m->n_param * sizeof(double), cudaMemcpyHostToDevice, m->aux));
+      for (int c = 0; c < n_piece; ++c) {
+        ODL_CUDA(cudaMemcpyAsync(const_cast<double*>(A.theta) + cut[c] * m->n_param, theta + cut[c] * m->n_param,
+                                 (size_t)(cut[c + 1] - cut[c]) * m->n_param * sizeof(double), cudaMemcpyHostToDevice, m->aux));
         ODL_CUDA(cudaEventRecord(m->ev_chunk[c], m->aux));
       }
       ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[0], 0));
     }
-    if (ordered && (rc = order_piece(0, half, 0))) return rc;
+    if (ordered && (rc = order_piece(0, cut[1], 0))) return rc;
     ODL_CUDA(cudaEventRecord(m->evp[1], s));
     const unsigned block0 = pick_block(D, m->block);
     const size_t smem0 = smem_bytes(D, (int)block0), smem_t = smem_bytes(D, 32);
@@ -693,7 +699,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     O2.lanes = so && so->tail_lanes > 0 ? std::min(32, so->tail_lanes) : 0;
     OdlSweepArgs A2 = A;
     A2.index = feed; A2.index_count = cnt(64); A2.counter = nullptr; A2.feed_ticket = ctr(128);
-    A2.prod_counter = ctr(0); A2.prod_n = chunked ? half : n;    // the (first) bulk launch's counter and item count
+    A2.prod_counter = ctr(0); A2.prod_n = cut[1];                // the (first) bulk launch's counter and item count
     A2.prod_started = cnt(192); A2.prod_exited = cnt(256);
     A2.watchdog = cnt(320);
     A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
@@ -714,14 +720,19 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       if (m->k_sweep_coop) { if ((rc = go_coop(s, O0, A0, n))) return rc; }      // n > 8: several lanes per system
       else if (!chunked) { if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc; }
       else {
-        OdlSweepArgs A1 = A0;
-        A0.n = half;                                         // pb points at A0: first piece, index[0..half)
-        if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc;
-        ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[1], 0));
-        if ((rc = order_piece(half, n, 1))) return rc;
-        A1.n = n - half; A1.index = index + half; A1.counter = ctr(384);
-        void* pb1[] = {&Dl, &O0, &A1};
-        if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb1))) return rc;
+        const OdlSweepArgs Aall = A0;
+        A0.n = cut[1];                                       // pb points at A0: first piece, index[0..cut[1])
+        const unsigned g0 = (unsigned)std::max<long long>(1, std::min<long long>((cut[1] + block0 - 1) / block0, (long long)grid0));
+        if ((rc = launch(m, m->k_sweep, g0, block0, smem0, s, pb))) return rc;
+        for (int c = 1; c < n_piece; ++c) {
+          ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[c], 0));
+          if ((rc = order_piece(cut[c], cut[c + 1], c))) return rc;
+          OdlSweepArgs Ac = Aall;
+          Ac.n = cut[c + 1] - cut[c]; Ac.index = index + cut[c]; Ac.counter = ctr(384 + 64 * (c - 1));
+          void* pbc[] = {&Dl, &O0, &Ac};
+          const unsigned gc = (unsigned)std::max<long long>(1, std::min<long long>((Ac.n + block0 - 1) / block0, (long long)grid0));
+          if ((rc = launch(m, m->k_sweep, gc, block0, smem0, s, pbc))) return rc;
+        }
       }
       ODL_CUDA(cudaEventRecord(m->evp[0], s));
       if ((rc = launch(m, k_tail, grid_t, 32, smem_t, s, pt))) return rc;

@@ -1520,8 +1520,10 @@ ODL_UNROLL
         double r2 = 1.0 - ss / D.sstot;
         if (status != ODL_OK) { chi = __longlong_as_double(0x7ff8000000000000LL); r2 = chi; }
         else if (nv == 0) { chi = __longlong_as_double(0x7ff8000000000000LL); status |= ODL_ALLMASKED; }
-        A.chi[row] = chi; A.r2[row] = r2; A.status[row] = status;
-        A.nsteps[row] = fin_nsteps;
+        A.chi[row] = chi;                                        // r2 / status / nsteps only when the caller asked for them
+        if (A.r2) A.r2[row] = r2;
+        if (A.status) A.status[row] = status;
+        if (A.nsteps) A.nsteps[row] = fin_nsteps;
         if (fin_status == ODL_MAXSTEPS && A.defer_list[0]) A.defer_list[0][atomicAdd(A.defer_count[0], 1)] = (int)row;
         if (fin_status == ODL_STIFF && A.defer_list[1]) A.defer_list[1][atomicAdd(A.defer_count[1], 1)] = (int)row;
       }
@@ -2272,7 +2274,10 @@ odl_sweep_coop_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
       double r2 = 1.0 - ss / D.sstot;
       if (status != ODL_OK) { chi = __longlong_as_double(0x7ff8000000000000LL); r2 = chi; }
       else if (nv == 0) { chi = __longlong_as_double(0x7ff8000000000000LL); status |= ODL_ALLMASKED; }
-      A.chi[row] = chi; A.r2[row] = r2; A.status[row] = status; A.nsteps[row] = st.nsteps;
+      A.chi[row] = chi;
+      if (A.r2) A.r2[row] = r2;
+      if (A.status) A.status[row] = status;
+      if (A.nsteps) A.nsteps[row] = st.nsteps;
       if (st.status == ODL_MAXSTEPS && A.defer_list[0]) A.defer_list[0][atomicAdd(A.defer_count[0], 1)] = (int)row;
     }
     __syncwarp(G.mask);

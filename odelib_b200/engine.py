@@ -172,10 +172,12 @@ class DeviceModel:
     # -- forward sweep: _Fit_worker (Framework.py:41-48) -------------------------------------------
     def sweep(self, theta, rtol=None, atol=None, max_steps=500000, solver="dopri5", stiff_check=False,
               return_pred=False, out=None, stiff_min_steps=0, pass_caps=(0, 0), tail_solver=None, early_check_steps=0,
-              tail_lanes=0, tail_warps=0, auto_flags=0):
+              tail_lanes=0, tail_warps=0, auto_flags=0, outputs=("chi", "r2", "status", "nsteps")):
         """theta [n, P] (numpy -> host path, torch cuda tensor -> device path).
 
-        Returns dict(chi, r2, status, nsteps[, pred]) of the same kind as the input."""
+        Returns dict(chi, r2, status, nsteps[, pred]) of the same kind as the input.  ``outputs``: which of r2 / status /
+        nsteps to produce besides chi (the others come back as None and are neither written nor copied)."""
+        want = set(outputs) | {"chi"}
         so = self._solver_opts(rtol, atol, max_steps, solver, stiff_check, stiff_min_steps=stiff_min_steps,
                                pass_caps=pass_caps, tail_solver=tail_solver, early_check_steps=early_check_steps, tail_lanes=tail_lanes,
                                tail_warps=tail_warps, auto_flags=auto_flags)
@@ -186,9 +188,9 @@ class DeviceModel:
             n = th.shape[0]
             o = out or {}
             chi = o.get("chi") if "chi" in o else torch.empty(n, dtype=torch.float64, device=th.device)
-            r2 = o.get("r2") if "r2" in o else torch.empty(n, dtype=torch.float64, device=th.device)
-            status = o.get("status") if "status" in o else torch.empty(n, dtype=torch.int32, device=th.device)
-            nsteps = o.get("nsteps") if "nsteps" in o else torch.empty(n, dtype=torch.int32, device=th.device)
+            r2 = (o.get("r2") if "r2" in o else torch.empty(n, dtype=torch.float64, device=th.device)) if "r2" in want else None
+            status = (o.get("status") if "status" in o else torch.empty(n, dtype=torch.int32, device=th.device)) if "status" in want else None
+            nsteps = (o.get("nsteps") if "nsteps" in o else torch.empty(n, dtype=torch.int32, device=th.device)) if "nsteps" in want else None
             pred = (o.get("pred") if "pred" in o else torch.empty((n, self.n_obs), dtype=torch.float64, device=th.device)) if return_pred else None
             mem, stream = _capi.MEM_DEVICE, self._stream()
         else:
@@ -198,9 +200,9 @@ class DeviceModel:
             n = th.shape[0]
             o = out or {}
             chi = o.get("chi") if "chi" in o else np.empty(n, np.float64)
-            r2 = o.get("r2") if "r2" in o else np.empty(n, np.float64)
-            status = o.get("status") if "status" in o else np.empty(n, np.int32)
-            nsteps = o.get("nsteps") if "nsteps" in o else np.empty(n, np.int32)
+            r2 = (o.get("r2") if "r2" in o else np.empty(n, np.float64)) if "r2" in want else None
+            status = (o.get("status") if "status" in o else np.empty(n, np.int32)) if "status" in want else None
+            nsteps = (o.get("nsteps") if "nsteps" in o else np.empty(n, np.int32)) if "nsteps" in want else None
             pred = (o.get("pred") if "pred" in o else np.empty((n, self.n_obs), np.float64)) if return_pred else None
             mem, stream = _capi.MEM_HOST, None
         _capi.check(self._L.odl_sweep(self._h, C.byref(so), n, _ptr(th), mem, _ptr(chi), _ptr(r2), _ptr(status),

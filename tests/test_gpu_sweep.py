@@ -90,6 +90,25 @@ def test_device_and_host_paths_agree_bitwise():
     assert np.array_equal(host["nsteps"], dev["nsteps"].cpu().numpy())
 
 
+def test_optional_outputs_are_neither_written_nor_copied():
+    """chi alone is what the reference's batch seam returns (_Fit_worker, Framework.py:41-48): R^2, status and step
+    counts are produced only on request, and chi does not depend on what else was asked for."""
+    import torch
+    dm, _ = device_model("two_i")
+    theta = prior_draws("two_i", 3000, seed=8)
+    full = dm.sweep(theta, solver="auto")
+    for solver in ("auto", "dopri5", "bdf"):
+        ref = dm.sweep(theta, solver=solver, max_steps=200000)
+        only = dm.sweep(theta, solver=solver, max_steps=200000, outputs=("chi",))
+        assert only["r2"] is None and only["status"] is None and only["nsteps"] is None
+        np.testing.assert_array_equal(only["chi"], ref["chi"])
+    some = dm.sweep(torch.from_numpy(theta).cuda(), solver="auto", outputs=("chi", "status"))
+    assert some["r2"] is None and some["nsteps"] is None
+    np.testing.assert_array_equal(some["chi"].cpu().numpy(), full["chi"])
+    np.testing.assert_array_equal(some["status"].cpu().numpy(), full["status"])
+    assert np.all(np.isnan(full["chi"]) == (full["status"] != 0))   # a failed solve shows in chi itself
+
+
 def test_edge_cases_empty_ragged_and_failures():
     dm, _ = device_model("zero_i")
     out = dm.sweep(np.empty((0, 3)))
