@@ -531,10 +531,9 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   Staging st{m, s, 0, mem};
   OdlSweepArgs A{};
   int rc;
-  // Host-memory ODL_SOLVER_AUTO sweep of a large table: theta travels in three pieces (1/8, 3/8, 1/2 of the rows) on the
-  // helper stream; only the small first piece is waited for, the others arrive while the piece before is being ordered
-  // and integrated (each piece is ordered and swept on its own; the stiff pass runs once over what all of them leave).
-  // Rows are independent, so the pieces change nothing in the results.
+  // Host-memory ODL_SOLVER_AUTO sweep of a large table: theta travels in two pieces on the helper stream and the second
+  // piece arrives while the first is being ordered and integrated (each piece is ordered and swept on its own; the
+  // stiff pass runs once over what both leave).  Rows are independent, so the pieces change nothing in the results.
   const int auto_flags = so ? so->auto_flags : 0;
   const bool chunked = mem == ODL_MEM_HOST && solver == ODL_SOLVER_AUTO && n >= (1 << 18) && !m->k_sweep_coop &&
                        !(auto_flags & (ODL_AUTO_UNORDERED | ODL_AUTO_CONCURRENT | ODL_AUTO_ONE_PIECE));
@@ -643,10 +642,12 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       if ((r = launch(m, m->k_order_scan, 1, ODL_ORDER_BINS, 0, s, p2))) return r;
       return launch(m, m->k_order_scatter, g3, 256, 0, s, p2);
     };
-    // piece boundaries: [0, n/8, n/2, n] rounded to 1024 rows (one piece when the table is already on the device)
-    const int n_piece = chunked ? 3 : 1;
+    // piece boundaries: [0, n/2, n] rounded to 1024 rows (one piece when the table is already on the device).  Measured
+    // on B200, 1M two_i rows through host buffers: two halves 190 M solves/s, three pieces (1/8, 3/8, 1/2) 180 M/s --
+    // every extra bulk launch ends on its own stragglers, which costs more than the shorter wait for the first piece.
+    const int n_piece = chunked ? 2 : 1;
     long long cut[4] = {0, n, n, n};
-    if (chunked) { cut[1] = ((n / 8 + 1023) / 1024) * 1024; cut[2] = ((n / 2 + 1023) / 1024) * 1024; }
+    if (chunked) cut[1] = ((n / 2 + 1023) / 1024) * 1024;
     if (chunked) {
       for (int c = 0; c < n_piece; ++c) {
         ODL_CUDA(cudaMemcpyAsync(const_cast<double*>(A.theta) + cut[c] * m->n_param, theta + cut[c] * m->n_param,
