@@ -143,7 +143,10 @@ __device__ __forceinline__ void odl_score(const OdlShared& S, const OdlData& D, 
     const double d = __dadd_rn(S.lnO[o], -log(pred));          // masked_invalid(O) - C
     const double dd = __dmul_rn(d, d);                          // (...)**2   : masked when not finite
     const double den = S.denom[o];
-    const double term = dd / den;                               // / (2*S**2): masked on domain or non-finite
+    // / (2*S**2): masked on domain or non-finite.  (A NaN numerator -- log of a prediction that dipped below zero, ~2 of
+    // the 37 observations per prior draw -- takes the division's out-of-line slow path: 3.6 % of the sweep kernel's
+    // instructions, but issued for two lanes beside 30 busy ones; dividing 1.0 instead measured no gain, profiles/r1f.)
+    const double term = dd / den;
     const bool ok = odl_finite(dd) && odl_finite(term) && !(fabs(dd) * ODL_DBL_MIN >= fabs(den));
     if (ok) { c += term; ++k; }
     const double r = __dadd_rn(pred, -S.lin[o]);
@@ -1514,6 +1517,7 @@ ODL_UNROLL
       const int statL = __shfl_sync(ODL_FULL, fin_status, L);
       double chi, ss; int nv;
       double* pred_out = (A.pred && statL == ODL_OK) ? A.pred + rowL * D.n_obs : nullptr;
+      // (unfinished solves are scored too: a branch around the inlined scorer costs more -- +2 % -- than their 2.5 %)
       odl_score(S, D, S.stage + (size_t)((threadIdx.x & ~31) + L) * D.stage_stride, lane, pred_out, chi, ss, nv);
       if (lane == L) {
         int status = fin_status;
