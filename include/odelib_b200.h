@@ -83,8 +83,9 @@ typedef struct odl_solver_opts {
   int tail_solver;     /* ODL_SOLVER_AUTO: stepper of the pass over what DOPRI5 did not finish:
                           0 = default (ODL_SOLVER_BDF), or ODL_SOLVER_RADAU5 */
   int early_check_steps; /* ODL_SOLVER_AUTO: the first pass drops a system after this many attempts when its progress
-                          projects beyond pass_cap0 (0 = pass_cap0/2, -1 = never) */
-  int tail_lanes;      /* ODL_SOLVER_AUTO: lanes per warp that take systems in the stiff pass (0 = 32) */
+                          projects beyond pass_cap0 (0 = 3/4 of pass_cap0, -1 = never) */
+  int tail_lanes;      /* ODL_SOLVER_AUTO: lanes per warp that take systems in the stiff pass (0 = as few as spreading its
+                          systems over every resident warp takes; 32 = full warps) */
   int auto_flags;      /* ODL_SOLVER_AUTO: ODL_AUTO_* bits, 0 = cost-ordered DOPRI5 pass, then the stiff pass */
 } odl_solver_opts;
 

@@ -598,7 +598,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     //            (Spearman 0.73 with the DOPRI5 step count on the demo priors; the 1 % longest systems all sit in
     //            the first tenth).  Long systems start first, so the launch does not end on a few stragglers, and
     //            the ones DOPRI5 cannot finish are found while most of the sweep is still ahead.
-    //   bulk     DOPRI5, every system in that order, at most cap0 attempted steps (a half-way check drops systems
+    //   bulk     DOPRI5, every system in that order, at most cap0 attempted steps (a check at 3/4 of them drops systems
     //            whose progress projects beyond the cap; Hairer's test drops the ones it calls stiff) -> feed list
     //   stiff    variable-order BDF (or Radau5) over the feed list, single-warp CTAs, as many as fit.  It is bound by
     //            the latency of its longest systems (~1000 sequential steps), not by throughput.
@@ -689,15 +689,18 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       tail_warps = per_sm_t;
     }
     OdlOpts O0 = O; O0.stiff_check = 1; O0.max_steps = std::min(cap0, O.max_steps);
-    // half-way check: a system whose progress projects beyond the cap leaves at cap0/2 (recall ~100 %, precision ~50 %
-    // on the demo priors)
-    O0.early_check_steps = so && so->early_check_steps != 0 ? std::max(0, so->early_check_steps) : O0.max_steps / 2;
+    // projection check at 3/4 of the cap: a system whose progress projects beyond the cap leaves there.  (At cap0/2 the
+    // check has recall ~100 % but precision ~50 %: it doubled the stiff pass's load with long NON-stiff systems -- 19 %
+    // of the zero_i sweep, 1-2 % of one_i / two_i, measured with tools/variant_ab.py.)
+    O0.early_check_steps = so && so->early_check_steps != 0 ? std::max(0, so->early_check_steps) : O0.max_steps * 3 / 4;
     OdlSweepArgs A0 = A;
     A0.index = ordered ? index : nullptr;
     A0.defer_list[0] = A0.defer_list[1] = feed; A0.defer_count[0] = A0.defer_count[1] = cnt(64);
     A0.prod_started = cnt(192); A0.prod_exited = cnt(256);
     OdlOpts O2 = O; O2.stiff_check = 0;
-    O2.lanes = so && so->tail_lanes > 0 ? std::min(32, so->tail_lanes) : 0;
+    // lanes per warp in the stiff pass: given, or (after the bulk pass, feed complete) as few as spreading the feed over
+    // every resident warp takes -- measured 1.80 -> 1.73 ms at 24 of 32 lanes; beside the bulk pass all 32
+    O2.lanes = so && so->tail_lanes > 0 ? std::min(32, so->tail_lanes) : (concurrent ? 0 : -1);
     OdlSweepArgs A2 = A;
     A2.index = feed; A2.index_count = cnt(64); A2.counter = nullptr; A2.feed_ticket = ctr(128);
     A2.prod_counter = ctr(0); A2.prod_n = cut[1];                // the (first) bulk launch's counter and item count
