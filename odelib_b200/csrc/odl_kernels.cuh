@@ -1639,6 +1639,7 @@ extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
 odl_sweep_ros23_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<1>(D, O, A); }
 extern "C" __global__ void __launch_bounds__(32, 1)
 odl_sweep_radau5_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<3>(D, O, A); }
+// (register caps for more resident warps spill: 168 registers -> 3.1 ms against 1.6 ms at 226, tools/variant_ab.py)
 extern "C" __global__ void __launch_bounds__(32, 1)
 odl_sweep_bdf_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<4>(D, O, A); }
 

@@ -35,5 +35,5 @@ for variant in (sys.argv[1:] or [""]):
         torch.cuda.synchronize()
         if rep and dm.last_kernel_ms() < best:
             best, passes = dm.last_kernel_ms(), dm.last_pass_ms()
-    print("%-70s total %.3f ms  passes %s  regs %s" % (label or "(default)", best, [round(x, 3) for x in passes], dm.kernel_info("sweep")), flush=True)
+    print("%-70s total %.3f ms  passes %s  regs %s bdf %s" % (label or "(default)", best, [round(x, 3) for x in passes], dm.kernel_info("sweep"), dm.kernel_info("sweep_bdf")), flush=True)
     dm.close()
