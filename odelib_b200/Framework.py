@@ -525,7 +525,8 @@ class ModelFramework:
         theta_dev = self._lhs_samples_device(samples, sampler)
         if theta_dev is not None:
             res = self._device().sweep(theta_dev, rtol=self.rtol, atol=self.atol, solver="auto", outputs=("chi",))
-            out = pd.DataFrame(theta_dev.cpu().numpy(), columns=list(self._flat_names))
+            # the host copy of the table is fresh memory nobody else holds: the frame adopts it (no second 40 MB copy)
+            out = pd.DataFrame(theta_dev.cpu().numpy(), columns=list(self._flat_names), copy=False)
             out['chi'] = res['chi'].cpu().numpy()
             return out
         ps = self._lhs_samples(samples)[list(self._flat_names)]
@@ -575,7 +576,7 @@ class ModelFramework:
         else:
             chi = torch.empty(0, dtype=torch.float64, device=theta.device)
         chi = allgather_rows(chi)
-        out = pd.DataFrame(theta.cpu().numpy(), columns=list(self._flat_names))
+        out = pd.DataFrame(theta.cpu().numpy(), columns=list(self._flat_names), copy=False)
         out['chi'] = chi.cpu().numpy()
         return out
 
@@ -811,7 +812,7 @@ class ModelFramework:
         """One frame for all chains from the kernel's kept rows [C, n_keep, P+5], assembled without per-chain pandas
         work (Framework.py:1035-1038 equivalent)."""
         cols = list(self._flat_names) + ['chi', 'rsquared', 'aic', 'iteration', 'acceptance_ratio']
-        df = pd.DataFrame(samples.reshape(-1, samples.shape[-1]), columns=cols)
+        df = pd.DataFrame(samples.reshape(-1, samples.shape[-1]), columns=cols, copy=False)   # adopts the kernel's rows
         df['iteration'] = df['iteration'].astype(np.int64)
         for f, p in zip(self._flat_names, self._flat_owner()):
             if p in static:            # reference quirk A13: static columns report the prior's scale (Samplers.py:166-170)
