@@ -50,6 +50,16 @@ def test_array_valued_parameters_flat_layout():
     ps = m.get_parameters()[0]
     assert np.shape(ps[1]) == (2,) and np.shape(ps[0]) == ()
     assert m._pnum == 4                                           # AIC counts non-zero elements (Framework.py:260-263)
+    # the fixture recorded from the unmodified reference (tests/golden/make_array_param.py) is what scipy gives on the
+    # facade's own tables: same y0, grid, observation picks and chi
+    import os
+    from scipy.integrate import odeint
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "array_param.npz"))
+    np.testing.assert_array_equal(np.asarray(m.get_inits(), float), g["y0"])
+    mod = odeint(split_phi, m.get_inits(), m.times, args=(m.get_parameters()[0],))
+    pred = {s_: mod[:, i][m._pred_tindex[s_]] for i, s_ in enumerate(m.get_snames()) if s_ in m._pred_tindex}
+    np.testing.assert_array_equal(pred["S"], g["pred_S"])
+    assert m.get_chi(pred) == float(g["chi"])
     # the RHS traced through the slot adapter == the user's function on arrays
     tm = trace(m._device_ode(), 2, 4)
     y = np.array([5.0e6, 1.0e7])

@@ -219,9 +219,16 @@ def test_array_valued_parameters_on_the_device():
     (its value for this model, recorded from the unmodified reference, is below); its sample_lhs (Samplers.py:45) and
     chain (Framework.py:99) branches for arrays raise, so surveys and chains are checked against the equivalent scalar
     model instead."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "array_param.npz"))   # tests/golden/make_array_param.py
     m = make_array_model()
-    chi = m.get_chi(m.integrate(predict_obs=True, as_dataframe=False))
-    assert chi == pytest.approx(107.95005049151386, rel=2e-6)     # reference at odeint's default tolerance
+    np.testing.assert_array_equal(m._current_theta(), g["theta"])
+    pred = m.integrate(predict_obs=True, as_dataframe=False)
+    assert m.get_chi(pred) == pytest.approx(float(g["chi"]), rel=2e-6)        # reference at odeint's default tolerance
+    for s_ in ("S", "V"):
+        ok = g["pred_" + s_] > 1.0
+        np.testing.assert_allclose(pred[s_][ok], g["pred_" + s_][ok], rtol=5e-6)
+    assert list(g["raises"]) == ["ValueError", "TypeError"]                   # what the reference does with arrays there
     z = make_model("zero_i")                                      # phi = phi[0] + phi[1]: the same arithmetic
     rows = np.exp(np.random.default_rng(0).normal(size=(64, 4)) * 0.3) * m._current_theta()
     a = m.sweep(rows)
