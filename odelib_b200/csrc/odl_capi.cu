@@ -141,7 +141,7 @@ struct odl_model {
   CUfunction k_sweep_coop = nullptr, k_mcmc_coop = nullptr;   // n > 8 only: several lanes per system
   Tables data, grid;
   DevBuf counter;
-  DevBuf scratch[16];
+  DevBuf scratch[24];                        // [0, 20): staging slots of one call; 21-23: select / gather / sample helpers
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evp[2] = {nullptr, nullptr};   // between the cohort passes of an AUTO sweep
   cudaEvent_t ev_aux = nullptr, ev_fork = nullptr;
@@ -489,6 +489,7 @@ struct Staging {
   template <class T> int in(const T* host, size_t count, const T** dev) {
     if (!host) { *dev = nullptr; return 0; }
     if (mem == ODL_MEM_DEVICE) { *dev = host; return 0; }
+    if (next >= 20) return fail(ODL_EINVAL, "internal: staging slots exhausted");
     DevBuf& b = m->scratch[next++];
     int rc = b.ensure(count * sizeof(T)); if (rc) return rc;
     ODL_CUDA(cudaMemcpyAsync(b.p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
@@ -498,6 +499,7 @@ struct Staging {
   template <class T> int inout(T* host, size_t count, T** dev, bool copy_in) {
     if (!host) { *dev = nullptr; return 0; }
     if (mem == ODL_MEM_DEVICE) { *dev = host; return 0; }
+    if (next >= 20) return fail(ODL_EINVAL, "internal: staging slots exhausted");
     DevBuf& b = m->scratch[next++];
     int rc = b.ensure(count * sizeof(T)); if (rc) return rc;
     if (copy_in) ODL_CUDA(cudaMemcpyAsync(b.p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
@@ -1010,7 +1012,7 @@ extern "C" int odl_select_below(odl_model* m, const double* chi_dev, long long n
   ODL_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
   const int n_tile = (int)((n + ODL_SEL_TILE - 1) / ODL_SEL_TILE);
-  DevBuf& b = m->scratch[15];
+  DevBuf& b = m->scratch[23];
   int rc = b.ensure((size_t)n_tile * sizeof(int) + 16);
   if (rc) return rc;
   int* tiles = static_cast<int*>(b.p);
@@ -1032,7 +1034,7 @@ extern "C" int odl_gather_rows(odl_model* m, const double* src_dev, int row_len,
   if (n_pick == 0) return 0;
   ODL_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
-  DevBuf& b = m->scratch[14];
+  DevBuf& b = m->scratch[22];
   int rc = b.ensure((size_t)n_pick * sizeof(long long));
   if (rc) return rc;
   ODL_CUDA(cudaMemcpyAsync(b.p, picks_host, (size_t)n_pick * sizeof(long long), cudaMemcpyHostToDevice, s));
@@ -1125,7 +1127,7 @@ extern "C" int odl_sample_lhs(odl_model* m, long long n, int n_param, const int*
   if (n == 0) return 0;
   ODL_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
-  DevBuf& bk = m->scratch[13];
+  DevBuf& bk = m->scratch[21];
   int rc = bk.ensure((size_t)n_param * (sizeof(int) + 3 * sizeof(double)) + 64);
   if (rc) return rc;
   char* base = static_cast<char*>(bk.p);
