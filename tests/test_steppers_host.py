@@ -86,6 +86,24 @@ def test_bdf_converges_with_tolerance_and_is_cheap_on_the_stiff_variant(two_i):
     assert st == 0 and ns < 600 and _relerr(out, _ref(stiff, tab, slots)) < 1e-6
 
 
+def test_bdf_step_counts_on_the_stiff_tail_match_lsoda(two_i):
+    """The stiff pass of the sweep is bound by the latency of its longest systems, so their STEP COUNT is what its time
+    rests on: on the prior draws DOPRI5 does not finish in 512 attempts, the BDF stepper needs about as many steps as
+    LSODA itself reports (nst) -- 883 vs 870 on the worst of 60,000 draws when this was written."""
+    from tests.helpers import prior_draws
+    lib, tab, slots = two_i
+    theta = prior_draws("two_i", 12000, seed=0)
+    tail = [i for i in range(len(theta)) if hh.solve(lib, "dopri5", theta[i], slots, tab.y0, TOL, TOL, max_steps=512)[1] != 0]
+    assert 60 < len(tail) < 400                                  # ~1.2 % of the draws
+    steps = np.array([hh.solve(lib, "bdf", theta[i], slots, tab.y0, TOL, TOL)[2] for i in tail])
+    assert steps.max() < 1000 and np.median(steps) < 600
+    worst = [tail[k] for k in np.argsort(steps)[-6:]]
+    for i in worst:
+        _, info = odeint(orc.two_i, list(tab.y0), slots, args=(list(theta[i]),), full_output=True, mxstep=500000)
+        mine = hh.solve(lib, "bdf", theta[i], slots, tab.y0, TOL, TOL)[2]
+        assert mine < 1.25 * info["nst"][-1] + 50, (i, mine, info["nst"][-1])
+
+
 def test_step_budget_and_nonfinite_inputs_end_in_status_words(two_i):
     lib, tab, slots = two_i
     th = golden("two_i")["theta"][0]
