@@ -123,32 +123,80 @@ def cpu_sweep_rate(theta, cores, pool=None):
     return len(theta) / dt, dt
 
 
+def reference_model():
+    """The UNMODIFIED reference's ModelFramework for the demo two_i model (oracle/_ref), or None when the install is absent."""
+    from oracle import ref_runner
+    if not ref_runner.available():
+        return None, ref_runner
+    return ref_runner.demo_model(MODEL, os.path.join(ROOT, "tests", "golden", "demodata.csv")), ref_runner
+
+
+def cpu_reference_sweep(n, cores, repeats=1, warmup=0):
+    """solves/s of the reference's own `fit_survey(samples=n, cpu_cores=cores)` (Framework.py:800-816): LHS of the two_i
+    priors, multiprocessing.Pool fan-out of `_Fit_worker`, frame concat -- stock code path, pool start-up included, as a
+    user of the reference pays it.  -> (rate, seconds per call) or None without oracle/_ref."""
+    model, rr = reference_model()
+    if model is None:
+        return None
+    for k in range(warmup):
+        rr.time_fit_survey(model, n, cores, seed=100 + k)
+    total = 0.0
+    for k in range(repeats):
+        total += rr.time_fit_survey(model, n, cores, seed=k)[1]
+    return n * repeats / total, total / repeats
+
+
+def cpu_reference_chains(cores):
+    """CPU chain-steps/s of the reference's sampler: `Samplers.MetropolisHastings` 1 chain x
+    1000 iterations on one core, and `ModelFramework.MCMC(32 chains x 1000, cpu_cores=all)` from explicit starts."""
+    from oracle import ref_runner as rr
+    if not rr.available():
+        return None
+    names = [p[0] for p in rr.PRIORS[MODEL]]
+    model = rr.demo_model(MODEL, os.path.join(ROOT, "tests", "golden", "demodata.csv"), init=CENTER[MODEL])
+    r1, t1, f1 = rr.time_single_chain(model, 1000, seed=0)
+    rng = np.random.default_rng(1)
+    starts = [dict(zip(names, np.array(CENTER[MODEL]) * np.exp(0.05 * rng.standard_normal(len(names))))) for _ in range(32)]
+    r32, t32, f32 = rr.time_mcmc(model, starts, 1000, cores)
+    return {"kind": "reference", "cores": cores,
+            "single_chain": {"chain_steps_per_s": r1, "seconds": t1, "iterations": 1000, "cores": 1,
+                             "api": "ODElib.Statistics.Samplers.MetropolisHastings(model, nits=1000)"},
+            "mcmc_32x1000": {"chain_steps_per_s": r32, "seconds": t32, "chains": 32, "iterations": 1000, "cores": cores,
+                             "rows": int(len(f32)),
+                             "api": "ODElib.ModelFramework.MCMC(chain_inits=[32 dicts], iterations_per_chain=1000, cpu_cores=all)"}}
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm for the path, all host cores, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path -- `ModelFramework.fit_survey` of the
+    unmodified package (oracle/_ref) with all host cores -- on a bounded sample of the workload per step; the oracle
+    port (scipy odeint + masked chi, bare) is timed beside it as a second figure."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    n = cores * 2000
+    n = cores * 1500
+    ref = cpu_reference_sweep(n, cores, repeats=args.steps, warmup=min(args.warmup, 2))
     theta = prior_draws(n, 0)
     pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
     pool.map(_cpu_chunk, [theta[:2]] * cores)
-    for _ in range(args.warmup):
-        cpu_sweep_rate(theta, cores, pool)
-    total = 0.0
-    for _ in range(args.steps):
-        _, dt = cpu_sweep_rate(theta, cores, pool)
-        total += dt
+    port_rate, port_dt = cpu_sweep_rate(theta, cores, pool)
     pool.close(); pool.join()
-    value = n * args.steps / total
-    sample = f"{n} of the 1,048,576-set sweep's prior draws per step (seed 0), scipy odeint + masked chi, {cores} processes"
+    port = {"value": port_rate, "unit": "solves/s", "cores": cores, "kind": "port",
+            "sample": f"{n} prior draws, scipy odeint + numpy masked chi in {cores} forked processes (no frame, no pool start-up)"}
+    if ref is not None:
+        value, per_step = ref
+        kind = "reference"
+        sample = (f"ODElib.ModelFramework.fit_survey(samples={n}, cpu_cores={cores}) of the unmodified reference (oracle/_ref): "
+                  f"LHS of the two_i priors + Pool fan-out of _Fit_worker + concat, {per_step:.1f} s per step")
+    else:
+        value, per_step, kind, sample = port_rate, port_dt, "port", port["sample"]
     print(json.dumps({
         "impl": "reference", "metric": "ode_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": kind, "sample": sample, "port": port},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -368,16 +416,26 @@ def run_ours(args):
 
     launches = _capi.lib().odl_launch_count() - launches0
 
-    # ---- CPU baseline (rank 0, N=1 only): the reference's algorithm on the host cores ---------------
+    # ---- CPU baseline (rank 0, N=1 only): the reference itself on the host cores, the bare port beside it ----------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         ncpu = min(cores * 4000, n)
         rate, dt = cpu_sweep_rate(theta_host.numpy()[:ncpu], cores)
-        # cross-check while we are here: GPU chi vs oracle chi on healthy rows
-        cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
-               "sample": f"first {ncpu} parameter sets of the same sweep, scipy odeint (LSODA, default tol) + numpy "
-                         f"masked chi in {cores} forked processes, {dt:.1f} s"}
+        port = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
+                "sample": f"first {ncpu} parameter sets of the same sweep, scipy odeint (LSODA, default tol) + numpy "
+                          f"masked chi in {cores} forked processes, {dt:.1f} s"}
+        nref = cores * 1500
+        ref = cpu_reference_sweep(nref, cores, repeats=2, warmup=1)
+        if ref is not None:
+            cpu = {"value": ref[0], "unit": "solves/s", "cores": cores, "kind": "reference",
+                   "sample": f"ODElib.ModelFramework.fit_survey(samples={nref}, cpu_cores={cores}) of the unmodified reference "
+                             f"(oracle/_ref, stock code path: LHS of the two_i priors, Pool fan-out of _Fit_worker, concat), "
+                             f"{ref[1]:.1f} s per call", "port": port}
+        else:
+            cpu = port
+        if mcmc is not None:
+            mcmc["cpu_reference"] = cpu_reference_chains(cores)
 
     traffic = ncu_traffic()
     if rank == 0:

@@ -32,7 +32,11 @@
  * device scratch; copies are inside the call) or ODL_MEM_DEVICE (CUDA device pointers, e.g. torch
  * tensor .data_ptr(); nothing is copied).  `stream` is a cudaStream_t (NULL = default stream).
  * Calls are asynchronous only for ODL_MEM_DEVICE; host-memory calls return after their results
- * have landed.  Handles are not thread-safe; use one per host thread / per GPU.
+ * have landed.  Handles are not thread-safe and allow ONE call in flight: the per-model scratch buffers, the
+ * counter block, the events and the helper stream are shared by all calls on a handle, so a second call (from another
+ * host thread, or an ODL_MEM_DEVICE call on another stream) must wait until the previous one's work has completed.
+ * Use one handle per host thread / per GPU.  Every entry point runs on the model's device and restores the calling
+ * thread's current CUDA device before it returns.
  */
 #ifndef ODELIB_B200_H
 #define ODELIB_B200_H
@@ -63,8 +67,11 @@ typedef struct odl_build_opts {
   int block_threads;   /* threads per CTA, 0 = default (128) */
   int min_blocks;      /* __launch_bounds__ min CTAs per SM, 0 = default (4) */
   int dense_output;    /* 1 = dense output at the observation times (default), 0 = land on them */
-  int compile_only;    /* 1 = NVRTC-compile (and cache) but do not touch a GPU */
-  int y0_from_param;   /* 1 = some state's initial value is a parameter ('<state>0', Samplers.py:110-114) */
+  int compile_only;    /* 1 = NVRTC-compile every kernel unit (and cache them) but do not touch a GPU; 2 = the same for
+                          the units of the default paths only */
+  int y0_from_param;   /* 1 = some state's initial value is a parameter ('<state>0', Samplers.py:110-114).  As in the
+                          reference this holds for the solves of MCMC PROPOSALS only: odl_sweep, odl_trajectory and a
+                          chain's a-priori solve start from y0 (istates, Framework.py:647-650; Samplers.py:88) */
   int coop_lanes;      /* n_state > 8: lanes per system of the cooperative kernels (4, 8, 16 or 32);
                           0 = by state count (4 up to 16 states, 8 up to 64, 16 up to 128, else 32) */
   int reserved[1];
@@ -149,7 +156,13 @@ const char* odl_model_build_log(const odl_model* m);
 /* resource usage of a compiled kernel ("sweep", "mcmc", "traj", "sweep_ros23", "mcmc_ros23", "mcmc_auto",
    "sweep_radau5", "mcmc_radau5", "sweep_bdf", "mcmc_bdf", and for n_state > 8 "sweep_coop", "mcmc_coop"):
    registers/thread, local (spill) bytes, resident CTAs per SM */
-int odl_model_kernel_info(const odl_model* m, const char* kernel, int* regs, int* local_bytes, int* max_blocks_per_sm);
+int odl_model_kernel_info(odl_model* m, const char* kernel, int* regs, int* local_bytes, int* max_blocks_per_sm);
+/* Kernels are compiled per unit (one NVRTC program per kernel: "sweep", "traj", "mcmc", "sweep_bdf", "mcmc_bdf",
+   "sweep_ros23", "mcmc_ros23", "mcmc_auto", "sweep_radau5", "mcmc_radau5", "sweep_coop", "mcmc_coop", "order"), in
+   parallel host threads: odl_model_create starts the units of the default paths (ordering, DOPRI5 sweep, BDF stiff pass,
+   trajectories, chains) and returns; a call waits for the units it launches and compiles any other on first use.
+   *seconds = NVRTC time of the unit (cache hits: the file read), -1 when it has not been compiled; never compiles. */
+int odl_model_unit_seconds(const odl_model* m, const char* unit, double* seconds, int* cache_hit_or_null);
 
 int odl_model_set_data(odl_model* m, int n_slot, const double* slot_time, int n_obs, const int* obs_slot,
                        const int* obs_col, const double* ln_obs, const double* log_sigma, double sstot,

@@ -126,7 +126,6 @@ class ModelFramework:
         # `cpu_cores` is to the reference (Framework.py:755-785).  Every rank must then make the same calls.
         self.distributed = bool(kwargs.pop("distributed", False))
         self._dm = None
-        self._dm_stamp = None
         if state_summations:
             (self._summations_index, self._summation_snames, self._sumkeep,
              self._suminds) = self._get_summation_index(state_summations)
@@ -170,7 +169,6 @@ class ModelFramework:
         for org, abundance in self.df[self.df['time'] == 0]['abundance'].items():
             inits.setdefault(org, abundance)
         self.set_inits(**inits)
-        self._dm_stamp = None
 
     def _formatdf(self, df):
         """(organism, time, abundance[, log_sigma | replicate]) -> frame indexed by organism, time-sorted."""
@@ -367,24 +365,36 @@ class ModelFramework:
             return [(i,) for i in range(len(self._snames))]
         return [self._summations_index.get(i, (i,)) for i in self._sumkeep]
 
+    def _tables_stamp(self, y0):
+        """Content key of everything `_device` uploads: output grid, initial states, '<state>0' map, observation rows."""
+        parts = [self.times.tobytes(), y0.tobytes(), self._y0_map().tobytes()]
+        if self.df is not None:
+            for s in self._pred_tindex:
+                parts += [str(s).encode(), self._pred_tindex[s].tobytes(), self._obs_logabundance[s].tobytes(),
+                          self._obs_logsigma[s].tobytes()]
+        return hash(tuple(parts))
+
     def _device(self):
-        """Compile (once) and (re)load tables when data / initial states changed."""
+        """Compile (once) and (re)load tables when data / initial states changed.
+
+        ``copy()`` shares the compiled DeviceModel between instances, so "what is loaded" is recorded on the
+        DeviceModel itself (``_loaded_stamp``) and compared by content: a copy with other initial states or data
+        re-uploads its own tables (a few KB) before it computes, and so does the original after it."""
         if self._dm is None or getattr(self, "_dm_shapes", None) != self._pshapes():
             self._dm_shapes = self._pshapes()                     # the slot layout is part of the compiled model
             self._dm = DeviceModel(self._device_ode(), len(self._snames), len(self._flat_names), self._observe_groups(),
                                    device=self.device, y0_from_param=bool((self._y0_map() >= 0).any()))
-            self._dm_stamp = None
         y0 = np.asarray(self.get_inits(), dtype=np.float64)
-        stamp = (self.times.tobytes(), y0.tobytes(), id(self.df), self._samples)
-        if stamp != self._dm_stamp:
+        stamp = self._tables_stamp(y0)
+        if stamp != getattr(self._dm, "_loaded_stamp", None):
+            self._dm._loaded_stamp = None                         # stays invalid if an upload below raises
             if self.df is not None:
                 out_names = self.get_snames(after_summation=True)
                 cols = [(i, self._pred_tindex[s], self._obs_logabundance[s], self._obs_logsigma[s])
                         for i, s in enumerate(out_names) if s in self._pred_tindex]
-                self._obs_order = [s for s in out_names if s in self._pred_tindex]
                 self._dm.set_data(ObsTables(self.times, cols), y0, self._y0_map())
             self._dm.set_grid(self.times, y0, self._y0_map())
-            self._dm_stamp = stamp
+            self._dm._loaded_stamp = stamp
         return self._dm
 
     # ------------------------------------------------------------------ integrate + score (Framework.py:617-722)
@@ -619,11 +629,12 @@ class ModelFramework:
         ps = self._lhs_samples(samples, **parameter_mapping)[list(self._flat_names)]
         dm = self._device()
         y0 = np.asarray(self.get_inits(), dtype=np.float64)
+        dm._loaded_stamp = None                                   # another grid is loaded for the duration of this call
         dm.set_grid(np.array([self.times[0], self.times[-1]]), y0, self._y0_map())
         try:
             traj, _, _ = dm.trajectory(ps.to_numpy(dtype=np.float64), rtol=self.rtol, atol=self.atol)
         finally:
-            dm.set_grid(self.times, y0, self._y0_map())           # integrate() expects the full grid
+            self._device()                                        # integrate() expects the full grid
         df = pd.DataFrame(traj[:, -1, :], columns=self.get_snames(after_summation=False))
         for p in self._flat_names:
             df[p] = ps[p].to_numpy()
@@ -658,6 +669,7 @@ class ModelFramework:
         no_map = np.full(len(self._snames), -1, np.int32)          # explicit initial states win, as in integrate(inits=)
         y0 = np.asarray(self.get_inits(), dtype=np.float64)
         grid = np.array([self.times[0], self.times[-1]]) if aggregate_enpoints else self.times
+        dm._loaded_stamp = None                                   # another grid is loaded for the duration of this call
         dm.set_grid(grid, y0, no_map)
         try:
             if seed_equilibrium:
@@ -670,7 +682,7 @@ class ModelFramework:
             else:
                 traj = dm.trajectory(theta, y0=init, rtol=self.rtol, atol=self.atol)[0]
         finally:
-            dm.set_grid(self.times, y0, self._y0_map())
+            self._device()
         if print_status:
             print("100.00% Complete")
         if aggregate_enpoints:

@@ -18,7 +18,8 @@ ST_OK, ST_MAXSTEPS, ST_NONFINITE, ST_HUNDERFLOW, ST_STIFF, ST_ALLMASKED = 0, 1, 
 
 EXPORTS = ["odl_abi_version", "odl_last_error", "odl_model_create", "odl_model_destroy", "odl_model_build_log",
            "odl_model_kernel_info", "odl_model_set_data", "odl_model_set_grid", "odl_sweep", "odl_trajectory",
-           "odl_mcmc", "odl_model_last_kernel_ms", "odl_model_last_pass_ms", "odl_launch_count", "odl_fp64_peak", "odl_debug_counters", "odl_select_below", "odl_gather_rows", "odl_sample_lhs", "odl_reference_streams"]
+           "odl_mcmc", "odl_model_last_kernel_ms", "odl_model_last_pass_ms", "odl_launch_count", "odl_fp64_peak", "odl_debug_counters", "odl_select_below", "odl_gather_rows", "odl_sample_lhs", "odl_reference_streams",
+           "odl_model_unit_seconds"]
 
 
 class OdlError(RuntimeError):
@@ -93,6 +94,7 @@ def lib():
     L.odl_reference_streams.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
     L.odl_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
                                   C.c_void_p]
+    L.odl_model_unit_seconds.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.odl_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     if L.odl_abi_version() != 2:
         raise OdlError(EIO, "libodelib_b200.so ABI version mismatch - rebuild")

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <unistd.h>
 #include <cstring>
+#include <future>
 #include <string>
 #include <thread>
 #include <vector>
@@ -124,15 +125,37 @@ struct Tables {
   bool set = false;
 };
 
+// One NVRTC program per kernel ("unit", see ODL_UNIT in odl_kernels.cuh): compiled on demand, in parallel host
+// threads, cached per unit -- a new model is ready as soon as the kernels the first call needs are, instead of after
+// every stepper variant has been compiled (round 1: 19 s for two_i, 35 s for the 35-state network).
+enum { U_SWEEP = 1, U_TRAJ = 2, U_MCMC = 3, U_SWEEP_BDF = 4, U_MCMC_BDF = 5, U_SWEEP_ROS = 6, U_MCMC_ROS = 7, U_MCMC_AUTO = 8,
+       U_SWEEP_RADAU = 9, U_MCMC_RADAU = 10, U_SWEEP_COOP = 11, U_MCMC_COOP = 12, U_ORDER = 13, U_COUNT = 14 };
+static const char* kUnitName[U_COUNT] = {"", "sweep", "traj", "mcmc", "sweep_bdf", "mcmc_bdf", "sweep_ros23", "mcmc_ros23",
+                                         "mcmc_auto", "sweep_radau5", "mcmc_radau5", "sweep_coop", "mcmc_coop", "order"};
+struct Compiled {
+  int rc = 0;
+  std::vector<char> cubin;
+  std::string log, err;
+  double seconds = 0.0;
+  bool cache_hit = false;
+};
+struct Unit {
+  std::future<Compiled> job;     // compile in flight (valid() until collected)
+  Compiled c;
+  bool have = false;             // c holds a cubin
+  CUmodule mod = nullptr;
+};
+
 struct odl_model {
   int device = 0;
   int n_state = 0, n_param = 0, n_out = 0;
   int block = 128, minblocks = 4, dense = 1, y0p = 0, coop = 0;
   int sm_count = 0;
   bool on_gpu = false;
-  std::vector<char> cubin;
+  std::string src, cache_dir;
+  std::vector<std::string> opt;  // NVRTC options common to all units
   std::string log;
-  CUmodule mod = nullptr;
+  Unit units[U_COUNT];
   CUfunction k_sweep = nullptr, k_traj = nullptr, k_mcmc = nullptr;
   CUfunction k_sweep_ros = nullptr, k_mcmc_ros = nullptr, k_mcmc_auto = nullptr;
   CUfunction k_sweep_radau = nullptr, k_mcmc_radau = nullptr;
@@ -146,10 +169,27 @@ struct odl_model {
   cudaEvent_t evp[2] = {nullptr, nullptr};   // between the cohort passes of an AUTO sweep
   cudaEvent_t ev_aux = nullptr, ev_fork = nullptr;
   cudaEvent_t ev_chunk[3] = {nullptr, nullptr, nullptr};   // host-memory sweeps: theta arrives in pieces on the helper stream
-  cudaStream_t aux = nullptr;                // helper stream: the Radau5 pass runs beside the deferred DOPRI5 pass
+  cudaStream_t aux = nullptr;                // helper stream: the stiff pass beside the DOPRI5 pass
   int n_pass = 0;
   bool timed = false;
+  bool coop_model() const { return n_state > 8; }
 };
+
+// The calling thread's current device is the caller's business (torch keeps its own notion of it): every entry point
+// switches to the model's device for its own duration only.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev != device) { err = cudaSetDevice(device); switched = (err == cudaSuccess) && prev >= 0; }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define ODL_ON_DEVICE(m)                                                                                   \
+  DeviceGuard guard_((m)->device);                                                                         \
+  if (guard_.err != cudaSuccess) return fail(ODL_ENODEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(guard_.err))
 
 // cooperative kernels (n > 8): default lanes per system, as odl_kernels.cuh's ODL_G
 static int coop_lanes_default(int n_state) { return n_state <= 16 ? 4 : (n_state <= 64 ? 8 : (n_state <= 128 ? 16 : 32)); }
@@ -160,77 +200,146 @@ static uint64_t fnv1a(const void* data, size_t n, uint64_t h = 14695981039346656
   return h;
 }
 
-static int compile_model(odl_model* m, const std::string& src, const char* cache_dir) {
-  std::vector<std::string> opt = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device",
-                                  "-DODL_BLOCK=" + std::to_string(m->block),
-                                  "-DODL_MINBLOCKS=" + std::to_string(m->minblocks),
-                                  "-DODL_DENSE=" + std::to_string(m->dense), "-DODL_Y0P=" + std::to_string(m->y0p)};
-  if (m->n_state > 8) opt.push_back("-DODL_G=" + std::to_string(m->coop));
-  // tuning hook (development): extra -D options for the kernel source, e.g. ODL_KERNEL_DEFINES="-DODL_INNER=8"
-  if (const char* extra = getenv("ODL_KERNEL_DEFINES")) {
-    std::string e(extra);
-    size_t pos = 0;
-    while (pos < e.size()) {
-      size_t sp = e.find(' ', pos);
-      if (sp == std::string::npos) sp = e.size();
-      if (sp > pos) opt.push_back(e.substr(pos, sp - pos));
-      pos = sp + 1;
-    }
-  }
+static double now_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+// NVRTC -> sm_100a cubin of one unit.  Pure function of its arguments (runs on worker threads; NVRTC programs are
+// independent objects): no access to the model, no thread-local error state.
+static Compiled compile_unit(std::string src, std::vector<std::string> opt, int unit, std::string cache_dir) {
+  Compiled out;
+  const double t0 = now_s();
+  opt.push_back("-DODL_UNIT=" + std::to_string(unit));
   int major = 0, minor = 0;
   nvrtcVersion(&major, &minor);
   std::string keysrc = src + kKernelSrc + kAbiHeaderSrc;
   for (auto& o : opt) keysrc += o;
   keysrc += "nvrtc" + std::to_string(major) + "." + std::to_string(minor);
-  char name[64];
-  snprintf(name, sizeof name, "odl_%016llx.cubin", (unsigned long long)fnv1a(keysrc.data(), keysrc.size()));
+  char name[96];
+  snprintf(name, sizeof name, "odl_%016llx_%s.cubin", (unsigned long long)fnv1a(keysrc.data(), keysrc.size()), kUnitName[unit]);
   std::string path;
-  if (cache_dir && *cache_dir) {
-    path = std::string(cache_dir) + "/" + name;
+  if (!cache_dir.empty()) {
+    path = cache_dir + "/" + name;
     if (FILE* f = fopen(path.c_str(), "rb")) {
       fseek(f, 0, SEEK_END);
       long sz = ftell(f);
       fseek(f, 0, SEEK_SET);
-      m->cubin.resize(sz > 0 ? sz : 0);
-      size_t got = sz > 0 ? fread(m->cubin.data(), 1, sz, f) : 0;
+      out.cubin.resize(sz > 0 ? sz : 0);
+      size_t got = sz > 0 ? fread(out.cubin.data(), 1, sz, f) : 0;
       fclose(f);
-      if (sz > 0 && got == (size_t)sz) { m->log = "cubin cache hit: " + path; return 0; }
-      m->cubin.clear();
+      if (sz > 0 && got == (size_t)sz) {
+        out.log = std::string(kUnitName[unit]) + ": cubin cache hit: " + path;
+        out.cache_hit = true;
+        out.seconds = now_s() - t0;
+        return out;
+      }
+      out.cubin.clear();
     }
   }
   nvrtcProgram prog;
   const char* hdr_src[2] = {kKernelSrc, kAbiHeaderSrc};
   const char* hdr_name[2] = {"odl_kernels.cuh", "odl_abi.h"};
   std::string full = src + "\n#include \"odl_kernels.cuh\"\n";
-  if (nvrtcCreateProgram(&prog, full.c_str(), "odl_model.cu", 2, hdr_src, hdr_name) != NVRTC_SUCCESS)
-    return fail(ODL_ECOMPILE, "nvrtcCreateProgram failed");
+  if (nvrtcCreateProgram(&prog, full.c_str(), "odl_model.cu", 2, hdr_src, hdr_name) != NVRTC_SUCCESS) {
+    out.rc = ODL_ECOMPILE; out.err = "nvrtcCreateProgram failed";
+    return out;
+  }
   std::vector<const char*> copt;
   for (auto& o : opt) copt.push_back(o.c_str());
   nvrtcResult r = nvrtcCompileProgram(prog, (int)copt.size(), copt.data());
   size_t logsz = 0;
   nvrtcGetProgramLogSize(prog, &logsz);
-  m->log.assign(logsz, '\0');
-  if (logsz) nvrtcGetProgramLog(prog, &m->log[0]);
+  std::string log(logsz, '\0');
+  if (logsz) nvrtcGetProgramLog(prog, &log[0]);
+  while (!log.empty() && (log.back() == '\0' || log.back() == '\n')) log.pop_back();
   if (r != NVRTC_SUCCESS) {
     nvrtcDestroyProgram(&prog);
-    return fail(ODL_ECOMPILE, std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + m->log);
+    out.rc = ODL_ECOMPILE;
+    out.err = std::string("NVRTC (") + kUnitName[unit] + "): " + nvrtcGetErrorString(r) + "\n" + log;
+    return out;
   }
   size_t sz = 0;
   if (nvrtcGetCUBINSize(prog, &sz) != NVRTC_SUCCESS || sz == 0) {
     nvrtcDestroyProgram(&prog);
-    return fail(ODL_ECOMPILE, "NVRTC produced no cubin");
+    out.rc = ODL_ECOMPILE; out.err = "NVRTC produced no cubin";
+    return out;
   }
-  m->cubin.resize(sz);
-  nvrtcGetCUBIN(prog, m->cubin.data());
+  out.cubin.resize(sz);
+  nvrtcGetCUBIN(prog, out.cubin.data());
   nvrtcDestroyProgram(&prog);
   if (!path.empty()) {
-    std::string tmp = path + ".tmp." + std::to_string((long long)getpid());   // one writer per file: ranks compile the same model
+    std::string tmp = path + ".tmp." + std::to_string((long long)getpid()) + "." + std::to_string(unit);   // one writer per file
     if (FILE* f = fopen(tmp.c_str(), "wb")) {
-      fwrite(m->cubin.data(), 1, sz, f);
+      fwrite(out.cubin.data(), 1, sz, f);
       fclose(f);
       rename(tmp.c_str(), path.c_str());
     }
   }
+  out.seconds = now_s() - t0;
+  char head[96];
+  snprintf(head, sizeof head, "%s: compiled in %.2f s", kUnitName[unit], out.seconds);
+  out.log = head + (log.empty() ? std::string() : "\n" + log);
+  return out;
+}
+
+static bool unit_applies(const odl_model* m, int unit) {
+  if (unit == U_SWEEP_COOP || unit == U_MCMC_COOP) return m->coop_model();
+  return unit >= 1 && unit < U_COUNT;
+}
+// start compiling a unit on a worker thread (no-op when it is compiled, compiling or loaded already)
+static void unit_start(odl_model* m, int unit) {
+  Unit& u = m->units[unit];
+  if (u.have || u.job.valid() || !unit_applies(m, unit)) return;
+  u.job = std::async(std::launch::async, compile_unit, m->src, m->opt, unit, m->cache_dir);
+}
+// wait for / run the compile of a unit
+static int unit_compiled(odl_model* m, int unit) {
+  Unit& u = m->units[unit];
+  if (u.have) return 0;
+  if (!unit_applies(m, unit)) return fail(ODL_EINVAL, std::string("kernel unit '") + kUnitName[unit] + "' does not exist for this model");
+  if (!u.job.valid()) unit_start(m, unit);
+  u.c = u.job.get();
+  if (u.c.rc) return fail(u.c.rc, u.c.err);
+  u.have = true;
+  m->log += (m->log.empty() ? "" : "\n") + u.c.log;
+  return 0;
+}
+static std::string cu_err(CUresult r);
+static int load_driver();
+struct KernelSlot { const char* name; CUfunction odl_model::*fn; int unit; };
+static const KernelSlot kKernels[] = {
+    {"odl_sweep_kernel", &odl_model::k_sweep, U_SWEEP}, {"odl_traj_kernel", &odl_model::k_traj, U_TRAJ},
+    {"odl_mcmc_kernel", &odl_model::k_mcmc, U_MCMC}, {"odl_sweep_ros23_kernel", &odl_model::k_sweep_ros, U_SWEEP_ROS},
+    {"odl_mcmc_ros23_kernel", &odl_model::k_mcmc_ros, U_MCMC_ROS}, {"odl_mcmc_auto_kernel", &odl_model::k_mcmc_auto, U_MCMC_AUTO},
+    {"odl_sweep_radau5_kernel", &odl_model::k_sweep_radau, U_SWEEP_RADAU},
+    {"odl_mcmc_radau5_kernel", &odl_model::k_mcmc_radau, U_MCMC_RADAU}, {"odl_sweep_bdf_kernel", &odl_model::k_sweep_bdf, U_SWEEP_BDF},
+    {"odl_mcmc_bdf_kernel", &odl_model::k_mcmc_bdf, U_MCMC_BDF}, {"odl_order_key_kernel", &odl_model::k_order_key, U_ORDER},
+    {"odl_order_scan_kernel", &odl_model::k_order_scan, U_ORDER}, {"odl_order_scatter_kernel", &odl_model::k_order_scatter, U_ORDER},
+    {"odl_sweep_coop_kernel", &odl_model::k_sweep_coop, U_SWEEP_COOP}, {"odl_mcmc_coop_kernel", &odl_model::k_mcmc_coop, U_MCMC_COOP}};
+
+// compiled + loaded on the model's device + its CUfunctions fetched
+static int unit_ready(odl_model* m, int unit) {
+  Unit& u = m->units[unit];
+  if (u.mod) return 0;
+  if (!m->on_gpu) return fail(ODL_ENODEVICE, "model was created compile_only / without a GPU");
+  int rc = unit_compiled(m, unit);
+  if (rc) return rc;
+  CUresult r = g_drv.ModuleLoadData(&u.mod, u.c.cubin.data());
+  if (r != CUDA_SUCCESS) { u.mod = nullptr; return fail(ODL_ECUDA, "cuModuleLoadData: " + cu_err(r)); }
+  for (const KernelSlot& k : kKernels) {
+    if (k.unit != unit) continue;
+    CUfunction f = nullptr;
+    r = g_drv.ModuleGetFunction(&f, u.mod, k.name);
+    if (r != CUDA_SUCCESS) return fail(ODL_ECUDA, std::string("cuModuleGetFunction(") + k.name + "): " + cu_err(r));
+    m->*(k.fn) = f;
+  }
+  return 0;
+}
+static int units_ready(odl_model* m, std::initializer_list<int> units) {
+  for (int u : units) unit_start(m, u);          // all of them compile side by side ...
+  for (int u : units) { int rc = unit_ready(m, u); if (rc) return rc; }
   return 0;
 }
 
@@ -247,8 +356,7 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
   odl_model* m = new odl_model();
   m->n_state = n_state; m->n_param = n_param; m->n_out = n_out;
   int device = -1;
-  bool compile_only = false;
-  const char* cache_dir = nullptr;
+  int compile_only = 0;
   if (opts) {
     device = opts->device;
     if (opts->block_threads > 0) m->block = opts->block_threads;
@@ -256,41 +364,66 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
     m->dense = opts->dense_output ? 1 : 0;
     m->y0p = opts->y0_from_param ? 1 : 0;
     m->coop = opts->coop_lanes;
-    compile_only = opts->compile_only != 0;
-    cache_dir = opts->cache_dir;
+    compile_only = opts->compile_only;
+    if (opts->cache_dir) m->cache_dir = opts->cache_dir;
   }
   if (m->block % 32 || m->block > 1024) { delete m; return fail(ODL_EINVAL, "block_threads must be a multiple of 32, <= 1024"); }
   if (m->coop == 0) m->coop = coop_lanes_default(n_state);
   if (m->coop != 4 && m->coop != 8 && m->coop != 16 && m->coop != 32) { delete m; return fail(ODL_EINVAL, "coop_lanes must be 4, 8, 16 or 32"); }
-  int rc = compile_model(m, model_cuda_src, cache_dir);
-  if (rc) { delete m; return rc; }
-  if (compile_only) { *out = m; return 0; }
+  m->src = model_cuda_src;
+  m->opt = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device",
+            "-DODL_BLOCK=" + std::to_string(m->block), "-DODL_MINBLOCKS=" + std::to_string(m->minblocks),
+            "-DODL_DENSE=" + std::to_string(m->dense), "-DODL_Y0P=" + std::to_string(m->y0p)};
+  if (m->n_state > 8) m->opt.push_back("-DODL_G=" + std::to_string(m->coop));
+  // tuning hook (development): extra -D options for the kernel source, e.g. ODL_KERNEL_DEFINES="-DODL_INNER=8"
+  if (const char* extra = getenv("ODL_KERNEL_DEFINES")) {
+    std::string e(extra);
+    size_t pos = 0;
+    while (pos < e.size()) {
+      size_t sp = e.find(' ', pos);
+      if (sp == std::string::npos) sp = e.size();
+      if (sp > pos) m->opt.push_back(e.substr(pos, sp - pos));
+      pos = sp + 1;
+    }
+  }
+  // The kernels the default paths use start compiling now, side by side on worker threads: forward sweep
+  // (ordering + DOPRI5 + the BDF stiff pass), trajectories, chains.  The other steppers (ROS23, Radau5, the per-proposal
+  // DOPRI5->ROS23 kernel, the BDF chain kernel) compile when a call first asks for them.  compile_only = 1: every unit,
+  // waited for (fills the cubin cache, reports any compile error); compile_only = 2: the default set only.
+  const bool coop = m->coop_model();
+  std::vector<int> first = {U_ORDER, U_SWEEP_BDF, U_TRAJ, coop ? U_SWEEP_COOP : U_SWEEP, coop ? U_MCMC_COOP : U_MCMC};
+  if (compile_only == 1) {
+    first.clear();
+    for (int u = 1; u < U_COUNT; ++u) if (unit_applies(m, u)) first.push_back(u);
+  }
+  if (compile_only) {
+    // bounded parallelism on the build box: as many programs at once as there are cores
+    size_t par = std::max(1u, std::thread::hardware_concurrency());
+    for (size_t i = 0; i < first.size(); i += par) {
+      for (size_t j = i; j < std::min(first.size(), i + par); ++j) unit_start(m, first[j]);
+      for (size_t j = i; j < std::min(first.size(), i + par); ++j) {
+        int rc = unit_compiled(m, first[j]);
+        if (rc) { odl_model_destroy(m); return rc; }
+      }
+    }
+    *out = m;
+    return 0;
+  }
+  for (int u : first) unit_start(m, u);
   // ---- GPU side ----
   auto bail = [&](int code) { odl_model_destroy(m); return code; };
+  int prev_device = -1;
+  if (cudaGetDevice(&prev_device) != cudaSuccess) { cudaGetLastError(); prev_device = -1; }
   if (device >= 0) { cudaError_t e = cudaSetDevice(device); if (e != cudaSuccess) return bail(fail(ODL_ENODEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e))); }
   { cudaError_t e = cudaFree(0); if (e != cudaSuccess) return bail(fail(ODL_ENODEVICE, std::string("no usable CUDA device: ") + cudaGetErrorString(e))); }
   if (cudaGetDevice(&m->device) != cudaSuccess) return bail(fail(ODL_ENODEVICE, "cudaGetDevice failed"));
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_device};
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, m->device) != cudaSuccess) return bail(fail(ODL_ECUDA, "cudaGetDeviceProperties failed"));
   if (prop.major != 10) return bail(fail(ODL_ENODEVICE, std::string("device '") + prop.name + "' is not sm_100 (Blackwell B200); this library has no other code path"));
   m->sm_count = prop.multiProcessorCount;
+  int rc;
   if ((rc = load_driver())) return bail(rc);
-  { CUresult r = g_drv.ModuleLoadData(&m->mod, m->cubin.data()); if (r != CUDA_SUCCESS) return bail(fail(ODL_ECUDA, "cuModuleLoadData: " + cu_err(r))); }
-  struct { const char* name; CUfunction* fn; bool required; } ks[] = {
-      {"odl_sweep_kernel", &m->k_sweep, true}, {"odl_traj_kernel", &m->k_traj, true}, {"odl_mcmc_kernel", &m->k_mcmc, true},
-      {"odl_sweep_ros23_kernel", &m->k_sweep_ros, true}, {"odl_mcmc_ros23_kernel", &m->k_mcmc_ros, true},
-      {"odl_mcmc_auto_kernel", &m->k_mcmc_auto, true}, {"odl_sweep_radau5_kernel", &m->k_sweep_radau, true},
-      {"odl_mcmc_radau5_kernel", &m->k_mcmc_radau, true}, {"odl_sweep_bdf_kernel", &m->k_sweep_bdf, true},
-      {"odl_mcmc_bdf_kernel", &m->k_mcmc_bdf, true}, {"odl_order_key_kernel", &m->k_order_key, true},
-      {"odl_order_scan_kernel", &m->k_order_scan, true}, {"odl_order_scatter_kernel", &m->k_order_scatter, true},
-      {"odl_sweep_coop_kernel", &m->k_sweep_coop, m->n_state > 8}, {"odl_mcmc_coop_kernel", &m->k_mcmc_coop, m->n_state > 8}};
-  for (auto& k : ks) {
-    CUresult r = g_drv.ModuleGetFunction(k.fn, m->mod, k.name);
-    if (r != CUDA_SUCCESS) {
-      *k.fn = nullptr;
-      if (k.required) return bail(fail(ODL_ECUDA, std::string("cuModuleGetFunction(") + k.name + "): " + cu_err(r)));
-    }
-  }
   if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess ||
       cudaEventCreate(&m->evp[0]) != cudaSuccess || cudaEventCreate(&m->evp[1]) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_aux, cudaEventDisableTiming) != cudaSuccess ||
@@ -308,9 +441,12 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
 
 extern "C" int odl_model_destroy(odl_model* m) {
   if (!m) return 0;
-  if (m->on_gpu || m->mod) {
+  for (Unit& u : m->units) if (u.job.valid()) u.job.wait();          // worker threads hold copies of their inputs only
+  int prev = -1;
+  if (m->on_gpu) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
     cudaSetDevice(m->device);
-    if (m->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(m->mod);
+    for (Unit& u : m->units) if (u.mod && g_drv.ModuleUnload) g_drv.ModuleUnload(u.mod);
   }
   m->data.buf.release(); m->grid.buf.release(); m->counter.release();
   for (auto& s : m->scratch) s.release();
@@ -321,27 +457,44 @@ extern "C" int odl_model_destroy(odl_model* m) {
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   for (auto& e : m->ev_chunk) if (e) cudaEventDestroy(e);
   if (m->aux) cudaStreamDestroy(m->aux);
+  if (m->on_gpu && prev >= 0 && prev != m->device) cudaSetDevice(prev);
   delete m;
   return 0;
 }
 
 extern "C" const char* odl_model_build_log(const odl_model* m) { return m ? m->log.c_str() : ""; }
 
-static CUfunction kernel_by_name(const odl_model* m, const char* k) {
-  if (!k) return nullptr;
-  if (!strcmp(k, "sweep")) return m->k_sweep;
-  if (!strcmp(k, "mcmc")) return m->k_mcmc;
-  if (!strcmp(k, "traj")) return m->k_traj;
-  if (!strcmp(k, "sweep_ros23")) return m->k_sweep_ros;
-  if (!strcmp(k, "mcmc_ros23")) return m->k_mcmc_ros;
-  if (!strcmp(k, "mcmc_auto")) return m->k_mcmc_auto;
-  if (!strcmp(k, "sweep_radau5")) return m->k_sweep_radau;
-  if (!strcmp(k, "mcmc_radau5")) return m->k_mcmc_radau;
-  if (!strcmp(k, "sweep_coop")) return m->k_sweep_coop;
-  if (!strcmp(k, "mcmc_coop")) return m->k_mcmc_coop;
-  if (!strcmp(k, "sweep_bdf")) return m->k_sweep_bdf;
-  if (!strcmp(k, "mcmc_bdf")) return m->k_mcmc_bdf;
-  return nullptr;
+// seconds NVRTC spent on a unit (0 = cache hit), -1 = not compiled (yet); the unit is NOT compiled by asking
+extern "C" int odl_model_unit_seconds(const odl_model* m, const char* unit, double* seconds, int* cache_hit) {
+  if (!m || !unit || !seconds) return fail(ODL_EINVAL, "odl_model_unit_seconds: null argument");
+  for (int u = 1; u < U_COUNT; ++u)
+    if (!strcmp(unit, kUnitName[u])) {
+      *seconds = m->units[u].have ? m->units[u].c.seconds : -1.0;
+      if (cache_hit) *cache_hit = m->units[u].have && m->units[u].c.cache_hit;
+      return 0;
+    }
+  return fail(ODL_EINVAL, "odl_model_unit_seconds: unknown unit");
+}
+
+// the unit's kernel, compiled and loaded on demand
+static int kernel_by_name(odl_model* m, const char* k, CUfunction* f) {
+  struct { const char* name; CUfunction odl_model::*fn; int unit; } tab[] = {
+      {"sweep", &odl_model::k_sweep, U_SWEEP}, {"mcmc", &odl_model::k_mcmc, U_MCMC}, {"traj", &odl_model::k_traj, U_TRAJ},
+      {"sweep_ros23", &odl_model::k_sweep_ros, U_SWEEP_ROS}, {"mcmc_ros23", &odl_model::k_mcmc_ros, U_MCMC_ROS},
+      {"mcmc_auto", &odl_model::k_mcmc_auto, U_MCMC_AUTO}, {"sweep_radau5", &odl_model::k_sweep_radau, U_SWEEP_RADAU},
+      {"mcmc_radau5", &odl_model::k_mcmc_radau, U_MCMC_RADAU}, {"sweep_coop", &odl_model::k_sweep_coop, U_SWEEP_COOP},
+      {"mcmc_coop", &odl_model::k_mcmc_coop, U_MCMC_COOP}, {"sweep_bdf", &odl_model::k_sweep_bdf, U_SWEEP_BDF},
+      {"mcmc_bdf", &odl_model::k_mcmc_bdf, U_MCMC_BDF}, {"order_key", &odl_model::k_order_key, U_ORDER},
+      {"order_scatter", &odl_model::k_order_scatter, U_ORDER}};
+  if (!k) return fail(ODL_EINVAL, "null kernel name");
+  for (auto& t : tab)
+    if (!strcmp(k, t.name)) {
+      int rc = unit_ready(m, t.unit);
+      if (rc) return rc;
+      *f = m->*(t.fn);
+      return 0;
+    }
+  return fail(ODL_EINVAL, "unknown kernel");
 }
 
 static size_t smem_bytes(const OdlData& d, int block);
@@ -364,17 +517,22 @@ static size_t smem_bytes(const OdlData& d, int block) {
   return doubles * sizeof(double);
 }
 
-extern "C" int odl_model_kernel_info(const odl_model* m, const char* kernel, int* regs, int* local_bytes,
+extern "C" int odl_model_kernel_info(odl_model* m, const char* kernel, int* regs, int* local_bytes,
                                      int* max_blocks_per_sm) {
   if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_model_kernel_info: model is not loaded on a GPU");
-  CUfunction f = kernel_by_name(m, kernel);
-  if (!f) return fail(ODL_EINVAL, "odl_model_kernel_info: unknown kernel");
+  ODL_ON_DEVICE(m);
+  CUfunction f = nullptr;
+  int rc = kernel_by_name(m, kernel, &f);
+  if (rc) return rc;
   int r = 0, l = 0, b = 0;
   ODL_CU(g_drv.FuncGetAttribute(&r, CU_FUNC_ATTRIBUTE_NUM_REGS, f));
   ODL_CU(g_drv.FuncGetAttribute(&l, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f));
-  size_t sm = m->data.set ? smem_bytes(m->data.d, m->block) : 0;
+  const bool warp_cta = f == m->k_sweep_bdf || f == m->k_mcmc_bdf || f == m->k_sweep_radau || f == m->k_mcmc_radau;
+  const bool coop = f == m->k_sweep_coop || f == m->k_mcmc_coop;
+  const int block = coop ? (int)kCoopBlock : (warp_cta ? 32 : m->block);
+  size_t sm = !m->data.set ? 0 : (coop ? coop_smem_bytes(m, m->data.d) : smem_bytes(m->data.d, block));
   g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max<size_t>(sm, 1024));
-  ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&b, f, m->block, sm));
+  ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&b, f, block, sm));
   if (regs) *regs = r;
   if (local_bytes) *local_bytes = l;
   if (max_blocks_per_sm) *max_blocks_per_sm = b;
@@ -392,7 +550,7 @@ static int upload_tables(odl_model* m, Tables& T, int n_slot, const double* slot
   for (int i = 1; i < n_slot; ++i)
     if (!(slot_time[i] > slot_time[i - 1])) return fail(ODL_EINVAL, "output times must be strictly ascending");
   if (!(slot_time[0] >= t0)) return fail(ODL_EINVAL, "first output time precedes t0");
-  ODL_CUDA(cudaSetDevice(m->device));
+  ODL_ON_DEVICE(m);
   const int N = m->n_state;
   // layout: slot_t[K] lnO[n_obs] denom[n_obs] lin[n_obs] y0[N] | src[n_obs] y0p[N]
   size_t nd = (size_t)n_slot + 3 * (size_t)n_obs + N;
@@ -528,16 +686,28 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   const int tail_solver = so && so->tail_solver > 0 ? so->tail_solver : ODL_SOLVER_BDF;
   if (tail_solver != ODL_SOLVER_BDF && tail_solver != ODL_SOLVER_RADAU5)
     return fail(ODL_EINVAL, "odl_sweep: tail_solver must be ODL_SOLVER_BDF or ODL_SOLVER_RADAU5");
-  ODL_CUDA(cudaSetDevice(m->device));
+  ODL_ON_DEVICE(m);
+  int rc;
+  {
+    // the kernels this call launches (compiled side by side if they are not yet)
+    const bool coop = m->coop_model();
+    const int tail_unit = tail_solver == ODL_SOLVER_RADAU5 ? U_SWEEP_RADAU : U_SWEEP_BDF;
+    const bool coop_plain = coop && !(so && (so->stiff_check || so->early_check_steps > 0));
+    if (solver == ODL_SOLVER_AUTO) rc = coop ? units_ready(m, {U_ORDER, U_SWEEP_COOP, tail_unit}) : units_ready(m, {U_ORDER, U_SWEEP, tail_unit});
+    else if (solver == ODL_SOLVER_DOPRI5) rc = units_ready(m, {coop_plain ? U_SWEEP_COOP : U_SWEEP});
+    else rc = units_ready(m, {solver == ODL_SOLVER_ROS23 ? U_SWEEP_ROS : (solver == ODL_SOLVER_RADAU5 ? U_SWEEP_RADAU : U_SWEEP_BDF)});
+    if (rc) return rc;
+  }
+  if (solver == ODL_SOLVER_AUTO && n > 2147483647LL)
+    return fail(ODL_EINVAL, "odl_sweep: ODL_SOLVER_AUTO orders rows through 32-bit indices; split tables beyond 2^31-1 rows");
   cudaStream_t s = (cudaStream_t)stream;
   Staging st{m, s, 0, mem};
   OdlSweepArgs A{};
-  int rc;
   // Host-memory ODL_SOLVER_AUTO sweep of a large table: theta travels in two pieces on the helper stream and the second
   // piece arrives while the first is being ordered and integrated (each piece is ordered and swept on its own; the
   // stiff pass runs once over what both leave).  Rows are independent, so the pieces change nothing in the results.
   const int auto_flags = so ? so->auto_flags : 0;
-  const bool chunked = mem == ODL_MEM_HOST && solver == ODL_SOLVER_AUTO && n >= (1 << 18) && !m->k_sweep_coop &&
+  const bool chunked = mem == ODL_MEM_HOST && solver == ODL_SOLVER_AUTO && n >= (1 << 18) && !m->coop_model() &&
                        !(auto_flags & (ODL_AUTO_UNORDERED | ODL_AUTO_CONCURRENT | ODL_AUTO_ONE_PIECE));
   if (chunked) {
     DevBuf& bt = m->scratch[st.next++];
@@ -591,7 +761,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     const bool warp_cta = solver == ODL_SOLVER_RADAU5 || solver == ODL_SOLVER_BDF;   // compiled for one warp per CTA
     CUfunction f1 = solver == ODL_SOLVER_ROS23 ? m->k_sweep_ros : (solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau :
                     (solver == ODL_SOLVER_BDF ? m->k_sweep_bdf : m->k_sweep));
-    if (solver == ODL_SOLVER_DOPRI5 && m->k_sweep_coop && !O.stiff_check && O.early_check_steps == 0) {
+    if (solver == ODL_SOLVER_DOPRI5 && m->coop_model() && !O.stiff_check && O.early_check_steps == 0) {
       if ((rc = go_coop(s, O, A, n))) return rc;               // n > 8: several lanes per system
     } else if ((rc = go(s, f1, O, A, warp_cta ? 32u : pick_block(D, m->block), n))) return rc;
   } else {
@@ -621,7 +791,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     int* feed = static_cast<int*>(bfeed.p);
     const int flags = so ? so->auto_flags : 0;
     const bool ordered = !(flags & ODL_AUTO_UNORDERED);
-    const bool concurrent = (flags & ODL_AUTO_CONCURRENT) != 0 && !m->k_sweep_coop;
+    const bool concurrent = (flags & ODL_AUTO_CONCURRENT) != 0 && !m->coop_model();
     const int cap0 = so && so->pass_cap0 > 0 ? so->pass_cap0 : 512;
     CUfunction k_tail = tail_solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau : m->k_sweep_bdf;
     // counter block (zeroed above): [0] bulk work counter, [64] feed count, [128] feed ticket, [192] warps entered,
@@ -662,16 +832,17 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     ODL_CUDA(cudaEventRecord(m->evp[1], s));
     const unsigned block0 = pick_block(D, m->block);
     const size_t smem0 = smem_bytes(D, (int)block0), smem_t = smem_bytes(D, 32);
-    if (smem0 > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(m->k_sweep, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem0));
+    const bool coop_bulk = m->coop_model();                      // n > 8: the bulk pass is the cooperative kernel (go_coop)
+    if (!coop_bulk && smem0 > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(m->k_sweep, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem0));
     if (smem_t > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(k_tail, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem_t));
     // both kernels must ask for the same L1/shared split, or no SM can hold CTAs of both at once (the second kernel
     // would wait for the first to drain: measured -- the bulk pass started only after the consumers had given up)
-    ODL_CU(g_drv.FuncSetAttribute(m->k_sweep, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100));
+    if (!coop_bulk) ODL_CU(g_drv.FuncSetAttribute(m->k_sweep, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100));
     ODL_CU(g_drv.FuncSetAttribute(k_tail, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100));
-    int per_sm0 = 0, per_sm_t = 0, regs0 = 0, regs_t = 0;
-    ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, m->k_sweep, (int)block0, smem0));
+    int per_sm0 = 1, per_sm_t = 0, regs0 = 0, regs_t = 0;
+    if (!coop_bulk) ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, m->k_sweep, (int)block0, smem0));
     ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, k_tail, 32, smem_t));
-    ODL_CU(g_drv.FuncGetAttribute(&regs0, CU_FUNC_ATTRIBUTE_NUM_REGS, m->k_sweep));
+    if (!coop_bulk) ODL_CU(g_drv.FuncGetAttribute(&regs0, CU_FUNC_ATTRIBUTE_NUM_REGS, m->k_sweep));
     ODL_CU(g_drv.FuncGetAttribute(&regs_t, CU_FUNC_ATTRIBUTE_NUM_REGS, k_tail));
     if (per_sm0 < 1 || per_sm_t < 1) return fail(ODL_ECUDA, "sweep kernel does not fit on an SM (shared memory / registers)");
     int tail_warps = so && so->tail_warps > 0 ? so->tail_warps : 2;
@@ -723,7 +894,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       ODL_CUDA(cudaEventRecord(m->evp[0], s));
       ODL_CUDA(cudaStreamWaitEvent(s, m->ev_aux, 0));
     } else {
-      if (m->k_sweep_coop) { if ((rc = go_coop(s, O0, A0, n))) return rc; }      // n > 8: several lanes per system
+      if (coop_bulk) { if ((rc = go_coop(s, O0, A0, n))) return rc; }            // n > 8: several lanes per system
       else if (!chunked) { if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc; }
       else {
         const OdlSweepArgs Aall = A0;
@@ -762,11 +933,12 @@ extern "C" int odl_trajectory(odl_model* m, const odl_solver_opts* so, long long
   if (!m->grid.set) return fail(ODL_EINVAL, "odl_trajectory: call odl_model_set_grid first");
   if (n < 0 || (n > 0 && (!theta || !traj || !status || !nsteps))) return fail(ODL_EINVAL, "odl_trajectory: null buffer");
   if (n == 0) return 0;
-  ODL_CUDA(cudaSetDevice(m->device));
+  ODL_ON_DEVICE(m);
+  int rc;
+  if ((rc = units_ready(m, {U_TRAJ}))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   Staging st{m, s, 0, mem};
   OdlTrajArgs A{};
-  int rc;
   OdlData D = m->grid.d;
   if ((rc = st.in(theta, (size_t)n * m->n_param, &A.theta))) return rc;
   if ((rc = st.in(y0_or_null, (size_t)n * m->n_state, &A.y0))) return rc;
@@ -805,11 +977,15 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   if (stride < P + 5) return fail(ODL_EINVAL, "odl_mcmc: row_stride < n_param+5");
   if (mo->rng_mode == ODL_RNG_HOST_STREAMS && (!io->z || !io->u)) return fail(ODL_EINVAL, "odl_mcmc: host streams need z and u");
   if (mo->rng_mode == ODL_RNG_FORCED && (!io->forced || !io->u)) return fail(ODL_EINVAL, "odl_mcmc: forced mode needs proposals and u");
-  ODL_CUDA(cudaSetDevice(m->device));
+  ODL_ON_DEVICE(m);
+  int rc;
+  const bool use_coop = solver == ODL_SOLVER_DOPRI5 && m->coop_model() && mo->speculate <= 0;
+  if ((rc = units_ready(m, {use_coop ? U_MCMC_COOP : (solver == ODL_SOLVER_DOPRI5 ? U_MCMC : (solver == ODL_SOLVER_ROS23 ? U_MCMC_ROS :
+                            (solver == ODL_SOLVER_RADAU5 ? U_MCMC_RADAU : (solver == ODL_SOLVER_BDF ? U_MCMC_BDF : U_MCMC_AUTO))))})))
+    return rc;
   cudaStream_t s = (cudaStream_t)stream;
   Staging st{m, s, 0, mem};
   OdlMcmcArgs A{};
-  int rc;
   if ((rc = st.inout(io->theta, (size_t)C * P, &A.theta_cur, true))) return rc;
   if ((rc = st.inout(io->chain_state, (size_t)C * ODL_CHAIN_STATE, &A.chain_state, true))) return rc;
   if ((rc = st.inout(io->best_theta, (size_t)C * P, &A.best_theta, it_begin > 1))) return rc;
@@ -855,7 +1031,7 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   if (warp_cta) block = 32;
   const size_t smem = smem_bytes(D, (int)block);
   unsigned grid = (unsigned)((threads + block - 1) / block);
-  if (solver == ODL_SOLVER_DOPRI5 && m->k_mcmc_coop && mo->speculate <= 0) {
+  if (use_coop) {
     // n > 8: one chain per K groups of lanes (odl_mcmc_coop_kernel); the chain is the same chain as with every other
     // mapping.  speculate = -K asks for K groups per chain (K * coop_lanes <= 32), 0 = automatic as above
     const size_t smem_c = coop_smem_bytes(m, D);
@@ -897,7 +1073,7 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
 extern "C" int odl_debug_counters(odl_model* m, int* out, int count) {
   if (!m || !out || !m->on_gpu) return fail(ODL_EINVAL, "odl_debug_counters: bad argument");
   if (count < 0 || count > 1024) return fail(ODL_EINVAL, "odl_debug_counters: count out of range");
-  ODL_CUDA(cudaSetDevice(m->device));
+  ODL_ON_DEVICE(m);
   ODL_CUDA(cudaMemcpy(out, m->counter.p, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -1009,7 +1185,7 @@ extern "C" int odl_select_below(odl_model* m, const double* chi_dev, long long n
   if (n < 0 || n > 2147483647LL || !count_host || (n > 0 && (!chi_dev || !index_dev))) return fail(ODL_EINVAL, "odl_select_below: bad argument");
   *count_host = 0;
   if (n == 0) return 0;
-  ODL_CUDA(cudaSetDevice(m->device));
+  ODL_ON_DEVICE(m);
   cudaStream_t s = (cudaStream_t)stream;
   const int n_tile = (int)((n + ODL_SEL_TILE - 1) / ODL_SEL_TILE);
   DevBuf& b = m->scratch[23];
@@ -1032,7 +1208,7 @@ extern "C" int odl_gather_rows(odl_model* m, const double* src_dev, int row_len,
   if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_gather_rows: model is not loaded on a GPU (no CPU fallback exists)");
   if (n_pick < 0 || row_len < 1 || (n_pick > 0 && (!src_dev || !picks_host || !dst_dev))) return fail(ODL_EINVAL, "odl_gather_rows: bad argument");
   if (n_pick == 0) return 0;
-  ODL_CUDA(cudaSetDevice(m->device));
+  ODL_ON_DEVICE(m);
   cudaStream_t s = (cudaStream_t)stream;
   DevBuf& b = m->scratch[22];
   int rc = b.ensure((size_t)n_pick * sizeof(long long));
@@ -1125,7 +1301,7 @@ extern "C" int odl_sample_lhs(odl_model* m, long long n, int n_param, const int*
     return fail(ODL_EINVAL, "odl_sample_lhs: bad argument");
   for (int j = 0; j < n_param; ++j) if (kind[j] < 0 || kind[j] > 3) return fail(ODL_EINVAL, "odl_sample_lhs: unknown prior kind");
   if (n == 0) return 0;
-  ODL_CUDA(cudaSetDevice(m->device));
+  ODL_ON_DEVICE(m);
   cudaStream_t s = (cudaStream_t)stream;
   DevBuf& bk = m->scratch[21];
   int rc = bk.ensure((size_t)n_param * (sizeof(int) + 3 * sizeof(double)) + 64);
@@ -1249,6 +1425,9 @@ __global__ void __launch_bounds__(256) odl_dfma_peak_kernel(double* out, int ite
 
 extern "C" int odl_fp64_peak(int device, int repeats, double* tflops, float* ms_per_launch) {
   if (!tflops) return fail(ODL_EINVAL, "null argument");
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{device >= 0 && device != prev ? prev : -1};
   if (device >= 0) ODL_CUDA(cudaSetDevice(device));
   ODL_CUDA(cudaFree(0));
   int dev = 0;

@@ -45,6 +45,15 @@
 #ifndef ODL_MINBLOCKS_MCMC
 #define ODL_MINBLOCKS_MCMC ODL_MINBLOCKS
 #endif
+// Compilation units.  The library compiles ONE kernel (the small ordering trio counts as one) per NVRTC
+// program, on demand and in parallel host threads, so that a new model is ready when the kernels a call needs are
+// (odl_capi.cu: Unit): -DODL_UNIT=<k> keeps only that unit's __global__ functions, 0 (default) keeps everything.
+//   1 sweep   2 traj   3 mcmc   4 sweep_bdf   5 mcmc_bdf   6 sweep_ros23   7 mcmc_ros23   8 mcmc_auto
+//   9 sweep_radau5   10 mcmc_radau5   11 sweep_coop   12 mcmc_coop   13 order_key / order_scan / order_scatter
+#ifndef ODL_UNIT
+#define ODL_UNIT 0
+#endif
+#define ODL_HAS(u) (ODL_UNIT == 0 || ODL_UNIT == (u))
 #ifndef ODL_MINBLOCKS_ROS
 #define ODL_MINBLOCKS_ROS (ODL_MINBLOCKS > 2 ? ODL_MINBLOCKS - 1 : ODL_MINBLOCKS)
 #endif
@@ -239,15 +248,21 @@ __constant__ double ODL_TAB[36] = {
     0.3, 0.8, 8.0 / 9.0, 0.0};                                                                        // 32 c3 c4 c5
 #define ODL_T(i) ODL_TAB[i]
 
+// y0_from_params: the '<state>0' convention.  The reference copies such a parameter into the state's initial value
+// in ONE place only -- the proposal loop of MetropolisHastings (Samplers.py:110-114; restored on reject :139-143) --
+// so it holds for the solves of PROPOSALS.  integrate(), the survey (_Fit_worker, Framework.py:41-48) and the chain's
+// a-priori solve (Samplers.py:88) start from the model's istates (Framework.py:647-650) whatever the parameter says.
 __device__ __forceinline__ void odl_init_system(OdlStepper& st, const double (&p)[ODL_P], const OdlData& D,
-                                                const OdlOpts& O, const double* y0_override) {
+                                                const OdlOpts& O, const double* y0_override, bool y0_from_params) {
 ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) {
     double v = y0_override ? y0_override[i] : D.y0[i];
 #if ODL_Y0P
-    const int src = D.y0_from_param[i];
+    if (y0_from_params) {
+      const int src = D.y0_from_param[i];
 ODL_UNROLL
-    for (int q = 0; q < ODL_P; ++q) if (src == q) v = p[q];     // '<state>0' parameters (Samplers.py:110-114)
+      for (int q = 0; q < ODL_P; ++q) if (src == q) v = p[q];   // Samplers.py:110-114
+    }
 #endif
     st.y[i] = v;
   }
@@ -1388,15 +1403,7 @@ __device__ __forceinline__ int odl_order_bin(const OdlData& D, const double* the
 ODL_UNROLL
   for (int q = 0; q < ODL_P; ++q) p[q] = theta_row[q];
 ODL_UNROLL
-  for (int i = 0; i < ODL_N; ++i) {
-    double v = D.y0[i];
-#if ODL_Y0P
-    const int src = D.y0_from_param[i];
-ODL_UNROLL
-    for (int q = 0; q < ODL_P; ++q) if (src == q) v = p[q];
-#endif
-    y[i] = v;
-  }
+  for (int i = 0; i < ODL_N; ++i) y[i] = D.y0[i];             // a sweep starts from istates (see odl_init_system)
   double J[ODL_N][ODL_N];
   odl_jac(y, D.t0, p, J);
   double nrm = 0.0;
@@ -1413,6 +1420,7 @@ ODL_UNROLL
   const int b = (int)floorf((__log2f(key) + 32.0f) * 4.0f);                      // quarter octaves over 2^-32 .. 2^32
   return b < 0 ? 0 : (b > ODL_ORDER_BINS - 1 ? ODL_ORDER_BINS - 1 : b);
 }
+#if ODL_HAS(13)
 extern "C" __global__ void __launch_bounds__(256)
 odl_order_key_kernel(const OdlData D, const OdlOrderArgs A) {
   __shared__ int h[ODL_ORDER_BINS];
@@ -1468,6 +1476,7 @@ odl_order_scatter_kernel(const OdlOrderArgs A) {
     __syncthreads();
   }
 }
+#endif  // unit 13
 
 // ------------------------------------------------------------------------------------------------
 // Forward sweep: Framework.py:41-48 (_Fit_worker) for n parameter sets
@@ -1554,7 +1563,7 @@ ODL_UNROLL
           row = A.index ? (long long)A.index[sys] : sys;
 ODL_UNROLL
           for (int q = 0; q < ODL_P; ++q) p[q] = A.theta[row * ODL_P + q];
-          odl_init_system(st, p, D, O, nullptr);
+          odl_init_system(st, p, D, O, nullptr, false);
           ax.reset();
           odl_emit_initial_slots(st, S, D, sink);
           active = true;
@@ -1586,7 +1595,7 @@ ODL_UNROLL
             sys = ticket; row = r;
 ODL_UNROLL
             for (int q = 0; q < ODL_P; ++q) p[q] = A.theta[row * ODL_P + q];
-            odl_init_system(st, p, D, O, nullptr);
+            odl_init_system(st, p, D, O, nullptr, false);
             ax.reset();
             odl_emit_initial_slots(st, S, D, sink);
             active = true; pending = false;
@@ -1636,19 +1645,28 @@ ODL_UNROLL
     if (lane == 0) atomicAdd(A.prod_exited, 1);
   }
 }
+#if ODL_HAS(1)
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
 odl_sweep_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<0>(D, O, A); }
+#endif
+#if ODL_HAS(6)
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
 odl_sweep_ros23_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<1>(D, O, A); }
+#endif
+#if ODL_HAS(9)
 extern "C" __global__ void __launch_bounds__(32, 1)
 odl_sweep_radau5_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<3>(D, O, A); }
+#endif
 // (register caps for more resident warps spill: 168 registers -> 3.1 ms against 1.6 ms at 226, tools/variant_ab.py)
+#if ODL_HAS(4)
 extern "C" __global__ void __launch_bounds__(32, 1)
 odl_sweep_bdf_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<4>(D, O, A); }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Full trajectories on the output grid (ModelFramework.integrate, Framework.py:622-683)
 // ------------------------------------------------------------------------------------------------
+#if ODL_HAS(2)
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
 odl_traj_kernel(const OdlData D, const OdlOpts O, const OdlTrajArgs A) {
   OdlShared S;
@@ -1662,7 +1680,7 @@ ODL_UNROLL
   for (int q = 0; q < ODL_P; ++q) p[q] = A.theta[sys * ODL_P + q];
   OdlStepper st;
   OdlTrajSink sink; sink.traj = A.traj + sys * (long long)D.n_slot * ODL_N;
-  odl_init_system(st, p, D, O, A.y0 ? A.y0 + sys * ODL_N : nullptr);
+  odl_init_system(st, p, D, O, A.y0 ? A.y0 + sys * ODL_N : nullptr, false);
   odl_emit_initial_slots(st, S, D, sink);
   while (st.slot < D.n_slot && st.status == ODL_OK) odl_dopri5_attempt(st, p, S, D, O, sink);
   if (st.status != ODL_OK) {
@@ -1672,6 +1690,7 @@ ODL_UNROLL
   }
   A.status[sys] = st.status; A.nsteps[sys] = st.nsteps;
 }
+#endif  // unit 2
 
 // ------------------------------------------------------------------------------------------------
 // Metropolis-Hastings: Samplers.py:53-174, one chain per thread, device resident
@@ -1821,7 +1840,7 @@ ODL_UNROLL
       } else {
         odl_propose(p, A, chain, it + sub);
       }
-      odl_init_system(st, p, D, O, nullptr);
+      odl_init_system(st, p, D, O, nullptr, !apriori);          // proposals: '<state>0' parameters set y0 (Samplers.py:110-114)
       ax.reset();
       odl_emit_initial_slots(st, S, D, sink);
       active = true;
@@ -1843,7 +1862,7 @@ ODL_UNROLL
           if (restart) {
             if (A.step_count) atomicAdd((unsigned long long*)&A.step_count[chain], (unsigned long long)st.nsteps);
             use_ros = true;
-            odl_init_system(st, p, D, O, nullptr);
+            odl_init_system(st, p, D, O, nullptr, !apriori);
             ax.reset();
             odl_emit_initial_slots(st, S, D, sink);
             done = (st.slot >= D.n_slot);
@@ -1927,29 +1946,27 @@ ODL_UNROLL
       // Welford over ln(theta) of the kept rows for R-hat: sequential in the iteration (the same recurrence, in the
       // same order, whatever K is), by the group's first lane
       if (A.summaries && has_chain && sub == 0 && it + adv - 1 > A.burnin) {
+        // one parameter at a time (all of them at once kept 4 P doubles live and spilled at 128 registers)
         double* sm = A.summaries + (size_t)chain * (1 + 2 * ODL_P);
-        double cnt = sm[0];
-        double mean[ODL_P], m2[ODL_P], xr[ODL_P], xa[ODL_P];
+        const double cnt0 = sm[0];
+        double cnt = cnt0;
 ODL_UNROLL
         for (int q = 0; q < ODL_P; ++q) {
-          mean[q] = sm[1 + q]; m2[q] = sm[1 + ODL_P + q];
-          xr[q] = (jstar == 0) ? 0.0 : log(cur[q]);              // jstar == 0: the only consumed row is the accepted one
-          xa[q] = (jstar >= 0) ? log(pacc[q]) : 0.0;
-        }
-        for (int i = 0; i < adv; ++i) {
-          if (it + i <= A.burnin) continue;
-          cnt += 1.0;
-ODL_UNROLL
-          for (int q = 0; q < ODL_P; ++q) {
-            const double x = (i == jstar) ? xa[q] : xr[q];
-            const double dlt = x - mean[q];
-            mean[q] += dlt / cnt;
-            m2[q] += dlt * (x - mean[q]);
+          double mean = sm[1 + q], m2 = sm[1 + ODL_P + q];
+          const double xr = (jstar == 0) ? 0.0 : log(cur[q]);    // jstar == 0: the only consumed row is the accepted one
+          const double xa = (jstar >= 0) ? log(pacc[q]) : 0.0;
+          cnt = cnt0;
+          for (int i = 0; i < adv; ++i) {
+            if (it + i <= A.burnin) continue;
+            cnt += 1.0;
+            const double x = (i == jstar) ? xa : xr;
+            const double dlt = x - mean;
+            mean += dlt / cnt;
+            m2 += dlt * (x - mean);
           }
+          sm[1 + q] = mean; sm[1 + ODL_P + q] = m2;
         }
         sm[0] = cnt;
-ODL_UNROLL
-        for (int q = 0; q < ODL_P; ++q) { sm[1 + q] = mean[q]; sm[1 + ODL_P + q] = m2[q]; }
       }
       // Best kept row (set_best_params' idxmin, Framework.py:725-731): the first kept row carries the current point;
       // after that only an accepted proposal can be a new minimum (rejected rows repeat a chi already seen)
@@ -1985,16 +2002,26 @@ ODL_UNROLL
     more = has_chain && it < A.it_end;
   }
 }
+#if ODL_HAS(3)
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_MCMC)
 odl_mcmc_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<0>(D, O, A); }
+#endif
+#if ODL_HAS(7)
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
 odl_mcmc_ros23_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<1>(D, O, A); }
+#endif
+#if ODL_HAS(8)
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
 odl_mcmc_auto_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<2>(D, O, A); }
+#endif
+#if ODL_HAS(10)
 extern "C" __global__ void __launch_bounds__(32, 1)
 odl_mcmc_radau5_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<3>(D, O, A); }
+#endif
+#if ODL_HAS(5)
 extern "C" __global__ void __launch_bounds__(32, 1)
 odl_mcmc_bdf_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<4>(D, O, A); }
+#endif
 // ================================================================================================
 // Cooperative kernels for larger systems (n > 8): ODL_G lanes per system.
 //
@@ -2083,7 +2110,8 @@ __device__ __forceinline__ void odl_coop_emit(const double (&yi)[ODL_C], int slo
   __syncwarp(G.mask);
 }
 
-__device__ __forceinline__ void odl_coop_init(OdlCoopStepper& st, const OdlGroup& G, const OdlData& D, const OdlOpts& O) {
+__device__ __forceinline__ void odl_coop_init(OdlCoopStepper& st, const OdlGroup& G, const OdlData& D, const OdlOpts& O,
+                                              bool y0_from_params) {
 #pragma unroll
   for (int c = 0; c < ODL_C; ++c) {
     const int i = G.sub + c * ODL_G;
@@ -2092,7 +2120,7 @@ __device__ __forceinline__ void odl_coop_init(OdlCoopStepper& st, const OdlGroup
       v = D.y0[i];
 #if ODL_Y0P
       const int src = D.y0_from_param[i];
-      if (src >= 0) v = G.psm[src];
+      if (y0_from_params && src >= 0) v = G.psm[src];              // proposals only (see odl_init_system)
 #endif
     }
     st.y[c] = v;
@@ -2263,6 +2291,7 @@ __device__ __forceinline__ OdlGroup odl_coop_group(const OdlShared& S, const Odl
   return G;
 }
 
+#if ODL_HAS(11)
 // ---- forward sweep, one group per system at a time, work counter refill ----
 extern "C" __global__ void __launch_bounds__(ODL_COOP_BLOCK, ODL_COOP_MINBLOCKS)
 odl_sweep_coop_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
@@ -2280,7 +2309,7 @@ odl_sweep_coop_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
     const long long row = A.index ? (long long)A.index[sys] : sys;
     for (int q = G.sub; q < ODL_P; q += ODL_G) G.psm[q] = A.theta[row * ODL_P + q];
     __syncwarp(G.mask);
-    odl_coop_init(st, G, D, O);
+    odl_coop_init(st, G, D, O, false);
     while (st.slot < D.n_slot && st.status == ODL_OK) odl_coop_attempt(st, G, S, D, O);
     double chi, ss; int nv;
     double* pred_out = (A.pred && st.status == ODL_OK) ? A.pred + row * D.n_obs : nullptr;
@@ -2304,6 +2333,7 @@ odl_sweep_coop_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
     if ((threadIdx.x & 31) == 0) atomicAdd(A.prod_exited, 1);
   }
 }
+#endif  // unit 11
 
 // ---- Metropolis-Hastings, one group per chain (Samplers.py:53-174); same outputs as odl_mcmc_body ----
 __device__ __forceinline__ void odl_coop_propose(const OdlGroup& G, const OdlMcmcArgs& A, int chain, int it) {
@@ -2337,6 +2367,7 @@ __device__ __forceinline__ void odl_coop_propose(const OdlGroup& G, const OdlMcm
   __syncwarp(G.mask);
 }
 
+#if ODL_HAS(12)
 // One chain per K groups (A.spec = K, a power of two with K * ODL_G <= 32): prefetching MH as in odl_mcmc_body, a
 // group taking the place of a lane -- group kk evaluates iteration it+kk along the all-rejected path, the K groups
 // consume iterations up to and including the first acceptance.  The chain does not depend on K.
@@ -2374,7 +2405,7 @@ odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
       } else {
         odl_coop_propose(G, A, chain, it + kk);
       }
-      odl_coop_init(st, G, D, O);
+      odl_coop_init(st, G, D, O, !apriori);
       while (st.slot < D.n_slot && st.status == ODL_OK) odl_coop_attempt(st, G, S, D, O);
       double chi, ss; int nv;
       odl_coop_score(S, D, G, nullptr, chi, ss, nv);
@@ -2475,5 +2506,6 @@ odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
     __syncwarp(smask);
   }
 }
+#endif  // unit 12
 #endif  // !ODL_SMALL
 #endif  // ODL_HOST_HARNESS

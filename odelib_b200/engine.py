@@ -79,7 +79,7 @@ class DeviceModel:
             block_threads = 64
         bo.block_threads, bo.min_blocks = int(block_threads), int(min_blocks)
         bo.dense_output = 1 if dense_output else 0
-        bo.compile_only = 1 if compile_only else 0
+        bo.compile_only = int(compile_only)                       # 1 / True: every kernel unit; 2: the default paths' units
         bo.y0_from_param = 1 if y0_from_param else 0
         bo.coop_lanes = int(coop_lanes)
         bo.cache_dir = cache_dir.encode() if cache_dir else None
@@ -116,6 +116,12 @@ class DeviceModel:
         r, l, b = C.c_int(), C.c_int(), C.c_int()
         _capi.check(self._L.odl_model_kernel_info(self._h, kernel.encode(), C.byref(r), C.byref(l), C.byref(b)))
         return {"regs": r.value, "local_bytes": l.value, "blocks_per_sm": b.value}
+
+    def unit_seconds(self, unit):
+        """(NVRTC seconds, cache hit) of a kernel unit ("sweep", "sweep_bdf", "mcmc", ...); (-1, False) = not compiled."""
+        sec, hit = C.c_double(), C.c_int()
+        _capi.check(self._L.odl_model_unit_seconds(self._h, unit.encode(), C.byref(sec), C.byref(hit)))
+        return sec.value, bool(hit.value)
 
     def last_kernel_ms(self):
         ms = C.c_float()

@@ -201,7 +201,8 @@ class Sym:
         raise TraceError("data-dependent control flow / comparison on a state, parameter or time "
                          "value cannot be traced into a CUDA device function")
 
-    __bool__ = __lt__ = __le__ = __gt__ = __ge__ = _nope
+    # == / != as well: falling back to object identity would trace `if y[0] == 0:` down ONE branch, silently
+    __bool__ = __lt__ = __le__ = __gt__ = __ge__ = __eq__ = __ne__ = _nope
     __float__ = __int__ = __index__ = _nope
     __hash__ = object.__hash__
 

@@ -260,8 +260,10 @@ def mh_chain(rhs, theta0, tab: Tables, n_params_total, nits=1000, burnin=None, w
     theta0: start values in parameter_names order.  walk: boolean mask of walking parameters
     (static_parameters are the False entries).  z[nits-1, n_walk], u[nits-1]: host streams
     (generated with ``reference_streams(seed, ...)`` when omitted).
-    y0_from_param: optional {state_index: param_index} for the '<state>0' convention
-    (Samplers.py:110-114).
+    y0_from_param: optional {state_index: param_index} for the '<state>0' convention: the proposal
+    loop copies such a parameter into the state's initial value (Samplers.py:110-114) and the reject
+    branch restores it (:139-143).  The a-priori solve (Samplers.py:88) runs BEFORE any of that, from
+    the model's istates (tab.y0), whatever the '<state>0' parameter holds.
 
     log_prior: None = the reference's chain (prior densities are evaluated but never enter the ratio,
     Samplers.py:118-127 -- SURVEY.md A1, A3).  A callable theta -> log prior density switches to the
@@ -288,8 +290,7 @@ def mh_chain(rhs, theta0, tab: Tables, n_params_total, nits=1000, burnin=None, w
             for si, pi in y0_from_param.items():
                 y0[si] = th[pi]
 
-    apply_y0(theta)
-    _, chi_cur, r2_cur = solve_unit(rhs, theta, tab, rtol, atol, y0)        # :88-90
+    _, chi_cur, r2_cur = solve_unit(rhs, theta, tab, rtol, atol, y0)        # :88-90: istates, not '<state>0'
     aic_cur = aic_of(chi_cur, n_params_total)
     lp_cur = log_prior(theta) if log_prior is not None else 0.0
     old = theta.copy()

@@ -70,7 +70,7 @@ extern "C" int harness_solve(int solver, const double* theta, const double* slot
   for (int q = 0; q < ODL_P; ++q) p[q] = theta[q];
   OdlStepper st;
   HostSink sink{out};
-  odl_init_system(st, p, D, O, nullptr);
+  odl_init_system(st, p, D, O, nullptr, false);
   odl_emit_initial_slots(st, S, D, sink);
   OdlRadauAux ax;
   ax.reset();
@@ -107,7 +107,7 @@ extern "C" int harness_progress(const double* theta, const double* slot_t, int n
   static double scratch[4096];
   OdlStepper st;
   HostSink sink{scratch};
-  odl_init_system(st, p, D, O, nullptr);
+  odl_init_system(st, p, D, O, nullptr, false);
   odl_emit_initial_slots(st, S, D, sink);
   for (int k = 0; k < n_check; ++k) { marks[k] = NAN; hs[k] = NAN; }
   while (st.slot < D.n_slot && st.status == ODL_OK) {

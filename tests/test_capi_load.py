@@ -32,12 +32,26 @@ def test_library_exports_every_declared_symbol():
 def test_nvrtc_compiles_demo_models_offline(name, tmp_path):
     f, n, P, g = demo_models.MODELS[name]
     m = engine.DeviceModel(f, n, P, g, compile_only=True, cache_dir=str(tmp_path))
-    cubins = [p for p in os.listdir(tmp_path) if p.endswith(".cubin")]
-    assert len(cubins) == 1 and os.path.getsize(tmp_path / cubins[0]) > 10000
-    # second build hits the cache
+    # one NVRTC program (one cubin) per kernel unit, compiled side by side on host threads
+    units = ["sweep", "traj", "mcmc", "sweep_bdf", "mcmc_bdf", "sweep_ros23", "mcmc_ros23", "mcmc_auto", "sweep_radau5",
+             "mcmc_radau5", "order"]
+    cubins = sorted(p for p in os.listdir(tmp_path) if p.endswith(".cubin"))
+    assert len(cubins) == len(units) and all(os.path.getsize(tmp_path / c) > 3000 for c in cubins)
+    assert sorted(c.split("_", 2)[2][:-len(".cubin")] for c in cubins) == sorted(units)
+    for u in units:
+        sec, hit = m.unit_seconds(u)
+        assert sec > 0 and not hit
+    assert m.unit_seconds("sweep_coop") == (-1.0, False)           # n <= 8: no cooperative kernels
+    # second build hits the cache, unit by unit
     m2 = engine.DeviceModel(f, n, P, g, compile_only=True, cache_dir=str(tmp_path))
-    assert "cache hit" in m2.build_log
+    assert m2.build_log.count("cache hit") == len(units) and all(m2.unit_seconds(u)[1] for u in units)
     m.close(); m2.close()
+    # compile_only = 2: only what the default paths launch (ordering, DOPRI5 sweep, BDF stiff pass, trajectories, chains)
+    sub = tmp_path / "default_only"
+    m3 = engine.DeviceModel(f, n, P, g, compile_only=2, cache_dir=str(sub))
+    got = sorted(c.split("_", 2)[2][:-len(".cubin")] for c in os.listdir(sub) if c.endswith(".cubin"))
+    assert got == sorted(["order", "sweep", "sweep_bdf", "traj", "mcmc"])
+    m3.close()
 
 
 def test_bad_model_source_reports_nvrtc_log():

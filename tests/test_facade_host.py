@@ -257,3 +257,76 @@ def test_chain_start_picks_are_what_dataframe_sample_draws():
         np.random.seed(seed)
         picks = np.random.choice(len(good), size=17, replace=True)
         assert np.array_equal(good["a"].to_numpy()[picks], ref)
+
+
+class _RecordingDeviceModel:
+    """Stands in for engine.DeviceModel: records what the facade uploads (no GPU, no compile)."""
+    instances = 0
+
+    def __init__(self, ode, n_state, n_param, groups, device=None, y0_from_param=False):
+        type(self).instances += 1
+        self.n_state, self.n_param, self.y0_from_param = n_state, n_param, y0_from_param
+        self.loaded_y0 = self.loaded_grid = self.loaded_map = None
+        self.uploads = 0
+
+    def set_data(self, tables, y0, y0_from_param=None):
+        self.loaded_y0, self.loaded_obs = np.array(y0), tables.ln_obs.copy()
+        self.loaded_map = None if y0_from_param is None else np.array(y0_from_param)
+        self.uploads += 1
+
+    def set_grid(self, times, y0, y0_from_param=None):
+        self.loaded_grid = np.array(times)
+
+
+def test_copies_share_the_compiled_model_but_not_its_loaded_tables(monkeypatch):
+    """a copy with other initial states / data must not leave ITS tables behind for the original."""
+    import odelib_b200.Framework as F
+    monkeypatch.setattr(F, "DeviceModel", _RecordingDeviceModel)
+    _RecordingDeviceModel.instances = 0
+    a = make_model("two_i")
+    dm = a._device()
+    n0 = dm.uploads
+    assert a._device() is dm and dm.uploads == n0                      # nothing changed: nothing re-uploaded
+    b = a.copy(overwrite={"S": 1.0e6})
+    assert b._device() is dm and _RecordingDeviceModel.instances == 1   # shared compiled model
+    assert dm.loaded_y0[0] == 1.0e6
+    a._device()                                                         # the original loads its own states again
+    assert dm.loaded_y0[0] == 5236900 and dm.uploads == n0 + 2
+    # a copy given other data: its observation rows are what is loaded when IT computes, the original's when it does
+    df2 = demo_df("two_i").copy()
+    df2["abundance"] = df2["abundance"] * 2.0
+    c = a.copy()
+    c.reset_dataframe(df2)
+    c._device()
+    obs_c = dm.loaded_obs.copy()
+    a._device()
+    assert not np.array_equal(obs_c, dm.loaded_obs)
+    np.testing.assert_allclose(obs_c, dm.loaded_obs + np.log(2.0), rtol=1e-14)
+    # interleaved calls never reuse the other instance's tables
+    for m_, s0 in ((b, 1.0e6), (a, 5236900), (b, 1.0e6)):
+        m_._device()
+        assert dm.loaded_y0[0] == s0
+
+
+def test_state0_parameters_host_semantics(monkeypatch):
+    """'<state>0' parameters: the map reaches the device tables; set_best_params copies the best row's values into the
+    initial states (Framework.py:725-731) exactly as the unmodified reference did (tests/golden/make_state0.py)."""
+    import odelib_b200.Framework as F
+    monkeypatch.setattr(F, "DeviceModel", _RecordingDeviceModel)
+    g = golden("state0")
+    LN = scipy.stats.lognorm
+    pri = [("mu", 3, 1e-8), ("phi", 3, 1e-8), ("beta", 1, 25), ("S0", 0.3, 5.0e6), ("V0", 0.3, 1.1e7)]
+    pobj = {n: ODElib.parameter(stats_gen=LN, hyperparameters={"s": s, "scale": sc}, init_value=v)
+            for (n, s, sc), v in zip(pri, g["start"])}
+    m = ODElib.ModelFramework(ODE=lambda y, t, ps: demo_models.zero_i(y, t, ps), parameter_names=[p[0] for p in pri],
+                              state_names=["S", "V"], dataframe=demo_df("zero_i"), t_steps=288, **pobj)
+    np.testing.assert_array_equal(m._y0_map(), [3, 4])
+    dm = m._device()
+    assert dm.y0_from_param and np.array_equal(dm.loaded_map, [3, 4])
+    np.testing.assert_array_equal(dm.loaded_y0, g["y0"])              # istates from the data, not S0 / V0
+    cols = [p[0] for p in pri] + ["chi", "rsquared", "aic", "iteration", "acceptance_ratio"]
+    post = pd.DataFrame(g["chain_walk_kept"], columns=cols)
+    post["chain#"] = 0
+    m.set_best_params(post)
+    np.testing.assert_array_equal(np.asarray(m.get_inits(), float), g["best_inits"])
+    np.testing.assert_array_equal(m._current_theta(), g["best_theta"])

@@ -90,3 +90,50 @@ def test_rhat_definition():
     assert np.all(np.abs(r - 1) < 0.02)
     x[0] += 3.0
     assert np.all(orc.rhat(x) > 1.2)
+
+
+# ---- '<state>0' parameters (tests/golden/make_state0.py; Samplers.py:110-114, :139-143, Framework.py:730-731) ----
+STATE0_MAP = {0: 3, 1: 4}          # state S <- parameter S0 (slot 3), V <- V0 (slot 4)
+
+
+def state0_rhs(y, t, ps):
+    return orc.zero_i(y, t, ps[:3])
+
+
+def test_state0_values_are_ignored_outside_the_proposal_loop():
+    """integrate / _Fit_worker start from istates whatever S0, V0 hold (Framework.py:647-650, :41-48)."""
+    g = golden("state0")
+    tab = oracle_tables("zero_i")
+    assert np.array_equal(tab.y0, g["y0"])
+    for k, th in enumerate(g["theta"]):
+        vec, chi, r2 = orc.solve_unit(state0_rhs, th, tab)
+        np.testing.assert_allclose(vec, g["pred_def"][k], rtol=1e-12)
+        np.testing.assert_allclose(chi, g["chi_def"][k], rtol=1e-12)
+        np.testing.assert_allclose(chi, g["fit_worker_chi"][k], rtol=1e-12)
+        np.testing.assert_allclose(r2, g["r2_def"][k], rtol=1e-12)
+
+
+@pytest.mark.parametrize("tag,walk", [("walk", [1, 1, 1, 1, 1]), ("staticV0", [1, 1, 1, 1, 0])])
+def test_state0_chain_matches_reference(tag, walk):
+    """A-priori solve from istates, every proposal from its own S0 / V0 (a static V0 included), restored on reject."""
+    g = golden("state0")
+    tab = oracle_tables("zero_i")
+    pre = f"chain_{tag}_"
+    nits = int(g[pre + "nits"])
+    z, u = orc.reference_streams(3, sum(walk), nits - 1)
+    assert np.array_equal(z, g[pre + "z"]) and np.array_equal(u, g[pre + "u"])
+    out = orc.mh_chain(state0_rhs, g[pre + "theta0"], tab, int(g["pnum"]), nits=nits, walk=np.array(walk, bool), z=z, u=u,
+                       y0_from_param=STATE0_MAP)
+    assert np.array_equal(g[pre + "y0_apriori"], tab.y0)                       # the reference's own a-priori solve
+    np.testing.assert_array_equal(g[pre + "y0_solves"], g[pre + "proposals"][:, 3:5])
+    assert np.array_equal(out["accepted"], g[pre + "accepted"]) and out["accepted"].sum() > 5
+    np.testing.assert_allclose(out["proposals"], g[pre + "proposals"], rtol=1e-13)
+    np.testing.assert_allclose(out["chinew"], g[pre + "chinew"], rtol=1e-12)
+    kept = g[pre + "kept"].copy()
+    if tag == "staticV0":                                                      # quirk A13: static column = prior scale
+        assert np.all(kept[:, 4] == 1.1e7)
+        kept[:, 4] = out["kept"][:, 4]
+    np.testing.assert_allclose(out["kept"], kept, rtol=1e-12)
+    # without the a-priori exception the chain is a different chain: the restatement must not apply S0 there
+    _, chi_wrong, _ = orc.solve_unit(state0_rhs, g[pre + "theta0"], tab, y0=g[pre + "theta0"][3:5])
+    assert abs(chi_wrong - float(g[pre + "chi0"])) > 1e-3

@@ -62,3 +62,20 @@ def test_control_flow_is_rejected_loudly():
 def test_wrong_arity_is_rejected():
     with pytest.raises(TraceError):
         trace(orc.zero_i, 3, 3)
+
+
+def test_equality_on_traced_values_is_refused():
+    """`==` / `!=` on a proxy must raise like the ordering comparisons do (object identity would silently pick a branch)."""
+    from odelib_b200.tracer import TraceError, trace
+
+    def rhs_eq(y, t, ps):
+        if y[0] == 0:
+            return [ps[0] * y[0]]
+        return [-ps[0] * y[0]]
+
+    def rhs_ne(y, t, ps):
+        return [ps[0] * y[0] if ps[0] != 0 else y[0]]
+
+    for f in (rhs_eq, rhs_ne):
+        with pytest.raises(TraceError):
+            trace(f, 1, 1)
