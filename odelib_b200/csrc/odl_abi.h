@@ -5,6 +5,7 @@
 #define ODL_ABI_H
 #define ODL_MAX_WALK 64
 #define ODL_CHAIN_STATE 8
+#define ODL_LOGTAB 256        // intervals of [1, 2) in the scorer's logarithm table (odl_log): 2 doubles each, per CTA
 
 // status words (per system)
 #define ODL_OK 0
@@ -28,6 +29,7 @@ struct OdlData {                 // constant tables of one ModelFramework (SURVE
   int pad_;
   double t0;
   double sstot;                  // sum_s n_s * var(O_s)               (stats.py:55)
+  double inv_sstot;              // 1 / sstot: R^2 = 1 - ssres * inv_sstot without a division per solve
 };
 
 struct OdlOpts {

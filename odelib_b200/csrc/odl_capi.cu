@@ -508,12 +508,12 @@ static unsigned pick_block(const OdlData& d, int preferred) {
 static const unsigned kCoopBlock = 128;
 static size_t coop_smem_bytes(const odl_model* m, const OdlData& d) {
   const size_t groups = kCoopBlock / m->coop;
-  size_t doubles = (size_t)d.n_slot + 3 * (size_t)d.n_obs + ((size_t)d.n_obs + 1) / 2 +
+  size_t doubles = 2 * ODL_LOGTAB + (size_t)d.n_slot + 3 * (size_t)d.n_obs + ((size_t)d.n_obs + 1) / 2 +
                    groups * ((size_t)m->n_state + m->n_param + d.stage_stride);
   return doubles * sizeof(double);
 }
 static size_t smem_bytes(const OdlData& d, int block) {
-  size_t doubles = (size_t)d.n_slot + 3 * (size_t)d.n_obs + ((size_t)d.n_obs + 1) / 2 + (size_t)block * d.stage_stride;
+  size_t doubles = 2 * ODL_LOGTAB + (size_t)d.n_slot + 3 * (size_t)d.n_obs + ((size_t)d.n_obs + 1) / 2 + (size_t)block * d.stage_stride;
   return doubles * sizeof(double);
 }
 
@@ -594,7 +594,7 @@ static int upload_tables(odl_model* m, Tables& T, int n_slot, const double* slot
   d.obs_src = di; d.y0_from_param = di + n_obs;
   d.n_slot = n_slot; d.n_obs = n_obs;
   d.stage_stride = (n_slot * m->n_out) | 1;
-  d.pad_ = 0; d.t0 = t0; d.sstot = sstot;
+  d.pad_ = 0; d.t0 = t0; d.sstot = sstot; d.inv_sstot = 1.0 / sstot;
   T.set = true;
   return 0;
 }

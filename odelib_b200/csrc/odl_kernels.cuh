@@ -117,11 +117,14 @@ __device__ __forceinline__ double odl_u53(unsigned int a, unsigned int b) {
 // ------------------------------------------------------------------------------------------------
 // shared-memory view of the data tables + per-thread staging
 // ------------------------------------------------------------------------------------------------
+// ODL_LOGTAB intervals of [1, 2) for odl_log below: (invc, -ln invc) per interval, 4 KB, filled by every CTA at start
 struct OdlShared {
-  double* slot_t; double* lnO; double* denom; double* lin; int* src; double* stage;
+  double* slot_t; double* lnO; double* denom; double* lin; int* src; double* stage; double* logtab;
 };
 __device__ __forceinline__ OdlShared odl_carve(double* base, const OdlData& D) {
   OdlShared S;
+  S.logtab = base;               // first: 16-byte aligned pairs
+  base += 2 * ODL_LOGTAB;
   S.slot_t = base;
   S.lnO = S.slot_t + D.n_slot;
   S.denom = S.lnO + D.n_obs;
@@ -133,11 +136,45 @@ __device__ __forceinline__ OdlShared odl_carve(double* base, const OdlData& D) {
 #ifndef ODL_HOST_HARNESS
 extern __shared__ double odl_smem[];   // dynamic shared memory of every kernel: tables, then staging
 __device__ __forceinline__ void odl_load_tables(const OdlShared& S, const OdlData& D) {
+  for (int i = threadIdx.x; i < ODL_LOGTAB; i += blockDim.x) {
+    const double invc = 1.0 / (1.0 + ((double)i + 0.5) * (1.0 / ODL_LOGTAB));
+    S.logtab[2 * i] = invc; S.logtab[2 * i + 1] = -log(invc);
+  }
   for (int i = threadIdx.x; i < D.n_slot; i += blockDim.x) S.slot_t[i] = D.slot_t[i];
   for (int i = threadIdx.x; i < D.n_obs; i += blockDim.x) {
     S.lnO[i] = D.obs_lnO[i]; S.denom[i] = D.obs_denom[i]; S.lin[i] = D.obs_lin[i]; S.src[i] = D.obs_src[i];
   }
   __syncthreads();
+}
+
+// ln(x) for the scorer (np.log at Framework.py:692).  CUDA's log() is ~80 instructions and ran 37 times per solve: 7.9 %
+// of the sweep kernel's instructions (profiles/r1f).  Table-driven instead (Tang / glibc style), ~20 instructions: x =
+// 2^k m, m in [1,2); interval i = top 8 mantissa bits, invc_i ~ 1/centre_i; r = m invc_i - 1 is EXACT up to one rounding
+// of a number below 2^-9 (FMA), and ln m = -ln(invc_i) + log1p(r) holds exactly for whatever invc_i is -- so the only
+// table error is the rounding of -ln(invc_i); log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5 (next term < 1e-17).
+// k ln2 in two pieces as in fdlibm (k ln2_hi is exact).  Error <= ~1 ulp of the result, like log() itself; arguments
+// that are not positive normal numbers (<= 0, denormal, inf, NaN: masked terms) take log().
+#ifndef ODL_FASTLOG
+#define ODL_FASTLOG 1
+#endif
+__device__ __forceinline__ double odl_log(const OdlShared& S, double x) {
+#if ODL_FASTLOG
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  if ((unsigned int)(hi - 0x00100000) < 0x7fe00000u) {
+    const double kd = (double)((hi >> 20) - 1023);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double2 tc = reinterpret_cast<const double2*>(S.logtab)[(hi >> 12) & (ODL_LOGTAB - 1)];
+    const double r = fma(m, tc.x, -1.0);
+    double t = fma(r, 0.2, -0.25);
+    t = fma(r, t, 0.3333333333333333);
+    t = fma(r, t, -0.5);
+    const double head = fma(kd, 6.93147180369123816490e-01, tc.y);
+    double tail = fma(r * r, t, r);
+    tail = fma(kd, 1.90821492927058770002e-10, tail);
+    return head + tail;
+  }
+#endif
+  return log(x);
 }
 
 // Warp-cooperative chi + R^2 of the system staged by lane `leader` (stats.py:41, :49-56).
@@ -149,7 +186,7 @@ __device__ __forceinline__ void odl_score(const OdlShared& S, const OdlData& D, 
   for (int o = lane; o < D.n_obs; o += 32) {
     const double pred = stage_leader[S.src[o]];
     if (pred_out) pred_out[o] = pred;
-    const double d = __dadd_rn(S.lnO[o], -log(pred));          // masked_invalid(O) - C
+    const double d = __dadd_rn(S.lnO[o], -odl_log(S, pred));   // masked_invalid(O) - C
     const double dd = __dmul_rn(d, d);                          // (...)**2   : masked when not finite
     const double den = S.denom[o];
     // / (2*S**2): masked on domain or non-finite.  A ZERO numerator sends the division through its out-of-line slow
@@ -180,7 +217,7 @@ __device__ __forceinline__ void odl_score_self(const OdlShared& S, const OdlData
   int k = 0;
   for (int o = 0; o < D.n_obs; ++o) {
     const double pred = stage[S.src[o]];
-    const double d = __dadd_rn(S.lnO[o], -log(pred));
+    const double d = __dadd_rn(S.lnO[o], -odl_log(S, pred));
     const double dd = __dmul_rn(d, d);
     const double den = S.denom[o];
     const double term = dd / den;
@@ -201,7 +238,7 @@ struct OdlStepper {
   double y[ODL_N];       // state at t
   double k1[ODL_N];      // f(t, y)  (FSAL)
   double t, h, tend;
-  float facold;
+  float lgfac;           // log2 of the PI controller's previous error (facold of dopri5.f), >= ODL_LG_FACMIN
   int nsteps;            // attempted steps
   int slot;              // next observation slot to produce
   int status;
@@ -231,6 +268,27 @@ __device__ __forceinline__ float odl_sqrt_approx(float x) {
 #else
 __device__ __forceinline__ float odl_sqrt_approx(float x) { return sqrtf(x); }
 #endif
+
+// 2^x on the SFU without exp2f()'s denormal rescaling (step-size factors only), and 1/x to full precision from the
+// 20-bit SFU seed + two Newton steps (5 instructions instead of the IEEE division's ~14; used for the dense-output
+// abscissa, where an ulp of theta is 1e-16 of a step)
+#ifndef ODL_HOST_HARNESS
+__device__ __forceinline__ float odl_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ double odl_rcp(double x) {
+  double r = odl_rcp_approx(x);
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+#else
+__device__ __forceinline__ float odl_ex2(float x) { return exp2f(x); }
+__device__ __forceinline__ double odl_rcp(double x) { return 1.0 / x; }
+#endif
+#define ODL_LG_FACMIN -13.287712f              /* log2(1e-4): floor of the PI controller's memory (Hairer: facold >= 1e-4) */
 
 // Butcher tableau of DOPRI5 (Hairer/Norsett/Wanner, dopri5.f) in constant memory: DFMA takes c[bank][offset]
 // operands directly, whereas literals are re-materialised with two UMOVs per use (13 % of the issued
@@ -269,7 +327,7 @@ ODL_UNROLL
   st.t = D.t0;
   st.tend = D.slot_t[D.n_slot - 1];
   st.nsteps = 0; st.slot = 0; st.status = ODL_OK; st.iasti = 0; st.nonsti = 0;
-  st.facold = 1e-4f; st.last_rejected = false;
+  st.lgfac = ODL_LG_FACMIN; st.last_rejected = false;
   odl_rhs(st.y, st.t, p, st.k1);
   const double span = st.tend - st.t;
   const double hmax = (O.hmax > 0.0) ? O.hmax : span;
@@ -377,10 +435,12 @@ ODL_UNROLL
   const float lg_err = __log2f(err);
   if (err <= 1.0f && finite_all) {
     // ---- accepted ----
-    const float inv = 0.9f * exp2f(0.04f * __log2f(st.facold) - (0.2f - 0.04f * 0.75f) * lg_err);
-    double hnew = h * (double)fminf(10.0f, fmaxf(0.2f, inv));   // growth <= 10, shrink <= 5
-    if (!(err > 0.f)) hnew = h * 10.0;
-    st.facold = fmaxf(err, 1e-4f);
+    const float inv = 0.9f * odl_ex2(0.04f * st.lgfac - (0.2f - 0.04f * 0.75f) * lg_err);
+    float fac = fminf(10.0f, fmaxf(0.2f, inv));                 // growth <= 10, shrink <= 5
+    if (!(err > 0.f)) fac = 10.0f;
+    if (st.last_rejected) fac = fminf(fac, 1.0f);               // no growth right after a rejection (fp32: no fp64 min)
+    double hnew = h * (double)fac;
+    st.lgfac = fmaxf(lg_err, ODL_LG_FACMIN);
     if (O.stiff_check && ((st.nsteps % 10) == 0 || st.iasti > 0)) {
       // Hairer's test: h * |k7 - k6| / |ynew - y6| approximates h * |lambda_max|
       double num = 0.0, den = 0.0;
@@ -416,7 +476,7 @@ ODL_UNROLL
         rc5[i] = h * (ODL_T(26) * st.k1[i] + ODL_T(27) * k3[i] + ODL_T(28) * k4[i] + ODL_T(29) * k5[i] +
                       ODL_T(30) * k6[i] + ODL_T(31) * k7[i]);
       }
-      const double rh = 1.0 / h;
+      const double rh = odl_rcp(h);
       do {
         const double th = (S.slot_t[st.slot] - t) * rh, th1 = 1.0 - th;
         double yi[ODL_N];
@@ -437,7 +497,6 @@ ODL_UNROLL
 ODL_UNROLL
     for (int i = 0; i < ODL_N; ++i) { st.y[i] = yn[i]; st.k1[i] = k7[i]; }
     st.t = tnew;
-    if (st.last_rejected) hnew = fmin(hnew, h);
     st.last_rejected = false;
     st.h = hnew;
     (void)truncated; (void)h_untrunc;
@@ -445,18 +504,21 @@ ODL_UNROLL
     // ---- rejected ----
     double hnew;
     if (err == err && finite_all && err < 3.0e38f)
-      hnew = h * (double)fmaxf(0.2f, 0.9f * exp2f(-(0.2f - 0.04f * 0.75f) * lg_err));
+      hnew = h * (double)fmaxf(0.2f, 0.9f * odl_ex2(-(0.2f - 0.04f * 0.75f) * lg_err));
     else hnew = 0.2 * h;                                        // NaN / overflow inside the step
     st.last_rejected = true;
     st.h = hnew;
     if (!(fabs(hnew) > 4.0 * 2.220446049250313e-16 * fmax(fabs(t), fabs(st.tend)))) st.status = ODL_HUNDERFLOW;
   }
-  if (st.nsteps >= O.max_steps && st.slot < D.n_slot && st.status == ODL_OK) st.status = ODL_MAXSTEPS;
-  // capped pass of the cohort sweep: a system whose progress after early_check_steps attempts projects to more
-  // than max_steps in total leaves now instead of burning the rest of its budget (its warp waits for it)
-  if (O.early_check_steps > 0 && st.nsteps == O.early_check_steps && st.slot < D.n_slot && st.status == ODL_OK &&
-      (double)st.nsteps * (st.tend - D.t0) > (double)O.max_steps * (st.t - D.t0))
-    st.status = ODL_MAXSTEPS;
+  // Step budget.  One compare per attempt until the first of the two checks is due: the cap itself, and -- capped pass
+  // of the cohort sweep -- the projection check: a system whose progress after early_check_steps attempts projects to
+  // more than max_steps in total leaves now instead of burning the rest of its budget (its warp waits for it).
+  const int first_check = (O.early_check_steps > 0 && O.early_check_steps < O.max_steps) ? O.early_check_steps : O.max_steps;
+  if (st.nsteps >= first_check && st.slot < D.n_slot && st.status == ODL_OK) {
+    if (st.nsteps >= O.max_steps) st.status = ODL_MAXSTEPS;
+    else if (st.nsteps == O.early_check_steps && (double)st.nsteps * (st.tend - D.t0) > (double)O.max_steps * (st.t - D.t0))
+      st.status = ODL_MAXSTEPS;
+  }
 }
 
 // slots at (or before) the start time take the initial state (odeint returns y0 at times[0])
@@ -1500,7 +1562,7 @@ __device__ __forceinline__ void odl_sweep_body(const OdlData& D, const OdlOpts& 
   // a defined state for lanes without a system: in the DOPRI5 kernel every lane runs the step code (see (C)), and a
   // lane with slot == n_slot writes nothing
   st.status = ODL_OK; st.nsteps = 0; st.slot = D.n_slot; st.iasti = 0; st.nonsti = 0;
-  st.t = 0.0; st.h = 0.0; st.tend = 0.0; st.facold = 1.f; st.last_rejected = false;
+  st.t = 0.0; st.h = 0.0; st.tend = 0.0; st.lgfac = 0.f; st.last_rejected = false;
 ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) { st.y[i] = 0.0; st.k1[i] = 0.0; }
 ODL_UNROLL
@@ -1541,7 +1603,7 @@ ODL_UNROLL
       odl_score(S, D, S.stage + (size_t)((threadIdx.x & ~31) + L) * D.stage_stride, lane, pred_out, chi, ss, nv);
       if (lane == L) {
         int status = fin_status;
-        double r2 = 1.0 - ss / D.sstot;
+        double r2 = fma(-ss, D.inv_sstot, 1.0);                   // 1 - ssres/sstot (stats.py:56), reciprocal from the host
         if (status != ODL_OK) { chi = __longlong_as_double(0x7ff8000000000000LL); r2 = chi; }
         else if (nv == 0) { chi = __longlong_as_double(0x7ff8000000000000LL); status |= ODL_ALLMASKED; }
         A.chi[row] = chi;                                        // r2 / status / nsteps only when the caller asked for them
@@ -1877,7 +1939,7 @@ ODL_UNROLL
     if (valid) {
       double chi, ss; int nv;
       odl_score_self(S, D, my_stage, chi, ss, nv);
-      if (st.status == ODL_OK) { my_chi = (nv > 0) ? chi : nan; my_r2 = 1.0 - ss / D.sstot; }   // nv == 0: np.ma.masked
+      if (st.status == ODL_OK) { my_chi = (nv > 0) ? chi : nan; my_r2 = fma(-ss, D.inv_sstot, 1.0); }   // nv == 0: np.ma.masked
     }
     if (apriori) {
       // the starting point's own chi: no decision, no iteration consumed
@@ -2090,7 +2152,7 @@ __device__ __forceinline__ void odl_coop_rhs(const double (&yl)[ODL_C], double t
 struct OdlCoopStepper {
   double y[ODL_C], k1[ODL_C];
   double t, h, tend;
-  float facold;
+  float lgfac;
   int nsteps, slot, status;
   bool last_rejected;
 };
@@ -2128,7 +2190,7 @@ __device__ __forceinline__ void odl_coop_init(OdlCoopStepper& st, const OdlGroup
   st.t = D.t0;
   st.tend = D.slot_t[D.n_slot - 1];
   st.nsteps = 0; st.slot = 0; st.status = ODL_OK;
-  st.facold = 1e-4f; st.last_rejected = false;
+  st.lgfac = ODL_LG_FACMIN; st.last_rejected = false;
   odl_coop_rhs(st.y, st.t, G, st.k1);
   const double span = st.tend - st.t;
   const double hmax = (O.hmax > 0.0) ? O.hmax : span;
@@ -2214,10 +2276,12 @@ __device__ __forceinline__ void odl_coop_attempt(OdlCoopStepper& st, const OdlGr
   const float err = odl_sqrt_approx((float)errsq * (1.0f / ODL_N));
   const float lg_err = __log2f(err);
   if (err <= 1.0f && finite_all) {
-    const float inv = 0.9f * exp2f(0.04f * __log2f(st.facold) - (0.2f - 0.04f * 0.75f) * lg_err);
-    double hnew = h * (double)fminf(10.0f, fmaxf(0.2f, inv));
-    if (!(err > 0.f)) hnew = h * 10.0;
-    st.facold = fmaxf(err, 1e-4f);
+    const float inv = 0.9f * odl_ex2(0.04f * st.lgfac - (0.2f - 0.04f * 0.75f) * lg_err);
+    float fac = fminf(10.0f, fmaxf(0.2f, inv));
+    if (!(err > 0.f)) fac = 10.0f;
+    if (st.last_rejected) fac = fminf(fac, 1.0f);
+    double hnew = h * (double)fac;
+    st.lgfac = fmaxf(lg_err, ODL_LG_FACMIN);
     const double tnew = last ? st.tend : tph;
     if (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew) {
       double rc2[ODL_C], rc3[ODL_C], rc4[ODL_C], rc5[ODL_C];
@@ -2229,7 +2293,7 @@ __device__ __forceinline__ void odl_coop_attempt(OdlCoopStepper& st, const OdlGr
         rc5[i] = h * (ODL_T(26) * st.k1[i] + ODL_T(27) * k3[i] + ODL_T(28) * k4[i] + ODL_T(29) * k5[i] +
                       ODL_T(30) * k6[i] + ODL_T(31) * k7[i]);
       }
-      const double rh = 1.0 / h;
+      const double rh = odl_rcp(h);
       do {
         const double th = (S.slot_t[st.slot] - t) * rh, th1 = 1.0 - th;
         double yi[ODL_C];
@@ -2242,13 +2306,12 @@ __device__ __forceinline__ void odl_coop_attempt(OdlCoopStepper& st, const OdlGr
 #pragma unroll
     for (int i = 0; i < ODL_C; ++i) { st.y[i] = yn[i]; st.k1[i] = k7[i]; }
     st.t = tnew;
-    if (st.last_rejected) hnew = fmin(hnew, h);
     st.last_rejected = false;
     st.h = hnew;
   } else {
     double hnew;
     if (err == err && finite_all && err < 3.0e38f)
-      hnew = h * (double)fmaxf(0.2f, 0.9f * exp2f(-(0.2f - 0.04f * 0.75f) * lg_err));
+      hnew = h * (double)fmaxf(0.2f, 0.9f * odl_ex2(-(0.2f - 0.04f * 0.75f) * lg_err));
     else hnew = 0.2 * h;
     st.last_rejected = true;
     st.h = hnew;
@@ -2264,7 +2327,7 @@ __device__ __forceinline__ void odl_coop_score(const OdlShared& S, const OdlData
   for (int o = G.sub; o < D.n_obs; o += ODL_G) {
     const double pred = G.stage[S.src[o]];
     if (pred_out) pred_out[o] = pred;
-    const double d = __dadd_rn(S.lnO[o], -log(pred));
+    const double d = __dadd_rn(S.lnO[o], -odl_log(S, pred));
     const double dd = __dmul_rn(d, d);
     const double den = S.denom[o];
     const double term = dd / den;
@@ -2316,7 +2379,7 @@ odl_sweep_coop_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
     odl_coop_score(S, D, G, pred_out, chi, ss, nv);
     if (G.sub == 0) {
       int status = st.status;
-      double r2 = 1.0 - ss / D.sstot;
+      double r2 = fma(-ss, D.inv_sstot, 1.0);
       if (status != ODL_OK) { chi = __longlong_as_double(0x7ff8000000000000LL); r2 = chi; }
       else if (nv == 0) { chi = __longlong_as_double(0x7ff8000000000000LL); status |= ODL_ALLMASKED; }
       A.chi[row] = chi;
@@ -2409,7 +2472,7 @@ odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
       while (st.slot < D.n_slot && st.status == ODL_OK) odl_coop_attempt(st, G, S, D, O);
       double chi, ss; int nv;
       odl_coop_score(S, D, G, nullptr, chi, ss, nv);
-      if (st.status == ODL_OK) { my_chi = (nv > 0) ? chi : nan; my_r2 = 1.0 - ss / D.sstot; }
+      if (st.status == ODL_OK) { my_chi = (nv > 0) ? chi : nan; my_r2 = fma(-ss, D.inv_sstot, 1.0); }
     }
     if (apriori) {
       if (valid && lead) {
