@@ -52,9 +52,11 @@ enum { ODL_MEM_HOST = 0, ODL_MEM_DEVICE = 1 };
 enum { ODL_SOLVER_DOPRI5 = 0, ODL_SOLVER_ROS23 = 1, ODL_SOLVER_AUTO = 2, ODL_SOLVER_RADAU5 = 3, ODL_SOLVER_BDF = 4 };
 /* odl_solver_opts.auto_flags */
 enum { ODL_AUTO_UNORDERED = 1,   /* process rows in input order (no cost ordering) */
-       ODL_AUTO_CONCURRENT = 2,  /* run the stiff pass beside the DOPRI5 pass instead of after it (measured slower) */
-       ODL_AUTO_ONE_PIECE = 4    /* ODL_MEM_HOST: upload theta in one piece before anything runs (default: two pieces,
-                                    the second travelling while the first is swept) */ };
+       ODL_AUTO_CONCURRENT = 2,  /* run the stiff pass BESIDE the DOPRI5 pass on SMs of its own whatever the table size
+                                    (default: from 262,144 rows on) */
+       ODL_AUTO_ONE_PIECE = 4,   /* ODL_MEM_HOST: upload theta in one piece before anything runs (default: two pieces,
+                                    the second travelling while the first is swept) */
+       ODL_AUTO_SEQUENTIAL = 8   /* run the stiff pass AFTER the DOPRI5 pass (single-warp CTAs over every SM) */ };
 enum { ODL_RNG_PHILOX = 0, ODL_RNG_HOST_STREAMS = 1, ODL_RNG_FORCED = 2 };
 /* per-system status words */
 enum { ODL_ST_OK = 0, ODL_ST_MAXSTEPS = 1, ODL_ST_NONFINITE = 2, ODL_ST_HUNDERFLOW = 3, ODL_ST_STIFF = 4,
@@ -86,7 +88,8 @@ typedef struct odl_solver_opts {
   int stiff_check;     /* DOPRI5: detect stiffness and stop with ODL_ST_STIFF */
   int stiff_min_steps; /* ... only while more than this many steps of the current size remain (0 = 2000) */
   int pass_cap0;       /* ODL_SOLVER_AUTO: step cap of the first DOPRI5 pass (0 = 512) */
-  int tail_warps;      /* ODL_AUTO_CONCURRENT: single-warp CTAs of the stiff pass per SM beside the DOPRI5 pass (0 = 2) */
+  int tail_warps;      /* ODL_SOLVER_AUTO: SMs set aside for the stiff pass when it runs beside the DOPRI5 pass (one CTA
+                          of 8 warps each; 0 = a quarter of them) */
   int tail_solver;     /* ODL_SOLVER_AUTO: stepper of the pass over what DOPRI5 did not finish:
                           0 = default (ODL_SOLVER_BDF), or ODL_SOLVER_RADAU5 */
   int early_check_steps; /* ODL_SOLVER_AUTO: the first pass drops a system after this many attempts when its progress
@@ -207,12 +210,15 @@ int odl_reference_streams(const unsigned int* seeds, int n_chain, int n_iter, in
    model, measured with CUDA events on the launching stream; blocks until they have completed */
 int odl_model_last_kernel_ms(odl_model* m, float* ms);
 /* the same split for the last ODL_SOLVER_AUTO sweep: ms3[0] cost ordering (of the first piece), ms3[1] DOPRI5 bulk
-   pass, ms3[2] stiff pass -- with ODL_AUTO_CONCURRENT: what it still needed after the bulk pass had ended
+   pass, ms3[2] stiff pass -- when it runs beside the bulk pass: what it still needed after the bulk pass had ended
    (single-pass calls: ms3[0]) */
 int odl_model_last_pass_ms(odl_model* m, float* ms3);
 /* development aid: copies the first `count` ints of the device-side counter block of the last odl_sweep
    ([0] work counter, [16] feed count, [32] feed ticket, [48] warps entered, [64] warps left, [80] watchdog) */
 int odl_debug_counters(odl_model* m, int* out, int count);
+/* development aid: with ODL_TIMELINE=1 in the environment and kernels built with -DODL_TIMELINE=1 (ODL_KERNEL_DEFINES),
+   an AUTO sweep records per feed entry %globaltimer (ns) at deferral, start and end of its stiff solve */
+int odl_debug_timeline(odl_model* m, long long* out, long long entries);
 /* number of kernel launches issued by this library in this process */
 long long odl_launch_count(void);
 

@@ -65,63 +65,46 @@ NO_SPILL = ("odl_sweep_kernel", "odl_mcmc_kernel", "odl_traj_kernel", "odl_sweep
             "odl_order_scatter_kernel")
 
 
-def _check_specs():
-    """(label, ode, n, P, groups, extra defines): the demo models with every kernel, and the two n > 8 workloads of
-    BASELINE configs 3 / 5 with their cooperative kernels (the thread-per-system kernels keep such systems in local
-    memory by design and are not the default there)."""
-    from odelib_b200 import demo_models
-    specs = []
-    for name in ("zero_i", "one_i", "two_i"):
-        f, n, P, groups = demo_models.MODELS[name]
-        mb = 4 if n <= 4 else 3
-        specs.append((name, f, n, P, groups, [f"-DODL_MINBLOCKS={mb}"]))
-    f = demo_models.n_class(10)
-    specs.append(("n_class_10", f, 12, 5, [tuple(range(11)), (11,)], ["-DODL_MINBLOCKS=1", "-DODL_BLOCK=64", "-DODL_G=4", "-DODL_UNIT=11"]))
-    specs.append(("n_class_10", f, 12, 5, [tuple(range(11)), (11,)], ["-DODL_MINBLOCKS=1", "-DODL_BLOCK=64", "-DODL_G=4", "-DODL_UNIT=12"]))
-    f, n, P, groups = demo_models.network(5, 5)
-    specs.append(("network_5x5", f, n, P, groups, ["-DODL_MINBLOCKS=1", "-DODL_BLOCK=64", "-DODL_G=8", "-DODL_UNIT=11"]))
-    specs.append(("network_5x5", f, n, P, groups, ["-DODL_MINBLOCKS=1", "-DODL_BLOCK=64", "-DODL_G=8", "-DODL_UNIT=12"]))
-    return specs
+def parse_ptxas_log(log):
+    """NVRTC program log (compiled with --ptxas-options=-v) -> {kernel: {regs, spill, stack}}."""
+    info, cur = {}, None
+    for line in log.splitlines():
+        mm = re.search(r"Compiling entry function '(\w+)'", line)
+        if mm:
+            cur = mm.group(1)
+        mm = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", line)
+        if mm and cur:
+            info.setdefault(cur, {}).update(stack=int(mm.group(1)), spill=int(mm.group(2)) + int(mm.group(3)))
+        mm = re.search(r"Used (\d+) registers", line)
+        if mm and cur:
+            info.setdefault(cur, {})["regs"] = int(mm.group(1))
+    return info
 
 
-def check_kernels(outdir=None, strict=True):
-    """nvcc -Xptxas -v of the integrator kernels for traced models -> {model: {kernel: {regs, spill, stack}}}.
+def check_kernels(strict=True, models=None):
+    """Registers / spill bytes / stack of every kernel AS THE LIBRARY COMPILES IT: NVRTC for sm_100a with ptxas -v, through
+    odl_model_create(compile_only) -- the very cubins the GPU box runs (nvcc's front end allocates differently: it
+    showed 0 B where NVRTC spilled 8 B).  -> {model: {kernel: {regs, spill, stack}}}.
 
     strict: raise when a kernel of the default paths (NO_SPILL) spills registers."""
     sys.path.insert(0, ROOT)
-    from concurrent.futures import ThreadPoolExecutor
-    from odelib_b200.tracer import trace
-    outdir = outdir or os.path.join(HERE, "_check")
-    os.makedirs(outdir, exist_ok=True)
-
-    def one(k, spec):
-        name, f, n, P, groups, defs = spec
-        src = trace(f, n, P).cuda_source(fmad=True, observe_groups=groups)
-        cu = os.path.join(outdir, f"{name}_{k}.cu")
-        open(cu, "w").write(src + '#include "odl_kernels.cuh"\n')
-        cmd = [NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-I" + HERE, "-DODL_DENSE=1", "-DODL_Y0P=0", *defs,
-               "-Xptxas", "-v", "-cubin", "-o", os.path.join(outdir, f"{name}_{k}.cubin"), cu]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode != 0:
-            raise RuntimeError(f"nvcc failed for {name}:\n{res.stderr}")
-        info, cur = {}, None
-        for line in res.stderr.splitlines():
-            mm = re.search(r"Compiling entry function '(\w+)'", line)
-            if mm:
-                cur = mm.group(1)
-            mm = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", line)
-            if mm and cur:
-                info.setdefault(cur, {}).update(stack=int(mm.group(1)), spill=int(mm.group(2)) + int(mm.group(3)))
-            mm = re.search(r"Used (\d+) registers", line)
-            if mm and cur:
-                info.setdefault(cur, {})["regs"] = int(mm.group(1))
-        return name, info
-
-    specs = _check_specs()
+    import tempfile
+    from odelib_b200 import demo_models, engine
+    specs = []
+    for name in ("zero_i", "one_i", "two_i"):
+        f, n, P, groups = demo_models.MODELS[name]
+        specs.append((name, f, n, P, groups, 1))
+    specs.append(("n_class_10", demo_models.n_class(10), 12, 5, [tuple(range(11)), (11,)], 2))
+    f, n, P, groups = demo_models.network(5, 5)
+    specs.append(("network_5x5", f, n, P, groups, 2))
     report = {}
-    with ThreadPoolExecutor(max_workers=min(len(specs), os.cpu_count() or 1)) as ex:
-        for name, info in ex.map(lambda a: one(*a), enumerate(specs)):
-            report.setdefault(name, {}).update(info)
+    for name, f, n, P, groups, mode in specs:
+        if models and name not in models:
+            continue
+        with tempfile.TemporaryDirectory() as tmp:
+            m = engine.DeviceModel(f, n, P, groups, compile_only=mode, cache_dir=tmp)
+            report[name] = parse_ptxas_log(m.build_log)
+            m.close()
     bad = [(m, k, v["spill"]) for m, ks in report.items() for k, v in ks.items() if k in NO_SPILL and v.get("spill", 0) > 0]
     if strict and bad:
         raise RuntimeError("register spills in default-path kernels: " + ", ".join(f"{m}:{k} {b} B" for m, k, b in bad))

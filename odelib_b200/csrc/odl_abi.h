@@ -58,14 +58,14 @@ struct OdlSweepArgs {
   unsigned long long* counter;   // work counter, zeroed by the host before launch
   int* defer_list[2];            // optional: rows that stopped with [0] ODL_MAXSTEPS, [1] ODL_STIFF are appended
   int* defer_count[2];           //           here for a later pass (device-side lists, no host round trip)
-  // Coupling of the bulk pass (producer) and the stiff pass that runs BESIDE it (consumer), ODL_SOLVER_AUTO:
-  int* prod_started;             // producer: +1 per warp on entry ...
-  int* prod_exited;              //           ... and on exit (after its last deferral is visible)
-  const unsigned long long* prod_counter;  // consumer: the producer's work counter and item count; the feed is
-  long long prod_n;                        //   complete once the counter is dry and every warp that entered has left
+  // The stiff pass BESIDE the bulk pass (ODL_SOLVER_AUTO on SMs of its own): consumer of a feed that is still growing
   unsigned long long* feed_ticket;         // consumer mode switch: next unclaimed entry of index[] (entries of index[]
-                                           //   start as -1 and land while the producer runs; *index_count grows)
-  int* watchdog;                           // consumer: incremented when a warp gave up waiting for the producer
+                                           //   start as -1 and land while the bulk pass runs; *index_count grows; the
+                                           //   consumer overwrites an entry with -2 when it takes it)
+  const int* feed_done;                    // set to 1 by odl_feed_done_kernel after the last bulk launch of the sweep
+  int* watchdog;                           // consumer: incremented when a warp gave up waiting for the feed
+  long long* timeline;                     // development (kernels built with -DODL_TIMELINE=1, else unused): per feed
+                                           //   entry %globaltimer at [0] deferral, [1] start and [2] end of its stiff solve
 };
 
 // Cost ordering of a sweep (ODL_SOLVER_AUTO): key = |J(t0, y0, theta)|_inf (t_end - t0), quarter-octave bins,

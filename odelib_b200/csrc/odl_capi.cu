@@ -160,7 +160,7 @@ struct odl_model {
   CUfunction k_sweep_ros = nullptr, k_mcmc_ros = nullptr, k_mcmc_auto = nullptr;
   CUfunction k_sweep_radau = nullptr, k_mcmc_radau = nullptr;
   CUfunction k_sweep_bdf = nullptr, k_mcmc_bdf = nullptr;
-  CUfunction k_order_key = nullptr, k_order_scan = nullptr, k_order_scatter = nullptr;
+  CUfunction k_order_key = nullptr, k_order_scan = nullptr, k_order_scatter = nullptr, k_feed_done = nullptr;
   CUfunction k_sweep_coop = nullptr, k_mcmc_coop = nullptr;   // n > 8 only: several lanes per system
   Tables data, grid;
   DevBuf counter;
@@ -169,7 +169,8 @@ struct odl_model {
   cudaEvent_t evp[2] = {nullptr, nullptr};   // between the cohort passes of an AUTO sweep
   cudaEvent_t ev_aux = nullptr, ev_fork = nullptr;
   cudaEvent_t ev_chunk[3] = {nullptr, nullptr, nullptr};   // host-memory sweeps: theta arrives in pieces on the helper stream
-  cudaStream_t aux = nullptr;                // helper stream: the stiff pass beside the DOPRI5 pass
+  cudaStream_t aux = nullptr;                // helper stream: theta pieces of a host-memory sweep
+  cudaStream_t aux2 = nullptr;               // helper stream: the stiff pass beside the DOPRI5 pass
   int n_pass = 0;
   bool timed = false;
   bool coop_model() const { return n_state > 8; }
@@ -190,6 +191,15 @@ struct DeviceGuard {
 #define ODL_ON_DEVICE(m)                                                                                   \
   DeviceGuard guard_((m)->device);                                                                         \
   if (guard_.err != cudaSuccess) return fail(ODL_ENODEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(guard_.err))
+
+// One call in flight per handle (scratch buffers, counter block, events and helper streams are per model): a call on
+// another stream than the previous one -- or a host-memory call right after a device-memory call that has not finished
+// -- is ordered behind it ON THE DEVICE (no host synchronisation): the caller's stream waits for the event that closed
+// the previous call; the helper streams are forked from the caller's stream after that.
+static int serialize_after_previous_call(odl_model* m, cudaStream_t s) {
+  if (m->timed) ODL_CUDA(cudaStreamWaitEvent(s, m->ev1, 0));
+  return 0;
+}
 
 // cooperative kernels (n > 8): default lanes per system, as odl_kernels.cuh's ODL_G
 static int coop_lanes_default(int n_state) { return n_state <= 16 ? 4 : (n_state <= 64 ? 8 : (n_state <= 128 ? 16 : 32)); }
@@ -317,6 +327,7 @@ static const KernelSlot kKernels[] = {
     {"odl_mcmc_radau5_kernel", &odl_model::k_mcmc_radau, U_MCMC_RADAU}, {"odl_sweep_bdf_kernel", &odl_model::k_sweep_bdf, U_SWEEP_BDF},
     {"odl_mcmc_bdf_kernel", &odl_model::k_mcmc_bdf, U_MCMC_BDF}, {"odl_order_key_kernel", &odl_model::k_order_key, U_ORDER},
     {"odl_order_scan_kernel", &odl_model::k_order_scan, U_ORDER}, {"odl_order_scatter_kernel", &odl_model::k_order_scatter, U_ORDER},
+    {"odl_feed_done_kernel", &odl_model::k_feed_done, U_ORDER},
     {"odl_sweep_coop_kernel", &odl_model::k_sweep_coop, U_SWEEP_COOP}, {"odl_mcmc_coop_kernel", &odl_model::k_mcmc_coop, U_MCMC_COOP}};
 
 // compiled + loaded on the model's device + its CUfunctions fetched
@@ -371,7 +382,7 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
   if (m->coop == 0) m->coop = coop_lanes_default(n_state);
   if (m->coop != 4 && m->coop != 8 && m->coop != 16 && m->coop != 32) { delete m; return fail(ODL_EINVAL, "coop_lanes must be 4, 8, 16 or 32"); }
   m->src = model_cuda_src;
-  m->opt = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device",
+  m->opt = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device", "--ptxas-options=-v",
             "-DODL_BLOCK=" + std::to_string(m->block), "-DODL_MINBLOCKS=" + std::to_string(m->minblocks),
             "-DODL_DENSE=" + std::to_string(m->dense), "-DODL_Y0P=" + std::to_string(m->y0p)};
   if (m->n_state > 8) m->opt.push_back("-DODL_G=" + std::to_string(m->coop));
@@ -431,7 +442,8 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
       cudaEventCreateWithFlags(&m->ev_chunk[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_chunk[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_chunk[2], cudaEventDisableTiming) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking) != cudaSuccess)
+      cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&m->aux2, cudaStreamNonBlocking) != cudaSuccess)
     return bail(fail(ODL_ECUDA, "cudaEventCreate / cudaStreamCreate failed"));
   if ((rc = m->counter.ensure(8192))) return bail(rc);
   m->on_gpu = true;
@@ -457,6 +469,7 @@ extern "C" int odl_model_destroy(odl_model* m) {
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   for (auto& e : m->ev_chunk) if (e) cudaEventDestroy(e);
   if (m->aux) cudaStreamDestroy(m->aux);
+  if (m->aux2) cudaStreamDestroy(m->aux2);
   if (m->on_gpu && prev >= 0 && prev != m->device) cudaSetDevice(prev);
   delete m;
   return 0;
@@ -633,8 +646,16 @@ static void fill_opts(OdlOpts& o, const odl_solver_opts* so) {
 }
 
 static int launch(odl_model* m, CUfunction f, unsigned grid, unsigned block, size_t smem, cudaStream_t s, void** params) {
+  if (!f) return fail(ODL_ECUDA, "internal: launch of a kernel whose unit is not loaded");
   if (smem > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
-  ODL_CU(g_drv.LaunchKernel(f, grid, 1, 1, block, 1, 1, (unsigned)smem, (CUstream)s, params, nullptr));
+  CUresult r = g_drv.LaunchKernel(f, grid, 1, 1, block, 1, 1, (unsigned)smem, (CUstream)s, params, nullptr);
+  if (r != CUDA_SUCCESS) {
+    const char* name = "?";
+    for (const KernelSlot& k : kKernels) if (m->*(k.fn) == f) name = k.name;
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuLaunchKernel(%s, grid %u, block %u, smem %zu): ", name, grid, block, smem);
+    return fail(ODL_ECUDA, buf + cu_err(r));
+  }
   g_launches.fetch_add(1);
   return 0;
 }
@@ -701,6 +722,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   if (solver == ODL_SOLVER_AUTO && n > 2147483647LL)
     return fail(ODL_EINVAL, "odl_sweep: ODL_SOLVER_AUTO orders rows through 32-bit indices; split tables beyond 2^31-1 rows");
   cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = serialize_after_previous_call(m, s))) return rc;
   Staging st{m, s, 0, mem};
   OdlSweepArgs A{};
   // Host-memory ODL_SOLVER_AUTO sweep of a large table: theta travels in two pieces on the helper stream and the second
@@ -708,7 +730,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   // stiff pass runs once over what both leave).  Rows are independent, so the pieces change nothing in the results.
   const int auto_flags = so ? so->auto_flags : 0;
   const bool chunked = mem == ODL_MEM_HOST && solver == ODL_SOLVER_AUTO && n >= (1 << 18) && !m->coop_model() &&
-                       !(auto_flags & (ODL_AUTO_UNORDERED | ODL_AUTO_CONCURRENT | ODL_AUTO_ONE_PIECE));
+                       !(auto_flags & (ODL_AUTO_UNORDERED | ODL_AUTO_ONE_PIECE));
   if (chunked) {
     DevBuf& bt = m->scratch[st.next++];
     if ((rc = bt.ensure((size_t)n * m->n_param * sizeof(double)))) return rc;
@@ -765,21 +787,24 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       if ((rc = go_coop(s, O, A, n))) return rc;               // n > 8: several lanes per system
     } else if ((rc = go(s, f1, O, A, warp_cta ? 32u : pick_block(D, m->block), n))) return rc;
   } else {
-    // Cost-ordered bulk pass, then the stiff pass (no host synchronisation; list lengths stay on the device):
+    // Cost-ordered bulk pass + the stiff pass (no host synchronisation; list lengths stay on the device):
     //   order    key = |J(t0,y0,theta)|_inf (t_end-t0) per system, quarter-octave bins, highest first -> index[]
     //            (Spearman 0.73 with the DOPRI5 step count on the demo priors; the 1 % longest systems all sit in
     //            the first tenth).  Long systems start first, so the launch does not end on a few stragglers, and
     //            the ones DOPRI5 cannot finish are found while most of the sweep is still ahead.
     //   bulk     DOPRI5, every system in that order, at most cap0 attempted steps (a check at 3/4 of them drops systems
     //            whose progress projects beyond the cap; Hairer's test drops the ones it calls stiff) -> feed list
-    //   stiff    variable-order BDF (or Radau5) over the feed list, single-warp CTAs, as many as fit.  It is bound by
-    //            the latency of its longest systems (~1000 sequential steps), not by throughput.
-    //            ODL_AUTO_CONCURRENT runs it BESIDE the bulk pass instead: a persistent grid of tail_warps CTAs
-    //            per SM, launched first on a helper stream, takes entries as they land, and the bulk grid is sized
-    //            to what fits next to it.  Measured on B200 (1M two_i prior draws): 6.5 ms against 5.25 ms for one
-    //            pass after the other -- a BDF warp holds 7.7k registers, the two consumer warps per SM that leave
-    //            room for three of the four bulk CTAs have to run three rounds, and every BDF step gets slower
-    //            next to twelve DOPRI5 warps.  Kept as an option; the default is sequential.
+    //   stiff    variable-order BDF (or Radau5) over the feed list.  It is bound by the LATENCY of its longest systems
+    //            (~900 sequential steps of ~600 dependent instructions, 1.4 ms), not by throughput, so it runs BESIDE
+    //            the bulk pass on SMs of its own: `tail_sms` CTAs of 8 warps, launched first on the helper stream,
+    //            each asking for so much shared memory that no bulk CTA fits next to it (sharing SMs was measured in
+    //            round 1: every BDF step slows down next to twelve DOPRI5 warps, 6.5 ms against 5.0 ms one after the
+    //            other); the bulk grid covers the remaining SMs.  The consumer takes feed entries as they land; a
+    //            one-thread kernel after the last bulk launch marks the feed complete.  A last launch of the stiff
+    //            kernel over the feed list picks up whatever the consumer did not finish (normally nothing: entries
+    //            it finished are marked) -- so the results never depend on the consumer having kept up, and a consumer
+    //            that gave up (watchdog) costs time, not rows.  Small sweeps (and ODL_AUTO_SEQUENTIAL) run the stiff
+    //            pass after the bulk pass on single-warp CTAs spread over every SM, as in round 1.
     // Step counts are heavy-tailed (two_i prior: median 56, mean 103, p99.9 3200, max > 1e5 for DOPRI5).
     DevBuf& bidx = m->scratch[st.next++];
     DevBuf& bfeed = m->scratch[st.next++];
@@ -791,11 +816,19 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     int* feed = static_cast<int*>(bfeed.p);
     const int flags = so ? so->auto_flags : 0;
     const bool ordered = !(flags & ODL_AUTO_UNORDERED);
-    const bool concurrent = (flags & ODL_AUTO_CONCURRENT) != 0 && !m->coop_model();
+    if (getenv("ODL_TIMELINE")) {                                // development: see OdlSweepArgs.timeline
+      DevBuf& bt = m->scratch[20];
+      if ((rc = bt.ensure((size_t)n * 3 * sizeof(long long)))) return rc;
+      ODL_CUDA(cudaMemsetAsync(bt.p, 0, (size_t)n * 3 * sizeof(long long), s));
+      A.timeline = static_cast<long long*>(bt.p);
+    }
+    const bool coop_bulk = m->coop_model();                      // n > 8: the bulk pass is the cooperative kernel (go_coop)
+    const bool beside = !coop_bulk && !(flags & ODL_AUTO_SEQUENTIAL) && ((flags & ODL_AUTO_CONCURRENT) || n >= (1 << 18));
     const int cap0 = so && so->pass_cap0 > 0 ? so->pass_cap0 : 512;
     CUfunction k_tail = tail_solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau : m->k_sweep_bdf;
-    // counter block (zeroed above): [0] bulk work counter, [64] feed count, [128] feed ticket, [192] warps entered,
-    // [256] warps left, [1024] hist[256], [2048] cursor[256]
+    // counter block (zeroed above): [0] bulk work counter (+ [384], [448] for later pieces), [64] feed count,
+    // [128] feed ticket, [192] feed-complete flag, [256] work counter of the pick-up launch, [320] watchdog,
+    // [1024] hist[256], [2048] cursor[256] (per piece)
     ODL_CUDA(cudaMemsetAsync(feed, 0xFF, (size_t)n * sizeof(int), s));
     // ordering of one piece [lo, hi) of the table -> index[lo..hi) (global row numbers)
     auto order_piece = [&](long long lo, long long hi, int piece) -> int {
@@ -821,45 +854,41 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     long long cut[4] = {0, n, n, n};
     if (chunked) cut[1] = ((n / 2 + 1023) / 1024) * 1024;
     if (chunked) {
+      ODL_CUDA(cudaEventRecord(m->ev_fork, s));                  // behind the previous call on this handle
+      ODL_CUDA(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
       for (int c = 0; c < n_piece; ++c) {
         ODL_CUDA(cudaMemcpyAsync(const_cast<double*>(A.theta) + cut[c] * m->n_param, theta + cut[c] * m->n_param,
                                  (size_t)(cut[c + 1] - cut[c]) * m->n_param * sizeof(double), cudaMemcpyHostToDevice, m->aux));
         ODL_CUDA(cudaEventRecord(m->ev_chunk[c], m->aux));
       }
-      ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[0], 0));
     }
-    if (ordered && (rc = order_piece(0, cut[1], 0))) return rc;
-    ODL_CUDA(cudaEventRecord(m->evp[1], s));
     const unsigned block0 = pick_block(D, m->block);
     const size_t smem0 = smem_bytes(D, (int)block0), smem_t = smem_bytes(D, 32);
-    const bool coop_bulk = m->coop_model();                      // n > 8: the bulk pass is the cooperative kernel (go_coop)
     if (!coop_bulk && smem0 > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(m->k_sweep, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem0));
     if (smem_t > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(k_tail, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem_t));
-    // both kernels must ask for the same L1/shared split, or no SM can hold CTAs of both at once (the second kernel
-    // would wait for the first to drain: measured -- the bulk pass started only after the consumers had given up)
+    // both kernels ask for the same L1/shared split (kernels with different carve-outs cannot share an SM, and a
+    // carve-out switch drains the SM first)
     if (!coop_bulk) ODL_CU(g_drv.FuncSetAttribute(m->k_sweep, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100));
     ODL_CU(g_drv.FuncSetAttribute(k_tail, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100));
-    int per_sm0 = 1, per_sm_t = 0, regs0 = 0, regs_t = 0;
+    int per_sm0 = 1, per_sm_t = 0;
     if (!coop_bulk) ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, m->k_sweep, (int)block0, smem0));
     ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, k_tail, 32, smem_t));
-    if (!coop_bulk) ODL_CU(g_drv.FuncGetAttribute(&regs0, CU_FUNC_ATTRIBUTE_NUM_REGS, m->k_sweep));
-    ODL_CU(g_drv.FuncGetAttribute(&regs_t, CU_FUNC_ATTRIBUTE_NUM_REGS, k_tail));
     if (per_sm0 < 1 || per_sm_t < 1) return fail(ODL_ECUDA, "sweep kernel does not fit on an SM (shared memory / registers)");
-    int tail_warps = so && so->tail_warps > 0 ? so->tail_warps : 2;
-    int bulk_ctas = per_sm0;
-    if (concurrent) {
-      // what fits beside tail_warps single-warp CTAs of the stiff kernel: registers (allocated per warp in units of
-      // 8 per thread) and shared memory of one SM
-      const long long reg_file = 65536, smem_sm = 227 * 1024;
-      const long long rt = (long long)((regs_t + 7) / 8 * 8) * 32, r0 = (long long)((regs0 + 7) / 8 * 8) * block0;
-      tail_warps = std::min(tail_warps, per_sm_t);
-      while (tail_warps > 1 && (reg_file - tail_warps * rt < r0 || smem_sm - tail_warps * (long long)(smem_t + 1024) < (long long)(smem0 + 1024)))
-        --tail_warps;
-      const long long by_regs = (reg_file - tail_warps * rt) / r0;
-      const long long by_smem = (smem_sm - tail_warps * (long long)(smem_t + 1024)) / (long long)(smem0 + 1024);
-      bulk_ctas = (int)std::max<long long>(1, std::min<long long>(per_sm0, std::min(by_regs, by_smem)));
-    } else {
-      tail_warps = per_sm_t;
+    // SMs set aside for the stiff pass when it runs beside the bulk pass
+    int tail_sms = 0;
+    size_t smem_wide = 0;
+    const unsigned wide_block = 256;
+    if (beside) {
+      // measured on B200, 1M two_i prior draws (13k rows, ~6.8M BDF steps for the consumer): 24 SMs 4.96 ms, 32 4.03,
+      // 36 3.76, 40 3.71, 44 3.85 (sequential: 4.27) -- about a quarter of the SMs
+      tail_sms = so && so->tail_warps > 0 ? so->tail_warps : (m->sm_count * 26 + 50) / 100;
+      tail_sms = std::max(1, std::min(tail_sms, m->sm_count / 3));
+      // a CTA of the consumer must leave no room for a bulk CTA on its SM: ask for (SM shared memory) - (one bulk CTA)
+      const size_t sm_total = 228 * 1024, reserve = 1024;
+      smem_wide = std::max(smem_bytes(D, (int)wide_block), sm_total - reserve - (smem0 + reserve) + 1024);
+      smem_wide = std::min<size_t>(smem_wide, 227 * 1024);
+      if (smem_bytes(D, (int)wide_block) > 227 * 1024) return fail(ODL_ECUDA, "stiff pass: tables + staging exceed shared memory");
+      ODL_CU(g_drv.FuncSetAttribute(k_tail, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem_wide));
     }
     OdlOpts O0 = O; O0.stiff_check = 1; O0.max_steps = std::min(cap0, O.max_steps);
     // projection check at 3/4 of the cap: a system whose progress projects beyond the cap leaves there.  (At cap0/2 the
@@ -869,61 +898,65 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     OdlSweepArgs A0 = A;
     A0.index = ordered ? index : nullptr;
     A0.defer_list[0] = A0.defer_list[1] = feed; A0.defer_count[0] = A0.defer_count[1] = cnt(64);
-    A0.prod_started = cnt(192); A0.prod_exited = cnt(256);
     OdlOpts O2 = O; O2.stiff_check = 0;
-    // lanes per warp in the stiff pass: given, or (after the bulk pass, feed complete) as few as spreading the feed over
-    // every resident warp takes -- measured 1.80 -> 1.73 ms at 24 of 32 lanes; beside the bulk pass all 32
-    O2.lanes = so && so->tail_lanes > 0 ? std::min(32, so->tail_lanes) : (concurrent ? 0 : -1);
+    // the pass over the feed list AFTER the bulk pass: as few lanes per warp as spreading the entries over every
+    // resident warp takes (a warp pays for the union of its lanes' branches: 1.80 -> 1.61 ms at 11 of 32 lanes)
+    O2.lanes = so && so->tail_lanes > 0 ? std::min(32, so->tail_lanes) : -1;
     OdlSweepArgs A2 = A;
-    A2.index = feed; A2.index_count = cnt(64); A2.counter = nullptr; A2.feed_ticket = ctr(128);
-    A2.prod_counter = ctr(0); A2.prod_n = cut[1];                // the (first) bulk launch's counter and item count
-    A2.prod_started = cnt(192); A2.prod_exited = cnt(256);
-    A2.watchdog = cnt(320);
+    A2.index = feed; A2.index_count = cnt(64); A2.counter = ctr(256);
     A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
-    const unsigned grid0 = (unsigned)std::max<long long>(1, std::min<long long>((n + block0 - 1) / block0, (long long)bulk_ctas * m->sm_count));
-    const unsigned grid_t = (unsigned)std::max<long long>(1, std::min<long long>((n + 31) / 32, (long long)tail_warps * m->sm_count));
+    const int bulk_sms = m->sm_count - tail_sms;
+    const unsigned grid0 = (unsigned)std::max<long long>(1, std::min<long long>((n + block0 - 1) / block0, (long long)per_sm0 * bulk_sms));
+    const unsigned grid_t = (unsigned)std::max<long long>(1, std::min<long long>((n + 31) / 32, (long long)per_sm_t * m->sm_count));
     OdlData Dl = D;
-    void* pb[] = {&Dl, &O0, &A0};
-    void* pt[] = {&Dl, &O2, &A2};
-    if (concurrent) {
-      ODL_CUDA(cudaEventRecord(m->ev_fork, s));
-      ODL_CUDA(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
-      if ((rc = launch(m, k_tail, grid_t, 32, smem_t, m->aux, pt))) return rc;      // first: takes its SM share
-      ODL_CUDA(cudaEventRecord(m->ev_aux, m->aux));
-      if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc;
-      ODL_CUDA(cudaEventRecord(m->evp[0], s));
-      ODL_CUDA(cudaStreamWaitEvent(s, m->ev_aux, 0));
-    } else {
-      if (coop_bulk) { if ((rc = go_coop(s, O0, A0, n))) return rc; }            // n > 8: several lanes per system
-      else if (!chunked) { if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc; }
-      else {
-        const OdlSweepArgs Aall = A0;
-        A0.n = cut[1];                                       // pb points at A0: first piece, index[0..cut[1])
-        const unsigned g0 = (unsigned)std::max<long long>(1, std::min<long long>((cut[1] + block0 - 1) / block0, (long long)grid0));
-        if ((rc = launch(m, m->k_sweep, g0, block0, smem0, s, pb))) return rc;
-        for (int c = 1; c < n_piece; ++c) {
-          ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[c], 0));
-          if ((rc = order_piece(cut[c], cut[c + 1], c))) return rc;
-          OdlSweepArgs Ac = Aall;
-          Ac.n = cut[c + 1] - cut[c]; Ac.index = index + cut[c]; Ac.counter = ctr(384 + 64 * (c - 1));
-          void* pbc[] = {&Dl, &O0, &Ac};
-          const unsigned gc = (unsigned)std::max<long long>(1, std::min<long long>((Ac.n + block0 - 1) / block0, (long long)grid0));
-          if ((rc = launch(m, m->k_sweep, gc, block0, smem0, s, pbc))) return rc;
-        }
-      }
-      ODL_CUDA(cudaEventRecord(m->evp[0], s));
-      if ((rc = launch(m, k_tail, grid_t, 32, smem_t, s, pt))) return rc;
+    if (beside) {
+      // consumer first, on the helper stream: it is resident on its SMs before the bulk grid is launched
+      OdlOpts Oc = O2; Oc.lanes = 0;
+      OdlSweepArgs Ac = A2;
+      Ac.counter = nullptr; Ac.feed_ticket = ctr(128); Ac.feed_done = cnt(192); Ac.watchdog = cnt(320);
+      void* pc[] = {&Dl, &Oc, &Ac};
+      ODL_CUDA(cudaEventRecord(m->ev_fork, s));                  // after the counter block and the feed list are reset
+      ODL_CUDA(cudaStreamWaitEvent(m->aux2, m->ev_fork, 0));
+      if ((rc = launch(m, k_tail, (unsigned)tail_sms, wide_block, smem_wide, m->aux2, pc))) return rc;
+      ODL_CUDA(cudaEventRecord(m->ev_aux, m->aux2));
     }
+    if (chunked) ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[0], 0));
+    if (ordered && (rc = order_piece(0, cut[1], 0))) return rc;
+    ODL_CUDA(cudaEventRecord(m->evp[1], s));
+    void* pb[] = {&Dl, &O0, &A0};
+    if (coop_bulk) { if ((rc = go_coop(s, O0, A0, n))) return rc; }              // n > 8: several lanes per system
+    else if (!chunked) { if ((rc = launch(m, m->k_sweep, grid0, block0, smem0, s, pb))) return rc; }
+    else {
+      const OdlSweepArgs Aall = A0;
+      A0.n = cut[1];                                         // pb points at A0: first piece, index[0..cut[1])
+      const unsigned g0 = (unsigned)std::max<long long>(1, std::min<long long>((cut[1] + block0 - 1) / block0, (long long)grid0));
+      if ((rc = launch(m, m->k_sweep, g0, block0, smem0, s, pb))) return rc;
+      for (int c = 1; c < n_piece; ++c) {
+        ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[c], 0));
+        if ((rc = order_piece(cut[c], cut[c + 1], c))) return rc;
+        OdlSweepArgs Ac = Aall;
+        Ac.n = cut[c + 1] - cut[c]; Ac.index = index + cut[c]; Ac.counter = ctr(384 + 64 * (c - 1));   // chunked => ordered
+        void* pbc[] = {&Dl, &O0, &Ac};
+        const unsigned gc = (unsigned)std::max<long long>(1, std::min<long long>((Ac.n + block0 - 1) / block0, (long long)grid0));
+        if ((rc = launch(m, m->k_sweep, gc, block0, smem0, s, pbc))) return rc;
+      }
+    }
+    ODL_CUDA(cudaEventRecord(m->evp[0], s));
+    if (beside) {
+      int* flag = cnt(192);
+      void* pf[] = {&flag};
+      if ((rc = launch(m, m->k_feed_done, 1, 1, 0, s, pf))) return rc;
+      ODL_CUDA(cudaStreamWaitEvent(s, m->ev_aux, 0));            // the consumer has drained the feed
+    }
+    // the stiff pass proper (sequential mode) / the pick-up of entries the consumer left (beside mode: normally none)
+    void* pt[] = {&Dl, &O2, &A2};
+    if (smem_t > 48 * 1024 || beside) ODL_CU(g_drv.FuncSetAttribute(k_tail, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max(smem_t, smem_wide)));
+    if ((rc = launch(m, k_tail, grid_t, 32, smem_t, s, pt))) return rc;
     m->n_pass = 3;
   }
   ODL_CUDA(cudaEventRecord(m->ev1, s));
   m->timed = true;
   if ((rc = st.finish())) return rc;
-  if (solver == ODL_SOLVER_AUTO && mem == ODL_MEM_HOST) {
-    int gave_up = 0;
-    ODL_CUDA(cudaMemcpy(&gave_up, cnt(320), sizeof(int), cudaMemcpyDeviceToHost));
-    if (gave_up) return fail(ODL_ECUDA, "odl_sweep: the stiff pass gave up waiting for the DOPRI5 pass (watchdog); results are incomplete");
-  }
   return 0;
 }
 
@@ -937,6 +970,7 @@ extern "C" int odl_trajectory(odl_model* m, const odl_solver_opts* so, long long
   int rc;
   if ((rc = units_ready(m, {U_TRAJ}))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = serialize_after_previous_call(m, s))) return rc;
   Staging st{m, s, 0, mem};
   OdlTrajArgs A{};
   OdlData D = m->grid.d;
@@ -984,6 +1018,7 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
                             (solver == ODL_SOLVER_RADAU5 ? U_MCMC_RADAU : (solver == ODL_SOLVER_BDF ? U_MCMC_BDF : U_MCMC_AUTO))))})))
     return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = serialize_after_previous_call(m, s))) return rc;
   Staging st{m, s, 0, mem};
   OdlMcmcArgs A{};
   if ((rc = st.inout(io->theta, (size_t)C * P, &A.theta_cur, true))) return rc;
@@ -1067,6 +1102,15 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   ODL_CUDA(cudaEventRecord(m->ev1, s));
   m->timed = true;
   return st.finish();
+}
+
+/* development aid: the feed timeline of the last AUTO sweep run with ODL_TIMELINE=1 (3 timestamps per feed entry) */
+extern "C" int odl_debug_timeline(odl_model* m, long long* out, long long entries) {
+  if (!m || !out || !m->on_gpu || !m->scratch[20].p) return fail(ODL_EINVAL, "odl_debug_timeline: nothing recorded");
+  ODL_ON_DEVICE(m);
+  if ((size_t)entries * 3 * sizeof(long long) > m->scratch[20].cap) return fail(ODL_EINVAL, "odl_debug_timeline: count out of range");
+  ODL_CUDA(cudaMemcpy(out, m->scratch[20].p, (size_t)entries * 3 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 /* development aid: the first `count` ints of the counter block of the last sweep (see odl_sweep) */

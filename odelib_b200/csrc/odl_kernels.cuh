@@ -54,6 +54,9 @@
 #define ODL_UNIT 0
 #endif
 #define ODL_HAS(u) (ODL_UNIT == 0 || ODL_UNIT == (u))
+#ifndef ODL_TIMELINE
+#define ODL_TIMELINE 0     // 1: development build that timestamps the feed of the stiff pass (OdlSweepArgs.timeline)
+#endif
 #ifndef ODL_MINBLOCKS_ROS
 #define ODL_MINBLOCKS_ROS (ODL_MINBLOCKS > 2 ? ODL_MINBLOCKS - 1 : ODL_MINBLOCKS)
 #endif
@@ -513,6 +516,9 @@ ODL_UNROLL
   // Step budget.  One compare per attempt until the first of the two checks is due: the cap itself, and -- capped pass
   // of the cohort sweep -- the projection check: a system whose progress after early_check_steps attempts projects to
   // more than max_steps in total leaves now instead of burning the rest of its budget (its warp waits for it).
+  // (Earlier checks against multiples of the cap -- 64 / 128 / 256 attempts against 8x / 4x / 2x -- were measured: the
+  // hopeless systems reach the stiff pass 0.4 ms sooner, but 40 % more rows do (slow starters), and that pass, which
+  // runs beside this one on a quarter of the SMs, is bound by its throughput: 3.88 against 3.71 ms per 1M rows.)
   const int first_check = (O.early_check_steps > 0 && O.early_check_steps < O.max_steps) ? O.early_check_steps : O.max_steps;
   if (st.nsteps >= first_check && st.slot < D.n_slot && st.status == ODL_OK) {
     if (st.nsteps >= O.max_steps) st.status = ODL_MAXSTEPS;
@@ -1432,6 +1438,11 @@ __device__ __forceinline__ void odl_attempt(OdlStepper& st, typename OdlAuxOf<SO
 }
 
 #ifndef ODL_HOST_HARNESS
+__device__ __forceinline__ long long odl_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // fetch `want` lanes' worth of indices from a global counter with one atomic per warp
 __device__ __forceinline__ long long odl_fetch(unsigned long long* counter, bool want, int lane) {
   const unsigned m = __ballot_sync(ODL_FULL, want);
@@ -1538,6 +1549,8 @@ odl_order_scatter_kernel(const OdlOrderArgs A) {
     __syncthreads();
   }
 }
+// follows the last bulk launch of an AUTO sweep in its stream: the feed list of the stiff pass is complete
+extern "C" __global__ void odl_feed_done_kernel(int* flag) { atomicExch(flag, 1); }
 #endif  // unit 13
 
 // ------------------------------------------------------------------------------------------------
@@ -1586,7 +1599,6 @@ ODL_UNROLL
   bool pending = false;
   long long ticket = -1;
   unsigned int idle_spins = 0;
-  if (A.prod_started && !consumer && lane == 0) atomicAdd(A.prod_started, 1);     // before this warp's first fetch
   for (;;) {
     // ---- (A) finished lanes: cooperative score, write-back ----
     const bool fin = active && done;
@@ -1610,8 +1622,17 @@ ODL_UNROLL
         if (A.r2) A.r2[row] = r2;
         if (A.status) A.status[row] = status;
         if (A.nsteps) A.nsteps[row] = fin_nsteps;
+#if ODL_TIMELINE
+        if ((fin_status == ODL_MAXSTEPS || fin_status == ODL_STIFF) && A.defer_list[0]) {
+          const int pos = atomicAdd(A.defer_count[0], 1);
+          if (A.timeline) A.timeline[3 * pos] = odl_globaltimer();
+          A.defer_list[0][pos] = (int)row;
+        }
+        if (consumer && A.timeline) A.timeline[3 * sys + 2] = odl_globaltimer();
+#else
         if (fin_status == ODL_MAXSTEPS && A.defer_list[0]) A.defer_list[0][atomicAdd(A.defer_count[0], 1)] = (int)row;
         if (fin_status == ODL_STIFF && A.defer_list[1]) A.defer_list[1][atomicAdd(A.defer_count[1], 1)] = (int)row;
+#endif
       }
     }
     if (fin) { active = false; done = false; want = lane_on; }
@@ -1620,9 +1641,13 @@ ODL_UNROLL
       const long long got = odl_fetch(A.counter, want, lane);
       if (want) {
         want = false;
-        if (got >= 0 && got < n) {
+        long long r_ = -1;
+        if (got >= 0 && got < n) r_ = A.index ? (long long)A.index[got] : got;
+        // a feed entry below zero was finished by the pass that ran beside the bulk pass: take the next one
+        if (got >= 0 && got < n && r_ < 0) want = lane_on;
+        if (r_ >= 0) {
           sys = got;
-          row = A.index ? (long long)A.index[sys] : sys;
+          row = r_;
 ODL_UNROLL
           for (int q = 0; q < ODL_P; ++q) p[q] = A.theta[row * ODL_P + q];
           odl_init_system(st, p, D, O, nullptr, false);
@@ -1633,19 +1658,19 @@ ODL_UNROLL
           if (done) { fin_status = st.status; fin_nsteps = st.nsteps; }
         }
       }
-      if (!__any_sync(ODL_FULL, active)) break;
+      if (!__any_sync(ODL_FULL, active)) {
+        if (__any_sync(ODL_FULL, want)) continue;                // only skipped entries this time: fetch again
+        break;
+      }
     } else {
       const long long got = odl_fetch(A.feed_ticket, want, lane);
       if (want) { want = false; pending = true; ticket = got; }
       if (__any_sync(ODL_FULL, pending)) {
-        // producer state, read in this order: work counter dry -> warps entered -> warps left -> entries published.
-        // A warp that enters after the counter ran dry gets no work, so "dry and left == entered" is final.
+        // *feed_done is set by a one-thread kernel that follows the last bulk launch in its stream: once it reads 1,
+        // the count read AFTER it is final
         int landed = 0, complete = 0;
         if (lane == 0) {
-          const bool dry = odl_ld_acquire(A.prod_counter) >= (unsigned long long)A.prod_n;
-          const int entered = odl_ld_acquire(A.prod_started);
-          const int left = odl_ld_acquire(A.prod_exited);
-          complete = (dry && entered == left) ? 1 : 0;
+          complete = odl_ld_acquire(A.feed_done);
           landed = odl_ld_acquire(A.index_count);
         }
         landed = __shfl_sync(ODL_FULL, landed, 0);
@@ -1654,7 +1679,13 @@ ODL_UNROLL
           if (ticket < (long long)landed) {
             int r;
             do { r = odl_ld_acquire(A.index + ticket); } while (r < 0);       // written right after the count moved
+            // taken: a lane that starts a system finishes it (a warp leaves only with no lane at work), so the pass
+            // that follows this one skips the entry
+            const_cast<int*>(A.index)[ticket] = -2;
             sys = ticket; row = r;
+#if ODL_TIMELINE
+            if (A.timeline) A.timeline[3 * ticket + 1] = odl_globaltimer();
+#endif
 ODL_UNROLL
             for (int q = 0; q < ODL_P; ++q) p[q] = A.theta[row * ODL_P + q];
             odl_init_system(st, p, D, O, nullptr, false);
@@ -1702,10 +1733,6 @@ ODL_UNROLL
       if (!__any_sync(ODL_FULL, active && !done)) break;
     }
   }
-  if (A.prod_exited && !consumer) {
-    __threadfence();                                                           // this warp's deferrals first
-    if (lane == 0) atomicAdd(A.prod_exited, 1);
-  }
 }
 #if ODL_HAS(1)
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
@@ -1716,12 +1743,13 @@ extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
 odl_sweep_ros23_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<1>(D, O, A); }
 #endif
 #if ODL_HAS(9)
-extern "C" __global__ void __launch_bounds__(32, 1)
+extern "C" __global__ void __launch_bounds__(256, 1)
 odl_sweep_radau5_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<3>(D, O, A); }
 #endif
-// (register caps for more resident warps spill: 168 registers -> 3.1 ms against 1.6 ms at 226, tools/variant_ab.py)
+// (register caps for more resident warps spill: 168 registers -> 3.1 ms against 1.6 ms at 226, tools/variant_ab.py).
+// CTAs of one warp when the pass runs after the bulk pass, of 8 warps when it runs beside it on SMs of its own.
 #if ODL_HAS(4)
-extern "C" __global__ void __launch_bounds__(32, 1)
+extern "C" __global__ void __launch_bounds__(256, 1)
 odl_sweep_bdf_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<4>(D, O, A); }
 #endif
 
@@ -2363,7 +2391,6 @@ odl_sweep_coop_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
   const OdlGroup G = odl_coop_group(S, D);
   const long long n = A.index_count ? (long long)(*A.index_count) : A.n;
   OdlCoopStepper st;
-  if (A.prod_started && (threadIdx.x & 31) == 0) atomicAdd(A.prod_started, 1);
   for (;;) {
     long long sys = 0;
     if (G.sub == 0) sys = (long long)atomicAdd(A.counter, 1ull);
@@ -2389,11 +2416,6 @@ odl_sweep_coop_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) {
       if (st.status == ODL_MAXSTEPS && A.defer_list[0]) A.defer_list[0][atomicAdd(A.defer_count[0], 1)] = (int)row;
     }
     __syncwarp(G.mask);
-  }
-  __syncwarp();
-  if (A.prod_exited) {
-    __threadfence();
-    if ((threadIdx.x & 31) == 0) atomicAdd(A.prod_exited, 1);
   }
 }
 #endif  // unit 11

@@ -199,10 +199,16 @@ def test_auto_sweep_is_independent_of_ordering_and_of_how_the_passes_are_schedul
     theta = prior_draws("two_i", 40000, seed=11)
     base = dm.sweep(theta, solver="auto", max_steps=200000)
     assert np.all(base["status"] == 0)
-    for flags in (_capi.AUTO_UNORDERED, _capi.AUTO_CONCURRENT, _capi.AUTO_UNORDERED | _capi.AUTO_CONCURRENT):
+    for flags in (_capi.AUTO_UNORDERED, _capi.AUTO_CONCURRENT, _capi.AUTO_UNORDERED | _capi.AUTO_CONCURRENT,
+                  _capi.AUTO_SEQUENTIAL, _capi.AUTO_UNORDERED | _capi.AUTO_SEQUENTIAL):
         other = dm.sweep(theta, solver="auto", max_steps=200000, auto_flags=flags)
         for k in ("chi", "r2", "status", "nsteps"):
             assert np.array_equal(base[k], other[k], equal_nan=True), (flags, k)
+    # the stiff pass beside the bulk pass on 1, 8 or 40 SMs of its own: scheduling only
+    for sms in (1, 8, 40):
+        other = dm.sweep(theta, solver="auto", max_steps=200000, auto_flags=_capi.AUTO_CONCURRENT, tail_warps=sms)
+        for k in ("chi", "r2", "status", "nsteps"):
+            assert np.array_equal(base[k], other[k], equal_nan=True), (sms, k)
     # the DOPRI5 pass alone (cap 512, projection check at 384) finishes a set of rows; the rest carries BDF numbers
     dop = dm.sweep(theta, solver="dopri5", max_steps=512, stiff_check=True, early_check_steps=384)
     fin = dop["status"] == 0
@@ -227,10 +233,30 @@ def test_host_memory_sweep_in_two_pieces_equals_one_piece_and_the_device_call():
     a = dm.sweep(theta, solver="auto", max_steps=200000)
     b = dm.sweep(theta, solver="auto", max_steps=200000, auto_flags=_capi.AUTO_ONE_PIECE)
     c = dm.sweep(torch.from_numpy(theta).cuda(), solver="auto", max_steps=200000)
+    d = dm.sweep(theta, solver="auto", max_steps=200000, auto_flags=_capi.AUTO_SEQUENTIAL)
     assert np.all(a["status"] == 0) and (a["nsteps"] > 512).sum() > 100
     for k in ("chi", "r2", "status", "nsteps"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
         assert np.array_equal(a[k], c[k].cpu().numpy(), equal_nan=True), k
+        assert np.array_equal(a[k], d[k], equal_nan=True), k
+
+
+def test_a_consumer_that_gives_up_costs_time_not_rows(monkeypatch):
+    """The stiff pass beside the bulk pass stops polling after `watchdog_spins` idle polls; whatever it has not finished
+    by then is picked up by the launch that follows the bulk pass.  With an absurdly short patience the consumer leaves
+    at once: same rows, same numbers, on the device-buffer path too (no NaN rows without an error)."""
+    import torch
+    dm, _ = device_model("two_i")
+    theta = prior_draws("two_i", 60000, seed=17)
+    from odelib_b200 import _capi
+    base = dm.sweep(theta, solver="auto", max_steps=200000, auto_flags=_capi.AUTO_SEQUENTIAL)
+    monkeypatch.setenv("ODL_WATCHDOG_SPINS", "1000")            # the floor: ~0.4 ms of patience
+    host = dm.sweep(theta, solver="auto", max_steps=200000, auto_flags=_capi.AUTO_CONCURRENT)
+    dev = dm.sweep(torch.from_numpy(theta).cuda(), solver="auto", max_steps=200000, auto_flags=_capi.AUTO_CONCURRENT)
+    assert np.all(base["status"] == 0) and (base["nsteps"] > 512).sum() > 50
+    for k in ("chi", "r2", "status", "nsteps"):
+        assert np.array_equal(base[k], host[k], equal_nan=True), k
+        assert np.array_equal(base[k], dev[k].cpu().numpy(), equal_nan=True), k
 
 
 def test_auto_sweep_rows_of_both_steppers_against_the_oracle():
