@@ -18,7 +18,7 @@
 struct OdlData {                 // constant tables of one ModelFramework
   const double* slot_t;          // [n_slot] distinct observation grid times, ascending
   const double* obs_lnO;         // [n_obs] ln(abundance)              (Framework.py:326)
-  const double* obs_denom;       // [n_obs] 2*sigma^2                  (stats.py:41)
+  const double* obs_w;           // [n_obs] 1 / (2*sigma^2)            (stats.py:41; inf for sigma = 0: term masked)
   const double* obs_lin;         // [n_obs] exp(ln O)                  (Framework.py:700)
   const int* obs_src;            // [n_obs] slot*n_out + column
   const double* y0;              // [n_state]

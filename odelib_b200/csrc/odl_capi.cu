@@ -565,7 +565,7 @@ static int upload_tables(odl_model* m, Tables& T, int n_slot, const double* slot
   if (!(slot_time[0] >= t0)) return fail(ODL_EINVAL, "first output time precedes t0");
   ODL_ON_DEVICE(m);
   const int N = m->n_state;
-  // layout: slot_t[K] lnO[n_obs] denom[n_obs] lin[n_obs] y0[N] | src[n_obs] y0p[N]
+  // layout: slot_t[K] lnO[n_obs] w[n_obs] lin[n_obs] y0[N] | src[n_obs] y0p[N]
   size_t nd = (size_t)n_slot + 3 * (size_t)n_obs + N;
   size_t ni = (size_t)n_obs + N;
   std::vector<double> hd(nd);
@@ -583,7 +583,7 @@ static int upload_tables(odl_model* m, Tables& T, int n_slot, const double* slot
       return fail(ODL_EINVAL, "observation row refers to a slot/column out of range");
     lnO[o] = ln_obs[o];
     const double s2 = log_sigma[o] * log_sigma[o];     // S**2
-    den[o] = 2.0 * s2;                                 // 2*(S**2)     (stats.py:41)
+    den[o] = 1.0 / (2.0 * s2);                         // 1 / (2*(S**2))   (stats.py:41); sigma = 0 -> inf -> masked term
     lin[o] = std::exp(ln_obs[o]);                      // Framework.py:700
     src[o] = obs_slot[o] * m->n_out + obs_col[o];
   }
@@ -602,7 +602,7 @@ static int upload_tables(odl_model* m, Tables& T, int n_slot, const double* slot
   double* dd = reinterpret_cast<double*>(base);
   int* di = reinterpret_cast<int*>(base + nd * sizeof(double));
   OdlData& d = T.d;
-  d.slot_t = dd; d.obs_lnO = dd + n_slot; d.obs_denom = d.obs_lnO + n_obs; d.obs_lin = d.obs_denom + n_obs;
+  d.slot_t = dd; d.obs_lnO = dd + n_slot; d.obs_w = d.obs_lnO + n_obs; d.obs_lin = d.obs_w + n_obs;
   d.y0 = d.obs_lin + n_obs;
   d.obs_src = di; d.y0_from_param = di + n_obs;
   d.n_slot = n_slot; d.n_obs = n_obs;
@@ -850,9 +850,19 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     // piece boundaries: [0, n/2, n] rounded to 1024 rows (one piece when the table is already on the device).  Measured
     // on B200, 1M two_i rows through host buffers: two halves 190 M solves/s, three pieces (1/8, 3/8, 1/2) 180 M/s --
     // every extra bulk launch ends on its own stragglers, which costs more than the shorter wait for the first piece.
+    const bool beside_first_quarter = !m->coop_model() && !(flags & ODL_AUTO_SEQUENTIAL);
     const int n_piece = chunked ? 2 : 1;
     long long cut[4] = {0, n, n, n};
-    if (chunked) cut[1] = ((n / 2 + 1023) / 1024) * 1024;
+    if (chunked) {
+      // share of the rows in the first piece.  Stiff pass beside the bulk pass: a quarter -- the rows of the SECOND
+      // piece that the stiff pass has to take reach it one bulk launch late, and it needs ~2.5 ms for the longest of
+      // them, so the second launch should be the long one (1M rows through pinned host buffers: 5.44 ms at 1/2,
+      // 4.88 at 1/3 .. 1/5, 4.85 at 0.15; one piece 5.09).  Stiff pass after the bulk pass: halves (5.10 / 5.04 / 5.12
+      // at 1/2, 1/3, 1/4).
+      double first = beside_first_quarter ? 0.25 : 0.5;
+      if (const char* e = getenv("ODL_FIRST_PIECE")) first = std::min(0.9, std::max(0.05, atof(e)));   // development knob
+      cut[1] = (((long long)(n * first) + 1023) / 1024) * 1024;
+    }
     if (chunked) {
       ODL_CUDA(cudaEventRecord(m->ev_fork, s));                  // behind the previous call on this handle
       ODL_CUDA(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));

@@ -122,7 +122,7 @@ __device__ __forceinline__ double odl_u53(unsigned int a, unsigned int b) {
 // ------------------------------------------------------------------------------------------------
 // ODL_LOGTAB intervals of [1, 2) for odl_log below: (invc, -ln invc) per interval, 4 KB, filled by every CTA at start
 struct OdlShared {
-  double* slot_t; double* lnO; double* denom; double* lin; int* src; double* stage; double* logtab;
+  double* slot_t; double* lnO; double* w; double* lin; int* src; double* stage; double* logtab;
 };
 __device__ __forceinline__ OdlShared odl_carve(double* base, const OdlData& D) {
   OdlShared S;
@@ -130,8 +130,8 @@ __device__ __forceinline__ OdlShared odl_carve(double* base, const OdlData& D) {
   base += 2 * ODL_LOGTAB;
   S.slot_t = base;
   S.lnO = S.slot_t + D.n_slot;
-  S.denom = S.lnO + D.n_obs;
-  S.lin = S.denom + D.n_obs;
+  S.w = S.lnO + D.n_obs;
+  S.lin = S.w + D.n_obs;
   S.src = (int*)(S.lin + D.n_obs);
   S.stage = S.lin + D.n_obs + (D.n_obs + 1) / 2;
   return S;
@@ -145,7 +145,7 @@ __device__ __forceinline__ void odl_load_tables(const OdlShared& S, const OdlDat
   }
   for (int i = threadIdx.x; i < D.n_slot; i += blockDim.x) S.slot_t[i] = D.slot_t[i];
   for (int i = threadIdx.x; i < D.n_obs; i += blockDim.x) {
-    S.lnO[i] = D.obs_lnO[i]; S.denom[i] = D.obs_denom[i]; S.lin[i] = D.obs_lin[i]; S.src[i] = D.obs_src[i];
+    S.lnO[i] = D.obs_lnO[i]; S.w[i] = D.obs_w[i]; S.lin[i] = D.obs_lin[i]; S.src[i] = D.obs_src[i];
   }
   __syncthreads();
 }
@@ -191,15 +191,12 @@ __device__ __forceinline__ void odl_score(const OdlShared& S, const OdlData& D, 
     if (pred_out) pred_out[o] = pred;
     const double d = __dadd_rn(S.lnO[o], -odl_log(S, pred));   // masked_invalid(O) - C
     const double dd = __dmul_rn(d, d);                          // (...)**2   : masked when not finite
-    const double den = S.denom[o];
-    // / (2*S**2): masked on domain or non-finite.  A ZERO numerator sends the division through its out-of-line slow
-    // path, and every system has two: the observations at t0 are the initial values themselves, so lnO - ln C == 0
-    // there (3.6 % of the sweep kernel's instructions, issued for 2 lanes: profiles/r1f).  0 / den needs no division:
-    // bulk pass 2.94 -> 2.85 ms.
-    const bool plain = (dd != 0.0);
-    double term = (plain ? dd : 1.0) / den;
-    if (!plain) term = (den == den && den != 0.0) ? 0.0 : __longlong_as_double(0x7ff8000000000000LL);
-    const bool ok = odl_finite(dd) && odl_finite(term) && !(fabs(dd) * ODL_DBL_MIN >= fabs(den));
+    // / (2*S**2), as a multiplication by the reciprocal the host tabulated (no division per observation: 1.9 % of the
+    // sweep kernel's instructions in profiles/r2f, plus the special case a zero numerator needed).  np.ma masks the
+    // term when the quotient is not finite or the denominator vanishes against the numerator: sigma = 0 (or a
+    // denormal 2 sigma^2) has the reciprocal inf -> inf or NaN here, masked as well.
+    const double term = __dmul_rn(dd, S.w[o]);
+    const bool ok = odl_finite(dd) && odl_finite(term);
     if (ok) { c += term; ++k; }
     const double r = __dadd_rn(pred, -S.lin[o]);
     const double rr = __dmul_rn(r, r);
@@ -207,9 +204,7 @@ __device__ __forceinline__ void odl_score(const OdlShared& S, const OdlData& D, 
   }
   chi = odl_warp_sum(c);
   ssres = odl_warp_sum(s);
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) k += __shfl_xor_sync(ODL_FULL, k, m);
-  nvalid = k;
+  nvalid = __reduce_add_sync(ODL_FULL, k);
 }
 
 
@@ -222,9 +217,8 @@ __device__ __forceinline__ void odl_score_self(const OdlShared& S, const OdlData
     const double pred = stage[S.src[o]];
     const double d = __dadd_rn(S.lnO[o], -odl_log(S, pred));
     const double dd = __dmul_rn(d, d);
-    const double den = S.denom[o];
-    const double term = dd / den;
-    const bool ok = odl_finite(dd) && odl_finite(term) && !(fabs(dd) * ODL_DBL_MIN >= fabs(den));
+    const double term = __dmul_rn(dd, S.w[o]);
+    const bool ok = odl_finite(dd) && odl_finite(term);
     if (ok) { c += term; ++k; }
     const double r = __dadd_rn(pred, -S.lin[o]);
     const double rr = __dmul_rn(r, r);
@@ -1603,6 +1597,8 @@ ODL_UNROLL
     // ---- (A) finished lanes: cooperative score, write-back ----
     const bool fin = active && done;
     unsigned m = __ballot_sync(ODL_FULL, fin);
+    double w_chi = 0.0, w_ss = 0.0;
+    int w_nv = 0;
     while (m) {
       const int L = __ffs(m) - 1;
       m &= m - 1;
@@ -1613,27 +1609,29 @@ ODL_UNROLL
       double* pred_out = (A.pred && statL == ODL_OK) ? A.pred + rowL * D.n_obs : nullptr;
       // (unfinished solves are scored too: a branch around the inlined scorer costs more -- +2 % -- than their 2.5 %)
       odl_score(S, D, S.stage + (size_t)((threadIdx.x & ~31) + L) * D.stage_stride, lane, pred_out, chi, ss, nv);
-      if (lane == L) {
-        int status = fin_status;
-        double r2 = fma(-ss, D.inv_sstot, 1.0);                   // 1 - ssres/sstot (stats.py:56), reciprocal from the host
-        if (status != ODL_OK) { chi = __longlong_as_double(0x7ff8000000000000LL); r2 = chi; }
-        else if (nv == 0) { chi = __longlong_as_double(0x7ff8000000000000LL); status |= ODL_ALLMASKED; }
-        A.chi[row] = chi;                                        // r2 / status / nsteps only when the caller asked for them
-        if (A.r2) A.r2[row] = r2;
-        if (A.status) A.status[row] = status;
-        if (A.nsteps) A.nsteps[row] = fin_nsteps;
+      if (lane == L) { w_chi = chi; w_ss = ss; w_nv = nv; }     // kept for the write-back below, all finished lanes at once
+    }
+    if (fin) {
+      int status = fin_status;
+      double chi = w_chi;
+      double r2 = fma(-w_ss, D.inv_sstot, 1.0);                   // 1 - ssres/sstot (stats.py:56), reciprocal from the host
+      if (status != ODL_OK) { chi = __longlong_as_double(0x7ff8000000000000LL); r2 = chi; }
+      else if (w_nv == 0) { chi = __longlong_as_double(0x7ff8000000000000LL); status |= ODL_ALLMASKED; }
+      A.chi[row] = chi;                                          // r2 / status / nsteps only when the caller asked for them
+      if (A.r2) A.r2[row] = r2;
+      if (A.status) A.status[row] = status;
+      if (A.nsteps) A.nsteps[row] = fin_nsteps;
 #if ODL_TIMELINE
-        if ((fin_status == ODL_MAXSTEPS || fin_status == ODL_STIFF) && A.defer_list[0]) {
-          const int pos = atomicAdd(A.defer_count[0], 1);
-          if (A.timeline) A.timeline[3 * pos] = odl_globaltimer();
-          A.defer_list[0][pos] = (int)row;
-        }
-        if (consumer && A.timeline) A.timeline[3 * sys + 2] = odl_globaltimer();
-#else
-        if (fin_status == ODL_MAXSTEPS && A.defer_list[0]) A.defer_list[0][atomicAdd(A.defer_count[0], 1)] = (int)row;
-        if (fin_status == ODL_STIFF && A.defer_list[1]) A.defer_list[1][atomicAdd(A.defer_count[1], 1)] = (int)row;
-#endif
+      if ((fin_status == ODL_MAXSTEPS || fin_status == ODL_STIFF) && A.defer_list[0]) {
+        const int pos = atomicAdd(A.defer_count[0], 1);
+        if (A.timeline) A.timeline[3 * pos] = odl_globaltimer();
+        A.defer_list[0][pos] = (int)row;
       }
+      if (consumer && A.timeline) A.timeline[3 * sys + 2] = odl_globaltimer();
+#else
+      if (fin_status == ODL_MAXSTEPS && A.defer_list[0]) A.defer_list[0][atomicAdd(A.defer_count[0], 1)] = (int)row;
+      if (fin_status == ODL_STIFF && A.defer_list[1]) A.defer_list[1][atomicAdd(A.defer_count[1], 1)] = (int)row;
+#endif
     }
     if (fin) { active = false; done = false; want = lane_on; }
     // ---- (B) refill ----
@@ -1760,7 +1758,7 @@ odl_sweep_bdf_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { o
 extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS)
 odl_traj_kernel(const OdlData D, const OdlOpts O, const OdlTrajArgs A) {
   OdlShared S;
-  S.slot_t = odl_smem; S.lnO = S.denom = S.lin = nullptr; S.src = nullptr; S.stage = nullptr;
+  S.slot_t = odl_smem; S.lnO = S.w = S.lin = nullptr; S.src = nullptr; S.stage = nullptr;
   for (int i = threadIdx.x; i < D.n_slot; i += blockDim.x) S.slot_t[i] = D.slot_t[i];
   __syncthreads();
   const long long sys = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2357,9 +2355,8 @@ __device__ __forceinline__ void odl_coop_score(const OdlShared& S, const OdlData
     if (pred_out) pred_out[o] = pred;
     const double d = __dadd_rn(S.lnO[o], -odl_log(S, pred));
     const double dd = __dmul_rn(d, d);
-    const double den = S.denom[o];
-    const double term = dd / den;
-    const bool ok = odl_finite(dd) && odl_finite(term) && !(fabs(dd) * ODL_DBL_MIN >= fabs(den));
+    const double term = __dmul_rn(dd, S.w[o]);
+    const bool ok = odl_finite(dd) && odl_finite(term);
     if (ok) { c += term; k += 1.0; }
     const double r = __dadd_rn(pred, -S.lin[o]);
     const double rr = __dmul_rn(r, r);

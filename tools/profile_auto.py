@@ -15,8 +15,9 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "auto"
 if mode == "auto":
     dm, tab = device_model("two_i")
     theta = torch.from_numpy(prior_draws("two_i", 1 << 20, seed=0)).cuda()
+    flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0       # 8 = stiff pass after the bulk pass (ncu serialises kernels)
     for _ in range(3):
-        out = dm.sweep(theta, solver="auto", max_steps=500000)
+        out = dm.sweep(theta, solver="auto", max_steps=500000, auto_flags=flags)
     torch.cuda.synchronize()
     print("auto kernel_ms", dm.last_kernel_ms(), dm.last_pass_ms(), dm.kernel_info("sweep"), dm.kernel_info("sweep_bdf"))
 elif mode == "mcmc":
