@@ -58,6 +58,7 @@ enum { ODL_AUTO_UNORDERED = 1,   /* process rows in input order (no cost orderin
                                     the second travelling while the first is swept) */
        ODL_AUTO_SEQUENTIAL = 8   /* run the stiff pass AFTER the DOPRI5 pass (single-warp CTAs over every SM) */ };
 enum { ODL_RNG_PHILOX = 0, ODL_RNG_HOST_STREAMS = 1, ODL_RNG_FORCED = 2 };
+enum { ODL_SAMPLES_CHAIN_MAJOR = 0, ODL_SAMPLES_ITERATION_MAJOR = 1 };
 /* per-system status words */
 enum { ODL_ST_OK = 0, ODL_ST_MAXSTEPS = 1, ODL_ST_NONFINITE = 2, ODL_ST_HUNDERFLOW = 3, ODL_ST_STIFF = 4,
        ODL_ST_ALLMASKED = 8 };
@@ -117,7 +118,9 @@ typedef struct odl_mcmc_opts {
                           0 = automatic (fills an otherwise latency-bound GPU), 1 = one proposal at a time.
                           n_state > 8: values >= 1 select the thread-per-system kernel; 0 and negative values the
                           cooperative kernel, -K = K groups of coop_lanes lanes per chain (K * coop_lanes <= 32) */
-  int reserved;
+  int sample_layout;   /* ODL_SAMPLES_CHAIN_MAJOR: samples[chain][row][row_stride] (the reference frame's order);
+                          ODL_SAMPLES_ITERATION_MAJOR: samples[row][chain][row_stride] -- the rows a warp keeps in one
+                          iteration are contiguous and leave as coalesced full-sector stores */
 } odl_mcmc_opts;
 
 typedef struct odl_mcmc_io {
@@ -125,7 +128,7 @@ typedef struct odl_mcmc_io {
   double* chain_state;     /* [n_chain][8] chi, r2, accepts, best_chi, best_iteration, 3 unused; in when
                               it_begin>1, always out.  best_* = the first minimum of chi over the kept rows
                               (what set_best_params' idxmin picks, Framework.py:725-731); best_iteration 0 = none */
-  double* samples;         /* [n_chain][nits-1-burnin][row_stride] or NULL:
+  double* samples;         /* [n_chain][nits-1-burnin][row_stride] (or iteration-major, see sample_layout) or NULL:
                               theta.., chi, rsquared, aic, iteration, acceptance_ratio (Samplers.py:160-165) */
   double* summaries;       /* [n_chain][1+2*n_param] count, mean, M2 of ln(theta) over kept rows, or NULL
                               (must be zeroed by the caller before the first segment) */

@@ -13,6 +13,7 @@ SUCCESS, EINVAL, ECUDA, ECOMPILE, ENODEVICE, EIO = range(6)
 MEM_HOST, MEM_DEVICE = 0, 1
 SOLVER_DOPRI5, SOLVER_ROS23, SOLVER_AUTO, SOLVER_RADAU5, SOLVER_BDF = 0, 1, 2, 3, 4
 RNG_PHILOX, RNG_HOST_STREAMS, RNG_FORCED = 0, 1, 2
+SAMPLES_CHAIN_MAJOR, SAMPLES_ITERATION_MAJOR = 0, 1
 AUTO_UNORDERED, AUTO_CONCURRENT, AUTO_ONE_PIECE, AUTO_SEQUENTIAL = 1, 2, 4, 8
 ST_OK, ST_MAXSTEPS, ST_NONFINITE, ST_HUNDERFLOW, ST_STIFF, ST_ALLMASKED = 0, 1, 2, 3, 4, 8
 
@@ -45,7 +46,7 @@ class McmcOpts(C.Structure):
     _fields_ = [("n_chain", C.c_int), ("chain_offset", C.c_int), ("nits", C.c_int), ("burnin", C.c_int),
                 ("it_begin", C.c_int), ("it_end", C.c_int), ("rng_mode", C.c_int), ("n_walk", C.c_int),
                 ("walk", C.POINTER(C.c_int)), ("pnum", C.c_int), ("row_stride", C.c_int), ("step_sd", C.c_double),
-                ("seed", C.c_ulonglong), ("speculate", C.c_int), ("reserved", C.c_int)]
+                ("seed", C.c_ulonglong), ("speculate", C.c_int), ("sample_layout", C.c_int)]
 
 
 class McmcIO(C.Structure):

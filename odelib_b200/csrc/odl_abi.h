@@ -115,7 +115,9 @@ struct OdlMcmcArgs {
   int n_iter_total;              // nits-1
   int spec;                      // lanes per chain (power of two <= 32): iterations evaluated at once along the
                                  //   all-rejected path (prefetching MH); 1 = one proposal at a time
-  double* samples;               // [C][n_keep][row_stride]: theta.., chi, rsquared, aic, iteration, acceptance_ratio
+  double* samples;               // kept rows (theta.., chi, rsquared, aic, iteration, acceptance_ratio): row (chain, r) at
+  long long smp_chain_pitch;     //   samples[chain * smp_chain_pitch + r * smp_row_pitch] (doubles): chain-major
+  long long smp_row_pitch;       //   [C][n_keep][row_stride] or iteration-major [n_keep][C][row_stride]
   double* summaries;             // [C][1+2*n_param]: count, mean[P], M2[P] of ln(theta) over kept rows
   double* trace_chinew;          // optional [C][n_iter_total]  chi of every proposal (parity tests)
   unsigned char* trace_accept;   // optional [C][n_iter_total]

@@ -887,7 +887,8 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     // SMs set aside for the stiff pass when it runs beside the bulk pass
     int tail_sms = 0;
     size_t smem_wide = 0;
-    const unsigned wide_block = 256;
+    unsigned wide_block = 256;
+    if (const char* e = getenv("ODL_WIDE_BLOCK")) wide_block = (unsigned)std::max(32, atoi(e));   // development knob
     if (beside) {
       // measured on B200, 1M two_i prior draws (13k rows, ~6.8M BDF steps for the consumer): 24 SMs 4.96 ms, 32 4.03,
       // 36 3.76, 40 3.71, 44 3.85 (sequential: 4.27) -- about a quarter of the SMs
@@ -1047,6 +1048,10 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   if ((rc = st.inout(io->step_count, (size_t)C, &A.step_count, true))) return rc;
   A.n_chain = C; A.chain_offset = mo->chain_offset; A.it_begin = it_begin; A.it_end = it_end;
   A.burnin = mo->burnin; A.n_keep = n_keep; A.row_stride = stride; A.rng_mode = mo->rng_mode;
+  if (mo->sample_layout != ODL_SAMPLES_CHAIN_MAJOR && mo->sample_layout != ODL_SAMPLES_ITERATION_MAJOR)
+    return fail(ODL_EINVAL, "odl_mcmc: unknown sample_layout");
+  if (mo->sample_layout == ODL_SAMPLES_ITERATION_MAJOR) { A.smp_chain_pitch = stride; A.smp_row_pitch = (long long)C * stride; }
+  else { A.smp_chain_pitch = (long long)n_keep * stride; A.smp_row_pitch = stride; }
   A.n_walk = mo->n_walk; A.pnum = mo->pnum;
   for (int j = 0; j < ODL_MAX_WALK; ++j) A.walk[j] = -1;
   for (int j = 0; j < mo->n_walk; ++j) {

@@ -1746,8 +1746,11 @@ odl_sweep_radau5_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) 
 #endif
 // (register caps for more resident warps spill: 168 registers -> 3.1 ms against 1.6 ms at 226, tools/variant_ab.py).
 // CTAs of one warp when the pass runs after the bulk pass, of 8 warps when it runs beside it on SMs of its own.
+#ifndef ODL_BDF_THREADS
+#define ODL_BDF_THREADS 256
+#endif
 #if ODL_HAS(4)
-extern "C" __global__ void __launch_bounds__(256, 1)
+extern "C" __global__ void __launch_bounds__(ODL_BDF_THREADS, 1)
 odl_sweep_bdf_kernel(const OdlData D, const OdlOpts O, const OdlSweepArgs A) { odl_sweep_body<4>(D, O, A); }
 #endif
 
@@ -2000,12 +2003,6 @@ ODL_UNROLL
       const int adv = (jstar >= 0) ? jstar + 1 : nvalid;                                  // iterations consumed
       const bool consumed = valid && sub < adv;
       const bool is_acc = consumed && sub == jstar;
-      // the accepted proposal, on every lane of the group (for the summaries; lane jstar holds it in p)
-      double pacc[ODL_P];
-      const int src = gbase + (jstar >= 0 ? jstar : 0);
-ODL_UNROLL
-      for (int q = 0; q < ODL_P; ++q) pacc[q] = __shfl_sync(ODL_FULL, p[q], src);
-      const double chi_acc = __shfl_sync(ODL_FULL, my_chi, src), r2_acc = __shfl_sync(ODL_FULL, my_r2, src);
       if (consumed) {
         // counters cover CONSUMED solves only (speculative work that was discarded is not counted)
         if (A.step_count) atomicAdd((unsigned long long*)&A.step_count[chain], (unsigned long long)st.nsteps);
@@ -2014,23 +2011,65 @@ ODL_UNROLL
         const long long k = (long long)chain * A.n_iter_total + (iter - 1);
         if (A.trace_chinew) A.trace_chinew[k] = my_chi;
         if (A.trace_accept) A.trace_accept[k] = is_acc ? 1 : 0;
-        if (iter > A.burnin) {                                   // Samplers.py:147
-          const int rowi = iter - A.burnin - 1;
-          if (A.samples && rowi < A.n_keep) {
-            double* row = A.samples + ((size_t)chain * A.n_keep + rowi) * A.row_stride;
-            const double c = is_acc ? my_chi : chi_cur;
-            double v[ODL_P + 5];
+      }
+      // ---- kept rows (Samplers.py:147-153) -> HBM.  Row (chain, rowi) lives at samples[chain * chain_pitch + rowi *
+      //      row_pitch]: chain-major (the reference frame's order) or iteration-major.  Iteration-major with one lane per
+      //      chain -- the throughput regime, where the stream matters -- puts the 32 rows a warp keeps in one round next
+      //      to each other: they go through the warp's (free) staging rows in shared memory and leave as 32-lane
+      //      contiguous stores, every instruction writing whole sectors.  Otherwise one 16-byte-vector row per lane.
+      {
+        const int iter = it + sub;
+        const int rowi = iter - A.burnin - 1;
+        const bool keep = consumed && rowi >= 0 && A.samples && rowi < A.n_keep;
+        constexpr int LEN = ODL_P + 5;
+        const bool together = K == 1 && A.smp_chain_pitch == (long long)LEN && A.row_stride == LEN && D.stage_stride >= LEN &&
+                              __all_sync(ODL_FULL, keep);
+        const double c = is_acc ? my_chi : chi_cur;
+        if (together) {
 ODL_UNROLL
-            for (int q = 0; q < ODL_P; ++q) v[q] = is_acc ? p[q] : cur[q];
-            v[ODL_P + 0] = c;
-            v[ODL_P + 1] = is_acc ? my_r2 : r2_cur;
-            v[ODL_P + 2] = 2.0 * c + 2.0 * (double)A.pnum;        // stats.py:46
-            v[ODL_P + 3] = (double)iter;
-            v[ODL_P + 4] = (double)(accepts + (is_acc ? 1 : 0)) / (double)iter;   // Samplers.py:153
-            odl_store_row(row, v);
+          for (int q = 0; q < ODL_P; ++q) my_stage[q] = is_acc ? p[q] : cur[q];
+          my_stage[ODL_P + 0] = c;
+          my_stage[ODL_P + 1] = is_acc ? my_r2 : r2_cur;
+          my_stage[ODL_P + 2] = 2.0 * c + 2.0 * (double)A.pnum;   // stats.py:46
+          my_stage[ODL_P + 3] = (double)iter;
+          my_stage[ODL_P + 4] = (double)(accepts + (is_acc ? 1 : 0)) / (double)iter;   // Samplers.py:153
+          __syncwarp();
+          const double* wst = S.stage + (size_t)(threadIdx.x & ~31) * D.stage_stride;
+          double* base = A.samples + (long long)rowi * A.smp_row_pitch + (long long)(chain - lane) * LEN;
+          if ((LEN & 1) == 0 && (((unsigned long long)base) & 15ull) == 0ull) {
+#pragma unroll
+            for (int j = 0; j < LEN / 2; ++j) {                   // 16 bytes per lane, 512 contiguous bytes per instruction
+              const int f = 2 * (j * 32 + lane), l = f / LEN, e = f - l * LEN;
+              const double* src = wst + l * D.stage_stride + e;
+              reinterpret_cast<double2*>(base)[j * 32 + lane] = make_double2(src[0], src[1]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < LEN; ++j) {
+              const int f = j * 32 + lane, l = f / LEN, e = f - l * LEN;
+              base[f] = wst[l * D.stage_stride + e];
+            }
           }
+          __syncwarp();                                            // the staging rows are free again for the next solve
+        } else if (keep) {
+          double v[ODL_P + 5];
+ODL_UNROLL
+          for (int q = 0; q < ODL_P; ++q) v[q] = is_acc ? p[q] : cur[q];
+          v[ODL_P + 0] = c;
+          v[ODL_P + 1] = is_acc ? my_r2 : r2_cur;
+          v[ODL_P + 2] = 2.0 * c + 2.0 * (double)A.pnum;
+          v[ODL_P + 3] = (double)iter;
+          v[ODL_P + 4] = (double)(accepts + (is_acc ? 1 : 0)) / (double)iter;
+          odl_store_row(A.samples + (long long)chain * A.smp_chain_pitch + (long long)rowi * A.smp_row_pitch, v);
         }
       }
+      // the accepted proposal, on every lane of the group (for the summaries; lane jstar holds it in p) -- fetched
+      // only now: nothing above needs it, and the row stores are short of registers
+      double pacc[ODL_P];
+      const int src = gbase + (jstar >= 0 ? jstar : 0);
+ODL_UNROLL
+      for (int q = 0; q < ODL_P; ++q) pacc[q] = __shfl_sync(ODL_FULL, p[q], src);
+      const double chi_acc = __shfl_sync(ODL_FULL, my_chi, src), r2_acc = __shfl_sync(ODL_FULL, my_r2, src);
       // Welford over ln(theta) of the kept rows for R-hat: sequential in the iteration (the same recurrence, in the
       // same order, whatever K is), by the group's first lane
       if (A.summaries && has_chain && sub == 0 && it + adv - 1 > A.burnin) {
@@ -2538,7 +2577,7 @@ odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
       if (iter > A.burnin) {
         const int rowi = iter - A.burnin - 1;
         if (A.samples && rowi < A.n_keep) {
-          double* rowp = A.samples + ((size_t)chain * A.n_keep + rowi) * A.row_stride;
+          double* rowp = A.samples + (long long)chain * A.smp_chain_pitch + (long long)rowi * A.smp_row_pitch;
           const double c = is_acc ? my_chi : chi_cur;
           for (int q = 0; q < ODL_P; ++q) rowp[q] = is_acc ? G.psm[q] : cur[q];
           rowp[ODL_P + 0] = c; rowp[ODL_P + 1] = is_acc ? my_r2 : r2_cur;

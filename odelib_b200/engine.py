@@ -271,11 +271,16 @@ class DeviceModel:
     def mcmc(self, theta0, nits=1000, burnin=None, walk=None, pnum=None, rng_mode="philox", seed=0, chain_offset=0,
              z=None, u=None, forced=None, rtol=None, atol=None, max_steps=500000, solver="dopri5", step_sd=0.05,
              trace=False, keep_samples=True, summaries=True, segments=1, device_buffers=False, speculate=0,
-             chain_ids=None, prior=None):
+             chain_ids=None, prior=None, sample_layout="iteration"):
         """Run len(theta0) independent chains.  Returns dict with numpy arrays (or torch tensors when
         device_buffers=True): theta (final points), samples [C, nits-1-burnin, P+5], summaries
         [C, 1+2P], chain_state [C,8] (chi, r2, accepts, best_chi, best_iteration, ...), best_theta [C, P] (the
         chain's first minimum of chi over its kept rows), and with trace=True chinew/accepted [C, nits-1].
+
+        sample_layout: how the kernel lays the kept rows out in memory -- "iteration" (default: [n_keep][C][P+5], the rows
+        a warp keeps in one iteration are contiguous and leave as coalesced stores) or "chain" ([C][n_keep][P+5]).  Either
+        way ``samples`` comes back indexed [chain, row, column]; for "iteration" that is a transposed VIEW of the buffer
+        (nothing is copied until somebody asks for chain-major memory, e.g. the frame builder's reshape).
 
         prior: None = the reference's chain (prior densities never enter the acceptance ratio, Samplers.py:118-127);
         a list of (kind, a, b, c) per parameter (as sample_lhs) = Metropolis-Hastings on the posterior, the prior
@@ -297,6 +302,8 @@ class DeviceModel:
         mo.row_stride = P + 5
         mo.step_sd, mo.seed = float(step_sd), int(seed) & 0xFFFFFFFFFFFFFFFF
         mo.speculate = int(speculate)
+        it_major = {"iteration": True, "chain": False}[sample_layout]
+        mo.sample_layout = _capi.SAMPLES_ITERATION_MAJOR if it_major else _capi.SAMPLES_CHAIN_MAJOR
 
         if device_buffers:
             import torch
@@ -320,7 +327,7 @@ class DeviceModel:
         mo.n_chain = Cn
         state = new((Cn, 8))
         best = new((Cn, P))
-        samples = new((Cn, n_keep, P + 5)) if keep_samples else None
+        samples = (new((n_keep, Cn, P + 5)) if it_major else new((Cn, n_keep, P + 5))) if keep_samples else None
         summ = new((Cn, 1 + 2 * P)) if summaries else None
         tr_chi = new((Cn, n_iter)) if trace else None
         tr_acc = new((Cn, n_iter), u8) if trace else None
@@ -352,6 +359,8 @@ class DeviceModel:
             _capi.check(self._L.odl_mcmc(self._h, C.byref(so), C.byref(mo), C.byref(io), mem, stream))
             if not device_buffers:
                 ms += self.last_kernel_ms()
+        if samples is not None and it_major:                   # [chain, row, column] view of the iteration-major buffer
+            samples = samples.permute(1, 0, 2) if device_buffers else samples.transpose(1, 0, 2)
         res = {"theta": theta, "chain_state": state, "samples": samples, "summaries": summ, "fail_count": fails,
                "step_count": steps, "kernel_ms": ms, "n_keep": n_keep, "burnin": burnin,
                "best_theta": best, "best_chi": state[:, 3], "best_iteration": state[:, 4]}

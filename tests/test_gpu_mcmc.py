@@ -231,3 +231,26 @@ def test_posterior_ratio_with_device_prior_log_densities_matches_the_oracle():
         assert np.array_equal(k["samples"], with_prior["samples"]) and np.array_equal(k["accepted"], with_prior["accepted"])
     out = dm.mcmc(starts, prior=[("uniform", 0.0, 1.0, 1.0)] * 5, **kw)       # every proposal outside the support
     assert out["accepted"].sum() == 0
+
+
+@pytest.mark.parametrize("C", [5, 64, 70])
+def test_sample_layouts_hold_the_same_rows(C):
+    """Kept rows in chain-major memory (the reference frame's order) and in iteration-major memory (a warp's rows of one
+    iteration contiguous: coalesced full-sector stores when every lane of the warp keeps a row, per-lane rows otherwise
+    -- ragged last warp, speculation) are the same rows; `samples` is indexed [chain, row, column] either way."""
+    import torch
+    name = "two_i"
+    g = golden(name)
+    dm, _ = device_model(name)
+    theta0 = np.tile(g["chain_def_s0_theta0"], (C, 1)) * np.exp(0.02 * np.random.default_rng(C).standard_normal((C, 5)))
+    a = dm.mcmc(theta0, nits=61, seed=4, sample_layout="chain", speculate=1)
+    b = dm.mcmc(theta0, nits=61, seed=4, sample_layout="iteration", speculate=1)
+    c = dm.mcmc(theta0, nits=61, seed=4, sample_layout="iteration", speculate=4)
+    d = dm.mcmc(torch.from_numpy(theta0).cuda(), nits=61, seed=4, speculate=1, device_buffers=True)
+    assert a["samples"].shape == b["samples"].shape == (C, 30, 10) and a["samples"].flags.c_contiguous
+    assert b["samples"].transpose(1, 0, 2).flags.c_contiguous       # the buffer itself is [row][chain][column]
+    assert np.array_equal(a["samples"], b["samples"]) and np.array_equal(a["samples"], c["samples"])
+    assert np.array_equal(a["samples"], d["samples"].cpu().numpy())
+    assert np.all(a["samples"][:, :, 8] == np.arange(31, 61)[None, :])   # iteration column: rows in order, none missing
+    for k in ("summaries", "chain_state", "theta"):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k])
