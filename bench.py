@@ -218,7 +218,6 @@ def run_ours(args):
     import torch.distributed as dist
     import odelib_b200 as ODElib
     from odelib_b200 import _capi, demo_models, engine
-    from odelib_b200.rhat import allgather_summaries, rhat_from_summaries
     import scipy.stats
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -361,8 +360,13 @@ def run_ours(args):
         b.record()
         barrier()
         t_m = max_over_ranks(a.elapsed_time(b) * 1e-3)
-        summ = allgather_summaries(res["summaries"]) if world > 1 else res["summaries"]     # the one collective
-        rh = rhat_from_summaries(summ.cpu().numpy(), P)
+        # the one collective of the path: odl_rhat = ncclAllGather of the chain summaries over NVLink + reduction on the
+        # device, behind the C ABI (torch.distributed only hands the communicator's id to the ranks)
+        dm.comm_init()
+        torch.cuda.synchronize(); t_r0 = time.perf_counter()
+        rh, _, chains_seen = dm.rhat(res["summaries"])
+        t_rhat = time.perf_counter() - t_r0
+        assert chains_seen == C * world
         steps_total = sum_over_ranks(float(res["step_count"].sum().item()))
         kept_bytes = C * res["n_keep"] * (P + 5) * 8
         mcmc = {"chain_steps_per_s": C * world * (nits - 1) / t_m, "chains_per_gpu": C, "chains_total": C * world,
@@ -370,7 +374,10 @@ def run_ours(args):
                 "fp64_tflops": (steps_total * flops_step) / t_m / 1e12 / world,
                 "sample_stream_GBps": kept_bytes / t_m / 1e9,
                 "accept_rate": float(res["chain_state"][:, 2].mean().item()) / (nits - 1),
-                "rhat_max": float(np.nanmax(rh)), "rhat_collective": "nccl all_gather" if world > 1 else "none (1 GPU)"}
+                "rhat_max": float(np.nanmax(rh)), "rhat_seconds": t_rhat,
+                "rhat_note": "500 iterations from scattered starts do not converge (R-hat >> 1): this leg times the kernel",
+                "rhat_collective": "odl_rhat: ncclAllGather over %d ranks + device reduction" % world if world > 1
+                                   else "odl_rhat: device reduction (1 GPU, no collective)"}
 
         # the same kernel with the GPU filled (BASELINE config 5's chain count per GPU x 8): throughput regime
         if args.chains_large > 0:

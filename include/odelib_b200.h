@@ -22,6 +22,7 @@
  *   odl_gather_rows         resampling of acceptable survey rows (Framework.py:993-1016).
  *   odl_sample_lhs       <- Samplers.sample_lhs (Statistics/Samplers.py:6-51) under _lhs_samples
  *                           (Framework.py:589-615), for large surveys.
+ *   odl_comm_*, odl_rhat <- the gather of the workers' results (Framework.py:1035-1038); R-hat itself is new.
  *   odl_fp64_peak        <- (no reference counterpart) measures the FP64 FMA roofline denominator.
  *
  * Conventions: every function returns 0 on success or an ODL_E* code; odl_last_error() gives the
@@ -208,6 +209,22 @@ int odl_sample_lhs(odl_model* m, long long n, int n_param, const int* kind, cons
    u [n_chain][n_iter]; feed them to odl_mcmc with ODL_RNG_HOST_STREAMS. */
 int odl_reference_streams(const unsigned int* seeds, int n_chain, int n_iter, int n_walk, int n_prior_draws,
                           double step_sd, double* z, double* u);
+
+/* The one collective of the path (the reference gathers its workers' frames with pd.concat,
+   Framework.py:1035-1038, and has no R-hat): Gelman-Rubin R-hat on ln(theta) over the chains of EVERY rank.
+   odl_comm_unique_id: rank 0 draws an NCCL id (ODL_COMM_ID_BYTES bytes) and hands it to the other ranks by whatever
+   means the launcher offers; odl_comm_init: every rank joins (ncclCommInitRank on the model's device; world 1 needs no
+   NCCL); odl_rhat: ncclAllGather of the per-chain summaries (count, mean[P], M2[P] -- odl_mcmc_io.summaries; shards may
+   differ in length) over NVLink, reduction on the device: rhat_host[P] = sqrt(((n-1)/n W + B/n) / W) with W = mean_j
+   s_j^2, B = n var_j(mean_j) (ddof 1); pooled_host[1+2P] = count, mean[P], M2[P] of ALL kept rows pooled (the two
+   moments the fitting report's rawstats takes from the frame, Framework.py:11-17).  Without odl_comm_init: the local
+   chains alone.  NCCL is dlopen()ed at the first use; the library has no link dependency on it. */
+#define ODL_COMM_ID_BYTES 128
+int odl_comm_unique_id(unsigned char* id128);
+int odl_comm_init(odl_model* m, const unsigned char* id128, int world, int rank);
+int odl_comm_destroy(odl_model* m);
+int odl_rhat(odl_model* m, const double* summaries, int n_chain_local, int n_param, int mem, double* rhat_host,
+             double* pooled_host_or_null, long long* n_chain_total_or_null, void* stream);
 
 /* device time (ms) of the kernels launched by the last odl_sweep/odl_mcmc/odl_trajectory call on this
    model, measured with CUDA events on the launching stream; blocks until they have completed */

@@ -613,6 +613,10 @@ class ModelFramework:
                      "fail_count": np.empty(0, np.int32), "step_count": np.empty(0, np.int64), "best_theta": np.empty((0, P)),
                      "samples": np.empty((0, n_keep, P + 5)) if want_frame else None, "n_keep": n_keep, "burnin": burnin}
         out = dict(local)
+        if C > 1 and local["n_keep"] > 1:                         # R-hat: odl_rhat (ncclAllGather + device reduction)
+            dm = self._device()
+            dm.comm_init()
+            out["rhat_device"] = dm.rhat(np.asarray(local["summaries"]))
         for key in ("theta", "chain_state", "summaries", "fail_count", "step_count", "best_theta"):
             out[key] = allgather_rows(np.asarray(local[key]))
         out["best_chi"], out["best_iteration"] = out["chain_state"][:, 3], out["chain_state"][:, 4]
@@ -792,6 +796,8 @@ class ModelFramework:
             out = {k: (v.cpu().numpy() if hasattr(v, "is_cuda") and k != "samples" else v) for k, v in out.items()}
             if out["samples"] is not None and (return_frame or not return_raw):
                 out["samples"] = out["samples"].cpu().numpy()
+        if C > 1 and out["n_keep"] > 1 and out.get("summaries") is not None and self._world()[0] == 1:
+            out["rhat_device"] = dm.rhat(np.asarray(out["summaries"]))   # odl_rhat: reduction on the device
         self._last_mcmc = out
         if return_raw:
             return out
@@ -878,7 +884,10 @@ class ModelFramework:
             if p in (static_parameters or ()):
                 best[f] = self.parameters[p].hp['scale']
         C = len(best_chi)
-        rh = dict(zip(fn, rhat_from_summaries(out["summaries"], P))) if C > 1 and out["n_keep"] > 1 else None
+        if C > 1 and out["n_keep"] > 1:                           # from odl_rhat when the chains ran through it
+            rh = dict(zip(fn, out["rhat_device"][0] if "rhat_device" in out else rhat_from_summaries(out["summaries"], P)))
+        else:
+            rh = None
         ess = dict(zip(fn, ess_from_summaries(out["summaries"], P))) if rh is not None else None
         n_iter = max(1, int(out["n_keep"]) + int(out["burnin"]))
         acc = float(np.asarray(out["chain_state"])[:, 2].mean()) / n_iter

@@ -14,13 +14,15 @@ MEM_HOST, MEM_DEVICE = 0, 1
 SOLVER_DOPRI5, SOLVER_ROS23, SOLVER_AUTO, SOLVER_RADAU5, SOLVER_BDF = 0, 1, 2, 3, 4
 RNG_PHILOX, RNG_HOST_STREAMS, RNG_FORCED = 0, 1, 2
 SAMPLES_CHAIN_MAJOR, SAMPLES_ITERATION_MAJOR = 0, 1
+COMM_ID_BYTES = 128
 AUTO_UNORDERED, AUTO_CONCURRENT, AUTO_ONE_PIECE, AUTO_SEQUENTIAL = 1, 2, 4, 8
 ST_OK, ST_MAXSTEPS, ST_NONFINITE, ST_HUNDERFLOW, ST_STIFF, ST_ALLMASKED = 0, 1, 2, 3, 4, 8
 
 EXPORTS = ["odl_abi_version", "odl_last_error", "odl_model_create", "odl_model_destroy", "odl_model_build_log",
            "odl_model_kernel_info", "odl_model_set_data", "odl_model_set_grid", "odl_sweep", "odl_trajectory",
            "odl_mcmc", "odl_model_last_kernel_ms", "odl_model_last_pass_ms", "odl_launch_count", "odl_fp64_peak", "odl_debug_counters", "odl_select_below", "odl_gather_rows", "odl_sample_lhs", "odl_reference_streams",
-           "odl_model_unit_seconds", "odl_debug_timeline"]
+           "odl_model_unit_seconds", "odl_debug_timeline", "odl_comm_unique_id", "odl_comm_init", "odl_comm_destroy",
+           "odl_rhat"]
 
 
 class OdlError(RuntimeError):
@@ -97,6 +99,10 @@ def lib():
     L.odl_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
                                   C.c_void_p]
     L.odl_model_unit_seconds.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.odl_comm_unique_id.argtypes = [C.c_void_p]
+    L.odl_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.odl_comm_destroy.argtypes = [C.c_void_p]
+    L.odl_rhat.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_longlong), C.c_void_p]
     L.odl_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     if L.odl_abi_version() != 2:
         raise OdlError(EIO, "libodelib_b200.so ABI version mismatch - rebuild")

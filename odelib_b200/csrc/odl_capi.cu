@@ -7,6 +7,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <nvrtc.h>
+#include <nccl.h>     // types and prototypes only: the library is dlopen()ed at the first collective (no link dependency)
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -171,6 +173,8 @@ struct odl_model {
   cudaEvent_t ev_chunk[3] = {nullptr, nullptr, nullptr};   // host-memory sweeps: theta arrives in pieces on the helper stream
   cudaStream_t aux = nullptr;                // helper stream: theta pieces of a host-memory sweep
   cudaStream_t aux2 = nullptr;               // helper stream: the stiff pass beside the DOPRI5 pass
+  ncclComm_t comm = nullptr;                 // odl_comm_init: the ranks that share an MCMC run (R-hat all-gather)
+  int comm_world = 1, comm_rank = 0;
   int n_pass = 0;
   bool timed = false;
   bool coop_model() const { return n_state > 8; }
@@ -460,6 +464,7 @@ extern "C" int odl_model_destroy(odl_model* m) {
     cudaSetDevice(m->device);
     for (Unit& u : m->units) if (u.mod && g_drv.ModuleUnload) g_drv.ModuleUnload(u.mod);
   }
+  odl_comm_destroy(m);
   m->data.buf.release(); m->grid.buf.release(); m->counter.release();
   for (auto& s : m->scratch) s.release();
   if (m->ev0) cudaEventDestroy(m->ev0);
@@ -1463,6 +1468,191 @@ extern "C" int odl_reference_streams(const unsigned int* seeds, int n_chain, int
   for (int t = 0; t < n_thr; ++t)
     pool.emplace_back(run, (int)((long long)n_chain * t / n_thr), (int)((long long)n_chain * (t + 1) / n_thr));
   for (auto& th : pool) th.join();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The one collective of the path: Gelman-Rubin R-hat over the chains of every rank.  The reference
+// has no counterpart (its gather is pd.concat of the workers' frames, Framework.py:1035-1038, and it has no R-hat);
+// here the per-chain Welford summaries (count, mean[P], M2[P] of ln theta, written by the MCMC kernel) are all-gathered
+// with ncclAllGather over NVLink / NVSwitch and reduced on the device: per parameter W = mean_j s_j^2,
+// B = n var_j(mean_j) (ddof 1), R-hat = sqrt(((n-1)/n W + B/n) / W), plus the pooled count / mean / M2 of all kept rows
+// (what the fitting report's rawstats needs).  NCCL is loaded with dlopen at the first use: no link-time dependency,
+// the library still loads (and computes on one GPU) where NCCL is absent.
+// ---------------------------------------------------------------------------------------------
+struct Nccl {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static Nccl g_nccl;
+static int load_nccl() {
+  if (g_nccl.ok) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);       // a copy torch has loaded already is reused (same SONAME)
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(ODL_ENODEVICE, std::string("NCCL is not available: ") + dlerror());
+  auto sym = [&](const char* n) { return dlsym(h, n); };
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(sym("ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(sym("ncclCommInitRank"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(sym("ncclCommDestroy"));
+  g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(sym("ncclAllGather"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(sym("ncclAllReduce"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(sym("ncclGetErrorString"));
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.AllReduce || !g_nccl.GetErrorString)
+    return fail(ODL_ENODEVICE, "NCCL library lacks an expected entry point");
+  g_nccl.ok = true;
+  return 0;
+}
+#define ODL_NCCL(call)                                                                                      \
+  do {                                                                                                      \
+    ncclResult_t r_ = (call);                                                                               \
+    if (r_ != ncclSuccess) return fail(ODL_ECUDA, std::string(#call) + ": " + g_nccl.GetErrorString(r_));   \
+  } while (0)
+
+extern "C" int odl_comm_unique_id(unsigned char* id128) {
+  if (!id128) return fail(ODL_EINVAL, "odl_comm_unique_id: null argument");
+  int rc = load_nccl();
+  if (rc) return rc;
+  ncclUniqueId id;
+  ODL_NCCL(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(id) == ODL_COMM_ID_BYTES, "ncclUniqueId size");
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+
+extern "C" int odl_comm_init(odl_model* m, const unsigned char* id128, int world, int rank) {
+  if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_comm_init: model is not loaded on a GPU");
+  if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(ODL_EINVAL, "odl_comm_init: bad argument");
+  odl_comm_destroy(m);
+  m->comm_world = world; m->comm_rank = rank;
+  if (world == 1) return 0;                                       // nothing to gather from
+  int rc = load_nccl();
+  if (rc) return rc;
+  ODL_ON_DEVICE(m);
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  ODL_NCCL(g_nccl.CommInitRank(&m->comm, world, id, rank));
+  return 0;
+}
+
+extern "C" int odl_comm_destroy(odl_model* m) {
+  if (m && m->comm && g_nccl.ok) { g_nccl.CommDestroy(m->comm); }
+  if (m) { m->comm = nullptr; m->comm_world = 1; m->comm_rank = 0; }
+  return 0;
+}
+
+// one CTA per parameter; chains with count == 0 (padding of ragged shards) are skipped.  out[q] = R-hat,
+// pooled[0] = N, pooled[1+q] = mean, pooled[1+P+q] = M2 over all kept rows of all chains.
+__device__ __forceinline__ double odl_block_sum(double v, double* sh) {
+  const int t = threadIdx.x;
+  sh[t] = v;
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) {            // fixed tree: the same result on every rank, every run
+    if (t < off) sh[t] += sh[t + off];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+__global__ void __launch_bounds__(256) odl_rhat_kernel(const double* summ, long long n_chain, int P, double* rhat, double* pooled) {
+  __shared__ double sh[256];
+  const int q = blockIdx.x;
+  const int W = 1 + 2 * P;
+  double m = 0.0, n_first = 0.0, N = 0.0, sm = 0.0, sw = 0.0, nsm = 0.0;
+  for (long long c = threadIdx.x; c < n_chain; c += blockDim.x) {
+    const double n = summ[c * W];
+    if (n > 0.0) {
+      m += 1.0; N += n;
+      if (n_first == 0.0) n_first = n;
+      sm += summ[c * W + 1 + q];
+      nsm += n * summ[c * W + 1 + q];
+      sw += summ[c * W + 1 + P + q] / (n - 1.0);                  // s_j^2
+    }
+  }
+  const double M = odl_block_sum(m, sh), Nall = odl_block_sum(N, sh);
+  const double mean_of_means = odl_block_sum(sm, sh) / M;
+  const double pooled_mean = odl_block_sum(nsm, sh) / Nall;
+  const double Wv = odl_block_sum(sw, sh) / M;
+  // n: the reference keeps the same number of rows in every chain (nits - 1 - burnin); take the largest count seen
+  sh[threadIdx.x] = n_first;
+  __syncthreads();
+  for (int off = blockDim.x >> 1; off > 0; off >>= 1) { if (threadIdx.x < off) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + off]); __syncthreads(); }
+  const double n = sh[0];
+  __syncthreads();
+  double sb = 0.0, m2 = 0.0;
+  for (long long c = threadIdx.x; c < n_chain; c += blockDim.x) {
+    const double nc = summ[c * W];
+    if (nc > 0.0) {
+      const double mu = summ[c * W + 1 + q];
+      sb += (mu - mean_of_means) * (mu - mean_of_means);
+      m2 += summ[c * W + 1 + P + q] + nc * (mu - pooled_mean) * (mu - pooled_mean);
+    }
+  }
+  const double B = n * odl_block_sum(sb, sh) / (M - 1.0);
+  const double M2 = odl_block_sum(m2, sh);
+  if (threadIdx.x == 0) {
+    rhat[q] = sqrt(((n - 1.0) / n * Wv + B / n) / Wv);
+    pooled[1 + q] = pooled_mean; pooled[1 + P + q] = M2;
+    if (q == 0) pooled[0] = Nall;
+  }
+}
+
+extern "C" int odl_rhat(odl_model* m, const double* summaries, int n_chain_local, int n_param, int mem, double* rhat_host,
+                        double* pooled_host_or_null, long long* n_chain_total_or_null, void* stream) {
+  if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_rhat: model is not loaded on a GPU (no CPU fallback exists)");
+  if (n_chain_local < 0 || n_param < 1 || !rhat_host || (n_chain_local > 0 && !summaries)) return fail(ODL_EINVAL, "odl_rhat: bad argument");
+  ODL_ON_DEVICE(m);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if ((rc = serialize_after_previous_call(m, s))) return rc;
+  ODL_CUDA(cudaEventRecord(m->ev0, s));
+  const size_t W = 1 + 2 * (size_t)n_param;
+  const int world = m->comm ? m->comm_world : 1;
+  // scratch: [0] padded local block, [1] gathered table, [2] results (rhat[P], pooled[1+2P], n_pad)
+  DevBuf &bloc = m->scratch[0], &ball = m->scratch[1], &bres = m->scratch[2];
+  if ((rc = bres.ensure((n_param + W + 2) * sizeof(double)))) return rc;
+  double* d_rhat = static_cast<double*>(bres.p);
+  double* d_pooled = d_rhat + n_param;
+  int* d_npad = reinterpret_cast<int*>(d_pooled + W);
+  int n_pad = n_chain_local;
+  if (world > 1) {
+    // shards may differ in length: everybody sends the largest shard's row count, short shards pad with count-0 rows
+    ODL_CUDA(cudaMemcpyAsync(d_npad, &n_chain_local, sizeof(int), cudaMemcpyHostToDevice, s));
+    ODL_NCCL(g_nccl.AllReduce(d_npad, d_npad, 1, ncclInt32, ncclMax, m->comm, s));
+    ODL_CUDA(cudaMemcpyAsync(&n_pad, d_npad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ODL_CUDA(cudaStreamSynchronize(s));
+  }
+  const double* table = summaries;
+  long long n_total = n_chain_local;
+  if (world > 1 || mem == ODL_MEM_HOST) {
+    if ((rc = bloc.ensure(std::max<size_t>(1, (size_t)n_pad) * W * sizeof(double)))) return rc;
+    ODL_CUDA(cudaMemsetAsync(bloc.p, 0, std::max<size_t>(1, (size_t)n_pad) * W * sizeof(double), s));
+    if (n_chain_local > 0)
+      ODL_CUDA(cudaMemcpyAsync(bloc.p, summaries, (size_t)n_chain_local * W * sizeof(double),
+                               mem == ODL_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    table = static_cast<const double*>(bloc.p);
+  }
+  if (world > 1) {
+    if ((rc = ball.ensure((size_t)world * n_pad * W * sizeof(double)))) return rc;
+    ODL_NCCL(g_nccl.AllGather(bloc.p, ball.p, (size_t)n_pad * W, ncclFloat64, m->comm, s));
+    table = static_cast<const double*>(ball.p);
+    n_total = (long long)world * n_pad;
+  }
+  if (n_total < 1) return fail(ODL_EINVAL, "odl_rhat: no chains");
+  odl_rhat_kernel<<<n_param, 256, 0, s>>>(table, n_total, n_param, d_rhat, d_pooled);
+  g_launches.fetch_add(1);
+  ODL_CUDA(cudaGetLastError());
+  ODL_CUDA(cudaMemcpyAsync(rhat_host, d_rhat, n_param * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (pooled_host_or_null) ODL_CUDA(cudaMemcpyAsync(pooled_host_or_null, d_pooled, W * sizeof(double), cudaMemcpyDeviceToHost, s));
+  ODL_CUDA(cudaEventRecord(m->ev1, s));
+  m->timed = true; m->n_pass = 1;
+  ODL_CUDA(cudaStreamSynchronize(s));
+  if (n_chain_total_or_null) *n_chain_total_or_null = n_total;
   return 0;
 }
 

@@ -254,6 +254,49 @@ class DeviceModel:
                                             picks.size, _ptr(dst), self._stream()))
         return dst
 
+    # -- the one collective: R-hat over the chains of every rank ----------------------
+    def comm_init(self, group=None):
+        """Join the NCCL communicator of this model's library handle: rank 0 draws the id (odl_comm_unique_id), the
+        process group that torchrun set up carries its 128 bytes to the other ranks (plumbing), every rank calls
+        odl_comm_init.  Without an initialised process group (one GPU): world 1, no NCCL."""
+        import torch
+        import torch.distributed as dist
+        if getattr(self, "_comm_world", None) is not None:
+            return self._comm_world
+        world, rank = 1, 0
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+        idbuf = np.zeros(_capi.COMM_ID_BYTES, np.uint8)
+        if world > 1:
+            if rank == 0:
+                _capi.check(self._L.odl_comm_unique_id(idbuf.ctypes.data))
+            dev = torch.device("cuda", self.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            t = torch.from_numpy(idbuf).to(dev)
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            idbuf = t.cpu().numpy()
+        _capi.check(self._L.odl_comm_init(self._h, idbuf.ctypes.data, world, rank))
+        self._comm_world = world
+        return world
+
+    def rhat(self, summaries):
+        """Gelman-Rubin R-hat [P] over the chains of all ranks from this rank's per-chain summaries [m_local, 1+2P]
+        (numpy or CUDA tensor): odl_rhat -- ncclAllGather + reduction on the device.  Also returns the pooled
+        (count, log_mean[P], log_std[P]) of all kept rows and the total number of chains."""
+        P = self.n_param
+        if _is_torch_cuda(summaries):
+            sm, mem = summaries.contiguous(), _capi.MEM_DEVICE
+        else:
+            sm, mem = np.ascontiguousarray(summaries, dtype=np.float64), _capi.MEM_HOST
+        rh = np.empty(P)
+        pooled = np.empty(1 + 2 * P)
+        total = C.c_longlong(0)
+        _capi.check(self._L.odl_rhat(self._h, _ptr(sm), int(sm.shape[0]), P, mem, rh.ctypes.data, pooled.ctypes.data,
+                                     C.byref(total), self._stream() if mem == _capi.MEM_DEVICE else None))
+        N = pooled[0]
+        with np.errstate(all="ignore"):
+            std = np.sqrt(pooled[1 + P:] / (N - 1.0)) if N > 1 else np.full(P, np.nan)
+        return rh, (float(N), pooled[1:1 + P].copy(), std), int(total.value)
+
     # -- full-grid trajectories: ModelFramework.integrate (Framework.py:656) -----------------------
     def trajectory(self, theta, y0=None, rtol=None, atol=None, max_steps=500000):
         so = self._solver_opts(rtol, atol, max_steps, "dopri5", False)

@@ -147,6 +147,8 @@ def sharded_mcmc(dm, theta0_all, group=None, **mcmc_kw):
     rank = dist.get_rank(group) if ws > 1 else 0
     lo, hi = shard_bounds(len(theta0_all), ws, rank)
     res = dm.mcmc(theta0_all[lo:hi], chain_offset=lo, device_buffers=True, **mcmc_kw)
-    summ = allgather_summaries(res["summaries"], group=group)
-    rh = rhat_from_summaries(summ.cpu().numpy(), dm.n_param)
+    # the one collective of the path, behind the C ABI: odl_rhat = ncclAllGather of the chain summaries + reduction on
+    # the device (torch.distributed only carried the communicator's id to the ranks)
+    dm.comm_init(group)
+    rh, _, _ = dm.rhat(res["summaries"])
     return res, rh, (lo, hi)

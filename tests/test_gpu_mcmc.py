@@ -254,3 +254,28 @@ def test_sample_layouts_hold_the_same_rows(C):
     assert np.all(a["samples"][:, :, 8] == np.arange(31, 61)[None, :])   # iteration column: rows in order, none missing
     for k in ("summaries", "chain_state", "theta"):
         assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k])
+
+
+def test_rhat_through_the_abi_equals_numpy():
+    """odl_rhat (device reduction; with several ranks behind an ncclAllGather): R-hat and the pooled log-moments of all
+    kept rows against the numpy formulas on the same summaries; rows with count 0 (padding of ragged shards) are skipped."""
+    import torch
+    from odelib_b200.rhat import pooled_log_stats, rhat_from_summaries
+    name = "two_i"
+    g = golden(name)
+    dm, _ = device_model(name)
+    C = 300
+    theta0 = np.tile(g["chain_def_s0_theta0"], (C, 1)) * np.exp(0.05 * np.random.default_rng(5).standard_normal((C, 5)))
+    out = dm.mcmc(theta0, nits=120, seed=8, keep_samples=False)
+    assert dm.comm_init() == 1                                      # no process group: world of one, no NCCL
+    for summ in (out["summaries"], torch.from_numpy(out["summaries"]).cuda()):
+        rh, (N, mean, std), total = dm.rhat(summ)
+        assert total == C and N == C * out["n_keep"]
+        np.testing.assert_allclose(rh, rhat_from_summaries(out["summaries"], 5), rtol=1e-12)
+        N2, mean2, std2 = pooled_log_stats(out["summaries"], 5)
+        np.testing.assert_allclose(mean, mean2, rtol=1e-13)
+        np.testing.assert_allclose(std, std2, rtol=1e-11)
+    padded = np.vstack([out["summaries"][:100], np.zeros((7, 11)), out["summaries"][100:]])
+    rh2, _, total2 = dm.rhat(padded)
+    assert total2 == C + 7
+    np.testing.assert_allclose(rh2, rhat_from_summaries(out["summaries"], 5), rtol=1e-12)

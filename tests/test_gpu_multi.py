@@ -32,12 +32,12 @@ def test_one_vs_n_gpus_identical(tmp_path):
     assert int(b["world"]) >= 2
     np.testing.assert_array_equal(a["samples"], b["samples"])
     np.testing.assert_array_equal(a["chi"], b["chi"])
-    np.testing.assert_allclose(a["rhat"], b["rhat"], rtol=1e-13)
+    np.testing.assert_allclose(a["rhat"], b["rhat"], rtol=1e-12)       # odl_rhat: ncclAllGather + device reduction
     # ModelFramework(distributed=True): fit_survey / MCMC sharded by the facade return what one GPU returns
     np.testing.assert_array_equal(a["facade_survey"], b["facade_survey"])
     assert b["facade_post"].shape == (7 * 39, 11)
     np.testing.assert_array_equal(a["facade_post"], b["facade_post"])
     np.testing.assert_array_equal(a["facade_one"], b["facade_one"])
-    np.testing.assert_allclose(a["facade_rhat"], b["facade_rhat"], rtol=1e-13)
+    np.testing.assert_allclose(a["facade_rhat"], b["facade_rhat"], rtol=1e-12)
     np.testing.assert_allclose(a["facade_ess"], b["facade_ess"], rtol=1e-12)
     np.testing.assert_array_equal(a["facade_best"], b["facade_best"])
