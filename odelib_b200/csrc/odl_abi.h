@@ -64,6 +64,8 @@ struct OdlSweepArgs {
                                            //   consumer overwrites an entry with -2 when it takes it)
   const int* feed_done;                    // set to 1 by odl_feed_done_kernel after the last bulk launch of the sweep
   int* watchdog;                           // consumer: incremented when a warp gave up waiting for the feed
+  int* resident;                           // consumer: +1 per CTA once it runs (odl_gate_kernel holds the bulk launch
+                                           //   back until every consumer CTA has its SM)
   long long* timeline;                     // development (kernels built with -DODL_TIMELINE=1, else unused): per feed
                                            //   entry %globaltimer at [0] deferral, [1] start and [2] end of its stiff solve
 };

@@ -64,6 +64,7 @@ struct Driver {
   CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
   CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;
   bool ok = false;
 };
 static Driver g_drv;
@@ -83,7 +84,7 @@ static int load_driver() {
             entry("cuModuleGetFunction", g_drv.ModuleGetFunction) && entry("cuLaunchKernel", g_drv.LaunchKernel) &&
             entry("cuFuncSetAttribute", g_drv.FuncSetAttribute) && entry("cuFuncGetAttribute", g_drv.FuncGetAttribute) &&
             entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", g_drv.OccupancyMaxActiveBlocksPerMultiprocessor) &&
-            entry("cuGetErrorString", g_drv.GetErrorString);
+            entry("cuGetErrorString", g_drv.GetErrorString) && entry("cuLaunchKernelEx", g_drv.LaunchKernelEx);
   if (!ok) {
     cudaGetLastError();
     return fail(ODL_ENODEVICE, "CUDA driver entry points unavailable (no GPU / driver on this host)");
@@ -162,7 +163,7 @@ struct odl_model {
   CUfunction k_sweep_ros = nullptr, k_mcmc_ros = nullptr, k_mcmc_auto = nullptr;
   CUfunction k_sweep_radau = nullptr, k_mcmc_radau = nullptr;
   CUfunction k_sweep_bdf = nullptr, k_mcmc_bdf = nullptr;
-  CUfunction k_order_key = nullptr, k_order_scan = nullptr, k_order_scatter = nullptr, k_feed_done = nullptr;
+  CUfunction k_order_key = nullptr, k_order_scan = nullptr, k_order_scatter = nullptr, k_feed_done = nullptr, k_gate = nullptr;
   CUfunction k_sweep_coop = nullptr, k_mcmc_coop = nullptr;   // n > 8 only: several lanes per system
   Tables data, grid;
   DevBuf counter;
@@ -331,7 +332,7 @@ static const KernelSlot kKernels[] = {
     {"odl_mcmc_radau5_kernel", &odl_model::k_mcmc_radau, U_MCMC_RADAU}, {"odl_sweep_bdf_kernel", &odl_model::k_sweep_bdf, U_SWEEP_BDF},
     {"odl_mcmc_bdf_kernel", &odl_model::k_mcmc_bdf, U_MCMC_BDF}, {"odl_order_key_kernel", &odl_model::k_order_key, U_ORDER},
     {"odl_order_scan_kernel", &odl_model::k_order_scan, U_ORDER}, {"odl_order_scatter_kernel", &odl_model::k_order_scatter, U_ORDER},
-    {"odl_feed_done_kernel", &odl_model::k_feed_done, U_ORDER},
+    {"odl_feed_done_kernel", &odl_model::k_feed_done, U_ORDER}, {"odl_gate_kernel", &odl_model::k_gate, U_ORDER},
     {"odl_sweep_coop_kernel", &odl_model::k_sweep_coop, U_SWEEP_COOP}, {"odl_mcmc_coop_kernel", &odl_model::k_mcmc_coop, U_MCMC_COOP}};
 
 // compiled + loaded on the model's device + its CUfunctions fetched
@@ -665,6 +666,30 @@ static int launch(odl_model* m, CUfunction f, unsigned grid, unsigned block, siz
   return 0;
 }
 
+// launch with thread-block clusters of `cluster` CTAs: the CTAs of a cluster are placed on SMs of one GPC next to each
+// other (2 = the two SMs of a TPC).  The kernels do not use cluster features; this is about WHERE the CTAs land.
+static int launch_clustered(odl_model* m, CUfunction f, unsigned grid, unsigned block, size_t smem, cudaStream_t s, void** params,
+                            unsigned cluster) {
+  if (cluster <= 1) return launch(m, f, grid, block, smem, s, params);
+  if (!f) return fail(ODL_ECUDA, "internal: launch of a kernel whose unit is not loaded");
+  if (smem > 48 * 1024) ODL_CU(g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+  CUlaunchAttribute attr{};
+  attr.id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
+  attr.value.clusterDim.x = cluster; attr.value.clusterDim.y = 1; attr.value.clusterDim.z = 1;
+  CUlaunchConfig cfg{};
+  cfg.gridDimX = grid; cfg.gridDimY = 1; cfg.gridDimZ = 1;
+  cfg.blockDimX = block; cfg.blockDimY = 1; cfg.blockDimZ = 1;
+  cfg.sharedMemBytes = (unsigned)smem; cfg.hStream = (CUstream)s; cfg.attrs = &attr; cfg.numAttrs = 1;
+  CUresult r = g_drv.LaunchKernelEx(&cfg, f, params, nullptr);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuLaunchKernelEx(grid %u, block %u, smem %zu, cluster %u): ", grid, block, smem, cluster);
+    return fail(ODL_ECUDA, buf + cu_err(r));
+  }
+  g_launches.fetch_add(1);
+  return 0;
+}
+
 // stage a host array on the device (in) or reserve room for a result (out)
 struct Staging {
   odl_model* m; cudaStream_t s; int next = 0; int mem;
@@ -833,6 +858,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     CUfunction k_tail = tail_solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau : m->k_sweep_bdf;
     // counter block (zeroed above): [0] bulk work counter (+ [384], [448] for later pieces), [64] feed count,
     // [128] feed ticket, [192] feed-complete flag, [256] work counter of the pick-up launch, [320] watchdog,
+    // [512] consumer CTAs resident,
     // [1024] hist[256], [2048] cursor[256] (per piece)
     ODL_CUDA(cudaMemsetAsync(feed, 0xFF, (size_t)n * sizeof(int), s));
     // ordering of one piece [lo, hi) of the table -> index[lo..hi) (global row numbers)
@@ -891,14 +917,23 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     if (per_sm0 < 1 || per_sm_t < 1) return fail(ODL_ECUDA, "sweep kernel does not fit on an SM (shared memory / registers)");
     // SMs set aside for the stiff pass when it runs beside the bulk pass
     int tail_sms = 0;
+    unsigned tail_cluster = 1;
     size_t smem_wide = 0;
     unsigned wide_block = 256;
     if (const char* e = getenv("ODL_WIDE_BLOCK")) wide_block = (unsigned)std::max(32, atoi(e));   // development knob
     if (beside) {
-      // measured on B200, 1M two_i prior draws (13k rows, ~6.8M BDF steps for the consumer): 24 SMs 4.96 ms, 32 4.03,
-      // 36 3.76, 40 3.71, 44 3.85 (sequential: 4.27) -- about a quarter of the SMs
-      tail_sms = so && so->tail_warps > 0 ? so->tail_warps : (m->sm_count * 26 + 50) / 100;
+      // measured on B200, 1M two_i prior draws (15k rows, ~7M BDF steps for the consumer), back-to-back calls behind an
+      // L2 flush as bench.py times them, consumer CTAs in clusters of 2: 34 SMs 3.98 ms, 36 3.88, 40 3.73, 42 3.62,
+      // 44 3.67 (stiff pass after the bulk pass: 4.1-4.3) -- between a quarter and a third of the SMs
+      tail_sms = so && so->tail_warps > 0 ? so->tail_warps : (m->sm_count * 29 + 50) / 100;
       tail_sms = std::max(1, std::min(tail_sms, m->sm_count / 3));
+      // Placement: on an idle GPU the block scheduler packs the consumer's CTAs onto neighbouring SMs, behind other
+      // work it scatters them -- and a consumer SM whose TPC partner runs the bulk kernel steps 8-12 % slower
+      // (measured with %smid: both kernels are large, 46 and 58 KB of code).  Clusters of CTAs keep the consumer on
+      // whole TPCs (2) or larger pieces of a GPC.
+      tail_cluster = 2;
+      if (const char* e = getenv("ODL_TAIL_CLUSTER")) tail_cluster = (unsigned)std::max(1, atoi(e));   // development knob
+      tail_sms = std::max((int)tail_cluster, tail_sms / (int)tail_cluster * (int)tail_cluster);
       // a CTA of the consumer must leave no room for a bulk CTA on its SM: ask for (SM shared memory) - (one bulk CTA)
       const size_t sm_total = 228 * 1024, reserve = 1024;
       smem_wide = std::max(smem_bytes(D, (int)wide_block), sm_total - reserve - (smem0 + reserve) + 1024);
@@ -929,15 +964,22 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       // consumer first, on the helper stream: it is resident on its SMs before the bulk grid is launched
       OdlOpts Oc = O2; Oc.lanes = 0;
       OdlSweepArgs Ac = A2;
-      Ac.counter = nullptr; Ac.feed_ticket = ctr(128); Ac.feed_done = cnt(192); Ac.watchdog = cnt(320);
+      Ac.counter = nullptr; Ac.feed_ticket = ctr(128); Ac.feed_done = cnt(192); Ac.watchdog = cnt(320); Ac.resident = cnt(512);
       void* pc[] = {&Dl, &Oc, &Ac};
       ODL_CUDA(cudaEventRecord(m->ev_fork, s));                  // after the counter block and the feed list are reset
       ODL_CUDA(cudaStreamWaitEvent(m->aux2, m->ev_fork, 0));
-      if ((rc = launch(m, k_tail, (unsigned)tail_sms, wide_block, smem_wide, m->aux2, pc))) return rc;
+      if ((rc = launch_clustered(m, k_tail, (unsigned)tail_sms, wide_block, smem_wide, m->aux2, pc, tail_cluster))) return rc;
       ODL_CUDA(cudaEventRecord(m->ev_aux, m->aux2));
     }
     if (chunked) ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[0], 0));
     if (ordered && (rc = order_piece(0, cut[1], 0))) return rc;
+    if (beside) {
+      // the bulk grid must not arrive before the consumer's CTAs have their SMs (see odl_gate_kernel)
+      const int* res = cnt(512);
+      int want = tail_sms, spins = 4000;                         // ~2 ms at most
+      void* pg[] = {&res, &want, &spins};
+      if ((rc = launch(m, m->k_gate, 1, 1, 0, s, pg))) return rc;
+    }
     ODL_CUDA(cudaEventRecord(m->evp[1], s));
     void* pb[] = {&Dl, &O0, &A0};
     if (coop_bulk) { if ((rc = go_coop(s, O0, A0, n))) return rc; }              // n > 8: several lanes per system

@@ -1545,6 +1545,15 @@ odl_order_scatter_kernel(const OdlOrderArgs A) {
 }
 // follows the last bulk launch of an AUTO sweep in its stream: the feed list of the stiff pass is complete
 extern "C" __global__ void odl_feed_done_kernel(int* flag) { atomicExch(flag, 1); }
+// precedes the first bulk launch in its stream: holds it back until the CTAs of the stiff pass (launched on another
+// stream) are resident on SMs of their own -- a bulk grid that arrives first spreads over every SM and leaves none
+// free for them until it ends.  Gives up after `spins` polls (~0.5 us each): late consumers cost time, not results.
+extern "C" __global__ void odl_gate_kernel(const int* resident, int want, int spins) {
+  for (int i = 0; i < spins; ++i) {
+    if (odl_ld_acquire(resident) >= want) return;
+    __nanosleep(500);
+  }
+}
 #endif  // unit 13
 
 // ------------------------------------------------------------------------------------------------
@@ -1593,6 +1602,15 @@ ODL_UNROLL
   bool pending = false;
   long long ticket = -1;
   unsigned int idle_spins = 0;
+  if (consumer && A.resident && threadIdx.x == 0) atomicAdd(A.resident, 1);      // this CTA has its SM
+#if ODL_TIMELINE
+  if (consumer && A.timeline && threadIdx.x == 0) {                               // which SM, at the far end of the buffer
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    A.timeline[3 * (A.n - 1 - blockIdx.x)] = (long long)smid + 1;
+    A.timeline[3 * (A.n - 1 - blockIdx.x) + 1] = odl_globaltimer();
+  }
+#endif
   for (;;) {
     // ---- (A) finished lanes: cooperative score, write-back ----
     const bool fin = active && done;

@@ -9,20 +9,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests.helpers import device_model, prior_draws  # noqa: E402
 
 dm, _ = device_model("two_i")
+kw = {k: int(v) for k, v in (a.split("=") for a in sys.argv[1:])}
 theta = torch.from_numpy(prior_draws("two_i", 1 << 20, seed=0)).cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for _ in range(3):
-    dm.sweep(theta, solver="auto")
+    dm.sweep(theta, solver="auto", **kw)
 torch.cuda.synchronize()
-for label, sync, fl in (("sync, no flush", True, False), ("no sync, no flush", False, False), ("no sync, flush", False, True),
-                        ("sync, flush", True, True)):
+for label, sync, fl in (("sync, no flush", True, False), ("no sync, flush", False, True), ("no sync, flush", False, True)):
     ev = []
     for rep in range(5):
         if fl:
             flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        dm.sweep(theta, solver="auto")
+        dm.sweep(theta, solver="auto", **kw)
         b.record()
         ev.append((a, b))
         if sync:

@@ -21,17 +21,26 @@ kw = {k: int(v) for k, v in (a.split("=") for a in sys.argv[1:])}
 for _ in range(3):
     dm.sweep(theta, solver="auto", **kw)
 torch.cuda.synchronize()
-for label, fl in (("idle GPU", False), ("behind an L2 flush", True), ("idle GPU", False)):
-    if fl:
-        flush.fill_(1)
-    out = dm.sweep(theta, solver="auto", **kw)
+for label, fl, reps in (("idle GPU", False, 1), ("behind an L2 flush", True, 1), ("4th of 4 back-to-back calls, flush before each", True, 4),
+                        ("4th of 4 back-to-back calls", False, 4), ("idle GPU", False, 1)):
+    for _ in range(reps):
+        if fl:
+            flush.fill_(1)
+        out = dm.sweep(theta, solver="auto", **kw)
     torch.cuda.synchronize()
     cnt = np.zeros(128, np.int32)
     _capi.check(dm._L.odl_debug_counters(dm._h, cnt.ctypes.data, 128))
     m = int(cnt[16])
     tl = np.zeros((m, 3), np.int64)
     _capi.check(dm._L.odl_debug_timeline(dm._h, tl.ctypes.data, m))
+    tail = np.zeros((n, 3), np.int64)
+    _capi.check(dm._L.odl_debug_timeline(dm._h, tail.ctypes.data, n))
+    sm = tail[::-1][:64]
+    sm = sm[sm[:, 0] > 0]
+    smids = np.sort(sm[:, 0] - 1)
     t0 = tl[:, 0].min()
+    print("  consumer CTAs on SMs", smids.tolist(), "| both SMs of a TPC taken:", int(np.sum(np.diff(smids // 2) == 0)),
+          "| resident (ms rel. to first arrival) min/max", round((sm[:, 1].min() - t0) * 1e-6, 3), round((sm[:, 1].max() - t0) * 1e-6, 3))
     arr, beg, end = (tl[:, 0] - t0) * 1e-6, (tl[:, 1] - t0) * 1e-6, (tl[:, 2] - t0) * 1e-6
     picked = tl[:, 1] > 0
     ns = out["nsteps"].cpu().numpy()
@@ -41,5 +50,7 @@ for label, fl in (("idle GPU", False), ("behind an L2 flush", True), ("idle GPU"
     print("  wait (start-arrival)                 ", q((beg - arr)[picked]))
     print("  solve duration                       ", q((end - beg)[picked]))
     print("  end                                  ", q(end[picked]))
+    print("  steps/ms of the solves (pace)        ", q((ns[out["status"].cpu().numpy() == 0][:1] * 0 + 1)), "BDF rows:", int((ns > 512).sum()),
+          "mean duration", round(float((end - beg)[picked].mean()), 3), "sum of durations (lane-ms)", round(float((end - beg)[picked].sum()), 1))
     late = np.argsort(end)[-5:]
     print("  last five to end: arrival", np.round(arr[late], 3).tolist(), "start", np.round(beg[late], 3).tolist(), "end", np.round(end[late], 3).tolist())
