@@ -212,6 +212,172 @@ def workload_config(args, n_gpus):
             "parallelism": f"shard{n_gpus}"}
 
 
+
+# ----------------------------------------------------------------------------------------------------
+# BASELINE.json configs 3-5 and the cold start: extra legs of the same JSON line (key "configs" / "cold_start_s")
+# ----------------------------------------------------------------------------------------------------
+def config_legs(world, rank, local, dev, peak_tflops, barrier, max_over_ranks, sum_over_ranks):
+    """Config 3 (N-class chains, 4096 chains x 10,000 iterations per GPU), config 4 (stiff variant: 65,536-set sweep +
+    1024 chains x 2000 iterations on the BDF kernels, per GPU), config 5 (5x5 network: 65,536 chains SHARED by the
+    GPUs -- strong scaling -- with the R-hat all-gather timed).  All through ModelFramework-built models on synthetic
+    data of each config's shape (odelib_b200/workloads.py)."""
+    import torch
+    from odelib_b200 import workloads
+
+    def flops_per_step(dm):
+        return 6 * dm.rhs_flops + 71 * dm.n_state + 10
+
+    def run_chains(dm, starts, nits, **kw):
+        dm.mcmc(starts, nits=min(nits, 40), rng_mode="philox", seed=1, device_buffers=True, keep_samples=False, **kw)   # warm-up
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        res = dm.mcmc(starts, nits=nits, rng_mode="philox", seed=1, device_buffers=True, keep_samples=False, **kw)
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) * 1e-3), res
+
+    out = {}
+    legs = os.environ.get("ODL_BENCH_LEGS", "c3,c4,c5").split(",")    # development: run a subset
+    note = lambda msg: print("[bench] " + msg, file=sys.stderr, flush=True) if rank == 0 else None
+    # ---- config 3 ----
+    c3 = {}
+    for N in ((1, 4, 10) if "c3" in legs else ()):
+        note(f"config 3, N={N}")
+        m, center = workloads.nclass(N, device=local)
+        dm = m._device()
+        C, nits, P = 4096, 10000, dm.n_param
+        rng = np.random.default_rng([3, N, rank])
+        starts = torch.from_numpy(center * np.exp(0.02 * rng.standard_normal((C, P)))).to(dev)
+        seeds = list(range(rank * C, rank * C + C))
+        # through the facade's chain runner (what ModelFramework.MCMC calls): every solve has a budget of 1024 DOPRI5
+        # attempts, and a chain that ever exhausts it -- a proposal in a stiff corner, where the reference's LSODA switches
+        # to BDF -- is re-run, whole, on the BDF kernel with the same random stream.  (Unbounded, one such proposal in
+        # 4e7 holds its warp for seconds: 10,000 iterations took 81 s instead of 2 s.)
+        kw = dict(rng="philox", return_raw=True, keep_samples=False)
+        m._run_chains(starts, seeds, 60, 30, (), **kw)                          # warm-up (kernels, buffers)
+        barrier(); t0 = time.perf_counter()
+        res = m._run_chains(starts, seeds, nits, nits // 2, (), **kw)
+        torch.cuda.synchronize()
+        t = max_over_ranks(time.perf_counter() - t0)
+        steps = sum_over_ranks(float(np.asarray(res["step_count"]).sum()))
+        coop = dm.n_state > 8
+        c3[f"N={N}"] = {"states": dm.n_state, "parameters": P, "chains_per_gpu": C, "iterations": nits, "seconds": t,
+                        "chain_steps_per_s": C * world * (nits - 1) / t,
+                        "fp64_tflops_per_gpu": steps * flops_per_step(dm) / t / 1e12 / world,
+                        "frac_of_fp64_peak": steps * flops_per_step(dm) / t / 1e12 / world / peak_tflops,
+                        "accept_rate": float(np.asarray(res["chain_state"])[:, 2].mean()) / (nits - 1),
+                        "chains_rerun_on_bdf": int(getattr(m, "_last_rerun", 0)),
+                        "api": "ModelFramework._run_chains (the body of ModelFramework.MCMC): solver='auto', Philox streams",
+                        "kernel": "odl_mcmc_coop_kernel (%d lanes per system)" % (4 if dm.n_state <= 16 else 8) if coop
+                                  else "odl_mcmc_kernel (thread per system, prefetching MH)"}
+    out["c3_nclass_chains"] = c3
+    if "c4" not in legs and "c5" not in legs:
+        return out
+    # ---- config 4 ----
+    note("config 4")
+    m, center = workloads.stiff(device=local)
+    dm = m._device()
+    n4 = 65536
+    theta = torch.from_numpy(workloads.stiff_thetas(n4, seed=rank)).to(dev)
+    for _ in range(2):
+        r4 = dm.sweep(theta, solver="auto", max_steps=2000000)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+    barrier()
+    for a, b in ev:
+        a.record(); r4 = dm.sweep(theta, solver="auto", max_steps=2000000); b.record()
+    barrier()
+    t4 = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) * 1e-3 / 3)
+    starts = theta[:1024].contiguous()
+    t4c, res4 = run_chains(dm, starts, 2000, solver="bdf", max_steps=2000000, chain_offset=rank * 1024)
+    out["c4_stiff"] = {"sweep": {"sets_per_gpu": n4, "seconds": t4, "solves_per_s": n4 * world / t4,
+                                 "ok_fraction": float((r4["status"] == 0).double().mean().item()),
+                                 "mean_steps": float(r4["nsteps"].double().mean().item()),
+                                 "path": "odl_sweep(auto): capped DOPRI5 pass, every row finished by the variable-order BDF pass"},
+                       "chains": {"chains_per_gpu": 1024, "iterations": 2000, "seconds": t4c,
+                                  "chain_steps_per_s": 1024 * world * 1999 / t4c, "kernel": "odl_mcmc_bdf_kernel",
+                                  "accept_rate": float(res4["chain_state"][:, 2].mean().item()) / 1999}}
+    # ---- config 5: strong scaling ----
+    note("config 5")
+    m, center = workloads.network(device=local)
+    dm = m._device()
+    total = 65536
+    C5 = total // world
+    nits5 = {1: 100, 2: 200, 4: 400}.get(world, 1000)
+    rng = np.random.default_rng([5, rank])
+    starts = torch.from_numpy(center * np.exp(0.02 * rng.standard_normal((C5, dm.n_param)))).to(dev)
+    t5, res5 = run_chains(dm, starts, nits5, chain_offset=rank * C5, max_steps=2048)      # bounded solves (see config 3)
+    steps5 = sum_over_ranks(float(res5["step_count"].sum().item()))
+    dm.comm_init()
+    dm.rhat(res5["summaries"])                                   # first call: NCCL sets its channels up
+    barrier(); t0 = time.perf_counter()
+    rh, _, seen = dm.rhat(res5["summaries"])
+    torch.cuda.synchronize(); t_rh = time.perf_counter() - t0
+    out["c5_network_5x5"] = {"states": dm.n_state, "parameters": dm.n_param, "chains_total": total, "chains_per_gpu": C5,
+                             "iterations": nits5, "scaling": "strong", "seconds": t5, "chain_steps_per_s": total * (nits5 - 1) / t5,
+                             "fp64_tflops_per_gpu": steps5 * flops_per_step(dm) / t5 / 1e12 / world,
+                             "frac_of_fp64_peak": steps5 * flops_per_step(dm) / t5 / 1e12 / world / peak_tflops,
+                             "rhat": {"seconds": t_rh, "chains_gathered": int(seen), "bytes_gathered": int(seen) * (1 + 2 * dm.n_param) * 8,
+                                      "max": float(np.nanmax(rh)),
+                                      "collective": "odl_rhat: ncclAllGather over %d ranks + device reduction" % world if world > 1
+                                                    else "odl_rhat: device reduction (1 GPU, no collective)"},
+                             "kernel": "odl_mcmc_coop_kernel (8 lanes per system)",
+                             "proposals_over_the_step_budget": int(sum_over_ranks(float(res5["fail_count"].sum().item()))),
+                             "note": "iterations shortened below 8 GPUs (100 / 200 / 400 / 1000 at 1 / 2 / 4 / 8) so that the leg stays "
+                                     "within seconds; the rate is per chain-step"}
+    return out
+
+
+def cold_start_leg(local, reference_single_chain_s):
+    """Seconds from `ModelFramework(...)` of a model the library has never seen (empty cubin cache: NVRTC runs) to the first
+    results, and the same with the cache warm (a new process on a machine that has run the model before)."""
+    import shutil
+    import tempfile
+    import scipy.stats
+    import odelib_b200 as ODElib
+    from odelib_b200 import demo_models, workloads
+    from odelib_b200.Statistics import Samplers
+    out = {}
+    tmp = tempfile.mkdtemp(prefix="odl_cold_")
+    try:
+        for label in ("cold", "warm_cache"):
+            pri = demo_models.PRIORS[MODEL]
+            t0 = time.perf_counter()
+            pobj = {p: ODElib.parameter(stats_gen=scipy.stats.lognorm, hyperparameters={"s": s, "scale": sc}, init_value=c)
+                    for (p, (s, sc)), c in zip(pri.items(), CENTER[MODEL])}
+            m = ODElib.ModelFramework(ODE=demo_models.two_i, parameter_names=demo_models.PARAMETER_NAMES[MODEL],
+                                      state_names=demo_models.STATE_NAMES[MODEL], dataframe=demo_frame(),
+                                      state_summations={"H": ["S", "I1", "I2"]}, S=5236900, t_steps=TSTEPS, device=local,
+                                      cache_dir=tmp, **pobj)
+            m.sweep(prior_draws(4096, 7))
+            t_sweep = time.perf_counter() - t0
+            frame = Samplers.MetropolisHastings(m, nits=1000, print_progress=False)
+            t_chain = time.perf_counter() - t0
+            out[label] = {"two_i_first_sweep_s": t_sweep, "two_i_sweep_then_single_chain_1000_s": t_chain, "kept_rows": int(len(frame))}
+            t0 = time.perf_counter()
+            m2 = ODElib.ModelFramework(ODE=demo_models.two_i, parameter_names=demo_models.PARAMETER_NAMES[MODEL],
+                                       state_names=demo_models.STATE_NAMES[MODEL], dataframe=demo_frame(),
+                                       state_summations={"H": ["S", "I1", "I2"]}, S=5236900, t_steps=TSTEPS, device=local,
+                                       cache_dir=(tmp + "/c1_" + label if label == "cold" else tmp + "/c1_cold"), **pobj)
+            os.makedirs(m2._cache_dir, exist_ok=True)
+            Samplers.MetropolisHastings(m2, nits=1000, print_progress=False)
+            out[label]["config1_single_chain_1000_s"] = time.perf_counter() - t0
+        rhs, n, P, groups = workloads.network(spec_only=True)
+        from odelib_b200 import engine
+        for label in ("cold", "warm_cache"):
+            t0 = time.perf_counter()
+            dmn = engine.DeviceModel(rhs, n, P, groups, device=local, cache_dir=tmp)
+            dmn.kernel_info("mcmc_coop"); dmn.kernel_info("sweep_coop")          # waits for the units a first call needs
+            out[label]["network_5x5_kernels_ready_s"] = time.perf_counter() - t0
+            dmn.close()
+        out["reference_config1_single_chain_1000_s"] = reference_single_chain_s
+        out["note"] = ("cold = empty cubin cache (NVRTC compiles the kernels a call needs, side by side on host threads); warm_cache = "
+                       "what every later process pays.  config1 = Samplers.MetropolisHastings(model, nits=1000) from a fresh "
+                       "ModelFramework (BASELINE config 1), the reference's time for the same call beside it")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
 # ----------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -421,6 +587,9 @@ def run_ours(args):
                                        "api": "ModelFramework.MCMC(chain_inits=4096, posterior='summary'): survey, start "
                                               "selection, chains, report reductions on the device"}}
 
+    configs = None
+    if not args.no_configs:
+        configs = config_legs(world, rank, local, dev, peak_tflops, barrier, max_over_ranks, sum_over_ranks)
     launches = _capi.lib().odl_launch_count() - launches0
 
     # ---- CPU baseline (rank 0, N=1 only): the reference itself on the host cores, the bare port beside it ----------
@@ -443,6 +612,10 @@ def run_ours(args):
             cpu = port
         if mcmc is not None:
             mcmc["cpu_reference"] = cpu_reference_chains(cores)
+    cold = None
+    if rank == 0 and world == 1 and not args.no_cold:
+        ref1 = (mcmc or {}).get("cpu_reference") or {}
+        cold = cold_start_leg(local, (ref1.get("single_chain") or {}).get("seconds"))
 
     traffic = ncu_traffic()
     if rank == 0:
@@ -469,7 +642,7 @@ def run_ours(args):
                                  "achieved_GBps": bytes_launch / (avg_ms * 1e-3) / 1e9, "peak_GBps": hbm_peak(),
                                  "frac": bytes_launch / (avg_ms * 1e-3) / 1e9 / hbm_peak()}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(timed_launches), "gpu_launches_total": int(launches),
-            "clocks": clk, "ok_fraction": ok_frac, "mcmc": mcmc, "facade": facade,
+            "clocks": clk, "ok_fraction": ok_frac, "mcmc": mcmc, "facade": facade, "configs": configs, "cold_start_s": cold,
         }
         print(json.dumps(line))
     if world > 1:
@@ -504,6 +677,8 @@ def main():
     ap.add_argument("--nits-large", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-facade", action="store_true", help="skip the fit_survey / MCMC-from-survey timings")
+    ap.add_argument("--no-configs", action="store_true", help="skip the legs for BASELINE configs 3-5")
+    ap.add_argument("--no-cold", action="store_true", help="skip the cold-start leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

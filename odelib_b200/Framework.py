@@ -125,6 +125,8 @@ class ModelFramework:
         # their rows / chains over the ranks in contiguous blocks and every rank returns the complete result -- what
         # `cpu_cores` is to the reference (Framework.py:755-785).  Every rank must then make the same calls.
         self.distributed = bool(kwargs.pop("distributed", False))
+        # where the library keeps the compiled cubins of this model ("default": odelib_b200/_cubin_cache; None: no cache)
+        self._cache_dir = kwargs.pop("cache_dir", "default")
         self._dm = None
         if state_summations:
             (self._summations_index, self._summation_snames, self._sumkeep,
@@ -382,8 +384,9 @@ class ModelFramework:
         re-uploads its own tables (a few KB) before it computes, and so does the original after it."""
         if self._dm is None or getattr(self, "_dm_shapes", None) != self._pshapes():
             self._dm_shapes = self._pshapes()                     # the slot layout is part of the compiled model
+            extra = {} if getattr(self, "_cache_dir", "default") == "default" else {"cache_dir": self._cache_dir}
             self._dm = DeviceModel(self._device_ode(), len(self._snames), len(self._flat_names), self._observe_groups(),
-                                   device=self.device, y0_from_param=bool((self._y0_map() >= 0).any()))
+                                   device=self.device, y0_from_param=bool((self._y0_map() >= 0).any()), **extra)
         y0 = np.asarray(self.get_inits(), dtype=np.float64)
         stamp = self._tables_stamp(y0)
         if stamp != getattr(self._dm, "_loaded_stamp", None):
@@ -495,6 +498,7 @@ class ModelFramework:
     # slowest one, and the BDF re-run costs about the same whether it holds 24 chains or 300 (it is latency-bound):
     # 4096 chains x 200 iterations from a wide survey take 0.29 s at 4096, 0.20 s at 2048, 0.15 s at 1024, 0.13 s at 512
     EXPLICIT_STEP_BUDGET = 1024
+    PROBE_STEPS = 2048                 # solver="auto": DOPRI5 attempts the probe of the chain starts may take
 
     def _prior_table(self):
         """(kind, a, b, c) per parameter for the device sampler (engine.DeviceModel.sample_lhs), or None when a prior
@@ -555,17 +559,18 @@ class ModelFramework:
             return 1, 0
         return dist.get_world_size(), dist.get_rank()
 
-    def _unfinished_fraction(self, n_bad, n):
-        """Share of the probed chain starts the capped DOPRI5 pass did not finish -- over ALL ranks when the chains
-        are sharded, so that the stepper (and with it every chain) does not depend on the number of GPUs."""
+    def _unfinished_fraction(self, n_bad, n, steps_ok=0.0):
+        """Share of the probed chain starts the capped DOPRI5 pass did not finish, and the mean attempted-step count of
+        the ones it did -- over ALL ranks when the chains are sharded, so that the stepper and the step budget (and with
+        them every chain) do not depend on the number of GPUs."""
         if self._world()[0] > 1:
             import torch
             import torch.distributed as dist
             from .rhat import _collective_device
-            t = torch.tensor([float(n_bad), float(n)], dtype=torch.float64, device=_collective_device())
+            t = torch.tensor([float(n_bad), float(n), float(steps_ok)], dtype=torch.float64, device=_collective_device())
             dist.all_reduce(t)
-            n_bad, n = t[0].item(), t[1].item()
-        return n_bad / max(1.0, float(n))
+            n_bad, n, steps_ok = t[0].item(), t[1].item(), t[2].item()
+        return n_bad / max(1.0, float(n)), steps_ok / max(1.0, float(n) - float(n_bad))
 
     def _fit_survey_sharded(self, samples, sampler):
         """fit_survey over all ranks: rank 0 draws the design (its numpy / device stream alone decides it) and
@@ -743,10 +748,19 @@ class ModelFramework:
         solver = self.solver
         if solver == "auto":
             probe = dm.sweep(theta0, rtol=self.rtol if rtol is None else rtol, atol=self.atol if atol is None else atol,
-                             solver="dopri5", max_steps=512, stiff_check=True)
-            st_ = probe["status"]
-            n_bad = int((st_ != 0).sum().item()) if on_device else int(np.sum(np.asarray(st_) != 0))
-            solver = "bdf" if self._unfinished_fraction(n_bad, C) > 0.25 else "dopri5"
+                             solver="dopri5", max_steps=self.PROBE_STEPS, stiff_check=True, early_check_steps=-1)
+            st_, ns_ = probe["status"], probe["nsteps"]
+            if on_device:
+                n_bad, steps_ok = int((st_ != 0).sum().item()), float(ns_[st_ == 0].sum().item())
+            else:
+                n_bad, steps_ok = int(np.sum(np.asarray(st_) != 0)), float(np.asarray(ns_)[np.asarray(st_) == 0].sum())
+            frac, typical = self._unfinished_fraction(n_bad, C, steps_ok)
+            solver = "bdf" if frac > 0.25 else "dopri5"
+            # the budget of an explicit solve: well above what this model's solves take (a fixed 1024 sent a third of
+            # the chains of a 12-state model, whose ordinary solves take 350 attempts, to the stiff re-run)
+            budget = int(max(self.EXPLICIT_STEP_BUDGET, 8 * typical))
+        else:
+            budget = self.EXPLICIT_STEP_BUDGET
         self._last_solver = solver
         # "auto" that settled on DOPRI5: every solve gets a bounded step budget, and a chain that ever exhausts it (a
         # proposal in a stiff corner -- the reference's LSODA would switch to BDF there) is re-run, whole, on the BDF
@@ -754,7 +768,7 @@ class ModelFramework:
         retry = self.solver == "auto" and solver == "dopri5"
         kw = dict(nits=nits, burnin=burnin, walk=walk, pnum=self._pnum, rtol=self.rtol if rtol is None else rtol,
                   atol=self.atol if atol is None else atol, keep_samples=keep_samples, device_buffers=on_device,
-                  solver=solver, max_steps=self.EXPLICIT_STEP_BUDGET if retry else 2000000)
+                  solver=solver, max_steps=budget if retry else 2000000)
         if use_priors:
             # not the reference's chain: the reference evaluates the priors and never uses them (Samplers.py:118-127)
             table = self._prior_table()
@@ -777,6 +791,11 @@ class ModelFramework:
             bad = np.flatnonzero((fails.cpu().numpy() if on_device else np.asarray(fails)) > 0)
             if bad.size:
                 self._last_rerun = int(bad.size)
+                # n <= 8: the BDF chain kernel.  Larger systems have no cooperative stiff stepper yet: their re-run is the
+                # cooperative DOPRI5 kernel WITHOUT a budget -- exact as well (the plain DOPRI5 chain), slow only where
+                # the chain really sits in a stiff corner; the thread-per-system BDF kernel keeps such systems in local
+                # memory and took 13 ms per iteration for 12 states
+                redo = "bdf" if dm.n_state <= 8 else "dopri5"
                 sub = dict(streams)
                 if rng == "reference":
                     sub["z"], sub["u"] = z[bad], u[bad]
@@ -785,10 +804,10 @@ class ModelFramework:
                 if on_device:
                     import torch
                     sel = torch.as_tensor(bad, device=theta0.device)
-                    again = dm.mcmc(theta0[sel].contiguous(), **sub, **dict(kw, solver="bdf", max_steps=2000000))
+                    again = dm.mcmc(theta0[sel].contiguous(), **sub, **dict(kw, solver=redo, max_steps=2000000))
                 else:
                     sel = bad
-                    again = dm.mcmc(theta0[bad], **sub, **dict(kw, solver="bdf", max_steps=2000000))
+                    again = dm.mcmc(theta0[bad], **sub, **dict(kw, solver=redo, max_steps=2000000))
                 for key in ("theta", "chain_state", "samples", "summaries", "fail_count", "step_count", "best_theta"):
                     if out.get(key) is not None:
                         out[key][sel] = again[key]

@@ -105,7 +105,12 @@ def check_kernels(strict=True, models=None):
             m = engine.DeviceModel(f, n, P, groups, compile_only=mode, cache_dir=tmp)
             report[name] = parse_ptxas_log(m.build_log)
             m.close()
-    bad = [(m, k, v["spill"]) for m, ks in report.items() for k, v in ks.items() if k in NO_SPILL and v.get("spill", 0) > 0]
+    # n > 8: the bulk of every default path is a cooperative kernel; the thread-per-system kernels (BDF for the stiff rows
+    # of an AUTO sweep, trajectories) keep such systems in local memory by design and are not held to the rule
+    big = {name for name, _, n, _, _, _ in specs if n > 8}
+    coop_only = ("odl_sweep_coop_kernel", "odl_mcmc_coop_kernel", "odl_order_key_kernel", "odl_order_scan_kernel", "odl_order_scatter_kernel")
+    bad = [(m, k, v["spill"]) for m, ks in report.items() for k, v in ks.items()
+           if k in (coop_only if m in big else NO_SPILL) and v.get("spill", 0) > 0]
     if strict and bad:
         raise RuntimeError("register spills in default-path kernels: " + ", ".join(f"{m}:{k} {b} B" for m, k, b in bad))
     return report

@@ -1785,13 +1785,25 @@ odl_traj_kernel(const OdlData D, const OdlOpts O, const OdlTrajArgs A) {
   const long long sys = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (sys >= A.n) return;
   double p[ODL_P];
-ODL_UNROLL
-  for (int q = 0; q < ODL_P; ++q) p[q] = A.theta[sys * ODL_P + q];
+  const double* theta_row = A.theta + sys * ODL_P;
+#pragma unroll
+  for (int q = 0; q < ODL_P; ++q) p[q] = theta_row[q];
   OdlStepper st;
   OdlTrajSink sink; sink.traj = A.traj + sys * (long long)D.n_slot * ODL_N;
   odl_init_system(st, p, D, O, A.y0 ? A.y0 + sys * ODL_N : nullptr, false);
+#ifdef ODL_DEBUG_TRAJ
+  if (sys == 0) {
+    printf("traj init: t %g h %g tend %g rtol %g atol %g y0 %g %g k1 %g %g p %g %g n_slot %d\n", st.t, st.h, st.tend, O.rtol, O.atol,
+           st.y[0], st.y[ODL_N - 1], st.k1[0], st.k1[ODL_N - 1], p[0], p[ODL_P - 1], D.n_slot);
+  }
+#endif
   odl_emit_initial_slots(st, S, D, sink);
-  while (st.slot < D.n_slot && st.status == ODL_OK) odl_dopri5_attempt(st, p, S, D, O, sink);
+  while (st.slot < D.n_slot && st.status == ODL_OK) {
+    odl_dopri5_attempt(st, p, S, D, O, sink);
+#ifdef ODL_DEBUG_TRAJ
+    if (sys == 0 && st.nsteps < 4) printf("traj step %d: t %g h %g y %g %g status %d slot %d\n", st.nsteps, st.t, st.h, st.y[0], st.y[ODL_N - 1], st.status, st.slot);
+#endif
+  }
   if (st.status != ODL_OK) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     for (int s = st.slot; s < D.n_slot; ++s)

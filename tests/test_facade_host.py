@@ -263,7 +263,7 @@ class _RecordingDeviceModel:
     """Stands in for engine.DeviceModel: records what the facade uploads (no GPU, no compile)."""
     instances = 0
 
-    def __init__(self, ode, n_state, n_param, groups, device=None, y0_from_param=False):
+    def __init__(self, ode, n_state, n_param, groups, device=None, y0_from_param=False, cache_dir=None):
         type(self).instances += 1
         self.n_state, self.n_param, self.y0_from_param = n_state, n_param, y0_from_param
         self.loaded_y0 = self.loaded_grid = self.loaded_map = None
