@@ -499,6 +499,7 @@ class ModelFramework:
     # 4096 chains x 200 iterations from a wide survey take 0.29 s at 4096, 0.20 s at 2048, 0.15 s at 1024, 0.13 s at 512
     EXPLICIT_STEP_BUDGET = 1024
     PROBE_STEPS = 2048                 # solver="auto": DOPRI5 attempts the probe of the chain starts may take
+    STEP_BUDGET_FACTOR = 8             # ... and the budget of a solve in multiples of the probe's mean step count
 
     def _prior_table(self):
         """(kind, a, b, c) per parameter for the device sampler (engine.DeviceModel.sample_lhs), or None when a prior
@@ -758,7 +759,7 @@ class ModelFramework:
             solver = "bdf" if frac > 0.25 else "dopri5"
             # the budget of an explicit solve: well above what this model's solves take (a fixed 1024 sent a third of
             # the chains of a 12-state model, whose ordinary solves take 350 attempts, to the stiff re-run)
-            budget = int(max(self.EXPLICIT_STEP_BUDGET, 8 * typical))
+            budget = int(max(self.EXPLICIT_STEP_BUDGET, self.STEP_BUDGET_FACTOR * typical))
         else:
             budget = self.EXPLICIT_STEP_BUDGET
         self._last_solver = solver

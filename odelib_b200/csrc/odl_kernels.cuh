@@ -1784,6 +1784,8 @@ odl_traj_kernel(const OdlData D, const OdlOpts O, const OdlTrajArgs A) {
   __syncthreads();
   const long long sys = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (sys >= A.n) return;
+  // (fully unrolled whatever the state count: with `unroll 1` -- ODL_UNROLL for n > 8 -- NVRTC 12.9 treated p[0] as never
+  // written and folded dy[0] to a NaN constant: every trajectory of a model with more than 8 states failed at once)
   double p[ODL_P];
   const double* theta_row = A.theta + sys * ODL_P;
 #pragma unroll
@@ -1791,19 +1793,8 @@ odl_traj_kernel(const OdlData D, const OdlOpts O, const OdlTrajArgs A) {
   OdlStepper st;
   OdlTrajSink sink; sink.traj = A.traj + sys * (long long)D.n_slot * ODL_N;
   odl_init_system(st, p, D, O, A.y0 ? A.y0 + sys * ODL_N : nullptr, false);
-#ifdef ODL_DEBUG_TRAJ
-  if (sys == 0) {
-    printf("traj init: t %g h %g tend %g rtol %g atol %g y0 %g %g k1 %g %g p %g %g n_slot %d\n", st.t, st.h, st.tend, O.rtol, O.atol,
-           st.y[0], st.y[ODL_N - 1], st.k1[0], st.k1[ODL_N - 1], p[0], p[ODL_P - 1], D.n_slot);
-  }
-#endif
   odl_emit_initial_slots(st, S, D, sink);
-  while (st.slot < D.n_slot && st.status == ODL_OK) {
-    odl_dopri5_attempt(st, p, S, D, O, sink);
-#ifdef ODL_DEBUG_TRAJ
-    if (sys == 0 && st.nsteps < 4) printf("traj step %d: t %g h %g y %g %g status %d slot %d\n", st.nsteps, st.t, st.h, st.y[0], st.y[ODL_N - 1], st.status, st.slot);
-#endif
-  }
+  while (st.slot < D.n_slot && st.status == ODL_OK) odl_dopri5_attempt(st, p, S, D, O, sink);
   if (st.status != ODL_OK) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     for (int s = st.slot; s < D.n_slot; ++s)

@@ -189,6 +189,7 @@ def test_chains_that_exhaust_the_explicit_budget_are_rerun_on_bdf():
                               state_names=demo_models.STATE_NAMES["two_i"], dataframe=demo_df("two_i"),
                               state_summations={"H": ["S", "I1", "I2"]}, S=5236900, **pobj)
     m.EXPLICIT_STEP_BUDGET = 230                                 # low enough that some chains of this set exhaust it
+    m.STEP_BUDGET_FACTOR = 0                                     # (no headroom over the probe's step counts)
     rng = np.random.default_rng(3)
     center = np.array([7.475e-09, 1.069e-07, 19.73, 1.934, 2.799])
     starts = center * np.exp(0.3 * rng.standard_normal((48, 5)))
