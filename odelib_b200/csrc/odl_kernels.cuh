@@ -2188,7 +2188,15 @@ odl_mcmc_bdf_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl
 #ifndef ODL_G
 #define ODL_G (ODL_N <= 16 ? 4 : (ODL_N <= 64 ? 8 : (ODL_N <= 128 ? 16 : 32)))
 #endif
+// Which components a lane owns.  With a slice plan from the tracer (ODL_COOP_SLICED: odl_rhs_slice, ODL_SLICE_PERM)
+// components are laid out class by class -- outputs of the same SHAPE next to each other -- so that the lanes of a
+// round evaluate one code on different leaves; without one, lane `sub` owns sub, sub+G, ...
+#ifdef ODL_COOP_SLICED
+static_assert(ODL_SLICE_G == ODL_G, "the slice plan was made for another number of lanes per system");
+#define ODL_C ODL_CS
+#else
 #define ODL_C ((ODL_N + ODL_G - 1) / ODL_G)
+#endif
 #ifndef ODL_COOP_BLOCK
 #define ODL_COOP_BLOCK 128
 #endif
@@ -2215,6 +2223,7 @@ struct OdlGroup {                // this lane's place in its group and the group
   double* ysm;                   // [ODL_N]  stage state published for the RHS / the observation sums
   double* psm;                   // [ODL_P]  parameters of the group's system
   double* stage;                 // [stage_stride] predictions at the observation slots
+  int comp[ODL_C];               // component this lane owns in round c (-1: none, padding)
 };
 __device__ __forceinline__ double odl_group_sum(double v, unsigned mask) {
 #pragma unroll
@@ -2227,11 +2236,17 @@ __device__ __forceinline__ double odl_group_sum(double v, unsigned mask) {
 // f = rhs(t, state published from the lanes' slices `yl`), slice of this lane
 __device__ __forceinline__ void odl_coop_rhs(const double (&yl)[ODL_C], double t, const OdlGroup& G, double (&f)[ODL_C]) {
 #pragma unroll
-  for (int c = 0; c < ODL_C; ++c) { const int i = G.sub + c * ODL_G; if (i < ODL_N) G.ysm[i] = yl[c]; f[c] = 0.0; }
+  for (int c = 0; c < ODL_C; ++c) { const int i = G.comp[c]; if (i >= 0) G.ysm[i] = yl[c]; f[c] = 0.0; }
   __syncwarp(G.mask);
   const OdlSmemView yv{G.ysm}, pv{G.psm};
+#ifdef ODL_COOP_SLICED
+  // this lane's outputs only: one class code per round, leaves through the index table (tracer.slice_plan).  The
+  // whole traced RHS on every lane (below) is G-fold redundant: 8 x 260 flops per evaluation of the 35-state network
+  odl_rhs_slice(yv, t, pv, G.sub, f);
+#else
   OdlSliceOut out{f, G.sub};
   odl_rhs(yv, t, pv, out);
+#endif
   __syncwarp(G.mask);            // every lane has read the row before it is published again
 }
 
@@ -2246,7 +2261,7 @@ struct OdlCoopStepper {
 // observation columns of the state slices `yi` at `slot` -> the group's staging row (lane 0 writes)
 __device__ __forceinline__ void odl_coop_emit(const double (&yi)[ODL_C], int slot, const OdlGroup& G) {
 #pragma unroll
-  for (int c = 0; c < ODL_C; ++c) { const int i = G.sub + c * ODL_G; if (i < ODL_N) G.ysm[i] = yi[c]; }
+  for (int c = 0; c < ODL_C; ++c) { const int i = G.comp[c]; if (i >= 0) G.ysm[i] = yi[c]; }
   __syncwarp(G.mask);
   if (G.sub == 0) {
     const OdlSmemView yv{G.ysm};
@@ -2262,9 +2277,9 @@ __device__ __forceinline__ void odl_coop_init(OdlCoopStepper& st, const OdlGroup
                                               bool y0_from_params) {
 #pragma unroll
   for (int c = 0; c < ODL_C; ++c) {
-    const int i = G.sub + c * ODL_G;
+    const int i = G.comp[c];
     double v = 0.0;
-    if (i < ODL_N) {
+    if (i >= 0) {
       v = D.y0[i];
 #if ODL_Y0P
       const int src = D.y0_from_param[i];
@@ -2436,6 +2451,14 @@ __device__ __forceinline__ OdlGroup odl_coop_group(const OdlShared& S, const Odl
   const int group = threadIdx.x / ODL_G;
   double* base = S.stage + (size_t)group * (ODL_N + ODL_P + D.stage_stride);
   G.ysm = base; G.psm = base + ODL_N; G.stage = base + ODL_N + ODL_P;
+#pragma unroll
+  for (int c = 0; c < ODL_C; ++c) {
+#ifdef ODL_COOP_SLICED
+    G.comp[c] = ODL_SLICE_PERM[c * ODL_G + G.sub];
+#else
+    G.comp[c] = (G.sub + c * ODL_G < ODL_N) ? G.sub + c * ODL_G : -1;
+#endif
+  }
   return G;
 }
 

@@ -61,12 +61,25 @@ class ObsTables:
 class DeviceModel:
     def __init__(self, ode, n_state, n_param, observe_groups=None, device=None, block_threads=0, min_blocks=0,
                  dense_output=True, fmad=True, compile_only=False, cache_dir=_capi.CACHE_DIR, y0_from_param=False,
-                 coop_lanes=0):
+                 coop_lanes=0, sliced_rhs=None):
         self.traced = trace(ode, n_state, n_param)
         self.n_state, self.n_param = n_state, n_param
         self.groups = [tuple(g) for g in observe_groups] if observe_groups is not None else [(i,) for i in range(n_state)]
         self.n_out = len(self.groups)
-        self.source = self.traced.cuda_source(fmad=fmad, observe_groups=self.groups)
+        # n > 8: the cooperative kernels spread a system over `lanes` lanes; the tracer lays the outputs out class by class
+        # and emits the per-lane right-hand side for exactly that many lanes (tracer.slice_plan)
+        lanes = 0
+        if n_state > 8:
+            lanes = int(coop_lanes) or (4 if n_state <= 16 else 8 if n_state <= 64 else 16 if n_state <= 128 else 32)
+        # sliced_rhs: the per-lane right-hand side (each lane evaluates only its own outputs, leaves through an index table).
+        # Measured on B200 and NOT the default: it halves the FP64 work of the 35-state network (FP64 pipe 25 % -> 12 %) but the
+        # index arithmetic adds more instructions than the flops it saves (LDG/PRMT/IMAD/LEA = 47 % of the executed
+        # instructions), and the kernels are bound by shared-memory latency at 8 warps per SM either way: 2.45 against
+        # 2.56 M chain-steps/s for the network, 6.9 against 9.9 for the 12-state chain (profiles/r2j_*)
+        if sliced_rhs is None:
+            sliced_rhs = os.environ.get("ODL_COOP_SLICED", "0") == "1"
+        self.source = self.traced.cuda_source(fmad=fmad, observe_groups=self.groups, coop_lanes=lanes if sliced_rhs else 0)
+        coop_lanes = lanes
         self.rhs_flops = self.traced.flops()
         L = _capi.lib()
         if cache_dir:

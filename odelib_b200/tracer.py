@@ -378,6 +378,163 @@ class TracedModel:
                 val[i] = f2[op](val[node[1]], val[node[2]])
         return [val[r] for r in roots]
 
+    # -- cooperative kernels: one lane, a few outputs ---------------------------------------------
+    def _canonical(self, o):
+        """Shape of output ``o``: its expression DAG with the leaf INDICES abstracted away.  Returns (signature, leaves):
+        signature = (ops in evaluation order, root reference, kinds of the leaf slots); leaves = [(kind, index)] per slot.
+        Two outputs with the same signature are the same computation on different states / parameters."""
+        g = self.g
+        local, ops, leaves, slot = {}, [], [], {}
+
+        def rec(i):
+            r = local.get(i)
+            if r is not None:
+                return r
+            node = g.nodes[i]
+            op = node[0]
+            if op in ("y", "p"):
+                key = (op, node[1])
+                if key not in slot:
+                    slot[key] = len(leaves)
+                    leaves.append(key)
+                r = ("L", op, slot[key])
+            elif op == "t":
+                r = ("T",)
+            elif op == "c":
+                r = ("C", node[1])
+            else:
+                args = tuple(rec(a) for a in node[1:])
+                ops.append((op,) + args)
+                r = ("N", len(ops) - 1)
+            local[i] = r
+            return r
+
+        import sys
+        old = sys.getrecursionlimit()
+        sys.setrecursionlimit(max(old, 20000))
+        try:
+            root = rec(o)
+        finally:
+            sys.setrecursionlimit(old)
+        return (tuple(ops), root, tuple(k for k, _ in leaves)), leaves
+
+    def slice_plan(self, lanes):
+        """How ``lanes`` lanes share the right-hand side of one system without every lane evaluating all of it.
+
+        Outputs are grouped into CLASSES of identical shape (``_canonical``); components are laid out class by class,
+        ``lanes`` per round, so that the lanes of a round run the same code on different leaves -- looked up in an index
+        table -- instead of each lane evaluating the whole traced RHS and keeping 1/lanes of it.  A round that holds the
+        end of one class and the start of the next runs both codes under lane predicates.
+        -> dict: rounds, perm [rounds*lanes] (output index or -1), classes [(signature, n_slots)],
+                 segments [per round: (class id, lane_lo, lane_hi, table offset)], table (flat leaf indices)."""
+        sigs, members, leaves_of = {}, [], {}
+        for k, o in enumerate(self.outputs):
+            sig, leaves = self._canonical(o)
+            cid = sigs.setdefault(sig, len(sigs))
+            if cid == len(members):
+                members.append([])
+            members[cid].append(k)
+            leaves_of[k] = leaves
+        classes = [None] * len(sigs)
+        for sig, cid in sigs.items():
+            classes[cid] = (sig, len(sig[2]))
+        order = [k for cid in range(len(members)) for k in members[cid]]
+        cls_of = {k: cid for cid in range(len(members)) for k in members[cid]}
+        rounds = (len(order) + lanes - 1) // lanes
+        perm = order + [-1] * (rounds * lanes - len(order))
+        table, segments = [], []
+        for c in range(rounds):
+            segs, lane = [], 0
+            while lane < lanes and perm[c * lanes + lane] >= 0:
+                cid = cls_of[perm[c * lanes + lane]]
+                hi = lane
+                while hi < lanes and perm[c * lanes + hi] >= 0 and cls_of[perm[c * lanes + hi]] == cid:
+                    hi += 1
+                segs.append((cid, lane, hi, len(table)))
+                for l in range(lane, hi):
+                    table += [idx for _, idx in leaves_of[perm[c * lanes + l]]]
+                lane = hi
+            segments.append(segs)
+        return {"rounds": rounds, "perm": perm, "classes": classes, "segments": segments, "table": table, "lanes": lanes}
+
+    def evaluate_sliced(self, plan, y, t, p):
+        """Host evaluation THROUGH a slice plan (tests): every output from its class code and its table row."""
+        f1 = {"neg": lambda a: -a, "abs": abs, "exp": math.exp, "log": math.log, "sqrt": math.sqrt, "sin": math.sin,
+              "cos": math.cos, "tan": math.tan, "tanh": math.tanh, "log10": math.log10, "log2": math.log2,
+              "exp2": lambda a: 2.0 ** a, "log1p": math.log1p, "expm1": math.expm1, "sign": lambda a: (a > 0) - (a < 0)}
+        f2 = {"add": lambda a, b: a + b, "sub": lambda a, b: a - b, "mul": lambda a, b: a * b, "div": lambda a, b: a / b,
+              "pow": lambda a, b: a ** b, "min": min, "max": max, "sel_min": lambda a, b: float(a <= b),
+              "sel_max": lambda a, b: float(a >= b)}
+        out = [None] * len(self.outputs)
+        G = plan["lanes"]
+        for c, segs in enumerate(plan["segments"]):
+            for cid, lo, hi, off in segs:
+                (ops, root, kinds), ns = plan["classes"][cid]
+                for lane in range(lo, hi):
+                    ix = plan["table"][off + (lane - lo) * ns: off + (lane - lo + 1) * ns]
+                    vals = []
+
+                    def ref(r):
+                        if r[0] == "L":
+                            return float(y[ix[r[2]]]) if r[1] == "y" else float(p[ix[r[2]]])
+                        if r[0] == "T":
+                            return float(t)
+                        if r[0] == "C":
+                            return float.fromhex(r[1])
+                        return vals[r[1]]
+                    for op in ops:
+                        vals.append(f1[op[0]](ref(op[1])) if len(op) == 2 else f2[op[0]](ref(op[1]), ref(op[2])))
+                    out[plan["perm"][c * G + lane]] = ref(root)
+        return out
+
+    def _emit_sliced(self, L, lanes, fmad):
+        """odl_rhs_slice<...>: this lane's outputs of every round (see slice_plan)."""
+        plan = self.slice_plan(lanes)
+        g = self.g
+        L.append(f"#define ODL_COOP_SLICED 1")
+        L.append(f"#define ODL_SLICE_G {lanes}")
+        L.append(f"#define ODL_CS {plan['rounds']}")
+        L.append("__device__ const short ODL_SLICE_PERM[ODL_CS * ODL_SLICE_G] = {" + ", ".join(str(v) for v in plan["perm"]) + "};")
+        tab = plan["table"] or [0]
+        L.append(f"__device__ const short ODL_SLICE_IX[{len(tab)}] = {{" + ", ".join(str(v) for v in tab) + "};")
+        L.append("template <class YV, class PV>")
+        L.append("__device__ __forceinline__ void odl_rhs_slice(const YV& y, const double t, const PV& p, const int sub, "
+                 "double (&f)[ODL_CS]) {")
+        uid = 0
+        for c, segs in enumerate(plan["segments"]):
+            L.append(f"  f[{c}] = 0.0;")
+            for cid, lo, hi, off in segs:
+                (ops, root, kinds), ns = plan["classes"][cid]
+                full = lo == 0 and hi == lanes
+                L.append("  {" if full else f"  if (sub >= {lo} && sub < {hi}) {{")
+                L.append(f"    const short* ix = ODL_SLICE_IX + {off} + (sub - {lo}) * {ns};")
+                for s_, kind in enumerate(kinds):
+                    L.append(f"    const double l{s_} = {kind}[ix[{s_}]];")
+                names = []
+
+                def ref(r):
+                    if r[0] == "L":
+                        return f"l{r[2]}"
+                    if r[0] == "T":
+                        return "t"
+                    if r[0] == "C":
+                        return _c_double(float.fromhex(r[1]))
+                    return names[r[1]]
+                for op in ops:
+                    a = ref(op[1])
+                    b = ref(op[2]) if len(op) == 3 else None
+                    node = (op[0], None, None)
+                    if op[0] == "pow" and op[2][0] == "C":
+                        expr = _c_pow_const(a, float.fromhex(op[2][1]), fmad)
+                    else:
+                        expr = _c_expr(op[0], a, b, fmad, None, None) if op[0] != "pow" else f"pow({a}, {b})"
+                    names.append(f"w{uid}")
+                    L.append(f"    const double w{uid} = {expr};")
+                    uid += 1
+                L.append(f"    f[{c}] = {ref(root)};")
+                L.append("  }")
+        L.append("}")
+
     # -- code generation -----------------------------------------------------------------------
     def _emit(self, roots, lines, fmad, names=None):
         g = self.g
@@ -402,7 +559,7 @@ class TracedModel:
                 lines.append(f"  const double v{i} = {_c_expr(op, a, b, fmad, g, node)};")
         return names
 
-    def cuda_source(self, fmad=True, observe_groups=None):
+    def cuda_source(self, fmad=True, observe_groups=None, coop_lanes=0):
         """CUDA source of odl_rhs / odl_jac / odl_dfdt / odl_observe for this model.
 
         fmad=False prints every add/sub/mul as an ``__d*_rn`` intrinsic, which the compiler never
@@ -443,6 +600,8 @@ class TracedModel:
         for k, o in enumerate(self.dfdt()):
             L.append(f"  ft[{k}] = {names[o]};")
         L.append("}")
+        if coop_lanes:
+            self._emit_sliced(L, int(coop_lanes), fmad)
         L.append("template <class YV>")
         L.append("__device__ __forceinline__ void odl_observe(const YV& y, double (&out)[ODL_NOUT]) {")
         for c, grp in enumerate(groups):
@@ -461,6 +620,14 @@ def _c_double(v):
     if math.isinf(v):
         return ("-" if v < 0 else "") + "__longlong_as_double(0x7ff0000000000000LL)"
     return f"({v!r})" if v < 0 or (v == 0 and math.copysign(1, v) < 0) else repr(v)
+
+
+def _c_pow_const(a, c, fmad):
+    if c == 2.0:
+        return f"{a} * {a}" if fmad else f"__dmul_rn({a}, {a})"
+    if c == 0.5:
+        return f"sqrt({a})"
+    return f"pow({a}, {_c_double(c)})"
 
 
 def _c_expr(op, a, b, fmad, g, node):

@@ -123,3 +123,24 @@ def test_cooperative_mapping_agrees_with_thread_per_system(which):
         k = dm.mcmc(theta[:C], nits=nits, seed=4, trace=True, speculate=-K)
         for key in ("samples", "chinew", "accepted", "summaries", "chain_state", "theta", "step_count", "fail_count", "best_theta"):
             assert np.array_equal(a[key], k[key], equal_nan=True), (K, key)
+
+
+def test_sliced_cooperative_rhs_agrees_with_the_full_one():
+    """The per-lane right-hand side of the cooperative kernels (tracer.slice_plan; an option) against the
+    default (every lane evaluates the whole traced RHS): same arithmetic per output, another component-to-lane layout,
+    so the group-reduced error norms sum in another order -- chi to solver accuracy, decisions identical."""
+    from odelib_b200.engine import DeviceModel
+    rhs, names, sums, center, y0, orgs = nclass_problem(10)
+    dm, tab = synthetic_problem(rhs, names, sums, center, y0, orgs, seed=10)
+    ds = DeviceModel(rhs, 12, 5, dm.groups, sliced_rhs=True)
+    ds.set_data(dm.tables, tab.y0)
+    rng = np.random.default_rng(3)
+    theta = center * np.exp(0.1 * rng.standard_normal((64, 5)))
+    a = dm.sweep(theta, rtol=1e-10, atol=1e-10, max_steps=2000000)
+    b = ds.sweep(theta, rtol=1e-10, atol=1e-10, max_steps=2000000)
+    assert np.all(a["status"] == 0) and np.all(b["status"] == 0)
+    np.testing.assert_allclose(b["chi"], a["chi"], rtol=1e-7)
+    ra = dm.mcmc(theta[:16], nits=40, seed=2, trace=True, rtol=1e-10, atol=1e-10)
+    rb = ds.mcmc(theta[:16], nits=40, seed=2, trace=True, rtol=1e-10, atol=1e-10)
+    assert np.array_equal(ra["accepted"], rb["accepted"])
+    np.testing.assert_allclose(rb["chinew"], ra["chinew"], rtol=1e-6)

@@ -79,3 +79,25 @@ def test_equality_on_traced_values_is_refused():
     for f in (rhs_eq, rhs_ne):
         with pytest.raises(TraceError):
             trace(f, 1, 1)
+
+
+@pytest.mark.parametrize("which,lanes", [("network", 8), ("network", 16), ("n_class_10", 4), ("two_i", 4)])
+def test_slice_plan_reproduces_every_output(which, lanes):
+    """tracer.slice_plan: outputs grouped into classes of identical shape, laid out class by class, `lanes` per round;
+    evaluating every output through its class code + index-table row gives exactly the traced value, every component
+    appears once, and the emitted odl_rhs_slice covers every round."""
+    from odelib_b200 import demo_models
+    from odelib_b200.tracer import trace
+    f, n, P = {"network": demo_models.network(5, 5)[:3], "n_class_10": (demo_models.n_class(10), 12, 5),
+               "two_i": demo_models.MODELS["two_i"][:3]}[which]
+    tm = trace(f, n, P)
+    plan = tm.slice_plan(lanes)
+    assert sorted(k for k in plan["perm"] if k >= 0) == list(range(n)) and len(plan["perm"]) == plan["rounds"] * lanes
+    rng = np.random.default_rng(0)
+    y, p = rng.uniform(0.5, 2.0, n), rng.uniform(0.1, 1.0, P)
+    assert tm.evaluate_sliced(plan, y, 0.3, p) == tm.evaluate(tm.outputs, y, 0.3, p)          # bit for bit
+    if which == "network":
+        assert len(plan["classes"]) == 3                              # dS_i, dI_ij, dV_j
+    src = tm.cuda_source(coop_lanes=lanes)
+    assert f"#define ODL_CS {plan['rounds']}" in src and src.count("f[") >= plan["rounds"]
+    assert "ODL_COOP_SLICED" not in tm.cuda_source()
