@@ -2,14 +2,16 @@
 """bench.py -- the hot path's headline metric on B200 (BASELINE.json: ODE solves/s + MCMC chain-steps/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one rank per GPU under torchrun)
-    python bench.py --impl reference [--gpus N] --steps K --warmup W   the reference's CPU path (oracle port)
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   the reference's own CPU path (oracle/_ref)
 
 One "step" = one pass of the forward sweep (BASELINE.json configs[1]): `--sets` (default 1,048,576) parameter
 sets per GPU drawn from the two_i priors of the demo, each integrated to the demo's observation grid and
-scored (chi, R^2) -- one launch of odl_sweep_kernel.  `value` = solves/s with theta resident in HBM, timed
-with CUDA events on the launching stream; `e2e` = the same through ModelFramework.sweep with pinned HOST
-buffers (H2D + D2H inside the timed call).  The MCMC leg (chain-steps/s) is reported in the same JSON line
-under "mcmc".  Prints exactly one JSON line on rank 0.
+scored (chi, R^2) -- one odl_sweep call (ODL_SOLVER_AUTO: ordering, DOPRI5 bulk pass, BDF stiff pass beside it).
+`value` = solves/s with theta resident in HBM, timed with CUDA events on the launching stream; `e2e` = the same
+through ModelFramework.sweep with pinned HOST buffers (H2D + D2H inside the timed call).  In the same JSON line:
+"mcmc" (chain-steps/s, the reference's CPU sampler timed beside it), "configs" (BASELINE configs 3-5), "cold_start_s",
+"cpu_baseline" (the unmodified reference's fit_survey on the host cores, oracle/_ref).  Prints exactly one JSON line
+on rank 0 (the last line of stdout).
 """
 import argparse
 import json
@@ -207,7 +209,8 @@ def workload_config(args, n_gpus):
                         f"(19 grid times of t_steps={TSTEPS}) + chi/R^2 [BASELINE.json configs[1]]",
             "sets_per_gpu": args.sets, "sets_total": args.sets * n_gpus, "rtol": 1.49012e-8, "atol": 1.49012e-8,
             "solver": "auto: rows cost-ordered on the device (|J(y0)| key), dopri5(4) with dense output <=512 attempted "
-                      "steps (projection check at 384), then variable-order BDF for what is left (~2.5 %)",
+                      "steps (projection check at 384) on ~72 % of the SMs, variable-order BDF for what is left (~1.4 %) "
+                      "BESIDE it on SMs of its own (42 CTAs of 8 warps, clusters of 2)",
             "l2": "flushed between timed steps (256 MiB write)",
             "parallelism": f"shard{n_gpus}"}
 
@@ -632,7 +635,8 @@ def run_ours(args):
                          "frac": achieved / peak_tflops,
                          "traffic": traffic.get("bytes") if n == (1 << 20) else None,
                          "traffic_note": traffic.get("note"),
-                         "kernel": "odl_sweep (5 launches: 3 ordering kernels + odl_sweep_kernel + odl_sweep_bdf_kernel)",
+                         "kernel": "odl_sweep (8 launches: 3 ordering kernels, odl_sweep_bdf_kernel (consumer, beside), odl_gate_kernel, "
+                                   "odl_sweep_kernel, odl_feed_done_kernel, odl_sweep_bdf_kernel (pick-up of what the consumer left: normally nothing))",
                          "avg_launch_ms": avg_ms,
                          "peak_source": "measured live: odl_fp64_peak DFMA chains (MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_per_launch": flops_launch, "flops_per_step_attempt": flops_step,
@@ -640,7 +644,7 @@ def run_ours(args):
                          "flop_model": "per attempted DOPRI5 step 6*F_rhs+71n+10 (F_rhs=11, n=4 -> 360), + 19*(30+12n) + 37*8 per "
                                        "solve; steps of the BDF-finished systems at F_rhs+2n^2+37n (= 191) per attempt; the "
                                        "DOPRI5 attempts of deferred systems, ordering, LU and change_D work are not counted",
-                         "passes_ms": {"ordering": pass_ms[0], "dopri5_bulk": pass_ms[1], "bdf_stiff": pass_ms[2]},
+                         "passes_ms": {"ordering": pass_ms[0], "dopri5_bulk": pass_ms[1], "bdf_stiff_after_bulk_ended": pass_ms[2]},
                          "bulk_kernel": bulk,
                          "hbm": {"algorithmic_bytes_per_launch": bytes_launch,
                                  "achieved_GBps": bytes_launch / (avg_ms * 1e-3) / 1e9, "peak_GBps": hbm_peak(),

@@ -20,6 +20,15 @@ if mode == "auto":
         out = dm.sweep(theta, solver="auto", max_steps=500000, auto_flags=flags)
     torch.cuda.synchronize()
     print("auto kernel_ms", dm.last_kernel_ms(), dm.last_pass_ms(), dm.kernel_info("sweep"), dm.kernel_info("sweep_bdf"))
+elif mode in ("stream_iteration", "stream_chain"):
+    # the sample stream of a filled GPU: 65,536 chains, one lane per chain, every kept row written
+    dm, tab = device_model("two_i")
+    C = 65536
+    starts = torch.from_numpy(np.array(bench.CENTER["two_i"]) * np.exp(0.05 * np.random.default_rng(1).standard_normal((C, 5)))).cuda()
+    for _ in range(2):
+        res = dm.mcmc(starts, nits=41, seed=0, device_buffers=True, sample_layout=mode.split("_")[1])
+    torch.cuda.synchronize()
+    print(mode, "kernel_ms", dm.last_kernel_ms(), "kept bytes", C * 20 * 80, dm.kernel_info("mcmc"))
 elif mode == "mcmc":
     dm, tab = device_model("two_i")
     C = 4096
