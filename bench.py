@@ -259,7 +259,7 @@ def config_legs(world, rank, local, dev, peak_tflops, barrier, max_over_ranks, s
         seeds = list(range(rank * C, rank * C + C))
         # through the facade's chain runner (what ModelFramework.MCMC calls): every solve has a budget of 1024 DOPRI5
         # attempts, and a chain that ever exhausts it -- a proposal in a stiff corner, where the reference's LSODA switches
-        # to BDF -- is re-run, whole, on the BDF kernel with the same random stream.  (Unbounded, one such proposal in
+        # to BDF -- stops there and is re-run, whole, on the BDF kernel with the same random stream.  (Unbounded, one such proposal in
         # 4e7 holds its warp for seconds: 10,000 iterations took 81 s instead of 2 s.)
         kw = dict(rng="philox", return_raw=True, keep_samples=False)
         m._run_chains(starts, seeds, 60, 30, (), **kw)                          # warm-up (kernels, buffers)

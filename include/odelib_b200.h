@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define ODL_ABI_VERSION 2
+#define ODL_ABI_VERSION 3
 
 enum { ODL_SUCCESS = 0, ODL_EINVAL = 1, ODL_ECUDA = 2, ODL_ECOMPILE = 3, ODL_ENODEVICE = 4, ODL_EIO = 5 };
 enum { ODL_MEM_HOST = 0, ODL_MEM_DEVICE = 1 };
@@ -89,7 +89,7 @@ typedef struct odl_solver_opts {
   int solver;          /* ODL_SOLVER_* */
   int stiff_check;     /* DOPRI5: detect stiffness and stop with ODL_ST_STIFF */
   int stiff_min_steps; /* ... only while more than this many steps of the current size remain (0 = 2000) */
-  int pass_cap0;       /* ODL_SOLVER_AUTO: step cap of the first DOPRI5 pass (0 = 512) */
+  int pass_cap0;       /* ODL_SOLVER_AUTO: step cap of the first DOPRI5 pass (odl_sweep: 0 = 512; odl_mcmc: see there) */
   int tail_warps;      /* ODL_SOLVER_AUTO: SMs set aside for the stiff pass when it runs beside the DOPRI5 pass (one CTA
                           of 8 warps each; 0 = a quarter of them) */
   int tail_solver;     /* ODL_SOLVER_AUTO: stepper of the pass over what DOPRI5 did not finish:
@@ -122,6 +122,11 @@ typedef struct odl_mcmc_opts {
   int sample_layout;   /* ODL_SAMPLES_CHAIN_MAJOR: samples[chain][row][row_stride] (the reference frame's order);
                           ODL_SAMPLES_ITERATION_MAJOR: samples[row][chain][row_stride] -- the rows a warp keeps in one
                           iteration are contiguous and leave as coalesced full-sector stores */
+  int stop_failed_chains; /* 1 = a chain stops at the first consumed solve that failed (fail_count > 0 marks it; its other
+                          outputs are then incomplete).  For callers that run such chains again with another stepper --
+                          the facade's solver="auto" does -- so that they do not burn max_steps on every later proposal
+                          while the chains beside them wait; the chains that never fail are not affected */
+  int reserved;
 } odl_mcmc_opts;
 
 typedef struct odl_mcmc_io {
@@ -182,6 +187,12 @@ int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, const double
               double* chi, double* r2, int* status, int* nsteps, double* pred_or_null, void* stream);
 int odl_trajectory(odl_model* m, const odl_solver_opts* so, long long n, const double* theta,
                    const double* y0_or_null, int mem, double* traj, int* status, int* nsteps, void* stream);
+/* odl_mcmc with so->solver = ODL_SOLVER_AUTO: every solve of a chain (a-priori point and proposals) is attempted with
+   DOPRI5 and, when that gives up, done again with the variable-order BDF stepper -- the per-solve method switch LSODA makes
+   for the reference (Framework.py:656).  "Gives up": so->pass_cap0 > 0 = that many attempted steps (Hairer's stiffness
+   test only with so->stiff_check); pass_cap0 = 0 = Hairer's test (and max_steps).  Which stepper finishes a solve depends
+   on that solve alone, so a chain whose solves all stay within pass_cap0 equals the ODL_SOLVER_DOPRI5 chain run with
+   max_steps = pass_cap0 bit for bit.  fail_count counts solves that neither stepper finished. */
 int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_opts* mo, const odl_mcmc_io* io, int mem,
              void* stream);
 

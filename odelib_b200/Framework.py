@@ -495,7 +495,7 @@ class ModelFramework:
 
     DEVICE_SAMPLING_FROM = 65536       # surveys at least this large are sampled on the device (sampler="auto")
     # solver="auto": DOPRI5 attempts per solve before the chain is handed to BDF.  The chains of a launch wait for its
-    # slowest one, and the BDF re-run costs about the same whether it holds 24 chains or 300 (it is latency-bound):
+    # slowest one (measured before chains stopped at their first failed solve), and the BDF re-run costs about the same whether it holds 24 chains or 300 (it is latency-bound):
     # 4096 chains x 200 iterations from a wide survey take 0.29 s at 4096, 0.20 s at 2048, 0.15 s at 1024, 0.13 s at 512
     EXPLICIT_STEP_BUDGET = 1024
     PROBE_STEPS = 2048                 # solver="auto": DOPRI5 attempts the probe of the chain starts may take
@@ -765,11 +765,13 @@ class ModelFramework:
         self._last_solver = solver
         # "auto" that settled on DOPRI5: every solve gets a bounded step budget, and a chain that ever exhausts it (a
         # proposal in a stiff corner -- the reference's LSODA would switch to BDF there) is re-run, whole, on the BDF
-        # kernel.  A chain's result depends on that chain alone: all DOPRI5, or all BDF.
+        # kernel.  A chain's result depends on that chain alone: all DOPRI5, or all BDF.  In the first run such a chain
+        # stops at the failed solve (stop_failed): a chain that sits in a stiff corner would otherwise burn the whole
+        # budget on every later proposal while the chains of its warp -- and the launch -- wait for it.
         retry = self.solver == "auto" and solver == "dopri5"
         kw = dict(nits=nits, burnin=burnin, walk=walk, pnum=self._pnum, rtol=self.rtol if rtol is None else rtol,
                   atol=self.atol if atol is None else atol, keep_samples=keep_samples, device_buffers=on_device,
-                  solver=solver, max_steps=budget if retry else 2000000)
+                  solver=solver, max_steps=budget if retry else 2000000, stop_failed=retry)
         if use_priors:
             # not the reference's chain: the reference evaluates the priors and never uses them (Samplers.py:118-127)
             table = self._prior_table()
@@ -805,10 +807,10 @@ class ModelFramework:
                 if on_device:
                     import torch
                     sel = torch.as_tensor(bad, device=theta0.device)
-                    again = dm.mcmc(theta0[sel].contiguous(), **sub, **dict(kw, solver=redo, max_steps=2000000))
+                    again = dm.mcmc(theta0[sel].contiguous(), **sub, **dict(kw, solver=redo, max_steps=2000000, stop_failed=False))
                 else:
                     sel = bad
-                    again = dm.mcmc(theta0[bad], **sub, **dict(kw, solver=redo, max_steps=2000000))
+                    again = dm.mcmc(theta0[bad], **sub, **dict(kw, solver=redo, max_steps=2000000, stop_failed=False))
                 for key in ("theta", "chain_state", "samples", "summaries", "fail_count", "step_count", "best_theta"):
                     if out.get(key) is not None:
                         out[key][sel] = again[key]

@@ -48,7 +48,8 @@ class McmcOpts(C.Structure):
     _fields_ = [("n_chain", C.c_int), ("chain_offset", C.c_int), ("nits", C.c_int), ("burnin", C.c_int),
                 ("it_begin", C.c_int), ("it_end", C.c_int), ("rng_mode", C.c_int), ("n_walk", C.c_int),
                 ("walk", C.POINTER(C.c_int)), ("pnum", C.c_int), ("row_stride", C.c_int), ("step_sd", C.c_double),
-                ("seed", C.c_ulonglong), ("speculate", C.c_int), ("sample_layout", C.c_int)]
+                ("seed", C.c_ulonglong), ("speculate", C.c_int), ("sample_layout", C.c_int),
+                ("stop_failed_chains", C.c_int), ("reserved", C.c_int)]
 
 
 class McmcIO(C.Structure):
@@ -104,7 +105,7 @@ def lib():
     L.odl_comm_destroy.argtypes = [C.c_void_p]
     L.odl_rhat.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_longlong), C.c_void_p]
     L.odl_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
-    if L.odl_abi_version() != 2:
+    if L.odl_abi_version() != 3:
         raise OdlError(EIO, "libodelib_b200.so ABI version mismatch - rebuild")
     _lib = L
     return L

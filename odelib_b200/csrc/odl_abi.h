@@ -43,6 +43,9 @@ struct OdlOpts {
                                  //      progress so far projects to more than max_steps attempts in total
   int lanes;                     // sweep kernels: lanes per warp that take systems (0 = all 32)
   int watchdog_spins;            // consumer: idle polls (~0.4 us each) of a warp before it gives up on the producer
+  int explicit_cap;              // odl_mcmc_auto_kernel: attempted DOPRI5 steps a solve may take before it is redone on
+                                 //   BDF (0 = max_steps; Hairer's test alone routes)
+  int pad_;
 };
 
 struct OdlSweepArgs {
@@ -132,6 +135,8 @@ struct OdlMcmcArgs {
                                  //   is the posterior's, exp((chi-chinew) + (lp'-lp) + sum ln(theta'/theta)); without,
                                  //   the reference's (priors never enter, Samplers.py:118-127); lp of the current point
                                  //   lives in chain_state[5]
+  int stop_failed;               // 1 = a chain stops at its first consumed solve that failed (the caller runs such chains
+  int pad2_;                     //   again with another stepper: what they would still compute is thrown away)
 };
 
 #endif  // ODL_ABI_H

@@ -647,6 +647,7 @@ static void fill_opts(OdlOpts& o, const odl_solver_opts* so) {
   o.stiff_min_steps = so && so->stiff_min_steps > 0 ? so->stiff_min_steps : 2000;
   o.early_check_steps = so && so->early_check_steps > 0 ? so->early_check_steps : 0;   // AUTO sets its own default
   o.lanes = 0;
+  o.explicit_cap = 0; o.pad_ = 0;
   o.watchdog_spins = 75000000;   // ~30 s without a single entry and without the producer finishing
   if (const char* w = getenv("ODL_WATCHDOG_SPINS")) o.watchdog_spins = std::max(1000, atoi(w));
 }
@@ -810,7 +811,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
   m->n_pass = 1;
   if (solver != ODL_SOLVER_AUTO) {
     A.defer_list[0] = A.defer_list[1] = nullptr; A.defer_count[0] = A.defer_count[1] = nullptr;
-    const bool warp_cta = solver == ODL_SOLVER_RADAU5 || solver == ODL_SOLVER_BDF;   // compiled for one warp per CTA
+    const bool warp_cta = solver == ODL_SOLVER_RADAU5 || solver == ODL_SOLVER_BDF || solver == ODL_SOLVER_AUTO;   // compiled for one warp per CTA
     CUfunction f1 = solver == ODL_SOLVER_ROS23 ? m->k_sweep_ros : (solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau :
                     (solver == ODL_SOLVER_BDF ? m->k_sweep_bdf : m->k_sweep));
     if (solver == ODL_SOLVER_DOPRI5 && m->coop_model() && !O.stiff_check && O.early_check_steps == 0) {
@@ -1107,9 +1108,10 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   }
   A.step_sd = mo->step_sd > 0 ? mo->step_sd : 0.05;
   A.seed = mo->seed; A.n_iter_total = n_iter;
+  A.stop_failed = mo->stop_failed_chains ? 1 : 0; A.pad2_ = 0;
   OdlOpts O; fill_opts(O, so);
   OdlData D = m->data.d;
-  const bool warp_cta = solver == ODL_SOLVER_RADAU5 || solver == ODL_SOLVER_BDF;   // compiled for one warp per CTA
+  const bool warp_cta = solver == ODL_SOLVER_RADAU5 || solver == ODL_SOLVER_BDF || solver == ODL_SOLVER_AUTO;   // compiled for one warp per CTA
   // Prefetching MH: K lanes per chain evaluate K iterations at once along the all-rejected path (odl_mcmc_body).
   // The chain itself does not depend on K; K only fills a GPU that few chains would leave latency-bound.
   // Automatic: the largest power of two that keeps chains*K within half of what the kernel can hold, at most 16.
@@ -1156,7 +1158,13 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   }
   CUfunction f = (solver == ODL_SOLVER_DOPRI5) ? m->k_mcmc : (solver == ODL_SOLVER_ROS23 ? m->k_mcmc_ros :
                  (solver == ODL_SOLVER_RADAU5 ? m->k_mcmc_radau : (solver == ODL_SOLVER_BDF ? m->k_mcmc_bdf : m->k_mcmc_auto)));
-  if (solver == ODL_SOLVER_AUTO) O.stiff_check = 1;
+  if (solver == ODL_SOLVER_AUTO) {
+    // per solve: DOPRI5, and the same solve again on BDF when it gives up.  pass_cap0 > 0: "gives up" = that many attempted
+    // steps (then Hairer's test runs only if the caller asked for it, so that a chain whose solves all stay within the
+    // budget is the plain DOPRI5 chain under max_steps = pass_cap0, bit for bit); else Hairer's test routes.
+    O.explicit_cap = so && so->pass_cap0 > 0 ? so->pass_cap0 : 0;
+    O.stiff_check = O.explicit_cap > 0 ? (so->stiff_check ? 1 : 0) : 1;
+  }
   ODL_CUDA(cudaEventRecord(m->ev0, s));
   void* params[] = {&D, &O, &A};
   m->n_pass = 1;

@@ -15,7 +15,8 @@
 //   stats.py:49-56  R^2                                    -> odl_score
 //   Framework.py:41-48   _Fit_worker loop                  -> odl_sweep_kernel
 //   Samplers.py:53-174   MetropolisHastings                -> odl_mcmc_kernel (one chain per thread)
-//   (stiff parameter regions, LSODA's BDF branch)         -> ROS23 stepper: odl_*_ros23_kernel, odl_mcmc_auto_kernel
+//   (stiff parameter regions, LSODA's BDF branch)         -> variable-order BDF: odl_*_bdf_kernel, odl_mcmc_auto_kernel
+//                                                             (DOPRI5, then BDF, per solve); ROS23: odl_*_ros23_kernel
 //
 // Execution model: every thread owns one ODE system at a time and keeps its state, the 7 stage
 // derivatives and the parameter vector in registers.  The main loop is a flat state machine:
@@ -1417,18 +1418,21 @@ ODL_UNROLL
 }
 
 template <int SOLVER> struct OdlAuxOf { typedef OdlNoAux type; };
+template <> struct OdlAuxOf<2> { typedef OdlBdfAux type; };
 template <> struct OdlAuxOf<3> { typedef OdlRadauAux type; };
 template <> struct OdlAuxOf<4> { typedef OdlBdfAux type; };
 
-// solver dispatch: 0 = DOPRI5, 1 = ROS23, 2 = per-system choice (DOPRI5 until it reports stiffness), 3 = Radau5, 4 = BDF
+// solver dispatch: 0 = DOPRI5, 1 = ROS23, 2 = per-solve choice (DOPRI5 until it gives up -- step budget or Hairer's
+// stiffness test --, then the same solve again on BDF: what LSODA's method switch does for the reference), 3 = Radau5,
+// 4 = BDF
 template <int SOLVER, class Sink>
 __device__ __forceinline__ void odl_attempt(OdlStepper& st, typename OdlAuxOf<SOLVER>::type& ax, const double (&p)[ODL_P],
-                                            const OdlShared& S, const OdlData& D, const OdlOpts& O, Sink& sink, bool use_ros) {
+                                            const OdlShared& S, const OdlData& D, const OdlOpts& O, Sink& sink, bool use_alt) {
   if constexpr (SOLVER == 0) odl_dopri5_attempt(st, p, S, D, O, sink);
   else if constexpr (SOLVER == 1) odl_ros23_attempt(st, p, S, D, O, sink);
   else if constexpr (SOLVER == 3) odl_radau5_attempt(st, ax, p, S, D, O, sink);
   else if constexpr (SOLVER == 4) odl_bdf_attempt(st, ax, p, S, D, O, sink);
-  else { if (use_ros) odl_ros23_attempt(st, p, S, D, O, sink); else odl_dopri5_attempt(st, p, S, D, O, sink); }
+  else { if (use_alt) odl_bdf_attempt(st, ax, p, S, D, O, sink); else odl_dopri5_attempt(st, p, S, D, O, sink); }
 }
 
 #ifndef ODL_HOST_HARNESS
@@ -1937,14 +1941,18 @@ __device__ __forceinline__ void odl_mcmc_body(const OdlData& D, const OdlOpts& O
   // lanes of a chain; apriori marks the solve of the starting point of a fresh chain (Samplers.py:88-90).
   int it = A.it_begin;
   bool apriori = A.it_begin == 1;                               // warp-uniform: the branches below hold collectives
-  bool active = false, done = false, use_ros = false;
+  bool active = false, done = false, use_alt = false;
+  bool dead = false;                                             // stop_failed: this chain met a solve that failed
+  // SOLVER 2: the explicit attempt of a solve runs under its own step budget
+  OdlOpts Oe = O;
+  if (SOLVER == 2 && O.explicit_cap > 0) Oe.max_steps = min(O.explicit_cap, O.max_steps);
   double* cs = A.chain_state + (size_t)(has_chain ? chain : 0) * ODL_CHAIN_STATE;
   bool more = has_chain && (apriori || it < A.it_end);
 
   while (__any_sync(ODL_FULL, more)) {
     // ---- start a round: lane `sub` takes iteration it+sub ----
     const bool valid = more && (apriori ? (sub == 0) : (it + sub < A.it_end));
-    active = false; done = false; use_ros = false;
+    active = false; done = false; use_alt = false;
     if (valid) {
       if (apriori) {
 ODL_UNROLL
@@ -1963,17 +1971,18 @@ ODL_UNROLL
     //      of neighbouring chains, and the K proposals of one chain, cost nearly the same number of steps.) ----
     for (;;) {
       if (active && !done) {
-        odl_attempt<SOLVER>(st, ax, p, S, D, O, sink, use_ros);
+        odl_attempt<SOLVER>(st, ax, p, S, D, (SOLVER == 2 && !use_alt) ? Oe : O, sink, use_alt);
         done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
       }
       if (__ballot_sync(ODL_FULL, active && !done)) continue;
       if (SOLVER == 2) {
-        // DOPRI5 gave up on a stiff proposal: redo this very solve with the Rosenbrock stepper
-        const bool restart = active && st.status == ODL_STIFF && !use_ros;
+        // DOPRI5 gave up on this proposal (step budget spent, or Hairer's test called it stiff): redo this very solve
+        // with the BDF stepper.  Which stepper finishes a solve depends on that solve alone.
+        const bool restart = active && (st.status == ODL_STIFF || st.status == ODL_MAXSTEPS) && !use_alt;
         if (__ballot_sync(ODL_FULL, restart)) {
           if (restart) {
             if (A.step_count) atomicAdd((unsigned long long*)&A.step_count[chain], (unsigned long long)st.nsteps);
-            use_ros = true;
+            use_alt = true;
             odl_init_system(st, p, D, O, nullptr, !apriori);
             ax.reset();
             odl_emit_initial_slots(st, S, D, sink);
@@ -1999,6 +2008,7 @@ ODL_UNROLL
         if (A.step_count) atomicAdd((unsigned long long*)&A.step_count[chain], (unsigned long long)st.nsteps);
         if (A.fail_count && st.status != ODL_OK) atomicAdd(&A.fail_count[chain], 1);
       }
+      if (A.stop_failed && ((__ballot_sync(ODL_FULL, valid && st.status != ODL_OK) >> gbase) & gbits)) dead = true;
       apriori = false;
       __syncwarp();
     } else {
@@ -2024,6 +2034,7 @@ ODL_UNROLL
       const int adv = (jstar >= 0) ? jstar + 1 : nvalid;                                  // iterations consumed
       const bool consumed = valid && sub < adv;
       const bool is_acc = consumed && sub == jstar;
+      if (A.stop_failed && ((__ballot_sync(ODL_FULL, consumed && st.status != ODL_OK) >> gbase) & gbits)) dead = true;
       if (consumed) {
         // counters cover CONSUMED solves only (speculative work that was discarded is not counted)
         if (A.step_count) atomicAdd((unsigned long long*)&A.step_count[chain], (unsigned long long)st.nsteps);
@@ -2147,7 +2158,7 @@ ODL_UNROLL
       it += adv;
       __syncwarp();                                              // the next round's proposals read cur[]
     }
-    more = has_chain && it < A.it_end;
+    more = has_chain && !dead && it < A.it_end;
   }
 }
 #if ODL_HAS(3)
@@ -2159,7 +2170,7 @@ extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
 odl_mcmc_ros23_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<1>(D, O, A); }
 #endif
 #if ODL_HAS(8)
-extern "C" __global__ void __launch_bounds__(ODL_BLOCK, ODL_MINBLOCKS_ROS)
+extern "C" __global__ void __launch_bounds__(32, 1)
 odl_mcmc_auto_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) { odl_mcmc_body<2>(D, O, A); }
 #endif
 #if ODL_HAS(10)
@@ -2584,6 +2595,7 @@ odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
         if (A.fail_count && st.status != ODL_OK) A.fail_count[chain] += 1;
       }
       apriori = false;
+      if (A.stop_failed && __ballot_sync(smask, valid && lead && st.status != ODL_OK)) break;   // see OdlMcmcArgs
       __syncwarp(smask);
       continue;
     }
@@ -2608,6 +2620,7 @@ odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
     const int adv = (jstar >= 0) ? jstar + 1 : nvalid;
     const bool consumed = valid && kk < adv;
     const bool is_acc = consumed && kk == jstar;
+    const bool dead = A.stop_failed && __ballot_sync(smask, consumed && lead && st.status != ODL_OK);
     const int src = sbase + (jstar >= 0 ? jstar : 0) * ODL_G;
     const double chi_acc = __shfl_sync(smask, my_chi, src), r2_acc = __shfl_sync(smask, my_r2, src);
     const double* pacc = G.psm + (long long)((jstar >= 0 ? jstar : kk) - kk) * (long long)group_doubles;   // accepted proposal (shared)
@@ -2669,6 +2682,7 @@ odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
     }
     it += adv;
     __syncwarp(smask);
+    if (dead) break;                                               // uniform over the lanes of the chain
   }
 }
 #endif  // unit 12

@@ -327,7 +327,7 @@ class DeviceModel:
     def mcmc(self, theta0, nits=1000, burnin=None, walk=None, pnum=None, rng_mode="philox", seed=0, chain_offset=0,
              z=None, u=None, forced=None, rtol=None, atol=None, max_steps=500000, solver="dopri5", step_sd=0.05,
              trace=False, keep_samples=True, summaries=True, segments=1, device_buffers=False, speculate=0,
-             chain_ids=None, prior=None, sample_layout="iteration"):
+             chain_ids=None, prior=None, sample_layout="iteration", explicit_budget=0, stop_failed=False):
         """Run len(theta0) independent chains.  Returns dict with numpy arrays (or torch tensors when
         device_buffers=True): theta (final points), samples [C, nits-1-burnin, P+5], summaries
         [C, 1+2P], chain_state [C,8] (chi, r2, accepts, best_chi, best_iteration, ...), best_theta [C, P] (the
@@ -340,8 +340,12 @@ class DeviceModel:
 
         prior: None = the reference's chain (prior densities never enter the acceptance ratio, Samplers.py:118-127);
         a list of (kind, a, b, c) per parameter (as sample_lhs) = Metropolis-Hastings on the posterior, the prior
-        log-densities and the Hastings term of the multiplicative walk evaluated in the kernel."""
-        so = self._solver_opts(rtol, atol, max_steps, solver, False)
+        log-densities and the Hastings term of the multiplicative walk evaluated in the kernel.
+
+        solver="auto": per solve, DOPRI5 within ``explicit_budget`` attempted steps (0: until Hairer's test calls the solve
+        stiff), else the same solve again on BDF (odl_mcmc_auto_kernel).  stop_failed: a chain stops at its first failed
+        solve (the caller re-runs it with another stepper; fail_count > 0 marks it)."""
+        so = self._solver_opts(rtol, atol, max_steps, solver, False, pass_caps=int(explicit_budget))
         P = self.n_param
         walk = list(range(P)) if walk is None else [int(w) for w in walk]
         if not burnin:
@@ -358,6 +362,7 @@ class DeviceModel:
         mo.row_stride = P + 5
         mo.step_sd, mo.seed = float(step_sd), int(seed) & 0xFFFFFFFFFFFFFFFF
         mo.speculate = int(speculate)
+        mo.stop_failed_chains = 1 if stop_failed else 0
         it_major = {"iteration": True, "chain": False}[sample_layout]
         mo.sample_layout = _capi.SAMPLES_ITERATION_MAJOR if it_major else _capi.SAMPLES_CHAIN_MAJOR
 

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/odelib_b200.h but not exported"
     assert sorted(_capi.EXPORTS) == names
-    assert L.odl_abi_version() == 2
+    assert L.odl_abi_version() == 3
 
 
 @pytest.mark.parametrize("name", ["zero_i", "one_i", "two_i"])

@@ -118,7 +118,8 @@ def test_bdf_matches_lsoda_on_stiff_systems():
 
 
 def test_mcmc_on_the_stiff_variant_ros23_and_auto():
-    """Config 4: chains on synthetic stiff data; ROS23 and auto make the same decisions on host streams."""
+    """Config 4: chains on synthetic stiff data; ROS23, BDF and auto (per solve: DOPRI5 until Hairer's test calls the solve
+    stiff, then the same solve on BDF) make the same decisions on host streams."""
     from odelib_b200 import demo_models
     from odelib_b200.engine import DeviceModel
     center = np.array([0.5, 1e-7, 50.0, 1e-2, 1e4])
@@ -140,9 +141,15 @@ def test_mcmc_on_the_stiff_variant_ros23_and_auto():
     a = dm.mcmc(starts, nits=nits, rng_mode="host", z=z, u=u, solver="ros23", trace=True, max_steps=2000000)
     b = dm.mcmc(starts, nits=nits, rng_mode="host", z=z, u=u, solver="auto", trace=True, max_steps=2000000)
     assert np.isfinite(a["chinew"]).all() and a["fail_count"].sum() == 0
-    # auto = DOPRI5 until Hairer's test calls a proposal stiff, then ROS23 for that solve: same chi to solver accuracy
-    np.testing.assert_allclose(b["chinew"], a["chinew"], rtol=1e-5)
-    assert (a["accepted"] != b["accepted"]).sum() <= 2
+    # auto = DOPRI5 until Hairer's test calls a proposal stiff, then BDF for that solve: same chi to solver accuracy
+    # (BDF at the default tolerance: chi within 1e-4 of the tight solve, see test_bdf_sweep_matches_odeint)
+    np.testing.assert_allclose(b["chinew"], a["chinew"], rtol=2e-4)
+    assert (a["accepted"] != b["accepted"]).sum() <= 2 and b["fail_count"].sum() == 0
+    # every solve here is stiff: the solves auto hands to BDF are the BDF kernel's solves, bit for bit
+    d = dm.mcmc(starts, nits=nits, rng_mode="host", z=z, u=u, solver="bdf", trace=True, max_steps=2000000)
+    same = b["chinew"] == d["chinew"]                             # (the rest DOPRI5 finished itself, stiff or not)
+    assert same.mean() > 0.5, same.mean()
+    np.testing.assert_allclose(b["chinew"], d["chinew"], rtol=2e-4)
     ref = orc.mh_chain(orc.two_i, starts[0], tab, 5, nits=nits, z=z[0], u=u[0], rtol=1e-10, atol=1e-10)
     np.testing.assert_allclose(a["chinew"][0], ref["chinew"], rtol=5e-4)
     c = dm.mcmc(starts, nits=nits, rng_mode="host", z=z, u=u, solver="radau5", trace=True)
@@ -179,7 +186,8 @@ def test_facade_picks_the_bdf_kernel_for_a_stiff_posterior():
 def test_chains_that_exhaust_the_explicit_budget_are_rerun_on_bdf():
     """solver='auto' on a non-stiff start: DOPRI5 with a bounded step budget per solve; a chain that ever exhausts it is
     re-run whole on the BDF kernel with the same random streams (chain_ids keep its Philox key).  Every chain is then
-    either the plain DOPRI5 chain or the plain BDF chain, bit for bit."""
+    either the plain DOPRI5 chain or the plain BDF chain, bit for bit.  (In the first run a failing chain stops at its
+    first failed solve -- stop_failed -- which the chains that never fail must not notice.)"""
     import scipy.stats
     import odelib_b200 as ODElib
     from odelib_b200 import demo_models
@@ -201,12 +209,50 @@ def test_chains_that_exhaust_the_explicit_budget_are_rerun_on_bdf():
     raw = m._run_chains([s for s in starts], list(range(C)), nits, nits // 2, [], rng="philox", return_raw=True)
     assert m._last_solver == "dopri5" and 0 < m._last_rerun < C
     assert raw["fail_count"].sum() == 0
-    plain = dm.mcmc(starts, nits=nits, rng_mode="philox", seed=int(m.random_seed), chain_ids=np.arange(C), max_steps=230)
-    bdf = dm.mcmc(starts, nits=nits, rng_mode="philox", seed=int(m.random_seed), chain_ids=np.arange(C), solver="bdf",
-                  max_steps=2000000)
+    key = dict(nits=nits, rng_mode="philox", seed=int(m.random_seed), chain_ids=np.arange(C), trace=True)
+    plain = dm.mcmc(starts, max_steps=230, **key)
+    bdf = dm.mcmc(starts, solver="bdf", max_steps=2000000, **key)
     bad = plain["fail_count"] > 0
     assert bad.sum() == m._last_rerun
     assert np.array_equal(raw["samples"][~bad], plain["samples"][~bad])
     assert np.array_equal(raw["samples"][bad], bdf["samples"][bad])
     assert np.array_equal(raw["summaries"][bad], bdf["summaries"][bad])
     assert np.array_equal(raw["best_chi"][bad], bdf["best_chi"][bad], equal_nan=True)
+    # stop_failed: the same chains are marked, the others are untouched, a marked chain is the plain chain up to its stop
+    for K in (1, 8):
+        stop = dm.mcmc(starts, max_steps=230, stop_failed=True, speculate=K, **key)
+        assert np.array_equal(stop["fail_count"] > 0, bad)
+        assert np.array_equal(stop["samples"][~bad], plain["samples"][~bad])
+        assert np.array_equal(stop["summaries"][~bad], plain["summaries"][~bad])
+        first = np.argmax(np.isnan(plain["chinew"]), axis=1)
+        for c in np.flatnonzero(bad):
+            assert np.array_equal(stop["chinew"][c, :first[c] + 1], plain["chinew"][c, :first[c] + 1], equal_nan=True)
+            # (K lanes per chain: the round that holds the first failure may consume further failed proposals -- all of
+            # them rejected -- before the chain stops)
+            assert 1 <= stop["fail_count"][c] <= K
+
+
+def test_two_stepper_chain_kernel_hands_single_solves_to_bdf():
+    """odl_mcmc(solver=auto) with an explicit budget: per solve, DOPRI5 within the budget, else the same solve on BDF
+    (LSODA's method switch, per solve).  A chain whose solves all stay within the budget is the plain DOPRI5 chain bit for
+    bit; in the others every solve the plain kernel gave up on has a finite chi, and up to the first of them the chain is
+    the plain chain."""
+    dm, _ = device_model("two_i")
+    rng = np.random.default_rng(3)
+    center = np.array([7.475e-09, 1.069e-07, 19.73, 1.934, 2.799])
+    starts = center * np.exp(0.3 * rng.standard_normal((48, 5)))
+    probe = dm.sweep(starts, solver="dopri5", max_steps=230)
+    starts = starts[probe["status"] == 0][:32]
+    C, nits = len(starts), 60
+    key = dict(nits=nits, rng_mode="philox", seed=11, chain_ids=np.arange(C), trace=True)
+    plain = dm.mcmc(starts, max_steps=230, **key)
+    both = dm.mcmc(starts, solver="auto", explicit_budget=230, max_steps=2000000, **key)
+    bad = plain["fail_count"] > 0
+    assert 0 < bad.sum() < C and both["fail_count"].sum() == 0
+    for k in ("samples", "summaries", "theta", "chinew", "accepted"):
+        assert np.array_equal(both[k][~bad], plain[k][~bad]), k
+    gave_up = np.isnan(plain["chinew"]) & bad[:, None]
+    first = np.argmax(gave_up, axis=1)
+    assert np.isfinite(both["chinew"][bad, first[bad]]).all()
+    for c in np.flatnonzero(bad):
+        assert np.array_equal(both["chinew"][c, :first[c]], plain["chinew"][c, :first[c]])
