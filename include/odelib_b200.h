@@ -191,8 +191,9 @@ int odl_trajectory(odl_model* m, const odl_solver_opts* so, long long n, const d
    DOPRI5 and, when that gives up, done again with the variable-order BDF stepper -- the per-solve method switch LSODA makes
    for the reference (Framework.py:656).  "Gives up": so->pass_cap0 > 0 = that many attempted steps (Hairer's stiffness
    test only with so->stiff_check); pass_cap0 = 0 = Hairer's test (and max_steps).  Which stepper finishes a solve depends
-   on that solve alone, so a chain whose solves all stay within pass_cap0 equals the ODL_SOLVER_DOPRI5 chain run with
-   max_steps = pass_cap0 bit for bit.  fail_count counts solves that neither stepper finished. */
+   on that solve alone, so a chain whose solves all stay within pass_cap0 is the ODL_SOLVER_DOPRI5 chain run with
+   max_steps = pass_cap0 (same decisions; chi to rounding -- the two kernels are compiled separately).  fail_count counts
+   solves that neither stepper finished. */
 int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_opts* mo, const odl_mcmc_io* io, int mem,
              void* stream);
 

@@ -7,6 +7,13 @@
 #define ODL_CHAIN_STATE 8
 #define ODL_LOGTAB 256        // intervals of [1, 2) in the scorer's logarithm table (odl_log): 2 doubles each, per CTA
 
+// Cooperative kernels (n > 8, g lanes per system): doubles between the shared-memory rows (state | parameters | staging)
+// of two groups.  The 32/g groups of a warp load the SAME index of their own rows at once (each a broadcast inside the
+// group): the rows must start in different banks.  A row length divisible by g puts them in the same ones -- the 5x5
+// network's rows were 35 + 40 + 181 = 256 doubles: every shared load of the right-hand side was served in 2-4 passes
+// (9.7e9 bank conflicts for 3.3e9 LDS, profiles/r2j_mcmc_coop_network_full_ncu.txt) -- so such a row gets one more.
+#define ODL_COOP_ROW(base, g) ((base) + (((g) < 32 && (base) % (g) == 0) ? 1 : 0))
+
 // status words (per system)
 #define ODL_OK 0
 #define ODL_MAXSTEPS 1

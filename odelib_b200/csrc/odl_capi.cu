@@ -528,7 +528,7 @@ static const unsigned kCoopBlock = 128;
 static size_t coop_smem_bytes(const odl_model* m, const OdlData& d) {
   const size_t groups = kCoopBlock / m->coop;
   size_t doubles = 2 * ODL_LOGTAB + (size_t)d.n_slot + 3 * (size_t)d.n_obs + ((size_t)d.n_obs + 1) / 2 +
-                   groups * ((size_t)m->n_state + m->n_param + d.stage_stride);
+                   groups * (size_t)ODL_COOP_ROW(m->n_state + m->n_param + d.stage_stride, m->coop);
   return doubles * sizeof(double);
 }
 static size_t smem_bytes(const OdlData& d, int block) {
@@ -1161,7 +1161,7 @@ extern "C" int odl_mcmc(odl_model* m, const odl_solver_opts* so, const odl_mcmc_
   if (solver == ODL_SOLVER_AUTO) {
     // per solve: DOPRI5, and the same solve again on BDF when it gives up.  pass_cap0 > 0: "gives up" = that many attempted
     // steps (then Hairer's test runs only if the caller asked for it, so that a chain whose solves all stay within the
-    // budget is the plain DOPRI5 chain under max_steps = pass_cap0, bit for bit); else Hairer's test routes.
+    // budget is the plain DOPRI5 chain under max_steps = pass_cap0); else Hairer's test routes.
     O.explicit_cap = so && so->pass_cap0 > 0 ? so->pass_cap0 : 0;
     O.stiff_check = O.explicit_cap > 0 ? (so->stiff_check ? 1 : 0) : 1;
   }

@@ -2460,7 +2460,7 @@ __device__ __forceinline__ OdlGroup odl_coop_group(const OdlShared& S, const Odl
   G.sub = lane & (ODL_G - 1);
   G.mask = (ODL_G == 32) ? 0xffffffffu : (((1u << ODL_G) - 1u) << (lane & ~(ODL_G - 1)));
   const int group = threadIdx.x / ODL_G;
-  double* base = S.stage + (size_t)group * (ODL_N + ODL_P + D.stage_stride);
+  double* base = S.stage + (size_t)group * ODL_COOP_ROW(ODL_N + ODL_P + D.stage_stride, ODL_G);
   G.ysm = base; G.psm = base + ODL_N; G.stage = base + ODL_N + ODL_P;
 #pragma unroll
   for (int c = 0; c < ODL_C; ++c) {
@@ -2564,7 +2564,7 @@ odl_mcmc_coop_kernel(const OdlData D, const OdlOpts O, const OdlMcmcArgs A) {
   if (gthread / span >= (long long)A.n_chain) return;             // the lanes of a chain leave together
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   const bool lead = G.sub == 0;
-  const size_t group_doubles = (size_t)ODL_N + ODL_P + D.stage_stride;
+  const size_t group_doubles = (size_t)ODL_COOP_ROW(ODL_N + ODL_P + D.stage_stride, ODL_G);
   double* cs = A.chain_state + (size_t)chain * ODL_CHAIN_STATE;
   double* cur = A.theta_cur + (size_t)chain * ODL_P;
   OdlCoopStepper st;

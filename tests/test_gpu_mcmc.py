@@ -28,9 +28,12 @@ def _replay(chi0, chinew, u):
 
 
 @pytest.mark.parametrize("name", MODELS)
-@pytest.mark.parametrize("tag,tol,delta,rtol_chi", [("def", None, 1e-4, 2e-5), ("tight", 1e-13, 1e-8, 1e-9)])
+@pytest.mark.parametrize("tag,tol,delta,rtol_chi", [("def", None, 1e-4, 1e-6), ("tight", 1e-13, 1e-8, 1e-9)])
 def test_teacher_forced_decisions_match_reference(name, tag, tol, delta, rtol_chi):
-    """Reference proposals fed to the GPU: chinew within tolerance, decisions identical except near-ties."""
+    """Reference proposals fed to the GPU: chinew within tolerance, decisions identical except near-ties
+    |(chi - chinew) - ln u| < delta.  The recorded chains hold NO near-tie (smallest decision margin 7.7e-4 at the
+    default tolerance, where chinew differs by <= 2.6e-7 relative / 4.5e-5 absolute from the reference's -- measured,
+    tools/tolerance_probe.py), so every decision and every kept sample must be the reference's."""
     g = golden(name)
     pre = f"chain_{tag}_s0_"
     nits = int(g[pre + "nits"])
@@ -42,7 +45,7 @@ def test_teacher_forced_decisions_match_reference(name, tag, tol, delta, rtol_ch
     fin = np.isfinite(g[pre + "chinew"])
     np.testing.assert_allclose(out["chinew"][0][fin], g[pre + "chinew"][fin], rtol=rtol_chi, atol=1e-7)
     tie = _near_tie(ref_cur, g[pre + "chinew"], g[pre + "u"], delta)
-    assert tie.sum() <= 2
+    assert tie.sum() == 0
     first_tie = np.flatnonzero(tie)[0] if tie.any() else len(tie)
     assert np.array_equal(out["accepted"][0][:first_tie].astype(bool), ref_acc[:first_tie])
     if not tie.any():

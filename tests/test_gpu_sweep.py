@@ -16,15 +16,22 @@ def _healthy(pred_ref):
 
 @pytest.mark.parametrize("name", MODELS)
 def test_trajectories_at_observations_default_tolerance(name):
-    """vs the reference at scipy's default tolerance: both sides carry ~1e-7 integration error; rtol 5e-6."""
+    """vs the reference at scipy's default tolerance (rtol = atol = 1.49e-8 on both sides).  Measured on B200
+    (tools/tolerance_probe.py): predictions differ by <= 1.3e-7 relative, chi by <= 7.5e-8, R^2 by <= 2.6e-7 -- and most of
+    that is the REFERENCE's own integration error: against the reference at 1e-13 the GPU's default-tolerance predictions
+    are off by 8e-8 / 2e-8 / 1e-9 (zero_i / one_i / two_i), LSODA's by 1.3e-7 / 6e-8 / 4e-8.  Thresholds: 4x the measured
+    difference, and the GPU must be no further from the tight solution than 2x what the reference itself is."""
     g = golden(name)
     dm, _ = device_model(name)
     out = dm.sweep(g["theta"], return_pred=True)
-    ok = _healthy(g["pred_def"]) & (out["status"] == 0)
+    ok = _healthy(g["pred_def"]) & _healthy(g["pred_tight"]) & (out["status"] == 0)
     assert ok.sum() >= 0.6 * len(ok)
-    np.testing.assert_allclose(out["pred"][ok], g["pred_def"][ok], rtol=5e-6)
-    np.testing.assert_allclose(out["chi"][ok], g["chi_def"][ok], rtol=2e-5, atol=1e-6)
-    np.testing.assert_allclose(out["r2"][ok], g["r2_def"][ok], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(out["pred"][ok], g["pred_def"][ok], rtol=5e-7)
+    np.testing.assert_allclose(out["chi"][ok], g["chi_def"][ok], rtol=3e-7, atol=1e-7)
+    np.testing.assert_allclose(out["r2"][ok], g["r2_def"][ok], rtol=1e-6, atol=1e-7)
+    err = lambda a, b: float(np.max(np.abs(a[ok] - b[ok]) / np.abs(b[ok])))
+    assert err(out["pred"], g["pred_tight"]) <= 2 * err(g["pred_def"], g["pred_tight"])
+    assert err(out["chi"], g["chi_tight"]) <= 2 * err(g["chi_def"], g["chi_tight"])
 
 
 @pytest.mark.parametrize("name", MODELS)
