@@ -2224,7 +2224,16 @@ struct OdlSliceOut {             // dy[k] = v of the traced code: kept when comp
   int sub;
   struct Ref {
     OdlSliceOut& o; int k;
-    __device__ __forceinline__ void operator=(double v) { if ((k % ODL_G) == o.sub) o.mine[k / ODL_G] = v; }
+    // a SELECT, not a branch.  Written as `if (mine) slot = v` the compiler branched around every output and sank the
+    // arithmetic that feeds only that output into the branch: executed once per lane-of-the-group (G times) by 32/G lanes
+    // each instead of once by all of them -- 19 % of the kernel's instructions at 7 lanes, 30 % of its stall samples, half
+    // of all branches divergent (profiles/r2m_mcmc_coop_network_ncu.txt)
+    __device__ __forceinline__ void operator=(double v) {
+      const bool own = (k % ODL_G) == o.sub;
+      const int hi = own ? __double2hiint(v) : __double2hiint(o.mine[k / ODL_G]);
+      const int lo = own ? __double2loint(v) : __double2loint(o.mine[k / ODL_G]);
+      o.mine[k / ODL_G] = __hiloint2double(hi, lo);
+    }
   };
   __device__ __forceinline__ Ref operator[](int k) { return Ref{*this, k}; }
 };
