@@ -276,7 +276,7 @@ def config_legs(world, rank, local, dev, peak_tflops, barrier, max_over_ranks, s
                         "accept_rate": float(np.asarray(res["chain_state"])[:, 2].mean()) / (nits - 1),
                         "chains_rerun_on_bdf": int(getattr(m, "_last_rerun", 0)),
                         "api": "ModelFramework._run_chains (the body of ModelFramework.MCMC): solver='auto', Philox streams",
-                        "kernel": "odl_mcmc_coop_kernel (%d lanes per system)" % (4 if dm.n_state <= 16 else 8) if coop
+                        "kernel": "odl_mcmc_coop_kernel (%d lanes per system)" % dm.coop_lanes if coop
                                   else "odl_mcmc_kernel (thread per system, prefetching MH)"}
     out["c3_nclass_chains"] = c3
     if "c4" not in legs and "c5" not in legs:
@@ -328,7 +328,7 @@ def config_legs(world, rank, local, dev, peak_tflops, barrier, max_over_ranks, s
                                       "max": float(np.nanmax(rh)),
                                       "collective": "odl_rhat: ncclAllGather over %d ranks + device reduction" % world if world > 1
                                                     else "odl_rhat: device reduction (1 GPU, no collective)"},
-                             "kernel": "odl_mcmc_coop_kernel (8 lanes per system)",
+                             "kernel": "odl_mcmc_coop_kernel (%d lanes per system)" % dm.coop_lanes,
                              "proposals_over_the_step_budget": int(sum_over_ranks(float(res5["fail_count"].sum().item()))),
                              "note": "iterations shortened below 8 GPUs (100 / 200 / 400 / 1000 at 1 / 2 / 4 / 8) so that the leg stays "
                                      "within seconds; the rate is per chain-step"}

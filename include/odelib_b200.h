@@ -76,8 +76,9 @@ typedef struct odl_build_opts {
   int y0_from_param;   /* 1 = some state's initial value is a parameter ('<state>0', Samplers.py:110-114).  As in the
                           reference this holds for the solves of MCMC PROPOSALS only: odl_sweep, odl_trajectory and a
                           chain's a-priori solve start from y0 (istates, Framework.py:647-650; Samplers.py:88) */
-  int coop_lanes;      /* n_state > 8: lanes per system of the cooperative kernels (4, 8, 16 or 32);
-                          0 = by state count (4 up to 16 states, 8 up to 64, 16 up to 128, else 32) */
+  int coop_lanes;      /* n_state > 8: lanes per system of the cooperative kernels (2, 4, 8, 16 or 32);
+                          0 = by state count, the fewest lanes with at most 9 components per lane (2 up to 18 states,
+                          4 up to 36, 8 up to 72, 16 up to 144, else 32) */
   int reserved[1];
   const char* cache_dir; /* directory for compiled cubins, NULL = no cache */
 } odl_build_opts;

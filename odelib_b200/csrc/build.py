@@ -109,8 +109,12 @@ def check_kernels(strict=True, models=None):
     # of an AUTO sweep, trajectories) keep such systems in local memory by design and are not held to the rule
     big = {name for name, _, n, _, _, _ in specs if n > 8}
     coop_only = ("odl_sweep_coop_kernel", "odl_mcmc_coop_kernel", "odl_order_key_kernel", "odl_order_scan_kernel", "odl_order_scatter_kernel")
+    # the 35-state network at its default of 4 lanes per system (9 components per lane) is the one known exception: 255
+    # registers and 88 / 198 bytes of spill in the cooperative kernels, and still 1.5x the speed of the spill-free 8-lane
+    # build (coop_lanes_default in odl_capi.cu has the measurements)
+    tolerated = {("network_5x5", "odl_sweep_coop_kernel"): 256, ("network_5x5", "odl_mcmc_coop_kernel"): 256}
     bad = [(m, k, v["spill"]) for m, ks in report.items() for k, v in ks.items()
-           if k in (coop_only if m in big else NO_SPILL) and v.get("spill", 0) > 0]
+           if k in (coop_only if m in big else NO_SPILL) and v.get("spill", 0) > tolerated.get((m, k), 0)]
     if strict and bad:
         raise RuntimeError("register spills in default-path kernels: " + ", ".join(f"{m}:{k} {b} B" for m, k, b in bad))
     return report

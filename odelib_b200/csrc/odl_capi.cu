@@ -207,7 +207,14 @@ static int serialize_after_previous_call(odl_model* m, cudaStream_t s) {
 }
 
 // cooperative kernels (n > 8): default lanes per system, as odl_kernels.cuh's ODL_G
-static int coop_lanes_default(int n_state) { return n_state <= 16 ? 4 : (n_state <= 64 ? 8 : (n_state <= 128 ? 16 : 32)); }
+// Lanes per system of the cooperative kernels: the fewest that keep a lane's slice at <= 9 components (10 slice-sized
+// vectors of DOPRI5 in registers).  Every lane of a group evaluates the whole right-hand side, so fewer lanes mean less
+// redundant arithmetic -- measured on B200: 12 states, 2 lanes against 4: sweep 30.8 against 23.9 M solves/s, 8192 chains
+// 17.6 against 16.3 M chain-steps/s; 35 states, 4 lanes against 8: sweep 8.3 against 5.9 M solves/s, 8192 chains 7.0
+// against 4.7 M chain-steps/s (at 255 registers with 88 / 198 bytes of spill -- 8 lanes: none)
+static int coop_lanes_default(int n_state) {
+  return n_state <= 18 ? 2 : (n_state <= 36 ? 4 : (n_state <= 72 ? 8 : (n_state <= 144 ? 16 : 32)));
+}
 
 static uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
   const unsigned char* p = static_cast<const unsigned char*>(data);
@@ -385,7 +392,7 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
   }
   if (m->block % 32 || m->block > 1024) { delete m; return fail(ODL_EINVAL, "block_threads must be a multiple of 32, <= 1024"); }
   if (m->coop == 0) m->coop = coop_lanes_default(n_state);
-  if (m->coop != 4 && m->coop != 8 && m->coop != 16 && m->coop != 32) { delete m; return fail(ODL_EINVAL, "coop_lanes must be 4, 8, 16 or 32"); }
+  if (m->coop != 2 && m->coop != 4 && m->coop != 8 && m->coop != 16 && m->coop != 32) { delete m; return fail(ODL_EINVAL, "coop_lanes must be 2, 4, 8, 16 or 32"); }
   m->src = model_cuda_src;
   m->opt = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device", "--ptxas-options=-v",
             "-DODL_BLOCK=" + std::to_string(m->block), "-DODL_MINBLOCKS=" + std::to_string(m->minblocks),

@@ -70,7 +70,7 @@ class DeviceModel:
         # and emits the per-lane right-hand side for exactly that many lanes (tracer.slice_plan)
         lanes = 0
         if n_state > 8:
-            lanes = int(coop_lanes) or (4 if n_state <= 16 else 8 if n_state <= 64 else 16 if n_state <= 128 else 32)
+            lanes = int(coop_lanes) or (2 if n_state <= 18 else 4 if n_state <= 36 else 8 if n_state <= 72 else 16 if n_state <= 144 else 32)
         # sliced_rhs: the per-lane right-hand side (each lane evaluates only its own outputs, leaves through an index table).
         # Measured on B200 and NOT the default: it halves the FP64 work of the 35-state network (FP64 pipe 25 % -> 12 %) but the
         # index arithmetic adds more instructions than the flops it saves (LDG/PRMT/IMAD/LEA = 47 % of the executed
@@ -80,6 +80,7 @@ class DeviceModel:
             sliced_rhs = os.environ.get("ODL_COOP_SLICED", "0") == "1"
         self.source = self.traced.cuda_source(fmad=fmad, observe_groups=self.groups, coop_lanes=lanes if sliced_rhs else 0)
         coop_lanes = lanes
+        self.coop_lanes = lanes                                   # 0 for n <= 8 (thread per system)
         self.rhs_flops = self.traced.flops()
         L = _capi.lib()
         if cache_dir:
