@@ -542,6 +542,16 @@ def run_ours(args):
         assert chains_seen == C * world
         steps_total = sum_over_ranks(float(res["step_count"].sum().item()))
         kept_bytes = C * res["n_keep"] * (P + 5) * 8
+        # a chain is the same chain wherever and beside whatever it runs (Philox key = global chain index): every rank
+        # runs its LAST chain again alone (another launch shape, another prefetching width) and compares bit for bit;
+        # global chain 0 has the same start on every world size, so its hash must be the same in every line of a
+        # 1/2/4/8-GPU scaling run
+        import hashlib
+        alone = dm.mcmc(starts[C - 1:C].contiguous(), **dict(kw, chain_offset=rank * C + C - 1))
+        same_alone = bool(torch.equal(alone["samples"][0].contiguous().view(torch.int64),
+                                      res["samples"][C - 1].contiguous().view(torch.int64)))   # bits (NaN-safe)
+        assert sum_over_ranks(0.0 if same_alone else 1.0) == 0.0, "a chain re-run alone differs from the same chain in the sharded launch"
+        chain0_sha1 = hashlib.sha1(res["samples"][0].contiguous().cpu().numpy().tobytes()).hexdigest()
         mcmc = {"chain_steps_per_s": C * world * (nits - 1) / t_m, "chains_per_gpu": C, "chains_total": C * world,
                 "iterations": nits, "seconds": t_m, "solves_per_s": C * world * nits / t_m,
                 "fp64_tflops": (steps_total * flops_step) / t_m / 1e12 / world,
@@ -550,7 +560,10 @@ def run_ours(args):
                 "rhat_max": float(np.nanmax(rh)), "rhat_seconds": t_rhat,
                 "rhat_note": "500 iterations from scattered starts do not converge (R-hat >> 1): this leg times the kernel",
                 "rhat_collective": "odl_rhat: ncclAllGather over %d ranks + device reduction" % world if world > 1
-                                   else "odl_rhat: device reduction (1 GPU, no collective)"}
+                                   else "odl_rhat: device reduction (1 GPU, no collective)",
+                "identity": {"last_chain_of_every_rank_rerun_alone_bit_identical": same_alone,
+                             "global_chain0_samples_sha1": chain0_sha1,
+                             "note": "the sha1 must be the same on every world size (same start, Philox key = global chain index)"}}
 
         # the same kernel with the GPU filled (BASELINE config 5's chain count per GPU x 8): throughput regime
         if args.chains_large > 0:
