@@ -208,9 +208,10 @@ def workload_config(args, n_gpus):
                         f"infection model (4 states, 5 parameters) integrated to the 37 demo observations "
                         f"(19 grid times of t_steps={TSTEPS}) + chi/R^2 [BASELINE.json configs[1]]",
             "sets_per_gpu": args.sets, "sets_total": args.sets * n_gpus, "rtol": 1.49012e-8, "atol": 1.49012e-8,
-            "solver": "auto: rows cost-ordered on the device (|J(y0)| key), dopri5(4) with dense output <=512 attempted "
-                      "steps (projection check at 384) on ~72 % of the SMs, variable-order BDF for what is left (~1.4 %) "
-                      "BESIDE it on SMs of its own (42 CTAs of 8 warps, clusters of 2)",
+            "solver": "auto: rows cost-ordered on the device (|J(y0)| key), dopri5(4) with dense output <=704 attempted "
+                      "steps (projection check at 384) on ~78 % of the SMs, variable-order BDF for what is left (~0.9 %) "
+                      "BESIDE it on SMs of its own (32 CTAs of 8 warps, clusters of 2; a second consumer on the SMs the "
+                      "DOPRI5 pass frees when it ends)",
             "l2": "flushed between timed steps (256 MiB write)",
             "parallelism": f"shard{n_gpus}"}
 
@@ -467,12 +468,13 @@ def run_ours(args):
     bytes_launch = n * (P * 8 + 8 + 8 + 4 + 4)
     ok_frac = float((status == 0).float().mean().item())
     mean_steps = float(nsteps.double().mean().item())
-    # the bulk kernel on its own: the DOPRI5 pass of the sweep (<= 512 attempted steps, projection check at 384) in
+    # the bulk kernel on its own: the DOPRI5 pass of the sweep (<= 704 attempted steps, projection check at 384) in
     # input order.  A solve depends on nothing but its own row, so this is also the exact set the sweep's DOPRI5 pass
     # finishes; the rest was finished by the BDF pass.
     bulk_out = {k: torch.empty_like(v) for k, v in out.items()}
     for _ in range(2):
-        dm.sweep(theta_dev, out=bulk_out, solver="dopri5", max_steps=512, stiff_check=True, early_check_steps=384)
+        dm.sweep(theta_dev, out=bulk_out, solver="dopri5", max_steps=engine.AUTO_CAP, stiff_check=True,
+                 early_check_steps=engine.AUTO_EARLY_CHECK)
     torch.cuda.synchronize()
     bulk_ms = dm.last_kernel_ms()
     bulk_ok = bulk_out["status"] == 0
@@ -483,7 +485,7 @@ def run_ours(args):
     stiff_steps = float(nsteps[~bulk_ok].sum().item())
     flops_launch = bulk_flops + stiff_steps * flops_bdf_step + float((~bulk_ok).sum().item()) * flops_solve
     achieved = flops_launch / (avg_ms * 1e-3) / 1e12
-    bulk = {"kernel": "odl_sweep_kernel (DOPRI5 pass: <= 512 attempted steps, projection check at 384), input order",
+    bulk = {"kernel": "odl_sweep_kernel (DOPRI5 pass: <= 704 attempted steps, projection check at 384), input order",
             "ms": bulk_ms, "finished_fraction": float(bulk_ok.float().mean().item()),
             "achieved_TFLOPs": bulk_flops / (bulk_ms * 1e-3) / 1e12,
             "frac_of_fp64_peak": bulk_flops / (bulk_ms * 1e-3) / 1e12 / peak_tflops}
@@ -648,8 +650,9 @@ def run_ours(args):
                          "frac": achieved / peak_tflops,
                          "traffic": traffic.get("bytes") if n == (1 << 20) else None,
                          "traffic_note": traffic.get("note"),
-                         "kernel": "odl_sweep (8 launches: 3 ordering kernels, odl_sweep_bdf_kernel (consumer, beside), odl_gate_kernel, "
-                                   "odl_sweep_kernel, odl_feed_done_kernel, odl_sweep_bdf_kernel (pick-up of what the consumer left: normally nothing))",
+                         "kernel": "odl_sweep (9 launches: 3 ordering kernels, odl_sweep_bdf_kernel (consumer, beside), odl_gate_kernel, "
+                                   "odl_sweep_kernel, odl_feed_done_kernel, odl_sweep_bdf_kernel (second consumer on the SMs the bulk "
+                                   "pass frees), odl_sweep_bdf_kernel (pick-up of what the consumers left: normally nothing))",
                          "avg_launch_ms": avg_ms,
                          "peak_source": "measured live: odl_fp64_peak DFMA chains (MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_per_launch": flops_launch, "flops_per_step_attempt": flops_step,

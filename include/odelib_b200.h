@@ -57,7 +57,9 @@ enum { ODL_AUTO_UNORDERED = 1,   /* process rows in input order (no cost orderin
                                     (default: from 262,144 rows on) */
        ODL_AUTO_ONE_PIECE = 4,   /* ODL_MEM_HOST: upload theta in one piece before anything runs (default: two pieces,
                                     the second travelling while the first is swept) */
-       ODL_AUTO_SEQUENTIAL = 8   /* run the stiff pass AFTER the DOPRI5 pass (single-warp CTAs over every SM) */ };
+       ODL_AUTO_SEQUENTIAL = 8,  /* run the stiff pass AFTER the DOPRI5 pass (single-warp CTAs over every SM) */
+       ODL_AUTO_NO_HELPER = 16   /* stiff pass beside the DOPRI5 pass: no second consumer on the SMs that pass frees when it
+                                    ends (development: the state of the code before that helper existed) */ };
 enum { ODL_RNG_PHILOX = 0, ODL_RNG_HOST_STREAMS = 1, ODL_RNG_FORCED = 2 };
 enum { ODL_SAMPLES_CHAIN_MAJOR = 0, ODL_SAMPLES_ITERATION_MAJOR = 1 };
 /* per-system status words */
@@ -90,13 +92,13 @@ typedef struct odl_solver_opts {
   int solver;          /* ODL_SOLVER_* */
   int stiff_check;     /* DOPRI5: detect stiffness and stop with ODL_ST_STIFF */
   int stiff_min_steps; /* ... only while more than this many steps of the current size remain (0 = 2000) */
-  int pass_cap0;       /* ODL_SOLVER_AUTO: step cap of the first DOPRI5 pass (odl_sweep: 0 = 512; odl_mcmc: see there) */
+  int pass_cap0;       /* ODL_SOLVER_AUTO: step cap of the first DOPRI5 pass (odl_sweep: 0 = 704; odl_mcmc: see there) */
   int tail_warps;      /* ODL_SOLVER_AUTO: SMs set aside for the stiff pass when it runs beside the DOPRI5 pass (one CTA
-                          of 8 warps each; 0 = a quarter of them) */
+                          of 8 warps each; 0 = 22 % of them) */
   int tail_solver;     /* ODL_SOLVER_AUTO: stepper of the pass over what DOPRI5 did not finish:
                           0 = default (ODL_SOLVER_BDF), or ODL_SOLVER_RADAU5 */
   int early_check_steps; /* ODL_SOLVER_AUTO: the first pass drops a system after this many attempts when its progress
-                          projects beyond pass_cap0 (0 = 3/4 of pass_cap0, -1 = never) */
+                          projects beyond pass_cap0 (0 = 3/4 of pass_cap0 but at most 384, -1 = never) */
   int tail_lanes;      /* ODL_SOLVER_AUTO: lanes per warp that take systems in the stiff pass (0 = as few as spreading its
                           systems over every resident warp takes; 32 = full warps) */
   int auto_flags;      /* ODL_SOLVER_AUTO: ODL_AUTO_* bits, 0 = cost-ordered DOPRI5 pass, then the stiff pass */

@@ -207,6 +207,10 @@ static int serialize_after_previous_call(odl_model* m, cudaStream_t s) {
 }
 
 // cooperative kernels (n > 8): default lanes per system, as odl_kernels.cuh's ODL_G
+// ODL_SOLVER_AUTO sweeps: attempted steps of the DOPRI5 pass, and the attempt at which a system whose progress projects
+// beyond that cap leaves for the stiff pass (odl_sweep has the measurements)
+static const int ODL_AUTO_CAP_DEFAULT = 704, ODL_AUTO_EARLY_DEFAULT = 384;
+
 // Lanes per system of the cooperative kernels: the fewest that keep a lane's slice at <= 9 components (10 slice-sized
 // vectors of DOPRI5 in registers).  Every lane of a group evaluates the whole right-hand side, so fewer lanes mean less
 // redundant arithmetic -- measured on B200: 12 states, 2 lanes against 4: sweep 30.8 against 23.9 M solves/s, 8192 chains
@@ -862,7 +866,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     }
     const bool coop_bulk = m->coop_model();                      // n > 8: the bulk pass is the cooperative kernel (go_coop)
     const bool beside = !coop_bulk && !(flags & ODL_AUTO_SEQUENTIAL) && ((flags & ODL_AUTO_CONCURRENT) || n >= (1 << 18));
-    const int cap0 = so && so->pass_cap0 > 0 ? so->pass_cap0 : 512;
+    const int cap0 = so && so->pass_cap0 > 0 ? so->pass_cap0 : ODL_AUTO_CAP_DEFAULT;
     CUfunction k_tail = tail_solver == ODL_SOLVER_RADAU5 ? m->k_sweep_radau : m->k_sweep_bdf;
     // counter block (zeroed above): [0] bulk work counter (+ [384], [448] for later pieces), [64] feed count,
     // [128] feed ticket, [192] feed-complete flag, [256] work counter of the pick-up launch, [320] watchdog,
@@ -870,7 +874,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     // [1024] hist[256], [2048] cursor[256] (per piece)
     ODL_CUDA(cudaMemsetAsync(feed, 0xFF, (size_t)n * sizeof(int), s));
     // ordering of one piece [lo, hi) of the table -> index[lo..hi) (global row numbers)
-    auto order_piece = [&](long long lo, long long hi, int piece) -> int {
+    auto order_piece = [&](long long lo, long long hi, int piece, cudaStream_t so_) -> int {
       OdlOrderArgs R{};
       const long long np = hi - lo;
       R.theta = A.theta + lo * m->n_param; R.n = np; R.bins = static_cast<unsigned char*>(bbins.p) + lo;
@@ -882,9 +886,9 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       const unsigned g1 = (unsigned)std::max<long long>(1, std::min<long long>((np + 255) / 256, (long long)m->sm_count * 8));
       const unsigned g3 = (unsigned)std::max<long long>(1, std::min<long long>((np + 2047) / 2048, (long long)m->sm_count * 8));
       int r;
-      if ((r = launch(m, m->k_order_key, g1, 256, 0, s, p1))) return r;
-      if ((r = launch(m, m->k_order_scan, 1, ODL_ORDER_BINS, 0, s, p2))) return r;
-      return launch(m, m->k_order_scatter, g3, 256, 0, s, p2);
+      if ((r = launch(m, m->k_order_key, g1, 256, 0, so_, p1))) return r;
+      if ((r = launch(m, m->k_order_scan, 1, ODL_ORDER_BINS, 0, so_, p2))) return r;
+      return launch(m, m->k_order_scatter, g3, 256, 0, so_, p2);
     };
     // piece boundaries: [0, n/2, n] rounded to 1024 rows (one piece when the table is already on the device).  Measured
     // on B200, 1M two_i rows through host buffers: two halves 190 M solves/s, three pieces (1/8, 3/8, 1/2) 180 M/s --
@@ -893,12 +897,11 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     const int n_piece = chunked ? 2 : 1;
     long long cut[4] = {0, n, n, n};
     if (chunked) {
-      // share of the rows in the first piece.  Stiff pass beside the bulk pass: a quarter -- the rows of the SECOND
-      // piece that the stiff pass has to take reach it one bulk launch late, and it needs ~2.5 ms for the longest of
-      // them, so the second launch should be the long one (1M rows through pinned host buffers: 5.44 ms at 1/2,
-      // 4.88 at 1/3 .. 1/5, 4.85 at 0.15; one piece 5.09).  Stiff pass after the bulk pass: halves (5.10 / 5.04 / 5.12
-      // at 1/2, 1/3, 1/4).
-      double first = beside_first_quarter ? 0.25 : 0.5;
+      // share of the rows in the first piece: its upload is the one nothing hides.  Stiff pass beside the bulk pass, the
+      // pieces' launches overlapping (below): 1M rows through pinned buffers 4.62 ms at 1/4, 4.40 at 0.15, 4.33 at 0.1,
+      // 4.40 at 0.05 (round 2 before the overlap, one launch after the other: 5.44 at 1/2, 4.88 at 1/3 .. 1/5, 4.85 at 0.15).
+      // Stiff pass after the bulk pass: halves (5.10 / 5.04 / 5.12 at 1/2, 1/3, 1/4).
+      double first = beside_first_quarter ? 0.15 : 0.5;
       if (const char* e = getenv("ODL_FIRST_PIECE")) first = std::min(0.9, std::max(0.05, atof(e)));   // development knob
       cut[1] = (((long long)(n * first) + 1023) / 1024) * 1024;
     }
@@ -933,7 +936,12 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       // measured on B200, 1M two_i prior draws (15k rows, ~7M BDF steps for the consumer), back-to-back calls behind an
       // L2 flush as bench.py times them, consumer CTAs in clusters of 2: 34 SMs 3.98 ms, 36 3.88, 40 3.73, 42 3.62,
       // 44 3.67 (stiff pass after the bulk pass: 4.1-4.3) -- between a quarter and a third of the SMs
-      tail_sms = so && so->tail_warps > 0 ? so->tail_warps : (m->sm_count * 29 + 50) / 100;
+      // Round 2, with the DOPRI5 cap at 704 (projection check still at 384: 9.4k rows and 5.0M BDF steps instead of 15k
+      // and 7.5M) the consumer keeps up on fewer SMs: 704 / 42 SMs 3.82 ms (its rows arrive later and its longest end after
+      // the bulk pass), 36 3.44, 34 3.38, 32 3.32, 30 3.37, 28 3.61 (backlog when the bulk pass ends); cap 640 / 34 3.40,
+      // 736 / 32 3.33, 768 / 34 3.66 (profiles/r2q_beside_grid.log)
+      // (two-piece host-memory sweeps: two SMs more -- the rows of the second piece reach the consumer in a shorter time)
+      tail_sms = so && so->tail_warps > 0 ? so->tail_warps : (m->sm_count * 22 + 50) / 100 + (chunked ? 2 : 0);
       tail_sms = std::max(1, std::min(tail_sms, m->sm_count / 3));
       // Placement: on an idle GPU the block scheduler packs the consumer's CTAs onto neighbouring SMs, behind other
       // work it scatters them -- and a consumer SM whose TPC partner runs the bulk kernel steps 8-12 % slower
@@ -953,7 +961,10 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     // projection check at 3/4 of the cap: a system whose progress projects beyond the cap leaves there.  (At cap0/2 the
     // check has recall ~100 % but precision ~50 %: it doubled the stiff pass's load with long NON-stiff systems -- 19 %
     // of the zero_i sweep, 1-2 % of one_i / two_i, measured with tools/variant_ab.py.)
-    O0.early_check_steps = so && so->early_check_steps != 0 ? std::max(0, so->early_check_steps) : O0.max_steps * 3 / 4;
+    // (and at most ODL_AUTO_EARLY_DEFAULT: the rows that leave here are on the stiff pass's critical path -- ~860 BDF steps of
+    // 1.7 us -- and must reach it early whatever the cap is)
+    O0.early_check_steps = so && so->early_check_steps != 0 ? std::max(0, so->early_check_steps)
+                                                            : std::min(O0.max_steps * 3 / 4, ODL_AUTO_EARLY_DEFAULT);
     OdlSweepArgs A0 = A;
     A0.index = ordered ? index : nullptr;
     A0.defer_list[0] = A0.defer_list[1] = feed; A0.defer_count[0] = A0.defer_count[1] = cnt(64);
@@ -980,7 +991,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       ODL_CUDA(cudaEventRecord(m->ev_aux, m->aux2));
     }
     if (chunked) ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[0], 0));
-    if (ordered && (rc = order_piece(0, cut[1], 0))) return rc;
+    if (ordered && (rc = order_piece(0, cut[1], 0, s))) return rc;
     if (beside) {
       // the bulk grid must not arrive before the consumer's CTAs have their SMs (see odl_gate_kernel)
       const int* res = cnt(512);
@@ -996,22 +1007,43 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       const OdlSweepArgs Aall = A0;
       A0.n = cut[1];                                         // pb points at A0: first piece, index[0..cut[1])
       const unsigned g0 = (unsigned)std::max<long long>(1, std::min<long long>((cut[1] + block0 - 1) / block0, (long long)grid0));
+      // The later pieces are ordered and swept on the HELPER stream, behind their own upload: their grids wait for SM
+      // slots, not for the end of the launch before them.  One after the other on one stream every bulk launch ended on
+      // its own stragglers -- a launch cannot end before its longest row, cap0 attempts of ~2.4 us, whatever the size
+      // of its piece -- and with the cap at 704 that idle tail made the two-piece call SLOWER than with 512 (5.1 against
+      // 4.8 ms per 1M rows through pinned buffers); now the CTAs of the next piece take the slots as the stragglers'
+      // neighbours retire.  (The ordering kernels of a later piece get their first slot the same way.)
+      ODL_CUDA(cudaEventRecord(m->ev_fork, s));              // counters reset, consumer resident, first piece ordered
       if ((rc = launch(m, m->k_sweep, g0, block0, smem0, s, pb))) return rc;
-      for (int c = 1; c < n_piece; ++c) {
-        ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[c], 0));
-        if ((rc = order_piece(cut[c], cut[c + 1], c))) return rc;
+      ODL_CUDA(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
+      for (int c = 1; c < n_piece; ++c) {                    // (the stream's own order puts piece c behind its upload)
+        if ((rc = order_piece(cut[c], cut[c + 1], c, m->aux))) return rc;
         OdlSweepArgs Ac = Aall;
         Ac.n = cut[c + 1] - cut[c]; Ac.index = index + cut[c]; Ac.counter = ctr(384 + 64 * (c - 1));   // chunked => ordered
         void* pbc[] = {&Dl, &O0, &Ac};
         const unsigned gc = (unsigned)std::max<long long>(1, std::min<long long>((Ac.n + block0 - 1) / block0, (long long)grid0));
-        if ((rc = launch(m, m->k_sweep, gc, block0, smem0, s, pbc))) return rc;
+        if ((rc = launch(m, m->k_sweep, gc, block0, smem0, m->aux, pbc))) return rc;
       }
+      ODL_CUDA(cudaEventRecord(m->ev_chunk[2], m->aux));
+      ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[2], 0));   // every bulk launch has ended: the feed is complete
     }
     ODL_CUDA(cudaEventRecord(m->evp[0], s));
     if (beside) {
       int* flag = cnt(192);
       void* pf[] = {&flag};
       if ((rc = launch(m, m->k_feed_done, 1, 1, 0, s, pf))) return rc;
+      // The bulk pass has ended and left most SMs idle: a second consumer over the SAME ticket counter -- single-warp CTAs
+      // on every SM, as many lanes per warp as spreading what is left of the feed takes -- helps the first one finish.
+      // (Without it the sweep ends when the 20-30 % of the SMs the first consumer owns have worked the feed off alone:
+      // one_i 0.37 ms, zero_i 2.1 ms after the bulk pass, and the split of the SMs had to be tuned per model.)
+      if (!(flags & ODL_AUTO_NO_HELPER)) {
+        OdlOpts Oh = O2; Oh.lanes = -1;
+        OdlSweepArgs Ah = A2;
+        Ah.counter = nullptr; Ah.feed_ticket = ctr(128); Ah.feed_done = cnt(192); Ah.watchdog = cnt(320); Ah.resident = nullptr;
+        void* ph[] = {&Dl, &Oh, &Ah};
+        ODL_CU(g_drv.FuncSetAttribute(k_tail, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max(smem_t, smem_wide)));
+        if ((rc = launch(m, k_tail, grid_t, 32, smem_t, s, ph))) return rc;
+      }
       ODL_CUDA(cudaStreamWaitEvent(s, m->ev_aux, 0));            // the consumer has drained the feed
     }
     // the stiff pass proper (sequential mode) / the pick-up of entries the consumer left (beside mode: normally none)

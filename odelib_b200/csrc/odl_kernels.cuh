@@ -1594,7 +1594,9 @@ ODL_UNROLL
   // spread evenly over all warps of the grid, each warp using as few lanes as that takes.
   int lanes_used = O.lanes;
   if (O.lanes < 0) {
-    const int count = A.index_count ? *A.index_count : 32 * (int)(gridDim.x * (blockDim.x >> 5));
+    int count = A.index_count ? *A.index_count : 32 * (int)(gridDim.x * (blockDim.x >> 5));
+    // a consumer launched behind the bulk pass (the feed is complete): what the first consumer has not taken yet
+    if (A.feed_ticket) count = max(0, count - (int)min((unsigned long long)count, *(volatile unsigned long long*)A.feed_ticket));
     const int warps = (int)(gridDim.x * (blockDim.x >> 5));
     lanes_used = min(32, max(1, (count + warps - 1) / warps));
   }

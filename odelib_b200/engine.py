@@ -31,6 +31,8 @@ def _is_torch_cuda(a):
 
 
 SOLVERS = {"dopri5": 0, "ros23": 1, "auto": 2, "radau5": 3, "bdf": 4}
+# defaults of the ODL_SOLVER_AUTO sweep (odl_capi.cu): the DOPRI5 pass's step cap and its projection check
+AUTO_CAP, AUTO_EARLY_CHECK = 704, 384
 
 
 class ObsTables:

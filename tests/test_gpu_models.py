@@ -4,6 +4,8 @@ checked against the oracle (scipy odeint) on synthetic data of the demo's shape.
 import numpy as np
 import pytest
 
+from odelib_b200 import engine
+
 from odelib_b200 import demo_models
 from oracle import odelib_oracle as orc
 from tests.helpers import synthetic_problem
@@ -96,7 +98,7 @@ def test_cooperative_mapping_agrees_with_thread_per_system(which):
     np.testing.assert_allclose(coop["chi"], tps["chi"], rtol=1e-7)
     # AUTO's bulk pass is the cooperative kernel (rows it finishes within its step cap carry exactly its numbers)
     auto = dm.sweep(theta, solver="auto", max_steps=2000000)
-    plain = dm.sweep(theta, max_steps=512)
+    plain = dm.sweep(theta, max_steps=engine.AUTO_CAP)
     fin = plain["status"] == 0
     assert fin.sum() >= 30 and np.all(auto["status"] == 0)
     assert np.array_equal(auto["chi"][fin], plain["chi"][fin])

@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 
+from odelib_b200 import engine
 from oracle import odelib_oracle as orc
 from tests.helpers import device_model, golden, oracle_rhs, prior_draws
 
@@ -216,8 +217,8 @@ def test_auto_sweep_is_independent_of_ordering_and_of_how_the_passes_are_schedul
         other = dm.sweep(theta, solver="auto", max_steps=200000, auto_flags=_capi.AUTO_CONCURRENT, tail_warps=sms)
         for k in ("chi", "r2", "status", "nsteps"):
             assert np.array_equal(base[k], other[k], equal_nan=True), (sms, k)
-    # the DOPRI5 pass alone (cap 512, projection check at 384) finishes a set of rows; the rest carries BDF numbers
-    dop = dm.sweep(theta, solver="dopri5", max_steps=512, stiff_check=True, early_check_steps=384)
+    # the DOPRI5 pass alone (its cap, its projection check) finishes a set of rows; the rest carries BDF numbers
+    dop = dm.sweep(theta, solver="dopri5", max_steps=engine.AUTO_CAP, stiff_check=True, early_check_steps=engine.AUTO_EARLY_CHECK)
     fin = dop["status"] == 0
     assert 0.95 < fin.mean() < 0.999
     assert np.array_equal(base["chi"][fin], dop["chi"][fin]) and np.array_equal(base["nsteps"][fin], dop["nsteps"][fin])
@@ -241,7 +242,7 @@ def test_host_memory_sweep_in_two_pieces_equals_one_piece_and_the_device_call():
     b = dm.sweep(theta, solver="auto", max_steps=200000, auto_flags=_capi.AUTO_ONE_PIECE)
     c = dm.sweep(torch.from_numpy(theta).cuda(), solver="auto", max_steps=200000)
     d = dm.sweep(theta, solver="auto", max_steps=200000, auto_flags=_capi.AUTO_SEQUENTIAL)
-    assert np.all(a["status"] == 0) and (a["nsteps"] > 512).sum() > 100
+    assert np.all(a["status"] == 0) and (a["nsteps"] > engine.AUTO_CAP).sum() > 50
     for k in ("chi", "r2", "status", "nsteps"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
         assert np.array_equal(a[k], c[k].cpu().numpy(), equal_nan=True), k
@@ -260,7 +261,7 @@ def test_a_consumer_that_gives_up_costs_time_not_rows(monkeypatch):
     monkeypatch.setenv("ODL_WATCHDOG_SPINS", "1000")            # the floor: ~0.4 ms of patience
     host = dm.sweep(theta, solver="auto", max_steps=200000, auto_flags=_capi.AUTO_CONCURRENT)
     dev = dm.sweep(torch.from_numpy(theta).cuda(), solver="auto", max_steps=200000, auto_flags=_capi.AUTO_CONCURRENT)
-    assert np.all(base["status"] == 0) and (base["nsteps"] > 512).sum() > 50
+    assert np.all(base["status"] == 0) and (base["nsteps"] > engine.AUTO_CAP).sum() > 20
     for k in ("chi", "r2", "status", "nsteps"):
         assert np.array_equal(base[k], host[k], equal_nan=True), k
         assert np.array_equal(base[k], dev[k].cpu().numpy(), equal_nan=True), k
@@ -274,7 +275,7 @@ def test_auto_sweep_rows_of_both_steppers_against_the_oracle():
     theta = prior_draws("two_i", 30000, seed=21)
     out = dm.sweep(theta, solver="auto", max_steps=200000, return_pred=True)
     assert np.all(out["status"] == 0)
-    dop = dm.sweep(theta, solver="dopri5", max_steps=512, stiff_check=True, early_check_steps=384)
+    dop = dm.sweep(theta, solver="dopri5", max_steps=engine.AUTO_CAP, stiff_check=True, early_check_steps=engine.AUTO_EARLY_CHECK)
     by_bdf = np.flatnonzero(dop["status"] != 0)
     by_dop = np.flatnonzero(dop["status"] == 0)
     assert len(by_bdf) > 200
