@@ -50,6 +50,8 @@ extern "C" {
 
 enum { ODL_SUCCESS = 0, ODL_EINVAL = 1, ODL_ECUDA = 2, ODL_ECOMPILE = 3, ODL_ENODEVICE = 4, ODL_EIO = 5 };
 enum { ODL_MEM_HOST = 0, ODL_MEM_DEVICE = 1 };
+enum { ODL_RHAT_LOCAL = 256 };  /* odl_rhat only, or-ed into `mem`: reduce THIS rank's chains, no collective, whatever
+                                   communicator the handle has joined */
 enum { ODL_SOLVER_DOPRI5 = 0, ODL_SOLVER_ROS23 = 1, ODL_SOLVER_AUTO = 2, ODL_SOLVER_RADAU5 = 3, ODL_SOLVER_BDF = 4 };
 /* odl_solver_opts.auto_flags */
 enum { ODL_AUTO_UNORDERED = 1,   /* process rows in input order (no cost ordering) */

@@ -819,7 +819,7 @@ class ModelFramework:
             if out["samples"] is not None and (return_frame or not return_raw):
                 out["samples"] = out["samples"].cpu().numpy()
         if C > 1 and out["n_keep"] > 1 and out.get("summaries") is not None and self._world()[0] == 1:
-            out["rhat_device"] = dm.rhat(np.asarray(out["summaries"]))   # odl_rhat: reduction on the device
+            out["rhat_device"] = dm.rhat(np.asarray(out["summaries"]), local=True)   # odl_rhat: reduction on the device
         self._last_mcmc = out
         if return_raw:
             return out

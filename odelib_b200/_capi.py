@@ -15,6 +15,7 @@ SOLVER_DOPRI5, SOLVER_ROS23, SOLVER_AUTO, SOLVER_RADAU5, SOLVER_BDF = 0, 1, 2, 3
 RNG_PHILOX, RNG_HOST_STREAMS, RNG_FORCED = 0, 1, 2
 SAMPLES_CHAIN_MAJOR, SAMPLES_ITERATION_MAJOR = 0, 1
 COMM_ID_BYTES = 128
+RHAT_LOCAL = 256
 AUTO_UNORDERED, AUTO_CONCURRENT, AUTO_ONE_PIECE, AUTO_SEQUENTIAL, AUTO_NO_HELPER = 1, 2, 4, 8, 16
 ST_OK, ST_MAXSTEPS, ST_NONFINITE, ST_HUNDERFLOW, ST_STIFF, ST_ALLMASKED = 0, 1, 2, 3, 4, 8
 

@@ -1701,7 +1701,12 @@ extern "C" int odl_rhat(odl_model* m, const double* summaries, int n_chain_local
   if ((rc = serialize_after_previous_call(m, s))) return rc;
   ODL_CUDA(cudaEventRecord(m->ev0, s));
   const size_t W = 1 + 2 * (size_t)n_param;
-  const int world = m->comm ? m->comm_world : 1;
+  // ODL_RHAT_LOCAL: this rank's chains only, whatever communicator the handle has joined -- a single-GPU caller (the
+  // facade without distributed=True) on a handle that other code has joined to a communicator must not start a collective
+  // the other ranks never enter (bench.py under torchrun hung exactly there)
+  const bool local_only = (mem & ODL_RHAT_LOCAL) != 0;
+  mem &= ~ODL_RHAT_LOCAL;
+  const int world = (m->comm && !local_only) ? m->comm_world : 1;
   // scratch: [0] padded local block, [1] gathered table, [2] results (rhat[P], pooled[1+2P], n_pad)
   DevBuf &bloc = m->scratch[0], &ball = m->scratch[1], &bres = m->scratch[2];
   if ((rc = bres.ensure((n_param + W + 2) * sizeof(double)))) return rc;

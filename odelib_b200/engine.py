@@ -294,7 +294,7 @@ class DeviceModel:
         self._comm_world = world
         return world
 
-    def rhat(self, summaries):
+    def rhat(self, summaries, local=False):
         """Gelman-Rubin R-hat [P] over the chains of all ranks from this rank's per-chain summaries [m_local, 1+2P]
         (numpy or CUDA tensor): odl_rhat -- ncclAllGather + reduction on the device.  Also returns the pooled
         (count, log_mean[P], log_std[P]) of all kept rows and the total number of chains."""
@@ -306,6 +306,8 @@ class DeviceModel:
         rh = np.empty(P)
         pooled = np.empty(1 + 2 * P)
         total = C.c_longlong(0)
+        if local:                                                 # this rank's chains only, no collective (see odl_rhat)
+            mem |= _capi.RHAT_LOCAL
         _capi.check(self._L.odl_rhat(self._h, _ptr(sm), int(sm.shape[0]), P, mem, rh.ctypes.data, pooled.ctypes.data,
                                      C.byref(total), self._stream() if mem == _capi.MEM_DEVICE else None))
         N = pooled[0]

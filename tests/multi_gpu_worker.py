@@ -49,6 +49,13 @@ def main(out_path):
     summ = m.MCMC(chain_inits=[m.get_parameters(as_dict=True)] * 5, iterations_per_chain=60, print_report=False,
                   posterior="summary", rng="philox")
     one = m.MCMC(chain_inits=[{}], iterations_per_chain=40, print_report=False)      # fewer chains than ranks
+    # a NON-distributed facade on a handle that has joined the communicator (what bench.py does: its MCMC leg joins the
+    # model's handle, then rank 0 alone runs ModelFramework.MCMC): rank 0's R-hat must not start a collective
+    m1 = make_model("two_i", device=local)
+    m1._device().comm_init()
+    if rank == 0:
+        solo = m1.MCMC(chain_inits=[m1.get_parameters(as_dict=True)] * 6, iterations_per_chain=40, print_report=False)
+        assert len(solo) == 6 * 19 and np.all(np.isfinite(list(m1.rhat.values())))
     if ws > 1:
         frames = [None] * ws
         dist.all_gather_object(frames, (sv.to_numpy(), post.to_numpy()))
