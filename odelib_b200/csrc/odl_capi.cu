@@ -174,6 +174,8 @@ struct odl_model {
   cudaEvent_t ev_chunk[3] = {nullptr, nullptr, nullptr};   // host-memory sweeps: theta arrives in pieces on the helper stream
   cudaStream_t aux = nullptr;                // helper stream: theta pieces of a host-memory sweep
   cudaStream_t aux2 = nullptr;               // helper stream: the stiff pass beside the DOPRI5 pass
+  cudaStream_t piece_stream[2] = {nullptr, nullptr};   // host-memory sweeps: the later pieces are ordered and swept here
+  cudaEvent_t ev_piece[2] = {nullptr, nullptr};        //   ... and these mark the end of their bulk launches
   ncclComm_t comm = nullptr;                 // odl_comm_init: the ranks that share an MCMC run (R-hat all-gather)
   int comm_world = 1, comm_rank = 0;
   int n_pass = 0;
@@ -459,7 +461,11 @@ extern "C" int odl_model_create(const char* model_cuda_src, int n_state, int n_p
       cudaEventCreateWithFlags(&m->ev_chunk[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&m->ev_chunk[2], cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&m->aux2, cudaStreamNonBlocking) != cudaSuccess)
+      cudaStreamCreateWithFlags(&m->aux2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&m->piece_stream[0], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&m->piece_stream[1], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_piece[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->ev_piece[1], cudaEventDisableTiming) != cudaSuccess)
     return bail(fail(ODL_ECUDA, "cudaEventCreate / cudaStreamCreate failed"));
   if ((rc = m->counter.ensure(8192))) return bail(rc);
   m->on_gpu = true;
@@ -487,6 +493,8 @@ extern "C" int odl_model_destroy(odl_model* m) {
   for (auto& e : m->ev_chunk) if (e) cudaEventDestroy(e);
   if (m->aux) cudaStreamDestroy(m->aux);
   if (m->aux2) cudaStreamDestroy(m->aux2);
+  for (auto& st_ : m->piece_stream) if (st_) cudaStreamDestroy(st_);
+  for (auto& e : m->ev_piece) if (e) cudaEventDestroy(e);
   if (m->on_gpu && prev >= 0 && prev != m->device) cudaSetDevice(prev);
   delete m;
   return 0;
@@ -894,16 +902,28 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     // on B200, 1M two_i rows through host buffers: two halves 190 M solves/s, three pieces (1/8, 3/8, 1/2) 180 M/s --
     // every extra bulk launch ends on its own stragglers, which costs more than the shorter wait for the first piece.
     const bool beside_first_quarter = !m->coop_model() && !(flags & ODL_AUTO_SEQUENTIAL);
-    const int n_piece = chunked ? 2 : 1;
+    // Two pieces.  Three (10 / 30 / 60 %, ODL_PIECES=3) keep the SMs fed while the table is still arriving but were measured
+    // SLOWER (5.0 against 4.3 ms): every piece is cost-ordered on its own, the rows the stiff pass has to take start when
+    // their PIECE starts, and from there they need ~0.9 ms to reach that pass and up to 1.5 ms in it -- the last piece
+    // has to start early, so it has to be the big one.
+    const int n_piece = chunked ? ((beside_first_quarter && getenv("ODL_PIECES") && atoi(getenv("ODL_PIECES")) == 3) ? 3 : 2) : 1;
     long long cut[4] = {0, n, n, n};
     if (chunked) {
       // share of the rows in the first piece: its upload is the one nothing hides.  Stiff pass beside the bulk pass, the
       // pieces' launches overlapping (below): 1M rows through pinned buffers 4.62 ms at 1/4, 4.40 at 0.15, 4.33 at 0.1,
       // 4.40 at 0.05 (round 2 before the overlap, one launch after the other: 5.44 at 1/2, 4.88 at 1/3 .. 1/5, 4.85 at 0.15).
       // Stiff pass after the bulk pass: halves (5.10 / 5.04 / 5.12 at 1/2, 1/3, 1/4).
-      double first = beside_first_quarter ? 0.15 : 0.5;
+      double first = beside_first_quarter ? 0.10 : 0.5;
       if (const char* e = getenv("ODL_FIRST_PIECE")) first = std::min(0.9, std::max(0.05, atof(e)));   // development knob
       cut[1] = (((long long)(n * first) + 1023) / 1024) * 1024;
+      // three pieces (10 %, 30 %, 60 %): the upload runs at ~4x the speed of the sweep, so once the first piece is there
+      // every later one lands before the SMs run out of rows (with two pieces they idled ~0.15 ms waiting for the second)
+      if (n_piece == 3) {
+        double second = 0.30;
+        if (const char* e = getenv("ODL_SECOND_PIECE")) second = std::min(0.9, std::max(0.05, atof(e)));   // development knob
+        if (!getenv("ODL_FIRST_PIECE")) cut[1] = (((long long)(n * 0.10) + 1023) / 1024) * 1024;
+        cut[2] = std::min(n, cut[1] + (((long long)(n * second) + 1023) / 1024) * 1024);
+      }
     }
     if (chunked) {
       ODL_CUDA(cudaEventRecord(m->ev_fork, s));                  // behind the previous call on this handle
@@ -1015,17 +1035,20 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       // neighbours retire.  (The ordering kernels of a later piece get their first slot the same way.)
       ODL_CUDA(cudaEventRecord(m->ev_fork, s));              // counters reset, consumer resident, first piece ordered
       if ((rc = launch(m, m->k_sweep, g0, block0, smem0, s, pb))) return rc;
-      ODL_CUDA(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
-      for (int c = 1; c < n_piece; ++c) {                    // (the stream's own order puts piece c behind its upload)
-        if ((rc = order_piece(cut[c], cut[c + 1], c, m->aux))) return rc;
+      for (int c = 1; c < n_piece; ++c) {
+        if (cut[c + 1] <= cut[c]) continue;
+        cudaStream_t sp = m->piece_stream[c - 1];            // a stream of its own: behind ITS upload, beside the others
+        ODL_CUDA(cudaStreamWaitEvent(sp, m->ev_fork, 0));
+        ODL_CUDA(cudaStreamWaitEvent(sp, m->ev_chunk[c], 0));
+        if ((rc = order_piece(cut[c], cut[c + 1], c, sp))) return rc;
         OdlSweepArgs Ac = Aall;
         Ac.n = cut[c + 1] - cut[c]; Ac.index = index + cut[c]; Ac.counter = ctr(384 + 64 * (c - 1));   // chunked => ordered
         void* pbc[] = {&Dl, &O0, &Ac};
         const unsigned gc = (unsigned)std::max<long long>(1, std::min<long long>((Ac.n + block0 - 1) / block0, (long long)grid0));
-        if ((rc = launch(m, m->k_sweep, gc, block0, smem0, m->aux, pbc))) return rc;
+        if ((rc = launch(m, m->k_sweep, gc, block0, smem0, sp, pbc))) return rc;
+        ODL_CUDA(cudaEventRecord(m->ev_piece[c - 1], sp));
+        ODL_CUDA(cudaStreamWaitEvent(s, m->ev_piece[c - 1], 0));   // every bulk launch has ended: the feed is complete
       }
-      ODL_CUDA(cudaEventRecord(m->ev_chunk[2], m->aux));
-      ODL_CUDA(cudaStreamWaitEvent(s, m->ev_chunk[2], 0));   // every bulk launch has ended: the feed is complete
     }
     ODL_CUDA(cudaEventRecord(m->evp[0], s));
     if (beside) {
