@@ -24,7 +24,9 @@ static inline void sincospi(double x, double* s, double* c) { *s = sin(M_PI * x)
 #include "odl_kernels.cuh"
 
 struct HostSink {
+  static constexpr bool kObservedOnly = false;
   double* out;
+  inline void put(int, const double (&)[ODL_NOUT]) {}
   inline void operator()(int slot, const double (&yi)[ODL_N]) {
     for (int i = 0; i < ODL_N; ++i) out[(long long)slot * ODL_N + i] = yi[i];
   }

@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from odelib_b200 import engine  # noqa: E402
 from tests.helpers import device_model, prior_draws  # noqa: E402
 
 MODEL = os.environ.get("MODEL", "two_i")
@@ -45,12 +46,12 @@ for cfg in (sys.argv[1:] or DEFAULT):
                 best, passes = dm.last_kernel_ms(), dm.last_pass_ms()
         ns = out["nsteps"].cpu().numpy().astype(np.int64)
         st = out["status"].cpu().numpy()
-        cap = skw.get("pass_caps", 512)
+        cap = skw.get("pass_caps", engine.AUTO_CAP)
         # rows the bulk pass finished carry <= cap attempts; the others were finished by the stiff pass (its own count)
         chi = out["chi"].cpu().numpy()
         info_b = dm.kernel_info("sweep_bdf")
         # bench.py's flop count: rows the capped DOPRI5 pass finishes at 360 per attempt, the rest at the BDF rate
-        b = dm.sweep(theta, solver="dopri5", max_steps=cap, stiff_check=True, early_check_steps=skw.get("early_check_steps", cap * 3 // 4))
+        b = dm.sweep(theta, solver="dopri5", max_steps=cap, stiff_check=True, early_check_steps=skw.get("early_check_steps", min(cap * 3 // 4, engine.AUTO_EARLY_CHECK)))
         torch.cuda.synchronize()
         bulk_alone_ms = dm.last_kernel_ms()
         bok = (b["status"] == 0).cpu().numpy()
