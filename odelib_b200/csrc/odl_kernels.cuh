@@ -384,7 +384,9 @@ __device__ __forceinline__ void odl_dopri5_attempt(OdlStepper& st, const double 
   const double h_untrunc = h;
   if ((t + 1.01 * h - ttarget) > 0.0) { h = ttarget - t; truncated = true; last = (st.slot == D.n_slot - 1); }
 #endif
-  ++st.nsteps;
+  // attempts of a solve that is finished (slot == n_slot) or has failed are not counted: in the sweep and chain kernels a
+  // lane keeps running this code while it waits for its warp, and the count it holds stays that of its solve
+  st.nsteps += (st.slot < D.n_slot && st.status == ODL_OK) ? 1 : 0;
   double k2[ODL_N], k3[ODL_N], k4[ODL_N], k5[ODL_N], k6[ODL_N], k7[ODL_N], yt[ODL_N], yn[ODL_N];
 ODL_UNROLL
   for (int i = 0; i < ODL_N; ++i) yt[i] = st.y[i] + h * (ODL_T(0) * st.k1[i]);
@@ -2009,7 +2011,16 @@ ODL_UNROLL
     //      lanes finish left half of all issued instructions with one lane active -- profiles/r1a_mcmc_*; proposals
     //      of neighbouring chains, and the K proposals of one chain, cost nearly the same number of steps.) ----
     for (;;) {
-      if (active && !done) {
+      if constexpr (SOLVER == 0) {
+        // DOPRI5: every lane that has a solve this round runs the step code, finished or not (as in odl_sweep_body: the
+        // path AROUND the inlined step reconciles ~40 registers, and the lanes that wait for the slowest of the warp paid
+        // it on every attempt; now only a lane without a solve -- past the end of its chain -- takes it).  A finished
+        // lane writes nothing (slot == n_slot), its step count stands still and status words only ever leave OK.
+        if (active) {
+          odl_attempt<SOLVER>(st, ax, p, S, D, O, sink, false);
+          done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
+        }
+      } else if (active && !done) {
         odl_attempt<SOLVER>(st, ax, p, S, D, (SOLVER == 2 && !use_alt) ? Oe : O, sink, use_alt);
         done = (st.slot >= D.n_slot) || (st.status != ODL_OK);
       }
