@@ -471,7 +471,7 @@ ODL_UNROLL
       // the ODL_NOUT sums instead of the ODL_N states.  The continuous extension is linear in (y, y_new, k1, k3..k7), so
       // the polynomial of a sum is the sum of the polynomials: for the two_i model (4 states, 2 columns) half the
       // coefficient and Horner work of this block -- which a warp issues on nearly every step for the 9 of its 32 lanes
-      // that crossed an observation time -- for 16 additions (profiles/r2s_*: dense output 15 % of the instructions).
+      // that crossed an observation time -- for 16 additions (profiles/r2u_*: dense output 15 % of the instructions).
       if (st.slot < D.n_slot && S.slot_t[st.slot] <= tnew) {
         double oy[ODL_NOUT], on[ODL_NOUT], o1[ODL_NOUT], o3[ODL_NOUT], o4[ODL_NOUT], o5[ODL_NOUT], o6[ODL_NOUT], o7[ODL_NOUT];
         odl_observe(st.y, oy); odl_observe(yn, on); odl_observe(st.k1, o1); odl_observe(k3, o3);
