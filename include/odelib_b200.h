@@ -226,6 +226,12 @@ int odl_sample_lhs(odl_model* m, long long n, int n_param, const int* kind, cons
    u [n_chain][n_iter]; feed them to odl_mcmc with ODL_RNG_HOST_STREAMS. */
 int odl_reference_streams(const unsigned int* seeds, int n_chain, int n_iter, int n_walk, int n_prior_draws,
                           double step_sd, double* z, double* u);
+/* The same streams generated on the device (one thread per chain, MT19937 key arrays in device memory), for runs whose
+   streams would take the host generator longer than the chains take the GPU: z_dev [n_chain][n_iter][n_walk], u_dev
+   [n_chain][n_iter] device buffers, seeds on the host.  Uniforms are bit-identical to numpy's; a gaussian goes through
+   log(), where CUDA's and glibc's -- both within 1 ulp -- may round differently: z agrees to 1 ulp. */
+int odl_reference_streams_device(odl_model* m, const unsigned int* seeds_host, int n_chain, int n_iter, int n_walk,
+                                 int n_prior_draws, double step_sd, double* z_dev, double* u_dev, void* stream);
 
 /* The one collective of the path (the reference gathers its workers' frames with pd.concat,
    Framework.py:1035-1038, and has no R-hat): Gelman-Rubin R-hat on ln(theta) over the chains of EVERY rank.

@@ -781,7 +781,19 @@ class ModelFramework:
                            for p, (k, a, b, c) in zip(self._flat_owner(), table)]
         if rng == "reference":
             walking = [self.parameters[p] for p in walk_names]
-            z, u = Samplers.reference_streams_batch(seeds, walking, n_iter)
+            big = C * n_iter * (len(walk) + 1) > self.HOST_STREAM_DOUBLES
+            if big and Samplers.device_streams_possible(seeds, walking):
+                # too large for the host generator (~10 ns per draw): MT19937 per chain on the device; everything of
+                # this run then lives in device buffers
+                if not on_device:
+                    import torch
+                    theta0 = torch.from_numpy(np.ascontiguousarray(theta0)).to(torch.device("cuda", dm.device))
+                    on_device = True
+                    kw["device_buffers"] = True
+                z, u = dm.reference_streams(seeds, n_iter, sum(int(np.size(p.val)) for p in walking),
+                                            len([p for p in walking if p.dist]), Samplers.RWALK_SD)
+            else:
+                z, u = Samplers.reference_streams_batch(seeds, walking, n_iter)
             streams = dict(rng_mode="host", z=z, u=u)
         elif rng == "philox":
             streams = dict(rng_mode="philox", seed=int(self.random_seed), chain_ids=np.asarray(seeds, dtype=np.int64))
@@ -801,7 +813,12 @@ class ModelFramework:
                 redo = "bdf" if dm.n_state <= 8 else "dopri5"
                 sub = dict(streams)
                 if rng == "reference":
-                    sub["z"], sub["u"] = z[bad], u[bad]
+                    if hasattr(z, "is_cuda"):                     # streams generated on the device
+                        import torch
+                        pick = torch.as_tensor(bad, device=z.device)
+                        sub["z"], sub["u"] = z[pick].contiguous(), u[pick].contiguous()
+                    else:
+                        sub["z"], sub["u"] = z[bad], u[bad]
                 else:
                     sub["chain_ids"] = np.asarray(seeds, dtype=np.int64)[bad]
                 if on_device:
@@ -844,9 +861,15 @@ class ModelFramework:
                 self.set_inits(**{s: out["theta"][0][m] for s, m in zip(self._snames, self._y0_map()) if m >= 0})
         return frames
 
-    @staticmethod
-    def _auto_rng(n_chains, n_iter, n_walk):
-        return "reference" if n_chains * n_iter * (n_walk + 1) <= 20_000_000 else "philox"
+    HOST_STREAM_DOUBLES = 20_000_000         # reference streams up to this size are generated on the host (160 MB, bitwise numpy's)
+    DEVICE_STREAM_DOUBLES = 4_000_000_000    # ... up to this size (32 GB of HBM) on the device (odl_reference_streams_device)
+
+    @classmethod
+    def _auto_rng(cls, n_chains, n_iter, n_walk):
+        """'reference': the reference chain's own numpy random numbers (the library regenerates them: on the host while the
+        streams are small, on the device beyond that -- there the gaussians agree with numpy's to 1 ulp); 'philox' only for
+        runs whose streams would not fit in device memory either."""
+        return "reference" if n_chains * n_iter * (n_walk + 1) <= cls.DEVICE_STREAM_DOUBLES else "philox"
 
     def _frame_from_samples(self, samples, static):
         """One frame for all chains from the kernel's kept rows [C, n_keep, P+5], assembled without per-chain pandas

@@ -104,6 +104,12 @@ def reference_streams(seed, walking, n_iter):
     return z, u
 
 
+def device_streams_possible(seeds, walking):
+    """True when the library's own generators reproduce the reference's stream consumption: every prior's ``rvs`` is one
+    gaussian (lognorm, norm) and the seeds are 32-bit (numpy's init_genrand path)."""
+    return all(_one_gaussian_rvs(p) for p in walking if p.dist) and all(0 <= int(s) < 2 ** 32 for s in seeds)
+
+
 def reference_streams_batch(seeds, walking, n_iter):
     """reference_streams for many chains at once: z[C, n_iter, n_walk], u[C, n_iter].  Priors whose ``rvs`` is one
     gaussian (lognorm, norm) -- the demo's case -- are regenerated by the library's own MT19937 / polar-gauss

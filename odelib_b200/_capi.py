@@ -21,7 +21,7 @@ ST_OK, ST_MAXSTEPS, ST_NONFINITE, ST_HUNDERFLOW, ST_STIFF, ST_ALLMASKED = 0, 1, 
 
 EXPORTS = ["odl_abi_version", "odl_last_error", "odl_model_create", "odl_model_destroy", "odl_model_build_log",
            "odl_model_kernel_info", "odl_model_set_data", "odl_model_set_grid", "odl_sweep", "odl_trajectory",
-           "odl_mcmc", "odl_model_last_kernel_ms", "odl_model_last_pass_ms", "odl_launch_count", "odl_fp64_peak", "odl_debug_counters", "odl_select_below", "odl_gather_rows", "odl_sample_lhs", "odl_reference_streams",
+           "odl_mcmc", "odl_model_last_kernel_ms", "odl_model_last_pass_ms", "odl_launch_count", "odl_fp64_peak", "odl_debug_counters", "odl_select_below", "odl_gather_rows", "odl_sample_lhs", "odl_reference_streams", "odl_reference_streams_device",
            "odl_model_unit_seconds", "odl_debug_timeline", "odl_comm_unique_id", "odl_comm_init", "odl_comm_destroy",
            "odl_rhat"]
 
@@ -98,6 +98,8 @@ def lib():
     L.odl_sample_lhs.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_ulonglong, C.c_void_p, C.c_void_p]
     L.odl_reference_streams.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    L.odl_reference_streams_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]
     L.odl_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
                                   C.c_void_p]
     L.odl_model_unit_seconds.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]

@@ -168,6 +168,7 @@ struct odl_model {
   Tables data, grid;
   DevBuf counter;
   DevBuf scratch[24];                        // [0, 20): staging slots of one call; 21-23: select / gather / sample helpers
+  DevBuf mt_state;                           // odl_reference_streams_device: MT19937 key arrays, [624][n_chain] words
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evp[2] = {nullptr, nullptr};   // between the cohort passes of an AUTO sweep
   cudaEvent_t ev_aux = nullptr, ev_fork = nullptr;
@@ -483,7 +484,7 @@ extern "C" int odl_model_destroy(odl_model* m) {
     for (Unit& u : m->units) if (u.mod && g_drv.ModuleUnload) g_drv.ModuleUnload(u.mod);
   }
   odl_comm_destroy(m);
-  m->data.buf.release(); m->grid.buf.release(); m->counter.release();
+  m->data.buf.release(); m->grid.buf.release(); m->counter.release(); m->mt_state.release();
   for (auto& s : m->scratch) s.release();
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -1580,6 +1581,91 @@ extern "C" int odl_reference_streams(const unsigned int* seeds, int n_chain, int
   for (int t = 0; t < n_thr; ++t)
     pool.emplace_back(run, (int)((long long)n_chain * t / n_thr), (int)((long long)n_chain * (t + 1) / n_thr));
   for (auto& th : pool) th.join();
+  return 0;
+}
+
+// The same streams generated ON THE DEVICE, for runs whose streams would not fit the host side (4096 chains x 10,000
+// iterations x 11 gaussians are 1.2e9 MT19937 words: ~10 s on 16 host cores, and the chains themselves take 0.2 s): one
+// thread per chain, its 624-word key array in global memory laid out [624][n_chain] (the lanes of a warp read and
+// twist neighbouring words together), position and the polar method's cached value in registers.  Word for word the
+// generator above.  Uniforms are bit-identical to numpy's; a gaussian goes through log(), where CUDA's and glibc's
+// (both within 1 ulp of the truth) may round differently: z agrees with numpy to 1 ulp, most values exactly.
+__device__ __forceinline__ unsigned int odl_mt_next(unsigned int* key, long long C, int& pos) {
+  if (pos == 624) {
+    const unsigned int UPPER = 0x80000000u, LOWER = 0x7fffffffu, A = 0x9908b0dfu;
+    unsigned int cur = key[0], y;                     // cur / nxt: words i, i + 1 as they were BEFORE this twist
+    for (int i = 0; i < 623; ++i) {
+      const unsigned int nxt = key[(long long)(i + 1) * C];
+      y = (cur & UPPER) | (nxt & LOWER);
+      const int j = (i < 624 - 397) ? i + 397 : i + (397 - 624);
+      key[(long long)i * C] = key[(long long)j * C] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+      cur = nxt;
+    }
+    y = (cur & UPPER) | (key[0] & LOWER);             // word 0 as the loop has just rewritten it (genrand's order)
+    key[623LL * C] = key[396LL * C] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+    pos = 0;
+  }
+  unsigned int y = key[(long long)pos * C];
+  ++pos;
+  y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+  return y;
+}
+__device__ __forceinline__ double odl_mt_double(unsigned int* key, long long C, int& pos) {
+  const int a = (int)(odl_mt_next(key, C, pos) >> 5), b = (int)(odl_mt_next(key, C, pos) >> 6);
+  return __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+}
+__global__ void __launch_bounds__(128) odl_refstream_kernel(const unsigned int* seeds, unsigned int* keys, long long C, int n_iter,
+                                                            int n_walk, int n_prior, double step_sd, double* z, double* u) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  unsigned int* key = keys + c;
+  unsigned int seed = seeds[c];
+  for (int i = 0; i < 624; ++i) { key[(long long)i * C] = seed; seed = 1812433253u * (seed ^ (seed >> 30)) + (unsigned int)i + 1u; }
+  int pos = 624;
+  bool has_gauss = false;
+  double cached = 0.0;
+  auto gauss = [&]() -> double {
+    if (has_gauss) { has_gauss = false; const double t = cached; cached = 0.0; return t; }
+    double x1, x2, r2;
+    do {
+      x1 = __dadd_rn(__dmul_rn(2.0, odl_mt_double(key, C, pos)), -1.0);
+      x2 = __dadd_rn(__dmul_rn(2.0, odl_mt_double(key, C, pos)), -1.0);
+      r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));     // no contraction: numpy's build does not fuse these
+    } while (r2 >= 1.0 || r2 == 0.0);
+    const double f = __dsqrt_rn(__ddiv_rn(__dmul_rn(-2.0, log(r2)), r2));
+    cached = __dmul_rn(f, x1); has_gauss = true;
+    return __dmul_rn(f, x2);
+  };
+  double* zc = z + c * (long long)n_iter * n_walk;
+  double* uc = u + c * (long long)n_iter;
+  for (int i = 0; i < n_iter; ++i) {
+    for (int j = 0; j < n_walk; ++j) zc[(long long)i * n_walk + j] = __dadd_rn(0.0, __dmul_rn(step_sd, gauss()));
+    for (int j = 0; j < n_prior; ++j) gauss();
+    uc[i] = odl_mt_double(key, C, pos);
+  }
+}
+
+extern "C" int odl_reference_streams_device(odl_model* m, const unsigned int* seeds_host, int n_chain, int n_iter, int n_walk,
+                                            int n_prior_draws, double step_sd, double* z_dev, double* u_dev, void* stream) {
+  if (!m || !m->on_gpu) return fail(ODL_ENODEVICE, "odl_reference_streams_device: model is not loaded on a GPU (odl_reference_streams is the host generator)");
+  if (n_chain < 0 || n_iter < 0 || n_walk < 0 || n_prior_draws < 0 || (n_chain > 0 && (!seeds_host || !u_dev || (n_walk > 0 && !z_dev))))
+    return fail(ODL_EINVAL, "odl_reference_streams_device: bad argument");
+  if (n_chain == 0 || n_iter == 0) return 0;
+  ODL_ON_DEVICE(m);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if ((rc = serialize_after_previous_call(m, s))) return rc;
+  if ((rc = m->mt_state.ensure(((size_t)624 + 1) * n_chain * sizeof(unsigned int)))) return rc;
+  unsigned int* keys = static_cast<unsigned int*>(m->mt_state.p);
+  unsigned int* seeds = keys + (size_t)624 * n_chain;
+  ODL_CUDA(cudaMemcpyAsync(seeds, seeds_host, (size_t)n_chain * sizeof(unsigned int), cudaMemcpyHostToDevice, s));
+  ODL_CUDA(cudaEventRecord(m->ev0, s));
+  odl_refstream_kernel<<<(unsigned)((n_chain + 127) / 128), 128, 0, s>>>(seeds, keys, n_chain, n_iter, n_walk, n_prior_draws, step_sd, z_dev, u_dev);
+  g_launches.fetch_add(1);
+  ODL_CUDA(cudaGetLastError());
+  ODL_CUDA(cudaEventRecord(m->ev1, s));
+  m->timed = true; m->n_pass = 1;
+  ODL_CUDA(cudaStreamSynchronize(s));          // seeds_host may be reused by the caller
   return 0;
 }
 

@@ -248,6 +248,19 @@ class DeviceModel:
                                            c.ctypes.data, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(theta), self._stream()))
         return theta
 
+    # -- the reference chain's numpy random numbers, generated on the device (Samplers.py:70, :108, :127) -------
+    def reference_streams(self, seeds, n_iter, n_walk, n_prior_draws, step_sd=0.05):
+        """z [C, n_iter, n_walk], u [C, n_iter] as CUDA tensors: numpy's legacy RandomState(seed) per chain, consumed as
+        MetropolisHastings consumes it (odl_reference_streams_device; uniforms bit-identical, gaussians to 1 ulp)."""
+        import torch
+        sd = np.ascontiguousarray(seeds, dtype=np.uint32)
+        dev = torch.device("cuda", self.device)
+        z = torch.empty((len(sd), int(n_iter), int(n_walk)), dtype=torch.float64, device=dev)
+        u = torch.empty((len(sd), int(n_iter)), dtype=torch.float64, device=dev)
+        _capi.check(self._L.odl_reference_streams_device(self._h, sd.ctypes.data, len(sd), int(n_iter), int(n_walk),
+                                                         int(n_prior_draws), float(step_sd), _ptr(z), _ptr(u), self._stream()))
+        return z, u
+
     # -- chain-start selection on the device (Framework.py:1004-1012) -------------------------------
     def select_below(self, chi, cut):
         """Rows of the CUDA tensor `chi` with chi < cut, ascending -> (index tensor [n] int32, count)."""

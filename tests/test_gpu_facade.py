@@ -336,3 +336,20 @@ def test_mcmc_use_priors_is_opt_in_and_changes_the_target(capsys):
     d = m.MCMC(chain_inits=[th] * 2, iterations_per_chain=60, print_report=False, rng="philox", use_priors=True,
                static_parameters=["tau"])
     assert np.all(d["tau"] == 1)
+
+
+def test_large_reference_runs_take_their_streams_from_the_device_generator(monkeypatch):
+    """Beyond HOST_STREAM_DOUBLES the facade regenerates the reference's numpy streams on the device
+    (odl_reference_streams_device) instead of switching to Philox: the same chains as with host-generated streams --
+    decisions identical, samples to rounding (the gaussians agree to 1 ulp)."""
+    m = make_model("two_i")
+    g = golden("two_i")
+    th = dict(zip(m.get_pnames(), g["chain_def_s0_theta0"]))
+    a = m.MCMC(chain_inits=[th] * 6, iterations_per_chain=120, print_report=False)
+    monkeypatch.setattr(type(m), "HOST_STREAM_DOUBLES", 100)
+    b = m.MCMC(chain_inits=[th] * 6, iterations_per_chain=120, print_report=False)
+    assert len(a) == len(b) == 6 * 59
+    assert np.array_equal(a["iteration"].to_numpy(), b["iteration"].to_numpy())
+    assert np.array_equal(a["acceptance_ratio"].to_numpy(), b["acceptance_ratio"].to_numpy())   # same decisions
+    np.testing.assert_allclose(b[m.get_pnames()].to_numpy(), a[m.get_pnames()].to_numpy(), rtol=1e-12)
+    np.testing.assert_allclose(b["chi"].to_numpy(), a["chi"].to_numpy(), rtol=1e-9)

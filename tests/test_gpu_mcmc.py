@@ -282,3 +282,40 @@ def test_rhat_through_the_abi_equals_numpy():
     rh2, _, total2 = dm.rhat(padded)
     assert total2 == C + 7
     np.testing.assert_allclose(rh2, rhat_from_summaries(out["summaries"], 5), rtol=1e-12)
+
+
+def test_reference_streams_generated_on_the_device():
+    """odl_reference_streams_device (MT19937 + polar gauss per chain on the GPU, for runs too large for the host
+    generator) against the host generator, which is bitwise numpy's: uniforms bit-identical; gaussians through CUDA's log(),
+    within 1 ulp of glibc's -- most values identical, the others a few ulp apart; a chain run on them makes the reference's
+    decisions."""
+    from odelib_b200 import _capi
+    dm, _ = device_model("two_i")
+    seeds = np.array([0, 1, 7, 299, 12345, 2 ** 32 - 1, 42, 43], dtype=np.uint32)
+    for n_walk, n_prior in ((5, 5), (4, 3), (1, 0)):             # even and odd draws per iteration (the gauss cache)
+        n_iter = 700                                            # > 624 words per chain: several twists
+        z = np.empty((len(seeds), n_iter, n_walk)); u = np.empty((len(seeds), n_iter))
+        _capi.check(_capi.lib().odl_reference_streams(seeds.ctypes.data, len(seeds), n_iter, n_walk, n_prior, 0.05,
+                                                      z.ctypes.data, u.ctypes.data))
+        zd, ud = dm.reference_streams(seeds, n_iter, n_walk, n_prior, 0.05)
+        zd, ud = zd.cpu().numpy(), ud.cpu().numpy()
+        assert np.array_equal(ud, u)
+        assert (zd == z).mean() > 0.9
+        rel = np.abs(zd - z) / np.abs(z)
+        print("device streams: identical", (zd == z).mean(), "max rel diff", rel.max())
+        np.testing.assert_allclose(zd, z, rtol=2e-15, atol=0)    # a few ulp: 1 ulp of log() through a division and a root
+    rs = np.random.RandomState(7)                               # and numpy itself, for one chain
+    g = rs.standard_normal(10); u0 = rs.random_sample()
+    z7, u7 = dm.reference_streams(np.array([7], np.uint32), 3, 5, 5, 0.05)
+    np.testing.assert_allclose(z7.cpu().numpy()[0, 0], 0.05 * g[:5], rtol=2e-15)
+    assert u7.cpu().numpy()[0, 0] == u0
+    # the golden chain of the reference (seed 0) on device-generated streams: the reference's decisions
+    g2 = golden("two_i")
+    pre = "chain_tight_s0_"
+    nits = int(g2[pre + "nits"])
+    zr, ur = dm.reference_streams(np.array([0], np.uint32), nits - 1, dm.n_param, dm.n_param, 0.05)
+    import torch
+    out = dm.mcmc(torch.from_numpy(g2[pre + "theta0"][None, :]).cuda(), nits=nits, rng_mode="host", z=zr, u=ur, rtol=1e-13,
+                  atol=1e-13, trace=True, pnum=int(g2["pnum"]), max_steps=2000000, device_buffers=True)
+    assert np.array_equal(out["accepted"][0].cpu().numpy().astype(bool), g2[pre + "accepted"])
+    np.testing.assert_allclose(out["samples"][0].cpu().numpy()[:, :dm.n_param], g2[pre + "kept"][:, :dm.n_param], rtol=1e-12)
