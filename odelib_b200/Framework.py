@@ -861,7 +861,10 @@ class ModelFramework:
                 self.set_inits(**{s: out["theta"][0][m] for s, m in zip(self._snames, self._y0_map()) if m >= 0})
         return frames
 
-    HOST_STREAM_DOUBLES = 20_000_000         # reference streams up to this size are generated on the host (160 MB, bitwise numpy's)
+    # reference streams up to this size are generated on the host (2 GB; bitwise numpy's, 16 threads: 4096 chains x 10,000
+    # iterations in 0.5 s -- the device generator, one thread per chain with its key array in global memory, needs 2 s for
+    # the same and only wins from ~65,536 chains on)
+    HOST_STREAM_DOUBLES = 250_000_000
     DEVICE_STREAM_DOUBLES = 4_000_000_000    # ... up to this size (32 GB of HBM) on the device (odl_reference_streams_device)
 
     @classmethod
