@@ -278,6 +278,9 @@ def test_rhat_through_the_abi_equals_numpy():
         N2, mean2, std2 = pooled_log_stats(out["summaries"], 5)
         np.testing.assert_allclose(mean, mean2, rtol=1e-13)
         np.testing.assert_allclose(std, std2, rtol=1e-11)
+    # ODL_RHAT_LOCAL (this rank's chains only, whatever communicator the handle has joined): the same numbers on one GPU
+    rh_l, (N_l, mean_l, _), total_l = dm.rhat(out["summaries"], local=True)
+    assert total_l == C and N_l == N and np.array_equal(rh_l, rh) and np.array_equal(mean_l, mean)
     padded = np.vstack([out["summaries"][:100], np.zeros((7, 11)), out["summaries"][100:]])
     rh2, _, total2 = dm.rhat(padded)
     assert total2 == C + 7
