@@ -193,14 +193,14 @@ def run_reference(args):
                   f"LHS of the two_i priors + Pool fan-out of _Fit_worker + concat, {per_step:.1f} s per step")
     else:
         value, per_step, kind, sample = port_rate, port_dt, "port", port["sample"]
-    print(json.dumps({
+    emit_record({
         "impl": "reference", "metric": "ode_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": kind, "sample": sample, "port": port},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 def workload_config(args, n_gpus):
@@ -679,7 +679,7 @@ def run_ours(args):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(timed_launches), "gpu_launches_total": int(launches),
             "clocks": clk, "ok_fraction": ok_frac, "mcmc": mcmc, "facade": facade, "configs": configs, "cold_start_s": cold,
         }
-        print(json.dumps(line))
+        emit_record(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -699,6 +699,18 @@ def hbm_peak():
         return 6650.0   # fallback stated in B200_PROFILING.md
 
 
+_RECORD_FD = None
+
+
+def emit_record(obj):
+    """The one JSON line of the run, to the process's ORIGINAL stdout (see main)."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _RECORD_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RECORD_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -715,6 +727,13 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the legs for BASELINE configs 3-5")
     ap.add_argument("--no-cold", action="store_true", help="skip the cold-start leg")
     args = ap.parse_args()
+    # stdout carries ONE line, the JSON record: whatever libraries print there meanwhile (NCCL's version banner under
+    # NCCL_DEBUG, the reference's own per-iteration prints) goes to stderr -- at the descriptor level, so that C code is
+    # covered too; the record itself is written to the saved descriptor
+    global _RECORD_FD
+    sys.stdout.flush()
+    _RECORD_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
