@@ -22,6 +22,9 @@
  *   odl_gather_rows         resampling of acceptable survey rows (Framework.py:993-1016).
  *   odl_sample_lhs       <- Samplers.sample_lhs (Statistics/Samplers.py:6-51) under _lhs_samples
  *                           (Framework.py:589-615), for large surveys.
+ *   odl_reference_streams,        <- numpy's legacy RandomState(seed) exactly as MetropolisHastings consumes it per
+ *   odl_reference_streams_device     iteration (Samplers.py:70, :108, :118-121, :127; Framework.py:103, :119): fed to
+ *                                    odl_mcmc (ODL_RNG_HOST_STREAMS) they make every chain the reference chain of its seed.
  *   odl_comm_*, odl_rhat <- the gather of the workers' results (Framework.py:1035-1038); R-hat itself is new.
  *   odl_fp64_peak        <- (no reference counterpart) measures the FP64 FMA roofline denominator.
  *
