@@ -42,3 +42,18 @@ def solve(lib, solver, theta, slot_t, y0, rtol, atol, max_steps=2000000):
                            slot_t.size, y0.ctypes.data, float(slot_t[0]) if slot_t[0] <= 0 else 0.0, rtol, atol,
                            max_steps, out.ctypes.data, C.byref(ns))
     return out, st, ns.value
+
+
+def solve_observed(lib, theta, slot_t, y0, rtol, atol, max_steps=2000000):
+    """DOPRI5 through the observed-columns sink of the sweep / chain kernels -> (out [n_slot, n_out], status, steps)."""
+    theta = np.ascontiguousarray(theta, np.float64)
+    slot_t = np.ascontiguousarray(slot_t, np.float64)
+    y0 = np.ascontiguousarray(y0, np.float64)
+    lib.harness_solve_observed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                           C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    out = np.full((slot_t.size, lib.harness_nout()), np.nan)
+    ns = C.c_int()
+    st = lib.harness_solve_observed(theta.ctypes.data, slot_t.ctypes.data, slot_t.size, y0.ctypes.data,
+                                    float(slot_t[0]) if slot_t[0] <= 0 else 0.0, rtol, atol, max_steps, out.ctypes.data,
+                                    C.byref(ns))
+    return out, st, ns.value

@@ -88,6 +88,45 @@ extern "C" int harness_solve(int solver, const double* theta, const double* slot
   return st.status;
 }
 
+// DOPRI5 with the sink of the sweep / chain kernels' kind: observed columns only, interpolated in OBSERVED space (the
+// kObservedOnly path of odl_dopri5_attempt).  out: [n_slot][ODL_NOUT].
+struct HostObsSink {
+  static constexpr bool kObservedOnly = true;
+  double* out;
+  inline void operator()(int slot, const double (&yi)[ODL_N]) {
+    double o[ODL_NOUT];
+    odl_observe(yi, o);
+    put(slot, o);
+  }
+  inline void put(int slot, const double (&o)[ODL_NOUT]) {
+    for (int c = 0; c < ODL_NOUT; ++c) out[(long long)slot * ODL_NOUT + c] = o[c];
+  }
+};
+extern "C" int harness_nout(void) { return ODL_NOUT; }
+extern "C" int harness_solve_observed(const double* theta, const double* slot_t, int n_slot, const double* y0, double t0,
+                                      double rtol, double atol, int max_steps, double* out, int* nsteps) {
+  int y0p[ODL_N];
+  for (int i = 0; i < ODL_N; ++i) y0p[i] = -1;
+  OdlData D;
+  memset(&D, 0, sizeof D);
+  D.slot_t = slot_t; D.y0 = y0; D.y0_from_param = y0p; D.n_slot = n_slot; D.t0 = t0;
+  OdlOpts O;
+  memset(&O, 0, sizeof O);
+  O.rtol = rtol; O.atol = atol; O.max_steps = max_steps; O.stiff_min_steps = 2000;
+  OdlShared S;
+  memset(&S, 0, sizeof S);
+  S.slot_t = const_cast<double*>(slot_t);
+  double p[ODL_P];
+  for (int q = 0; q < ODL_P; ++q) p[q] = theta[q];
+  OdlStepper st;
+  HostObsSink sink{out};
+  odl_init_system(st, p, D, O, nullptr, false);
+  odl_emit_initial_slots(st, S, D, sink);
+  while (st.slot < D.n_slot && st.status == ODL_OK) odl_dopri5_attempt(st, p, S, D, O, sink);
+  *nsteps = st.nsteps;
+  return st.status;
+}
+
 // DOPRI5 progress profile (dev tool: how well does early progress predict the total step count?):
 // marks[k] = time reached after checkpoints[k] attempted steps (NaN if the solve ended earlier), hs[k] = step size then
 extern "C" int harness_progress(const double* theta, const double* slot_t, int n_slot, const double* y0, double t0,

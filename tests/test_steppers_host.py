@@ -145,3 +145,18 @@ def test_in_register_lu_with_pivoting(model):
         lib.harness_clu(ptr(A), ptr(Ai), ptr(b), ptr(bi), ptr(xr), ptr(xi))
         M, z = A + 1j * Ai, xr + 1j * xi
         assert np.abs(M @ z - (b + 1j * bi)).max() <= 1e-11 * (np.abs(M).max() * np.abs(z).max() + 1)
+
+
+def test_dense_output_in_observed_space_equals_the_observed_dense_states(two_i):
+    """The sweep / chain kernels interpolate the OBSERVED columns (sums of state groups) instead of the states -- the
+    continuous extension is linear, so both give the same numbers up to the order of the additions; the steps taken are
+    the same steps."""
+    lib, tab, slots = two_i
+    g = golden("two_i")
+    for th in g["theta"][:8]:
+        full, st, ns = hh.solve(lib, "dopri5", th, slots, tab.y0, TOL, TOL)
+        obs, st2, ns2 = hh.solve_observed(lib, th, slots, tab.y0, TOL, TOL)
+        assert st == 0 and st2 == 0 and ns == ns2
+        want = np.column_stack([full[:, 0] + full[:, 1] + full[:, 2], full[:, 3]])      # H = S + I1 + I2, V
+        np.testing.assert_allclose(obs, want, rtol=1e-13)
+        assert not np.array_equal(obs, full[:, :2])                                      # (it really is the observed path)
