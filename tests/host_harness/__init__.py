@@ -16,7 +16,8 @@ def build(ode, n_state, n_param, groups=None):
     from odelib_b200.tracer import trace
     src = trace(ode, n_state, n_param).cuda_source(fmad=True, observe_groups=groups)
     kern = open(os.path.join(ROOT, "odelib_b200", "csrc", "odl_kernels.cuh")).read()
-    key = hashlib.sha1((src + kern + open(os.path.join(HERE, "harness.cpp")).read()).encode()).hexdigest()[:16]
+    key = hashlib.sha1((src + kern + open(os.path.join(HERE, "harness.cpp")).read() +
+                        os.environ.get("ODL_HARNESS_DEFINES", "")).encode()).hexdigest()[:16]
     d = os.path.join(tempfile.gettempdir(), "odl_harness")
     os.makedirs(d, exist_ok=True)
     so = os.path.join(d, f"h_{key}.so")
@@ -24,6 +25,7 @@ def build(ode, n_state, n_param, groups=None):
         hdr = os.path.join(d, f"m_{key}.h")
         open(hdr, "w").write(src)
         cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", f'-DODL_MODEL_HEADER="{hdr}"',
+               *os.environ.get("ODL_HARNESS_DEFINES", "").split(),
                "-I" + os.path.join(ROOT, "odelib_b200", "csrc"), os.path.join(HERE, "harness.cpp"), "-o", so]
         subprocess.run(cmd, check=True)
     lib = C.CDLL(so)
