@@ -63,8 +63,10 @@ enum { ODL_AUTO_UNORDERED = 1,   /* process rows in input order (no cost orderin
        ODL_AUTO_ONE_PIECE = 4,   /* ODL_MEM_HOST: upload theta in one piece before anything runs (default: two pieces,
                                     the second travelling while the first is swept) */
        ODL_AUTO_SEQUENTIAL = 8,  /* run the stiff pass AFTER the DOPRI5 pass (single-warp CTAs over every SM) */
-       ODL_AUTO_NO_HELPER = 16   /* stiff pass beside the DOPRI5 pass: no second consumer on the SMs that pass frees when it
-                                    ends (development: the state of the code before that helper existed) */ };
+       ODL_AUTO_NO_HELPER = 16,  /* stiff pass beside the DOPRI5 pass: no second consumer on the SMs that pass frees when it
+                                    ends (development: the state of the code before that helper existed) */
+       ODL_AUTO_NO_HANDOVER = 32 /* the stiff pass integrates its rows again from t0 instead of continuing from where the
+                                    DOPRI5 pass stopped (the rule of the code before the hand-over existed) */ };
 enum { ODL_RNG_PHILOX = 0, ODL_RNG_HOST_STREAMS = 1, ODL_RNG_FORCED = 2 };
 enum { ODL_SAMPLES_CHAIN_MAJOR = 0, ODL_SAMPLES_ITERATION_MAJOR = 1 };
 /* per-system status words */

@@ -16,7 +16,7 @@ RNG_PHILOX, RNG_HOST_STREAMS, RNG_FORCED = 0, 1, 2
 SAMPLES_CHAIN_MAJOR, SAMPLES_ITERATION_MAJOR = 0, 1
 COMM_ID_BYTES = 128
 RHAT_LOCAL = 256
-AUTO_UNORDERED, AUTO_CONCURRENT, AUTO_ONE_PIECE, AUTO_SEQUENTIAL, AUTO_NO_HELPER = 1, 2, 4, 8, 16
+AUTO_UNORDERED, AUTO_CONCURRENT, AUTO_ONE_PIECE, AUTO_SEQUENTIAL, AUTO_NO_HELPER, AUTO_NO_HANDOVER = 1, 2, 4, 8, 16, 32
 ST_OK, ST_MAXSTEPS, ST_NONFINITE, ST_HUNDERFLOW, ST_STIFF, ST_ALLMASKED = 0, 1, 2, 3, 4, 8
 
 EXPORTS = ["odl_abi_version", "odl_last_error", "odl_model_create", "odl_model_destroy", "odl_model_build_log",

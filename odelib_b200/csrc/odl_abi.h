@@ -76,6 +76,9 @@ struct OdlSweepArgs {
   int* watchdog;                           // consumer: incremented when a warp gave up waiting for the feed
   int* resident;                           // consumer: +1 per CTA once it runs (odl_gate_kernel holds the bulk launch
                                            //   back until every consumer CTA has its SM)
+  double* handover;                        // optional [n][handover_stride]: what the DOPRI5 pass had reached when it gave a
+  int handover_stride;                     //   row up -- t, next slot, y[n_state], the staged observation columns of the slots
+  int pad3_;                               //   behind it -- so that the stiff pass continues from there instead of from t0
   long long* timeline;                     // development (kernels built with -DODL_TIMELINE=1, else unused): per feed
                                            //   entry %globaltimer at [0] deferral, [1] start and [2] end of its stiff solve
 };

@@ -169,6 +169,7 @@ struct odl_model {
   DevBuf counter;
   DevBuf scratch[24];                        // [0, 20): staging slots of one call; 21-23: select / gather / sample helpers
   DevBuf mt_state;                           // odl_reference_streams_device: MT19937 key arrays, [624][n_chain] words
+  DevBuf handover;                           // AUTO sweeps: per row, what the DOPRI5 pass hands to the stiff pass
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evp[2] = {nullptr, nullptr};   // between the cohort passes of an AUTO sweep
   cudaEvent_t ev_aux = nullptr, ev_fork = nullptr;
@@ -484,7 +485,7 @@ extern "C" int odl_model_destroy(odl_model* m) {
     for (Unit& u : m->units) if (u.mod && g_drv.ModuleUnload) g_drv.ModuleUnload(u.mod);
   }
   odl_comm_destroy(m);
-  m->data.buf.release(); m->grid.buf.release(); m->counter.release(); m->mt_state.release();
+  m->data.buf.release(); m->grid.buf.release(); m->counter.release(); m->mt_state.release(); m->handover.release();
   for (auto& s : m->scratch) s.release();
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -947,6 +948,16 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     if (!coop_bulk) ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, m->k_sweep, (int)block0, smem0));
     ODL_CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, k_tail, 32, smem_t));
     if (per_sm0 < 1 || per_sm_t < 1) return fail(ODL_ECUDA, "sweep kernel does not fit on an SM (shared memory / registers)");
+    // What the DOPRI5 pass had reached when it gave a row up travels with the row (OdlSweepArgs.handover): the stiff pass
+    // continues from there.  [n][2 + n_state + stage_stride] doubles, written only for the rows of the feed list.
+    double* handover = nullptr;
+    int handover_stride = 0;
+    if (!coop_bulk && tail_solver != ODL_SOLVER_RADAU5 && !(flags & ODL_AUTO_NO_HANDOVER)) {
+      handover_stride = 2 + m->n_state + D.stage_stride;
+      DevBuf& bh = m->handover;
+      if ((rc = bh.ensure((size_t)n * handover_stride * sizeof(double)))) return rc;
+      handover = static_cast<double*>(bh.p);
+    }
     // SMs set aside for the stiff pass when it runs beside the bulk pass
     int tail_sms = 0;
     unsigned tail_cluster = 1;
@@ -961,8 +972,13 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       // and 7.5M) the consumer keeps up on fewer SMs: 704 / 42 SMs 3.82 ms (its rows arrive later and its longest end after
       // the bulk pass), 36 3.44, 34 3.38, 32 3.32, 30 3.37, 28 3.61 (backlog when the bulk pass ends); cap 640 / 34 3.40,
       // 736 / 32 3.33, 768 / 34 3.66 (profiles/r2q_beside_grid.log)
+      // With the HAND-OVER (the stiff pass continues from where the DOPRI5 pass stopped: 1.13M instead of 4.95M BDF steps for
+      // the 9.4k rows of the two_i sweep -- the hard part of these rows is their start, and DOPRI5 has done it) the consumer
+      // needs a fraction of that: 32 SMs 3.19 ms, 28 3.09, 24 2.99, 20 2.90, 16 2.82, 12 2.74, 8 3.26 (backlog).  A tenth
+      // of the SMs, with a margin over the edge.
       // (two-piece host-memory sweeps: two SMs more -- the rows of the second piece reach the consumer in a shorter time)
-      tail_sms = so && so->tail_warps > 0 ? so->tail_warps : (m->sm_count * 22 + 50) / 100 + (chunked ? 2 : 0);
+      const int share = handover ? 95 : 220;                     // per mille of the SMs
+      tail_sms = so && so->tail_warps > 0 ? so->tail_warps : (m->sm_count * share + 500) / 1000 + (chunked ? 2 : 0);
       tail_sms = std::max(1, std::min(tail_sms, m->sm_count / 3));
       // Placement: on an idle GPU the block scheduler packs the consumer's CTAs onto neighbouring SMs, behind other
       // work it scatters them -- and a consumer SM whose TPC partner runs the bulk kernel steps 8-12 % slower
@@ -988,6 +1004,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
                                                             : std::min(O0.max_steps * 3 / 4, ODL_AUTO_EARLY_DEFAULT);
     OdlSweepArgs A0 = A;
     A0.index = ordered ? index : nullptr;
+    A0.handover = handover; A0.handover_stride = handover_stride;
     A0.defer_list[0] = A0.defer_list[1] = feed; A0.defer_count[0] = A0.defer_count[1] = cnt(64);
     OdlOpts O2 = O; O2.stiff_check = 0;
     // the pass over the feed list AFTER the bulk pass: as few lanes per warp as spreading the entries over every
@@ -995,6 +1012,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     O2.lanes = so && so->tail_lanes > 0 ? std::min(32, so->tail_lanes) : -1;
     OdlSweepArgs A2 = A;
     A2.index = feed; A2.index_count = cnt(64); A2.counter = ctr(256);
+    A2.handover = handover; A2.handover_stride = handover_stride;
     A2.defer_list[0] = A2.defer_list[1] = nullptr; A2.defer_count[0] = A2.defer_count[1] = nullptr;
     const int bulk_sms = m->sm_count - tail_sms;
     const unsigned grid0 = (unsigned)std::max<long long>(1, std::min<long long>((n + block0 - 1) / block0, (long long)per_sm0 * bulk_sms));

@@ -81,16 +81,27 @@ def test_auto_routes_stiff_systems_and_keeps_the_rest():
     theta = np.vstack([stiff_thetas(24, seed=2), g["theta"][:24]])
     plain = dm.sweep(theta, solver="dopri5", stiff_check=True, max_steps=2000000)
     assert (plain["status"][:24] == 4).sum() >= 12            # DOPRI5 alone flags (most of) the stiff block
-    auto = dm.sweep(theta, solver="auto", max_steps=2000000)
-    assert np.all(auto["status"][:24] == 0)
-    # every system was finished by exactly one of the two steppers (DOPRI5, or the BDF stiff pass): same kernel,
-    # same numbers -- a solve does not depend on which systems share its warp or which pass it ran in
+    from odelib_b200 import _capi
+    auto0 = dm.sweep(theta, solver="auto", max_steps=2000000, auto_flags=_capi.AUTO_NO_HANDOVER)
+    assert np.all(auto0["status"][:24] == 0)
+    # stiff pass from t0 (AUTO_NO_HANDOVER): every system was finished by exactly one of the two steppers (DOPRI5, or the
+    # BDF stiff pass): same kernel, same numbers -- a solve does not depend on which systems share its warp or which pass
+    # it ran in
     bdf = dm.sweep(theta, solver="bdf", max_steps=2000000)
     dop = dm.sweep(theta, solver="dopri5", max_steps=2000000)
-    same_bdf = (auto["chi"] == bdf["chi"]) | (np.isnan(auto["chi"]) & np.isnan(bdf["chi"]))
-    same_dop = (auto["chi"] == dop["chi"]) | (np.isnan(auto["chi"]) & np.isnan(dop["chi"]))
+    same_bdf = (auto0["chi"] == bdf["chi"]) | (np.isnan(auto0["chi"]) & np.isnan(bdf["chi"]))
+    same_dop = (auto0["chi"] == dop["chi"]) | (np.isnan(auto0["chi"]) & np.isnan(dop["chi"]))
     assert np.all(same_bdf | same_dop)
     assert same_bdf[:24].sum() >= 12 and same_dop[24:].sum() >= 20
+    # the default: the stiff pass CONTINUES from where the DOPRI5 pass stopped (t, y and the observation columns staged so
+    # far travel with the row).  Rows DOPRI5 finished are untouched; the others agree with the BDF solve from t0 to
+    # solver accuracy and take fewer BDF steps
+    auto = dm.sweep(theta, solver="auto", max_steps=2000000)
+    assert np.all(auto["status"][:24] == 0)
+    assert np.array_equal(auto["chi"][same_dop], auto0["chi"][same_dop])
+    handed = same_bdf & ~same_dop
+    np.testing.assert_allclose(auto["chi"][handed], auto0["chi"][handed], rtol=5e-3)   # (BDF's chi at the default tolerance: ~1e-4)
+    assert auto["nsteps"][handed].sum() < auto0["nsteps"][handed].sum()
     # far fewer steps than the explicit method needs on the stiff block
     assert np.median(auto["nsteps"][:24]) < 0.2 * np.median(dop["nsteps"][:24])
     # the Radau5 stiff pass is still selectable and agrees with the BDF one to solver accuracy
