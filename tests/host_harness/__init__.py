@@ -59,3 +59,20 @@ def solve_observed(lib, theta, slot_t, y0, rtol, atol, max_steps=2000000):
                                     float(slot_t[0]) if slot_t[0] <= 0 else 0.0, rtol, atol, max_steps, out.ctypes.data,
                                     C.byref(ns))
     return out, st, ns.value
+
+
+def solve_handover(lib, theta, slot_t, y0, rtol, atol, cap=704, early=384, idle=0):
+    """DOPRI5 until it gives the row up, `idle` attempts of the stopped solve, BDF continuing from there (the AUTO sweep's
+    hand-over) -> (out [n_slot, n], status, dopri5 attempts, bdf steps, slot at the hand-over, time at the hand-over)."""
+    theta = np.ascontiguousarray(theta, np.float64)
+    slot_t = np.ascontiguousarray(slot_t, np.float64)
+    y0 = np.ascontiguousarray(y0, np.float64)
+    lib.harness_solve_handover.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                           C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    out = np.full((slot_t.size, y0.size), np.nan)
+    info = np.zeros(3, np.int32)
+    th = C.c_double()
+    st = lib.harness_solve_handover(theta.ctypes.data, slot_t.ctypes.data, slot_t.size, y0.ctypes.data,
+                                    float(slot_t[0]) if slot_t[0] <= 0 else 0.0, rtol, atol, cap, early, idle,
+                                    out.ctypes.data, info.ctypes.data, C.byref(th))
+    return out, st, int(info[0]), int(info[1]), int(info[2]), th.value

@@ -127,6 +127,52 @@ extern "C" int harness_solve_observed(const double* theta, const double* slot_t,
   return st.status;
 }
 
+// The AUTO sweep's hand-over on the host: DOPRI5 until it gives a row up (step cap / projection check), `idle` further
+// attempts of the stopped solve (what a lane of the sweep kernel does while it waits for its warp's write-back: they must
+// leave the state exactly as it is), then the BDF stepper continuing from that state.  out: [n_slot][ODL_N];
+// info[0] = DOPRI5 attempts, info[1] = BDF steps, info[2] = slot at the hand-over; t_hand = time at the hand-over.
+extern "C" int harness_solve_handover(const double* theta, const double* slot_t, int n_slot, const double* y0, double t0,
+                                      double rtol, double atol, int cap, int early, int idle, double* out, int* info,
+                                      double* t_hand) {
+  int y0p[ODL_N];
+  for (int i = 0; i < ODL_N; ++i) y0p[i] = -1;
+  OdlData D;
+  memset(&D, 0, sizeof D);
+  D.slot_t = slot_t; D.y0 = y0; D.y0_from_param = y0p; D.n_slot = n_slot; D.t0 = t0;
+  OdlOpts O;
+  memset(&O, 0, sizeof O);
+  O.rtol = rtol; O.atol = atol; O.max_steps = cap; O.early_check_steps = early; O.stiff_check = 1; O.stiff_min_steps = 2000;
+  OdlShared S;
+  memset(&S, 0, sizeof S);
+  S.slot_t = const_cast<double*>(slot_t);
+  double p[ODL_P];
+  for (int q = 0; q < ODL_P; ++q) p[q] = theta[q];
+  OdlStepper st;
+  HostSink sink{out};
+  odl_init_system(st, p, D, O, nullptr, false);
+  odl_emit_initial_slots(st, S, D, sink);
+  while (st.slot < D.n_slot && st.status == ODL_OK) odl_dopri5_attempt(st, p, S, D, O, sink);
+  info[0] = st.nsteps; info[1] = 0; info[2] = st.slot; *t_hand = st.t;
+  if (st.status != ODL_MAXSTEPS && st.status != ODL_STIFF) return st.status;       // finished (or failed otherwise)
+  const double t_stop = st.t;
+  double y_stop[ODL_N];
+  for (int i = 0; i < ODL_N; ++i) y_stop[i] = st.y[i];
+  const int slot_stop = st.slot;
+  for (int k = 0; k < idle; ++k) odl_dopri5_attempt(st, p, S, D, O, sink);
+  if (st.t != t_stop || st.slot != slot_stop || st.nsteps != info[0]) return -100;  // a stopped solve must stand still
+  for (int i = 0; i < ODL_N; ++i) if (memcmp(&st.y[i], &y_stop[i], 8) != 0) return -101;
+  // the stiff pass takes over (odl_take_over): t, y, slot; k1 = f(t, y); a fresh stepper of order 1
+  OdlOpts Ob = O;
+  Ob.max_steps = 2000000; Ob.early_check_steps = 0; Ob.stiff_check = 0;
+  st.status = ODL_OK; st.nsteps = 0;
+  odl_rhs(st.y, st.t, p, st.k1);
+  OdlBdfAux bx;
+  bx.reset();
+  while (st.slot < D.n_slot && st.status == ODL_OK) odl_bdf_attempt(st, bx, p, S, D, Ob, sink);
+  info[1] = st.nsteps;
+  return st.status;
+}
+
 // DOPRI5 progress profile (dev tool: how well does early progress predict the total step count?):
 // marks[k] = time reached after checkpoints[k] attempted steps (NaN if the solve ended earlier), hs[k] = step size then
 extern "C" int harness_progress(const double* theta, const double* slot_t, int n_slot, const double* y0, double t0,

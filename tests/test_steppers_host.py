@@ -160,3 +160,31 @@ def test_dense_output_in_observed_space_equals_the_observed_dense_states(two_i):
         want = np.column_stack([full[:, 0] + full[:, 1] + full[:, 2], full[:, 3]])      # H = S + I1 + I2, V
         np.testing.assert_allclose(obs, want, rtol=1e-13)
         assert not np.array_equal(obs, full[:, :2])                                      # (it really is the observed path)
+
+
+def test_hand_over_from_dopri5_to_bdf(two_i):
+    """The AUTO sweep's hand-over, on the host: on prior draws the capped DOPRI5 pass gives up on, the BDF stepper
+    continues from where it stopped.  (1) a stopped solve stands still while its lane waits (0 or 7 further attempts: the
+    same state bit for bit, hence the same result); (2) the result is the solution (odeint at 1e-12); (3) far fewer BDF
+    steps than the BDF solve from t0."""
+    from tests.helpers import prior_draws
+    lib, tab, slots = two_i
+    theta = prior_draws("two_i", 4000, seed=0)
+    handed, steps_cont, steps_t0 = 0, 0, 0
+    for th in theta:
+        a, st, nd, nb, slot, t_hand = hh.solve_handover(lib, th, slots, tab.y0, TOL, TOL, idle=0)
+        if nb == 0:
+            continue                                             # DOPRI5 finished this row itself
+        assert st == 0 and 0 < t_hand < slots[-1]
+        b, st2, nd2, nb2, slot2, _ = hh.solve_handover(lib, th, slots, tab.y0, TOL, TOL, idle=7)
+        assert st2 == 0 and (nd2, nb2, slot2) == (nd, nb, slot) and np.array_equal(a, b)
+        ref = _ref(th, tab, slots)
+        ok = ref > 1.0                                           # (below one cell/ml a state is integrator noise)
+        if ok.any():
+            assert np.max(np.abs(a[ok] - ref[ok]) / np.abs(ref[ok])) < 5e-6
+        _, st3, n0 = hh.solve(lib, "bdf", th, slots, tab.y0, TOL, TOL)
+        assert st3 == 0
+        handed += 1; steps_cont += nb; steps_t0 += n0
+        if handed == 25:
+            break
+    assert handed >= 20 and steps_cont < 0.5 * steps_t0, (handed, steps_cont, steps_t0)
