@@ -915,7 +915,9 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       // pieces' launches overlapping (below): 1M rows through pinned buffers 4.62 ms at 1/4, 4.40 at 0.15, 4.33 at 0.1,
       // 4.40 at 0.05 (round 2 before the overlap, one launch after the other: 5.44 at 1/2, 4.88 at 1/3 .. 1/5, 4.85 at 0.15).
       // Stiff pass after the bulk pass: halves (5.10 / 5.04 / 5.12 at 1/2, 1/3, 1/4).
-      double first = beside_first_quarter ? 0.10 : 0.5;
+      // With the hand-over (the stiff pass's rows are cheap and no longer sit on the critical path) the first piece is best
+      // sized so that its sweep covers the upload of the rest: 3.61 ms at 0.1, 3.47 at 0.15, 3.41 at 0.2 and 0.25, 3.46 at 0.3.
+      double first = beside_first_quarter ? 0.20 : 0.5;
       if (const char* e = getenv("ODL_FIRST_PIECE")) first = std::min(0.9, std::max(0.05, atof(e)));   // development knob
       cut[1] = (((long long)(n * first) + 1023) / 1024) * 1024;
       // three pieces (10 %, 30 %, 60 %): the upload runs at ~4x the speed of the sweep, so once the first piece is there
@@ -978,7 +980,7 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
       // of the SMs, with a margin over the edge.
       // (two-piece host-memory sweeps: two SMs more -- the rows of the second piece reach the consumer in a shorter time)
       const int share = handover ? 95 : 220;                     // per mille of the SMs
-      tail_sms = so && so->tail_warps > 0 ? so->tail_warps : (m->sm_count * share + 500) / 1000 + (chunked ? 2 : 0);
+      tail_sms = so && so->tail_warps > 0 ? so->tail_warps : (m->sm_count * share + 500) / 1000 + ((chunked && !handover) ? 2 : 0);
       tail_sms = std::max(1, std::min(tail_sms, m->sm_count / 3));
       // Placement: on an idle GPU the block scheduler packs the consumer's CTAs onto neighbouring SMs, behind other
       // work it scatters them -- and a consumer SM whose TPC partner runs the bulk kernel steps 8-12 % slower

@@ -11,7 +11,10 @@ out = {"chi": torch.empty(n, dtype=torch.float64).pin_memory().numpy(), "status"
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for cfg in sys.argv[1:]:
     cap, early, sms, first = cfg.split(",")
-    os.environ["ODL_FIRST_PIECE"] = first
+    if first == "default":
+        os.environ.pop("ODL_FIRST_PIECE", None)
+    else:
+        os.environ["ODL_FIRST_PIECE"] = first
     kw = dict(solver="auto", max_steps=500000, out=out, outputs=outs, pass_caps=int(cap), early_check_steps=int(early), tail_warps=int(sms))
     for _ in range(2):
         dm.sweep(theta, **kw)
