@@ -954,10 +954,13 @@ extern "C" int odl_sweep(odl_model* m, const odl_solver_opts* so, long long n, c
     // continues from there.  [n][2 + n_state + stage_stride] doubles, written only for the rows of the feed list.
     double* handover = nullptr;
     int handover_stride = 0;
-    if (!coop_bulk && tail_solver != ODL_SOLVER_RADAU5 && !(flags & ODL_AUTO_NO_HANDOVER)) {
+    // (a rule on the table's size alone, so that results do not depend on what else lives in device memory: tables whose
+    // records would take more than 8 GB -- 23M rows of the two_i model -- go without, their stiff rows start from t0)
+    const size_t handover_bytes = (size_t)n * (2 + m->n_state + D.stage_stride) * sizeof(double);
+    if (!coop_bulk && tail_solver != ODL_SOLVER_RADAU5 && !(flags & ODL_AUTO_NO_HANDOVER) && handover_bytes <= ((size_t)8 << 30)) {
       handover_stride = 2 + m->n_state + D.stage_stride;
       DevBuf& bh = m->handover;
-      if ((rc = bh.ensure((size_t)n * handover_stride * sizeof(double)))) return rc;
+      if ((rc = bh.ensure(handover_bytes))) return rc;
       handover = static_cast<double*>(bh.p);
     }
     // SMs set aside for the stiff pass when it runs beside the bulk pass
